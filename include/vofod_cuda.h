@@ -1,0 +1,287 @@
+/*
+ * libvofod_cuda — C ABI of the B200-native VoFOD per-scan volumetric hot path.
+ *
+ * The reference (ctu-mrs/vofod) has no FFI around this path: the nodelet holds three
+ * vofod::VoxelMap members by value (src/vofod_nodelet.cpp:2333-2339) and calls class methods and
+ * PCL templates inline.  This header is the boundary a maintainer binds instead: every entry point
+ * cites the reference code it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns int: 0 = VOFOD_OK, >0 = informational status (the reference logs and
+ *     carries on), <0 = error; vofod_last_error() gives a human string for the last error.
+ *   - the caller owns all host buffers and passes capacities; the library owns all device memory.
+ *   - no exceptions, no abort, no stdout/stderr output cross the ABI.
+ *   - one vofod_ctx = one CUDA device; calls on one ctx must be serialised by the caller exactly
+ *     as m_voxels_mtx does in the reference (src/vofod_nodelet.cpp:608,712,943,1146,1210,1530,1612);
+ *     distinct contexts are independent.
+ *   - there is NO CPU fallback: if no CUDA device is usable vofod_create fails with VOFOD_E_CUDA.
+ */
+#ifndef VOFOD_CUDA_H
+#define VOFOD_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define VOFOD_OK              0
+#define VOFOD_W_SENSOR_OOB    1  /* sensor origin outside the map: raycast skipped (vofod_nodelet.cpp:1432,1525) */
+#define VOFOD_W_EMPTY_RAYCAST 2  /* max raycast value is zero: apply + flag clear skipped (:1544-1548)          */
+#define VOFOD_W_PAUSED        3  /* raycast__pause / sepclusters__pause set (:1400,1128)                        */
+#define VOFOD_W_EMPTY         4  /* nothing to do (e.g. empty voxel-map cloud, :1155-1159)                      */
+#define VOFOD_E_INVALID      -1  /* bad argument                                                                */
+#define VOFOD_E_CUDA         -2  /* CUDA runtime failure (string in vofod_last_error)                           */
+#define VOFOD_E_CAPACITY     -3  /* output buffer too small; the needed count is written to the out-param       */
+#define VOFOD_E_STATE        -4  /* map not sized / sensor not set                                              */
+#define VOFOD_E_DIMS         -5  /* cloud size != sensor LUT size (:895-899, :1407-1411)                        */
+#define VOFOD_E_OVERFLOW     -6  /* voxel-grid index overflow (voxel_grid_weighted.cpp:61-69)                   */
+#define VOFOD_E_NOMEM        -7
+#define VOFOD_E_INTERNAL     -8  /* device-side watchdog tripped (bounded spin exceeded)                        */
+
+/* which grid (vofod_nodelet.cpp:2333-2339) */
+#define VOFOD_MAP_SCORE   0      /* m_voxel_map     : fp32 score                                   */
+#define VOFOD_MAP_FLAGS   1      /* m_voxel_flags   : 0 unmarked, 2 background point, 3 unknown    */
+#define VOFOD_MAP_RAYCAST 2      /* m_voxel_raycast : accumulated path length [m] of the last scan */
+
+/* cluster classes (vofod_nodelet.cpp:85-90) */
+#define VOFOD_CLASS_MAV     0
+#define VOFOD_CLASS_UNKNOWN 1
+#define VOFOD_CLASS_INVALID 2
+
+typedef struct vofod_ctx vofod_ctx;
+
+/* packed scan point: the fields of ouster_ros::Point the path reads (x,y,z,intensity,range) */
+typedef struct vofod_pt { float x, y, z, intensity; uint32_t range_mm; } vofod_pt;
+/* payload of vofod::PointXYZR (include/vofod/point_types.h:51-56) */
+typedef struct vofod_vox { float x, y, z; uint32_t count; } vofod_vox;
+/* payload of pcl::PointXYZI as produced by VoxelMap::voxelsAs[Voxel]PC (voxel_map.cpp:157-212) */
+typedef struct vofod_xyzi { float x, y, z, intensity; } vofod_xyzi;
+/* rigid sensor->world transform: R row-major (used both as Affine linear part, vofod_nodelet.cpp:640,
+ * and as tf.rotation(), :1428), t translation */
+typedef struct vofod_pose { float R[9]; float t[3]; } vofod_pose;
+
+/* Every tunable of config/detection_params.yaml + DetectionParams.cfg, passed PER CALL so that
+ * dynamic_reconfigure semantics (values re-read on every use) are preserved.
+ * double where the reference holds a dynamic_reconfigure double, float where it holds a float member. */
+typedef struct vofod_params {
+  double ground_points_max_distance;          /* 1.5   */
+  double output_position_sigma;               /* 0.1   */
+  double score_point;                         /* 0     voxel_map__scores__point   */
+  double score_unknown;                       /* -740  voxel_map__scores__unknown */
+  double score_ray;                           /* -1000 voxel_map__scores__ray     */
+  double thr_apriori_map;                     /* 0     */
+  double thr_sure_obstacles;                  /* -0.1  */
+  double thr_new_obstacles;                   /* -300  */
+  double thr_frontiers;                       /* -750  */
+  double cls_max_size;                        /* 3.0   */
+  double cls_max_distance;                    /* 50    */
+  double cls_max_explore_distance;            /* 3.0   */
+  double raycast_max_distance;                /* 20    */
+  double raycast_min_intensity;               /* 0     */
+  double raycast_weight_coefficient;          /* 0.003 */
+  double sep_max_bg_distance;                 /* 0.8   */
+  int32_t cls_min_points;                     /* 2     */
+  int32_t raycast_pause;                      /* 0     */
+  int32_t raycast_new_update_rule;            /* 1     */
+  int32_t sep_pause;                          /* 0     */
+  int32_t sep_min_sure_points;                /* 24    */
+  int32_t _pad0;
+  float score_init;                           /* -740  voxel_map/scores/init (static)     */
+  float background_sufficient_points_ratio;   /* 0.15  (static)                            */
+  float exclude_box_offset[3];                /* yaml values; z is the LOWEST face (:204)  */
+  float exclude_box_size[3];
+  float oparea_offset[3];                     /* yaml values; z is the LOWEST face (:212)  */
+  float oparea_size[3];
+  float sensor_vfov;                          /* radians (:869)                            */
+  float _pad1;
+} vofod_params;
+
+typedef struct vofod_map_info {
+  float offset[3];        /* corner of voxel (0,0,0)  (voxel_map.cpp:351-354)       */
+  int32_t sizes[3];       /* cells per axis = ceil(dims/vs)+1 (voxel_map.cpp:16)    */
+  float voxel_size;
+  uint64_t n_cells;
+  int32_t slab_axis, slab_lo, slab_hi;  /* owned index range along slab_axis (whole axis when unsharded) */
+} vofod_map_info;
+
+/* one entry per far cluster, in classification order (vofod_nodelet.cpp:110-119) */
+typedef struct vofod_cluster_info {
+  int32_t label;            /* canonical label = minimum point index of the cluster */
+  int32_t n_points;
+  int32_t cclass;           /* VOFOD_CLASS_*                                         */
+  float aabb_min[3], aabb_max[3];
+  float obb_min[3], obb_max[3], obb_center[3];
+  float obb_rot[9];         /* row-major, columns = major/middle/minor axes          */
+  float obb_size;           /* NaN when a gate returned before computing it (:115)   */
+  float eig_gap;            /* min relative gap between covariance eigenvalues (parity-test aid) */
+} vofod_cluster_info;
+
+/* msgs/Detection.msg:1-12 + detection_t (vofod_nodelet.cpp:121-130) */
+typedef struct vofod_detection {
+  int32_t id;
+  int32_t label;            /* canonical label of the source cluster */
+  uint64_t n_points;
+  float aabb_min[3], aabb_max[3];
+  float position[3];        /* = obb.center (:979-981) */
+  float obb_min[3], obb_max[3];
+  float obb_rot[9];
+  float covariance[9];
+  double confidence;
+  double detection_probability;
+} vofod_detection;
+
+/* which optional stages vofod_process_scan runs (deterministic schedule S1) */
+typedef struct vofod_schedule {
+  int32_t n_range_seeds;        /* rangefinder seeds before the scan (A23), world_pt = range_pt */
+  float   range_pt[3];
+  int32_t do_raycast;           /* accumulate + apply(its_diff) + flags.clear()                 */
+  int32_t raycast_its_diff;     /* >= 1                                                         */
+  int32_t do_classify;          /* classifyClusters + extractDetections                         */
+  int32_t do_sepclusters;       /* updateSeparatedBGClusters(its_diff) after the detections     */
+  int32_t sep_its_diff;
+} vofod_schedule;
+
+typedef struct vofod_scan_result {
+  uint64_t n_traversals;        /* forEachRay callbacks of this scan (voxel_map.cpp:253)  */
+  uint64_t n_bg;                /* nVoxelsOver(thr_new_obstacles) seen by findCloseFarClusters */
+  uint32_t n_filtered;          /* points surviving both crop boxes                        */
+  uint32_t n_voxels;            /* M = cloud_weighted->size()                              */
+  uint32_t n_clusters;
+  uint32_t n_close_clusters;
+  uint32_t n_far_clusters;
+  uint32_t n_detections;
+  int32_t  background_pts_sufficient;
+  int32_t  sure_background_sufficient;
+  int32_t  raycast_status;      /* VOFOD_OK / VOFOD_W_*                                     */
+  int32_t  sep_status;
+} vofod_scan_result;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int vofod_create(int device, vofod_ctx** out);
+int vofod_destroy(vofod_ctx* ctx);
+const char* vofod_last_error(const vofod_ctx* ctx);      /* never NULL; ctx may be NULL */
+int vofod_synchronize(vofod_ctx* ctx);
+void vofod_default_params(vofod_params* p);               /* config/detection_params.yaml verbatim */
+/* VoFOD::reset() (vofod_nodelet.cpp:1610-1632): resize the 3 grids from the operation area, score=init,
+ * flags=0, detection_its=0; also clears background flags and the detection id counter. */
+int vofod_reset(vofod_ctx* ctx, const vofod_params* p, float voxel_size);
+
+/* ---- C1: vofod::VoxelMap (include/vofod/voxel_map.h:27-112, src/voxel_map.cpp) ------------- */
+int vofod_map_resize(vofod_ctx*, const float center[3], const float dims[3], float voxel_size);       /* voxel_map.cpp:11-19 */
+int vofod_map_resize_idx(vofod_ctx*, const float offset[3], const int32_t sizes[3], float voxel_size); /* :21-48 */
+int vofod_map_info_get(const vofod_ctx*, vofod_map_info* out);                                         /* :343-374 */
+int vofod_map_set_to(vofod_ctx*, int which, float value);                                              /* :268-279 */
+int vofod_map_set_inf(vofod_ctx*, const float* xyz, size_t n);            /* apriori voxels, vofod_nodelet.cpp:339-341 */
+int vofod_map_download(vofod_ctx*, int which, float* host, size_t n_cells);    /* begin()/end() mirror (voxel_map.h:50-51) */
+int vofod_map_upload(vofod_ctx*, int which, const float* host, size_t n_cells);
+int vofod_map_get(vofod_ctx*, int which, int ix, int iy, int iz, float* value);  /* atIdx (voxel_map.cpp:105-133) */
+int vofod_map_set(vofod_ctx*, int which, int ix, int iy, int iz, float value);
+int vofod_map_count_over(vofod_ctx*, float threshold, uint64_t* out);            /* nVoxelsOver :216-222 */
+/* voxelsAsPC (metric=1) / voxelsAsVoxelPC (metric=0): emission order x-outer, y, z-inner (:157-212) */
+int vofod_map_compact_over(vofod_ctx*, float threshold, int greater_than, int metric,
+                           vofod_xyzi* out, size_t cap, size_t* n);
+int vofod_map_has_close_to(vofod_ctx*, const float* xyz, size_t n, float max_dist, float threshold,
+                           uint8_t* out);                                         /* :376-400 */
+int vofod_map_explore_to_ground(vofod_ctx*, const float pt[3], float unknown_threshold,
+                                float ground_threshold, float max_voxel_dist, int* connected,
+                                int32_t* explored_idx3, size_t cap, size_t* n_explored); /* :402-488 */
+int vofod_map_is_floating(vofod_ctx*, const float* xyz, size_t n, float threshold, uint8_t* out); /* :491-516 */
+int vofod_map_submap_copy(vofod_ctx*, const float min_pt[3], const float max_pt[3], int inflate,
+                          float* out, size_t cap, int32_t sizes_out[3], float offset_out[3]); /* :547-584 */
+/* forEachRay (:229-263): returns the callback sequence (ddist, ix,iy,iz) of ONE ray */
+int vofod_map_trace_ray(vofod_ctx*, const float start[3], const float dir[3], float length,
+                        float* ddist, int32_t* idx3, size_t cap, size_t* n);
+
+/* ---- sensor model (vofod_nodelet.cpp:77-81, 374-420, 506-560) ------------------------------- */
+/* dirs/offs: 3xN column-major as Eigen stores them (= N consecutive xyz triples), ray id = row*W+col;
+ * mask: N bytes, nonzero = valid pixel (NULL = all ones, :558) */
+int vofod_set_sensor(vofod_ctx*, int W, int H, const float* dirs3xN, const float* offs3xN,
+                     const uint8_t* mask);
+
+/* ---- C2/C3: voxel grids ---------------------------------------------------------------------- */
+/* filterAndTransform (vofod_nodelet.cpp:621-684): exclude-box crop, rigid transform, op-area crop,
+ * VoxelGridWeighted aligned to the map.  out: ascending voxel key order (voxel_grid_weighted.cpp:143). */
+int vofod_filter_voxelize(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*,
+                          const vofod_params*, vofod_vox* out, size_t cap, size_t* m);
+/* VoxelGridWeighted::filter on an arbitrary cloud (voxel_grid_weighted.cpp:41-190); align may be NULL */
+int vofod_voxel_grid_weighted(vofod_ctx*, const float* xyz, size_t n, float leaf, const float align[3],
+                              vofod_vox* out, size_t cap, size_t* m);
+/* VoxelGridCounted::filter (voxel_grid_counted.cpp:49-196), including its input-slice quirk (:185-187) */
+int vofod_voxel_grid_counted(vofod_ctx*, const vofod_xyzi* pts, size_t n, float leaf, float threshold,
+                             const float align[3], vofod_vox* out, size_t cap, size_t* m);
+
+/* ---- A13: clusterCloud (vofod_nodelet.cpp:689-698; pcl::EuclideanClusterExtraction) ---------- */
+/* labels[i] = minimum point index of i's connected component under strict d^2 < tol^2 */
+int vofod_cluster(vofod_ctx*, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters);
+
+/* ---- A14/A15: findCloseFarClusters (vofod_nodelet.cpp:703-750) -------------------------------- */
+int vofod_close_far(vofod_ctx*, const vofod_vox* pts, const int32_t* labels, size_t m,
+                    const vofod_params*, uint8_t* point_in_close_cluster, uint64_t* n_bg);
+
+/* ---- A23: rangefinder ground seed (vofod_nodelet.cpp:581-613) --------------------------------- */
+int vofod_range_update(vofod_ctx*, const float world_pt[3], const vofod_params*);
+
+/* ---- A11: updateVMaps (vofod_nodelet.cpp:777-815); sel may be NULL (all) else byte mask --------- */
+int vofod_update_points(vofod_ctx*, const vofod_vox* pts, const uint8_t* sel, int sel_value, size_t n,
+                        float score, float flag);
+
+/* ---- A3..A9: raycast_cloud (vofod_nodelet.cpp:1397-1606) -------------------------------------- */
+int vofod_raycast_accumulate(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*,
+                             const vofod_params*, uint64_t* n_traversals);
+/* parity/debug view of the accumulator before apply: per-cell callback count and path length.
+ * either pointer may be NULL. */
+int vofod_raycast_download(vofod_ctx*, uint32_t* counts, float* lengths, size_t n_cells);
+int vofod_raycast_apply(vofod_ctx*, int its_diff, const vofod_params*);
+
+/* ---- A16..A19: classifyClusters + extractDetections (vofod_nodelet.cpp:819-879, 1648-1731) ---- */
+int vofod_classify_detect(vofod_ctx*, const vofod_vox* pts, const int32_t* labels,
+                          const uint8_t* point_in_close_cluster, size_t m, const vofod_pose*,
+                          const vofod_params*, vofod_detection* dets, size_t det_cap, size_t* n_dets,
+                          vofod_cluster_info* clusters, size_t cl_cap, size_t* n_far_clusters);
+
+/* ---- C6: updateSeparatedBGClusters (vofod_nodelet.cpp:1126-1278) ------------------------------ */
+int vofod_sepclusters(vofod_ctx*, int its_diff, const vofod_params*, int* sure_background_sufficient);
+
+/* ---- nodelet state that lives beside the maps (vofod_nodelet.cpp:2323-2332) -------------------- */
+int vofod_state_get(const vofod_ctx*, int* background_pts_sufficient, int* sure_background_sufficient,
+                    uint32_t* last_detection_id);
+int vofod_state_set(vofod_ctx*, int background_pts_sufficient, int sure_background_sufficient,
+                    uint32_t last_detection_id);
+
+/* ---- whole scan, device-resident, no host round trip between stages (schedule S1) ------------- */
+int vofod_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*,
+                       const vofod_params*, const vofod_schedule*, vofod_scan_result* res,
+                       vofod_detection* dets, size_t det_cap);
+/* same, but the scan is already in device memory (bench "value" leg: inputs resident in HBM) */
+int vofod_upload_scan(vofod_ctx*, int slot, const vofod_pt* scan, size_t n);
+int vofod_process_scan_resident(vofod_ctx*, int slot, const vofod_pose*, const vofod_params*,
+                                const vofod_schedule*, vofod_scan_result* res,
+                                vofod_detection* dets, size_t det_cap);
+/* outputs of the last process_scan kept on the device, fetched on demand (debug topics) */
+int vofod_last_voxels(vofod_ctx*, vofod_vox* out, int32_t* labels, uint8_t* in_close, size_t cap, size_t* m);
+int vofod_last_clusters(vofod_ctx*, vofod_cluster_info* out, size_t cap, size_t* n);
+
+/* ---- multi-GPU slab mode (no counterpart in the reference) ---------------------- */
+/* restrict this context to cells lo <= idx[axis] < hi of the global grid */
+int vofod_set_slab(vofod_ctx*, int axis, int lo, int hi);
+/* boundary fragments for the cross-slab cluster merge: points within `halo` cells of a slab face */
+int vofod_slab_boundary(vofod_ctx*, int32_t* point_idx, int32_t* labels, size_t cap, size_t* n);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* device time [ms] of the stages of the last process_scan, names follow the reference's ScopeTimer
+ * checkpoints (vofod_nodelet.cpp:924-964, 1527-1604, 1147-1274) */
+#define VOFOD_N_STAGES 12
+int vofod_stage_times(vofod_ctx*, float ms[VOFOD_N_STAGES]);
+const char* vofod_stage_name(int i);
+/* number of kernels the library launched since the context was created */
+uint64_t vofod_kernel_launches(const vofod_ctx*);
+/* raw CUDA stream handle (cudaStream_t) the context enqueues on, for event timing by the caller */
+void* vofod_stream(vofod_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOFOD_CUDA_H */

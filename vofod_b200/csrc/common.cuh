@@ -1,0 +1,259 @@
+// libvofod_cuda internals: context, geometry, device helpers.  sm_100a only.
+// The whole library is compiled with -fmad=false: every fp32 op in the parity-critical device code is a
+// separately rounded IEEE operation, exactly like the reference's x86-64 build without -march
+// (CMakeLists.txt:10-15).  Division and sqrt are IEEE (--prec-div/--prec-sqrt default true).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/vofod_cuda.h"
+
+#define VOFOD_FULL 0xffffffffu
+
+// ---- geometry of the dense grid (voxel_map.cpp:21-48), passed by value to kernels -------------------
+struct Geom
+{
+  float off[3];
+  float vs, inv, half;
+  int size[3];      // global cells per axis
+  int st_lo[3];     // storage box (global index coords) held by this context: == 0 / size when unsharded
+  int st_size[3];
+  int own_lo, own_hi, slab_axis;  // owned range along slab_axis (cells outside are halo)
+};
+
+__host__ __device__ inline long long geom_cells(const Geom& g) { return (long long)g.st_size[0] * g.st_size[1] * g.st_size[2]; }
+
+// voxel_map.cpp:592-599 — sub, mul, floor, each rounded separately
+__device__ __forceinline__ int coord_to_idx1(const float x, const float off, const float inv) { return (int)floorf((x - off) * inv); }
+// voxel_map.cpp:607-613
+__device__ __forceinline__ float idx_to_coord1(const int i, const float off, const float vs) { return ((float)i + 0.5f) * vs + off; }
+// voxel_map.cpp:289-300 (global limits)
+__device__ __forceinline__ bool in_limits_idx(const Geom& g, const int x, const int y, const int z)
+{
+  return x >= 0 && x < g.size[0] && y >= 0 && y < g.size[1] && z >= 0 && z < g.size[2];
+}
+// storage index of a global cell, or -1 when this context does not hold it
+__device__ __forceinline__ long long cell_index(const Geom& g, const int x, const int y, const int z)
+{
+  const int lx = x - g.st_lo[0], ly = y - g.st_lo[1], lz = z - g.st_lo[2];
+  if (lx < 0 || lx >= g.st_size[0] || ly < 0 || ly >= g.st_size[1] || lz < 0 || lz >= g.st_size[2])
+    return -1;
+  return (long long)lx + (long long)ly * g.st_size[0] + (long long)lz * g.st_size[0] * g.st_size[1];
+}
+__device__ __forceinline__ bool cell_owned(const Geom& g, const int x, const int y, const int z)
+{
+  const int v = g.slab_axis == 0 ? x : (g.slab_axis == 1 ? y : z);
+  return v >= g.own_lo && v < g.own_hi;
+}
+
+// ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
+#define ACC_LEN_BITS 44
+__device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
+{
+  len_q = ((long long)(p << (64 - ACC_LEN_BITS))) >> (64 - ACC_LEN_BITS);
+  count = (unsigned)((p - (unsigned long long)len_q) >> ACC_LEN_BITS);
+}
+struct Window
+{
+  int lo[3];
+  int size[3];
+};
+
+// ---- grow-only device buffer ------------------------------------------------------------------------
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+struct Pose33
+{
+  float R[9];
+  float t[3];
+};
+
+// Euclidean-cluster workspace handles (cluster.cu)
+struct ClusterWs
+{
+  DevBuf pts;        // float4 per point
+  DevBuf table_key;  // u64 per slot
+  DevBuf table_head; // i32 per slot
+  DevBuf next;       // i32 per point
+  DevBuf parent;     // i32 per point
+  DevBuf sizes;      // i32 per point (size of the cluster rooted here)
+};
+
+#define MAX_TILE_STATES (1 << 15)
+
+struct vofod_ctx
+{
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t n_launches = 0;
+
+  // map
+  bool map_ready = false;
+  Geom g;
+  DevBuf score;   // float
+  DevBuf flags;   // uint8
+  bool flags_full_dirty = false;
+  DevBuf flagged; // u32 cell indices (storage index) written since the last clear
+  size_t flagged_cap = 0;
+
+  // raycast accumulator
+  DevBuf acc;     // u64 per window cell
+  Window win;
+  bool win_valid = false;   // window allocated + zeroed and matches `win`
+  int frac_bits = 24;
+  bool acc_has_data = false;
+
+  // sensor
+  int W = 0, H = 0;
+  DevBuf lut_dir, lut_off;  // float4 per ray
+  DevBuf mask;              // u8 per ray
+  bool lut_has_off = false;
+  float lut_max_off = 0.f;
+
+  // scan slots (device-resident scans)
+  DevBuf scan_slot[4];
+  size_t scan_slot_n[4] = {0, 0, 0, 0};
+  void* pinned = nullptr;   // small pinned host block for result read-back
+  size_t pinned_bytes = 0;
+
+  // voxel-grid workspace
+  DevBuf vg_pts;    // float4 per input point (x,y,z,valid/intensity)
+  DevBuf vg_keys_a, vg_keys_b;
+  DevBuf vg_flags, vg_scan, vg_ustart, vg_ukey, vg_pref;
+  DevBuf vox;       // vofod_vox per output voxel (cloud_weighted of the last scan)
+  DevBuf d_counters;  // u32/u64 scratch counters (see enum below)
+  DevBuf tile_state;  // u64 decoupled look-back states
+  DevBuf sort_hist;   // u32 [passes][256]
+  uint32_t epoch = 1;
+
+  // clustering / per-scan products
+  ClusterWs cl, cl_bg;
+  DevBuf labels;      // i32 per voxel
+  DevBuf pt_close;    // u8 per voxel: hasCloseTo result, then "in close cluster"
+  DevBuf cl_close;    // i32 per voxel: per-root close flag
+  DevBuf far_list, far_keys_a, far_keys_b;  // classification order
+  DevBuf cl_info;     // vofod_cluster_info per far cluster
+  DevBuf dets;        // vofod_detection
+  DevBuf explore_ws;
+  DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
+  size_t last_m = 0, last_far = 0;
+
+  // sepclusters workspace
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure;
+
+  // nodelet state (vofod_nodelet.cpp:2323-2332)
+  bool background_pts_sufficient = false;
+  bool sure_background_sufficient = false;
+  uint32_t last_detection_id = 0;
+  int detection_its = 0;
+  float cfg_voxel_size = 0.f;
+
+  // instrumentation
+  cudaEvent_t ev[VOFOD_N_STAGES + 1];
+  bool ev_ok = false;
+  float stage_ms[VOFOD_N_STAGES];
+};
+
+// device counter slots inside ctx->d_counters (u64 each)
+enum
+{
+  CNT_TRAVERSALS = 0,
+  CNT_APPLY_ANY,
+  CNT_FLAGGED,
+  CNT_FLAGGED_OVERFLOW,
+  CNT_NBG,
+  CNT_VG_MIN,     // 3 ints packed in 2 slots (see voxelgrid.cu) -> uses slots CNT_VG_MIN .. +1
+  CNT_VG_MIN2,
+  CNT_VG_MAX,
+  CNT_VG_MAX2,
+  CNT_VG_NVALID,
+  CNT_VG_M,
+  CNT_VG_OVERFLOW,
+  CNT_NCLUSTERS,
+  CNT_NCLOSE,
+  CNT_NFAR,
+  CNT_NDET,
+  CNT_WATCHDOG,
+  CNT_MAXVAL,
+  CNT_SEP_K,
+  CNT_SEP_KDS,
+  CNT_SEP_NCL,
+  CNT_SEP_ANY_SURE,
+  CNT_OOB,
+  CNT_EXPLORE_N,
+  CNT_SCRATCH0,
+  CNT_SCRATCH1,
+  CNT_N_SLOTS = 64
+};
+
+// ---- host helpers ----------------------------------------------------------------------------------
+int vf_fail(vofod_ctx* c, int code, const char* fmt, ...);
+int vf_ensure(vofod_ctx* c, DevBuf& b, size_t bytes);
+#define CK(call)                                                                                         \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return vf_fail(ctx, VOFOD_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define RET(call)          \
+  do                       \
+  {                        \
+    int r__ = (call);      \
+    if (r__ < 0)           \
+      return r__;          \
+  } while (0)
+#define ENSURE(buf, bytes) RET(vf_ensure(ctx, buf, bytes))
+// kernel launch with accounting
+#define LAUNCH(kern, grid, block, smem, ...)                                                             \
+  do                                                                                                     \
+  {                                                                                                      \
+    kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                        \
+    ctx->n_launches++;                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess)                                                                              \
+      return vf_fail(ctx, VOFOD_E_CUDA, "launch %s failed: %s (%s:%d)", #kern, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int vf_blocks(const vofod_ctx* c, size_t n, int block, int per_sm = 8)
+{
+  size_t b = (n + block - 1) / block;
+  const size_t cap = (size_t)c->num_sms * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static inline unsigned long long* vf_cnt(vofod_ctx* c, int slot) { return c->d_counters.as<unsigned long long>() + slot; }
+
+// ---- stage entry points shared between the staged C ABI and vofod_process_scan (device pointers) ----
+// voxelgrid.cu
+int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p);
+// cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
+int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
+                   int* d_labels, unsigned long long* d_ncl);
+// raycast.cu
+int vf_raycast_accumulate_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p);
+int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);
+// pipeline.cu
+int vf_range_update_dev(vofod_ctx* ctx, const float pt[3], const vofod_params& p, int repeats);
+int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
+int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score,
+                         float flag);
+int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out);
+// classify.cu
+int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
+                           const vofod_pose& tf, const vofod_params& p);
+// sepclusters.cu
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);

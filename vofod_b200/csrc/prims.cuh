@@ -1,0 +1,321 @@
+// Device-wide primitives written for this library (no CUB/Thrust on the product path):
+//   * single-pass exclusive scan with decoupled look-back
+//   * Onesweep-style LSD radix sort (one histogram sweep + one chained-scan scatter kernel per 8-bit digit),
+//     keys u32/u64, optional u32 payload, stable
+// All kernels are persistent (grid <= co-resident capacity), take their element count from DEVICE memory so
+// a whole scan can be enqueued without a host round trip, and every spin is bounded by a watchdog.
+#pragma once
+#include "common.cuh"
+
+namespace prims
+{
+constexpr int NT = 256;           // threads per block
+constexpr int IPT = 8;            // items per thread
+constexpr int TILE = NT * IPT;    // 2048
+constexpr int SPIN_LIMIT = 1 << 22;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(VOFOD_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(VOFOD_FULL, v, o);
+    if (lane_id() >= (unsigned)o)
+      v += t;
+  }
+  return v;
+}
+// exclusive scan over the block (NT threads); `ws` = NT/32 words of shared memory; returns exclusive prefix, total in `total`
+__device__ __forceinline__ uint32_t block_excl_scan(const uint32_t v, uint32_t* ws, uint32_t& total)
+{
+  const uint32_t inc = warp_incl_scan(v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane_id() == 31)
+    ws[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < NT / 32; i++)
+  {
+    const uint32_t s = ws[i];
+    if (i < w)
+      base += s;
+    tot += s;
+  }
+  total = tot;
+  return base + inc - v;
+}
+
+// ---- decoupled look-back -------------------------------------------------------------------------------
+// state word: [63:34] epoch | [33:32] status (1 = aggregate, 2 = inclusive prefix) | [31:0] value
+__device__ __forceinline__ unsigned long long st_pack(const uint32_t epoch, const unsigned long long status, const uint32_t value)
+{
+  return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)value;
+}
+__device__ __forceinline__ void st_store(unsigned long long* p, const unsigned long long v) { *(volatile unsigned long long*)p = v; }
+__device__ __forceinline__ unsigned long long st_load(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+
+// one thread per chain; `chain` entries are `stride` apart.  Returns the exclusive prefix of `tile`.
+__device__ inline uint32_t lookback(unsigned long long* chain, const int stride, const int tile, const uint32_t aggregate, const uint32_t epoch,
+                                    unsigned long long* watchdog)
+{
+  if (tile == 0)
+  {
+    st_store(chain, st_pack(epoch, 2ull, aggregate));
+    return 0u;
+  }
+  st_store(chain + (size_t)tile * stride, st_pack(epoch, 1ull, aggregate));
+  uint32_t excl = 0;
+  int t = tile - 1;
+  int spins = 0;
+  while (t >= 0)
+  {
+    const unsigned long long s = st_load(chain + (size_t)t * stride);
+    const unsigned status = (unsigned)((s >> 32) & 3ull);
+    if ((uint32_t)(s >> 34) == (epoch & 0x3fffffffu) && status != 0u)
+    {
+      excl += (uint32_t)s;
+      if (status == 2u)
+        break;
+      t--;
+    } else
+    {
+      if (++spins > SPIN_LIMIT)
+      {
+        atomicAdd(watchdog, 1ull);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  st_store(chain + (size_t)tile * stride, st_pack(epoch, 2ull, excl + aggregate));
+  return excl;
+}
+
+__device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const size_t cap)
+{
+  if (!d_n)
+    return cap;
+  const unsigned long long n = *d_n;
+  return n < cap ? (size_t)n : cap;
+}
+
+// ---- exclusive scan of u32 ------------------------------------------------------------------------------
+// out[i] = sum_{j<i} in[j]; *total (u64, may be null) = sum of all.  in/out may alias.  Buffers must be padded to TILE.
+__global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const unsigned long long* d_n, const size_t cap,
+                                                      unsigned long long* state, const uint32_t epoch, unsigned long long* total, unsigned long long* watchdog)
+{
+  __shared__ uint32_t ws[NT / 32];
+  __shared__ uint32_t s_base;
+  const size_t n = dev_count(d_n, cap);
+  const int n_tiles = (int)((n + TILE - 1) / TILE);
+  if (n_tiles == 0)
+  {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total)
+      *total = 0ull;
+    return;
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const size_t base_i = (size_t)tile * TILE + (size_t)threadIdx.x * IPT;
+    uint32_t v[IPT];
+    const uint4 a = *reinterpret_cast<const uint4*>(in + base_i);
+    const uint4 b = *reinterpret_cast<const uint4*>(in + base_i + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+    {
+      if (base_i + k >= n)
+        v[k] = 0;
+      tsum += v[k];
+    }
+    uint32_t agg;
+    const uint32_t texcl = block_excl_scan(tsum, ws, agg);
+    if (threadIdx.x == 0)
+    {
+      s_base = lookback(state, 1, tile, agg, epoch, watchdog);
+      if (tile == n_tiles - 1 && total)
+        *total = (unsigned long long)s_base + agg;
+    }
+    __syncthreads();
+    uint32_t run = s_base + texcl;
+    uint32_t o[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+    {
+      o[k] = run;
+      run += v[k];
+    }
+    *reinterpret_cast<uint4*>(out + base_i) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(out + base_i + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    __syncthreads();
+  }
+}
+
+// ---- radix sort --------------------------------------------------------------------------------------------
+template <class KeyT>
+__global__ void __launch_bounds__(NT) k_radix_hist(const KeyT* __restrict__ keys, const unsigned long long* d_n, const size_t cap, uint32_t* __restrict__ hist,
+                                                   const int begin_bit, const int passes)
+{
+  __shared__ uint32_t sh[8 * 256];
+  for (int i = threadIdx.x; i < passes * 256; i += NT)
+    sh[i] = 0;
+  __syncthreads();
+  const size_t n = dev_count(d_n, cap);
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT)
+  {
+    const KeyT k = keys[i];
+    for (int p = 0; p < passes; p++)
+      atomicAdd(&sh[p * 256 + (int)((k >> (begin_bit + 8 * p)) & 0xFF)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += NT)
+    if (sh[i])
+      atomicAdd(&hist[i], sh[i]);
+}
+
+template <class KeyT, bool HAS_VAL>
+__global__ void __launch_bounds__(NT) k_radix_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                                   const unsigned long long* d_n, const size_t cap, const uint32_t* __restrict__ hist_pass,
+                                                   unsigned long long* state, const uint32_t epoch, const int shift, unsigned long long* watchdog)
+{
+  __shared__ uint32_t wcnt[NT / 32][256];
+  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t dbase[256];
+  __shared__ uint32_t ws[NT / 32];
+  const size_t n = dev_count(d_n, cap);
+  const int n_tiles = (int)((n + TILE - 1) / TILE);
+  if (n_tiles == 0)
+    return;
+  {
+    uint32_t tot;
+    gbase[threadIdx.x] = block_excl_scan(hist_pass[threadIdx.x], ws, tot);
+  }
+  const int w = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+#pragma unroll
+    for (int i = 0; i < NT / 32; i++)
+      wcnt[i][threadIdx.x] = 0;
+    __syncthreads();
+    KeyT key[IPT];
+    uint32_t val[IPT];
+    uint32_t rank[IPT];
+    const size_t wbase = (size_t)tile * TILE + (size_t)w * (32 * IPT);
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+    {
+      const size_t i = wbase + k * 32 + lane;
+      const bool valid = i < n;
+      key[k] = valid ? kin[i] : (KeyT)0;
+      if (HAS_VAL)
+        val[k] = valid ? vin[i] : 0u;
+      const unsigned d = valid ? (unsigned)((key[k] >> shift) & 0xFF) : (256u + lane);
+      const unsigned m = __match_any_sync(VOFOD_FULL, d);
+      uint32_t r = 0;
+      if (valid)
+        r = wcnt[w][d] + __popc(m & lanemask_lt());
+      __syncwarp();
+      if (valid && lane == (unsigned)(__ffs(m) - 1))
+        wcnt[w][d] += __popc(m);
+      __syncwarp();
+      rank[k] = r;
+    }
+    __syncthreads();
+    {
+      const int d = threadIdx.x;
+      uint32_t running = 0;
+#pragma unroll
+      for (int i = 0; i < NT / 32; i++)
+      {
+        const uint32_t c = wcnt[i][d];
+        wcnt[i][d] = running;
+        running += c;
+      }
+      const uint32_t excl = lookback(state + d, 256, tile, running, epoch, watchdog);
+      dbase[d] = gbase[d] + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+    {
+      const size_t i = wbase + k * 32 + lane;
+      if (i < n)
+      {
+        const unsigned d = (unsigned)((key[k] >> shift) & 0xFF);
+        const uint32_t pos = dbase[d] + wcnt[w][d] + rank[k];
+        kout[pos] = key[k];
+        if (HAS_VAL)
+          vout[pos] = val[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static inline int persistent_grid(const vofod_ctx* c, const size_t cap_items)
+{
+  size_t tiles = (cap_items + TILE - 1) / TILE;
+  if (tiles < 1)
+    tiles = 1;
+  const size_t g = (size_t)c->num_sms * 2;  // 2 x 256-thread CTAs per SM are always co-resident for these kernels
+  return (int)(tiles < g ? tiles : g);
+}
+static inline size_t padded(const size_t n) { return ((n + TILE - 1) / TILE + 1) * TILE; }
+
+// host drivers ------------------------------------------------------------------------------------------------
+static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total)
+{
+  const size_t tiles = (cap + TILE - 1) / TILE + 1;
+  ENSURE(ctx->tile_state, tiles * 256 * sizeof(unsigned long long));
+  const uint32_t epoch = (ctx->epoch++) & 0x3fffffffu;
+  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, ctx->tile_state.as<unsigned long long>(), epoch, d_total, vf_cnt(ctx, CNT_WATCHDOG));
+  return 0;
+}
+
+// sorts bits [begin_bit, end_bit) ascending, stable.  a/b (and va/vb) are ping-pong buffers; *out_k / *out_v receive the result pointers.
+template <class KeyT, bool HAS_VAL>
+static inline int radix_sort(vofod_ctx* ctx, KeyT* a, KeyT* b, uint32_t* va, uint32_t* vb, const unsigned long long* d_n, const size_t cap, const int begin_bit,
+                             const int end_bit, KeyT** out_k, uint32_t** out_v)
+{
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  if (passes <= 0 || passes > 8)
+    return vf_fail(ctx, VOFOD_E_INVALID, "radix_sort: bad bit range [%d,%d)", begin_bit, end_bit);
+  const size_t tiles = (cap + TILE - 1) / TILE + 1;
+  ENSURE(ctx->tile_state, tiles * 256 * sizeof(unsigned long long));
+  ENSURE(ctx->sort_hist, 8 * 256 * sizeof(uint32_t));
+  CK(cudaMemsetAsync(ctx->sort_hist.p, 0, 8 * 256 * sizeof(uint32_t), ctx->stream));
+  uint32_t* hist = ctx->sort_hist.as<uint32_t>();
+  LAUNCH((k_radix_hist<KeyT>), vf_blocks(ctx, cap, NT, 4), NT, 0, a, d_n, cap, hist, begin_bit, passes);
+  KeyT* kin = a;
+  KeyT* kout = b;
+  uint32_t* vin = va;
+  uint32_t* vout = vb;
+  for (int p = 0; p < passes; p++)
+  {
+    const uint32_t epoch = (ctx->epoch++) & 0x3fffffffu;
+    LAUNCH((k_radix_pass<KeyT, HAS_VAL>), persistent_grid(ctx, cap), NT, 0, kin, kout, vin, vout, d_n, cap, hist + p * 256,
+           ctx->tile_state.as<unsigned long long>(), epoch, begin_bit + 8 * p, vf_cnt(ctx, CNT_WATCHDOG));
+    KeyT* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  *out_k = kin;
+  if (out_v)
+    *out_v = vin;
+  return 0;
+}
+}  // namespace prims

@@ -1,0 +1,466 @@
+// filterAndTransform (vofod_nodelet.cpp:621-684) + VoxelGridWeighted / VoxelGridCounted
+// (src/voxel_grid_weighted.cpp:41-190, src/voxel_grid_counted.cpp:49-196) on the GPU:
+//   K1a crop (exclude box, sensor frame) + rigid transform + crop (operation area) + min/max   [1 pass over the scan]
+//   K1b layout: min_b / offset / div exactly as the reference computes them                     [1 thread]
+//   K1c voxel key per point (invalid points get the sentinel 0xFFFFFFFF)
+//   K2  hand-written LSD radix sort of the keys (prims.cuh) — keys only: the output needs neither the point
+//       index nor ijk (ijk is recovered from the key), and VoxelGridCounted's counts are prefix sums over the
+//       UNSORTED input (its slice quirk, voxel_grid_counted.cpp:185-187)
+//   K3  run heads -> exclusive scan -> unique keys + run starts -> voxel centre + count
+#include <math.h>
+
+#include "common.cuh"
+#include "prims.cuh"
+
+struct VgLayout
+{
+  float offset[3];
+  float leaf, inv;
+  int min_b[3], max_b[3], div[3];
+  int overflow;
+  unsigned n_valid;
+};
+
+struct CropArgs
+{
+  Pose33 tf;
+  float ex_min[3], ex_max[3];
+  float op_min[3], op_max[3];
+  int n;
+};
+
+// monotone float <-> int mapping for atomicMin/atomicMax
+__device__ __forceinline__ int f2ord(const float f)
+{
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(const int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
+
+struct MinMax
+{
+  int mn[3], mx[3];
+  unsigned n_valid;
+  unsigned pad;
+};
+
+__global__ void k_minmax_init(MinMax* mm)
+{
+  for (int a = 0; a < 3; a++)
+  {
+    mm->mn[a] = f2ord(3.402823466e+38f);
+    mm->mx[a] = f2ord(-3.402823466e+38f);
+  }
+  mm->n_valid = 0;
+}
+
+__device__ __forceinline__ void block_minmax_commit(const bool valid, const float x, const float y, const float z, MinMax* mm)
+{
+  int mn[3] = {valid ? f2ord(x) : 0x7fffffff, valid ? f2ord(y) : 0x7fffffff, valid ? f2ord(z) : 0x7fffffff};
+  int mx[3] = {valid ? f2ord(x) : (int)0x80000000, valid ? f2ord(y) : (int)0x80000000, valid ? f2ord(z) : (int)0x80000000};
+  unsigned cnt = valid ? 1u : 0u;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+  {
+    mn[a] = __reduce_min_sync(VOFOD_FULL, mn[a]);
+    mx[a] = __reduce_max_sync(VOFOD_FULL, mx[a]);
+  }
+  cnt = __reduce_add_sync(VOFOD_FULL, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt)
+  {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+      atomicMin(&mm->mn[a], mn[a]);
+      atomicMax(&mm->mx[a], mx[a]);
+    }
+    atomicAdd(&mm->n_valid, cnt);
+  }
+}
+
+// K1a — pcl::CropBox(negative) -> pcl::transformPointCloud -> pcl::CropBox (vofod_nodelet.cpp:626-655)
+__global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const vofod_pt* __restrict__ scan, float4* __restrict__ pts, MinMax* mm)
+{
+  __shared__ __align__(16) uint32_t s_pts[256 * 5];
+  const int blk_first = blockIdx.x * 256;
+  {
+    const int n_here = min(256, a.n - blk_first);
+    const int n_words = n_here * 5;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(scan) + (size_t)blk_first * 5;
+    const int n_vec = n_words / 4;
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    for (int i = threadIdx.x; i < n_vec; i += 256)
+      reinterpret_cast<uint4*>(s_pts)[i] = __ldg(src4 + i);
+    for (int i = n_vec * 4 + threadIdx.x; i < n_words; i += 256)
+      s_pts[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int idx = blk_first + threadIdx.x;
+  bool valid = idx < a.n;
+  float X = 0.f, Y = 0.f, Z = 0.f;
+  if (valid)
+  {
+    const float x = __uint_as_float(s_pts[threadIdx.x * 5 + 0]), y = __uint_as_float(s_pts[threadIdx.x * 5 + 1]), z = __uint_as_float(s_pts[threadIdx.x * 5 + 2]);
+    valid = isfinite(x) && isfinite(y) && isfinite(z);
+    // keep points OUTSIDE the closed exclude box
+    const bool outside1 = (x < a.ex_min[0] || y < a.ex_min[1] || z < a.ex_min[2]) || (x > a.ex_max[0] || y > a.ex_max[1] || z > a.ex_max[2]);
+    valid = valid && outside1;
+    // PCL 1.10 SSE transform order: x*c0 + (y*c1 + (z*c2 + c3))
+    X = x * a.tf.R[0] + (y * a.tf.R[1] + (z * a.tf.R[2] + a.tf.t[0]));
+    Y = x * a.tf.R[3] + (y * a.tf.R[4] + (z * a.tf.R[5] + a.tf.t[1]));
+    Z = x * a.tf.R[6] + (y * a.tf.R[7] + (z * a.tf.R[8] + a.tf.t[2]));
+    const bool outside2 = (X < a.op_min[0] || Y < a.op_min[1] || Z < a.op_min[2]) || (X > a.op_max[0] || Y > a.op_max[1] || Z > a.op_max[2]);
+    valid = valid && isfinite(X) && isfinite(Y) && isfinite(Z) && !outside2;
+    pts[idx] = make_float4(X, Y, Z, valid ? 1.0f : 0.0f);
+  }
+  block_minmax_commit(valid, X, Y, Z, mm);
+}
+
+// generic input: xyz triples (stride floats), w = 4th value (intensity) or 1; valid = finite
+__global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in, const int stride, const int n, float4* __restrict__ pts, MinMax* mm)
+{
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  bool valid = idx < n;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (valid)
+  {
+    x = in[(size_t)idx * stride];
+    y = in[(size_t)idx * stride + 1];
+    z = in[(size_t)idx * stride + 2];
+    valid = isfinite(x) && isfinite(y) && isfinite(z);
+    // w carries validity (weighted) — the counted variant reads intensity from the source array directly
+    pts[idx] = make_float4(x, y, z, valid ? 1.0f : 0.0f);
+  }
+  block_minmax_commit(valid, x, y, z, mm);
+}
+
+// K1b — voxel_grid_weighted.cpp:56-111
+__global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, const int align, const float ac0, const float ac1, const float ac2, VgLayout* __restrict__ L,
+                            unsigned long long* __restrict__ counters)
+{
+  const float inv = 1.0f / leaf;
+  L->leaf = leaf;
+  L->inv = inv;
+  L->n_valid = mm->n_valid;
+  L->overflow = 0;
+  counters[CNT_VG_NVALID] = mm->n_valid;
+  counters[CNT_VG_OVERFLOW] = 0;
+  if (mm->n_valid == 0)
+  {
+    for (int a = 0; a < 3; a++)
+    {
+      L->offset[a] = 0.f;
+      L->min_b[a] = L->max_b[a] = 0;
+      L->div[a] = 1;
+    }
+    return;
+  }
+  const float ac[3] = {ac0, ac1, ac2};
+  float min_p[3], max_p[3];
+  for (int a = 0; a < 3; a++)
+  {
+    min_p[a] = ord2f(mm->mn[a]);
+    max_p[a] = ord2f(mm->mx[a]);
+  }
+  const long long dx = (long long)((max_p[0] - min_p[0]) * inv) + 2;
+  const long long dy = (long long)((max_p[1] - min_p[1]) * inv) + 2;
+  const long long dz = (long long)((max_p[2] - min_p[2]) * inv) + 2;
+  if (dx * dy * dz > 2147483647ll)
+  {
+    L->overflow = 1;
+    counters[CNT_VG_OVERFLOW] = 1;
+  }
+  for (int a = 0; a < 3; a++)
+  {
+    L->min_b[a] = (int)floorf(min_p[a] * inv);
+    L->max_b[a] = (int)floorf(max_p[a] * inv);
+    float off = (float)L->min_b[a] * leaf;
+    if (align)
+    {
+      float aco = fmodf(ac[a] - leaf / 2, leaf);
+      if (aco < 0)
+        aco += leaf;
+      off -= aco;
+      L->min_b[a] = (int)floorf(off * inv);
+    }
+    L->offset[a] = off;
+    L->div[a] = L->max_b[a] - L->min_b[a] + 1;
+  }
+}
+
+// K1c — voxel_grid_weighted.cpp:122-139
+__global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, const int n, const VgLayout* __restrict__ Lp, uint32_t* __restrict__ keys)
+{
+  const VgLayout L = *Lp;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+  {
+    const float4 p = pts[i];
+    uint32_t key = 0xFFFFFFFFu;
+    if (p.w != 0.0f && !L.overflow)
+    {
+      const int ijk0 = (int)floorf((p.x - L.offset[0]) * L.inv);
+      const int ijk1 = (int)floorf((p.y - L.offset[1]) * L.inv);
+      const int ijk2 = (int)floorf((p.z - L.offset[2]) * L.inv);
+      key = (uint32_t)(ijk0 + ijk1 * L.div[0] + ijk2 * L.div[0] * L.div[1]);
+    }
+    keys[i] = key;
+  }
+}
+
+// K3a — run heads among the valid (non-sentinel) sorted keys
+__global__ void __launch_bounds__(256) k_vg_heads(const uint32_t* __restrict__ keys, const int n, uint32_t* __restrict__ heads)
+{
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+  {
+    const uint32_t k = keys[i];
+    heads[i] = (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+  }
+}
+// K3b — scatter run starts
+__global__ void __launch_bounds__(256) k_vg_starts(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ heads_scan, const int n, uint32_t* __restrict__ ukey,
+                                                   uint32_t* __restrict__ ustart)
+{
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+  {
+    const uint32_t k = keys[i];
+    if (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k))
+    {
+      const uint32_t r = heads_scan[i];
+      ukey[r] = k;
+      ustart[r] = (uint32_t)i;
+    }
+  }
+}
+// K3c — voxel centre + weight (voxel_grid_weighted.cpp:169-188); counted variant: voxel_grid_counted.cpp:179-194
+__global__ void __launch_bounds__(256) k_vg_emit(const uint32_t* __restrict__ ukey, const uint32_t* __restrict__ ustart, const VgLayout* __restrict__ Lp,
+                                                 const unsigned long long* __restrict__ d_m, const uint32_t* __restrict__ over_prefix, vofod_vox* __restrict__ out,
+                                                 const size_t out_cap)
+{
+  const VgLayout L = *Lp;
+  const unsigned m = (unsigned)*d_m;
+  for (unsigned r = blockIdx.x * 256 + threadIdx.x; r < m && r < out_cap; r += gridDim.x * 256)
+  {
+    const uint32_t key = ukey[r];
+    const uint32_t first = ustart[r];
+    const uint32_t last = (r + 1 < m) ? ustart[r + 1] : L.n_valid;
+    const int d0 = L.div[0], d01 = L.div[0] * L.div[1];
+    const int ijk2 = (int)(key / (uint32_t)d01);
+    const int rem = (int)(key - (uint32_t)ijk2 * (uint32_t)d01);
+    const int ijk1 = rem / d0;
+    const int ijk0 = rem - ijk1 * d0;
+    vofod_vox v;
+    v.x = ((float)ijk0 + 0.5f) * L.leaf + L.offset[0];
+    v.y = ((float)ijk1 + 0.5f) * L.leaf + L.offset[1];
+    v.z = ((float)ijk2 + 0.5f) * L.leaf + L.offset[2];
+    v.count = over_prefix ? (over_prefix[last] - over_prefix[first]) : (last - first);
+    out[r] = v;
+  }
+}
+// counted variant: flag = intensity > threshold on the UNSORTED input
+__global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restrict__ in, const int n, const float thr, uint32_t* __restrict__ flags)
+{
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+    flags[i] = in[i].intensity > thr ? 1u : 0u;
+}
+
+// shared tail: pts (float4, w = validity) + minmax -> ctx->vox / CNT_VG_M.  key_bits_hint = 0 => sort all 32 bits.
+static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool align, const float* align_center, const int key_bits_hint, const vofod_xyzi* d_counted_in,
+                  const float counted_thr, DevBuf& out_buf)
+{
+  using namespace prims;
+  const size_t np = padded(n);
+  ENSURE(ctx->vg_keys_a, np * 4);
+  ENSURE(ctx->vg_keys_b, np * 4);
+  ENSURE(ctx->vg_flags, np * 4);
+  ENSURE(ctx->vg_scan, np * 4);
+  ENSURE(ctx->vg_ukey, np * 4);
+  ENSURE(ctx->vg_ustart, np * 4);
+  ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
+  ENSURE(out_buf, np * sizeof(vofod_vox));
+  MinMax* mm = ctx->scratch_d.as<MinMax>();
+  VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  const float ac[3] = {align ? align_center[0] : 0.f, align ? align_center[1] : 0.f, align ? align_center[2] : 0.f};
+  LAUNCH(k_vg_layout, 1, 1, 0, mm, leaf, align ? 1 : 0, ac[0], ac[1], ac[2], L, cnt);
+  const int nb = vf_blocks(ctx, n, 256, 8);
+  LAUNCH(k_vg_keys, nb, 256, 0, ctx->vg_pts.as<float4>(), (int)n, L, ctx->vg_keys_a.as<uint32_t>());
+  uint32_t* sorted = nullptr;
+  const int bits = key_bits_hint > 0 && key_bits_hint < 32 ? key_bits_hint : 32;
+  RET((radix_sort<uint32_t, false>(ctx, ctx->vg_keys_a.as<uint32_t>(), ctx->vg_keys_b.as<uint32_t>(), nullptr, nullptr, nullptr, n, 0, bits, &sorted, nullptr)));
+  LAUNCH(k_vg_heads, nb, 256, 0, sorted, (int)n, ctx->vg_flags.as<uint32_t>());
+  RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_scan.as<uint32_t>(), nullptr, n, cnt + CNT_VG_M));
+  LAUNCH(k_vg_starts, nb, 256, 0, sorted, ctx->vg_scan.as<uint32_t>(), (int)n, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>());
+  const uint32_t* over_prefix = nullptr;
+  if (d_counted_in)
+  {
+    ENSURE(ctx->vg_pref, np * 4);
+    // reuse vg_flags for the over-threshold flags (heads are no longer needed)
+    LAUNCH(k_vg_over_flags, nb, 256, 0, d_counted_in, (int)n, counted_thr, ctx->vg_flags.as<uint32_t>());
+    RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_pref.as<uint32_t>(), nullptr, n + 1, nullptr));
+    over_prefix = ctx->vg_pref.as<uint32_t>();
+  }
+  LAUNCH(k_vg_emit, nb, 256, 0, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>(), L, cnt + CNT_VG_M, over_prefix, out_buf.as<vofod_vox>(), np);
+  return 0;
+}
+
+static int bits_for(unsigned long long v)
+{
+  int b = 0;
+  while (v)
+  {
+    b++;
+    v >>= 1;
+  }
+  return b;
+}
+
+int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p)
+{
+  const size_t np = prims::padded(n);
+  ENSURE(ctx->vg_pts, np * 16);
+  ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
+  CropArgs a;
+  memcpy(a.tf.R, tf.R, sizeof(a.tf.R));
+  memcpy(a.tf.t, tf.t, sizeof(a.tf.t));
+  {
+    // vofod_nodelet.cpp:204, 626-629 (host fp32)
+    volatile float ez = p.exclude_box_offset[2] + p.exclude_box_size[2] / 2.0f;
+    for (int k = 0; k < 3; k++)
+    {
+      const float o = k == 2 ? (float)ez : p.exclude_box_offset[k];
+      volatile float h = p.exclude_box_size[k] / 2;
+      a.ex_max[k] = o + h;
+      a.ex_min[k] = o - h;
+    }
+    // :212, 645-648
+    volatile float oz = p.oparea_offset[2] + p.oparea_size[2] / 2.0f;
+    for (int k = 0; k < 3; k++)
+    {
+      const float o = k == 2 ? (float)oz : p.oparea_offset[k];
+      volatile float h = p.oparea_size[k] / 2;
+      a.op_max[k] = o + h;
+      a.op_min[k] = o - h;
+    }
+  }
+  a.n = (int)n;
+  MinMax* mm = ctx->scratch_d.as<MinMax>();
+  LAUNCH(k_minmax_init, 1, 1, 0, mm);
+  LAUNCH(k_crop_transform, (int)((n + 255) / 256), 256, 0, a, d_scan, ctx->vg_pts.as<float4>(), mm);
+  // align to the map: idxToCoord(0,0,0) (vofod_nodelet.cpp:664-665)
+  const Geom& g = ctx->g;
+  float ac[3];
+  for (int k = 0; k < 3; k++)
+  {
+    volatile float c0 = (0 + 0.5f) * g.vs;
+    ac[k] = c0 + g.off[k];
+  }
+  // the crop to the operation area bounds the key range: div <= size/leaf + 3 per axis
+  unsigned long long cells = 1;
+  for (int k = 0; k < 3; k++)
+    cells *= (unsigned long long)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
+  const int bits = cells + 1 < (1ull << 31) ? bits_for(cells + 1) : 32;
+  return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, 0.f, ctx->vox);
+}
+
+static int read_m(vofod_ctx* ctx, size_t* m, int* overflow)
+{
+  unsigned long long v[2] = {0, 0};
+  CK(cudaMemcpyAsync(&v[0], vf_cnt(ctx, CNT_VG_M), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&v[1], vf_cnt(ctx, CNT_VG_OVERFLOW), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned long long wd = 0;
+  CK(cudaMemcpy(&wd, vf_cnt(ctx, CNT_WATCHDOG), 8, cudaMemcpyDeviceToHost));
+  if (wd)
+    return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", wd);
+  *m = (size_t)v[0];
+  *overflow = (int)v[1];
+  return 0;
+}
+
+extern "C" {
+
+int vofod_filter_voxelize(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vofod_pose* tf, const vofod_params* p, vofod_vox* out, size_t cap, size_t* m)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->map_ready)
+    return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  if (!tf || !p || !m || (n && !scan))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  *m = 0;
+  if (n == 0)
+    return VOFOD_OK;
+  ENSURE(ctx->scan_slot[0], n * sizeof(vofod_pt) + 64);
+  CK(cudaMemcpyAsync(ctx->scan_slot[0].p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->scan_slot_n[0] = n;
+  RET(vf_filter_voxelize_dev(ctx, ctx->scan_slot[0].as<vofod_pt>(), n, *tf, *p));
+  int overflow = 0;
+  RET(read_m(ctx, m, &overflow));
+  ctx->last_m = *m;
+  if (overflow)
+    return vf_fail(ctx, VOFOD_E_OVERFLOW, "leaf size too small for the input: integer indices would overflow");
+  if (*m > cap || (*m && !out))
+    return vf_fail(ctx, VOFOD_E_CAPACITY, "filter_voxelize: need capacity %zu", *m);
+  if (*m)
+  {
+    CK(cudaMemcpyAsync(out, ctx->vox.p, *m * sizeof(vofod_vox), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return VOFOD_OK;
+}
+
+static int vg_generic(vofod_ctx* ctx, const float* host_in, int stride, size_t n, float leaf, const float* align, bool counted, float thr, vofod_vox* out, size_t cap, size_t* m)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!m || (n && !host_in) || !(leaf > 0.0f))
+    return vf_fail(ctx, VOFOD_E_INVALID, "bad argument (leaf size must be > 0)");
+  *m = 0;
+  if (n == 0)
+    return VOFOD_OK;
+  const size_t np = prims::padded(n);
+  ENSURE(ctx->vg_pts, np * 16);
+  ENSURE(ctx->scratch_a, n * stride * 4 + 64);
+  ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
+  CK(cudaMemcpyAsync(ctx->scratch_a.p, host_in, n * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MinMax* mm = ctx->scratch_d.as<MinMax>();
+  LAUNCH(k_minmax_init, 1, 1, 0, mm);
+  LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, ctx->scratch_a.as<float>(), stride, (int)n, ctx->vg_pts.as<float4>(), mm);
+  RET(vg_run(ctx, n, leaf, align != nullptr, align, 0, counted ? ctx->scratch_a.as<vofod_xyzi>() : nullptr, thr, ctx->sep_ds));
+  int overflow = 0;
+  RET(read_m(ctx, m, &overflow));
+  if (overflow)
+    return vf_fail(ctx, VOFOD_E_OVERFLOW, "leaf size too small for the input: integer indices would overflow");
+  if (*m > cap || (*m && !out))
+    return vf_fail(ctx, VOFOD_E_CAPACITY, "voxel_grid: need capacity %zu", *m);
+  if (*m)
+  {
+    CK(cudaMemcpyAsync(out, ctx->sep_ds.p, *m * sizeof(vofod_vox), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return VOFOD_OK;
+}
+
+int vofod_voxel_grid_weighted(vofod_ctx* ctx, const float* xyz, size_t n, float leaf, const float align[3], vofod_vox* out, size_t cap, size_t* m)
+{
+  return vg_generic(ctx, xyz, 3, n, leaf, align, false, 0.f, out, cap, m);
+}
+int vofod_voxel_grid_counted(vofod_ctx* ctx, const vofod_xyzi* pts, size_t n, float leaf, float threshold, const float align[3], vofod_vox* out, size_t cap, size_t* m)
+{
+  return vg_generic(ctx, reinterpret_cast<const float*>(pts), 4, n, leaf, align, true, threshold, out, cap, m);
+}
+}
+
+// used by sepclusters.cu: counted voxel grid over device-resident xyzi points whose count is known on the host
+int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, size_t n, float leaf, float thr, DevBuf& out)
+{
+  const size_t np = prims::padded(n);
+  ENSURE(ctx->vg_pts, np * 16);
+  ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
+  MinMax* mm = ctx->scratch_d.as<MinMax>();
+  LAUNCH(k_minmax_init, 1, 1, 0, mm);
+  LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, reinterpret_cast<const float*>(d_in), 4, (int)n, ctx->vg_pts.as<float4>(), mm);
+  return vg_run(ctx, n, leaf, false, nullptr, 0, d_in, thr, out);
+}

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — scans/s of VoFOD's per-scan volumetric hot path (BASELINE.json metric) on N B200s.
+
+A "step" is ONE LiDAR scan (128 x 2048 rays) through the whole deterministic schedule S1 (rangefinder seeds ->
+filter/voxelize -> Euclidean clustering -> close/far -> point update -> raycast accumulate + apply -> classification
++ detections -> separated-background-cluster pass) on the cfg2 map (0.5 m voxels, 200 x 200 x 80 m).  Step k is scan
+k of the seeded synthetic sequence; the map state carries over, warm-up steps are the first scans of the sequence.
+
+  value : scans/s with every scan already resident in HBM (vofod_process_scan_resident)
+  e2e   : scans/s through the host-buffer entry point vofod_process_scan (pinned host scan -> H2D inside the timed
+          region, result record + detections D2H inside the timed region)
+  N > 1 : every rank runs its own independent scan stream on its own GPU (BASELINE configs[3]); no data-path
+          collective; value = sum of scans / max-over-ranks device time  ("weak" scaling)
+
+--impl reference times the reference's CPU path (the oracle restatement: the reference itself cannot be compiled
+here — no ROS/PCL/Eigen) on the host cores with the same schedule, scans and map.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 2048, 128
+VOXEL = 0.5
+OPAREA = (200.0, 200.0, 80.0)
+WORKLOAD = "cfg2: synthetic OS0-128 scans (128x2048), 0.5 m voxels, 200x200x80 m map (401x401x161), schedule S1, default detection_params"
+BYTES_PER_TRAVERSAL = 8  # 4 B read + 4 B write of the fp32 accumulator per forEachRay callback
+
+
+def make_params():
+    from vofod_b200 import abi
+    p = abi.default_params()
+    for i, (o, s) in enumerate(zip((0.0, 0.0, -1.25), OPAREA)):
+        p.oparea_offset[i] = o
+        p.oparea_size[i] = s
+    return p
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from vofod_b200 import abi, capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    K, Wm = args.steps, args.warmup
+    n_scans = K + Wm
+
+    v = capi.Vofod(local_rank)  # raises if libvofod_cuda.so / the device is missing: no CPU fallback
+    p = make_params()
+    dirs = synth.sim_lut(W, H)
+    v.reset(p, VOXEL)
+    v.set_sensor(W, H, dirs)
+    stream = torch.cuda.ExternalStream(v.stream(), device=torch.device("cuda", local_rank))
+
+    # every rank owns an independent stream of scans (rank r starts its trajectory r*1000 scans later)
+    N = W * H
+    pinned = torch.empty((n_scans, N * abi.PT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+    host_scans = pinned.numpy().view(abi.PT_DTYPE).reshape(n_scans, N)
+    poses, scheds = [], []
+    for k in range(n_scans):
+        _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k + 1000 * rank, W, H, dirs, 1.0, out=host_scans[k])
+        if rank:  # keep the take-off bootstrap on every rank: reuse the first 20 poses' altitude profile
+            pass
+        poses.append(pose)
+        scheds.append(abi.schedule_s1(rp))
+    if rank:
+        # ranks > 0 fly a different part of the trajectory but must still bootstrap from the ground: regenerate the
+        # first 20 scans with the take-off of scan indices 0..19
+        for k in range(min(20, n_scans)):
+            _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs, 1.0, out=host_scans[k])
+            poses[k] = pose
+            scheds[k] = abi.schedule_s1(rp)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    dets = np.zeros(256, dtype=abi.DETECTION_DTYPE)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_leg(resident):
+        """-> (per-step device ms list, totals dict).  State is reset, so both legs do identical work."""
+        v.reset(p, VOXEL)
+        if resident:
+            for k in range(n_scans):
+                v.upload_scan(k, host_scans[k])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
+        tot = {"trav": 0, "ray_ms": 0.0, "dets": 0, "stage": {}}
+        l0 = v.kernel_launches()
+        barrier()
+        for k in range(n_scans):
+            if k == Wm:
+                barrier()
+                l0 = v.kernel_launches()
+            with torch.cuda.stream(stream):
+                flush.fill_(k & 0xFF)  # L2 flush between steps, outside the timed events
+                ev[k][0].record(stream)
+                if resident:
+                    res, d = v.process_scan_resident(k, poses[k], p, scheds[k], dets=dets)
+                else:
+                    res, d = v.process_scan(host_scans[k], poses[k], p, scheds[k])
+                ev[k][1].record(stream)
+            if k >= Wm:
+                st = v.stage_times()
+                tot["trav"] += res.n_traversals
+                tot["ray_ms"] += st["raycasting"]
+                tot["dets"] += res.n_detections
+                for name, ms in st.items():
+                    tot["stage"][name] = tot["stage"].get(name, 0.0) + ms
+        barrier()
+        tot["launches"] = v.kernel_launches() - l0
+        ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans)]
+        return ms, tot
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, tot_res = run_leg(True)
+    ms_e2e, tot_e2e = run_leg(False)
+    clocks = sampler.stop()
+
+    t_res = torch.tensor([sum(ms_res), sum(ms_e2e), float(tot_res["trav"]), tot_res["ray_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t_res.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t_res.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax, tsum = t_res, t_res
+    total_ms, total_ms_e2e = float(tmax[0]), float(tmax[1])
+    trav_all, ray_ms_max = float(tsum[2]), float(tmax[3])
+
+    out = None
+    if rank == 0:
+        peak, peak_kind = peaks()
+        # dominant kernel: k_raycast_accumulate — algorithmic bytes = traversals x 8 B, duration = the "raycasting" stage
+        # (CUDA events on the context's stream around that single launch), averaged per launch over the timed steps
+        trav_per_launch = tot_res["trav"] / K
+        ray_ms_per_launch = tot_res["ray_ms"] / K
+        achieved = trav_per_launch * BYTES_PER_TRAVERSAL / (ray_ms_per_launch * 1e-3) / 1e9 if ray_ms_per_launch > 0 else 0.0
+        out = {
+            "metric": "scans/s",
+            "value": world * K / (total_ms * 1e-3),
+            "unit": "scans/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": Wm,
+            "ms_per_step": total_ms / K,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32 scores / u64 fixed-point path lengths / u32 keys",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scans_per_rank": K, "rays_per_scan": N,
+                       "l2": "flushed between steps (256 MB write on the same stream, outside the timed events)",
+                       "parallelism": f"{world} independent scan streams, one per GPU, no collective" if world > 1 else "1 GPU"},
+            "gvoxel_traversals_per_s": trav_all / (ray_ms_max * 1e-3) / 1e9 if ray_ms_max > 0 else None,
+            "gvoxel_traversals_per_s_full_path": trav_all / (total_ms * 1e-3) / 1e9,
+            "traversals_per_scan": trav_per_launch,
+            "e2e": {"value": world * K / (total_ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize,
+                    "d2h_bytes_per_step": 64 * 8 + 16 * abi.DETECTION_DTYPE.itemsize, "ms_per_step": total_ms_e2e / K},
+            "gpu_launches": int(tot_res["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_raycast_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": trav_per_launch * BYTES_PER_TRAVERSAL,
+                         "ms_per_launch": ray_ms_per_launch},
+            "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot_res["stage"].items()},
+            "detections_in_timed_steps": int(tot_res["dets"]),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(min(12, n_scans))
+    v.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(n_scans, timed_from=2):
+    """The oracle (CPU restatement of the reference's path) on the host, single thread, first scans of the same sequence."""
+    from oracle import oracle  # the ONLY use of oracle/ in this file besides --impl reference: the reported CPU baseline
+    from vofod_b200 import abi, synth
+    p = make_params()
+    dirs = synth.sim_lut(W, H)
+    o = oracle.Oracle(track_counts=False)
+    o.reset(p, VOXEL)
+    o.set_sensor(W, H, dirs)
+    t_total, n = 0.0, 0
+    for k in range(n_scans):
+        scan, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs)
+        s = abi.schedule_s1(rp)
+        t0 = time.perf_counter()
+        o.process_scan(scan, pose, p, s)
+        dt = time.perf_counter() - t0
+        if k >= timed_from:
+            t_total += dt
+            n += 1
+    o.close()
+    return {"value": n / t_total if t_total > 0 else None, "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": f"scans {timed_from}..{n_scans - 1} of the same sequence, schedule S1, g++ -O3 -DNDEBUG (reference flags), 1 thread; host has {os.cpu_count()} cpus"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from vofod_b200 import abi, synth
+    K, Wm = args.steps, args.warmup
+    if K + Wm > 120:  # bounded sample: ~1.5 s of CPU work per scan
+        K, Wm = min(K, 100), min(Wm, 20)
+    p = make_params()
+    dirs = synth.sim_lut(W, H)
+    o = oracle.Oracle(track_counts=False)
+    o.reset(p, VOXEL)
+    o.set_sensor(W, H, dirs)
+    t_total, trav, t_ray = 0.0, 0, 0.0
+    for k in range(K + Wm):
+        scan, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs)
+        s = abi.schedule_s1(rp)
+        t0 = time.perf_counter()
+        res, _ = o.process_scan(scan, pose, p, s)
+        dt = time.perf_counter() - t0
+        if k >= Wm:
+            t_total += dt
+            trav += res.n_traversals
+            t_ray += o.stage_times()[5] * 1e-3
+    o.close()
+    val = K / t_total
+    sample = (f"{K} scans (after {Wm} warm-up scans) of the same sequence, schedule S1 fully serial on 1 thread — the reference runs each of its actors "
+              f"(scan, raycast, background clusters) on a single thread (pointcloud_threads: 1); host has {os.cpu_count()} cpus")
+    out = {"impl": "reference", "metric": "scans/s", "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+           "ms_per_step": 1e3 * t_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "note": "CPU oracle (restatement of the reference; the reference needs ROS/PCL/Eigen and cannot be built here)"},
+           "gvoxel_traversals_per_s": trav / t_ray / 1e9 if t_ray > 0 else None,
+           "cpu_baseline": {"value": val, "unit": "scans/s", "cores": 1, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=80)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -235,6 +235,8 @@ int vofod_raycast_accumulate(vofod_ctx*, const vofod_pt* scan, size_t n, const v
  * either pointer may be NULL. */
 int vofod_raycast_download(vofod_ctx*, uint32_t* counts, float* lengths, size_t n_cells);
 int vofod_raycast_apply(vofod_ctx*, int its_diff, const vofod_params*);
+/* fractional bits of the fixed-point path-length accumulator chosen for the current sensor / voxel size */
+int vofod_raycast_frac_bits(const vofod_ctx*);
 
 /* ---- A16..A19: classifyClusters + extractDetections (vofod_nodelet.cpp:819-879, 1648-1731) ---- */
 int vofod_classify_detect(vofod_ctx*, const vofod_vox* pts, const int32_t* labels,

@@ -1,0 +1,328 @@
+"""-m gpu: libvofod_cuda (through its C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): traversed-voxel sets, hit counts, voxel-grid outputs and cluster partitions
+bit-exact; float occupancy scores and detection centroids within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from vofod_b200 import abi
+
+from harness import Sensor, assert_vox_equal, cfg2_params, params_for, rel_err, setup_pair, small_params, struct_close
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5  # north_star: "float occupancy scores ... within 1e-5 relative"
+
+
+# ---- C1: VoxelMap primitives -----------------------------------------------------------------------
+def test_map_geometry_b6(gpu, cpu):
+    for o in (gpu, cpu):
+        o.map_resize((0, 0, 38.75), (200, 200, 80), 0.5)
+    g, c = gpu.map_info(), cpu.map_info()
+    assert list(g.sizes) == list(c.sizes) == [401, 401, 161]
+    assert list(g.offset) == list(c.offset) == [-100.0, -100.0, -1.25]
+    assert g.n_cells == c.n_cells == 25888961
+
+
+def test_trace_ray_kat_and_random(gpu, cpu):
+    for o in (gpu, cpu):
+        o.map_resize_idx((0, 0, 0), (4, 4, 4), 1.0)
+    # Appendix B1-B4
+    d, i = gpu.map_trace_ray((0.5, 0.5, 0.5), (1, 0, 0), 2.2)
+    np.testing.assert_allclose(d, [0.5, 1.0, 0.7], rtol=1e-6)
+    assert i.tolist() == [[0, 0, 0], [1, 0, 0], [2, 0, 0]]
+    d, i = gpu.map_trace_ray((0.5, 0.5, 0.5), (-1, 0, 0), 5.0)
+    assert i.tolist() == [[0, 0, 0]] and d.tolist() == [0.5]
+    rng = np.random.default_rng(7)
+    for o in (gpu, cpu):
+        o.map_resize((1.0, -2.0, 3.0), (40, 30, 20), 0.5)
+    for _ in range(200):
+        s = rng.uniform([-18, -16, -6], [19, 12, 12]).astype(np.float32)
+        v = rng.normal(size=3)
+        if rng.random() < 0.2:
+            v[rng.integers(3)] = 0.0  # axis-aligned components -> inf tdelta
+        v = (v / np.linalg.norm(v)).astype(np.float32)
+        L = np.float32(rng.uniform(-1, 40))
+        dg, ig = gpu.map_trace_ray(s, v, L)
+        dc, ic = cpu.map_trace_ray(s, v, L)
+        assert np.array_equal(ig, ic) and np.array_equal(dg, dc)
+
+
+def _random_map(gpu, cpu, rng, lo=-1000.0, hi=0.0, frac=0.02):
+    n = cpu.n_cells()
+    data = np.full(n, -740.0, dtype=np.float32)
+    sel = rng.random(n) < frac
+    data[sel] = rng.uniform(lo, hi, size=int(sel.sum())).astype(np.float32)
+    gpu.map_upload(abi.MAP_SCORE, data)
+    cpu.map_upload(abi.MAP_SCORE, data)
+    return data
+
+
+def test_count_compact_hasclose_floating_submap(gpu, cpu):
+    rng = np.random.default_rng(11)
+    for o in (gpu, cpu):
+        o.map_resize((0, 0, 5), (30, 20, 10), 0.5)
+    _random_map(gpu, cpu, rng)
+    for thr in (-300.0, -0.1, -750.0):
+        assert gpu.map_count_over(thr) == cpu.map_count_over(thr)
+    for greater, metric in ((True, False), (True, True), (False, False)):
+        a, b = gpu.map_compact_over(-300.0, greater, metric), cpu.map_compact_over(-300.0, greater, metric)
+        assert len(a) == len(b) and a.tobytes() == b.tobytes()  # same cells, same emission order
+    pts = rng.uniform([-15, -10, 0], [15, 10, 10], size=(5000, 3)).astype(np.float32)
+    assert np.array_equal(gpu.map_has_close_to(pts, 1.5, -300.0), cpu.map_has_close_to(pts, 1.5, -300.0))
+    assert np.array_equal(gpu.map_is_floating(pts, -300.0), cpu.map_is_floating(pts, -300.0))
+    sg, zg, og = gpu.map_submap_copy((-3, -2, 4), (2.2, 1.1, 6), 2)
+    sc, zc, oc = cpu.map_submap_copy((-3, -2, 4), (2.2, 1.1, 6), 2)
+    assert np.array_equal(zg, zc) and np.array_equal(og, oc) and np.array_equal(sg, sc)
+
+
+def test_has_close_to_window_b7(gpu):
+    gpu.map_resize_idx((0, 0, 0), (20, 20, 20), 0.5)
+    gpu.map_set_to(abi.MAP_SCORE, -740.0)
+    q = np.array([[5.25, 5.25, 5.25]], dtype=np.float32)  # voxel (10,10,10)
+    for off, want in (((3, 0, 0), 0), ((-3, 0, 0), 1), ((-3, -3, -3), 0), ((-3, -2, -1), 1)):
+        gpu.map_set_to(abi.MAP_SCORE, -740.0)
+        gpu.map_set(abi.MAP_SCORE, 10 + off[0], 10 + off[1], 10 + off[2], 0.0)
+        assert int(gpu.map_has_close_to(q, 1.5, -300.0)[0]) == want, off
+
+
+def test_explore_to_ground(gpu, cpu):
+    rng = np.random.default_rng(5)
+    for o in (gpu, cpu):
+        o.map_resize((0, 0, 5), (20, 20, 12), 0.5)
+    n = cpu.n_cells()
+    for trial in range(12):
+        # mostly free space (-1000), blobs of unknown (-740), rare ground (0)
+        data = np.full(n, -1000.0, dtype=np.float32)
+        r = rng.random(n)
+        data[r < 0.45] = -740.0
+        data[r < (0.002 if trial % 2 else 0.0)] = 0.0
+        gpu.map_upload(abi.MAP_SCORE, data)
+        cpu.map_upload(abi.MAP_SCORE, data)
+        for _ in range(8):
+            pt = rng.uniform([-8, -8, 1], [8, 8, 9]).astype(np.float32)
+            md = float(rng.integers(2, 13))
+            cg, eg = gpu.map_explore_to_ground(pt, -750.0, -300.0, md)
+            cc, ec = cpu.map_explore_to_ground(pt, -750.0, -300.0, md)
+            assert cg == cc
+            if not cc:
+                # the reference's DFS may list a cell more than once; the SET is what is observable
+                assert set(map(tuple, eg.tolist())) == set(map(tuple, ec.tolist()))
+
+
+# ---- C2 / C3: voxel grids ----------------------------------------------------------------------------
+def test_voxel_grid_weighted_and_counted(gpu, cpu):
+    rng = np.random.default_rng(3)
+    b10 = np.array([[0.1, 0.1, 0.1], [0.4, 0.2, 0.3], [0.6, 0.1, 0.1]], dtype=np.float32)
+    out = gpu.voxel_grid_weighted(b10, 0.5, (0.25, 0.25, 0.25))
+    assert out["count"].tolist() == [2, 1] and out["x"].tolist() == [0.25, 0.75]
+    for n in (1, 5, 2047, 2048, 2049, 70000):
+        xyz = rng.normal(scale=(20, 15, 4), size=(n, 3)).astype(np.float32)
+        if n > 5:
+            xyz[::97] = np.nan  # non-finite points are dropped
+        for align in (None, (0.25, -99.75, -1.0)):
+            assert_vox_equal(gpu.voxel_grid_weighted(xyz, 0.5, align), cpu.voxel_grid_weighted(xyz, 0.5, align))
+        pts = np.zeros(n, dtype=abi.XYZI_DTYPE)
+        pts["x"], pts["y"], pts["z"] = np.floor(xyz[:, 0]), np.floor(xyz[:, 1]), np.floor(xyz[:, 2])
+        pts["intensity"] = rng.uniform(-1, 0.5, size=n).astype(np.float32)
+        assert_vox_equal(gpu.voxel_grid_counted(pts, 1.0, -0.1), cpu.voxel_grid_counted(pts, 1.0, -0.1))  # incl. the input-slice quirk
+    assert len(gpu.voxel_grid_weighted(np.zeros((0, 3), np.float32), 0.5)) == 0
+
+
+# ---- A13: Euclidean clustering ------------------------------------------------------------------------
+def test_cluster_kat_b11(gpu):
+    lab, n = gpu.cluster(np.array([[0, 0, 0], [1.5, 0, 0]], np.float32), 1.5)
+    assert n == 2 and lab.tolist() == [0, 1]  # d^2 = 2.25 is NOT < 2.25
+    lab, n = gpu.cluster(np.array([[0, 0, 0], [1.5, 0, 0], [1.49, 0, 0]], np.float32), 1.5)
+    assert n == 1 and lab.tolist() == [0, 0, 0]
+
+
+def test_cluster_partitions(gpu, cpu):
+    rng = np.random.default_rng(9)
+    for m, tol in ((1, 1.5), (300, 1.5), (20000, 1.5), (50000, 2.0), (4000, 0.0)):
+        # lattice points (voxel centres): exact-distance ties at the radius are systematic
+        ijk = rng.integers([-60, -60, 0], [60, 60, 12], size=(m, 3))
+        ijk = np.unique(ijk, axis=0)
+        rng.shuffle(ijk)
+        xyz = ((ijk + 0.5) * 0.5).astype(np.float32)
+        lg, ng = gpu.cluster(xyz, tol)
+        lc, nc = cpu.cluster(xyz, tol)
+        assert ng == nc and np.array_equal(lg, lc)
+
+
+# ---- A3..A9: raycast ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("new_rule", [1, 0])
+def test_raycast_counts_lengths_scores(gpu, cpu, new_rule):
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.raycast_new_update_rule = new_rule
+    setup_pair(cpu, gpu, p, vs, sensor)
+    rng = np.random.default_rng(1)
+    for k in (0, 25, 40):
+        scan, pose, rp, _ = sensor.scan(0, k)
+        scan["range_mm"][::13] = 300          # shorter than a voxel: zero callbacks
+        scan["range_mm"][5::17] = 0           # no return: cast to max_dist
+        rg, tg = gpu.raycast_accumulate(scan, pose, p)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits())
+        rc, tc = cpu.raycast_accumulate(scan, pose, p)
+        assert rg == rc == 0 and tg == tc > 0
+        cg, lg = gpu.raycast_download()
+        assert np.array_equal(cg, cpu.ray_counts())                      # traversed-voxel set + hit counts: bit exact
+        fixed = cpu.ray_fixed().astype(np.float64) * 2.0 ** -gpu.raycast_frac_bits()
+        assert np.array_equal(lg, fixed.astype(np.float32))              # path length: exact fixed-point sum
+        seq = cpu.map_download(abi.MAP_RAYCAST)                          # the reference's sequential fp32 sum
+        nz = seq > 0
+        assert rel_err(lg[nz], seq[nz], floor=1e-3).max() < 2e-4
+        # flag a few cells so that the apply has something to skip
+        vox = gpu.filter_voxelize(scan, pose, p)
+        for o in (gpu, cpu):
+            o.update_points(vox, None, 0, 0.0, 2.0)
+        assert gpu.raycast_apply(1 + (k % 2), p) == cpu.raycast_apply(1 + (k % 2), p) == 0
+        sg, sc = gpu.map_download(), cpu.map_download()
+        assert np.array_equal(sg, sc)                                    # same inputs -> bit-exact scores
+        assert not gpu.map_download(abi.MAP_FLAGS).any() and not cpu.map_download(abi.MAP_FLAGS).any()
+
+
+def test_raycast_vs_sequential_fp32_reference(gpu, cpu):
+    """Against the reference's own accumulation order (sequential fp32 +=): scores within 1e-5 relative."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    setup_pair(cpu, gpu, p, vs, sensor)
+    cpu.set_modes(True, False, 24)
+    for k in range(4):
+        scan, pose, rp, _ = sensor.scan(0, 25 + k)
+        for o in (gpu, cpu):
+            o.raycast_accumulate(scan, pose, p)
+            o.raycast_apply(1, p)
+        assert rel_err(gpu.map_download(), cpu.map_download()).max() < SCORE_RTOL
+
+
+def test_raycast_edge_cases(gpu, cpu):
+    sensor = Sensor(64, 8)
+    p, vs = small_params()
+    setup_pair(cpu, gpu, p, vs, sensor)
+    scan, pose, rp, _ = sensor.scan(0, 30)
+    # wrong cloud size
+    from vofod_b200.capi import VofodError
+    with pytest.raises(VofodError) as e:
+        gpu.raycast_accumulate(scan[:-1], pose, p)
+    assert e.value.code == abi.VOFOD_E_DIMS
+    # sensor outside the map: raycast skipped (vofod_nodelet.cpp:1432)
+    far = abi.Pose.from_arrays(np.eye(3), (500.0, 0.0, 5.0))
+    assert gpu.raycast_accumulate(scan, far, p)[0] == cpu.raycast_accumulate(scan, far, p)[0] == abi.VOFOD_W_SENSOR_OOB
+    # nothing accumulated -> apply is skipped and says so (max_val == 0, :1544-1548)
+    assert gpu.raycast_apply(1, p) == cpu.raycast_apply(1, p) == abi.VOFOD_W_EMPTY_RAYCAST
+    # paused
+    p.raycast_pause = 1
+    assert gpu.raycast_accumulate(scan, pose, p)[0] == abi.VOFOD_W_PAUSED
+    p.raycast_pause = 0
+    # masked no-return pixels are skipped, unmasked ones are cast (:1449)
+    mask = np.ones(64 * 8, np.uint8)
+    mask[::3] = 0
+    scan["range_mm"][::2] = 0
+    for o in (gpu, cpu):
+        o.set_sensor(64, 8, sensor.dirs, None, mask)
+    cpu.set_modes(True, True, gpu.raycast_frac_bits())
+    (rg, tg), (rc, tc) = gpu.raycast_accumulate(scan, pose, p), cpu.raycast_accumulate(scan, pose, p)
+    assert (rg, tg) == (rc, tc)
+    assert np.array_equal(gpu.raycast_download()[0], cpu.ray_counts())
+    # apriori +inf cells survive the point update and turn NaN under the ray update exactly as in the reference (Q17)
+    inf_pts = np.array([[pose.t[0] + 3.0, pose.t[1], pose.t[2]]], np.float32)
+    for o in (gpu, cpu):
+        o.map_set_inf(inf_pts)
+        o.raycast_apply(1, p)
+    a, b = gpu.map_download(), cpu.map_download()
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))
+
+
+# ---- staged A10-A15 + A16-A19 + C6 on a real scan sequence, then the fused per-scan call ---------------
+def _run_sequence(gpu, cpu, sensor, p, vs, scene, scans, fixed, check_maps_every=1):
+    setup_pair(cpu, gpu, p, vs, sensor)
+    n_det = 0
+    for k in scans:
+        scan, pose, rp, _ = sensor.scan(scene, k)
+        s = abi.schedule_s1(rp)
+        rg, dg = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, fixed, gpu.raycast_frac_bits() or 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        a, b = rg.as_dict(), rc.as_dict()
+        assert a == b, (k, a, b)
+        vg, lg, ig = gpu.last_voxels()
+        vc, lc, ic = cpu.last_voxels()
+        assert_vox_equal(vg, vc)
+        assert np.array_equal(lg, lc) and np.array_equal(ig, ic)         # cluster partition + close/far split: bit exact
+        cg, cc = gpu.last_clusters(), cpu.last_clusters()
+        assert len(cg) == len(cc)
+        for f in ("label", "n_points", "cclass"):
+            assert np.array_equal(cg[f], cc[f]), (k, f)
+        struct_close(cg, cc, ("aabb_min", "aabb_max"), rtol=0, atol=0)
+        ok = cc["eig_gap"] > 1e-3                                         # OBB is ill-defined when eigenvalues tie
+        struct_close(cg[ok], cc[ok], ("obb_center", "obb_min", "obb_max"), rtol=1e-5, atol=1e-5)
+        assert len(dg) == len(dc)
+        n_det += len(dc)
+        for f in ("id", "label", "n_points"):
+            assert np.array_equal(dg[f], dc[f])
+        struct_close(dg, dc, ("position", "covariance", "confidence", "detection_probability"), rtol=1e-5, atol=1e-7)
+        if k % check_maps_every == 0:
+            sg, sc = gpu.map_download(), cpu.map_download()
+            if fixed:
+                assert np.array_equal(sg, sc, equal_nan=True), k
+            else:
+                assert rel_err(sg, sc).max() < SCORE_RTOL, k
+    return n_det
+
+
+def test_process_scan_small_city(gpu, cpu):
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 30), fixed=True)
+
+
+def test_process_scan_small_gazebo_detections(gpu, cpu):
+    """cfg3 shape: ground + buildings + 3 sphere UAVs; detections must fire and agree."""
+    sensor = Sensor(1024, 64)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.05
+    n_det = _run_sequence(gpu, cpu, sensor, p, vs, 1, range(0, 36), fixed=True)
+    assert n_det > 0
+
+
+def test_process_scan_small_vs_sequential_reference(gpu, cpu):
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    _run_sequence(gpu, cpu, sensor, p, vs, 1, range(0, 12), fixed=False)
+
+
+def test_process_scan_cfg2_full_size(gpu, cpu):
+    """BASELINE.json configs[1] at full size (128 x 2048 rays, 401 x 401 x 161 cells), a few scans."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    _run_sequence(gpu, cpu, sensor, p, vs, 0, (0, 1, 2, 21), fixed=True, check_maps_every=1)
+
+
+def test_full_size_properties(gpu):
+    """Size-independent properties at full size, no oracle: traversal count is independent of aggregation, the
+    accumulator returns to zero after apply, flags are cleared, repeated identical scans are deterministic."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    gpu.reset(p, vs)
+    gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+    scan, pose, rp, _ = sensor.scan(0, 30)
+    runs = []
+    for _ in range(2):
+        gpu.reset(p, vs)
+        rc, t = gpu.raycast_accumulate(scan, pose, p)
+        c, l = gpu.raycast_download()
+        assert rc == 0 and int(c.sum()) == t
+        assert gpu.raycast_apply(1, p) == 0
+        c2, _ = gpu.raycast_download()
+        assert not c2.any()
+        runs.append((t, c, l, gpu.map_download()))
+    assert runs[0][0] == runs[1][0]
+    for a, b in zip(runs[0][1:], runs[1][1:]):
+        assert np.array_equal(a, b)
+    # every touched free cell moved towards the ray score, never past it
+    m = runs[0][3]
+    assert m.min() >= -1000.0 and m.max() <= -740.0

@@ -1,0 +1,390 @@
+"""ctypes binding of libvofod_cuda.so (include/vofod_cuda.h) — the test / bench driver's view of the C ABI.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is usable, construction fails
+loudly.  Nothing in this module imports or calls the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (CLUSTER_DTYPE, DETECTION_DTYPE, PT_DTYPE, VOX_DTYPE, XYZI_DTYPE, Detection, MapInfo, Params, Pose,
+                  ScanResult, Schedule)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvofod_cuda.so")
+_lib = None
+
+
+class VofodError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvofod_cuda error {code}: {msg}")
+        self.code = code
+
+
+def load_library():
+    """Load libvofod_cuda.so (built in-tree by `make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VofodError(abi.VOFOD_E_STATE, f"{LIB_PATH} not built (run `make` or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    P = C.POINTER
+    sigs = {
+        "vofod_create": (i32, [i32, P(vp)]),
+        "vofod_destroy": (i32, [vp]),
+        "vofod_last_error": (C.c_char_p, [vp]),
+        "vofod_synchronize": (i32, [vp]),
+        "vofod_default_params": (None, [P(Params)]),
+        "vofod_reset": (i32, [vp, P(Params), f32]),
+        "vofod_map_resize": (i32, [vp, vp, vp, f32]),
+        "vofod_map_resize_idx": (i32, [vp, vp, vp, f32]),
+        "vofod_map_info_get": (i32, [vp, P(MapInfo)]),
+        "vofod_map_set_to": (i32, [vp, i32, f32]),
+        "vofod_map_set_inf": (i32, [vp, vp, sz]),
+        "vofod_map_download": (i32, [vp, i32, vp, sz]),
+        "vofod_map_upload": (i32, [vp, i32, vp, sz]),
+        "vofod_map_get": (i32, [vp, i32, i32, i32, i32, P(f32)]),
+        "vofod_map_set": (i32, [vp, i32, i32, i32, i32, f32]),
+        "vofod_map_count_over": (i32, [vp, f32, P(C.c_uint64)]),
+        "vofod_map_compact_over": (i32, [vp, f32, i32, i32, vp, sz, P(sz)]),
+        "vofod_map_has_close_to": (i32, [vp, vp, sz, f32, f32, vp]),
+        "vofod_map_explore_to_ground": (i32, [vp, vp, f32, f32, f32, P(i32), vp, sz, P(sz)]),
+        "vofod_map_is_floating": (i32, [vp, vp, sz, f32, vp]),
+        "vofod_map_submap_copy": (i32, [vp, vp, vp, i32, vp, sz, vp, vp]),
+        "vofod_map_trace_ray": (i32, [vp, vp, vp, f32, vp, vp, sz, P(sz)]),
+        "vofod_set_sensor": (i32, [vp, i32, i32, vp, vp, vp]),
+        "vofod_filter_voxelize": (i32, [vp, vp, sz, P(Pose), P(Params), vp, sz, P(sz)]),
+        "vofod_voxel_grid_weighted": (i32, [vp, vp, sz, f32, vp, vp, sz, P(sz)]),
+        "vofod_voxel_grid_counted": (i32, [vp, vp, sz, f32, f32, vp, vp, sz, P(sz)]),
+        "vofod_cluster": (i32, [vp, vp, sz, f32, vp, P(sz)]),
+        "vofod_close_far": (i32, [vp, vp, vp, sz, P(Params), vp, P(C.c_uint64)]),
+        "vofod_range_update": (i32, [vp, vp, P(Params)]),
+        "vofod_update_points": (i32, [vp, vp, vp, i32, sz, f32, f32]),
+        "vofod_raycast_accumulate": (i32, [vp, vp, sz, P(Pose), P(Params), P(C.c_uint64)]),
+        "vofod_raycast_download": (i32, [vp, vp, vp, sz]),
+        "vofod_raycast_apply": (i32, [vp, i32, P(Params)]),
+        "vofod_raycast_frac_bits": (i32, [vp]),
+        "vofod_classify_detect": (i32, [vp, vp, vp, vp, sz, P(Pose), P(Params), vp, sz, P(sz), vp, sz, P(sz)]),
+        "vofod_sepclusters": (i32, [vp, i32, P(Params), P(i32)]),
+        "vofod_state_get": (i32, [vp, P(i32), P(i32), P(C.c_uint32)]),
+        "vofod_state_set": (i32, [vp, i32, i32, C.c_uint32]),
+        "vofod_process_scan": (i32, [vp, vp, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
+        "vofod_upload_scan": (i32, [vp, i32, vp, sz]),
+        "vofod_process_scan_resident": (i32, [vp, i32, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
+        "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
+        "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
+        "vofod_set_slab": (i32, [vp, i32, i32, i32]),
+        "vofod_slab_boundary": (i32, [vp, vp, vp, sz, P(sz)]),
+        "vofod_stage_times": (i32, [vp, vp]),
+        "vofod_stage_name": (C.c_char_p, [i32]),
+        "vofod_kernel_launches": (C.c_uint64, [vp]),
+        "vofod_stream": (vp, [vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here = a symbol of include/vofod_cuda.h is missing
+        fn.restype = res
+        fn.argtypes = args
+    lib._vofod_sigs = sigs
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Vofod:
+    """One vofod_ctx = one CUDA device.  Method names follow the C ABI minus the `vofod_` prefix."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.vofod_create(int(device), C.byref(h))
+        if rc != 0:
+            raise VofodError(rc, self.lib.vofod_last_error(None).decode())
+        self.h = h
+        self.n_rays = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vofod_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise VofodError(rc, self.lib.vofod_last_error(self.h).decode())
+        return rc
+
+    # ---- lifetime / map -------------------------------------------------------------------------
+    def synchronize(self):
+        self._ck(self.lib.vofod_synchronize(self.h))
+
+    def reset(self, params, voxel_size):
+        self._ck(self.lib.vofod_reset(self.h, C.byref(params), float(voxel_size)))
+
+    def map_resize(self, center, dims, voxel_size):
+        c, d = _f32(center, 3), _f32(dims, 3)
+        self._ck(self.lib.vofod_map_resize(self.h, _p(c), _p(d), float(voxel_size)))
+
+    def map_resize_idx(self, offset, sizes, voxel_size):
+        o = _f32(offset, 3)
+        s = np.ascontiguousarray(sizes, dtype=np.int32).reshape(3)
+        self._ck(self.lib.vofod_map_resize_idx(self.h, _p(o), _p(s), float(voxel_size)))
+
+    def map_info(self):
+        mi = MapInfo()
+        self._ck(self.lib.vofod_map_info_get(self.h, C.byref(mi)))
+        return mi
+
+    def n_cells(self):
+        return int(self.map_info().n_cells)
+
+    def map_set_to(self, which, value):
+        self._ck(self.lib.vofod_map_set_to(self.h, which, float(value)))
+
+    def map_set_inf(self, xyz):
+        xyz = _f32(xyz).reshape(-1, 3)
+        self._ck(self.lib.vofod_map_set_inf(self.h, _p(xyz), len(xyz)))
+
+    def map_download(self, which=abi.MAP_SCORE):
+        n = self.n_cells()
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self.lib.vofod_map_download(self.h, which, _p(out), n))
+        return out
+
+    def map_upload(self, which, data):
+        data = _f32(data).reshape(-1)
+        self._ck(self.lib.vofod_map_upload(self.h, which, _p(data), data.size))
+
+    def map_get(self, which, ix, iy, iz):
+        v = C.c_float()
+        self._ck(self.lib.vofod_map_get(self.h, which, ix, iy, iz, C.byref(v)))
+        return v.value
+
+    def map_set(self, which, ix, iy, iz, value):
+        self._ck(self.lib.vofod_map_set(self.h, which, ix, iy, iz, float(value)))
+
+    def map_count_over(self, thr):
+        v = C.c_uint64()
+        self._ck(self.lib.vofod_map_count_over(self.h, float(thr), C.byref(v)))
+        return v.value
+
+    def map_compact_over(self, thr, greater_than=True, metric=False):
+        n = C.c_size_t()
+        rc = self.lib.vofod_map_compact_over(self.h, float(thr), int(greater_than), int(metric), None, 0, C.byref(n))
+        if rc not in (0, abi.VOFOD_E_CAPACITY):
+            self._ck(rc)
+        out = np.zeros(n.value, dtype=XYZI_DTYPE)
+        if n.value:
+            self._ck(self.lib.vofod_map_compact_over(self.h, float(thr), int(greater_than), int(metric), _p(out), n.value, C.byref(n)))
+        return out
+
+    def map_has_close_to(self, xyz, max_dist, thr):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), dtype=np.uint8)
+        self._ck(self.lib.vofod_map_has_close_to(self.h, _p(xyz), len(xyz), float(max_dist), float(thr), _p(out)))
+        return out
+
+    def map_explore_to_ground(self, pt, unknown_thr, ground_thr, max_voxel_dist, cap=1 << 16):
+        pt = _f32(pt, 3)
+        conn = C.c_int()
+        n = C.c_size_t()
+        idx = np.zeros((cap, 3), dtype=np.int32)
+        self._ck(self.lib.vofod_map_explore_to_ground(self.h, _p(pt), float(unknown_thr), float(ground_thr), float(max_voxel_dist),
+                                                      C.byref(conn), _p(idx), cap, C.byref(n)))
+        return bool(conn.value), idx[:n.value].copy()
+
+    def map_is_floating(self, xyz, thr):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), dtype=np.uint8)
+        self._ck(self.lib.vofod_map_is_floating(self.h, _p(xyz), len(xyz), float(thr), _p(out)))
+        return out
+
+    def map_submap_copy(self, min_pt, max_pt, inflate=0, cap=1 << 22):
+        mn, mx = _f32(min_pt, 3), _f32(max_pt, 3)
+        out = np.zeros(cap, dtype=np.float32)
+        sizes = np.zeros(3, dtype=np.int32)
+        off = np.zeros(3, dtype=np.float32)
+        self._ck(self.lib.vofod_map_submap_copy(self.h, _p(mn), _p(mx), int(inflate), _p(out), cap, _p(sizes), _p(off)))
+        return out[:int(np.prod(sizes))].copy(), sizes, off
+
+    def map_trace_ray(self, start, direction, length, cap=4096):
+        s, d = _f32(start, 3), _f32(direction, 3)
+        dd = np.zeros(cap, dtype=np.float32)
+        idx = np.zeros((cap, 3), dtype=np.int32)
+        n = C.c_size_t()
+        self._ck(self.lib.vofod_map_trace_ray(self.h, _p(s), _p(d), float(length), _p(dd), _p(idx), cap, C.byref(n)))
+        return dd[:n.value].copy(), idx[:n.value].copy()
+
+    # ---- sensor ---------------------------------------------------------------------------------
+    def set_sensor(self, W, H, dirs, offs=None, mask=None):
+        dirs = _f32(dirs).reshape(-1)
+        assert dirs.size == 3 * W * H
+        offs = None if offs is None else _f32(offs).reshape(-1)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        self._ck(self.lib.vofod_set_sensor(self.h, W, H, _p(dirs), _p(offs), _p(mask)))
+        self.n_rays = W * H
+
+    # ---- stages ---------------------------------------------------------------------------------
+    def filter_voxelize(self, scan, pose, params):
+        scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+        out = np.zeros(len(scan), dtype=VOX_DTYPE)
+        m = C.c_size_t()
+        self._ck(self.lib.vofod_filter_voxelize(self.h, _p(scan), len(scan), C.byref(pose), C.byref(params), _p(out), len(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def voxel_grid_weighted(self, xyz, leaf, align=None):
+        xyz = _f32(xyz).reshape(-1, 3)
+        al = None if align is None else _f32(align, 3)
+        out = np.zeros(max(len(xyz), 1), dtype=VOX_DTYPE)
+        m = C.c_size_t()
+        self._ck(self.lib.vofod_voxel_grid_weighted(self.h, _p(xyz), len(xyz), float(leaf), _p(al), _p(out), len(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def voxel_grid_counted(self, pts, leaf, thr, align=None):
+        pts = np.ascontiguousarray(pts, dtype=XYZI_DTYPE)
+        al = None if align is None else _f32(align, 3)
+        out = np.zeros(max(len(pts), 1), dtype=VOX_DTYPE)
+        m = C.c_size_t()
+        self._ck(self.lib.vofod_voxel_grid_counted(self.h, _p(pts), len(pts), float(leaf), float(thr), _p(al), _p(out), len(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def cluster(self, xyz, tol):
+        xyz = _f32(xyz).reshape(-1, 3)
+        labels = np.zeros(len(xyz), dtype=np.int32)
+        n = C.c_size_t()
+        self._ck(self.lib.vofod_cluster(self.h, _p(xyz), len(xyz), float(tol), _p(labels), C.byref(n)))
+        return labels, n.value
+
+    def close_far(self, vox, labels, params):
+        vox = np.ascontiguousarray(vox, dtype=VOX_DTYPE)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        out = np.zeros(len(vox), dtype=np.uint8)
+        nbg = C.c_uint64()
+        self._ck(self.lib.vofod_close_far(self.h, _p(vox), _p(labels), len(vox), C.byref(params), _p(out), C.byref(nbg)))
+        return out, nbg.value
+
+    def range_update(self, pt, params):
+        pt = _f32(pt, 3)
+        self._ck(self.lib.vofod_range_update(self.h, _p(pt), C.byref(params)))
+
+    def update_points(self, vox, sel, sel_value, score, flag):
+        vox = np.ascontiguousarray(vox, dtype=VOX_DTYPE)
+        sel = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint8)
+        self._ck(self.lib.vofod_update_points(self.h, _p(vox), _p(sel), int(sel_value), len(vox), float(score), float(flag)))
+
+    def raycast_accumulate(self, scan, pose, params):
+        scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+        n = C.c_uint64()
+        rc = self._ck(self.lib.vofod_raycast_accumulate(self.h, _p(scan), len(scan), C.byref(pose), C.byref(params), C.byref(n)))
+        return rc, n.value
+
+    def raycast_download(self, counts=True, lengths=True):
+        n = self.n_cells()
+        c = np.zeros(n, dtype=np.uint32) if counts else None
+        l = np.zeros(n, dtype=np.float32) if lengths else None
+        self._ck(self.lib.vofod_raycast_download(self.h, _p(c), _p(l), n))
+        return c, l
+
+    def raycast_frac_bits(self):
+        return int(self.lib.vofod_raycast_frac_bits(self.h))
+
+    def raycast_apply(self, its_diff, params):
+        return self._ck(self.lib.vofod_raycast_apply(self.h, int(its_diff), C.byref(params)))
+
+    def classify_detect(self, vox, labels, in_close, pose, params, det_cap=1024):
+        vox = np.ascontiguousarray(vox, dtype=VOX_DTYPE)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        in_close = np.ascontiguousarray(in_close, dtype=np.uint8)
+        dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        cls = np.zeros(max(len(vox), 1), dtype=CLUSTER_DTYPE)
+        nd, nf = C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.vofod_classify_detect(self.h, _p(vox), _p(labels), _p(in_close), len(vox), C.byref(pose), C.byref(params),
+                                                _p(dets), det_cap, C.byref(nd), _p(cls), len(cls), C.byref(nf)))
+        return dets[:nd.value].copy(), cls[:nf.value].copy()
+
+    def sepclusters(self, its_diff, params):
+        sure = C.c_int()
+        rc = self._ck(self.lib.vofod_sepclusters(self.h, int(its_diff), C.byref(params), C.byref(sure)))
+        return rc, bool(sure.value)
+
+    def state_get(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_uint32()
+        self._ck(self.lib.vofod_state_get(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return bool(a.value), bool(b.value), c.value
+
+    def state_set(self, bg, sure, det_id):
+        self._ck(self.lib.vofod_state_set(self.h, int(bg), int(sure), int(det_id)))
+
+    # ---- whole scan -----------------------------------------------------------------------------
+    def process_scan(self, scan, pose, params, sched, det_cap=256):
+        """`scan` is a HOST buffer (numpy, ideally pinned): the H2D copy is part of the call."""
+        dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        res = ScanResult()
+        self._ck(self.lib.vofod_process_scan(self.h, _p(scan), len(scan), C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets), det_cap))
+        return res, dets[:res.n_detections].copy()
+
+    def upload_scan(self, slot, scan):
+        scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+        self._ck(self.lib.vofod_upload_scan(self.h, int(slot), _p(scan), len(scan)))
+
+    def process_scan_resident(self, slot, pose, params, sched, det_cap=256, dets=None):
+        if dets is None:
+            dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        res = ScanResult()
+        self._ck(self.lib.vofod_process_scan_resident(self.h, int(slot), C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets), len(dets)))
+        return res, dets[:res.n_detections]
+
+    def last_voxels(self):
+        m = C.c_size_t()
+        rc = self.lib.vofod_last_voxels(self.h, None, None, None, 0, C.byref(m))
+        if rc not in (0, abi.VOFOD_E_CAPACITY):
+            self._ck(rc)
+        k = m.value
+        vox = np.zeros(k, dtype=VOX_DTYPE)
+        labels = np.zeros(k, dtype=np.int32)
+        close = np.zeros(k, dtype=np.uint8)
+        if k:
+            self._ck(self.lib.vofod_last_voxels(self.h, _p(vox), _p(labels), _p(close), k, C.byref(m)))
+        return vox, labels, close
+
+    def last_clusters(self):
+        n = C.c_size_t()
+        rc = self.lib.vofod_last_clusters(self.h, None, 0, C.byref(n))
+        if rc not in (0, abi.VOFOD_E_CAPACITY):
+            self._ck(rc)
+        out = np.zeros(n.value, dtype=CLUSTER_DTYPE)
+        if n.value:
+            self._ck(self.lib.vofod_last_clusters(self.h, _p(out), n.value, C.byref(n)))
+        return out
+
+    def set_slab(self, axis, lo, hi):
+        self._ck(self.lib.vofod_set_slab(self.h, axis, lo, hi))
+
+    def stage_times(self):
+        ms = np.zeros(abi.N_STAGES, dtype=np.float32)
+        self._ck(self.lib.vofod_stage_times(self.h, _p(ms)))
+        return {self.lib.vofod_stage_name(i).decode(): float(ms[i]) for i in range(abi.N_STAGES)}
+
+    def kernel_launches(self):
+        return int(self.lib.vofod_kernel_launches(self.h))
+
+    def stream(self):
+        return self.lib.vofod_stream(self.h)

@@ -1,0 +1,739 @@
+// classifyClusters + extractDetections (vofod_nodelet.cpp:819-879, 1648-1731) on the GPU.
+//
+//   1. far clusters are put into the reference's processing order (clusters sorted by size, largest first —
+//      pcl::EuclideanClusterExtraction; ties by smallest point index) with a radix sort of (size, label) keys,
+//      and their points into ascending index order with a stable radix sort by label
+//   2. K13: one thread per far cluster restates pcl::MomentOfInertiaEstimation (fp32 mean / covariance summed in
+//      point order, eigenvectors, AABB, OBB) and evaluates the min_points / max_distance / max_size gates
+//   3. K14/K15: ONE thread block walks the gated clusters in order, because VoxelMap::exploreToGround of one point
+//      reads cells that the previous point's exploration wrote (frontiers write-back, :1712-1715).  Each
+//      exploration is a block-parallel flood fill: the reference's DFS visits the same cell SET whatever the
+//      order, and only the set (and whether ground / the search horizon was reached) is observable.  The same
+//      block then emits the detections (submap uncertainty summed sequentially in double, as the reference does).
+#include <math.h>
+
+#include "common.cuh"
+#include "prims.cuh"
+
+#define CLS_CANDIDATE (-1)
+#define MAX_DETS 16384
+
+__global__ void __launch_bounds__(256) k_cls_keys(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const unsigned long long* __restrict__ d_m,
+                                                  const size_t m_cap, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, int* __restrict__ sizes)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int l = labels[i];
+    const bool far = in_close[l] == 0;
+    keys[i] = far ? (uint32_t)l : 0xFFFFFFFFu;
+    idx[i] = (uint32_t)i;
+    if (far)
+      atomicAdd(sizes + l, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cls_roots(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const int* __restrict__ sizes,
+                                                   const unsigned long long* __restrict__ d_m, const size_t m_cap, const int bits, unsigned long long* __restrict__ okeys,
+                                                   unsigned long long* __restrict__ d_nfar)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  const unsigned long long maxv = (1ull << bits) - 1ull;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+    if (labels[i] == (int)i && in_close[i] == 0)
+    {
+      const unsigned long long pos = atomicAdd(d_nfar, 1ull);
+      okeys[pos] = ((maxv - (unsigned long long)sizes[i]) << bits) | (unsigned long long)i;  // size descending, label ascending
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cls_segments(const uint32_t* __restrict__ skeys, const unsigned long long* __restrict__ d_m, const size_t m_cap,
+                                                      int* __restrict__ seg_start)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < m; s += (size_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t k = skeys[s];
+    if (k != 0xFFFFFFFFu && (s == 0 || skeys[s - 1] != k))
+      seg_start[k] = (int)s;
+  }
+}
+
+// cyclic Jacobi, fixed sweep order, fp64 — identical operation sequence to the oracle's restatement
+__device__ void jacobi3_dev(const double Ain[3][3], double eval[3], double V[3][3])
+{
+  double A[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      A[i][j] = Ain[i][j];
+      V[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 16; sweep++)
+  {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off == 0.0)
+      break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++)
+      {
+        if (A[p][q] == 0.0)
+          continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0);
+        const double s = t * c;
+        const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+        A[p][p] = app - t * apq;
+        A[q][q] = aqq + t * apq;
+        A[p][q] = A[q][p] = 0.0;
+        const int r = 3 - p - q;
+        const double arp = A[r][p], arq = A[r][q];
+        A[r][p] = A[p][r] = c * arp - s * arq;
+        A[r][q] = A[q][r] = s * arp + c * arq;
+        for (int k = 0; k < 3; k++)
+        {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  eval[0] = A[0][0];
+  eval[1] = A[1][1];
+  eval[2] = A[2][2];
+}
+
+struct ClsArgs
+{
+  Geom g;
+  float sensor[3];
+  int min_points;
+  double max_distance, max_size, max_explore_distance;
+  float thr_frontiers, thr_new;
+  double score_ray;
+  double position_sigma;
+  double vfov;
+  int W, H;
+  int bits;
+  int side;        // stamp cube side = 2*Rmax+1
+  int rmax;
+  int terms_cap;
+};
+
+// K13 — pcl::MomentOfInertiaEstimation restated (vofod_nodelet.cpp:1655-1672) + the gates (:1679-1690)
+__global__ void __launch_bounds__(64) k_cluster_moi(const ClsArgs a, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
+                                                    const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
+                                                    vofod_cluster_info* __restrict__ out)
+{
+  const unsigned long long n_far = *d_nfar;
+  const unsigned long long lmask = (1ull << a.bits) - 1ull;
+  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_far; c += (unsigned long long)gridDim.x * blockDim.x)
+  {
+    const int label = (int)(okeys[c] & lmask);
+    const int n = sizes[label];
+    const uint32_t* idcs = sidx + seg_start[label];
+    vofod_cluster_info ci;
+    ci.label = label;
+    ci.n_points = n;
+    ci.cclass = VOFOD_CLASS_INVALID;
+    ci.obb_size = __int_as_float(0x7fc00000);
+    float mean[3] = {0.f, 0.f, 0.f};
+    float amin[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float amax[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int k = 0; k < n; k++)  // computeMeanValue
+    {
+      const vofod_vox v = vox[idcs[k]];
+      const float p[3] = {v.x, v.y, v.z};
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+      {
+        mean[q] += p[q];
+        if (p[q] <= amin[q]) amin[q] = p[q];
+        if (p[q] >= amax[q]) amax[q] = p[q];
+      }
+    }
+    const unsigned np = n == 0 ? 1u : (unsigned)n;
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      mean[q] /= (float)np;
+    float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < n; k++)  // computeCovarianceMatrix
+    {
+      const vofod_vox v = vox[idcs[k]];
+      const float d[3] = {v.x - mean[0], v.y - mean[1], v.z - mean[2]};
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          cov[r][q] += d[r] * d[q];
+    }
+    const float factor = 1.0f / (float)((n - 1 > 0) ? (n - 1) : 1);
+    double A[3][3];
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++)
+      {
+        cov[r][q] *= factor;
+        A[r][q] = (double)cov[r][q];
+      }
+    double evald[3], Vd[3][3];
+    jacobi3_dev(A, evald, Vd);
+    const float ev[3] = {(float)evald[0], (float)evald[1], (float)evald[2]};
+    unsigned major = 0, middle = 1, minor = 2, t;
+    if (ev[major] < ev[middle]) { t = major; major = middle; middle = t; }
+    if (ev[major] < ev[minor]) { t = major; major = minor; minor = t; }
+    if (ev[middle] < ev[minor]) { t = minor; minor = middle; middle = t; }
+    float ax[3][3];
+    const unsigned order[3] = {major, middle, minor};
+    for (int k = 0; k < 3; k++)
+    {
+      const float v[3] = {(float)Vd[0][order[k]], (float)Vd[1][order[k]], (float)Vd[2][order[k]]};
+      const float nrm = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      for (int q = 0; q < 3; q++)
+        ax[k][q] = v[q] / nrm;
+    }
+    const float cx = ax[1][1] * ax[2][2] - ax[1][2] * ax[2][1];
+    const float cy = ax[1][2] * ax[2][0] - ax[1][0] * ax[2][2];
+    const float cz = ax[1][0] * ax[2][1] - ax[1][1] * ax[2][0];
+    const float det = ax[0][0] * cx + ax[0][1] * cy + ax[0][2] * cz;
+    if (det <= 0.0f)
+      for (int q = 0; q < 3; q++)
+        ax[0][q] = -ax[0][q];
+    float omin[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float omax[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int k = 0; k < n; k++)  // computeOBB
+    {
+      const vofod_vox v = vox[idcs[k]];
+      const float d[3] = {v.x - mean[0], v.y - mean[1], v.z - mean[2]};
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+      {
+        const float pr = d[0] * ax[q][0] + d[1] * ax[q][1] + d[2] * ax[q][2];
+        if (pr <= omin[q]) omin[q] = pr;
+        if (pr >= omax[q]) omax[q] = pr;
+      }
+    }
+    float shift[3];
+    for (int q = 0; q < 3; q++)
+    {
+      shift[q] = (omax[q] + omin[q]) / 2.0f;
+      omin[q] -= shift[q];
+      omax[q] -= shift[q];
+    }
+    for (int q = 0; q < 3; q++)
+    {
+      ci.aabb_min[q] = amin[q];
+      ci.aabb_max[q] = amax[q];
+      ci.obb_min[q] = omin[q];
+      ci.obb_max[q] = omax[q];
+      ci.obb_center[q] = mean[q] + (ax[0][q] * shift[0] + (ax[1][q] * shift[1] + ax[2][q] * shift[2]));
+      for (int k = 0; k < 3; k++)
+        ci.obb_rot[q * 3 + k] = ax[k][q];
+    }
+    {
+      double s0 = evald[0], s1 = evald[1], s2 = evald[2], tt;
+      if (s0 > s1) { tt = s0; s0 = s1; s1 = tt; }
+      if (s1 > s2) { tt = s1; s1 = s2; s2 = tt; }
+      if (s0 > s1) { tt = s0; s0 = s1; s1 = tt; }
+      const double scale = fmax(fabs(s2), 1e-30);
+      ci.eig_gap = (float)(fmin(s1 - s0, s2 - s1) / scale);
+    }
+    // gates (:1679-1690)
+    if (n >= a.min_points)
+    {
+      const float ddx = a.sensor[0] - ci.obb_center[0], ddy = a.sensor[1] - ci.obb_center[1], ddz = a.sensor[2] - ci.obb_center[2];
+      const double dist = (double)sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+      if (!(dist > a.max_distance))
+      {
+        const float ex = omax[0] - omin[0], ey = omax[1] - omin[1], ez = omax[2] - omin[2];
+        ci.obb_size = sqrtf(ex * ex + ey * ey + ez * ez);
+        if (!((double)ci.obb_size > a.max_size))
+          ci.cclass = CLS_CANDIDATE;
+      }
+    }
+    out[c] = ci;
+  }
+}
+
+// K14 — VoxelMap::exploreToGround (voxel_map.cpp:402-488) as a block-parallel flood fill.  All threads of the block
+// call it with identical arguments.  Returns `connected`; when not connected, explored[0..*n_explored) holds the
+// cube-relative ids of the visited "unknown" cells (decode with explore_decode).  Shared scratch: sh[0..1] queue
+// sizes, sh[2] explored count, sh[3] connected flag.
+struct ExploreWs
+{
+  unsigned* stamps;
+  int *q0, *q1, *explored;
+  int side, rm;
+};
+__device__ __forceinline__ void explore_decode(const ExploreWs& w, const int rel, int& dx, int& dy, int& dz)
+{
+  const int side2 = w.side * w.side;
+  dz = rel / side2 - w.rm;
+  dy = (rel / w.side) % w.side - w.rm;
+  dx = rel % w.side - w.rm;
+}
+__device__ bool explore_to_ground_block(const float* score, const Geom& g, const int ox, const int oy, const int oz, const float unknown_thr, const float ground_thr,
+                                        const float maxd, const unsigned epoch, const ExploreWs& w, int* sh)
+{
+  const int tid = threadIdx.x;
+  const int side = w.side, side2 = w.side * w.side, rm = w.rm;
+  // voxel_map.cpp:408-416: border cells count as connected
+  if (ox <= 0 || oy <= 0 || oz <= 0 || ox >= g.size[0] - 1 || oy >= g.size[1] - 1 || oz >= g.size[2] - 1)
+  {
+    __syncthreads();
+    if (tid == 0)
+      sh[2] = 0;
+    __syncthreads();
+    return true;
+  }
+  int* q[2] = {w.q0, w.q1};
+  __syncthreads();
+  if (tid == 0)
+  {
+    sh[0] = 1;
+    sh[1] = 0;
+    sh[2] = 0;
+    sh[3] = 0;
+    const int rel0 = rm + rm * side + rm * side2;
+    w.q0[0] = rel0;
+    w.stamps[rel0] = epoch;
+  }
+  __syncthreads();
+  int cur = 0;
+  while (true)
+  {
+    const int qn = sh[cur];
+    if (qn == 0 || sh[3])
+      break;
+    for (int t = tid; t < qn; t += blockDim.x)
+    {
+      const int rel = q[cur][t];
+      int dx, dy, dz;
+      explore_decode(w, rel, dx, dy, dz);
+      const int x = ox + dx, y = oy + dy, z = oz + dz;
+      const long long ci = cell_index(g, x, y, z);
+      const float val = ci >= 0 ? score[ci] : 0.0f;
+      if (val > ground_thr)  // :423 -> connected
+        sh[3] = 1;
+      else if (val > unknown_thr)  // :427
+      {
+        w.explored[atomicAdd(&sh[2], 1)] = rel;
+        const int man = abs(dx) + abs(dy) + abs(dz);
+        if ((float)man == maxd - 1.0f)  // :433
+          sh[3] = 1;
+        else
+        {
+          const int nb[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+#pragma unroll
+          for (int e = 0; e < 6; e++)
+          {
+            const int nx = x + nb[e][0], ny = y + nb[e][1], nz = z + nb[e][2];
+            // :438-478: stay inside the grid and inside the Manhattan horizon
+            if (nx < 0 || ny < 0 || nz < 0 || nx > g.size[0] - 1 || ny > g.size[1] - 1 || nz > g.size[2] - 1)
+              continue;
+            const int ddx = dx + nb[e][0], ddy = dy + nb[e][1], ddz = dz + nb[e][2];
+            const int man2 = abs(ddx) + abs(ddy) + abs(ddz);
+            if (!((float)man2 <= maxd) || man2 > rm)
+              continue;
+            const int rel2 = (ddx + rm) + (ddy + rm) * side + (ddz + rm) * side2;
+            if (atomicExch(w.stamps + rel2, epoch) != epoch)
+              q[cur ^ 1][atomicAdd(&sh[cur ^ 1], 1)] = rel2;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0)
+      sh[cur] = 0;
+    cur ^= 1;
+    __syncthreads();
+  }
+  const bool connected = sh[3] != 0;
+  __syncthreads();
+  return connected;
+}
+
+// staged entry point (vofod_map_explore_to_ground): one exploration, NO write-back (the caller of the reference's
+// VoxelMap::exploreToGround decides what to do with the cells)
+__global__ void __launch_bounds__(256) k_explore_single(const float* score, const Geom g, const float x, const float y, const float z, const float unknown_thr,
+                                                        const float ground_thr, const float maxd, const ExploreWs w, int* __restrict__ out_idx3, const size_t cap,
+                                                        unsigned long long* __restrict__ counters)
+{
+  __shared__ int sh[4];
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0)
+  {
+    unsigned e = (unsigned)counters[CNT_EXPLORE_EPOCH] + 1u;
+    if (e == 0u)
+      e = 1u;
+    s_epoch = e;
+    counters[CNT_EXPLORE_EPOCH] = e;
+  }
+  __syncthreads();
+  const int ox = coord_to_idx1(x, g.off[0], g.inv), oy = coord_to_idx1(y, g.off[1], g.inv), oz = coord_to_idx1(z, g.off[2], g.inv);
+  const bool connected = explore_to_ground_block(score, g, ox, oy, oz, unknown_thr, ground_thr, maxd, s_epoch, w, sh);
+  const int ne = connected ? 0 : sh[2];
+  for (int t = threadIdx.x; t < ne && (size_t)t < cap; t += blockDim.x)
+  {
+    int dx, dy, dz;
+    explore_decode(w, w.explored[t], dx, dy, dz);
+    out_idx3[3 * t] = ox + dx;
+    out_idx3[3 * t + 1] = oy + dy;
+    out_idx3[3 * t + 2] = oz + dz;
+  }
+  if (threadIdx.x == 0)
+  {
+    counters[CNT_EXPLORE_N] = (unsigned long long)ne;
+    counters[CNT_SCRATCH0] = connected ? 1ull : 0ull;
+  }
+}
+
+// K14 + K15 — one block, sequential over clusters (see file header)
+__global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, float* score, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx,
+                                                      const int* __restrict__ seg_start, vofod_cluster_info* __restrict__ infos, const ExploreWs w,
+                                                      double* __restrict__ terms, vofod_detection* __restrict__ dets, unsigned long long* __restrict__ counters,
+                                                      const unsigned long long* __restrict__ d_nfar)
+{
+  __shared__ int sh[4];
+  __shared__ unsigned s_epoch;
+  __shared__ unsigned long long s_det_id, s_ndet;
+  const int tid = threadIdx.x;
+  const unsigned long long n_far = *d_nfar;
+  const bool active = counters[CNT_STATE_BG] != 0ull && counters[CNT_STATE_SURE] != 0ull;  // :1695
+  if (tid == 0)
+  {
+    s_epoch = (unsigned)counters[CNT_EXPLORE_EPOCH];
+    s_det_id = counters[CNT_DET_ID];
+    s_ndet = 0ull;
+  }
+  __syncthreads();
+  const Geom& g = a.g;
+  for (unsigned long long c = 0; c < n_far; c++)
+  {
+    if (infos[c].cclass != CLS_CANDIDATE)
+      continue;  // uniform: every thread reads the same global word
+    bool is_floating = true;
+    if (active)
+    {
+      const int label = infos[c].label, n = infos[c].n_points;
+      const uint32_t* idcs = sidx + seg_start[label];
+      const int R = (int)(((double)infos[c].obb_size + a.max_explore_distance) / (double)g.vs);  // :1698
+      for (int k = 0; k < n && is_floating; k++)
+      {
+        const vofod_vox v = vox[idcs[k]];
+        const int ox = coord_to_idx1(v.x, g.off[0], g.inv), oy = coord_to_idx1(v.y, g.off[1], g.inv), oz = coord_to_idx1(v.z, g.off[2], g.inv);
+        __syncthreads();
+        if (tid == 0)
+        {
+          s_epoch++;
+          if (s_epoch == 0u)
+            s_epoch = 1u;
+        }
+        __syncthreads();
+        const bool connected = explore_to_ground_block(score, g, ox, oy, oz, a.thr_frontiers, a.thr_new, (float)R, s_epoch, w, sh);
+        if (connected)
+          is_floating = false;
+        else
+        {
+          // :1712-1715 — mark the explored unknown cells as frontiers
+          const int ne = sh[2];
+          for (int t = tid; t < ne; t += blockDim.x)
+          {
+            int dx, dy, dz;
+            explore_decode(w, w.explored[t], dx, dy, dz);
+            const long long ci = cell_index(g, ox + dx, oy + dy, oz + dz);
+            if (ci >= 0)
+              score[ci] = a.thr_frontiers;
+          }
+        }
+        __syncthreads();
+      }
+    } else
+      is_floating = false;
+    __syncthreads();
+    if (tid == 0)
+      infos[c].cclass = is_floating ? VOFOD_CLASS_MAV : VOFOD_CLASS_UNKNOWN;
+    __syncthreads();
+  }
+
+  // ---- extractDetections (:834-879) ----
+  for (unsigned long long c = 0; c < n_far; c++)
+  {
+    if (infos[c].cclass != VOFOD_CLASS_MAV)
+      continue;
+    const vofod_cluster_info ci = infos[c];
+    const uint32_t* idcs = sidx + seg_start[ci.label];
+    // getSubmapCopy(aabb, inflate 2) (voxel_map.cpp:547-584)
+    int lo[3], ssz[3];
+    float sub_off[3];
+#pragma unroll
+    for (int q2 = 0; q2 < 3; q2++)
+    {
+      int mn = coord_to_idx1(ci.aabb_min[q2], g.off[q2], g.inv) - 2, mx = coord_to_idx1(ci.aabb_max[q2], g.off[q2], g.inv) + 2;
+      mn = mn < 0 ? 0 : (mn > g.size[q2] - 1 ? g.size[q2] - 1 : mn);
+      mx = mx < 0 ? 0 : (mx > g.size[q2] - 1 ? g.size[q2] - 1 : mx);
+      lo[q2] = mn;
+      ssz[q2] = mx - mn + 1;
+      sub_off[q2] = idx_to_coord1(mn, g.off[q2], g.vs) - g.vs / 2.0f;
+    }
+    const long long ncell = (long long)ssz[0] * ssz[1] * ssz[2];
+    const bool fits = ncell <= (long long)a.terms_cap;
+    if (fits)
+    {
+      for (int t = tid; t < (int)ncell; t += blockDim.x)
+      {
+        const int x = t % ssz[0], y = (t / ssz[0]) % ssz[1], z = t / (ssz[0] * ssz[1]);
+        const long long cell = cell_index(g, x + lo[0], y + lo[1], z + lo[2]);
+        const float val = cell >= 0 ? score[cell] : 0.0f;
+        terms[t] = 1.0 - (double)val / a.score_ray;  // :862
+      }
+      __syncthreads();
+      const float ray_f = (float)a.score_ray;
+      const double self_term = 1.0 - (double)ray_f / a.score_ray;
+      for (int k = tid; k < ci.n_points; k += blockDim.x)  // :855-859 cluster voxels count as certain
+      {
+        const vofod_vox v = vox[idcs[k]];
+        const int x = coord_to_idx1(v.x, sub_off[0], g.inv), y = coord_to_idx1(v.y, sub_off[1], g.inv), z = coord_to_idx1(v.z, sub_off[2], g.inv);
+        if (x >= 0 && y >= 0 && z >= 0 && x < ssz[0] && y < ssz[1] && z < ssz[2])
+          terms[x + y * ssz[0] + z * ssz[0] * ssz[1]] = self_term;
+      }
+      __syncthreads();
+    }
+    if (tid == 0)
+    {
+      const float ddx = a.sensor[0] - ci.obb_center[0], ddy = a.sensor[1] - ci.obb_center[1], ddz = a.sensor[2] - ci.obb_center[2];
+      const double det_dist = (double)sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+      vofod_detection d;
+      memset(&d, 0, sizeof(d));
+      d.id = (int32_t)(uint32_t)s_det_id++;
+      d.label = ci.label;
+      d.n_points = (uint64_t)ci.n_points;
+      for (int q2 = 0; q2 < 3; q2++)
+      {
+        d.aabb_min[q2] = ci.aabb_min[q2];
+        d.aabb_max[q2] = ci.aabb_max[q2];
+        d.obb_min[q2] = ci.obb_min[q2];
+        d.obb_max[q2] = ci.obb_max[q2];
+        d.position[q2] = ci.obb_center[q2];
+      }
+      for (int q2 = 0; q2 < 9; q2++)
+        d.obb_rot[q2] = ci.obb_rot[q2];
+      const float cv = (float)(sqrt(det_dist) * a.position_sigma);
+      d.covariance[0] = d.covariance[4] = d.covariance[8] = cv;
+      double u = 0.0;
+      if (fits)
+        for (long long t = 0; t < ncell; t++)
+          u += terms[t];
+      else
+        u = __longlong_as_double(0x7ff8000000000000ll);
+      u /= (double)ci.n_points;
+      d.confidence = (double)(float)(1.0 / exp(u));
+      const double vray_res = a.vfov / (double)a.H;
+      const double hray_res = 2 * 3.14159265358979323846 / (double)a.W;
+      const double pv = fmin(atan(1.0 / det_dist) / (vray_res * a.min_points), 1.0);
+      const double ph = fmin(atan(1.0 / det_dist) / hray_res, 1.0);
+      d.detection_probability = pv * ph;
+      if (s_ndet < MAX_DETS)
+        dets[s_ndet] = d;
+      s_ndet++;
+    }
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    counters[CNT_EXPLORE_EPOCH] = s_epoch;
+    counters[CNT_DET_ID] = s_det_id;
+    counters[CNT_NDET] = s_ndet;
+  }
+}
+
+static int bits_for_u(unsigned long long v)
+{
+  int b = 0;
+  while (v)
+  {
+    b++;
+    v >>= 1;
+  }
+  return b < 1 ? 1 : b;
+}
+
+int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
+                           const vofod_pose& tf, const vofod_params& p)
+{
+  using namespace prims;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  CK(cudaMemsetAsync(cnt + CNT_NDET, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(cnt + CNT_NFARPTS, 0, 8, ctx->stream));
+  if (m_cap == 0)
+    return 0;
+  const size_t np = padded(m_cap);
+  const int bits = bits_for_u(m_cap);  // 2^bits > m_cap: labels and sizes both fit, the 0xFFFFFFFF sentinel sorts last
+  // geometry-derived workspace bounds
+  const double vs = (double)ctx->g.vs;
+  const double rmax_d = (p.cls_max_size + p.cls_max_explore_distance) / vs;
+  if (!(rmax_d >= 0.0) || rmax_d > 200.0)
+    return vf_fail(ctx, VOFOD_E_INVALID, "classification max_size + max_explore_distance spans %.0f voxels (limit 200)", rmax_d);
+  const int rmax = (int)rmax_d + 1;
+  const int side = 2 * rmax + 1;
+  const size_t cube = (size_t)side * side * side;
+  const int sub_side = (int)ceil(p.cls_max_size / vs) + 8;
+  const size_t terms_cap = (size_t)sub_side * sub_side * sub_side;
+
+  ENSURE(ctx->far_keys_a, np * 4);
+  ENSURE(ctx->far_keys_b, np * 4);
+  ENSURE(ctx->far_list, np * 4);
+  ENSURE(ctx->scratch_c, np * 4);
+  ENSURE(ctx->cls_sizes, m_cap * 4);
+  ENSURE(ctx->cls_seg, m_cap * 4);
+  ENSURE(ctx->cls_okeys_a, np * 8);
+  ENSURE(ctx->cls_okeys_b, np * 8);
+  ENSURE(ctx->cl_info, m_cap * sizeof(vofod_cluster_info));
+  ENSURE(ctx->dets, (size_t)MAX_DETS * sizeof(vofod_detection));
+  ENSURE(ctx->explore_ws, cube * 4);          // stamps: zero-filled when (re)allocated
+  ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
+  ENSURE(ctx->cls_terms, terms_cap * 8);
+  CK(cudaMemsetAsync(ctx->cls_sizes.p, 0, m_cap * 4, ctx->stream));
+
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  LAUNCH(k_cls_keys, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->far_keys_a.as<uint32_t>(), ctx->far_list.as<uint32_t>(), ctx->cls_sizes.as<int>());
+  LAUNCH(k_cls_roots, nb, 256, 0, d_labels, d_in_close, ctx->cls_sizes.as<int>(), d_m, m_cap, bits, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS);
+  uint32_t *skeys = nullptr, *sidx = nullptr;
+  RET((radix_sort<uint32_t, true>(ctx, ctx->far_keys_a.as<uint32_t>(), ctx->far_keys_b.as<uint32_t>(), ctx->far_list.as<uint32_t>(), ctx->scratch_c.as<uint32_t>(), d_m, m_cap,
+                                  0, bits, &skeys, &sidx)));
+  LAUNCH(k_cls_segments, nb, 256, 0, skeys, d_m, m_cap, ctx->cls_seg.as<int>());
+  unsigned long long* okeys = nullptr;
+  RET((radix_sort<unsigned long long, false>(ctx, ctx->cls_okeys_a.as<unsigned long long>(), ctx->cls_okeys_b.as<unsigned long long>(), nullptr, nullptr, cnt + CNT_NFARPTS,
+                                             m_cap, 0, 2 * bits, &okeys, nullptr)));
+  ClsArgs a;
+  a.g = ctx->g;
+  for (int k = 0; k < 3; k++)
+    a.sensor[k] = tf.t[k];
+  a.min_points = p.cls_min_points;
+  a.max_distance = p.cls_max_distance;
+  a.max_size = p.cls_max_size;
+  a.max_explore_distance = p.cls_max_explore_distance;
+  a.thr_frontiers = (float)p.thr_frontiers;
+  a.thr_new = (float)p.thr_new_obstacles;
+  a.score_ray = p.score_ray;
+  a.position_sigma = p.output_position_sigma;
+  a.vfov = (double)p.sensor_vfov;
+  a.W = ctx->W ? ctx->W : 1;
+  a.H = ctx->H ? ctx->H : 1;
+  a.bits = bits;
+  a.side = side;
+  a.rmax = rmax;
+  a.terms_cap = (int)terms_cap;
+  LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap, 64, 16), 64, 0, a, d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
+         ctx->cl_info.as<vofod_cluster_info>());
+  int* qbase = ctx->cls_queues.as<int>();
+  ExploreWs w;
+  w.stamps = ctx->explore_ws.as<unsigned>();
+  w.q0 = qbase;
+  w.q1 = qbase + cube;
+  w.explored = qbase + 2 * cube;
+  w.side = side;
+  w.rm = rmax;
+  LAUNCH(k_classify_seq, 1, 256, 0, a, ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w, ctx->cls_terms.as<double>(),
+         ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS);
+  return 0;
+}
+
+extern "C" int vofod_map_explore_to_ground(vofod_ctx* ctx, const float pt[3], float unknown_threshold, float ground_threshold, float max_voxel_dist, int* connected,
+                                           int32_t* explored_idx3, size_t cap, size_t* n_explored)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->map_ready)
+    return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  if (!pt || !connected || !n_explored || (cap && !explored_idx3))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  if (!(max_voxel_dist >= 0.0f) || max_voxel_dist > 200.0f)
+    return vf_fail(ctx, VOFOD_E_INVALID, "max_voxel_dist %.1f out of range [0,200]", max_voxel_dist);
+  const int rmax = (int)ceilf(max_voxel_dist) + 1;
+  const int side = 2 * rmax + 1;
+  const size_t cube = (size_t)side * side * side;
+  ENSURE(ctx->explore_ws, cube * 4);
+  ENSURE(ctx->cls_queues, cube * 4 * 3);
+  ENSURE(ctx->scratch_b, cap * 12 + 16);
+  int* qbase = ctx->cls_queues.as<int>();
+  ExploreWs w;
+  w.stamps = ctx->explore_ws.as<unsigned>();
+  w.q0 = qbase;
+  w.q1 = qbase + cube;
+  w.explored = qbase + 2 * cube;
+  w.side = side;
+  w.rm = rmax;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  LAUNCH(k_explore_single, 1, 256, 0, ctx->score.as<float>(), ctx->g, pt[0], pt[1], pt[2], unknown_threshold, ground_threshold, max_voxel_dist, w, ctx->scratch_b.as<int>(), cap,
+         cnt);
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(&h[0], cnt + CNT_EXPLORE_N, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&h[1], cnt + CNT_SCRATCH0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *connected = h[1] != 0;
+  *n_explored = (size_t)h[0];
+  const size_t k = h[0] < cap ? (size_t)h[0] : cap;
+  if (k)
+  {
+    CK(cudaMemcpyAsync(explored_idx3, ctx->scratch_b.p, k * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return h[0] > cap ? vf_fail(ctx, VOFOD_E_CAPACITY, "explore_to_ground: need capacity %llu", h[0]) : VOFOD_OK;
+}
+
+extern "C" int vofod_classify_detect(vofod_ctx* ctx, const vofod_vox* pts, const int32_t* labels, const uint8_t* point_in_close_cluster, size_t m, const vofod_pose* tf,
+                                     const vofod_params* p, vofod_detection* dets, size_t det_cap, size_t* n_dets, vofod_cluster_info* clusters, size_t cl_cap,
+                                     size_t* n_far_clusters)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->map_ready)
+    return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  if (!tf || !p || !n_dets || !n_far_clusters || (m && (!pts || !labels || !point_in_close_cluster)))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  *n_dets = 0;
+  *n_far_clusters = 0;
+  if (m == 0)
+    return VOFOD_OK;
+  for (size_t i = 0; i < m; i++)
+    if (labels[i] < 0 || (size_t)labels[i] >= m)
+      return vf_fail(ctx, VOFOD_E_INVALID, "labels[%zu] = %d is not a point index", i, labels[i]);
+  ENSURE(ctx->vox, prims::padded(m) * sizeof(vofod_vox));
+  ENSURE(ctx->labels, m * 4);
+  ENSURE(ctx->pt_close, m + 64);
+  CK(cudaMemcpyAsync(ctx->vox.p, pts, m * sizeof(vofod_vox), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->labels.p, labels, m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pt_close.p, point_in_close_cluster, m, cudaMemcpyHostToDevice, ctx->stream));
+  RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), nullptr, m, *tf, *p));
+  unsigned long long h[CNT_N_SLOTS];
+  CK(cudaMemcpyAsync(h, ctx->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h[CNT_WATCHDOG])
+    return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", h[CNT_WATCHDOG]);
+  ctx->last_detection_id = (uint32_t)h[CNT_DET_ID];
+  ctx->last_m = m;
+  ctx->last_far = (size_t)h[CNT_NFARPTS];
+  *n_dets = (size_t)h[CNT_NDET];
+  *n_far_clusters = ctx->last_far;
+  if (clusters)
+  {
+    const size_t k = ctx->last_far < cl_cap ? ctx->last_far : cl_cap;
+    if (k)
+      CK(cudaMemcpyAsync(clusters, ctx->cl_info.p, k * sizeof(vofod_cluster_info), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (dets)
+  {
+    size_t k = *n_dets < det_cap ? *n_dets : det_cap;
+    if (k > MAX_DETS)
+      k = MAX_DETS;
+    if (k)
+      CK(cudaMemcpyAsync(dets, ctx->dets.p, k * sizeof(vofod_detection), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if ((dets && *n_dets > det_cap) || (clusters && ctx->last_far > cl_cap))
+    return vf_fail(ctx, VOFOD_E_CAPACITY, "classify_detect: %zu detections / %zu far clusters exceed the given capacities", *n_dets, ctx->last_far);
+  return VOFOD_OK;
+}

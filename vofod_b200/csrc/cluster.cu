@@ -1,0 +1,238 @@
+// clusterCloud (vofod_nodelet.cpp:689-698) = pcl::EuclideanClusterExtraction on the GPU.
+//
+// The reference builds a kd-tree and grows clusters by BFS; the result is the set of connected components of
+// the graph "a ~ b  iff  fp32 ((ax-bx)^2 + (ay-by)^2) + (az-bz)^2 < float(tol^2)" (strict).  Here:
+//   K4  spatial hash: cell pitch slightly above tol, open-addressing table keyed by the packed cell, one
+//       linked list of point indices per occupied cell
+//   K5  one thread per point scans the 27 neighbouring cells and unites itself with every lower-indexed point
+//       inside the radius (lock-free union-find, the larger root is always linked under the smaller one, so the
+//       root of a finished tree IS the minimum point index of the component = the canonical label)
+//   K5b flatten: labels[i] = root(i), per-root sizes, number of roots
+// Linked-list order is scheduling dependent; the partition and the labels are not.
+#include <math.h>
+
+#include "common.cuh"
+#include "prims.cuh"
+
+#define CL_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ unsigned long long cl_pack(const long long cx, const long long cy, const long long cz)
+{
+  return ((unsigned long long)(cx + (1 << 20)) & 0x1FFFFFull) | (((unsigned long long)(cy + (1 << 20)) & 0x1FFFFFull) << 21) |
+         (((unsigned long long)(cz + (1 << 20)) & 0x1FFFFFull) << 42);
+}
+__device__ __forceinline__ unsigned cl_hash(unsigned long long k)
+{
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (unsigned)k;
+}
+
+__global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz, const int stride, const unsigned long long* __restrict__ d_m, const size_t m_cap,
+                                                   const double inv_cell, float4* __restrict__ pts, unsigned long long* __restrict__ tkey, int* __restrict__ thead,
+                                                   const unsigned tmask, int* __restrict__ next, int* __restrict__ parent, int* __restrict__ sizes,
+                                                   unsigned long long* __restrict__ watchdog)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const float x = xyz[i * stride], y = xyz[i * stride + 1], z = xyz[i * stride + 2];
+    pts[i] = make_float4(x, y, z, 0.f);
+    parent[i] = (int)i;
+    sizes[i] = 0;
+    if (inv_cell == 0.0)
+    {
+      next[i] = -1;
+      continue;
+    }
+    const unsigned long long key = cl_pack((long long)floor((double)x * inv_cell), (long long)floor((double)y * inv_cell), (long long)floor((double)z * inv_cell));
+    unsigned slot = cl_hash(key) & tmask;
+    unsigned probes = 0;
+    while (true)
+    {
+      const unsigned long long prev = atomicCAS(tkey + slot, CL_EMPTY, key);
+      if (prev == CL_EMPTY || prev == key)
+      {
+        next[i] = atomicExch(thead + slot, (int)i);
+        break;
+      }
+      slot = (slot + 1) & tmask;
+      if (++probes > tmask)
+      {
+        atomicAdd(watchdog, 1ull);
+        next[i] = -1;
+        break;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int uf_find(int* __restrict__ parent, int a)
+{
+  // path halving; concurrent writers only ever replace a parent by one of its ancestors
+  while (true)
+  {
+    const int p = ((volatile int*)parent)[a];
+    if (p == a)
+      return a;
+    const int gp = ((volatile int*)parent)[p];
+    if (gp != p)
+      parent[a] = gp;
+    a = p;
+  }
+}
+__device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
+{
+  while (true)
+  {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b)
+      return;
+    if (a < b)
+    {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    // a > b: hang root a under b
+    const int old = atomicCAS(parent + a, a, b);
+    if (old == a)
+      return;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_cl_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const double inv_cell, const float r2,
+                                                  const float4* __restrict__ pts, const unsigned long long* __restrict__ tkey, const int* __restrict__ thead,
+                                                  const unsigned tmask, const int* __restrict__ next, int* __restrict__ parent)
+{
+  if (inv_cell == 0.0)
+    return;
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const float4 a = pts[i];
+    const long long cx = (long long)floor((double)a.x * inv_cell), cy = (long long)floor((double)a.y * inv_cell), cz = (long long)floor((double)a.z * inv_cell);
+    for (int dz = -1; dz <= 1; dz++)
+      for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++)
+        {
+          const unsigned long long key = cl_pack(cx + dx, cy + dy, cz + dz);
+          unsigned slot = cl_hash(key) & tmask;
+          int j = -1;
+          for (unsigned probes = 0; probes <= tmask; probes++)
+          {
+            const unsigned long long k = tkey[slot];
+            if (k == key)
+            {
+              j = thead[slot];
+              break;
+            }
+            if (k == CL_EMPTY)
+              break;
+            slot = (slot + 1) & tmask;
+          }
+          while (j >= 0)
+          {
+            if (j < (int)i)
+            {
+              const float4 b = pts[j];
+              // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
+              float d2 = 0.0f;
+              float diff = a.x - b.x;
+              d2 += diff * diff;
+              diff = a.y - b.y;
+              d2 += diff * diff;
+              diff = a.z - b.z;
+              d2 += diff * diff;
+              if (d2 < r2)
+                uf_union(parent, (int)i, j);
+            }
+            j = next[j];
+          }
+        }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __restrict__ d_m, const size_t m_cap, int* __restrict__ parent, int* __restrict__ labels,
+                                                    int* __restrict__ sizes, unsigned long long* __restrict__ d_ncl)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  unsigned roots = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    int r = (int)i;
+    while (true)
+    {
+      const int p = parent[r];
+      if (p == r)
+        break;
+      r = p;
+    }
+    labels[i] = r;
+    atomicAdd(sizes + r, 1);
+    roots += (r == (int)i);
+  }
+  roots = prims::warp_sum(roots);
+  if ((threadIdx.x & 31) == 0 && roots)
+    atomicAdd(d_ncl, (unsigned long long)roots);
+}
+
+int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol, int* d_labels,
+                   unsigned long long* d_ncl)
+{
+  CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
+  if (m_cap == 0)
+    return 0;
+  size_t tsize = 1024;
+  while (tsize < 2 * m_cap)
+    tsize <<= 1;
+  ENSURE(ws.pts, m_cap * 16);
+  ENSURE(ws.table_key, tsize * 8);
+  ENSURE(ws.table_head, tsize * 4);
+  ENSURE(ws.next, m_cap * 4);
+  ENSURE(ws.parent, m_cap * 4);
+  ENSURE(ws.sizes, m_cap * 4);
+  CK(cudaMemsetAsync(ws.table_key.p, 0xFF, tsize * 8, ctx->stream));
+  CK(cudaMemsetAsync(ws.table_head.p, 0xFF, tsize * 4, ctx->stream));
+  // pcl: r^2 = tolerance * tolerance evaluated in double, narrowed to the float the kd-tree compares with
+  const float r2 = (float)((double)tol * (double)tol);
+  // cell pitch a hair above tol: two points closer than tol in every axis always land in adjacent cells
+  const double inv_cell = tol > 0.0f ? 1.0 / ((double)tol * (1.0 + 1e-6)) : 0.0;
+  LAUNCH(k_cl_insert, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_xyz, stride_floats, d_m, m_cap, inv_cell, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(),
+         ws.table_head.as<int>(), (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>(), ws.sizes.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
+  LAUNCH(k_cl_union, vf_blocks(ctx, m_cap, 128, 16), 128, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), ws.table_head.as<int>(),
+         (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>());
+  LAUNCH(k_cl_flatten, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.parent.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
+  return 0;
+}
+
+extern "C" int vofod_cluster(vofod_ctx* ctx, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!n_clusters || (m && (!xyz || !labels)))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  *n_clusters = 0;
+  if (m == 0)
+    return VOFOD_OK;
+  if (m > (size_t)INT32_MAX)
+    return vf_fail(ctx, VOFOD_E_INVALID, "too many points");
+  ENSURE(ctx->scratch_a, m * 12);
+  ENSURE(ctx->labels, m * 4);
+  CK(cudaMemcpyAsync(ctx->scratch_a.p, xyz, m * 12, cudaMemcpyHostToDevice, ctx->stream));
+  RET(vf_cluster_dev(ctx, ctx->cl, ctx->scratch_a.as<float>(), 3, nullptr, m, tol, ctx->labels.as<int>(), vf_cnt(ctx, CNT_NCLUSTERS)));
+  unsigned long long ncl = 0, wd = 0;
+  CK(cudaMemcpyAsync(labels, ctx->labels.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&ncl, vf_cnt(ctx, CNT_NCLUSTERS), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&wd, vf_cnt(ctx, CNT_WATCHDOG), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (wd)
+    return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", wd);
+  *n_clusters = (size_t)ncl;
+  return VOFOD_OK;
+}

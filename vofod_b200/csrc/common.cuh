@@ -50,6 +50,32 @@ __device__ __forceinline__ bool cell_owned(const Geom& g, const int x, const int
   return v >= g.own_lo && v < g.own_hi;
 }
 
+// hasCloseTo (voxel_map.cpp:376-400): window [o-mv, o+mv) clamped, truncated integer norm
+__device__ inline bool has_close_to(const float* __restrict__ score, const Geom& g, const float x, const float y, const float z, const float max_dist, const float thr)
+{
+  const int ox = coord_to_idx1(x, g.off[0], g.inv), oy = coord_to_idx1(y, g.off[1], g.inv), oz = coord_to_idx1(z, g.off[2], g.inv);
+  const float md = max_dist * g.inv;
+  const int mv = (int)ceilf(md);
+  const int bx = max(ox - mv, 0), by = max(oy - mv, 0), bz = max(oz - mv, 0);
+  const int ex = min(ox + mv, g.size[0]), ey = min(oy + mv, g.size[1]), ez = min(oz + mv, g.size[2]);
+  for (int zi = bz; zi < ez; zi++)
+    for (int yi = by; yi < ey; yi++)
+      for (int xi = bx; xi < ex; xi++)
+      {
+        const long long ci = cell_index(g, xi, yi, zi);
+        if (ci < 0)
+          continue;
+        if (score[ci] > thr)
+        {
+          const int dx = xi - ox, dy = yi - oy, dz = zi - oz;
+          const int nrm = (int)sqrt((double)(dx * dx + dy * dy + dz * dz));
+          if ((float)nrm <= md)
+            return true;
+        }
+      }
+  return false;
+}
+
 // ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
 #define ACC_LEN_BITS 44
 __device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
@@ -90,6 +116,7 @@ struct ClusterWs
 };
 
 #define MAX_TILE_STATES (1 << 15)
+#define VOFOD_SCAN_SLOTS 256
 
 struct vofod_ctx
 {
@@ -123,8 +150,9 @@ struct vofod_ctx
   float lut_max_off = 0.f;
 
   // scan slots (device-resident scans)
-  DevBuf scan_slot[4];
-  size_t scan_slot_n[4] = {0, 0, 0, 0};
+  DevBuf scan_staging;  // device copy of the host scan of the current call
+  DevBuf scan_slot[VOFOD_SCAN_SLOTS];
+  size_t scan_slot_n[VOFOD_SCAN_SLOTS] = {0};
   void* pinned = nullptr;   // small pinned host block for result read-back
   size_t pinned_bytes = 0;
 
@@ -147,11 +175,14 @@ struct vofod_ctx
   DevBuf cl_info;     // vofod_cluster_info per far cluster
   DevBuf dets;        // vofod_detection
   DevBuf explore_ws;
+  DevBuf cls_sizes, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace
-  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure;
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets;
+  int sep_off_n = -1, sep_off_mv = 0;
+  float sep_off_md = 0.f;
 
   // nodelet state (vofod_nodelet.cpp:2323-2332)
   bool background_pts_sufficient = false;
@@ -195,6 +226,13 @@ enum
   CNT_EXPLORE_N,
   CNT_SCRATCH0,
   CNT_SCRATCH1,
+  CNT_STATE_BG,       // m_background_pts_sufficient (vofod_nodelet.cpp:2323) — device-resident so classification needs no host round trip
+  CNT_STATE_SURE,     // m_sure_background_sufficient
+  CNT_DET_ID,         // m_last_detection_id
+  CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
+  CNT_NFARPTS,
+  CNT_SEP_NENT,
+  CNT_SEP_NUNIQ,
   CNT_N_SLOTS = 64
 };
 
@@ -246,6 +284,7 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
 // raycast.cu
 int vf_raycast_accumulate_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p);
 int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);
+int vf_raycast_expand(vofod_ctx* ctx, uint32_t* d_counts, float* d_lengths);
 // pipeline.cu
 int vf_range_update_dev(vofod_ctx* ctx, const float pt[3], const vofod_params& p, int repeats);
 int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);

@@ -122,15 +122,17 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->scan_slot[0], &ctx->scan_slot[1],
-                    &ctx->scan_slot[2], &ctx->scan_slot[3], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
                     &ctx->far_keys_b, &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d,
-                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure};
+                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets,
+                    &ctx->cls_sizes, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms};
   for (DevBuf* b : bufs)
     free_buf(*b);
+  for (int i = 0; i < VOFOD_SCAN_SLOTS; i++)
+    free_buf(ctx->scan_slot[i]);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   if (ctx->ev_ok)
@@ -255,31 +257,6 @@ __global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* 
   }
 }
 
-// hasCloseTo (voxel_map.cpp:376-400): window [o-mv, o+mv) clamped, truncated integer norm
-__device__ bool has_close_to(const float* __restrict__ score, const Geom& g, const float x, const float y, const float z, const float max_dist, const float thr)
-{
-  const int ox = coord_to_idx1(x, g.off[0], g.inv), oy = coord_to_idx1(y, g.off[1], g.inv), oz = coord_to_idx1(z, g.off[2], g.inv);
-  const float md = max_dist * g.inv;
-  const int mv = (int)ceilf(md);
-  const int bx = max(ox - mv, 0), by = max(oy - mv, 0), bz = max(oz - mv, 0);
-  const int ex = min(ox + mv, g.size[0]), ey = min(oy + mv, g.size[1]), ez = min(oz + mv, g.size[2]);
-  for (int zi = bz; zi < ez; zi++)
-    for (int yi = by; yi < ey; yi++)
-      for (int xi = bx; xi < ex; xi++)
-      {
-        const long long ci = cell_index(g, xi, yi, zi);
-        if (ci < 0)
-          continue;
-        if (score[ci] > thr)
-        {
-          const int dx = xi - ox, dy = yi - oy, dz = zi - oz;
-          const int nrm = (int)sqrt((double)(dx * dx + dy * dy + dz * dz));
-          if ((float)nrm <= md)
-            return true;
-        }
-      }
-  return false;
-}
 __global__ void k_has_close_to(const float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const int stride, const size_t n, const float max_dist,
                                const float thr, uint8_t* __restrict__ out)
 {
@@ -466,7 +443,9 @@ static int map_alloc(vofod_ctx* ctx)
   ENSURE(ctx->flags, (size_t)n + 64);
   CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)n, ctx->stream));
   ctx->flags_full_dirty = false;
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, CNT_N_SLOTS * sizeof(unsigned long long), ctx->stream));
+  // every counter except the exploreToGround stamp generation (its visited cube keeps old stamps)
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, CNT_EXPLORE_EPOCH * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_EXPLORE_EPOCH + 1), 0, (CNT_N_SLOTS - CNT_EXPLORE_EPOCH - 1) * sizeof(unsigned long long), ctx->stream));
   ctx->win_valid = false;
   ctx->acc_has_data = false;
   ctx->map_ready = true;
@@ -592,7 +571,6 @@ int vofod_map_set_inf(vofod_ctx* ctx, const float* xyz, size_t n)
   return VOFOD_OK;
 }
 
-int vf_raycast_expand(vofod_ctx* ctx, uint32_t* d_counts, float* d_lengths);  // raycast.cu
 
 int vofod_map_download(vofod_ctx* ctx, int which, float* host, size_t n_cells)
 {
@@ -856,25 +834,6 @@ int vofod_set_sensor(vofod_ctx* ctx, int W, int H, const float* dirs, const floa
   ctx->lut_has_off = has_off;
   ctx->lut_max_off = max_off;
   ctx->win_valid = false;
-  return VOFOD_OK;
-}
-
-int vofod_state_get(const vofod_ctx* ctx, int* bg, int* sure, uint32_t* id)
-{
-  if (!ctx)
-    return VOFOD_E_INVALID;
-  if (bg) *bg = ctx->background_pts_sufficient;
-  if (sure) *sure = ctx->sure_background_sufficient;
-  if (id) *id = ctx->last_detection_id;
-  return VOFOD_OK;
-}
-int vofod_state_set(vofod_ctx* ctx, int bg, int sure, uint32_t id)
-{
-  if (!ctx)
-    return VOFOD_E_INVALID;
-  ctx->background_pts_sufficient = bg != 0;
-  ctx->sure_background_sufficient = sure != 0;
-  ctx->last_detection_id = id;
   return VOFOD_OK;
 }
 

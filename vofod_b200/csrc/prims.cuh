@@ -114,7 +114,7 @@ __device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const
 
 // ---- exclusive scan of u32 ------------------------------------------------------------------------------
 // out[i] = sum_{j<i} in[j]; *total (u64, may be null) = sum of all.  in/out may alias.  Buffers must be padded to TILE.
-__global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const unsigned long long* d_n, const size_t cap,
+static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const unsigned long long* d_n, const size_t cap,
                                                       unsigned long long* state, const uint32_t epoch, unsigned long long* total, unsigned long long* watchdog)
 {
   __shared__ uint32_t ws[NT / 32];

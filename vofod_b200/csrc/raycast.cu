@@ -497,10 +497,9 @@ int vofod_raycast_accumulate(vofod_ctx* ctx, const vofod_pt* scan, size_t n, con
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
-  ENSURE(ctx->scan_slot[0], n * sizeof(vofod_pt) + 64);
-  CK(cudaMemcpyAsync(ctx->scan_slot[0].p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->scan_slot_n[0] = n;
-  const int rc = vf_raycast_accumulate_dev(ctx, ctx->scan_slot[0].as<vofod_pt>(), n, *tf, *p);
+  ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+  CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = vf_raycast_accumulate_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p);
   if (rc < 0)
     return rc;
   unsigned long long t[2] = {0, 0};

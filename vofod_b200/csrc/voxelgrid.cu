@@ -136,15 +136,15 @@ __global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in
 
 // K1b — voxel_grid_weighted.cpp:56-111
 __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, const int align, const float ac0, const float ac1, const float ac2, VgLayout* __restrict__ L,
-                            unsigned long long* __restrict__ counters)
+                            unsigned long long* __restrict__ counters, const int slot_nvalid, const int slot_overflow)
 {
   const float inv = 1.0f / leaf;
   L->leaf = leaf;
   L->inv = inv;
   L->n_valid = mm->n_valid;
   L->overflow = 0;
-  counters[CNT_VG_NVALID] = mm->n_valid;
-  counters[CNT_VG_OVERFLOW] = 0;
+  counters[slot_nvalid] = mm->n_valid;
+  counters[slot_overflow] = 0;
   if (mm->n_valid == 0)
   {
     for (int a = 0; a < 3; a++)
@@ -168,7 +168,7 @@ __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, con
   if (dx * dy * dz > 2147483647ll)
   {
     L->overflow = 1;
-    counters[CNT_VG_OVERFLOW] = 1;
+    counters[slot_overflow] = 1;
   }
   for (int a = 0; a < 3; a++)
   {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restr
 
 // shared tail: pts (float4, w = validity) + minmax -> ctx->vox / CNT_VG_M.  key_bits_hint = 0 => sort all 32 bits.
 static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool align, const float* align_center, const int key_bits_hint, const vofod_xyzi* d_counted_in,
-                  const float counted_thr, DevBuf& out_buf)
+                  const float counted_thr, DevBuf& out_buf, const int slot_m = CNT_VG_M, const int slot_nvalid = CNT_VG_NVALID, const int slot_overflow = CNT_VG_OVERFLOW)
 {
   using namespace prims;
   const size_t np = padded(n);
@@ -281,14 +281,14 @@ static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool a
   VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
   const float ac[3] = {align ? align_center[0] : 0.f, align ? align_center[1] : 0.f, align ? align_center[2] : 0.f};
-  LAUNCH(k_vg_layout, 1, 1, 0, mm, leaf, align ? 1 : 0, ac[0], ac[1], ac[2], L, cnt);
+  LAUNCH(k_vg_layout, 1, 1, 0, mm, leaf, align ? 1 : 0, ac[0], ac[1], ac[2], L, cnt, slot_nvalid, slot_overflow);
   const int nb = vf_blocks(ctx, n, 256, 8);
   LAUNCH(k_vg_keys, nb, 256, 0, ctx->vg_pts.as<float4>(), (int)n, L, ctx->vg_keys_a.as<uint32_t>());
   uint32_t* sorted = nullptr;
   const int bits = key_bits_hint > 0 && key_bits_hint < 32 ? key_bits_hint : 32;
   RET((radix_sort<uint32_t, false>(ctx, ctx->vg_keys_a.as<uint32_t>(), ctx->vg_keys_b.as<uint32_t>(), nullptr, nullptr, nullptr, n, 0, bits, &sorted, nullptr)));
   LAUNCH(k_vg_heads, nb, 256, 0, sorted, (int)n, ctx->vg_flags.as<uint32_t>());
-  RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_scan.as<uint32_t>(), nullptr, n, cnt + CNT_VG_M));
+  RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_scan.as<uint32_t>(), nullptr, n, cnt + slot_m));
   LAUNCH(k_vg_starts, nb, 256, 0, sorted, ctx->vg_scan.as<uint32_t>(), (int)n, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>());
   const uint32_t* over_prefix = nullptr;
   if (d_counted_in)
@@ -299,7 +299,7 @@ static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool a
     RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_pref.as<uint32_t>(), nullptr, n + 1, nullptr));
     over_prefix = ctx->vg_pref.as<uint32_t>();
   }
-  LAUNCH(k_vg_emit, nb, 256, 0, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>(), L, cnt + CNT_VG_M, over_prefix, out_buf.as<vofod_vox>(), np);
+  LAUNCH(k_vg_emit, nb, 256, 0, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>(), L, cnt + slot_m, over_prefix, out_buf.as<vofod_vox>(), np);
   return 0;
 }
 
@@ -391,10 +391,9 @@ int vofod_filter_voxelize(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const 
   *m = 0;
   if (n == 0)
     return VOFOD_OK;
-  ENSURE(ctx->scan_slot[0], n * sizeof(vofod_pt) + 64);
-  CK(cudaMemcpyAsync(ctx->scan_slot[0].p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->scan_slot_n[0] = n;
-  RET(vf_filter_voxelize_dev(ctx, ctx->scan_slot[0].as<vofod_pt>(), n, *tf, *p));
+  ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+  CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  RET(vf_filter_voxelize_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p));
   int overflow = 0;
   RET(read_m(ctx, m, &overflow));
   ctx->last_m = *m;
@@ -462,5 +461,6 @@ int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, size_t n, 
   MinMax* mm = ctx->scratch_d.as<MinMax>();
   LAUNCH(k_minmax_init, 1, 1, 0, mm);
   LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, reinterpret_cast<const float*>(d_in), 4, (int)n, ctx->vg_pts.as<float4>(), mm);
-  return vg_run(ctx, n, leaf, false, nullptr, 0, d_in, thr, out);
+  // separate counter slots: the per-scan voxel counts (CNT_VG_*) must survive the background-cluster pass
+  return vg_run(ctx, n, leaf, false, nullptr, 0, d_in, thr, out, CNT_SEP_KDS, CNT_SCRATCH1, CNT_SEP_NUNIQ);
 }

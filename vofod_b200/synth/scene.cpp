@@ -104,6 +104,23 @@ inline double hit_sphere(const sphere_t& s, const double o[3], const double d[3]
 
 extern "C" {
 
+// Simulated-sensor XYZ LUT with the geometry of the reference's initialize_sensor_lut_simulation
+// (vofod_nodelet.cpp:374-420): yaw = col*2pi/(W-1), pitch = -vfov/2 + row*vfov/(H-1), double math stored as fp32,
+// ray id = row*W + col.  Harness input only; tests check it against the oracle's restatement.
+void vsyn_sim_lut(int W, int H, double vfov, float* dirs3xN)
+{
+  const double ystep = (2.0 * M_PI) / (W - 1), pstep = vfov / (H - 1);
+  for (int row = 0; row < H; row++)
+    for (int col = 0; col < W; col++)
+    {
+      const double yaw = col * ystep, pitch = row * pstep - vfov / 2.0;
+      float* d = dirs3xN + 3 * (size_t(col) + size_t(row) * W);
+      d[0] = float(std::cos(pitch) * std::cos(yaw));
+      d[1] = float(std::cos(pitch) * std::sin(yaw));
+      d[2] = float(std::sin(pitch));
+    }
+}
+
 // scene_id: 0 = city (24 boxes), 1 = gazebo-like (4 boxes + 3 spheres)
 // k: scan index.  dirs: 3xN LUT (column-major, ray id = row*W+col).  out: N points.
 // range_pt: ground point below the sensor for the rangefinder seeds of schedule S1.
@@ -125,7 +142,12 @@ int vsyn_generate(int scene_id, int k, int W, int H, const float* dirs, float ma
     built_scale[scene_id] = map_scale;
   }
   // sensor pose
-  const double px = 30.0 * map_scale * std::sin(0.02 * k), py = 30.0 * map_scale * std::sin(0.013 * k + 1.0), pz = 6.0 + 2.0 * std::sin(0.05 * k);
+  // take-off: the sensor starts 0.6 m above the ground and climbs to its cruise altitude over the first 20 scans.  Without it
+  // the background never bootstraps: the rangefinder seed (vofod_nodelet.cpp:581-613) lands directly below the sensor, and
+  // from cruise altitude the +-45 deg LiDAR sees no ground within ground_points_max_distance of that cell.
+  const double climb = k >= 20 ? 1.0 : (k / 20.0) * (k / 20.0) * (3.0 - 2.0 * (k / 20.0));
+  const double px = 30.0 * map_scale * std::sin(0.02 * k), py = 30.0 * map_scale * std::sin(0.013 * k + 1.0);
+  const double pz = 0.6 + climb * (5.4 + 2.0 * std::sin(0.05 * k));
   const double yaw = 0.01 * k, roll = 0.05 * std::sin(0.07 * k), pitch = 0.05 * std::sin(0.07 * k);
   const double cy = std::cos(yaw), sy = std::sin(yaw), cp = std::cos(pitch), sp = std::sin(pitch), cr = std::cos(roll), sr = std::sin(roll);
   // R = Rz(yaw) Ry(pitch) Rx(roll)

@@ -3,14 +3,18 @@
 // path (ctu-mrs/vofod).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library; the product (libvofod_cuda) never links or calls it.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and cannot be
-// compiled whole here (every translation unit needs PCL / Eigen / ROS headers, none installed).  The pins
-// are (1) the hand-derived known-answer tests of SURVEY.md Appendix B (tests/test_oracle_kat.py) and
-// (2) oracle/_ref: the reference's own voxel_map.cpp / voxel_grid_*.cpp compiled where they lie against the
-// minimal Eigen/PCL stand-in headers of oracle/shim/ (see oracle/Makefile), compared call by call in
-// tests/test_oracle_vs_ref.py.  Third-party arithmetic (PCL CropBox / transformPointCloud / VoxelGrid base /
-// EuclideanClusterExtraction / MomentOfInertiaEstimation, FLANN, Eigen) is restated from its published
-// behaviour (PCL 1.10, FLANN 1.9, Eigen 3.3 — versions unpinned in the reference, package.xml:164-165).
+// PARITY PINS.  The reference ships no tests, golden vectors or fixtures and cannot be built whole here
+// (its nodelet needs ROS / PCL / Eigen / FLANN, none installed).  What pins this restatement:
+//   (1) PINNED against the reference's own code — VoxelMap (C1), VoxelGridWeighted (C2), VoxelGridCounted (C3) and the
+//       raycast accumulate loop around forEachRay: oracle/_ref = the reference's voxel_map.cpp / voxel_grid_weighted.cpp /
+//       voxel_grid_counted.cpp compiled where they lie against the stand-in Eigen/PCL/ROS headers of oracle/shim
+//       (oracle/Makefile target `ref`); tests/golden/make_golden.py turns its outputs into tests/golden/ref_vectors.npz and
+//       tests/test_golden.py requires this file to reproduce them bit for bit (20 arrays incl. the sequential-fp32 grid).
+//   (2) PARITY UNPINNED for what lives in the nodelet (vofod_nodelet.cpp needs ROS to compile) and in third-party code:
+//       the per-scan orchestration, point / ray update rules, classification, detections, sepclusters, and PCL's CropBox /
+//       transformPointCloud / EuclideanClusterExtraction / MomentOfInertiaEstimation (restated from their published
+//       behaviour: PCL 1.10, FLANN 1.9, Eigen 3.3 — versions unpinned in the reference, package.xml:164-165).  These are
+//       held by the hand-derived known-answer tests of SURVEY.md Appendix B (tests/test_oracle_kat.py) only.
 //
 // Build: g++ -std=c++17 -O3 -DNDEBUG -ffp-contract=off  (= reference CMakeLists.txt:14-15, no -march, so
 // every fp32 op below is separately rounded exactly as in the reference's x86-64 build).

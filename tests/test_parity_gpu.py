@@ -326,3 +326,13 @@ def test_full_size_properties(gpu):
     # every touched free cell moved towards the ray score, never past it
     m = runs[0][3]
     assert m.min() >= -1000.0 and m.max() <= -740.0
+
+
+def test_golden_vectors_from_reference_build(gpu):
+    """libvofod_cuda against tests/golden/ref_vectors.npz — outputs of the REFERENCE's own voxel_map.cpp / voxel_grid_*.cpp
+    (compiled from /root/reference by oracle/Makefile, generated by tests/golden/make_golden.py)."""
+    import os
+    from golden_cases import GpuSide, compare, run_cases
+    want = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")))
+    got = run_cases(GpuSide(gpu))
+    compare(got, want, "libvofod_cuda")

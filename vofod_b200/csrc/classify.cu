@@ -119,54 +119,121 @@ struct ClsArgs
   int side;        // stamp cube side = 2*Rmax+1
   int rmax;
   int terms_cap;
+  int n_exact;     // clusters with more points cannot pass the max_size gate
 };
 
-// K13 — pcl::MomentOfInertiaEstimation restated (vofod_nodelet.cpp:1655-1672) + the gates (:1679-1690)
-__global__ void __launch_bounds__(64) k_cluster_moi(const ClsArgs a, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
-                                                    const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
-                                                    vofod_cluster_info* __restrict__ out)
+// K13 — pcl::MomentOfInertiaEstimation restated (vofod_nodelet.cpp:1655-1672) + the gates (:1679-1690).
+// One WARP per far cluster.  Two paths:
+//   n <= n_exact (every cluster small enough to pass the max_size gate is): the lanes load 32 points at a time and then
+//     ALL lanes run the same sequential fp32 sums over them via shuffles — the reference's summation order, bit for bit,
+//     with the memory latency of the index indirection paid once per 32 points;
+//   n >  n_exact (cannot fit into max_size, so the class is `invalid` whatever the last bits are): lane-strided fp64
+//     partial sums + a fixed-shape warp reduction; the reported box agrees with the sequential fp32 one to ~1e-6.
+__global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
+                                                     const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
+                                                     vofod_cluster_info* __restrict__ out)
 {
   const unsigned long long n_far = *d_nfar;
   const unsigned long long lmask = (1ull << a.bits) - 1ull;
-  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_far; c += (unsigned long long)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  const float FMAX = 3.402823466e+38f;
+  for (unsigned long long c = warp0; c < n_far; c += n_warps)
   {
     const int label = (int)(okeys[c] & lmask);
     const int n = sizes[label];
     const uint32_t* idcs = sidx + seg_start[label];
-    vofod_cluster_info ci;
-    ci.label = label;
-    ci.n_points = n;
-    ci.cclass = VOFOD_CLASS_INVALID;
-    ci.obb_size = __int_as_float(0x7fc00000);
+    const bool exact = n <= a.n_exact;
     float mean[3] = {0.f, 0.f, 0.f};
-    float amin[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
-    float amax[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    for (int k = 0; k < n; k++)  // computeMeanValue
+    float amin[3] = {FMAX, FMAX, FMAX}, amax[3] = {-FMAX, -FMAX, -FMAX};
+    float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const unsigned np = n == 0 ? 1u : (unsigned)n;
+    if (exact)
     {
-      const vofod_vox v = vox[idcs[k]];
-      const float p[3] = {v.x, v.y, v.z};
+      for (int base = 0; base < n; base += 32)  // computeMeanValue
+      {
+        const int k = base + (int)lane;
+        vofod_vox v = {0.f, 0.f, 0.f, 0u};
+        if (k < n)
+          v = vox[idcs[k]];
+        const int cnt = min(32, n - base);
+        for (int t = 0; t < cnt; t++)
+        {
+          const float p[3] = {__shfl_sync(VOFOD_FULL, v.x, t), __shfl_sync(VOFOD_FULL, v.y, t), __shfl_sync(VOFOD_FULL, v.z, t)};
+#pragma unroll
+          for (int q = 0; q < 3; q++)
+          {
+            mean[q] += p[q];
+            if (p[q] <= amin[q]) amin[q] = p[q];
+            if (p[q] >= amax[q]) amax[q] = p[q];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        mean[q] /= (float)np;
+      for (int base = 0; base < n; base += 32)  // computeCovarianceMatrix
+      {
+        const int k = base + (int)lane;
+        vofod_vox v = {0.f, 0.f, 0.f, 0u};
+        if (k < n)
+          v = vox[idcs[k]];
+        const int cnt = min(32, n - base);
+        for (int t = 0; t < cnt; t++)
+        {
+          const float d[3] = {__shfl_sync(VOFOD_FULL, v.x, t) - mean[0], __shfl_sync(VOFOD_FULL, v.y, t) - mean[1], __shfl_sync(VOFOD_FULL, v.z, t) - mean[2]};
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              cov[r][q] += d[r] * d[q];
+        }
+      }
+    } else
+    {
+      double sm[3] = {0.0, 0.0, 0.0};
+      for (int k = (int)lane; k < n; k += 32)
+      {
+        const vofod_vox v = vox[idcs[k]];
+        const float p[3] = {v.x, v.y, v.z};
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+        {
+          sm[q] += (double)p[q];
+          amin[q] = fminf(amin[q], p[q]);
+          amax[q] = fmaxf(amax[q], p[q]);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 3; q++)
       {
-        mean[q] += p[q];
-        if (p[q] <= amin[q]) amin[q] = p[q];
-        if (p[q] >= amax[q]) amax[q] = p[q];
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          sm[q] += __shfl_xor_sync(VOFOD_FULL, sm[q], o);
+          amin[q] = fminf(amin[q], __shfl_xor_sync(VOFOD_FULL, amin[q], o));
+          amax[q] = fmaxf(amax[q], __shfl_xor_sync(VOFOD_FULL, amax[q], o));
+        }
+        mean[q] = (float)(sm[q] / (double)np);
       }
-    }
-    const unsigned np = n == 0 ? 1u : (unsigned)n;
+      double sc[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = (int)lane; k < n; k += 32)
+      {
+        const vofod_vox v = vox[idcs[k]];
+        const float d[3] = {v.x - mean[0], v.y - mean[1], v.z - mean[2]};
+        sc[0] += (double)(d[0] * d[0]);
+        sc[1] += (double)(d[0] * d[1]);
+        sc[2] += (double)(d[0] * d[2]);
+        sc[3] += (double)(d[1] * d[1]);
+        sc[4] += (double)(d[1] * d[2]);
+        sc[5] += (double)(d[2] * d[2]);
+      }
 #pragma unroll
-    for (int q = 0; q < 3; q++)
-      mean[q] /= (float)np;
-    float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = 0; k < n; k++)  // computeCovarianceMatrix
-    {
-      const vofod_vox v = vox[idcs[k]];
-      const float d[3] = {v.x - mean[0], v.y - mean[1], v.z - mean[2]};
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-          cov[r][q] += d[r] * d[q];
+      for (int q = 0; q < 6; q++)
+        for (int o = 16; o > 0; o >>= 1)
+          sc[q] += __shfl_xor_sync(VOFOD_FULL, sc[q], o);
+      cov[0][0] = (float)sc[0]; cov[0][1] = cov[1][0] = (float)sc[1]; cov[0][2] = cov[2][0] = (float)sc[2];
+      cov[1][1] = (float)sc[3]; cov[1][2] = cov[2][1] = (float)sc[4]; cov[2][2] = (float)sc[5];
     }
     const float factor = 1.0f / (float)((n - 1 > 0) ? (n - 1) : 1);
     double A[3][3];
@@ -199,9 +266,9 @@ __global__ void __launch_bounds__(64) k_cluster_moi(const ClsArgs a, const vofod
     if (det <= 0.0f)
       for (int q = 0; q < 3; q++)
         ax[0][q] = -ax[0][q];
-    float omin[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
-    float omax[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    for (int k = 0; k < n; k++)  // computeOBB
+    // computeOBB: min / max of the projections — order independent, lane-strided + warp reduction
+    float omin[3] = {FMAX, FMAX, FMAX}, omax[3] = {-FMAX, -FMAX, -FMAX};
+    for (int k = (int)lane; k < n; k += 32)
     {
       const vofod_vox v = vox[idcs[k]];
       const float d[3] = {v.x - mean[0], v.y - mean[1], v.z - mean[2]};
@@ -209,10 +276,24 @@ __global__ void __launch_bounds__(64) k_cluster_moi(const ClsArgs a, const vofod
       for (int q = 0; q < 3; q++)
       {
         const float pr = d[0] * ax[q][0] + d[1] * ax[q][1] + d[2] * ax[q][2];
-        if (pr <= omin[q]) omin[q] = pr;
-        if (pr >= omax[q]) omax[q] = pr;
+        omin[q] = fminf(omin[q], pr);
+        omax[q] = fmaxf(omax[q], pr);
       }
     }
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        omin[q] = fminf(omin[q], __shfl_xor_sync(VOFOD_FULL, omin[q], o));
+        omax[q] = fmaxf(omax[q], __shfl_xor_sync(VOFOD_FULL, omax[q], o));
+      }
+    if (lane != 0)
+      continue;
+    vofod_cluster_info ci;
+    ci.label = label;
+    ci.n_points = n;
+    ci.cclass = VOFOD_CLASS_INVALID;
+    ci.obb_size = __int_as_float(0x7fc00000);
     float shift[3];
     for (int q = 0; q < 3; q++)
     {
@@ -624,7 +705,16 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   a.side = side;
   a.rmax = rmax;
   a.terms_cap = (int)terms_cap;
-  LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap, 64, 16), 64, 0, a, d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
+  {
+    // a cluster of distinct voxel centres whose OBB diagonal is <= max_size lies inside a ball of that diameter: it cannot
+    // have more points than a cube of (max_size/vs + 2) voxels per side (generous bound)
+    const double side_v = ceil(p.cls_max_size / vs) + 2.0;
+    const double cap = side_v * side_v * side_v;
+    a.n_exact = cap < 1e6 ? (int)cap : 1000000;
+    if (a.n_exact < 64)
+      a.n_exact = 64;
+  }
+  LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap * 32, 256, 4), 256, 0, a, d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
          ctx->cl_info.as<vofod_cluster_info>());
   int* qbase = ctx->cls_queues.as<int>();
   ExploreWs w;

@@ -4,7 +4,7 @@
 // the graph "a ~ b  iff  fp32 ((ax-bx)^2 + (ay-by)^2) + (az-bz)^2 < float(tol^2)" (strict).  Here:
 //   K4  spatial hash: cell pitch slightly above tol, open-addressing table keyed by the packed cell, one
 //       linked list of point indices per occupied cell
-//   K5  one thread per point scans the 27 neighbouring cells and unites itself with every lower-indexed point
+//   K5  one warp per point (one lane per neighbouring cell) scans the 27 cells and unites the point with every lower-indexed point
 //       inside the radius (lock-free union-find, the larger root is always linked under the smaller one, so the
 //       root of a finished tree IS the minimum point index of the component = the canonical label)
 //   K5b flatten: labels[i] = root(i), per-root sizes, number of roots
@@ -105,55 +105,60 @@ __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
   }
 }
 
-__global__ void __launch_bounds__(128) k_cl_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const double inv_cell, const float r2,
+// one WARP per point: lane l < 27 owns neighbour cell l (probe + walk of that cell's list), so the dependent-load chain of
+// a point is one cell long instead of 27 and a small cloud (10^4 points) still fills the machine
+__global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const double inv_cell, const float r2,
                                                   const float4* __restrict__ pts, const unsigned long long* __restrict__ tkey, const int* __restrict__ thead,
                                                   const unsigned tmask, const int* __restrict__ next, int* __restrict__ parent)
 {
   if (inv_cell == 0.0)
     return;
   const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int dz = (int)(lane / 9) - 1, dy = (int)((lane / 3) % 3) - 1, dx = (int)(lane % 3) - 1;
+  for (size_t i = warp0; i < m; i += n_warps)
   {
     const float4 a = pts[i];
-    const long long cx = (long long)floor((double)a.x * inv_cell), cy = (long long)floor((double)a.y * inv_cell), cz = (long long)floor((double)a.z * inv_cell);
-    for (int dz = -1; dz <= 1; dz++)
-      for (int dy = -1; dy <= 1; dy++)
-        for (int dx = -1; dx <= 1; dx++)
+    int j = -1;
+    if (lane < 27)
+    {
+      const long long cx = (long long)floor((double)a.x * inv_cell), cy = (long long)floor((double)a.y * inv_cell), cz = (long long)floor((double)a.z * inv_cell);
+      const unsigned long long key = cl_pack(cx + dx, cy + dy, cz + dz);
+      unsigned slot = cl_hash(key) & tmask;
+      for (unsigned probes = 0; probes <= tmask; probes++)
+      {
+        const unsigned long long k = tkey[slot];
+        if (k == key)
         {
-          const unsigned long long key = cl_pack(cx + dx, cy + dy, cz + dz);
-          unsigned slot = cl_hash(key) & tmask;
-          int j = -1;
-          for (unsigned probes = 0; probes <= tmask; probes++)
-          {
-            const unsigned long long k = tkey[slot];
-            if (k == key)
-            {
-              j = thead[slot];
-              break;
-            }
-            if (k == CL_EMPTY)
-              break;
-            slot = (slot + 1) & tmask;
-          }
-          while (j >= 0)
-          {
-            if (j < (int)i)
-            {
-              const float4 b = pts[j];
-              // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
-              float d2 = 0.0f;
-              float diff = a.x - b.x;
-              d2 += diff * diff;
-              diff = a.y - b.y;
-              d2 += diff * diff;
-              diff = a.z - b.z;
-              d2 += diff * diff;
-              if (d2 < r2)
-                uf_union(parent, (int)i, j);
-            }
-            j = next[j];
-          }
+          j = thead[slot];
+          break;
         }
+        if (k == CL_EMPTY)
+          break;
+        slot = (slot + 1) & tmask;
+      }
+    }
+    while (j >= 0)
+    {
+      const int nj = next[j];
+      if (j < (int)i)
+      {
+        const float4 b = pts[j];
+        // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
+        float d2 = 0.0f;
+        float diff = a.x - b.x;
+        d2 += diff * diff;
+        diff = a.y - b.y;
+        d2 += diff * diff;
+        diff = a.z - b.z;
+        d2 += diff * diff;
+        if (d2 < r2)
+          uf_union(parent, (int)i, j);
+      }
+      j = nj;
+    }
   }
 }
 
@@ -204,7 +209,7 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   const double inv_cell = tol > 0.0f ? 1.0 / ((double)tol * (1.0 + 1e-6)) : 0.0;
   LAUNCH(k_cl_insert, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_xyz, stride_floats, d_m, m_cap, inv_cell, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(),
          ws.table_head.as<int>(), (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>(), ws.sizes.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
-  LAUNCH(k_cl_union, vf_blocks(ctx, m_cap, 128, 16), 128, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), ws.table_head.as<int>(),
+  LAUNCH(k_cl_union, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), ws.table_head.as<int>(),
          (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>());
   LAUNCH(k_cl_flatten, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.parent.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;

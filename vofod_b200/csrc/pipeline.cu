@@ -89,16 +89,52 @@ __global__ void k_bg_state(unsigned long long* __restrict__ counters, const unsi
     counters[CNT_STATE_BG] = 1ull;
 }
 
-__global__ void __launch_bounds__(128) k_close_points(const float* __restrict__ score, const Geom g, const vofod_vox* __restrict__ vox, const int* __restrict__ labels,
+// one WARP per point: the lanes stride over the <= (2*mv)^3 window cells of VoxelMap::hasCloseTo (voxel_map.cpp:376-400)
+__global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ score, const Geom g, const vofod_vox* __restrict__ vox, const int* __restrict__ labels,
                                                       const unsigned long long* __restrict__ d_m, const size_t m_cap, const float max_dist, const float thr,
                                                       int* __restrict__ cl_close)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const float md = max_dist * g.inv;
+  const int mv = (int)ceilf(md);
+  for (size_t i = warp0; i < m; i += n_warps)
   {
+    const int label = labels[i];
+    // a cluster is close iff ANY of its points is (:730-741): once one point has said so the others need not look
+    if (((volatile int*)cl_close)[label])
+      continue;
     const vofod_vox v = vox[i];
-    if (has_close_to(score, g, v.x, v.y, v.z, max_dist, thr))
-      cl_close[labels[i]] = 1;  // a cluster is close iff ANY of its points is (:730-741)
+    const int ox = coord_to_idx1(v.x, g.off[0], g.inv), oy = coord_to_idx1(v.y, g.off[1], g.inv), oz = coord_to_idx1(v.z, g.off[2], g.inv);
+    const int bx = max(ox - mv, 0), by = max(oy - mv, 0), bz = max(oz - mv, 0);
+    const int ex = min(ox + mv, g.size[0]), ey = min(oy + mv, g.size[1]), ez = min(oz + mv, g.size[2]);
+    const int nx = ex - bx, ny = ey - by, nz = ez - bz;
+    bool hit = false;
+    if (nx > 0 && ny > 0 && nz > 0)
+    {
+      const int total = nx * ny * nz;
+      for (int base = 0; base < total && !hit; base += 32)
+      {
+        const int t = base + (int)lane;
+        bool h = false;
+        if (t < total)
+        {
+          const int xi = bx + t % nx, yi = by + (t / nx) % ny, zi = bz + t / (nx * ny);
+          const long long ci = cell_index(g, xi, yi, zi);
+          if (ci >= 0 && score[ci] > thr)
+          {
+            const int ddx = xi - ox, ddy = yi - oy, ddz = zi - oz;
+            const int nrm = (int)sqrt((double)(ddx * ddx + ddy * ddy + ddz * ddz));  // Eigen int-vector norm(): truncation
+            h = (float)nrm <= md;
+          }
+        }
+        hit = __any_sync(VOFOD_FULL, h);
+      }
+    }
+    if (hit && lane == 0)
+      cl_close[label] = 1;
   }
 }
 __global__ void __launch_bounds__(256) k_close_finish(const int* __restrict__ labels, const unsigned long long* __restrict__ d_m, const size_t m_cap,
@@ -147,7 +183,7 @@ int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels
   ENSURE(ctx->cl_close, m_cap * 4);
   ENSURE(ctx->pt_close, m_cap + 64);
   CK(cudaMemsetAsync(ctx->cl_close.p, 0, m_cap * 4, ctx->stream));
-  LAUNCH(k_close_points, vf_blocks(ctx, m_cap, 128, 16), 128, 0, ctx->score.as<float>(), ctx->g, d_vox, d_labels, d_m, m_cap, max_dist, thr, ctx->cl_close.as<int>());
+  LAUNCH(k_close_points, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_labels, d_m, m_cap, max_dist, thr, ctx->cl_close.as<int>());
   LAUNCH(k_close_finish, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_labels, d_m, m_cap, ctx->cl_close.as<int>(), ctx->pt_close.as<uint8_t>(),
          ctx->d_counters.as<unsigned long long>());
   return 0;

@@ -54,8 +54,11 @@ __global__ void k_minmax_init(MinMax* mm)
   mm->n_valid = 0;
 }
 
+// block-wide min/max/count, then ONE set of 7 global atomics per block (a per-warp commit serialises ~8k warps on 7 words)
 __device__ __forceinline__ void block_minmax_commit(const bool valid, const float x, const float y, const float z, MinMax* mm)
 {
+  __shared__ int s_mn[3][8], s_mx[3][8];
+  __shared__ unsigned s_cnt[8];
   int mn[3] = {valid ? f2ord(x) : 0x7fffffff, valid ? f2ord(y) : 0x7fffffff, valid ? f2ord(z) : 0x7fffffff};
   int mx[3] = {valid ? f2ord(x) : (int)0x80000000, valid ? f2ord(y) : (int)0x80000000, valid ? f2ord(z) : (int)0x80000000};
   unsigned cnt = valid ? 1u : 0u;
@@ -66,15 +69,43 @@ __device__ __forceinline__ void block_minmax_commit(const bool valid, const floa
     mx[a] = __reduce_max_sync(VOFOD_FULL, mx[a]);
   }
   cnt = __reduce_add_sync(VOFOD_FULL, cnt);
-  if ((threadIdx.x & 31) == 0 && cnt)
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
   {
 #pragma unroll
     for (int a = 0; a < 3; a++)
     {
-      atomicMin(&mm->mn[a], mn[a]);
-      atomicMax(&mm->mx[a], mx[a]);
+      s_mn[a][w] = mn[a];
+      s_mx[a][w] = mx[a];
     }
-    atomicAdd(&mm->n_valid, cnt);
+    s_cnt[w] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7)
+  {
+    const int nw = (blockDim.x + 31) >> 5;
+    if (threadIdx.x < 3)
+    {
+      int v = s_mn[threadIdx.x][0];
+      for (int i = 1; i < nw; i++)
+        v = min(v, s_mn[threadIdx.x][i]);
+      if (v != 0x7fffffff)
+        atomicMin(&mm->mn[threadIdx.x], v);
+    } else if (threadIdx.x < 6)
+    {
+      int v = s_mx[threadIdx.x - 3][0];
+      for (int i = 1; i < nw; i++)
+        v = max(v, s_mx[threadIdx.x - 3][i]);
+      if (v != (int)0x80000000)
+        atomicMax(&mm->mx[threadIdx.x - 3], v);
+    } else
+    {
+      unsigned v = 0;
+      for (int i = 0; i < nw; i++)
+        v += s_cnt[i];
+      if (v)
+        atomicAdd(&mm->n_valid, v);
+    }
   }
 }
 

@@ -103,7 +103,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from vofod_b200 import abi, capi, synth
+    from vofod_b200 import abi, capi, multi, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -127,18 +127,10 @@ def run_ours(args):
     host_scans = pinned.numpy().view(abi.PT_DTYPE).reshape(n_scans, N)
     poses, scheds = [], []
     for k in range(n_scans):
-        _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k + 1000 * rank, W, H, dirs, 1.0, out=host_scans[k])
-        if rank:  # keep the take-off bootstrap on every rank: reuse the first 20 poses' altitude profile
-            pass
+        # every stream bootstraps with the same take-off, then flies its own part of the trajectory
+        _, pose, rp, _ = synth.generate(synth.SCENE_CITY, multi.stream_scan_index(rank, k), W, H, dirs, 1.0, out=host_scans[k])
         poses.append(pose)
         scheds.append(abi.schedule_s1(rp))
-    if rank:
-        # ranks > 0 fly a different part of the trajectory but must still bootstrap from the ground: regenerate the
-        # first 20 scans with the take-off of scan indices 0..19
-        for k in range(min(20, n_scans)):
-            _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs, 1.0, out=host_scans[k])
-            poses[k] = pose
-            scheds[k] = abi.schedule_s1(rp)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     dets = np.zeros(256, dtype=abi.DETECTION_DTYPE)
@@ -149,8 +141,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_leg(resident):
-        """-> (per-step device ms list, totals dict).  State is reset, so both legs do identical work."""
+    def run_leg(resident, graph=True):
+        """-> (per-step device ms list, totals dict).  State is reset, so all legs do identical work."""
+        v.set_option(abi.OPT_GRAPH, int(graph))
         v.reset(p, VOXEL)
         if resident:
             for k in range(n_scans):
@@ -188,6 +181,12 @@ def run_ours(args):
     ms_res, tot_res = run_leg(True)
     ms_e2e, tot_e2e = run_leg(False)
     clocks = sampler.stop()
+    # per-stage device times (CUDA events between the stages on the library's stream) need the kernel-by-kernel path:
+    # the same sequence once more with graph replay switched off.  Only the stage table and the roofline use it.
+    ms_eager, tot_eager = run_leg(True, graph=False)
+    tot_res["ray_ms"] = tot_eager["ray_ms"]
+    tot_res["stage"] = tot_eager["stage"]
+    assert tot_eager["trav"] == tot_res["trav"]
 
     t_res = torch.tensor([sum(ms_res), sum(ms_e2e), float(tot_res["trav"]), tot_res["ray_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -234,6 +233,7 @@ def run_ours(args):
                          "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": trav_per_launch * BYTES_PER_TRAVERSAL,
                          "ms_per_launch": ray_ms_per_launch},
             "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot_res["stage"].items()},
+            "stage_note": "stage times and the roofline kernel time come from a third, kernel-by-kernel leg (graph replay off): %.4f ms/step" % (sum(ms_eager) / K),
             "detections_in_timed_steps": int(tot_res["dets"]),
             "clocks": clocks,
         }

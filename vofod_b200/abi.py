@@ -190,3 +190,4 @@ def ptr(a, ctype=None):
     if ctype is None:
         return a.ctypes.data_as(C.c_void_p)
     return a.ctypes.data_as(C.POINTER(ctype))
+OPT_GRAPH = 1

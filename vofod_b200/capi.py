@@ -83,6 +83,7 @@ def load_library():
         "vofod_stage_name": (C.c_char_p, [i32]),
         "vofod_kernel_launches": (C.c_uint64, [vp]),
         "vofod_stream": (vp, [vp]),
+        "vofod_set_option": (i32, [vp, i32, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = a symbol of include/vofod_cuda.h is missing
@@ -385,6 +386,9 @@ class Vofod:
 
     def kernel_launches(self):
         return int(self.lib.vofod_kernel_launches(self.h))
+
+    def set_option(self, option, value):
+        self._ck(self.lib.vofod_set_option(self.h, int(option), int(value)))
 
     def stream(self):
         return self.lib.vofod_stream(self.h)

@@ -107,7 +107,6 @@ __device__ void jacobi3_dev(const double Ain[3][3], double eval[3], double V[3][
 struct ClsArgs
 {
   Geom g;
-  float sensor[3];
   int min_points;
   double max_distance, max_size, max_explore_distance;
   float thr_frontiers, thr_new;
@@ -129,7 +128,7 @@ struct ClsArgs
 //     with the memory latency of the index indirection paid once per 32 points;
 //   n >  n_exact (cannot fit into max_size, so the class is `invalid` whatever the last bits are): lane-strided fp64
 //     partial sums + a fixed-shape warp reduction; the reported box agrees with the sequential fp32 one to ~1e-6.
-__global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
+__global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const ScanDyn* __restrict__ dyn, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
                                                      const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
                                                      vofod_cluster_info* __restrict__ out)
 {
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const vofo
     // gates (:1679-1690)
     if (n >= a.min_points)
     {
-      const float ddx = a.sensor[0] - ci.obb_center[0], ddy = a.sensor[1] - ci.obb_center[1], ddz = a.sensor[2] - ci.obb_center[2];
+      const float ddx = dyn->tf.t[0] - ci.obb_center[0], ddy = dyn->tf.t[1] - ci.obb_center[1], ddz = dyn->tf.t[2] - ci.obb_center[2];
       const double dist = (double)sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
       if (!(dist > a.max_distance))
       {
@@ -470,7 +469,7 @@ __global__ void __launch_bounds__(256) k_explore_single(const float* score, cons
 }
 
 // K14 + K15 — one block, sequential over clusters (see file header)
-__global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, float* score, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx,
+__global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const ScanDyn* __restrict__ dyn, float* score, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx,
                                                       const int* __restrict__ seg_start, vofod_cluster_info* __restrict__ infos, const ExploreWs w,
                                                       double* __restrict__ terms, vofod_detection* __restrict__ dets, unsigned long long* __restrict__ counters,
                                                       const unsigned long long* __restrict__ d_nfar)
@@ -582,7 +581,7 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, float* sc
     }
     if (tid == 0)
     {
-      const float ddx = a.sensor[0] - ci.obb_center[0], ddy = a.sensor[1] - ci.obb_center[1], ddz = a.sensor[2] - ci.obb_center[2];
+      const float ddx = dyn->tf.t[0] - ci.obb_center[0], ddy = dyn->tf.t[1] - ci.obb_center[1], ddz = dyn->tf.t[2] - ci.obb_center[2];
       const double det_dist = (double)sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
       vofod_detection d;
       memset(&d, 0, sizeof(d));
@@ -640,7 +639,7 @@ static int bits_for_u(unsigned long long v)
 }
 
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
-                           const vofod_pose& tf, const vofod_params& p)
+                           const vofod_params& p)
 {
   using namespace prims;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
@@ -688,8 +687,6 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
                                              m_cap, 0, 2 * bits, &okeys, nullptr)));
   ClsArgs a;
   a.g = ctx->g;
-  for (int k = 0; k < 3; k++)
-    a.sensor[k] = tf.t[k];
   a.min_points = p.cls_min_points;
   a.max_distance = p.cls_max_distance;
   a.max_size = p.cls_max_size;
@@ -714,7 +711,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
     if (a.n_exact < 64)
       a.n_exact = 64;
   }
-  LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap * 32, 256, 4), 256, 0, a, d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
+  LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap * 32, 256, 4), 256, 0, a, ctx->dyn.as<ScanDyn>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
          ctx->cl_info.as<vofod_cluster_info>());
   int* qbase = ctx->cls_queues.as<int>();
   ExploreWs w;
@@ -724,7 +721,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   w.explored = qbase + 2 * cube;
   w.side = side;
   w.rm = rmax;
-  LAUNCH(k_classify_seq, 1, 256, 0, a, ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w, ctx->cls_terms.as<double>(),
+  LAUNCH(k_classify_seq, 1, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w, ctx->cls_terms.as<double>(),
          ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS);
   return 0;
 }
@@ -797,7 +794,11 @@ extern "C" int vofod_classify_detect(vofod_ctx* ctx, const vofod_vox* pts, const
   CK(cudaMemcpyAsync(ctx->vox.p, pts, m * sizeof(vofod_vox), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->labels.p, labels, m * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->pt_close.p, point_in_close_cluster, m, cudaMemcpyHostToDevice, ctx->stream));
-  RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), nullptr, m, *tf, *p));
+  memcpy(ctx->h_dyn->tf.R, tf->R, sizeof(tf->R));
+  memcpy(ctx->h_dyn->tf.t, tf->t, sizeof(tf->t));
+  RET(vf_begin_call(ctx));
+  RET(vf_dyn_push(ctx));
+  RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), nullptr, m, *p));
   unsigned long long h[CNT_N_SLOTS];
   CK(cudaMemcpyAsync(h, ctx->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -5,9 +5,9 @@
 //   K4  spatial hash: cell pitch slightly above tol, open-addressing table keyed by the packed cell, one
 //       linked list of point indices per occupied cell
 //   K5  one warp per point (one lane per neighbouring cell) scans the 27 cells and unites the point with every lower-indexed point
-//       inside the radius (lock-free union-find, the larger root is always linked under the smaller one, so the
-//       root of a finished tree IS the minimum point index of the component = the canonical label)
-//   K5b flatten: labels[i] = root(i), per-root sizes, number of roots
+//       inside the radius (lock-free union-find with randomised linking)
+//   K5b roots + atomicMin of the point index per root; K5c labels[i] = min index of i's component (the canonical label),
+//       per-label sizes, number of components
 // Linked-list order is scheduling dependent; the partition and the labels are not.
 #include <math.h>
 
@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned cl_hash(unsigned long long k)
 __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz, const int stride, const unsigned long long* __restrict__ d_m, const size_t m_cap,
                                                    const double inv_cell, float4* __restrict__ pts, unsigned long long* __restrict__ tkey, int* __restrict__ thead,
                                                    const unsigned tmask, int* __restrict__ next, int* __restrict__ parent, int* __restrict__ sizes,
-                                                   unsigned long long* __restrict__ watchdog)
+                                                   int* __restrict__ minidx, unsigned long long* __restrict__ watchdog)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz
     pts[i] = make_float4(x, y, z, 0.f);
     parent[i] = (int)i;
     sizes[i] = 0;
+    minidx[i] = 0x7fffffff;
     if (inv_cell == 0.0)
     {
       next[i] = -1;
@@ -84,6 +85,11 @@ __device__ __forceinline__ int uf_find(int* __restrict__ parent, int a)
     a = p;
   }
 }
+// Linking by index (larger under smaller) degenerates on this input: the points arrive sorted by voxel key, every point's
+// first neighbour is its predecessor, and the forest becomes one chain per grid row (finds of hundreds of dependent L2
+// loads).  Link by a pseudo-random priority instead (expected depth O(log n)); the canonical min-index label is computed
+// afterwards with one atomicMin per point.
+__device__ __forceinline__ unsigned uf_prio(const int a) { return (unsigned)a * 2654435761u; }  // odd multiplier: a bijection on u32
 __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
 {
   while (true)
@@ -92,13 +98,13 @@ __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
     b = uf_find(parent, b);
     if (a == b)
       return;
-    if (a < b)
+    if (uf_prio(a) < uf_prio(b))
     {
       const int t = a;
       a = b;
       b = t;
     }
-    // a > b: hang root a under b
+    // prio(a) > prio(b): hang root a under b (parents always have the smaller priority => acyclic)
     const int old = atomicCAS(parent + a, a, b);
     if (old == a)
       return;
@@ -162,11 +168,11 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
   }
 }
 
-__global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __restrict__ d_m, const size_t m_cap, int* __restrict__ parent, int* __restrict__ labels,
-                                                    int* __restrict__ sizes, unsigned long long* __restrict__ d_ncl)
+// K5b: root of every point + minimum point index per root
+__global__ void __launch_bounds__(256) k_cl_roots(const unsigned long long* __restrict__ d_m, const size_t m_cap, int* __restrict__ parent, int* __restrict__ root,
+                                                  int* __restrict__ minidx)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
-  unsigned roots = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
   {
     int r = (int)i;
@@ -177,9 +183,23 @@ __global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __
         break;
       r = p;
     }
-    labels[i] = r;
-    atomicAdd(sizes + r, 1);
-    roots += (r == (int)i);
+    root[i] = r;
+    atomicMin(minidx + r, (int)i);
+  }
+}
+// K5c: canonical label = minimum point index of the component; per-label sizes; number of components
+__global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __restrict__ d_m, const size_t m_cap, const int* __restrict__ root,
+                                                    const int* __restrict__ minidx, int* __restrict__ labels, int* __restrict__ sizes,
+                                                    unsigned long long* __restrict__ d_ncl)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  unsigned roots = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int l = minidx[root[i]];
+    labels[i] = l;
+    atomicAdd(sizes + l, 1);
+    roots += (l == (int)i);
   }
   roots = prims::warp_sum(roots);
   if ((threadIdx.x & 31) == 0 && roots)
@@ -201,6 +221,8 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   ENSURE(ws.next, m_cap * 4);
   ENSURE(ws.parent, m_cap * 4);
   ENSURE(ws.sizes, m_cap * 4);
+  ENSURE(ws.root, m_cap * 4);
+  ENSURE(ws.minidx, m_cap * 4);
   CK(cudaMemsetAsync(ws.table_key.p, 0xFF, tsize * 8, ctx->stream));
   CK(cudaMemsetAsync(ws.table_head.p, 0xFF, tsize * 4, ctx->stream));
   // pcl: r^2 = tolerance * tolerance evaluated in double, narrowed to the float the kd-tree compares with
@@ -208,10 +230,11 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   // cell pitch a hair above tol: two points closer than tol in every axis always land in adjacent cells
   const double inv_cell = tol > 0.0f ? 1.0 / ((double)tol * (1.0 + 1e-6)) : 0.0;
   LAUNCH(k_cl_insert, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_xyz, stride_floats, d_m, m_cap, inv_cell, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(),
-         ws.table_head.as<int>(), (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>(), ws.sizes.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
+         ws.table_head.as<int>(), (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>(), ws.sizes.as<int>(), ws.minidx.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
   LAUNCH(k_cl_union, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), ws.table_head.as<int>(),
          (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>());
-  LAUNCH(k_cl_flatten, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.parent.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
+  LAUNCH(k_cl_roots, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
+  LAUNCH(k_cl_flatten, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;
 }
 

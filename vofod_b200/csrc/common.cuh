@@ -104,6 +104,21 @@ struct Pose33
   float t[3];
 };
 
+// Everything that changes from scan to scan and that kernels need.  It lives in device memory (ctx->dyn) and is refreshed
+// from a pinned host copy by ONE memcpy per call, so that the kernel arguments themselves are scan-invariant and a
+// whole scan can be replayed as a CUDA graph.
+struct ScanDyn
+{
+  Pose33 tf;                 // sensor -> world
+  Window win;                // raycast accumulator window of this scan
+  float range_pt[3];         // rangefinder seed point (A23)
+  int n_seeds;
+  const vofod_pt* scan;      // packed scan of this call (staging buffer or resident slot)
+  int its_raycast;           // detection_its_diff of the raycast apply
+  int pad;
+};
+#define EPOCH_STRIDE 64      // look-back launches per API call are numbered 0..63
+
 // Euclidean-cluster workspace handles (cluster.cu)
 struct ClusterWs
 {
@@ -112,7 +127,9 @@ struct ClusterWs
   DevBuf table_head; // i32 per slot
   DevBuf next;       // i32 per point
   DevBuf parent;     // i32 per point
-  DevBuf sizes;      // i32 per point (size of the cluster rooted here)
+  DevBuf sizes;      // i32 per point (size of the cluster labelled by this index)
+  DevBuf root;       // i32 per point
+  DevBuf minidx;     // i32 per point (min member index, valid at roots)
 };
 
 #define MAX_TILE_STATES (1 << 15)
@@ -164,7 +181,23 @@ struct vofod_ctx
   DevBuf d_counters;  // u32/u64 scratch counters (see enum below)
   DevBuf tile_state;  // u64 decoupled look-back states
   DevBuf sort_hist;   // u32 [passes][256]
-  uint32_t epoch = 1;
+  int epoch_local = 0;        // look-back launch number inside the current API call
+  uint64_t epoch_calls = 0;   // host mirror of CNT_EPOCH_BASE / EPOCH_STRIDE
+
+  // per-scan dynamic arguments
+  DevBuf dyn;                 // ScanDyn
+  ScanDyn* h_dyn = nullptr;   // pinned
+  size_t acc_cells_max = 0;
+
+  // CUDA-graph replay of vofod_process_scan
+  bool graph_enabled = true;
+  bool capturing = false;
+  bool capture_broken = false;
+  uint64_t alloc_gen = 0;
+  uint64_t graph_sig = 0, last_eager_sig = 0, last_eager_alloc_gen = ~0ull;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_kernels = 0;
+  size_t sep_cap = 0;         // capacity of the background-voxel list when sepclusters runs without a host round trip
 
   // clustering / per-scan products
   ClusterWs cl, cl_bg;
@@ -229,16 +262,21 @@ enum
   CNT_STATE_BG,       // m_background_pts_sufficient (vofod_nodelet.cpp:2323) — device-resident so classification needs no host round trip
   CNT_STATE_SURE,     // m_sure_background_sufficient
   CNT_DET_ID,         // m_last_detection_id
-  CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
   CNT_NFARPTS,
   CNT_SEP_NENT,
   CNT_SEP_NUNIQ,
-  CNT_N_SLOTS = 64
+  // ---- persistent slots (never zeroed by a map resize) ----
+  CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
+  CNT_EPOCH_BASE,     // generation base of the decoupled look-back states, advanced on the DEVICE once per API call (graph replay safe)
+  CNT_N_SLOTS = 64,
+  CNT_FIRST_PERSISTENT = CNT_EXPLORE_EPOCH
 };
 
 // ---- host helpers ----------------------------------------------------------------------------------
 int vf_fail(vofod_ctx* c, int code, const char* fmt, ...);
 int vf_ensure(vofod_ctx* c, DevBuf& b, size_t bytes);
+int vf_begin_call(vofod_ctx* ctx);  // advances the look-back generation; first thing of every entry point that sorts / scans
+int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
 #define CK(call)                                                                                         \
   do                                                                                                     \
   {                                                                                                      \
@@ -277,22 +315,23 @@ static inline unsigned long long* vf_cnt(vofod_ctx* c, int slot) { return c->d_c
 
 // ---- stage entry points shared between the staged C ABI and vofod_process_scan (device pointers) ----
 // voxelgrid.cu
-int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p);
+int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  // scan + pose come from ctx->dyn
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
                    int* d_labels, unsigned long long* d_ncl);
 // raycast.cu
-int vf_raycast_accumulate_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p);
+int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // scan comes from ctx->dyn
+int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // host only: OOB test + window -> h_dyn
 int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);
 int vf_raycast_expand(vofod_ctx* ctx, uint32_t* d_counts, float* d_lengths);
 // pipeline.cu
-int vf_range_update_dev(vofod_ctx* ctx, const float pt[3], const vofod_params& p, int repeats);
+int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p);  // point + repeat count come from ctx->dyn
 int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
 int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score,
                          float flag);
 int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out);
 // classify.cu
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
-                           const vofod_pose& tf, const vofod_params& p);
+                           const vofod_params& p);  // sensor position comes from ctx->dyn
 // sepclusters.cu
-int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap = 0);

@@ -28,6 +28,12 @@ int vf_ensure(vofod_ctx* ctx, DevBuf& b, size_t bytes)
     bytes = 256;
   if (b.cap >= bytes)
     return 0;
+  if (ctx->capturing)
+  {
+    ctx->capture_broken = true;  // an allocation cannot happen inside a stream capture: the caller falls back to the eager path
+    return vf_fail(ctx, VOFOD_E_STATE, "buffer growth during graph capture");
+  }
+  ctx->alloc_gen++;
   // grow geometrically for small buffers, exactly for large ones
   size_t want = bytes < (size_t(64) << 20) ? bytes + bytes / 2 : bytes;
   want = (want + 255) & ~size_t(255);
@@ -103,6 +109,14 @@ int vofod_create(int device, vofod_ctx** out)
     ctx->pinned = nullptr;
     cudaGetLastError();
   }
+  rc = vf_ensure(ctx, ctx->dyn, sizeof(ScanDyn) + 64);
+  if (rc < 0 || !ctx->pinned)
+  {
+    delete ctx;
+    return rc < 0 ? rc : vf_fail(nullptr, VOFOD_E_NOMEM, "cudaHostAlloc failed");
+  }
+  ctx->h_dyn = reinterpret_cast<ScanDyn*>((char*)ctx->pinned + 65536);
+  memset(ctx->h_dyn, 0, sizeof(ScanDyn));
   cudaStreamSynchronize(ctx->stream);
   *out = ctx;
   return VOFOD_OK;
@@ -122,9 +136,9 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
-                    &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
+                    &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
                     &ctx->far_keys_b, &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d,
                     &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets,
@@ -133,6 +147,8 @@ int vofod_destroy(vofod_ctx* ctx)
     free_buf(*b);
   for (int i = 0; i < VOFOD_SCAN_SLOTS; i++)
     free_buf(ctx->scan_slot[i]);
+  if (ctx->graph_exec)
+    cudaGraphExecDestroy(ctx->graph_exec);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   if (ctx->ev_ok)
@@ -150,6 +166,18 @@ int vofod_synchronize(vofod_ctx* ctx)
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return VOFOD_OK;
+}
+
+int vofod_set_option(vofod_ctx* ctx, int option, int value)
+{
+  if (!ctx)
+    return VOFOD_E_INVALID;
+  if (option == VOFOD_OPT_GRAPH)
+  {
+    ctx->graph_enabled = value != 0;
+    return VOFOD_OK;
+  }
+  return vf_fail(ctx, VOFOD_E_INVALID, "unknown option %d", option);
 }
 
 void* vofod_stream(vofod_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -194,6 +222,25 @@ void vofod_default_params(vofod_params* p)
 // ======================================================================================================
 // kernels
 // ======================================================================================================
+__global__ void k_begin_call(unsigned long long* __restrict__ counters) { counters[CNT_EPOCH_BASE] += EPOCH_STRIDE; }
+
+int vf_begin_call(vofod_ctx* ctx)
+{
+  ctx->epoch_local = 0;
+  ctx->epoch_calls++;
+  // the generation field of a look-back state has 30 bits: before it can repeat, forget every old state
+  if (((ctx->epoch_calls * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE && ctx->tile_state.p && !ctx->capturing)
+    CK(cudaMemsetAsync(ctx->tile_state.p, 0, ctx->tile_state.cap, ctx->stream));
+  LAUNCH(k_begin_call, 1, 1, 0, ctx->d_counters.as<unsigned long long>());
+  return 0;
+}
+
+int vf_dyn_push(vofod_ctx* ctx)
+{
+  CK(cudaMemcpyAsync(ctx->dyn.p, ctx->h_dyn, sizeof(ScanDyn), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
 __global__ void k_fill_f32(float* __restrict__ p, const float v, const size_t n)
 {
   const size_t n4 = n / 4;
@@ -363,45 +410,60 @@ __global__ void k_compact_count(const float* __restrict__ score, const Geom g, c
     colcnt[(size_t)x * g.st_size[1] + y] = cnt;  // x-major so that the scan runs in emission order
   }
 }
-// pass 2: emit
-__global__ void k_compact_emit(const float* __restrict__ score, const Geom g, const float thr, const int greater, const int metric, const uint32_t* __restrict__ coloff,
-                               vofod_xyzi* __restrict__ out, const size_t cap)
+// pass 2: emit.  Columns without a match (the vast majority) are skipped from their count alone; the others are read in
+// batches of 16 independent loads before the (order-preserving, hence serial) emission.
+__global__ void k_compact_emit(const float* __restrict__ score, const Geom g, const float thr, const int greater, const int metric, const uint32_t* __restrict__ colcnt,
+                               const uint32_t* __restrict__ coloff, vofod_xyzi* __restrict__ out, const size_t cap)
 {
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)g.st_size[0] * g.st_size[1];
+  const int sz = g.st_size[2];
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x)
   {
     const int x = c % g.st_size[0], y = c / g.st_size[0];
-    size_t o = coloff[(size_t)x * g.st_size[1] + y];
-    for (int z = 0; z < g.st_size[2]; z++)
+    const size_t t = (size_t)x * g.st_size[1] + y;
+    if (colcnt[t] == 0)
+      continue;
+    size_t o = coloff[t];
+    for (int z0 = 0; z0 < sz; z0 += 16)
     {
-      const float v = score[(size_t)c + (size_t)z * sxy];
-      if ((v > thr) == (greater != 0))
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        v[k] = (z0 + k < sz) ? score[(size_t)c + (size_t)(z0 + k) * sxy] : __int_as_float(0x7fc00000);
+#pragma unroll
+      for (int k = 0; k < 16; k++)
       {
-        if (o < cap)
+        if (z0 + k < sz && ((v[k] > thr) == (greater != 0)))
         {
-          vofod_xyzi p;
-          const int gx = x + g.st_lo[0], gy = y + g.st_lo[1], gz = z + g.st_lo[2];
-          if (metric)
+          if (o < cap)
           {
-            p.x = idx_to_coord1(gx, g.off[0], g.vs);
-            p.y = idx_to_coord1(gy, g.off[1], g.vs);
-            p.z = idx_to_coord1(gz, g.off[2], g.vs);
-          } else
-          {
-            p.x = (float)gx; p.y = (float)gy; p.z = (float)gz;
+            vofod_xyzi p;
+            const int gx = x + g.st_lo[0], gy = y + g.st_lo[1], gz = z0 + k + g.st_lo[2];
+            if (metric)
+            {
+              p.x = idx_to_coord1(gx, g.off[0], g.vs);
+              p.y = idx_to_coord1(gy, g.off[1], g.vs);
+              p.z = idx_to_coord1(gz, g.off[2], g.vs);
+            } else
+            {
+              p.x = (float)gx; p.y = (float)gy; p.z = (float)gz;
+            }
+            p.intensity = v[k];
+            out[o] = p;
           }
-          p.intensity = v;
-          out[o] = p;
+          o++;
         }
-        o++;
       }
     }
   }
 }
 
-// shared with sepclusters.cu
-int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total)
+// shared with sepclusters.cu.  Two modes:
+//   host_total != NULL : exact — one 8-byte read-back sizes the output (staged API, first scans)
+//   host_total == NULL : `cap` rows are reserved up front, no host round trip (graph replay); *d_total still receives the
+//                        true count, rows beyond cap are dropped and the caller must check d_total <= cap
+int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap)
 {
   const Geom& g = ctx->g;
   const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
@@ -409,15 +471,19 @@ int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevB
   ENSURE(ctx->sep_coloff, prims::padded(ncol) * sizeof(uint32_t));
   LAUNCH(k_compact_count, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, ctx->sep_colcnt.as<uint32_t>());
   RET(prims::scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncol, d_total));
-  // the emit capacity must be known on the host: one 8-byte read-back (the bg thread is not latency critical)
-  unsigned long long total = 0;
-  CK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  *host_total = (size_t)total;
-  ENSURE(out, prims::padded(total) * sizeof(vofod_xyzi));
-  if (total)
-    LAUNCH(k_compact_emit, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, metric, ctx->sep_coloff.as<uint32_t>(),
-           out.as<vofod_xyzi>(), (size_t)total);
+  if (host_total)
+  {
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *host_total = (size_t)total;
+    cap = (size_t)total;
+    if (total == 0)
+      return 0;
+  }
+  ENSURE(out, prims::padded(cap) * sizeof(vofod_xyzi));
+  LAUNCH(k_compact_emit, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, metric, ctx->sep_colcnt.as<uint32_t>(),
+         ctx->sep_coloff.as<uint32_t>(), out.as<vofod_xyzi>(), cap);
   return 0;
 }
 
@@ -443,9 +509,9 @@ static int map_alloc(vofod_ctx* ctx)
   ENSURE(ctx->flags, (size_t)n + 64);
   CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)n, ctx->stream));
   ctx->flags_full_dirty = false;
-  // every counter except the exploreToGround stamp generation (its visited cube keeps old stamps)
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, CNT_EXPLORE_EPOCH * sizeof(unsigned long long), ctx->stream));
-  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_EXPLORE_EPOCH + 1), 0, (CNT_N_SLOTS - CNT_EXPLORE_EPOCH - 1) * sizeof(unsigned long long), ctx->stream));
+  // every counter except the persistent generations (exploreToGround stamps, look-back states keep old values)
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, CNT_FIRST_PERSISTENT * sizeof(unsigned long long), ctx->stream));
+  ctx->alloc_gen++;
   ctx->win_valid = false;
   ctx->acc_has_data = false;
   ctx->map_ready = true;
@@ -695,7 +761,8 @@ int vofod_map_compact_over(vofod_ctx* ctx, float threshold, int greater_than, in
   if (!n)
     return vf_fail(ctx, VOFOD_E_INVALID, "n is NULL");
   size_t total = 0;
-  RET(vf_compact_over_dev(ctx, threshold, greater_than, metric, ctx->sep_raw, vf_cnt(ctx, CNT_SEP_K), &total));
+  RET(vf_begin_call(ctx));
+  RET(vf_compact_over_dev(ctx, threshold, greater_than, metric, ctx->sep_raw, vf_cnt(ctx, CNT_SEP_K), &total, 0));
   *n = total;
   if (total > cap || (!out && total))
     return vf_fail(ctx, VOFOD_E_CAPACITY, "compact_over: need capacity %zu", total);

@@ -8,10 +8,12 @@
 #include "prims.cuh"
 
 // ---- A23 rangefinder ground seed (vofod_nodelet.cpp:581-613) ----------------------------------------
-__global__ void k_range_update(float* __restrict__ score, const Geom g, const float x, const float y, const float z, const double score_point, const int repeats)
+__global__ void k_range_update(float* __restrict__ score, const Geom g, const ScanDyn* __restrict__ dyn, const double score_point)
 {
+  const float x = dyn->range_pt[0], y = dyn->range_pt[1], z = dyn->range_pt[2];
+  const int repeats = dyn->n_seeds;
   const int ix = coord_to_idx1(x, g.off[0], g.inv), iy = coord_to_idx1(y, g.off[1], g.inv), iz = coord_to_idx1(z, g.off[2], g.inv);
-  if (!in_limits_idx(g, ix, iy, iz))  // :599
+  if (repeats <= 0 || !in_limits_idx(g, ix, iy, iz))  // :599
     return;
   const long long ci = cell_index(g, ix, iy, iz);
   if (ci < 0)
@@ -22,11 +24,9 @@ __global__ void k_range_update(float* __restrict__ score, const Geom g, const fl
   score[ci] = m;
 }
 
-int vf_range_update_dev(vofod_ctx* ctx, const float pt[3], const vofod_params& p, int repeats)
+int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
 {
-  if (repeats <= 0)
-    return 0;
-  LAUNCH(k_range_update, 1, 1, 0, ctx->score.as<float>(), ctx->g, pt[0], pt[1], pt[2], p.score_point, repeats);
+  LAUNCH(k_range_update, 1, 1, 0, ctx->score.as<float>(), ctx->g, ctx->dyn.as<ScanDyn>(), p.score_point);
   return 0;
 }
 
@@ -240,7 +240,11 @@ int vofod_range_update(vofod_ctx* ctx, const float world_pt[3], const vofod_para
   NEED_MAP();
   if (!world_pt || !p)
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
-  RET(vf_range_update_dev(ctx, world_pt, *p, 1));
+  for (int a = 0; a < 3; a++)
+    ctx->h_dyn->range_pt[a] = world_pt[a];
+  ctx->h_dyn->n_seeds = 1;
+  RET(vf_dyn_push(ctx));
+  RET(vf_range_update_dev(ctx, *p));
   CK(cudaStreamSynchronize(ctx->stream));
   return VOFOD_OK;
 }
@@ -308,8 +312,115 @@ int vofod_upload_scan(vofod_ctx* ctx, int slot, const vofod_pt* scan, size_t n)
 }
 }  // extern "C"
 
-// classify.cu / sepclusters.cu read-back helpers
-int vf_classify_readback(vofod_ctx* ctx, vofod_detection* dets, size_t det_cap, size_t* n_dets, vofod_cluster_info* clusters, size_t cl_cap, size_t* n_far);
+// ======================================================================================================
+// vofod_process_scan: one scan of schedule S1
+// ======================================================================================================
+struct ScanPlan
+{
+  size_t n;
+  vofod_params p;
+  vofod_schedule s;
+  bool raycast_on;     // do_raycast && not paused && sensor inside the map
+  int raycast_status;  // VOFOD_OK / W_PAUSED / W_SENSOR_OOB as known on the host before launching
+  size_t sep_cap;      // 0 = exact sepclusters (host round trip inside), else capped list
+  bool timed;          // record the per-stage events
+};
+
+// Enqueues every device operation of one scan on ctx->stream.  Called directly (eager mode) or under stream capture
+// (graph mode): it must not synchronise, allocate or touch pageable host memory when plan.sep_cap != 0.
+static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_out, bool* applied_out)
+{
+  cudaStream_t st = ctx->stream;
+  const vofod_params& p = plan.p;
+  const vofod_schedule& s = plan.s;
+  const size_t n = plan.n;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  int e = 0;
+#define STAGE_EVENT()                         \
+  do                                          \
+  {                                           \
+    if (plan.timed)                           \
+      CK(cudaEventRecord(ctx->ev[e], st));    \
+    e++;                                      \
+  } while (0)
+  RET(vf_begin_call(ctx));
+  RET(vf_dyn_push(ctx));
+  STAGE_EVENT();
+  // rangefinder seeds (A23)
+  RET(vf_range_update_dev(ctx, p));
+  STAGE_EVENT();  // 0 "range"
+  // filterAndTransform (:928)
+  RET(vf_filter_voxelize_dev(ctx, n, p));
+  STAGE_EVENT();  // 1 "filtering"
+  // clusterCloud (:932)
+  ENSURE(ctx->labels, n * 4);
+  RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
+                     cnt + CNT_NCLUSTERS));
+  STAGE_EVENT();  // 2 "clusterization"
+  // findCloseFarClusters (:936)
+  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p));
+  STAGE_EVENT();  // 3 "close X far"
+  // updateVMaps (:946-949)
+  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 1, cnt + CNT_VG_M, n, (float)p.score_point, 2.0f));
+  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 0, cnt + CNT_VG_M, n, (float)p.score_unknown, 3.0f));
+  STAGE_EVENT();  // 4 "vmap update"
+  *applied_out = false;
+  if (plan.raycast_on)
+    RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
+  else
+  {
+    CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, st));
+    CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, st));
+    // the reference clears m_voxel_raycast before the sensor-in-map test (:1430-1432)
+    if (s.do_raycast && plan.raycast_status == VOFOD_W_SENSOR_OOB && ctx->acc_has_data && ctx->acc.p)
+    {
+      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, st));
+      ctx->acc_has_data = false;
+    }
+  }
+  STAGE_EVENT();  // 5 "raycasting"
+  if (plan.raycast_on)
+  {
+    const int rc = vf_raycast_apply_dev(ctx, 0, p);
+    if (rc < 0)
+      return rc;
+    *applied_out = rc == VOFOD_OK;
+  }
+  STAGE_EVENT();  // 6 raycast "vmap update"
+  CK(cudaMemsetAsync(cnt + CNT_NDET, 0, 8, st));
+  if (s.do_classify)
+    RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
+  STAGE_EVENT();  // 7 "classification" (+ 8 detections, fused)
+  STAGE_EVENT();
+  *sep_status_out = VOFOD_W_PAUSED;
+  CK(cudaMemsetAsync(cnt + CNT_SEP_K, 0, 8, st));
+  if (s.do_sepclusters)
+  {
+    const int rc = vf_sepclusters_dev(ctx, s.sep_its_diff, p, plan.sep_cap);
+    if (rc < 0)
+      return rc;
+    *sep_status_out = rc;
+  }
+  STAGE_EVENT();  // 9 "sep bg clusters"
+  // one read-back of every count (+ a bounded prefix of the detections) into pinned memory
+  CK(cudaMemcpyAsync(ctx->pinned, cnt, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+  if (s.do_classify && ctx->dets.p)
+    CK(cudaMemcpyAsync((char*)ctx->pinned + 4096, ctx->dets.p, 16 * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
+  STAGE_EVENT();  // 10 "readback"
+#undef STAGE_EVENT
+  return 0;
+}
+
+static uint64_t fnv1a(const void* data, size_t len, uint64_t h)
+{
+  const unsigned char* b = (const unsigned char*)data;
+  for (size_t i = 0; i < len; i++)
+  {
+    h ^= b[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
 
 static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p, const vofod_schedule& s, vofod_scan_result* res,
                             vofod_detection* dets, size_t det_cap)
@@ -319,89 +430,126 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   cudaStream_t st = ctx->stream;
-  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  int e = 0;
-  CK(cudaEventRecord(ctx->ev[e++], st));
-  // rangefinder seeds (A23)
-  RET(vf_range_update_dev(ctx, s.range_pt, p, s.n_range_seeds));
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 0 "range"
-  // filterAndTransform (:928)
-  RET(vf_filter_voxelize_dev(ctx, d_scan, n, tf, p));
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 1 "filtering"
-  // clusterCloud (:932)
-  ENSURE(ctx->labels, n * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
-                     cnt + CNT_NCLUSTERS));
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 2 "clusterization"
-  // findCloseFarClusters (:936)
-  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p));
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 3 "close X far"
-  // updateVMaps (:946-949)
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 1, cnt + CNT_VG_M, n, (float)p.score_point, 2.0f));
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 0, cnt + CNT_VG_M, n, (float)p.score_unknown, 3.0f));
-  ctx->detection_its++;
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 4 "vmap update"
-  int raycast_status = VOFOD_W_PAUSED;
-  bool applied = false;
+  ScanPlan plan;
+  plan.n = n;
+  plan.p = p;
+  plan.s = s;
+  plan.raycast_status = VOFOD_W_PAUSED;
+  plan.raycast_on = false;
   if (s.do_raycast)
   {
-    raycast_status = vf_raycast_accumulate_dev(ctx, d_scan, n, tf, p);
-    if (raycast_status < 0)
-      return raycast_status;
+    plan.raycast_status = vf_raycast_prepare(ctx, n, tf, p);  // host only; fills h_dyn->win
+    if (plan.raycast_status < 0)
+      return plan.raycast_status;
+    plan.raycast_on = plan.raycast_status == VOFOD_OK;
   }
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 5 "raycasting"
-  if (s.do_raycast && raycast_status == VOFOD_OK)
-  {
-    const int rc = vf_raycast_apply_dev(ctx, s.raycast_its_diff > 1 ? s.raycast_its_diff : 1, p);
-    if (rc < 0)
-      return rc;
-    if (rc == VOFOD_OK)
-      applied = true;
-    else
-      raycast_status = rc;
-  }
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 6 raycast "vmap update"
-  CK(cudaMemsetAsync(cnt + CNT_NDET, 0, 8, st));
-  ctx->last_far = 0;
-  if (s.do_classify)
-    RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, tf, p));
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 7 "classification" (+ 8 detections, fused)
-  CK(cudaEventRecord(ctx->ev[e++], st));
+  // per-scan dynamic arguments
+  ScanDyn* hd = ctx->h_dyn;
+  memcpy(hd->tf.R, tf.R, sizeof(tf.R));
+  memcpy(hd->tf.t, tf.t, sizeof(tf.t));
+  for (int a = 0; a < 3; a++)
+    hd->range_pt[a] = s.range_pt[a];
+  hd->n_seeds = s.n_range_seeds > 0 ? s.n_range_seeds : 0;
+  hd->scan = d_scan;
+  hd->its_raycast = s.raycast_its_diff > 1 ? s.raycast_its_diff : 1;
+
+  // ---- signature of the launch sequence: everything by-value or host-decided that enqueue_scan depends on
+  uint64_t sig = 1469598103934665603ull;
+  sig = fnv1a(&p, sizeof(p), sig);
+  const int flags[8] = {s.do_raycast, s.do_classify, s.do_sepclusters, s.sep_its_diff, plan.raycast_on ? 1 : 0, plan.raycast_status, ctx->flags_full_dirty ? 1 : 0,
+                        ctx->acc_has_data ? 1 : 0};
+  sig = fnv1a(flags, sizeof(flags), sig);
+  sig = fnv1a(&n, sizeof(n), sig);
+  sig = fnv1a(&ctx->g, sizeof(ctx->g), sig);
+  sig = fnv1a(&ctx->acc_cells_max, sizeof(size_t), sig);
+  sig = fnv1a(&ctx->frac_bits, sizeof(int), sig);
+  sig = fnv1a(&ctx->sep_cap, sizeof(size_t), sig);
+  sig = fnv1a(&ctx->alloc_gen, sizeof(uint64_t), sig);
+
   int sep_status = VOFOD_W_PAUSED;
-  if (s.do_sepclusters)
+  bool applied = false;
+  bool used_graph = false;
+  const bool epoch_wrap_soon = (((ctx->epoch_calls + 1) * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE;
+  const bool graph_ok = ctx->graph_enabled && !epoch_wrap_soon && (!s.do_sepclusters || p.sep_pause || ctx->sep_cap > 0);
+  CK(cudaEventRecord(ctx->ev[0], st));
+  if (graph_ok && ctx->graph_exec && ctx->graph_sig == sig)
   {
-    sep_status = vf_sepclusters_dev(ctx, s.sep_its_diff, p);
-    if (sep_status < 0)
-      return sep_status;
-  }
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 9 "sep bg clusters"
-  // one read-back of every count
-  unsigned long long h[CNT_N_SLOTS];
-  unsigned long long* hp = ctx->pinned ? (unsigned long long*)ctx->pinned : h;
-  CK(cudaMemcpyAsync(hp, cnt, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, st));
-  size_t nd_cap = 0;
-  vofod_detection* hdets = nullptr;
-  if (s.do_classify && dets && det_cap)
+    // ---- replay
+    ctx->epoch_calls++;
+    CK(cudaGraphLaunch(ctx->graph_exec, st));
+    ctx->n_launches += ctx->graph_kernels;
+    sep_status = (s.do_sepclusters && !p.sep_pause) ? VOFOD_OK : VOFOD_W_PAUSED;
+    applied = plan.raycast_on;
+    ctx->acc_has_data = plan.raycast_on ? !p.raycast_new_update_rule : ctx->acc_has_data;
+    used_graph = true;
+  } else if (graph_ok && ctx->last_eager_sig == sig && ctx->last_eager_alloc_gen == ctx->alloc_gen)
   {
-    // detections are few: copy a bounded prefix speculatively with the counters, the rest (rare) afterwards
-    nd_cap = det_cap < 16 ? det_cap : 16;
-    if (ctx->pinned && ctx->dets.p)
+    // ---- second identical eager scan without any allocation in between: capture, instantiate, launch
+    plan.sep_cap = ctx->sep_cap;
+    plan.timed = false;
+    const bool acc_before = ctx->acc_has_data;
+    const uint64_t calls_before = ctx->epoch_calls;
+    const uint64_t launches_before = ctx->n_launches;
+    cudaGraph_t graph = nullptr;
+    ctx->capturing = true;
+    ctx->capture_broken = false;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int erc = ce == cudaSuccess ? enqueue_scan(ctx, plan, &sep_status, &applied) : -1;
+    if (ce == cudaSuccess)
+      ce = cudaStreamEndCapture(st, &graph);
+    ctx->capturing = false;
+    cudaGraphExec_t exec = nullptr;
+    if (erc == 0 && ce == cudaSuccess && graph && !ctx->capture_broken && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
     {
-      hdets = (vofod_detection*)((char*)ctx->pinned + 4096);
-      CK(cudaMemcpyAsync(hdets, ctx->dets.p, nd_cap * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
+      if (ctx->graph_exec)
+        cudaGraphExecDestroy(ctx->graph_exec);
+      ctx->graph_exec = exec;
+      ctx->graph_sig = sig;
+      ctx->graph_kernels = ctx->n_launches - launches_before;
+      cudaGraphDestroy(graph);
+      CK(cudaGraphLaunch(ctx->graph_exec, st));
+      used_graph = true;
+    } else
+    {
+      // capture failed: forget it and run this scan eagerly
+      if (graph)
+        cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->acc_has_data = acc_before;
+      ctx->epoch_calls = calls_before;
+      ctx->n_launches = launches_before;
+      ctx->last_eager_sig = 0;
+      ctx->err.clear();
     }
   }
-  CK(cudaEventRecord(ctx->ev[e++], st));                         // 10 "readback"
+  if (!used_graph)
+  {
+    // ---- eager
+    plan.sep_cap = (graph_ok && ctx->sep_cap > 0) ? ctx->sep_cap : 0;
+    plan.timed = true;
+    const uint64_t gen_before = ctx->alloc_gen;
+    RET(enqueue_scan(ctx, plan, &sep_status, &applied));
+    ctx->last_eager_sig = (gen_before == ctx->alloc_gen) ? sig : 0;
+    ctx->last_eager_alloc_gen = ctx->alloc_gen;
+  }
+  ctx->detection_its++;
+  CK(cudaEventRecord(ctx->ev[11], st));
   CK(cudaStreamSynchronize(st));
-  for (int i = 0; i < 11; i++)
-    cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
+  if (!used_graph)
+    for (int i = 0; i < 11; i++)
+      cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
   cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[11]);
+
+  const unsigned long long* hp = (const unsigned long long*)ctx->pinned;
+  const vofod_detection* hdets = (const vofod_detection*)((const char*)ctx->pinned + 4096);
   if (hp[CNT_WATCHDOG])
     return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", hp[CNT_WATCHDOG]);
   if (hp[CNT_OOB])
     return vf_fail(ctx, VOFOD_E_INTERNAL, "%llu traversals fell outside the accumulator window", hp[CNT_OOB]);
   if (hp[CNT_VG_OVERFLOW])
     return vf_fail(ctx, VOFOD_E_OVERFLOW, "leaf size too small for the input: integer indices would overflow");
+  int raycast_status = plan.raycast_status;
   if (applied)
   {
     if (hp[CNT_APPLY_ANY])
@@ -409,16 +557,41 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     else
       raycast_status = VOFOD_W_EMPTY_RAYCAST;
   }
+  bool sure_flag = hp[CNT_STATE_SURE] != 0;
+  if (s.do_sepclusters && !p.sep_pause)
+  {
+    const size_t K = (size_t)hp[CNT_SEP_K];
+    if (plan.sep_cap > 0)
+    {
+      if (K > plan.sep_cap)
+      {
+        // the capped list overflowed: the pass did not touch the map; redo it exactly, and grow the list for the next scans
+        RET(vf_begin_call(ctx));
+        sep_status = vf_sepclusters_dev(ctx, s.sep_its_diff, p, 0);
+        if (sep_status < 0)
+          return sep_status;
+        unsigned long long sure = 0;
+        CK(cudaMemcpyAsync(&sure, vf_cnt(ctx, CNT_STATE_SURE), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        sure_flag = sure != 0;
+      } else if (K == 0)
+        sep_status = VOFOD_W_EMPTY;
+      if (hp[CNT_SEP_NUNIQ])
+        return vf_fail(ctx, VOFOD_E_OVERFLOW, "sepclusters: voxel-grid index overflow");
+    }
+    // keep the list comfortably larger than what the map currently holds (a change re-captures the graph)
+    if (K * 5 / 4 + 1024 > ctx->sep_cap)
+      ctx->sep_cap = K * 2 + 65536;
+  }
   ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
-  ctx->sure_background_sufficient = hp[CNT_STATE_SURE] != 0;
+  ctx->sure_background_sufficient = sure_flag;
   ctx->last_detection_id = (uint32_t)hp[CNT_DET_ID];
   ctx->last_m = (size_t)hp[CNT_VG_M];
   const size_t n_det = s.do_classify ? (size_t)hp[CNT_NDET] : 0;
-  if (s.do_classify)
-    ctx->last_far = (size_t)hp[CNT_NFARPTS];
+  ctx->last_far = s.do_classify ? (size_t)hp[CNT_NFARPTS] : 0;
   if (res)
   {
-    res->n_traversals = s.do_raycast ? hp[CNT_TRAVERSALS] : 0;
+    res->n_traversals = plan.raycast_on ? hp[CNT_TRAVERSALS] : 0;
     res->n_bg = hp[CNT_NBG];
     res->n_filtered = (uint32_t)hp[CNT_VG_NVALID];
     res->n_voxels = (uint32_t)hp[CNT_VG_M];
@@ -434,7 +607,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (n_det && dets)
   {
     const size_t k = n_det < det_cap ? n_det : det_cap;
-    if (hdets && k <= nd_cap)
+    if (k <= 16)
       memcpy(dets, hdets, k * sizeof(vofod_detection));
     else
     {

@@ -115,10 +115,12 @@ __device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const
 // ---- exclusive scan of u32 ------------------------------------------------------------------------------
 // out[i] = sum_{j<i} in[j]; *total (u64, may be null) = sum of all.  in/out may alias.  Buffers must be padded to TILE.
 static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const unsigned long long* d_n, const size_t cap,
-                                                      unsigned long long* state, const uint32_t epoch, unsigned long long* total, unsigned long long* watchdog)
+                                                      unsigned long long* state, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local, unsigned long long* total,
+                                                      unsigned long long* watchdog)
 {
   __shared__ uint32_t ws[NT / 32];
   __shared__ uint32_t s_base;
+  const uint32_t epoch = (uint32_t)(*epoch_base + epoch_local) & 0x3fffffffu;
   const size_t n = dev_count(d_n, cap);
   const int n_tiles = (int)((n + TILE - 1) / TILE);
   if (n_tiles == 0)
@@ -190,8 +192,10 @@ __global__ void __launch_bounds__(NT) k_radix_hist(const KeyT* __restrict__ keys
 template <class KeyT, bool HAS_VAL>
 __global__ void __launch_bounds__(NT) k_radix_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                    const unsigned long long* d_n, const size_t cap, const uint32_t* __restrict__ hist_pass,
-                                                   unsigned long long* state, const uint32_t epoch, const int shift, unsigned long long* watchdog)
+                                                   unsigned long long* state, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local, const int shift,
+                                                   unsigned long long* watchdog)
 {
+  const uint32_t epoch = (uint32_t)(*epoch_base + epoch_local) & 0x3fffffffu;
   __shared__ uint32_t wcnt[NT / 32][256];
   __shared__ uint32_t gbase[256];
   __shared__ uint32_t dbase[256];
@@ -282,8 +286,10 @@ static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* ou
 {
   const size_t tiles = (cap + TILE - 1) / TILE + 1;
   ENSURE(ctx->tile_state, tiles * 256 * sizeof(unsigned long long));
-  const uint32_t epoch = (ctx->epoch++) & 0x3fffffffu;
-  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, ctx->tile_state.as<unsigned long long>(), epoch, d_total, vf_cnt(ctx, CNT_WATCHDOG));
+  if (ctx->epoch_local >= EPOCH_STRIDE)
+    return vf_fail(ctx, VOFOD_E_INTERNAL, "more than %d look-back launches in one call", EPOCH_STRIDE);
+  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, ctx->tile_state.as<unsigned long long>(), vf_cnt(ctx, CNT_EPOCH_BASE),
+         (uint32_t)(ctx->epoch_local++), d_total, vf_cnt(ctx, CNT_WATCHDOG));
   return 0;
 }
 
@@ -307,9 +313,10 @@ static inline int radix_sort(vofod_ctx* ctx, KeyT* a, KeyT* b, uint32_t* va, uin
   uint32_t* vout = vb;
   for (int p = 0; p < passes; p++)
   {
-    const uint32_t epoch = (ctx->epoch++) & 0x3fffffffu;
+    if (ctx->epoch_local >= EPOCH_STRIDE)
+      return vf_fail(ctx, VOFOD_E_INTERNAL, "more than %d look-back launches in one call", EPOCH_STRIDE);
     LAUNCH((k_radix_pass<KeyT, HAS_VAL>), persistent_grid(ctx, cap), NT, 0, kin, kout, vin, vout, d_n, cap, hist + p * 256,
-           ctx->tile_state.as<unsigned long long>(), epoch, begin_bit + 8 * p, vf_cnt(ctx, CNT_WATCHDOG));
+           ctx->tile_state.as<unsigned long long>(), vf_cnt(ctx, CNT_EPOCH_BASE), (uint32_t)(ctx->epoch_local++), begin_bit + 8 * p, vf_cnt(ctx, CNT_WATCHDOG));
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

@@ -20,8 +20,6 @@
 struct RayArgs
 {
   Geom g;
-  Window w;
-  Pose33 tf;
   float max_dist, min_intensity;
   float scale;  // 2^F
   int n;
@@ -34,12 +32,15 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsi
 }
 
 template <bool AGGREGATE>
-__global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, const vofod_pt* __restrict__ scan, const float4* __restrict__ lut_dir,
+__global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                             const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                             unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
 {
   // stage this block's 256 packed points (20 B each) through shared memory with coalesced 16 B loads
   __shared__ __align__(16) uint32_t s_pts[256 * 5];
+  const vofod_pt* __restrict__ scan = dyn->scan;
+  const Pose33 tf = dyn->tf;
+  const Window w = dyn->win;
   const int blk_first = blockIdx.x * 256;
   {
     const int n_here = min(256, a.n - blk_first);
@@ -70,19 +71,19 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
       alive = false;
     const float4 d1 = __ldg(lut_dir + idx);
     // Eigen 3x3*3 coefficient product: r_i = R_i0*v0 + (R_i1*v1 + R_i2*v2)   (:1453)
-    const float dx = a.tf.R[0] * d1.x + (a.tf.R[1] * d1.y + a.tf.R[2] * d1.z);
-    const float dy = a.tf.R[3] * d1.x + (a.tf.R[4] * d1.y + a.tf.R[5] * d1.z);
-    const float dz = a.tf.R[6] * d1.x + (a.tf.R[7] * d1.y + a.tf.R[8] * d1.z);
+    const float dx = tf.R[0] * d1.x + (tf.R[1] * d1.y + tf.R[2] * d1.z);
+    const float dy = tf.R[3] * d1.x + (tf.R[4] * d1.y + tf.R[5] * d1.z);
+    const float dz = tf.R[6] * d1.x + (tf.R[7] * d1.y + tf.R[8] * d1.z);
     const float ray_dist = 0.001f * (float)range;                                             // :1456
     const float dmv = ray_dist - a.g.vs;
     len = ray_dist == 0.0f ? a.max_dist : (a.max_dist < dmv ? a.max_dist : dmv);              // :1457 (std::min)
-    float sx = a.tf.t[0], sy = a.tf.t[1], sz = a.tf.t[2];
+    float sx = tf.t[0], sy = tf.t[1], sz = tf.t[2];
     if (a.has_off)
     {
       const float4 o1 = __ldg(lut_off + idx);
-      sx = (a.tf.R[0] * o1.x + (a.tf.R[1] * o1.y + a.tf.R[2] * o1.z)) + a.tf.t[0];            // :1477
-      sy = (a.tf.R[3] * o1.x + (a.tf.R[4] * o1.y + a.tf.R[5] * o1.z)) + a.tf.t[1];
-      sz = (a.tf.R[6] * o1.x + (a.tf.R[7] * o1.y + a.tf.R[8] * o1.z)) + a.tf.t[2];
+      sx = (tf.R[0] * o1.x + (tf.R[1] * o1.y + tf.R[2] * o1.z)) + tf.t[0];            // :1477
+      sy = (tf.R[3] * o1.x + (tf.R[4] * o1.y + tf.R[5] * o1.z)) + tf.t[1];
+      sz = (tf.R[6] * o1.x + (tf.R[7] * o1.y + tf.R[8] * o1.z)) + tf.t[2];
     }
     cx = coord_to_idx1(sx, a.g.off[0], a.g.inv);
     cy = coord_to_idx1(sy, a.g.off[1], a.g.inv);
@@ -109,9 +110,9 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
     if (!(0.0f < len))  // while (prev_dist < length) with prev_dist = 0
       alive = false;
   }
-  const int wsx = a.w.size[0];
-  const long long wsxy = (long long)a.w.size[0] * a.w.size[1];
-  const long long wn = wsxy * a.w.size[2];
+  const int wsx = w.size[0];
+  const long long wsxy = (long long)w.size[0] * w.size[1];
+  const long long wn = wsxy * w.size[2];
   float prev = 0.0f;
   unsigned steps = 0;
   unsigned oob = 0;
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
       const float ddist = (len < dist ? len : dist) - prev;                                   // voxel_map.cpp:252
       const int q = __float2int_rn(ddist * a.scale);
       // window cell of the current voxel
-      const int wx = cx - a.w.lo[0], wy = cy - a.w.lo[1], wz = cz - a.w.lo[2];
-      const bool inside = wx >= 0 && wx < a.w.size[0] && wy >= 0 && wy < a.w.size[1] && wz >= 0 && wz < a.w.size[2];
+      const int wx = cx - w.lo[0], wy = cy - w.lo[1], wz = cz - w.lo[2];
+      const bool inside = wx >= 0 && wx < w.size[0] && wy >= 0 && wy < w.size[1] && wz >= 0 && wz < w.size[2];
       widx = inside ? ((long long)wx + (long long)wy * wsx + (long long)wz * wsxy) : (wn + lane);
       if (AGGREGATE)
       {
@@ -189,10 +190,8 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
 struct ApplyArgs
 {
   Geom g;
-  Window w;
   float inv_scale_unused;
   double inv_scale;       // 2^-F
-  float its;              // detection_its_diff as float (:1539)
   float ray_score;        // :1553
   float weighting_factor; // :1556 (new rule)
   float ray_weight;       // :1554 (old rule)
@@ -201,8 +200,9 @@ struct ApplyArgs
 };
 
 // max_element of the accumulator (:1542) — only needed by the old update rule
-__global__ void __launch_bounds__(256) k_raycast_max(const Window w, const unsigned long long* __restrict__ acc, const double inv_scale, unsigned* __restrict__ out_bits)
+__global__ void __launch_bounds__(256) k_raycast_max(const ScanDyn* __restrict__ dyn, const unsigned long long* __restrict__ acc, const double inv_scale, unsigned* __restrict__ out_bits)
 {
+  const Window w = dyn->win;
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
   float mx = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -223,12 +223,14 @@ __global__ void __launch_bounds__(256) k_raycast_max(const Window w, const unsig
     atomicMax(out_bits, __float_as_uint(mx));  // positive floats order like their bit patterns
 }
 
-__global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, unsigned long long* __restrict__ acc, float* __restrict__ score,
+__global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const ScanDyn* __restrict__ dyn, unsigned long long* __restrict__ acc, float* __restrict__ score,
                                                        const uint8_t* __restrict__ flags, const unsigned* __restrict__ max_bits,
                                                        unsigned long long* __restrict__ counters)
 {
-  const long long n = (long long)a.w.size[0] * a.w.size[1] * a.w.size[2];
-  const int wsx = a.w.size[0], wsy = a.w.size[1];
+  const Window w = dyn->win;
+  const float its = (float)dyn->its_raycast;  // detection_its_diff as float (:1539)
+  const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
+  const int wsx = w.size[0], wsy = w.size[1];
   float max_val = 0.f;
   if (!a.new_rule)
   {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, unsign
       continue;
     any = true;
     const int wx = (int)(i % wsx), wy = (int)((i / wsx) % wsy), wz = (int)(i / ((long long)wsx * wsy));
-    const long long ci = cell_index(a.g, wx + a.w.lo[0], wy + a.w.lo[1], wz + a.w.lo[2]);
+    const long long ci = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
     if (ci < 0 || flags[ci] != 0)  // flag == m_vflags_unmarked (:1561)
       continue;
     const float m = score[ci];
@@ -259,12 +261,12 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, unsign
     if (a.new_rule)
     {
       const float n_int = a.weighting_factor * rv;                    // :1565
-      w1 = (float)exp2((double)(-a.its * n_int));                     // :1567  std::pow(2, float) -> double pow
+      w1 = (float)exp2((double)(-its * n_int));                     // :1567  std::pow(2, float) -> double pow
     } else
     {
       const float norm_val = rv / max_val;                            // :1587
       const float ws = a.ray_weight * sqrtf(norm_val);                // :1591
-      w1 = powf(1.0f - ws, a.its);                                    // :1593
+      w1 = powf(1.0f - ws, its);                                    // :1593
       w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);                // std::clamp
     }
     const float w2 = 1.0f - w1;
@@ -354,12 +356,30 @@ int vf_raycast_expand(vofod_ctx* ctx, uint32_t* d_counts, float* d_lengths)
   return 0;
 }
 
-// window = voxels that can be reached from the sensor within max_dist (+ LUT offsets), clamped to the held box
-static int setup_window(vofod_ctx* ctx, const vofod_pose& tf, const float max_dist)
+// Host-side preparation of a raycast (no launches): the sensor-in-map test of vofod_nodelet.cpp:1432 and the accumulator
+// window = voxels that can be reached from the sensor within max_dist (+ LUT offsets), clamped to the held box.  Writes the
+// window into ctx->h_dyn (the caller pushes h_dyn to the device before any kernel of the call runs).
+// Returns VOFOD_OK, VOFOD_W_PAUSED or VOFOD_W_SENSOR_OOB.
+int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p)
 {
+  if (p.raycast_pause)
+    return VOFOD_W_PAUSED;
+  if (!ctx->W || n != (size_t)ctx->W * ctx->H)
+    return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   const Geom& g = ctx->g;
+  const float max_dist = (float)p.raycast_max_distance;
+  // sensor out of bounds => no raycast (:1432,1523-1526)
+  for (int a = 0; a < 3; a++)
+  {
+    volatile float d = tf.t[a] - g.off[a];
+    volatile float q = d * g.inv;
+    const int c = (int)floorf(q);
+    if (c < 0 || c >= g.size[a])
+      return VOFOD_W_SENSOR_OOB;
+  }
   Window w;
   const float reach = max_dist + ctx->lut_max_off;
+  size_t wn_max = 1;
   for (int a = 0; a < 3; a++)
   {
     const int c = (int)floorf((tf.t[a] - g.off[a]) * g.inv);
@@ -371,75 +391,54 @@ static int setup_window(vofod_ctx* ctx, const vofod_pose& tf, const float max_di
     if (hi <= lo) { lo = blo; hi = blo + 1; }
     w.lo[a] = lo;
     w.size[a] = hi - lo;
+    const int full = 2 * r + 1 < g.st_size[a] ? 2 * r + 1 : g.st_size[a];
+    wn_max *= (size_t)full;
   }
-  const size_t wn = (size_t)w.size[0] * w.size[1] * w.size[2];
-  const bool same = ctx->win_valid && memcmp(&w, &ctx->win, sizeof(Window)) == 0;
-  if (!same)
+  // sized for the largest window this max_dist can produce, so that the buffer (and the launch grids) never change
+  if (ctx->acc.cap < (wn_max + 32) * 8)
   {
-    // the accumulator is all-zero between scans (apply zeroes what it reads), so a moved window needs no clearing
-    // unless an accumulate was never applied
-    const size_t old_n = ctx->win_valid ? (size_t)ctx->win.size[0] * ctx->win.size[1] * ctx->win.size[2] : 0;
-    if (ctx->acc.cap < (wn + 32) * 8)
-    {
-      ENSURE(ctx->acc, (wn + 32) * 8);  // fresh allocations are zero-filled
-    } else if (ctx->acc_has_data && old_n)
-      CK(cudaMemsetAsync(ctx->acc.p, 0, old_n * 8, ctx->stream));
-    ctx->win = w;
-    ctx->win_valid = true;
+    ENSURE(ctx->acc, (wn_max + 32) * 8);  // fresh allocations are zero-filled
     ctx->acc_has_data = false;
   }
-  return 0;
+  ctx->acc_cells_max = wn_max;
+  ctx->win = w;
+  ctx->win_valid = true;
+  ctx->h_dyn->win = w;
+  ctx->frac_bits = choose_frac_bits(n, ctx->g.vs);
+  return VOFOD_OK;
 }
 
-int vf_raycast_accumulate_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p)
+int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p)
 {
-  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_TRAVERSALS), 0, 8, ctx->stream));
-  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_OOB), 0, 8, ctx->stream));
-  if (p.raycast_pause)
-    return VOFOD_W_PAUSED;
-  if (!ctx->W || n != (size_t)ctx->W * ctx->H)
-    return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
-  const float max_dist = (float)p.raycast_max_distance;
-  // m_voxel_raycast.clear() (:1430): a previous accumulate that was never applied must not leak into this one
-  if (ctx->win_valid && ctx->acc_has_data)
+  (void)tf;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, ctx->stream));
+  // m_voxel_raycast.clear() (:1430): an accumulate that was never applied (or an old-rule apply that bailed out on
+  // max_val == 0) must not leak into this one.  After a new-rule apply the accumulator is already all zero.
+  if (ctx->acc_has_data)
   {
-    const size_t old_n = (size_t)ctx->win.size[0] * ctx->win.size[1] * ctx->win.size[2];
-    CK(cudaMemsetAsync(ctx->acc.p, 0, old_n * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, ctx->stream));
     ctx->acc_has_data = false;
   }
-  // sensor out of bounds => no raycast (:1432,1523-1526)
-  {
-    const Geom& g = ctx->g;
-    for (int a = 0; a < 3; a++)
-    {
-      volatile float d = tf.t[a] - g.off[a];
-      volatile float q = d * g.inv;
-      const int c = (int)floorf(q);
-      if (c < 0 || c >= g.size[a])
-        return VOFOD_W_SENSOR_OOB;
-    }
-  }
-  RET(setup_window(ctx, tf, max_dist));
-  ctx->frac_bits = choose_frac_bits(n, ctx->g.vs);
   RayArgs a;
   a.g = ctx->g;
-  a.w = ctx->win;
-  memcpy(a.tf.R, tf.R, sizeof(a.tf.R));
-  memcpy(a.tf.t, tf.t, sizeof(a.tf.t));
-  a.max_dist = max_dist;
+  a.max_dist = (float)p.raycast_max_distance;
   a.min_intensity = (float)p.raycast_min_intensity;
   a.scale = ldexpf(1.0f, ctx->frac_bits);
   a.n = (int)n;
   a.has_off = ctx->lut_has_off ? 1 : 0;
   const int blocks = (int)((n + 255) / 256);
-  LAUNCH((k_raycast_accumulate<true>), blocks, 256, 0, a, d_scan, ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
-         ctx->acc.as<unsigned long long>(), ctx->d_counters.as<unsigned long long>());
+  LAUNCH((k_raycast_accumulate<true>), blocks, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
+         ctx->acc.as<unsigned long long>(), cnt);
   ctx->acc_has_data = true;
   return VOFOD_OK;
 }
 
+// its_diff comes from ctx->dyn (its_raycast)
 int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
 {
+  (void)its_diff;
   if (p.raycast_pause)
     return VOFOD_W_PAUSED;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
@@ -449,10 +448,8 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
     return VOFOD_W_EMPTY_RAYCAST;  // max_val == 0 (:1544-1548): nothing applied, flags NOT cleared
   ApplyArgs a;
   a.g = ctx->g;
-  a.w = ctx->win;
   a.inv_scale_unused = 0.f;
   a.inv_scale = ldexp(1.0, -ctx->frac_bits);
-  a.its = (float)its_diff;
   a.ray_score = (float)p.score_ray;
   a.ray_weight = (float)p.raycast_weight_coefficient;
   {
@@ -462,10 +459,11 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   }
   a.max_val = 0.f;
   a.new_rule = p.raycast_new_update_rule ? 1 : 0;
-  const size_t wn = (size_t)ctx->win.size[0] * ctx->win.size[1] * ctx->win.size[2];
+  const size_t wn = ctx->acc_cells_max;  // grid sized for the largest window: identical launches from scan to scan
+  const ScanDyn* dyn = ctx->dyn.as<ScanDyn>();
   if (!a.new_rule)
-    LAUNCH(k_raycast_max, vf_blocks(ctx, wn, 256), 256, 0, ctx->win, ctx->acc.as<unsigned long long>(), a.inv_scale, (unsigned*)(cnt + CNT_MAXVAL));
-  LAUNCH(k_raycast_apply, vf_blocks(ctx, wn, 256), 256, 0, a, ctx->acc.as<unsigned long long>(), ctx->score.as<float>(), ctx->flags.as<uint8_t>(),
+    LAUNCH(k_raycast_max, vf_blocks(ctx, wn, 256), 256, 0, dyn, ctx->acc.as<unsigned long long>(), a.inv_scale, (unsigned*)(cnt + CNT_MAXVAL));
+  LAUNCH(k_raycast_apply, vf_blocks(ctx, wn, 256), 256, 0, a, dyn, ctx->acc.as<unsigned long long>(), ctx->score.as<float>(), ctx->flags.as<uint8_t>(),
          (const unsigned*)(cnt + CNT_MAXVAL), cnt);
   // NOTE (old rule): when max_val == 0 the apply kernel returns before zeroing; the accumulator then only holds cells
   // whose length is <= 0, which the next accumulate clears because acc_has_data stays true.
@@ -499,7 +497,25 @@ int vofod_raycast_accumulate(vofod_ctx* ctx, const vofod_pt* scan, size_t n, con
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
   CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-  const int rc = vf_raycast_accumulate_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p);
+  if (n_traversals)
+    *n_traversals = 0;
+  const int prc = vf_raycast_prepare(ctx, n, *tf, *p);
+  if (prc != VOFOD_OK)
+  {
+    // the reference clears m_voxel_raycast before the sensor-in-map test (:1430-1432)
+    if (prc == VOFOD_W_SENSOR_OOB && ctx->acc_has_data && ctx->acc.p)
+    {
+      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, ctx->stream));
+      ctx->acc_has_data = false;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return prc;
+  }
+  memcpy(ctx->h_dyn->tf.R, tf->R, sizeof(tf->R));
+  memcpy(ctx->h_dyn->tf.t, tf->t, sizeof(tf->t));
+  ctx->h_dyn->scan = ctx->scan_staging.as<vofod_pt>();
+  RET(vf_dyn_push(ctx));
+  const int rc = vf_raycast_accumulate_dev(ctx, n, *tf, *p);
   if (rc < 0)
     return rc;
   unsigned long long t[2] = {0, 0};
@@ -543,9 +559,14 @@ int vofod_raycast_apply(vofod_ctx* ctx, int its_diff, const vofod_params* p)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
   if (!p || its_diff < 1)
     return vf_fail(ctx, VOFOD_E_INVALID, "bad argument (its_diff must be >= 1)");
+  ctx->h_dyn->its_raycast = its_diff;
+  RET(vf_dyn_push(ctx));
   const int rc = vf_raycast_apply_dev(ctx, its_diff, *p);
   if (rc != VOFOD_OK)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
     return rc;
+  }
   unsigned long long any = 0;
   CK(cudaMemcpyAsync(&any, vf_cnt(ctx, CNT_APPLY_ANY), 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -14,8 +14,8 @@
 #include "common.cuh"
 #include "prims.cuh"
 
-int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total);  // ctx.cu
-int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, size_t n, float leaf, float thr, DevBuf& out);                        // voxelgrid.cu
+int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap);  // ctx.cu
+int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsigned long long* d_n, size_t cap, float leaf, float thr, DevBuf& out);  // voxelgrid.cu
 
 // :1174-1183 — n_sure[cluster] = std::accumulate(range, int 0)
 __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__ ds, const int* __restrict__ labels, const unsigned long long* __restrict__ d_k,
@@ -37,8 +37,11 @@ __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels,
   if (__any_sync(VOFOD_FULL, any) && (threadIdx.x & 31) == 0)
     counters[CNT_SEP_ANY_SURE] = 1ull;
 }
-__global__ void k_sep_state(unsigned long long* __restrict__ counters)
+__global__ void k_sep_state(unsigned long long* __restrict__ counters, const unsigned long long k_cap)
 {
+  const unsigned long long k = counters[CNT_SEP_K];
+  if (k == 0ull || k > k_cap)
+    return;  // empty cloud: the reference returns before touching the flag (:1155-1159); overflow: the host redoes the pass
   counters[CNT_STATE_SURE] = counters[CNT_SEP_ANY_SURE] ? 1ull : 0ull;  // :1196 / :1205
 }
 
@@ -46,10 +49,10 @@ __global__ void k_sep_state(unsigned long long* __restrict__ counters)
 __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, const vofod_vox* __restrict__ ds, const int* __restrict__ labels,
                                                    const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
                                                    const int3* __restrict__ offsets, const int n_off, const unsigned min_sure, const float w1, const float w2,
-                                                   const float update_val, const unsigned long long* __restrict__ counters)
+                                                   const float update_val, const unsigned long long* __restrict__ counters, const unsigned long long k_cap)
 {
-  if (counters[CNT_SEP_ANY_SURE] == 0ull)
-    return;  // :1192-1199
+  if (counters[CNT_SEP_ANY_SURE] == 0ull || counters[CNT_SEP_K] > k_cap)
+    return;  // :1192-1199 (and: list overflow => nothing is touched, the host redoes the pass with a larger list)
   const size_t k = prims::dev_count(d_k, cap);
   const size_t total = k * (size_t)n_off;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
@@ -80,7 +83,10 @@ __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, c
   }
 }
 
-int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
+// k_cap == 0: exact mode (one host read-back sizes the background-voxel list).  k_cap > 0: the list is capped at k_cap rows and
+// nothing returns to the host; when the true count exceeds k_cap the pass leaves the map untouched and the caller, who sees
+// CNT_SEP_K > k_cap in its read-back, repeats it in exact mode.
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap)
 {
   if (p.sep_pause)
     return VOFOD_W_PAUSED;
@@ -92,14 +98,19 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   const float max_dist_idx = (float)(p.sep_max_bg_distance / (double)vs);  // :1142
   const int mv = (int)ceilf(max_dist_idx);                                 // :1143
   // :1146-1153 copy + voxelsAsVoxelPC (the private copy is unnecessary here: calls on a context are serialised)
-  size_t K = 0;
-  RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K));
-  if (K == 0)
-    return VOFOD_W_EMPTY;  // :1155-1159
+  size_t K = k_cap;
+  if (k_cap == 0)
+  {
+    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0));
+    if (K == 0)
+      return VOFOD_W_EMPTY;  // :1155-1159
+  } else
+    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, k_cap));
+  const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   const float lsz = (float)(mv - 1 > 0 ? mv - 1 : 0);  // :1163
   if (!(lsz > 0.0f))
     return vf_fail(ctx, VOFOD_E_INVALID, "sepclusters: max_bg_distance/voxel_size <= 1 gives a zero leaf size (the reference divides by it)");
-  RET(vf_voxel_grid_counted_dev(ctx, ctx->sep_raw.as<vofod_xyzi>(), K, lsz, thr_sure, ctx->sep_ds));
+  RET(vf_voxel_grid_counted_dev(ctx, ctx->sep_raw.as<vofod_xyzi>(), cnt + CNT_SEP_K, K, lsz, thr_sure, ctx->sep_ds));
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
   RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, cnt + CNT_SEP_KDS, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
@@ -108,7 +119,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   const int nb = vf_blocks(ctx, K, 256, 8);
   LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(), cnt + CNT_SEP_KDS, K, ctx->sep_nsure.as<int>());
   LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), cnt + CNT_SEP_KDS, K, min_sure, cnt);
-  LAUNCH(k_sep_state, 1, 1, 0, cnt);
+  LAUNCH(k_sep_state, 1, 1, 0, cnt, cap_guard);
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)
   if (ctx->sep_off_n < 0 || ctx->sep_off_mv != mv || ctx->sep_off_md != max_dist_idx)
   {
@@ -138,7 +149,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   volatile float w2v = 1.0f - w1;
   const float w2 = w2v;
   LAUNCH(k_sep_decay, vf_blocks(ctx, K * n_off, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(),
-         ctx->sep_nsure.as<int>(), cnt + CNT_SEP_KDS, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt);
+         ctx->sep_nsure.as<int>(), cnt + CNT_SEP_KDS, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt, cap_guard);
   return VOFOD_OK;
 }
 
@@ -151,7 +162,8 @@ extern "C" int vofod_sepclusters(vofod_ctx* ctx, int its_diff, const vofod_param
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
   if (!p)
     return vf_fail(ctx, VOFOD_E_INVALID, "params is NULL");
-  const int rc = vf_sepclusters_dev(ctx, its_diff, *p);
+  RET(vf_begin_call(ctx));
+  const int rc = vf_sepclusters_dev(ctx, its_diff, *p, 0);
   if (rc < 0)
     return rc;
   unsigned long long h[CNT_N_SLOTS];

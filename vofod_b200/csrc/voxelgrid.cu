@@ -23,7 +23,6 @@ struct VgLayout
 
 struct CropArgs
 {
-  Pose33 tf;
   float ex_min[3], ex_max[3];
   float op_min[3], op_max[3];
   int n;
@@ -110,9 +109,11 @@ __device__ __forceinline__ void block_minmax_commit(const bool valid, const floa
 }
 
 // K1a — pcl::CropBox(negative) -> pcl::transformPointCloud -> pcl::CropBox (vofod_nodelet.cpp:626-655)
-__global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const vofod_pt* __restrict__ scan, float4* __restrict__ pts, MinMax* mm)
+__global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const ScanDyn* __restrict__ dyn, float4* __restrict__ pts, MinMax* mm)
 {
   __shared__ __align__(16) uint32_t s_pts[256 * 5];
+  const vofod_pt* __restrict__ scan = dyn->scan;
+  const Pose33 tf = dyn->tf;
   const int blk_first = blockIdx.x * 256;
   {
     const int n_here = min(256, a.n - blk_first);
@@ -137,9 +138,9 @@ __global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const 
     const bool outside1 = (x < a.ex_min[0] || y < a.ex_min[1] || z < a.ex_min[2]) || (x > a.ex_max[0] || y > a.ex_max[1] || z > a.ex_max[2]);
     valid = valid && outside1;
     // PCL 1.10 SSE transform order: x*c0 + (y*c1 + (z*c2 + c3))
-    X = x * a.tf.R[0] + (y * a.tf.R[1] + (z * a.tf.R[2] + a.tf.t[0]));
-    Y = x * a.tf.R[3] + (y * a.tf.R[4] + (z * a.tf.R[5] + a.tf.t[1]));
-    Z = x * a.tf.R[6] + (y * a.tf.R[7] + (z * a.tf.R[8] + a.tf.t[2]));
+    X = x * tf.R[0] + (y * tf.R[1] + (z * tf.R[2] + tf.t[0]));
+    Y = x * tf.R[3] + (y * tf.R[4] + (z * tf.R[5] + tf.t[1]));
+    Z = x * tf.R[6] + (y * tf.R[7] + (z * tf.R[8] + tf.t[2]));
     const bool outside2 = (X < a.op_min[0] || Y < a.op_min[1] || Z < a.op_min[2]) || (X > a.op_max[0] || Y > a.op_max[1] || Z > a.op_max[2]);
     valid = valid && isfinite(X) && isfinite(Y) && isfinite(Z) && !outside2;
     pts[idx] = make_float4(X, Y, Z, valid ? 1.0f : 0.0f);
@@ -148,8 +149,10 @@ __global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const 
 }
 
 // generic input: xyz triples (stride floats), w = 4th value (intensity) or 1; valid = finite
-__global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in, const int stride, const int n, float4* __restrict__ pts, MinMax* mm)
+__global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in, const int stride, const unsigned long long* __restrict__ d_n, const int cap,
+                                                   float4* __restrict__ pts, MinMax* mm)
 {
+  const int n = (int)prims::dev_count(d_n, (size_t)cap);
   const int idx = blockIdx.x * 256 + threadIdx.x;
   bool valid = idx < n;
   float x = 0.f, y = 0.f, z = 0.f;
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in
     valid = isfinite(x) && isfinite(y) && isfinite(z);
     // w carries validity (weighted) — the counted variant reads intensity from the source array directly
     pts[idx] = make_float4(x, y, z, valid ? 1.0f : 0.0f);
-  }
+  } else if (idx < cap)
+    pts[idx] = make_float4(0.f, 0.f, 0.f, 0.0f);  // beyond the device-side count: invalid, sorts to the end
   block_minmax_commit(valid, x, y, z, mm);
 }
 
@@ -288,16 +292,19 @@ __global__ void __launch_bounds__(256) k_vg_emit(const uint32_t* __restrict__ uk
   }
 }
 // counted variant: flag = intensity > threshold on the UNSORTED input
-__global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restrict__ in, const int n, const float thr, uint32_t* __restrict__ flags)
+__global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restrict__ in, const unsigned long long* __restrict__ d_n, const int cap, const float thr,
+                                                      uint32_t* __restrict__ flags)
 {
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
-    flags[i] = in[i].intensity > thr ? 1u : 0u;
+  const int n = (int)prims::dev_count(d_n, (size_t)cap);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i <= cap; i += gridDim.x * 256)
+    flags[i] = (i < n && in[i].intensity > thr) ? 1u : 0u;
 }
 
 // shared tail: pts (float4, w = validity) + minmax -> ctx->vox / CNT_VG_M.  key_bits_hint = 0 => sort all 32 bits.
 static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool align, const float* align_center, const int key_bits_hint, const vofod_xyzi* d_counted_in,
-                  const float counted_thr, DevBuf& out_buf, const int slot_m = CNT_VG_M, const int slot_nvalid = CNT_VG_NVALID, const int slot_overflow = CNT_VG_OVERFLOW)
+                  const unsigned long long* d_counted_n, const float counted_thr, DevBuf& out_buf, const int slot_m = CNT_VG_M, const int slot_nvalid = CNT_VG_NVALID, const int slot_overflow = CNT_VG_OVERFLOW)
 {
+  // `n` is the CAPACITY of the input (all kernels run over it); rows past the device-side count carry w == 0 (invalid)
   using namespace prims;
   const size_t np = padded(n);
   ENSURE(ctx->vg_keys_a, np * 4);
@@ -326,7 +333,7 @@ static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool a
   {
     ENSURE(ctx->vg_pref, np * 4);
     // reuse vg_flags for the over-threshold flags (heads are no longer needed)
-    LAUNCH(k_vg_over_flags, nb, 256, 0, d_counted_in, (int)n, counted_thr, ctx->vg_flags.as<uint32_t>());
+    LAUNCH(k_vg_over_flags, nb, 256, 0, d_counted_in, d_counted_n, (int)n, counted_thr, ctx->vg_flags.as<uint32_t>());
     RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_pref.as<uint32_t>(), nullptr, n + 1, nullptr));
     over_prefix = ctx->vg_pref.as<uint32_t>();
   }
@@ -345,14 +352,12 @@ static int bits_for(unsigned long long v)
   return b;
 }
 
-int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p)
+int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
 {
   const size_t np = prims::padded(n);
   ENSURE(ctx->vg_pts, np * 16);
   ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
   CropArgs a;
-  memcpy(a.tf.R, tf.R, sizeof(a.tf.R));
-  memcpy(a.tf.t, tf.t, sizeof(a.tf.t));
   {
     // vofod_nodelet.cpp:204, 626-629 (host fp32)
     volatile float ez = p.exclude_box_offset[2] + p.exclude_box_size[2] / 2.0f;
@@ -376,7 +381,7 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, con
   a.n = (int)n;
   MinMax* mm = ctx->scratch_d.as<MinMax>();
   LAUNCH(k_minmax_init, 1, 1, 0, mm);
-  LAUNCH(k_crop_transform, (int)((n + 255) / 256), 256, 0, a, d_scan, ctx->vg_pts.as<float4>(), mm);
+  LAUNCH(k_crop_transform, (int)((n + 255) / 256), 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->vg_pts.as<float4>(), mm);
   // align to the map: idxToCoord(0,0,0) (vofod_nodelet.cpp:664-665)
   const Geom& g = ctx->g;
   float ac[3];
@@ -390,7 +395,7 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, con
   for (int k = 0; k < 3; k++)
     cells *= (unsigned long long)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
   const int bits = cells + 1 < (1ull << 31) ? bits_for(cells + 1) : 32;
-  return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, 0.f, ctx->vox);
+  return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, nullptr, 0.f, ctx->vox);
 }
 
 static int read_m(vofod_ctx* ctx, size_t* m, int* overflow)
@@ -424,7 +429,12 @@ int vofod_filter_voxelize(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const 
     return VOFOD_OK;
   ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
   CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-  RET(vf_filter_voxelize_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p));
+  memcpy(ctx->h_dyn->tf.R, tf->R, sizeof(tf->R));
+  memcpy(ctx->h_dyn->tf.t, tf->t, sizeof(tf->t));
+  ctx->h_dyn->scan = ctx->scan_staging.as<vofod_pt>();
+  RET(vf_begin_call(ctx));
+  RET(vf_dyn_push(ctx));
+  RET(vf_filter_voxelize_dev(ctx, n, *p));
   int overflow = 0;
   RET(read_m(ctx, m, &overflow));
   ctx->last_m = *m;
@@ -455,10 +465,11 @@ static int vg_generic(vofod_ctx* ctx, const float* host_in, int stride, size_t n
   ENSURE(ctx->scratch_a, n * stride * 4 + 64);
   ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
   CK(cudaMemcpyAsync(ctx->scratch_a.p, host_in, n * stride * 4, cudaMemcpyHostToDevice, ctx->stream));
+  RET(vf_begin_call(ctx));
   MinMax* mm = ctx->scratch_d.as<MinMax>();
   LAUNCH(k_minmax_init, 1, 1, 0, mm);
-  LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, ctx->scratch_a.as<float>(), stride, (int)n, ctx->vg_pts.as<float4>(), mm);
-  RET(vg_run(ctx, n, leaf, align != nullptr, align, 0, counted ? ctx->scratch_a.as<vofod_xyzi>() : nullptr, thr, ctx->sep_ds));
+  LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, ctx->scratch_a.as<float>(), stride, nullptr, (int)n, ctx->vg_pts.as<float4>(), mm);
+  RET(vg_run(ctx, n, leaf, align != nullptr, align, 0, counted ? ctx->scratch_a.as<vofod_xyzi>() : nullptr, nullptr, thr, ctx->sep_ds));
   int overflow = 0;
   RET(read_m(ctx, m, &overflow));
   if (overflow)
@@ -483,15 +494,16 @@ int vofod_voxel_grid_counted(vofod_ctx* ctx, const vofod_xyzi* pts, size_t n, fl
 }
 }
 
-// used by sepclusters.cu: counted voxel grid over device-resident xyzi points whose count is known on the host
-int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, size_t n, float leaf, float thr, DevBuf& out)
+// used by sepclusters.cu: counted voxel grid over device-resident xyzi points; `cap` rows are processed, of which the
+// first *d_n (device-side count, NULL = all) are real
+int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsigned long long* d_n, size_t cap, float leaf, float thr, DevBuf& out)
 {
-  const size_t np = prims::padded(n);
+  const size_t np = prims::padded(cap);
   ENSURE(ctx->vg_pts, np * 16);
   ENSURE(ctx->scratch_d, sizeof(MinMax) + sizeof(VgLayout) + 64);
   MinMax* mm = ctx->scratch_d.as<MinMax>();
   LAUNCH(k_minmax_init, 1, 1, 0, mm);
-  LAUNCH(k_load_cloud, (int)((n + 255) / 256), 256, 0, reinterpret_cast<const float*>(d_in), 4, (int)n, ctx->vg_pts.as<float4>(), mm);
+  LAUNCH(k_load_cloud, (int)((cap + 255) / 256), 256, 0, reinterpret_cast<const float*>(d_in), 4, d_n, (int)cap, ctx->vg_pts.as<float4>(), mm);
   // separate counter slots: the per-scan voxel counts (CNT_VG_*) must survive the background-cluster pass
-  return vg_run(ctx, n, leaf, false, nullptr, 0, d_in, thr, out, CNT_SEP_KDS, CNT_SCRATCH1, CNT_SEP_NUNIQ);
+  return vg_run(ctx, cap, leaf, false, nullptr, 0, d_in, d_n, thr, out, CNT_SEP_KDS, CNT_SCRATCH1, CNT_SEP_NUNIQ);
 }

@@ -176,6 +176,11 @@ def run_ours(args):
         ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans)]
         return ms, tot
 
+    if args.profile_leg:
+        ms, tot = run_leg(True, graph=args.profile_leg == "graph")
+        print(json.dumps({"profile_leg": args.profile_leg, "ms_per_step": sum(ms) / K, "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot["stage"].items()}}))
+        v.close()
+        return
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, tot_res = run_leg(True)
@@ -316,6 +321,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-leg", default="", choices=["", "graph", "eager"],
+                    help="profiling aid: run ONLY the HBM-resident leg (graph replay or kernel-by-kernel) and print nothing the driver parses")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,22 +71,26 @@ __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz
   }
 }
 
+// Union-find on plain (L1-cacheable) loads.  A load may return an OLD value of parent[x]; every old value is x itself or an
+// ancestor of x, so walking it still climbs the tree, and the only decision that needs the truth — "a is a root, hang it
+// under b" — is taken by the atomicCAS, whose return value (always fresh) is where the walk continues when it fails.
+// Volatile loads here would all funnel into the one L2 sector that holds the root of the ground cluster (measured: 180 us).
 __device__ __forceinline__ int uf_find(int* __restrict__ parent, int a)
 {
   // path halving; concurrent writers only ever replace a parent by one of its ancestors
   while (true)
   {
-    const int p = ((volatile int*)parent)[a];
+    const int p = parent[a];
     if (p == a)
       return a;
-    const int gp = ((volatile int*)parent)[p];
+    const int gp = parent[p];
     if (gp != p)
       parent[a] = gp;
     a = p;
   }
 }
 // Linking by index (larger under smaller) degenerates on this input: the points arrive sorted by voxel key, every point's
-// first neighbour is its predecessor, and the forest becomes one chain per grid row (finds of hundreds of dependent L2
+// first neighbour is its predecessor, and the forest becomes one chain per grid row (finds of hundreds of dependent
 // loads).  Link by a pseudo-random priority instead (expected depth O(log n)); the canonical min-index label is computed
 // afterwards with one atomicMin per point.
 __device__ __forceinline__ unsigned uf_prio(const int a) { return (unsigned)a * 2654435761u; }  // odd multiplier: a bijection on u32
@@ -104,10 +108,12 @@ __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
       a = b;
       b = t;
     }
-    // prio(a) > prio(b): hang root a under b (parents always have the smaller priority => acyclic)
+    // prio(a) > prio(b): hang a under b if a (still) is a root.  Parents always have the smaller priority => acyclic,
+    // whether or not b is still a root.
     const int old = atomicCAS(parent + a, a, b);
     if (old == a)
       return;
+    a = old;  // a had been linked meanwhile: continue from its true parent
   }
 }
 
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         d2 += diff * diff;
         diff = a.z - b.z;
         d2 += diff * diff;
-        if (d2 < r2)
+        if (d2 < r2 && parent[i] != parent[j])  // same parent => already united (the usual case after compression)
           uf_union(parent, (int)i, j);
       }
       j = nj;
@@ -168,23 +174,32 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
   }
 }
 
-// K5b: root of every point + minimum point index per root
+// K5b: root of every point + minimum point index per root.  Neighbouring indices mostly share their root (the ground
+// cluster): lanes with the same root are merged so that the hot root sees one atomic per warp, not 32.
 __global__ void __launch_bounds__(256) k_cl_roots(const unsigned long long* __restrict__ d_m, const size_t m_cap, int* __restrict__ parent, int* __restrict__ root,
                                                   int* __restrict__ minidx)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
   {
-    int r = (int)i;
-    while (true)
-    {
-      const int p = parent[r];
-      if (p == r)
-        break;
-      r = p;
-    }
-    root[i] = r;
-    atomicMin(minidx + r, (int)i);
+    const size_t i = i0 + lane;
+    const bool valid = i < m;
+    int r = valid ? (int)i : -1 - (int)lane;
+    if (valid)
+      while (true)
+      {
+        const int p = parent[r];
+        if (p == r)
+          break;
+        r = p;
+      }
+    if (valid)
+      root[i] = r;
+    const unsigned grp = __match_any_sync(VOFOD_FULL, r);
+    const int mn = __reduce_min_sync(grp, valid ? (int)i : 0x7fffffff);
+    if (valid && lane == (unsigned)(__ffs(grp) - 1))
+      atomicMin(minidx + r, mn);
   }
 }
 // K5c: canonical label = minimum point index of the component; per-label sizes; number of components
@@ -193,16 +208,22 @@ __global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __
                                                     unsigned long long* __restrict__ d_ncl)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
+  const unsigned lane = threadIdx.x & 31;
   unsigned roots = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
   {
-    const int l = minidx[root[i]];
-    labels[i] = l;
-    atomicAdd(sizes + l, 1);
-    roots += (l == (int)i);
+    const size_t i = i0 + lane;
+    const bool valid = i < m;
+    const int l = valid ? minidx[root[i]] : -1 - (int)lane;
+    if (valid)
+      labels[i] = l;
+    const unsigned grp = __match_any_sync(VOFOD_FULL, l);
+    if (valid && lane == (unsigned)(__ffs(grp) - 1))
+      atomicAdd(sizes + l, __popc(grp));
+    roots += (valid && l == (int)i);
   }
   roots = prims::warp_sum(roots);
-  if ((threadIdx.x & 31) == 0 && roots)
+  if (lane == 0 && roots)
     atomicAdd(d_ncl, (unsigned long long)roots);
 }
 

@@ -22,8 +22,19 @@ __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__
                                                    const size_t cap, int* __restrict__ nsure)
 {
   const size_t k = prims::dev_count(d_k, cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
-    atomicAdd(reinterpret_cast<unsigned*>(nsure) + labels[i], ds[i].count);
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < k; i0 += (size_t)gridDim.x * blockDim.x)
+  {
+    const size_t i = i0 + lane;
+    const bool valid = i < k;
+    const int l = valid ? labels[i] : -1 - (int)lane;
+    const unsigned c = valid ? ds[i].count : 0u;
+    // one atomic per (warp, cluster): the big background body would otherwise serialise every point on one word
+    const unsigned grp = __match_any_sync(VOFOD_FULL, l);
+    const unsigned sum = __reduce_add_sync(grp, c);
+    if (valid && lane == (unsigned)(__ffs(grp) - 1))
+      atomicAdd(reinterpret_cast<unsigned*>(nsure) + l, sum);
+  }
 }
 // :1186-1206
 __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels, const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,

@@ -150,6 +150,12 @@ struct vofod_ctx
   DevBuf flags;   // uint8
   bool flags_full_dirty = false;
   DevBuf flagged; // u32 cell indices (storage index) written since the last clear
+  // Columns (x,y) in which some cell was ever raised above the fill value by a point / rangefinder / apriori update.  Every
+  // other column only holds values <= max(fill value, ray score, frontiers threshold), so threshold passes over the grid
+  // (nVoxelsOver, voxelsAs*PC) can skip it without reading it.
+  DevBuf col_dirty;      // u8 per column of the storage box
+  bool col_all_dirty = true;   // unknown contents (after an upload / single-cell set): every column must be read
+  float untouched_max = 0.f;   // the fill value of the last setTo
   size_t flagged_cap = 0;
 
   // raycast accumulator
@@ -329,7 +335,8 @@ int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p);  // point + repe
 int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
 int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score,
                          float flag);
-int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out);
+int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, const vofod_params* p = nullptr);
+const uint8_t* vf_dirty_cols(vofod_ctx* ctx, float thr, const vofod_params* p);  // NULL = every column must be read
 // classify.cu
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
                            const vofod_params& p);  // sensor position comes from ctx->dyn

@@ -136,7 +136,7 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
@@ -291,7 +291,35 @@ __global__ void __launch_bounds__(256) k_count_over(const float* __restrict__ p,
   }
 }
 
-__global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const size_t n)
+// nVoxelsOver restricted to the columns that can hold a value above the threshold (see vofod_ctx::col_dirty)
+__global__ void __launch_bounds__(128) k_count_over_cols(const float* __restrict__ p, const Geom g, const uint8_t* __restrict__ dirty, const float thr,
+                                                         unsigned long long* out)
+{
+  const int ncol = g.st_size[0] * g.st_size[1];
+  const size_t sxy = (size_t)ncol;
+  const int sz = g.st_size[2];
+  unsigned cnt = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x)
+  {
+    if (!dirty[c])
+      continue;
+    for (int z0 = 0; z0 < sz; z0 += 8)
+    {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = (z0 + k < sz) ? p[(size_t)c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        cnt += v[k] > thr;
+    }
+  }
+  cnt = prims::warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt)
+    atomicAdd(out, (unsigned long long)cnt);
+}
+
+__global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const size_t n, uint8_t* __restrict__ col_dirty)
 {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
   {
@@ -300,7 +328,10 @@ __global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* 
       continue;
     const long long ci = cell_index(g, x, y, z);
     if (ci >= 0)
+    {
       score[ci] = __int_as_float(0x7f800000);
+      col_dirty[(x - g.st_lo[0]) + (y - g.st_lo[1]) * g.st_size[0]] = 1;
+    }
   }
 }
 
@@ -397,7 +428,8 @@ __global__ void k_submap_copy(const float* __restrict__ score, const Geom g, con
 
 // voxelsAsPC / voxelsAsVoxelPC (voxel_map.cpp:157-212): ordered compaction, emission order x-outer, y, z-inner.
 // pass 1: one thread per (x,y) column counts its matches (adjacent threads = adjacent x => coalesced reads)
-__global__ void k_compact_count(const float* __restrict__ score, const Geom g, const float thr, const int greater, uint32_t* __restrict__ colcnt)
+__global__ void k_compact_count(const float* __restrict__ score, const Geom g, const float thr, const int greater, uint32_t* __restrict__ colcnt,
+                                const uint8_t* __restrict__ dirty)
 {
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)g.st_size[0] * g.st_size[1];
@@ -405,8 +437,9 @@ __global__ void k_compact_count(const float* __restrict__ score, const Geom g, c
   {
     const int x = c % g.st_size[0], y = c / g.st_size[0];
     uint32_t cnt = 0;
-    for (int z = 0; z < g.st_size[2]; z++)
-      cnt += ((score[(size_t)c + (size_t)z * sxy] > thr) == (greater != 0));
+    if (!dirty || dirty[c])
+      for (int z = 0; z < g.st_size[2]; z++)
+        cnt += ((score[(size_t)c + (size_t)z * sxy] > thr) == (greater != 0));
     colcnt[(size_t)x * g.st_size[1] + y] = cnt;  // x-major so that the scan runs in emission order
   }
 }
@@ -463,13 +496,15 @@ __global__ void k_compact_emit(const float* __restrict__ score, const Geom g, co
 //   host_total != NULL : exact — one 8-byte read-back sizes the output (staged API, first scans)
 //   host_total == NULL : `cap` rows are reserved up front, no host round trip (graph replay); *d_total still receives the
 //                        true count, rows beyond cap are dropped and the caller must check d_total <= cap
-int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap)
+int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap,
+                        const vofod_params* p)
 {
   const Geom& g = ctx->g;
   const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
   ENSURE(ctx->sep_colcnt, prims::padded(ncol) * sizeof(uint32_t));
   ENSURE(ctx->sep_coloff, prims::padded(ncol) * sizeof(uint32_t));
-  LAUNCH(k_compact_count, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, ctx->sep_colcnt.as<uint32_t>());
+  const uint8_t* dirty = greater ? vf_dirty_cols(ctx, thr, p) : nullptr;
+  LAUNCH(k_compact_count, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, ctx->sep_colcnt.as<uint32_t>(), dirty);
   RET(prims::scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncol, d_total));
   if (host_total)
   {
@@ -507,6 +542,9 @@ static int map_alloc(vofod_ctx* ctx)
     return vf_fail(ctx, VOFOD_E_INVALID, "map has no cells");
   ENSURE(ctx->score, (size_t)n * sizeof(float) + 64);
   ENSURE(ctx->flags, (size_t)n + 64);
+  ENSURE(ctx->col_dirty, (size_t)g.st_size[0] * g.st_size[1] + 64);
+  CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)g.st_size[0] * g.st_size[1], ctx->stream));
+  ctx->col_all_dirty = true;  // the grid contents are unspecified until the first setTo
   CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)n, ctx->stream));
   ctx->flags_full_dirty = false;
   // every counter except the persistent generations (exploreToGround stamps, look-back states keep old values)
@@ -605,8 +643,12 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
   NEED_MAP();
   const size_t n = (size_t)geom_cells(ctx->g);
   if (which == VOFOD_MAP_SCORE)
+  {
     LAUNCH(k_fill_f32, vf_blocks(ctx, n / 4 + 1, 256), 256, 0, ctx->score.as<float>(), value, n);
-  else if (which == VOFOD_MAP_FLAGS)
+    CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], ctx->stream));
+    ctx->col_all_dirty = !(value == value) || value == __builtin_inff();  // NaN / +inf fills defeat the bound
+    ctx->untouched_max = value;
+  } else if (which == VOFOD_MAP_FLAGS)
   {
     CK(cudaMemsetAsync(ctx->flags.p, (int)(uint8_t)value, n, ctx->stream));
     CK(cudaMemsetAsync(vf_cnt(ctx, CNT_FLAGGED), 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -632,7 +674,7 @@ int vofod_map_set_inf(vofod_ctx* ctx, const float* xyz, size_t n)
     return vf_fail(ctx, VOFOD_E_INVALID, "xyz is NULL");
   ENSURE(ctx->scratch_a, n * 12);
   CK(cudaMemcpyAsync(ctx->scratch_a.p, xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_set_inf, vf_blocks(ctx, n, 256), 256, 0, ctx->score.as<float>(), ctx->g, ctx->scratch_a.as<float>(), n);
+  LAUNCH(k_set_inf, vf_blocks(ctx, n, 256), 256, 0, ctx->score.as<float>(), ctx->g, ctx->scratch_a.as<float>(), n, ctx->col_dirty.as<uint8_t>());
   CK(cudaStreamSynchronize(ctx->stream));
   return VOFOD_OK;
 }
@@ -669,7 +711,10 @@ int vofod_map_upload(vofod_ctx* ctx, int which, const float* host, size_t n_cell
   if (!host || n_cells != n)
     return vf_fail(ctx, VOFOD_E_INVALID, "vofod_map_upload: expected %zu cells", n);
   if (which == VOFOD_MAP_SCORE)
+  {
     CK(cudaMemcpyAsync(ctx->score.p, host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->col_all_dirty = true;
+  }
   else if (which == VOFOD_MAP_FLAGS)
   {
     ENSURE(ctx->scratch_a, n * 4);
@@ -719,7 +764,10 @@ int vofod_map_set(vofod_ctx* ctx, int which, int ix, int iy, int iz, float value
     return VOFOD_OK;  // another slab owns it
   const size_t ci = (size_t)lx + (size_t)ly * g.st_size[0] + (size_t)lz * g.st_size[0] * g.st_size[1];
   if (which == VOFOD_MAP_SCORE)
+  {
     CK(cudaMemcpyAsync(ctx->score.as<float>() + ci, &value, 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->col_all_dirty = true;
+  }
   else if (which == VOFOD_MAP_FLAGS)
   {
     const uint8_t f = (uint8_t)value;
@@ -732,11 +780,28 @@ int vofod_map_set(vofod_ctx* ctx, int which, int ix, int iy, int iz, float value
 }
 }  // extern "C"
 
-int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out)
+// Columns worth reading for a "value > thr" pass, or NULL when every column must be read.  A column nobody raised holds
+// only the fill value and what the decaying updates made of it: ray apply and the background-cluster decay mix towards
+// score_ray, classification writes thr_frontiers.  If thr is strictly above all three, such a column cannot match.
+const uint8_t* vf_dirty_cols(vofod_ctx* ctx, float thr, const vofod_params* p)
+{
+  if (ctx->col_all_dirty || !p || !ctx->col_dirty.p)
+    return nullptr;
+  float bound = ctx->untouched_max;
+  if ((float)p->score_ray > bound) bound = (float)p->score_ray;
+  if ((float)p->thr_frontiers > bound) bound = (float)p->thr_frontiers;
+  return thr > bound ? ctx->col_dirty.as<uint8_t>() : nullptr;
+}
+
+int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, const vofod_params* p)
 {
   const size_t n = (size_t)geom_cells(ctx->g);
   CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
-  LAUNCH(k_count_over, vf_blocks(ctx, n / 4 + 1, 256, 8), 256, 0, ctx->score.as<float>(), n, thr, d_out);
+  const uint8_t* dirty = vf_dirty_cols(ctx, thr, p);
+  if (dirty)
+    LAUNCH(k_count_over_cols, vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 16), 128, 0, ctx->score.as<float>(), ctx->g, dirty, thr, d_out);
+  else
+    LAUNCH(k_count_over, vf_blocks(ctx, n / 4 + 1, 256, 8), 256, 0, ctx->score.as<float>(), n, thr, d_out);
   return 0;
 }
 
@@ -762,7 +827,7 @@ int vofod_map_compact_over(vofod_ctx* ctx, float threshold, int greater_than, in
     return vf_fail(ctx, VOFOD_E_INVALID, "n is NULL");
   size_t total = 0;
   RET(vf_begin_call(ctx));
-  RET(vf_compact_over_dev(ctx, threshold, greater_than, metric, ctx->sep_raw, vf_cnt(ctx, CNT_SEP_K), &total, 0));
+  RET(vf_compact_over_dev(ctx, threshold, greater_than, metric, ctx->sep_raw, vf_cnt(ctx, CNT_SEP_K), &total, 0, nullptr));
   *n = total;
   if (total > cap || (!out && total))
     return vf_fail(ctx, VOFOD_E_CAPACITY, "compact_over: need capacity %zu", total);

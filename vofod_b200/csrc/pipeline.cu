@@ -8,7 +8,7 @@
 #include "prims.cuh"
 
 // ---- A23 rangefinder ground seed (vofod_nodelet.cpp:581-613) ----------------------------------------
-__global__ void k_range_update(float* __restrict__ score, const Geom g, const ScanDyn* __restrict__ dyn, const double score_point)
+__global__ void k_range_update(float* __restrict__ score, const Geom g, const ScanDyn* __restrict__ dyn, const double score_point, uint8_t* __restrict__ col_dirty)
 {
   const float x = dyn->range_pt[0], y = dyn->range_pt[1], z = dyn->range_pt[2];
   const int repeats = dyn->n_seeds;
@@ -22,11 +22,12 @@ __global__ void k_range_update(float* __restrict__ score, const Geom g, const Sc
   for (int r = 0; r < repeats; r++)
     m = (float)(((double)m + score_point) / 2.0);  // :610
   score[ci] = m;
+  col_dirty[(ix - g.st_lo[0]) + (iy - g.st_lo[1]) * g.st_size[0]] = 1;
 }
 
 int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
 {
-  LAUNCH(k_range_update, 1, 1, 0, ctx->score.as<float>(), ctx->g, ctx->dyn.as<ScanDyn>(), p.score_point);
+  LAUNCH(k_range_update, 1, 1, 0, ctx->score.as<float>(), ctx->g, ctx->dyn.as<ScanDyn>(), p.score_point, ctx->col_dirty.as<uint8_t>());
   return 0;
 }
 
@@ -34,7 +35,7 @@ int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
 __global__ void __launch_bounds__(256) k_update_points(float* __restrict__ score, uint8_t* __restrict__ flags, const Geom g, const vofod_vox* __restrict__ vox,
                                                        const uint8_t* __restrict__ sel, const int sel_value, const unsigned long long* __restrict__ d_m,
                                                        const size_t m_cap, const float vmap_score, const uint8_t vflag, uint32_t* __restrict__ flagged,
-                                                       const size_t flagged_cap, unsigned long long* __restrict__ counters)
+                                                       const size_t flagged_cap, unsigned long long* __restrict__ counters, uint8_t* __restrict__ col_dirty)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) k_update_points(float* __restrict__ score
     const float w = 1.0f / (float)(1ull << c);                          // :791
     score[ci] = w * score[ci] + (1.0f - w) * vmap_score;                // :794
     flags[ci] = vflag;                                                  // :796
+    col_dirty[(xc - g.st_lo[0]) + (yc - g.st_lo[1]) * g.st_size[0]] = 1;
     const unsigned long long k = atomicAdd(counters + CNT_FLAGGED, 1ull);
     if (k < flagged_cap)
       flagged[k] = (uint32_t)ci;
@@ -78,7 +80,7 @@ int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* 
     return 0;
   RET(ensure_flagged(ctx, 4 * m_cap > (size_t(1) << 20) ? 4 * m_cap : (size_t(1) << 20)));
   LAUNCH(k_update_points, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->score.as<float>(), ctx->flags.as<uint8_t>(), ctx->g, d_vox, d_sel, sel_value, d_m, m_cap, score,
-         (uint8_t)flag, ctx->flagged.as<uint32_t>(), ctx->flagged_cap, ctx->d_counters.as<unsigned long long>());
+         (uint8_t)flag, ctx->flagged.as<uint32_t>(), ctx->flagged_cap, ctx->d_counters.as<unsigned long long>(), ctx->col_dirty.as<uint8_t>());
   return 0;
 }
 
@@ -183,7 +185,7 @@ int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels
 {
   const float max_dist = (float)p.ground_points_max_distance;
   const float thr = (float)p.thr_new_obstacles;
-  RET(vf_count_over_dev(ctx, thr, vf_cnt(ctx, CNT_NBG)));
+  RET(vf_count_over_dev(ctx, thr, vf_cnt(ctx, CNT_NBG), &p));
   // vofod_nodelet.cpp:229-230 (fp32, left to right), converted to uint64_t
   const float vs = ctx->cfg_voxel_size > 0.f ? ctx->cfg_voxel_size : ctx->g.vs;
   volatile float a0 = p.oparea_size[0] / vs;
@@ -481,6 +483,9 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   sig = fnv1a(&ctx->frac_bits, sizeof(int), sig);
   sig = fnv1a(&ctx->sep_cap, sizeof(size_t), sig);
   sig = fnv1a(&ctx->alloc_gen, sizeof(uint64_t), sig);
+  const int dirty_mode = ctx->col_all_dirty ? 1 : 0;
+  sig = fnv1a(&dirty_mode, sizeof(int), sig);
+  sig = fnv1a(&ctx->untouched_max, sizeof(float), sig);
 
   int sep_status = VOFOD_W_PAUSED;
   bool applied = false;

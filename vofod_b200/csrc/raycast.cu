@@ -31,26 +31,28 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsi
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 
-template <bool AGGREGATE>
-__global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
-                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
-                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
+// RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
+// returns a few metres), so small blocks balance better: 128 threads = 4 warps = 128 neighbouring columns of one row.
+template <int RB>
+__global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
+                                                           const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
+                                                           unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
 {
-  // stage this block's 256 packed points (20 B each) through shared memory with coalesced 16 B loads
-  __shared__ __align__(16) uint32_t s_pts[256 * 5];
+  // stage this block's packed points (20 B each) through shared memory with coalesced 16 B loads
+  __shared__ __align__(16) uint32_t s_pts[RB * 5];
   const vofod_pt* __restrict__ scan = dyn->scan;
   const Pose33 tf = dyn->tf;
   const Window w = dyn->win;
-  const int blk_first = blockIdx.x * 256;
+  const int blk_first = blockIdx.x * RB;
   {
-    const int n_here = min(256, a.n - blk_first);
+    const int n_here = min(RB, a.n - blk_first);
     const int n_words = n_here * 5;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(scan) + (size_t)blk_first * 5;
     const int n_vec = n_words / 4;
-    const uint4* src4 = reinterpret_cast<const uint4*>(src);  // blk_first*20 B is a multiple of 16
-    for (int i = threadIdx.x; i < n_vec; i += 256)
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);  // blk_first*20 B is a multiple of 16 (RB % 4 == 0)
+    for (int i = threadIdx.x; i < n_vec; i += RB)
       reinterpret_cast<uint4*>(s_pts)[i] = __ldg(src4 + i);
-    for (int i = n_vec * 4 + threadIdx.x; i < n_words; i += 256)
+    for (int i = n_vec * 4 + threadIdx.x; i < n_words; i += RB)
       s_pts[i] = __ldg(src + i);
   }
   __syncthreads();
@@ -60,8 +62,10 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
   bool alive = idx < a.n;
   float len = 0.f;
   float tmx = 0.f, tmy = 0.f, tmz = 0.f, tdx = 0.f, tdy = 0.f, tdz = 0.f;
-  int cx = 0, cy = 0, cz = 0, stx = 0, sty = 0, stz = 0, lx = 0, ly = 0, lz = 0;
-  long long widx = 0;
+  int remx = 0, remy = 0, remz = 0;  // steps left before the ray stands in the last voxel of the map along that axis
+  int dwx = 0, dwy = 0, dwz = 0;     // window-index stride of one step along each axis
+  int widx = 0;
+  const int wn = w.size[0] * w.size[1] * w.size[2];
   if (alive)
   {
     const float intensity = __uint_as_float(s_pts[threadIdx.x * 5 + 3]);
@@ -81,20 +85,20 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
     if (a.has_off)
     {
       const float4 o1 = __ldg(lut_off + idx);
-      sx = (tf.R[0] * o1.x + (tf.R[1] * o1.y + tf.R[2] * o1.z)) + tf.t[0];            // :1477
+      sx = (tf.R[0] * o1.x + (tf.R[1] * o1.y + tf.R[2] * o1.z)) + tf.t[0];                    // :1477
       sy = (tf.R[3] * o1.x + (tf.R[4] * o1.y + tf.R[5] * o1.z)) + tf.t[1];
       sz = (tf.R[6] * o1.x + (tf.R[7] * o1.y + tf.R[8] * o1.z)) + tf.t[2];
     }
-    cx = coord_to_idx1(sx, a.g.off[0], a.g.inv);
-    cy = coord_to_idx1(sy, a.g.off[1], a.g.inv);
-    cz = coord_to_idx1(sz, a.g.off[2], a.g.inv);
+    const int cx = coord_to_idx1(sx, a.g.off[0], a.g.inv);
+    const int cy = coord_to_idx1(sy, a.g.off[1], a.g.inv);
+    const int cz = coord_to_idx1(sz, a.g.off[2], a.g.inv);
     if (!in_limits_idx(a.g, cx, cy, cz))                                                      // :1482
       alive = false;
     // voxel_map.cpp:232-244
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-    stx = (dx > 0.0f) - (dx < 0.0f);
-    sty = (dy > 0.0f) - (dy < 0.0f);
-    stz = (dz > 0.0f) - (dz < 0.0f);
+    const int stx = (dx > 0.0f) - (dx < 0.0f);
+    const int sty = (dy > 0.0f) - (dy < 0.0f);
+    const int stz = (dz > 0.0f) - (dz < 0.0f);
     tdx = (1.0f / ax) * a.g.vs;
     tdy = (1.0f / ay) * a.g.vs;
     tdz = (1.0f / az) * a.g.vs;
@@ -104,15 +108,17 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
     tmx = (a.g.half + (float)stx * ox) / ax;
     tmy = (a.g.half + (float)sty * oy) / ay;
     tmz = (a.g.half + (float)stz * oz) / az;
-    lx = stx > 0 ? a.g.size[0] - 1 : 0;
-    ly = sty > 0 ? a.g.size[1] - 1 : 0;
-    lz = stz > 0 ? a.g.size[2] - 1 : 0;
+    // `if (cur[i] == last[i]) break` with last = step > 0 ? size-1 : 0 (voxel_map.cpp:240-257), as a countdown
+    remx = stx > 0 ? a.g.size[0] - 1 - cx : cx;
+    remy = sty > 0 ? a.g.size[1] - 1 - cy : cy;
+    remz = stz > 0 ? a.g.size[2] - 1 - cz : cz;
+    dwx = stx;
+    dwy = sty * w.size[0];
+    dwz = stz * w.size[0] * w.size[1];
+    widx = (cx - w.lo[0]) + (cy - w.lo[1]) * w.size[0] + (cz - w.lo[2]) * w.size[0] * w.size[1];
     if (!(0.0f < len))  // while (prev_dist < length) with prev_dist = 0
       alive = false;
   }
-  const int wsx = w.size[0];
-  const long long wsxy = (long long)w.size[0] * w.size[1];
-  const long long wn = wsxy * w.size[2];
   float prev = 0.0f;
   unsigned steps = 0;
   unsigned oob = 0;
@@ -122,50 +128,42 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
     if (alive)
     {
       // tmax.minCoeff(&i): first minimum, strict '<'
-      int i = 0;
-      float dist = tmx;
-      if (tmy < dist) { dist = tmy; i = 1; }
-      if (tmz < dist) { dist = tmz; i = 2; }
+      const bool use_y = tmy < tmx;
+      const float d01 = use_y ? tmy : tmx;
+      const bool use_z = tmz < d01;
+      const float dist = use_z ? tmz : d01;
       const float ddist = (len < dist ? len : dist) - prev;                                   // voxel_map.cpp:252
       const int q = __float2int_rn(ddist * a.scale);
-      // window cell of the current voxel
-      const int wx = cx - w.lo[0], wy = cy - w.lo[1], wz = cz - w.lo[2];
-      const bool inside = wx >= 0 && wx < w.size[0] && wy >= 0 && wy < w.size[1] && wz >= 0 && wz < w.size[2];
-      widx = inside ? ((long long)wx + (long long)wy * wsx + (long long)wz * wsxy) : (wn + lane);
-      if (AGGREGATE)
-      {
-        const unsigned m = __match_any_sync(alive_mask, widx);
-        const int sum = __reduce_add_sync(m, q);
-        if (inside && lane == (unsigned)(__ffs(m) - 1))
-          red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
-      } else if (inside)
-        red_add_u64(acc + widx, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
+      const bool inside = (unsigned)widx < (unsigned)wn;  // always true: the window holds every voxel within max_dist
+      const int key = inside ? widx : -1 - (int)lane;
+      // lanes of the warp standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
+      const unsigned m = __match_any_sync(alive_mask, key);
+      const int sum = __reduce_add_sync(m, q);
+      if (inside && lane == (unsigned)(__ffs(m) - 1))
+        red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
       oob += !inside;
       steps++;
       prev = dist;
       // voxel_map.cpp:257-261
-      if (i == 0)
+      const int rem = use_z ? remz : (use_y ? remy : remx);
+      alive = rem != 0 && dist < len;
+      if (use_z)
       {
-        if (cx == lx) alive = false;
-        else { cx += stx; tmx += tdx; }
-      } else if (i == 1)
+        remz--; tmz += tdz; widx += dwz;
+      } else if (use_y)
       {
-        if (cy == ly) alive = false;
-        else { cy += sty; tmy += tdy; }
+        remy--; tmy += tdy; widx += dwy;
       } else
       {
-        if (cz == lz) alive = false;
-        else { cz += stz; tmz += tdz; }
+        remx--; tmx += tdx; widx += dwx;
       }
-      if (!(prev < len))
-        alive = false;
     }
     alive_mask = __ballot_sync(VOFOD_FULL, alive);
   }
   // per-block totals
   unsigned tot = prims::warp_sum(steps);
   unsigned toob = prims::warp_sum(oob);
-  __shared__ unsigned s_tot[8], s_oob[8];
+  __shared__ unsigned s_tot[RB / 32], s_oob[RB / 32];
   if (lane == 0)
   {
     s_tot[threadIdx.x >> 5] = tot;
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(256) k_raycast_accumulate(const RayArgs a, con
   if (threadIdx.x == 0)
   {
     unsigned t = 0, o = 0;
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < RB / 32; i++)
     {
       t += s_tot[i];
       o += s_oob[i];
@@ -428,8 +426,9 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.scale = ldexpf(1.0f, ctx->frac_bits);
   a.n = (int)n;
   a.has_off = ctx->lut_has_off ? 1 : 0;
-  const int blocks = (int)((n + 255) / 256);
-  LAUNCH((k_raycast_accumulate<true>), blocks, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
+  constexpr int RB = 128;
+  const int blocks = (int)((n + RB - 1) / RB);
+  LAUNCH((k_raycast_accumulate<RB>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
          ctx->acc.as<unsigned long long>(), cnt);
   ctx->acc_has_data = true;
   return VOFOD_OK;

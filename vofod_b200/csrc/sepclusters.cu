@@ -14,7 +14,8 @@
 #include "common.cuh"
 #include "prims.cuh"
 
-int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap);  // ctx.cu
+int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevBuf& out, unsigned long long* d_total, size_t* host_total, size_t cap,
+                        const vofod_params* p);  // ctx.cu
 int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsigned long long* d_n, size_t cap, float leaf, float thr, DevBuf& out);  // voxelgrid.cu
 
 // :1174-1183 — n_sure[cluster] = std::accumulate(range, int 0)
@@ -112,11 +113,11 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   size_t K = k_cap;
   if (k_cap == 0)
   {
-    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0));
+    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0, &p));
     if (K == 0)
       return VOFOD_W_EMPTY;  // :1155-1159
   } else
-    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, k_cap));
+    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, k_cap, &p));
   const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   const float lsz = (float)(mv - 1 > 0 ? mv - 1 : 0);  // :1163
   if (!(lsz > 0.0f))

@@ -18,21 +18,27 @@
 #define CLS_CANDIDATE (-1)
 #define MAX_DETS 16384
 
-__global__ void __launch_bounds__(256) k_cls_keys(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const unsigned long long* __restrict__ d_m,
-                                                  const size_t m_cap, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, int* __restrict__ sizes)
+// far clusters: per-label size and largest member index, list of far roots (unordered) with their sort keys
+__global__ void __launch_bounds__(256) k_cls_mark(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const unsigned long long* __restrict__ d_m,
+                                                  const size_t m_cap, int* __restrict__ sizes, int* __restrict__ maxidx)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
   {
-    const int l = labels[i];
-    const bool far = in_close[l] == 0;
-    keys[i] = far ? (uint32_t)l : 0xFFFFFFFFu;
-    idx[i] = (uint32_t)i;
-    if (far)
-      atomicAdd(sizes + l, 1);
+    const size_t i = i0 + lane;
+    const int l = i < m ? labels[i] : -1;
+    const bool far = i < m && in_close[l] == 0;
+    const int key = far ? l : -1 - (int)lane;
+    // one atomic per (warp, cluster)
+    const unsigned grp = __match_any_sync(VOFOD_FULL, key);
+    if (far && lane == (unsigned)(31 - __clz(grp)))  // the highest lane holds the largest index of the group
+    {
+      atomicAdd(sizes + l, __popc(grp));
+      atomicMax(maxidx + l, (int)i);
+    }
   }
 }
-
 __global__ void __launch_bounds__(256) k_cls_roots(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const int* __restrict__ sizes,
                                                    const unsigned long long* __restrict__ d_m, const size_t m_cap, const int bits, unsigned long long* __restrict__ okeys,
                                                    unsigned long long* __restrict__ d_nfar)
@@ -46,16 +52,59 @@ __global__ void __launch_bounds__(256) k_cls_roots(const int* __restrict__ label
       okeys[pos] = ((maxv - (unsigned long long)sizes[i]) << bits) | (unsigned long long)i;  // size descending, label ascending
     }
 }
-
-__global__ void __launch_bounds__(256) k_cls_segments(const uint32_t* __restrict__ skeys, const unsigned long long* __restrict__ d_m, const size_t m_cap,
-                                                      int* __restrict__ seg_start)
+// The reference processes clusters largest first (ties: smallest point index).  The keys are unique, so the rank of a key
+// IS its position: one warp per cluster counts the smaller keys.  n_far is a handful in steady state and a few thousand
+// during bootstrap; either way this beats a multi-pass radix sort of n_far 64-bit keys.
+__global__ void __launch_bounds__(256) k_cls_rank(const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
+                                                  unsigned long long* __restrict__ sorted)
 {
-  const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < m; s += (size_t)gridDim.x * blockDim.x)
+  const unsigned long long n = *d_nfar;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long c = warp0; c < n; c += n_warps)
   {
-    const uint32_t k = skeys[s];
-    if (k != 0xFFFFFFFFu && (s == 0 || skeys[s - 1] != k))
-      seg_start[k] = (int)s;
+    const unsigned long long key = okeys[c];
+    unsigned rank = 0;
+    for (unsigned long long j = lane; j < n; j += 32)
+      rank += okeys[j] < key;
+    rank = prims::warp_sum(rank);
+    if (lane == 0)
+      sorted[rank] = key;
+  }
+}
+// member lists: the points of every far cluster in ascending index order (the order pcl::EuclideanClusterExtraction
+// returns them in).  One warp per cluster walks labels[label .. maxidx] and compacts the matches with ballots.
+__global__ void __launch_bounds__(256) k_cls_members(const int* __restrict__ labels, const int* __restrict__ sizes, const int* __restrict__ maxidx,
+                                                     const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar, const int bits,
+                                                     uint32_t* __restrict__ memb, int* __restrict__ seg_start, unsigned long long* __restrict__ cursor)
+{
+  const unsigned long long n_far = *d_nfar;
+  const unsigned long long lmask = (1ull << bits) - 1ull;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long c = warp0; c < n_far; c += n_warps)
+  {
+    const int label = (int)(okeys[c] & lmask);
+    const int hi = maxidx[label];
+    unsigned long long start = 0;
+    if (lane == 0)
+    {
+      start = atomicAdd(cursor, (unsigned long long)sizes[label]);
+      seg_start[label] = (int)start;
+    }
+    start = __shfl_sync(VOFOD_FULL, start, 0);
+    unsigned cnt = 0;
+    for (int base = label; base <= hi; base += 32)
+    {
+      const int idx = base + (int)lane;
+      const bool match = idx <= hi && labels[idx] == label;
+      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
+      if (match)
+        memb[start + cnt + __popc(bal & prims::lanemask_lt())] = (uint32_t)idx;
+      cnt += __popc(bal);
+    }
   }
 }
 
@@ -660,11 +709,9 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   const int sub_side = (int)ceil(p.cls_max_size / vs) + 8;
   const size_t terms_cap = (size_t)sub_side * sub_side * sub_side;
 
-  ENSURE(ctx->far_keys_a, np * 4);
-  ENSURE(ctx->far_keys_b, np * 4);
-  ENSURE(ctx->far_list, np * 4);
-  ENSURE(ctx->scratch_c, np * 4);
+  ENSURE(ctx->far_list, np * 4);            // member lists
   ENSURE(ctx->cls_sizes, m_cap * 4);
+  ENSURE(ctx->cls_maxidx, m_cap * 4);
   ENSURE(ctx->cls_seg, m_cap * 4);
   ENSURE(ctx->cls_okeys_a, np * 8);
   ENSURE(ctx->cls_okeys_b, np * 8);
@@ -674,17 +721,18 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
   ENSURE(ctx->cls_terms, terms_cap * 8);
   CK(cudaMemsetAsync(ctx->cls_sizes.p, 0, m_cap * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->cls_maxidx.p, 0, m_cap * 4, ctx->stream));
+  CK(cudaMemsetAsync(cnt + CNT_SCRATCH0, 0, 8, ctx->stream));
 
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
-  LAUNCH(k_cls_keys, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->far_keys_a.as<uint32_t>(), ctx->far_list.as<uint32_t>(), ctx->cls_sizes.as<int>());
+  LAUNCH(k_cls_mark, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>());
   LAUNCH(k_cls_roots, nb, 256, 0, d_labels, d_in_close, ctx->cls_sizes.as<int>(), d_m, m_cap, bits, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS);
-  uint32_t *skeys = nullptr, *sidx = nullptr;
-  RET((radix_sort<uint32_t, true>(ctx, ctx->far_keys_a.as<uint32_t>(), ctx->far_keys_b.as<uint32_t>(), ctx->far_list.as<uint32_t>(), ctx->scratch_c.as<uint32_t>(), d_m, m_cap,
-                                  0, bits, &skeys, &sidx)));
-  LAUNCH(k_cls_segments, nb, 256, 0, skeys, d_m, m_cap, ctx->cls_seg.as<int>());
-  unsigned long long* okeys = nullptr;
-  RET((radix_sort<unsigned long long, false>(ctx, ctx->cls_okeys_a.as<unsigned long long>(), ctx->cls_okeys_b.as<unsigned long long>(), nullptr, nullptr, cnt + CNT_NFARPTS,
-                                             m_cap, 0, 2 * bits, &okeys, nullptr)));
+  const int nbw = vf_blocks(ctx, m_cap * 32, 256, 4);
+  LAUNCH(k_cls_rank, nbw, 256, 0, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS, ctx->cls_okeys_b.as<unsigned long long>());
+  const unsigned long long* okeys = ctx->cls_okeys_b.as<unsigned long long>();
+  uint32_t* sidx = ctx->far_list.as<uint32_t>();
+  LAUNCH(k_cls_members, nbw, 256, 0, d_labels, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>(), okeys, cnt + CNT_NFARPTS, bits, sidx, ctx->cls_seg.as<int>(),
+         cnt + CNT_SCRATCH0);
   ClsArgs a;
   a.g = ctx->g;
   a.min_points = p.cls_min_points;

@@ -196,6 +196,7 @@ struct vofod_ctx
   size_t acc_cells_max = 0;
 
   // CUDA-graph replay of vofod_process_scan
+  bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool graph_enabled = true;
   bool capturing = false;
   bool capture_broken = false;
@@ -214,7 +215,7 @@ struct vofod_ctx
   DevBuf cl_info;     // vofod_cluster_info per far cluster
   DevBuf dets;        // vofod_detection
   DevBuf explore_ws;
-  DevBuf cls_sizes, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
+  DevBuf cls_sizes, cls_maxidx, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
   size_t last_m = 0, last_far = 0;
 

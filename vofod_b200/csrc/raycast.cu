@@ -33,7 +33,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsi
 
 // RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
 // returns a few metres), so small blocks balance better: 128 threads = 4 warps = 128 neighbouring columns of one row.
-template <int RB>
+template <int RB, bool AGG>
 __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
@@ -137,10 +137,14 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
       const bool inside = (unsigned)widx < (unsigned)wn;  // always true: the window holds every voxel within max_dist
       const int key = inside ? widx : -1 - (int)lane;
       // lanes of the warp standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
-      const unsigned m = __match_any_sync(alive_mask, key);
-      const int sum = __reduce_add_sync(m, q);
-      if (inside && lane == (unsigned)(__ffs(m) - 1))
-        red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+      if (AGG)
+      {
+        const unsigned m = __match_any_sync(alive_mask, key);
+        const int sum = __reduce_add_sync(m, q);
+        if (inside && lane == (unsigned)(__ffs(m) - 1))
+          red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+      } else if (inside)
+        red_add_u64(acc + widx, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
       oob += !inside;
       steps++;
       prev = dist;
@@ -428,7 +432,11 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.has_off = ctx->lut_has_off ? 1 : 0;
   constexpr int RB = 128;
   const int blocks = (int)((n + RB - 1) / RB);
-  LAUNCH((k_raycast_accumulate<RB>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
+  if (ctx->raycast_no_agg)
+    LAUNCH((k_raycast_accumulate<RB, false>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
+           ctx->acc.as<unsigned long long>(), cnt);
+  else
+  LAUNCH((k_raycast_accumulate<RB, true>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
          ctx->acc.as<unsigned long long>(), cnt);
   ctx->acc_has_data = true;
   return VOFOD_OK;

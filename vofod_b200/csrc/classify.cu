@@ -722,7 +722,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   ENSURE(ctx->cls_terms, terms_cap * 8);
   CK(cudaMemsetAsync(ctx->cls_sizes.p, 0, m_cap * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cls_maxidx.p, 0, m_cap * 4, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_SCRATCH0, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(cnt + CNT_CLS_CURSOR, 0, 8, ctx->stream));
 
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
   LAUNCH(k_cls_mark, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>());
@@ -732,7 +732,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   const unsigned long long* okeys = ctx->cls_okeys_b.as<unsigned long long>();
   uint32_t* sidx = ctx->far_list.as<uint32_t>();
   LAUNCH(k_cls_members, nbw, 256, 0, d_labels, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>(), okeys, cnt + CNT_NFARPTS, bits, sidx, ctx->cls_seg.as<int>(),
-         cnt + CNT_SCRATCH0);
+         cnt + CNT_CLS_CURSOR);
   ClsArgs a;
   a.g = ctx->g;
   a.min_points = p.cls_min_points;

@@ -2,8 +2,8 @@
 //
 // The reference builds a kd-tree and grows clusters by BFS; the result is the set of connected components of
 // the graph "a ~ b  iff  fp32 ((ax-bx)^2 + (ay-by)^2) + (az-bz)^2 < float(tol^2)" (strict).  Here:
-//   K4  spatial hash: cell pitch slightly above tol, open-addressing table keyed by the packed cell, one
-//       linked list of point indices per occupied cell
+//   K4  spatial hash: cell pitch slightly above tol, open-addressing table keyed by the packed cell; the points of a
+//       cell are stored contiguously (count -> reserve -> fill)
 //   K5  one warp per point (one lane per neighbouring cell) scans the 27 cells and unites the point with every lower-indexed point
 //       inside the radius (lock-free union-find with randomised linking)
 //   K5b roots + atomicMin of the point index per root; K5c labels[i] = min index of i's component (the canonical label),
@@ -31,10 +31,11 @@ __device__ __forceinline__ unsigned cl_hash(unsigned long long k)
   return (unsigned)k;
 }
 
+// K4a: hash every point's cell; count the points per cell; remember the slot and the arrival rank of the point
 __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz, const int stride, const unsigned long long* __restrict__ d_m, const size_t m_cap,
-                                                   const double inv_cell, float4* __restrict__ pts, unsigned long long* __restrict__ tkey, int* __restrict__ thead,
-                                                   const unsigned tmask, int* __restrict__ next, int* __restrict__ parent, int* __restrict__ sizes,
-                                                   int* __restrict__ minidx, unsigned long long* __restrict__ watchdog)
+                                                   const double inv_cell, float4* __restrict__ pts, unsigned long long* __restrict__ tkey, int* __restrict__ tcount,
+                                                   const unsigned tmask, int* __restrict__ slot_of, int* __restrict__ rank_of, int* __restrict__ parent,
+                                                   int* __restrict__ sizes, int* __restrict__ minidx, unsigned long long* __restrict__ watchdog)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
@@ -44,11 +45,9 @@ __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz
     parent[i] = (int)i;
     sizes[i] = 0;
     minidx[i] = 0x7fffffff;
+    slot_of[i] = -1;
     if (inv_cell == 0.0)
-    {
-      next[i] = -1;
       continue;
-    }
     const unsigned long long key = cl_pack((long long)floor((double)x * inv_cell), (long long)floor((double)y * inv_cell), (long long)floor((double)z * inv_cell));
     unsigned slot = cl_hash(key) & tmask;
     unsigned probes = 0;
@@ -57,17 +56,46 @@ __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz
       const unsigned long long prev = atomicCAS(tkey + slot, CL_EMPTY, key);
       if (prev == CL_EMPTY || prev == key)
       {
-        next[i] = atomicExch(thead + slot, (int)i);
+        slot_of[i] = (int)slot;
+        rank_of[i] = atomicAdd(tcount + slot, 1);
         break;
       }
       slot = (slot + 1) & tmask;
       if (++probes > tmask)
       {
         atomicAdd(watchdog, 1ull);
-        next[i] = -1;
         break;
       }
     }
+  }
+}
+// K4b: the first point of every cell reserves the cell's contiguous range (any order will do)
+__global__ void __launch_bounds__(256) k_cl_alloc(const unsigned long long* __restrict__ d_m, const size_t m_cap, const int* __restrict__ slot_of,
+                                                  const int* __restrict__ rank_of, const int* __restrict__ tcount, int* __restrict__ tstart,
+                                                  unsigned long long* __restrict__ cursor)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int s = slot_of[i];
+    if (s >= 0 && rank_of[i] == 0)
+      tstart[s] = (int)atomicAdd(cursor, (unsigned long long)tcount[s]);
+  }
+}
+// K4c: cell-contiguous copy of the points: (x, y, z, index)
+__global__ void __launch_bounds__(256) k_cl_fill(const unsigned long long* __restrict__ d_m, const size_t m_cap, const float4* __restrict__ pts,
+                                                 const int* __restrict__ slot_of, const int* __restrict__ rank_of, const int* __restrict__ tstart,
+                                                 float4* __restrict__ cellpts)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int s = slot_of[i];
+    if (s < 0)
+      continue;
+    float4 p = pts[i];
+    p.w = __int_as_float((int)i);
+    cellpts[tstart[s] + rank_of[i]] = p;
   }
 }
 
@@ -117,11 +145,12 @@ __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
   }
 }
 
-// one WARP per point: lane l < 27 owns neighbour cell l (probe + walk of that cell's list), so the dependent-load chain of
-// a point is one cell long instead of 27 and a small cloud (10^4 points) still fills the machine
+// K5: one WARP per point, lane l < 27 owns neighbour cell l: one probe, then a walk over that cell's CONTIGUOUS point
+// range (independent 16-byte loads; a per-cell linked list makes the same walk a chain of dependent L2 round trips,
+// measured 68 us per call instead of ~20).
 __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const double inv_cell, const float r2,
-                                                  const float4* __restrict__ pts, const unsigned long long* __restrict__ tkey, const int* __restrict__ thead,
-                                                  const unsigned tmask, const int* __restrict__ next, int* __restrict__ parent)
+                                                  const float4* __restrict__ pts, const unsigned long long* __restrict__ tkey, const int* __restrict__ tcount,
+                                                  const int* __restrict__ tstart, const unsigned tmask, const float4* __restrict__ cellpts, int* __restrict__ parent)
 {
   if (inv_cell == 0.0)
     return;
@@ -133,7 +162,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
   for (size_t i = warp0; i < m; i += n_warps)
   {
     const float4 a = pts[i];
-    int j = -1;
+    int first = 0, count = 0;
     if (lane < 27)
     {
       const long long cx = (long long)floor((double)a.x * inv_cell), cy = (long long)floor((double)a.y * inv_cell), cz = (long long)floor((double)a.z * inv_cell);
@@ -144,7 +173,8 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         const unsigned long long k = tkey[slot];
         if (k == key)
         {
-          j = thead[slot];
+          first = tstart[slot];
+          count = tcount[slot];
           break;
         }
         if (k == CL_EMPTY)
@@ -152,12 +182,12 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         slot = (slot + 1) & tmask;
       }
     }
-    while (j >= 0)
+    for (int k = 0; k < count; k++)
     {
-      const int nj = next[j];
+      const float4 b = cellpts[first + k];
+      const int j = __float_as_int(b.w);
       if (j < (int)i)
       {
-        const float4 b = pts[j];
         // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
         float d2 = 0.0f;
         float diff = a.x - b.x;
@@ -169,7 +199,6 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         if (d2 < r2 && parent[i] != parent[j])  // same parent => already united (the usual case after compression)
           uf_union(parent, (int)i, j);
       }
-      j = nj;
     }
   }
 }
@@ -238,22 +267,31 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
     tsize <<= 1;
   ENSURE(ws.pts, m_cap * 16);
   ENSURE(ws.table_key, tsize * 8);
-  ENSURE(ws.table_head, tsize * 4);
-  ENSURE(ws.next, m_cap * 4);
+  ENSURE(ws.table_head, tsize * 4 * 2);  // per slot: point count, start of the cell's range
+  ENSURE(ws.next, m_cap * 4 * 2);        // per point: slot, arrival rank inside the cell
+  ENSURE(ws.cellpts, m_cap * 16);
   ENSURE(ws.parent, m_cap * 4);
   ENSURE(ws.sizes, m_cap * 4);
   ENSURE(ws.root, m_cap * 4);
   ENSURE(ws.minidx, m_cap * 4);
   CK(cudaMemsetAsync(ws.table_key.p, 0xFF, tsize * 8, ctx->stream));
-  CK(cudaMemsetAsync(ws.table_head.p, 0xFF, tsize * 4, ctx->stream));
+  CK(cudaMemsetAsync(ws.table_head.p, 0, tsize * 4, ctx->stream));  // counts
+  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_CL_CURSOR), 0, 8, ctx->stream));
+  int* tcount = ws.table_head.as<int>();
+  int* tstart = tcount + tsize;
+  int* slot_of = ws.next.as<int>();
+  int* rank_of = slot_of + m_cap;
   // pcl: r^2 = tolerance * tolerance evaluated in double, narrowed to the float the kd-tree compares with
   const float r2 = (float)((double)tol * (double)tol);
   // cell pitch a hair above tol: two points closer than tol in every axis always land in adjacent cells
   const double inv_cell = tol > 0.0f ? 1.0 / ((double)tol * (1.0 + 1e-6)) : 0.0;
-  LAUNCH(k_cl_insert, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_xyz, stride_floats, d_m, m_cap, inv_cell, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(),
-         ws.table_head.as<int>(), (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>(), ws.sizes.as<int>(), ws.minidx.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
-  LAUNCH(k_cl_union, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), ws.table_head.as<int>(),
-         (unsigned)(tsize - 1), ws.next.as<int>(), ws.parent.as<int>());
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  LAUNCH(k_cl_insert, nb, 256, 0, d_xyz, stride_floats, d_m, m_cap, inv_cell, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), tcount, (unsigned)(tsize - 1),
+         slot_of, rank_of, ws.parent.as<int>(), ws.sizes.as<int>(), ws.minidx.as<int>(), vf_cnt(ctx, CNT_WATCHDOG));
+  LAUNCH(k_cl_alloc, nb, 256, 0, d_m, m_cap, slot_of, rank_of, tcount, tstart, vf_cnt(ctx, CNT_CL_CURSOR));
+  LAUNCH(k_cl_fill, nb, 256, 0, d_m, m_cap, ws.pts.as<float4>(), slot_of, rank_of, tstart, ws.cellpts.as<float4>());
+  LAUNCH(k_cl_union, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, d_m, m_cap, inv_cell, r2, ws.pts.as<float4>(), ws.table_key.as<unsigned long long>(), tcount, tstart,
+         (unsigned)(tsize - 1), ws.cellpts.as<float4>(), ws.parent.as<int>());
   LAUNCH(k_cl_roots, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
   LAUNCH(k_cl_flatten, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;

@@ -125,7 +125,8 @@ struct ClusterWs
   DevBuf pts;        // float4 per point
   DevBuf table_key;  // u64 per slot
   DevBuf table_head; // i32 per slot
-  DevBuf next;       // i32 per point
+  DevBuf cellpts;    // float4 per point, grouped by cell (x, y, z, index)
+  DevBuf next;       // i32 x2 per point: hash slot, rank inside the cell
   DevBuf parent;     // i32 per point
   DevBuf sizes;      // i32 per point (size of the cluster labelled by this index)
   DevBuf root;       // i32 per point
@@ -272,6 +273,8 @@ enum
   CNT_NFARPTS,
   CNT_SEP_NENT,
   CNT_SEP_NUNIQ,
+  CNT_CL_CURSOR,      // range allocator of the clustering cell arrays
+  CNT_CLS_CURSOR,     // range allocator of the far-cluster member lists
   // ---- persistent slots (never zeroed by a map resize) ----
   CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
   CNT_EPOCH_BASE,     // generation base of the decoupled look-back states, advanced on the DEVICE once per API call (graph replay safe)

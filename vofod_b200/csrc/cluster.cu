@@ -158,12 +158,15 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
   const unsigned lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const int dz = (int)(lane / 9) - 1, dy = (int)((lane / 3) % 3) - 1, dx = (int)(lane % 3) - 1;
+  // every unordered pair of points is examined ONCE: lane 0 owns the point's own cell (pairs with a lower index only),
+  // lanes 1..13 the 13 "forward" neighbour cells (dz,dy,dx) > (0,0,0) in lexicographic order (all their points)
+  const int c = (int)lane + 13;  // 13 = the own cell in the 3x3x3 numbering
+  const int dz = c / 9 - 1, dy = (c / 3) % 3 - 1, dx = c % 3 - 1;
   for (size_t i = warp0; i < m; i += n_warps)
   {
     const float4 a = pts[i];
     int first = 0, count = 0;
-    if (lane < 27)
+    if (lane < 14)
     {
       const long long cx = (long long)floor((double)a.x * inv_cell), cy = (long long)floor((double)a.y * inv_cell), cz = (long long)floor((double)a.z * inv_cell);
       const unsigned long long key = cl_pack(cx + dx, cy + dy, cz + dz);
@@ -182,22 +185,33 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         slot = (slot + 1) & tmask;
       }
     }
-    for (int k = 0; k < count; k++)
+    int pi = parent[i];
+    for (int k0 = 0; k0 < count; k0 += 4)
     {
-      const float4 b = cellpts[first + k];
-      const int j = __float_as_int(b.w);
-      if (j < (int)i)
+      float4 b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        b[u] = cellpts[first + min(k0 + u, count - 1)];  // 4 independent loads in flight
+#pragma unroll
+      for (int u = 0; u < 4; u++)
       {
-        // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
-        float d2 = 0.0f;
-        float diff = a.x - b.x;
-        d2 += diff * diff;
-        diff = a.y - b.y;
-        d2 += diff * diff;
-        diff = a.z - b.z;
-        d2 += diff * diff;
-        if (d2 < r2 && parent[i] != parent[j])  // same parent => already united (the usual case after compression)
-          uf_union(parent, (int)i, j);
+        const int j = __float_as_int(b[u].w);
+        if (k0 + u < count && (lane != 0 || j < (int)i))
+        {
+          // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
+          float d2 = 0.0f;
+          float diff = a.x - b[u].x;
+          d2 += diff * diff;
+          diff = a.y - b[u].y;
+          d2 += diff * diff;
+          diff = a.z - b[u].z;
+          d2 += diff * diff;
+          if (d2 < r2 && parent[j] != pi)  // same parent => already united (the usual case after compression)
+          {
+            uf_union(parent, (int)i, j);
+            pi = parent[i];
+          }
+        }
       }
     }
   }

@@ -185,26 +185,39 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
         slot = (slot + 1) & tmask;
       }
     }
+    // spread the candidates of all 14 cells evenly over the 32 lanes (the fullest cell would otherwise set the pace)
+    const int incl = (int)prims::warp_incl_scan((uint32_t)count);
+    const int excl = incl - count;
+    const int total = __shfl_sync(VOFOD_FULL, incl, 31);
     int pi = parent[i];
-    for (int k0 = 0; k0 < count; k0 += 4)
+    for (int t0 = 0; t0 < total; t0 += 32)
     {
-      float4 b[4];
+      const int t = t0 + (int)lane;
+      // owner cell of candidate t: the largest lane l < 14 with excl_l <= t
+      int l = 0;
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        b[u] = cellpts[first + min(k0 + u, count - 1)];  // 4 independent loads in flight
-#pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int step = 8; step >= 1; step >>= 1)
       {
-        const int j = __float_as_int(b[u].w);
-        if (k0 + u < count && (lane != 0 || j < (int)i))
+        const int cand = l + step;
+        const int e = __shfl_sync(VOFOD_FULL, excl, cand & 31);
+        if (cand < 14 && e <= t)
+          l = cand;
+      }
+      const int f = __shfl_sync(VOFOD_FULL, first, l);
+      const int e0 = __shfl_sync(VOFOD_FULL, excl, l);
+      if (t < total)
+      {
+        const float4 b = cellpts[f + (t - e0)];
+        const int j = __float_as_int(b.w);
+        if (l != 0 || j < (int)i)
         {
           // FLANN L2_Simple: result += diff*diff over x, y, z (fp32, separately rounded)
           float d2 = 0.0f;
-          float diff = a.x - b[u].x;
+          float diff = a.x - b.x;
           d2 += diff * diff;
-          diff = a.y - b[u].y;
+          diff = a.y - b.y;
           d2 += diff * diff;
-          diff = a.z - b[u].z;
+          diff = a.z - b.z;
           d2 += diff * diff;
           if (d2 < r2 && parent[j] != pi)  // same parent => already united (the usual case after compression)
           {

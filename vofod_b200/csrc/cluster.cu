@@ -102,34 +102,31 @@ __global__ void __launch_bounds__(256) k_cl_fill(const unsigned long long* __res
 // Union-find on plain (L1-cacheable) loads.  A load may return an OLD value of parent[x]; every old value is x itself or an
 // ancestor of x, so walking it still climbs the tree, and the only decision that needs the truth — "a is a root, hang it
 // under b" — is taken by the atomicCAS, whose return value (always fresh) is where the walk continues when it fails.
-// Volatile loads here would all funnel into the one L2 sector that holds the root of the ground cluster (measured: 180 us).
-__device__ __forceinline__ int uf_find(int* __restrict__ parent, int a)
+// Two same-address hot spots had to go (both measured): volatile loads all funnel into the L2 sector that holds the root
+// of the ground cluster (180 us), and path compression inside find makes thousands of threads rewrite the same few
+// near-root entries.  So find is READ-ONLY here; trees stay shallow because (a) links go by a pseudo-random priority
+// (expected depth O(log n) — linking by index degenerates into one chain per grid row, the points arrive sorted by voxel
+// key) and (b) every point compresses only ITS OWN entry once, after its unions.
+__device__ __forceinline__ int uf_find(const int* __restrict__ parent, int a)
 {
-  // path halving; concurrent writers only ever replace a parent by one of its ancestors
   while (true)
   {
     const int p = parent[a];
     if (p == a)
       return a;
-    const int gp = parent[p];
-    if (gp != p)
-      parent[a] = gp;
     a = p;
   }
 }
-// Linking by index (larger under smaller) degenerates on this input: the points arrive sorted by voxel key, every point's
-// first neighbour is its predecessor, and the forest becomes one chain per grid row (finds of hundreds of dependent
-// loads).  Link by a pseudo-random priority instead (expected depth O(log n)); the canonical min-index label is computed
-// afterwards with one atomicMin per point.
 __device__ __forceinline__ unsigned uf_prio(const int a) { return (unsigned)a * 2654435761u; }  // odd multiplier: a bijection on u32
-__device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
+// unite the trees of roots-to-be a and b; returns the root both end up under (as far as this thread can tell)
+__device__ __forceinline__ int uf_link(int* __restrict__ parent, int a, int b)
 {
   while (true)
   {
     a = uf_find(parent, a);
     b = uf_find(parent, b);
     if (a == b)
-      return;
+      return a;
     if (uf_prio(a) < uf_prio(b))
     {
       const int t = a;
@@ -140,7 +137,7 @@ __device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b)
     // whether or not b is still a root.
     const int old = atomicCAS(parent + a, a, b);
     if (old == a)
-      return;
+      return b;
     a = old;  // a had been linked meanwhile: continue from its true parent
   }
 }
@@ -189,7 +186,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
     const int incl = (int)prims::warp_incl_scan((uint32_t)count);
     const int excl = incl - count;
     const int total = __shfl_sync(VOFOD_FULL, incl, 31);
-    int pi = parent[i];
+    int ri = (int)i;  // root of i as far as this lane knows
     for (int t0 = 0; t0 < total; t0 += 32)
     {
       const int t = t0 + (int)lane;
@@ -219,13 +216,23 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
           d2 += diff * diff;
           diff = a.z - b.z;
           d2 += diff * diff;
-          if (d2 < r2 && parent[j] != pi)  // same parent => already united (the usual case after compression)
+          if (d2 < r2)
           {
-            uf_union(parent, (int)i, j);
-            pi = parent[i];
+            const int rj = uf_find(parent, j);
+            ri = uf_find(parent, ri);
+            if (rj != ri)
+              ri = uf_link(parent, ri, rj);
           }
         }
       }
+    }
+    // compress this point's own entry (nobody else writes it once it is not a root)
+    __syncwarp();
+    if (lane == 0)
+    {
+      const int r = uf_find(parent, (int)i);
+      if (r != (int)i && parent[i] != r)
+        parent[i] = r;
     }
   }
 }

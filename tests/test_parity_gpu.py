@@ -289,6 +289,40 @@ def test_process_scan_small_gazebo_detections(gpu, cpu):
     assert n_det > 0
 
 
+def test_sepclusters_general_path_and_leaf2(gpu, cpu):
+    """The separated-background-cluster pass outside its leaf-size-1 fast path: forced general path (compaction ->
+    VoxelGridCounted radix sort), and max_bg_distance 1.2 m (ceil(2.4) = 3 -> leaf size 2, 125-offset ball)."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    gpu.set_option(3, 1)  # VOFOD_OPT_SEP_GENERAL
+    _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 26), fixed=True)
+    gpu.set_option(3, 0)
+    p.sep_max_bg_distance = 1.2
+    p.sep_min_sure_points = 6
+    _run_sequence(gpu, cpu, sensor, p, vs, 1, range(0, 26), fixed=True)
+
+
+def test_graph_replay_equals_kernel_by_kernel(gpu):
+    """CUDA-graph replay (default) and the kernel-by-kernel path must leave identical maps and results."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    outs = []
+    for graph in (1, 0):
+        gpu.set_option(abi.OPT_GRAPH, graph)
+        gpu.reset(p, vs)
+        gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        log = []
+        for k in range(40):
+            scan, pose, rp, _ = sensor.scan(1, k)
+            res, dets = gpu.process_scan(scan, pose, p, abi.schedule_s1(rp))
+            log.append((tuple(res.as_dict().items()), dets.tobytes()))
+        outs.append((log, gpu.map_download().tobytes()))
+    gpu.set_option(abi.OPT_GRAPH, 1)
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+
+
 def test_process_scan_small_vs_sequential_reference(gpu, cpu):
     sensor = Sensor(512, 32)
     p, vs = small_params()

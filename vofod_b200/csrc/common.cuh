@@ -221,7 +221,8 @@ struct vofod_ctx
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace
-  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets;
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff;
+  bool sep_force_general = false;  // test switch: never take the leaf-size-1 fast path
   int sep_off_n = -1, sep_off_mv = 0;
   float sep_off_md = 0.f;
 

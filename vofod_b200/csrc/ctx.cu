@@ -141,7 +141,7 @@ int vofod_destroy(vofod_ctx* ctx)
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
                     &ctx->far_keys_b, &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d,
-                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets,
+                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff,
                     &ctx->cls_sizes, &ctx->cls_maxidx, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms};
   for (DevBuf* b : bufs)
     free_buf(*b);
@@ -175,6 +175,12 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
   if (option == VOFOD_OPT_GRAPH)
   {
     ctx->graph_enabled = value != 0;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_SEP_GENERAL)
+  {
+    ctx->sep_force_general = value != 0;
+    ctx->alloc_gen++;
     return VOFOD_OK;
   }
   if (option == VOFOD_OPT_RAYCAST_NO_AGG)

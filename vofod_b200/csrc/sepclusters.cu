@@ -18,6 +18,142 @@ int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevB
                         const vofod_params* p);  // ctx.cu
 int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsigned long long* d_n, size_t cap, float leaf, float thr, DevBuf& out);  // voxelgrid.cu
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path for the reference's default geometry: ceil(max_bg_distance / voxel_size) == 2, i.e. VoxelGridCounted runs with
+// leaf size 1 on the integer voxel coordinates that voxelsAsVoxelPC emits.  Every input point then is its own leaf, and
+// the filter degenerates to a permutation:
+//     output r (r-th voxel in KEY order = storage order z,y,x) = centre (x+0.5, y+0.5, z+0.5) of that voxel,
+//     its count = [intensity > sure threshold] of the r-th voxel in INPUT order (= x-outer/z-inner emission order; this is
+//     the input-slice quirk of voxel_grid_counted.cpp:185-187 with runs of length one).
+// Both orders come out of ONE counting pass and ONE emission pass over the (dirty columns of the) grid — no sort:
+// a warp owns a 32-wide x segment of a row y and walks z; ballots give the rank inside the segment.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint8_t* __restrict__ dirty,
+                                                        const int nseg, uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segcnt)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
+  const size_t sxy = (size_t)sx * sy;
+  const int n_items = sy * nseg;
+  for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
+  {
+    const int y = item / nseg, seg = item % nseg;
+    const int x = seg * 32 + (int)lane;
+    const bool in = x < sx;
+    const size_t c = (size_t)y * sx + x;
+    const bool live = in && (!dirty || dirty[c]);
+    if (!__any_sync(VOFOD_FULL, live))
+    {
+      if (in)
+        colcnt[(size_t)x * sy + y] = 0;
+      continue;
+    }
+    uint32_t cnt = 0;
+    for (int z = 0; z < sz; z++)
+    {
+      const bool match = live && score[c + (size_t)z * sxy] > thr;
+      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
+      cnt += match;
+      if (bal && lane == 0)
+        segcnt[((size_t)z * sy + y) * nseg + seg] = __popc(bal);
+    }
+    if (in)
+      colcnt[(size_t)x * sy + y] = cnt;  // x-major: the scan then runs in the reference's emission order
+  }
+}
+__global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure,
+                                                       const uint8_t* __restrict__ dirty, const int nseg, const uint32_t* __restrict__ colcnt,
+                                                       const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds,
+                                                       uint32_t* __restrict__ flag_in_order, const size_t cap)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
+  const size_t sxy = (size_t)sx * sy;
+  const int n_items = sy * nseg;
+  for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
+  {
+    const int y = item / nseg, seg = item % nseg;
+    const int x = seg * 32 + (int)lane;
+    const bool in = x < sx;
+    const size_t c = (size_t)y * sx + x;
+    const bool live = in && colcnt[(size_t)(in ? x : 0) * sy + y] != 0;
+    if (!__any_sync(VOFOD_FULL, live))
+      continue;
+    size_t o = live ? coloff[(size_t)x * sy + y] : 0;
+    for (int z = 0; z < sz; z++)
+    {
+      const float v = live ? score[c + (size_t)z * sxy] : 0.0f;
+      const bool match = live && v > thr;
+      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
+      if (!bal)
+        continue;
+      const size_t base = segoff[((size_t)z * sy + y) * nseg + seg];
+      if (match)
+      {
+        const size_t r = base + __popc(bal & prims::lanemask_lt());
+        if (r < cap)
+        {
+          vofod_vox out;
+          out.x = (float)(x + g.st_lo[0]) + 0.5f;  // (float(ijk) + 0.5f) * 1 + float(min_b) with ijk = idx - min_b: exact
+          out.y = (float)(y + g.st_lo[1]) + 0.5f;
+          out.z = (float)(z + g.st_lo[2]) + 0.5f;
+          out.count = 0;
+          ds[r] = out;
+        }
+        if (o < cap)
+          flag_in_order[o] = v > thr_sure ? 1u : 0u;
+        o++;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_sep_fast_pair(vofod_vox* __restrict__ ds, const uint32_t* __restrict__ flag_in_order, const unsigned long long* __restrict__ d_k,
+                                                       const size_t cap)
+{
+  const size_t k = prims::dev_count(d_k, cap);
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < k; r += (size_t)gridDim.x * blockDim.x)
+    ds[r].count = flag_in_order[r];
+}
+
+// lists for the fast path; *host_total as in vf_compact_over_dev
+static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure, const vofod_params& p, size_t* host_total, size_t cap)
+{
+  using namespace prims;
+  const Geom& g = ctx->g;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  const int nseg = (g.st_size[0] + 31) / 32;
+  const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
+  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;
+  if (nsegs >= (size_t(1) << 31))
+    return 1;  // not representable here: use the general path
+  ENSURE(ctx->sep_colcnt, padded(ncol) * 4);
+  ENSURE(ctx->sep_coloff, padded(ncol) * 4);
+  ENSURE(ctx->sep_segcnt, padded(nsegs) * 4);
+  ENSURE(ctx->sep_segoff, padded(nsegs) * 4);
+  const uint8_t* dirty = vf_dirty_cols(ctx, thr, &p);
+  CK(cudaMemsetAsync(ctx->sep_segcnt.p, 0, nsegs * 4, ctx->stream));
+  const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * 32, 256, 8);
+  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
+  RET(scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncol, cnt + CNT_SEP_K));
+  RET(scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr));
+  if (host_total)
+  {
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, cnt + CNT_SEP_K, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *host_total = (size_t)total;
+    cap = (size_t)total;
+    if (total == 0)
+      return 0;
+  }
+  ENSURE(ctx->sep_ds, padded(cap) * sizeof(vofod_vox));
+  ENSURE(ctx->vg_flags, padded(cap) * 4);
+  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, dirty, nseg, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
+         ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cap);
+  LAUNCH(k_sep_fast_pair, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cnt + CNT_SEP_K, cap);
+  return 0;
+}
+
 // :1174-1183 — n_sure[cluster] = std::accumulate(range, int 0)
 __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__ ds, const int* __restrict__ labels, const unsigned long long* __restrict__ d_k,
                                                    const size_t cap, int* __restrict__ nsure)
@@ -110,27 +246,47 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   const float max_dist_idx = (float)(p.sep_max_bg_distance / (double)vs);  // :1142
   const int mv = (int)ceilf(max_dist_idx);                                 // :1143
   // :1146-1153 copy + voxelsAsVoxelPC (the private copy is unnecessary here: calls on a context are serialised)
-  size_t K = k_cap;
-  if (k_cap == 0)
-  {
-    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0, &p));
-    if (K == 0)
-      return VOFOD_W_EMPTY;  // :1155-1159
-  } else
-    RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, k_cap, &p));
-  const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   const float lsz = (float)(mv - 1 > 0 ? mv - 1 : 0);  // :1163
   if (!(lsz > 0.0f))
     return vf_fail(ctx, VOFOD_E_INVALID, "sepclusters: max_bg_distance/voxel_size <= 1 gives a zero leaf size (the reference divides by it)");
-  RET(vf_voxel_grid_counted_dev(ctx, ctx->sep_raw.as<vofod_xyzi>(), cnt + CNT_SEP_K, K, lsz, thr_sure, ctx->sep_ds));
+  size_t K = k_cap;
+  const unsigned long long* d_kds = cnt + CNT_SEP_KDS;
+  bool fast = lsz == 1.0f && !ctx->sep_force_general;
+  if (fast)
+  {
+    const int frc = sep_fast_lists(ctx, thr_new, thr_sure, p, k_cap == 0 ? &K : nullptr, k_cap);
+    if (frc < 0)
+      return frc;
+    fast = frc == 0;
+    if (fast)
+    {
+      if (k_cap == 0 && K == 0)
+        return VOFOD_W_EMPTY;  // :1155-1159
+      d_kds = cnt + CNT_SEP_K;  // every voxel is its own leaf
+      CK(cudaMemsetAsync(cnt + CNT_SEP_NUNIQ, 0, 8, ctx->stream));
+    }
+  }
+  if (!fast)
+  {
+    K = k_cap;
+    if (k_cap == 0)
+    {
+      RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0, &p));
+      if (K == 0)
+        return VOFOD_W_EMPTY;  // :1155-1159
+    } else
+      RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, k_cap, &p));
+    RET(vf_voxel_grid_counted_dev(ctx, ctx->sep_raw.as<vofod_xyzi>(), cnt + CNT_SEP_K, K, lsz, thr_sure, ctx->sep_ds));
+  }
+  const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, cnt + CNT_SEP_KDS, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
+  RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
   CK(cudaMemsetAsync(ctx->sep_nsure.p, 0, K * 4, ctx->stream));
   CK(cudaMemsetAsync(cnt + CNT_SEP_ANY_SURE, 0, 8, ctx->stream));
   const int nb = vf_blocks(ctx, K, 256, 8);
-  LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(), cnt + CNT_SEP_KDS, K, ctx->sep_nsure.as<int>());
-  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), cnt + CNT_SEP_KDS, K, min_sure, cnt);
+  LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(), d_kds, K, ctx->sep_nsure.as<int>());
+  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt);
   LAUNCH(k_sep_state, 1, 1, 0, cnt, cap_guard);
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)
   if (ctx->sep_off_n < 0 || ctx->sep_off_mv != mv || ctx->sep_off_md != max_dist_idx)
@@ -161,7 +317,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   volatile float w2v = 1.0f - w1;
   const float w2 = w2v;
   LAUNCH(k_sep_decay, vf_blocks(ctx, K * n_off, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(),
-         ctx->sep_nsure.as<int>(), cnt + CNT_SEP_KDS, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt, cap_guard);
+         ctx->sep_nsure.as<int>(), d_kds, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt, cap_guard);
   return VOFOD_OK;
 }
 

@@ -317,7 +317,7 @@ def test_graph_replay_equals_kernel_by_kernel(gpu):
         for k in range(40):
             scan, pose, rp, _ = sensor.scan(1, k)
             res, dets = gpu.process_scan(scan, pose, p, abi.schedule_s1(rp))
-            log.append((tuple(res.as_dict().items()), dets.tobytes()))
+            log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names)))  # fields, not struct padding
         outs.append((log, gpu.map_download().tobytes()))
     gpu.set_option(abi.OPT_GRAPH, 1)
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]

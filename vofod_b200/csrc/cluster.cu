@@ -75,11 +75,22 @@ __global__ void __launch_bounds__(256) k_cl_alloc(const unsigned long long* __re
                                                   unsigned long long* __restrict__ cursor)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
   {
-    const int s = slot_of[i];
-    if (s >= 0 && rank_of[i] == 0)
-      tstart[s] = (int)atomicAdd(cursor, (unsigned long long)tcount[s]);
+    const size_t i = i0 + lane;
+    const int s = i < m ? slot_of[i] : -1;
+    const bool first = s >= 0 && rank_of[i] == 0;
+    const uint32_t need = first ? (uint32_t)tcount[s] : 0u;
+    // one atomic per warp on the shared cursor
+    const uint32_t incl = prims::warp_incl_scan(need);
+    const uint32_t tot = __shfl_sync(VOFOD_FULL, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && tot)
+      base = atomicAdd(cursor, (unsigned long long)tot);
+    base = __shfl_sync(VOFOD_FULL, base, 31);
+    if (first)
+      tstart[s] = (int)(base + incl - need);
   }
 }
 // K4c: cell-contiguous copy of the points: (x, y, z, index)

@@ -49,13 +49,27 @@ __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict_
       continue;
     }
     uint32_t cnt = 0;
-    for (int z = 0; z < sz; z++)
+    for (int z0 = 0; z0 < sz; z0 += 8)
     {
-      const bool match = live && score[c + (size_t)z * sxy] > thr;
-      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
-      cnt += match;
-      if (bal && lane == 0)
-        segcnt[((size_t)z * sy + y) * nseg + seg] = __popc(bal);
+      // 8 independent loads in flight, then the (cheap) ballots
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = (live && z0 + k < sz) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        mine |= (v[k] > thr ? 1u : 0u) << k;
+      cnt += __popc(mine);
+      if (!__any_sync(VOFOD_FULL, mine != 0))
+        continue;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+        const unsigned bal = __ballot_sync(VOFOD_FULL, (mine >> k) & 1u);
+        if (bal && lane == 0)
+          segcnt[((size_t)(z0 + k) * sy + y) * nseg + seg] = __popc(bal);
+      }
     }
     if (in)
       colcnt[(size_t)x * sy + y] = cnt;  // x-major: the scan then runs in the reference's emission order
@@ -80,29 +94,43 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
     if (!__any_sync(VOFOD_FULL, live))
       continue;
     size_t o = live ? coloff[(size_t)x * sy + y] : 0;
-    for (int z = 0; z < sz; z++)
+    for (int z0 = 0; z0 < sz; z0 += 8)
     {
-      const float v = live ? score[c + (size_t)z * sxy] : 0.0f;
-      const bool match = live && v > thr;
-      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
-      if (!bal)
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = (live && z0 + k < sz) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        mine |= (v[k] > thr ? 1u : 0u) << k;
+      if (!__any_sync(VOFOD_FULL, mine != 0))
         continue;
-      const size_t base = segoff[((size_t)z * sy + y) * nseg + seg];
-      if (match)
+#pragma unroll
+      for (int k = 0; k < 8; k++)
       {
-        const size_t r = base + __popc(bal & prims::lanemask_lt());
-        if (r < cap)
+        const bool match = (mine >> k) & 1u;
+        const unsigned bal = __ballot_sync(VOFOD_FULL, match);
+        if (!bal)
+          continue;
+        const int z = z0 + k;
+        const size_t base = segoff[((size_t)z * sy + y) * nseg + seg];
+        if (match)
         {
-          vofod_vox out;
-          out.x = (float)(x + g.st_lo[0]) + 0.5f;  // (float(ijk) + 0.5f) * 1 + float(min_b) with ijk = idx - min_b: exact
-          out.y = (float)(y + g.st_lo[1]) + 0.5f;
-          out.z = (float)(z + g.st_lo[2]) + 0.5f;
-          out.count = 0;
-          ds[r] = out;
+          const size_t r = base + __popc(bal & prims::lanemask_lt());
+          if (r < cap)
+          {
+            vofod_vox out;
+            out.x = (float)(x + g.st_lo[0]) + 0.5f;  // (float(ijk) + 0.5f) * 1 + float(min_b) with ijk = idx - min_b: exact
+            out.y = (float)(y + g.st_lo[1]) + 0.5f;
+            out.z = (float)(z + g.st_lo[2]) + 0.5f;
+            out.count = 0;
+            ds[r] = out;
+          }
+          if (o < cap)
+            flag_in_order[o] = v[k] > thr_sure ? 1u : 0u;
+          o++;
         }
-        if (o < cap)
-          flag_in_order[o] = v > thr_sure ? 1u : 0u;
-        o++;
       }
     }
   }

@@ -105,6 +105,9 @@ typedef struct vofod_map_info {
   float voxel_size;
   uint64_t n_cells;
   int32_t slab_axis, slab_lo, slab_hi;  /* owned index range along slab_axis (whole axis when unsharded) */
+  int32_t storage_lo[3], storage_size[3]; /* box of global cells this context holds (= 0 / sizes when unsharded): the layout of
+                                             vofod_map_download / _upload is x + y*storage_size[0] + z*storage_size[0]*storage_size[1] */
+  int32_t _pad;
 } vofod_map_info;
 
 /* one entry per far cluster, in classification order (vofod_nodelet.cpp:110-119) */
@@ -267,8 +270,20 @@ int vofod_last_voxels(vofod_ctx*, vofod_vox* out, int32_t* labels, uint8_t* in_c
 int vofod_last_clusters(vofod_ctx*, vofod_cluster_info* out, size_t cap, size_t* n);
 
 /* ---- multi-GPU slab mode (no counterpart in the reference) ---------------------- */
-/* restrict this context to cells lo <= idx[axis] < hi of the global grid */
-int vofod_set_slab(vofod_ctx*, int axis, int lo, int hi);
+/* this context keeps only cells lo-halo <= idx[axis] < hi+halo of the global grid (axis 0 = x or 1 = y) and OWNS lo <= idx[axis] < hi.
+ * Call after vofod_map_resize / vofod_reset; the grid contents are unspecified afterwards (vofod_map_set_to).  Map downloads /
+ * uploads then address the storage box (vofod_map_info_get reports the global geometry and the own range). */
+int vofod_set_slab(vofod_ctx*, int axis, int lo, int hi, int halo);
+/* One scan of the MAPPING stages (seeds, filter/voxelize, cluster, close/far, point update, raycast accumulate + apply) in slab
+ * mode, in two phases.  Between them the caller combines, over all slabs, the two buffers vofod_slab_exchange_buffers returns:
+ * SUM of n_bg (u64[1]) and element-wise MAX of cluster_close (i32[n]) — ncclAllReduce on vofod_stream(), or a host loop through
+ * vofod_slab_exchange_io when several slabs are emulated on one device.  `scan` is a host pointer, or (scan_on_device) a device
+ * pointer, e.g. the target of the NCCL scan broadcast.  Classification / detections / sepclusters do not run in slab mode yet. */
+int vofod_slab_scan_begin(vofod_ctx*, const vofod_pt* scan, int scan_on_device, size_t n, const vofod_pose*, const vofod_params*,
+                          const vofod_schedule*);
+int vofod_slab_exchange_buffers(vofod_ctx*, void** d_n_bg, void** d_cluster_close, size_t* n_cluster_close);
+int vofod_slab_exchange_io(vofod_ctx*, uint64_t* n_bg, int32_t* cluster_close, size_t n, int to_device);
+int vofod_slab_scan_end(vofod_ctx*, const vofod_params*, const vofod_schedule*, vofod_scan_result* res);
 /* boundary fragments for the cross-slab cluster merge: points within `halo` cells of a slab face */
 int vofod_slab_boundary(vofod_ctx*, int32_t* point_idx, int32_t* labels, size_t cap, size_t* n);
 

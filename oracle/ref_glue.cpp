@@ -24,6 +24,8 @@ void vr_info(VoxelMap* m, vofod_map_info* out)
   out->n_cells = m->size();
   out->voxel_size = m->dimensions()[0] / float(s[0]);
   out->slab_axis = 0; out->slab_lo = 0; out->slab_hi = s[0];
+  for (int a = 0; a < 3; a++) { out->storage_lo[a] = 0; out->storage_size[a] = s[a]; }
+  out->_pad = 0;
 }
 float* vr_data(VoxelMap* m) { return &*m->begin(); }
 void vr_set_to(VoxelMap* m, float v) { m->setTo(v); }

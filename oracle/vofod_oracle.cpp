@@ -1262,6 +1262,8 @@ void vo_map_info_get(const Oracle* o, vofod_map_info* out)
   out->voxel_size = m.m_voxel_size;
   out->n_cells = m.size();
   out->slab_axis = 0; out->slab_lo = 0; out->slab_hi = m.m_size_x;
+  for (int a = 0; a < 3; a++) { out->storage_lo[a] = 0; out->storage_size[a] = out->sizes[a]; }
+  out->_pad = 0;
 }
 static vo::VoxelMap& which_map(Oracle* o, int which) { return which == VOFOD_MAP_SCORE ? o->voxel_map : which == VOFOD_MAP_FLAGS ? o->voxel_flags : o->voxel_raycast; }
 void vo_map_set_to(Oracle* o, int which, float v) { which_map(o, which).setTo(v); }

@@ -370,3 +370,54 @@ def test_golden_vectors_from_reference_build(gpu):
     want = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")))
     got = run_cases(GpuSide(gpu))
     compare(got, want, "libvofod_cuda")
+
+
+def test_slab_mode_emulated_on_one_gpu(cpu):
+    """Spatial-slab sharding of the grid (BASELINE configs[4]) with 3 slabs emulated as 3 contexts on one device: after every
+    scan each slab's storage box (own range + halo) must equal the matching slice of the monolithic oracle map bit for bit,
+    and the per-scan counts must agree.  The exchange (SUM n_bg, MAX cluster flags) is done on the host here; on several GPUs
+    it is an NCCL all-reduce (vofod_b200/slab.py)."""
+    from vofod_b200 import capi, multi
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    n_slab, halo = 3, 8
+    cpu.reset(p, vs)
+    cpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+    sx, sy, sz = list(cpu.map_info().sizes)
+    slabs = []
+    for r in range(n_slab):
+        g = capi.Vofod(0)
+        g.reset(p, vs)
+        lo, hi = multi.partition(sx, r, n_slab)
+        g.set_slab(0, lo, hi, halo)
+        g.map_set_to(abi.MAP_SCORE, p.score_init)
+        g.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        slabs.append(g)
+    try:
+        for k in range(26):
+            scan, pose, rp, _ = sensor.scan(0, k)
+            s = abi.schedule_s1(rp, do_classify=False, do_sepclusters=False)
+            for g in slabs:
+                g.slab_scan_begin(scan, pose, p, s)
+            parts = [g.slab_exchange_get(len(scan)) for g in slabs]
+            n_bg = sum(x[0] for x in parts)
+            close = np.maximum.reduce([x[1] for x in parts])
+            results = []
+            for g in slabs:
+                g.slab_exchange_set(n_bg, close)
+                results.append(g.slab_scan_end(p, s).as_dict())
+            cpu.set_modes(True, True, slabs[0].raycast_frac_bits() or 24)
+            want, _ = cpu.process_scan(scan, pose, p, s)
+            for r in results:
+                assert r == want.as_dict(), (k, r, want.as_dict())
+            full = cpu.map_download().reshape(sz, sy, sx)
+            flags = cpu.map_download(abi.MAP_FLAGS).reshape(sz, sy, sx)
+            for g in slabs:
+                mi = g.map_info()
+                x0, nx = mi.storage_lo[0], mi.storage_size[0]
+                assert np.array_equal(g.map_download().reshape(sz, sy, nx), full[:, :, x0:x0 + nx]), k   # own range AND halo
+                assert np.array_equal(g.map_download(abi.MAP_FLAGS).reshape(sz, sy, nx), flags[:, :, x0:x0 + nx]), k
+    finally:
+        for g in slabs:
+            g.close()

@@ -88,7 +88,8 @@ class Params(C.Structure):
 
 class MapInfo(C.Structure):
     _fields_ = [("offset", C.c_float * 3), ("sizes", C.c_int32 * 3), ("voxel_size", C.c_float), ("n_cells", C.c_uint64),
-                ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32)]
+                ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
+                ("storage_lo", C.c_int32 * 3), ("storage_size", C.c_int32 * 3), ("_pad", C.c_int32)]
 
 
 class ClusterInfo(C.Structure):

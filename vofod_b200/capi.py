@@ -77,7 +77,11 @@ def load_library():
         "vofod_process_scan_resident": (i32, [vp, i32, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
-        "vofod_set_slab": (i32, [vp, i32, i32, i32]),
+        "vofod_set_slab": (i32, [vp, i32, i32, i32, i32]),
+        "vofod_slab_scan_begin": (i32, [vp, vp, i32, sz, P(Pose), P(Params), P(Schedule)]),
+        "vofod_slab_exchange_buffers": (i32, [vp, P(vp), P(vp), P(sz)]),
+        "vofod_slab_exchange_io": (i32, [vp, P(C.c_uint64), vp, sz, i32]),
+        "vofod_slab_scan_end": (i32, [vp, P(Params), P(Schedule), P(ScanResult)]),
         "vofod_slab_boundary": (i32, [vp, vp, vp, sz, P(sz)]),
         "vofod_stage_times": (i32, [vp, vp]),
         "vofod_stage_name": (C.c_char_p, [i32]),
@@ -155,7 +159,9 @@ class Vofod:
         return mi
 
     def n_cells(self):
-        return int(self.map_info().n_cells)
+        """cells this context holds (= the whole grid unless vofod_set_slab cut it down)"""
+        mi = self.map_info()
+        return int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2])
 
     def map_set_to(self, which, value):
         self._ck(self.lib.vofod_map_set_to(self.h, which, float(value)))
@@ -376,8 +382,37 @@ class Vofod:
             self._ck(self.lib.vofod_last_clusters(self.h, _p(out), n.value, C.byref(n)))
         return out
 
-    def set_slab(self, axis, lo, hi):
-        self._ck(self.lib.vofod_set_slab(self.h, axis, lo, hi))
+    def set_slab(self, axis, lo, hi, halo):
+        self._ck(self.lib.vofod_set_slab(self.h, int(axis), int(lo), int(hi), int(halo)))
+
+    def slab_scan_begin(self, scan, pose, params, sched, device_ptr=None):
+        """scan: numpy array of PT_DTYPE on the host, or device_ptr = raw device address of the (broadcast) scan"""
+        if device_ptr is not None:
+            self._ck(self.lib.vofod_slab_scan_begin(self.h, C.c_void_p(device_ptr), 1, self.n_rays, C.byref(pose), C.byref(params), C.byref(sched)))
+        else:
+            scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+            self._ck(self.lib.vofod_slab_scan_begin(self.h, _p(scan), 0, len(scan), C.byref(pose), C.byref(params), C.byref(sched)))
+
+    def slab_exchange_buffers(self):
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.vofod_slab_exchange_buffers(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def slab_exchange_get(self, n):
+        nbg = C.c_uint64()
+        close = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.vofod_slab_exchange_io(self.h, C.byref(nbg), _p(close), n, 0))
+        return nbg.value, close
+
+    def slab_exchange_set(self, nbg, close):
+        v = C.c_uint64(int(nbg))
+        close = np.ascontiguousarray(close, dtype=np.int32)
+        self._ck(self.lib.vofod_slab_exchange_io(self.h, C.byref(v), _p(close), len(close), 1))
+
+    def slab_scan_end(self, params, sched):
+        res = ScanResult()
+        self._ck(self.lib.vofod_slab_scan_end(self.h, C.byref(params), C.byref(sched), C.byref(res)))
+        return res
 
     def stage_times(self):
         ms = np.zeros(abi.N_STAGES, dtype=np.float32)

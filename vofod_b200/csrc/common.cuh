@@ -76,6 +76,13 @@ __device__ inline bool has_close_to(const float* __restrict__ score, const Geom&
   return false;
 }
 
+// slab axis is horizontal (x or y): ownership is a property of the (x,y) column.  lx, ly = storage-local column coordinates.
+__device__ __forceinline__ bool column_owned(const Geom& g, const int lx, const int ly)
+{
+  const int v = g.slab_axis == 0 ? lx + g.st_lo[0] : ly + g.st_lo[1];
+  return v >= g.own_lo && v < g.own_hi;
+}
+
 // ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
 #define ACC_LEN_BITS 44
 __device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
@@ -197,6 +204,10 @@ struct vofod_ctx
   size_t acc_cells_max = 0;
 
   // CUDA-graph replay of vofod_process_scan
+  bool slab_on = false;         // this context holds a slab (own range + halo) of the global grid
+  int slab_halo = 0;
+  size_t slab_n = 0;            // rays of the scan between vofod_slab_scan_begin and _end (0 = none in flight)
+  int slab_raycast_status = 0;
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool graph_enabled = true;
   bool capturing = false;

@@ -304,25 +304,27 @@ __global__ void __launch_bounds__(256) k_count_over(const float* __restrict__ p,
 }
 
 // nVoxelsOver restricted to the columns that can hold a value above the threshold (see vofod_ctx::col_dirty)
+// blockIdx.y selects a chunk of 32 z-levels: a thread walking a whole column is a chain of ~20 dependent memory round trips,
+// which (not bandwidth) set the pace of this kernel
 __global__ void __launch_bounds__(128) k_count_over_cols(const float* __restrict__ p, const Geom g, const uint8_t* __restrict__ dirty, const float thr,
                                                          unsigned long long* out)
 {
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)ncol;
-  const int sz = g.st_size[2];
+  const int z_lo = blockIdx.y * 32, z_hi = min(z_lo + 32, g.st_size[2]);
   unsigned cnt = 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x)
   {
-    if (!dirty[c])
+    if ((dirty && !dirty[c]) || !column_owned(g, c % g.st_size[0], c / g.st_size[0]))
       continue;
-    for (int z0 = 0; z0 < sz; z0 += 8)
+    for (int z0 = z_lo; z0 < z_hi; z0 += 16)
     {
-      float v[8];
+      float v[16];
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = (z0 + k < sz) ? p[(size_t)c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+      for (int k = 0; k < 16; k++)
+        v[k] = (z0 + k < z_hi) ? p[(size_t)c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
 #pragma unroll
-      for (int k = 0; k < 8; k++)
+      for (int k = 0; k < 16; k++)
         cnt += v[k] > thr;
     }
   }
@@ -449,7 +451,7 @@ __global__ void k_compact_count(const float* __restrict__ score, const Geom g, c
   {
     const int x = c % g.st_size[0], y = c / g.st_size[0];
     uint32_t cnt = 0;
-    if (!dirty || dirty[c])
+    if ((!dirty || dirty[c]) && column_owned(g, x, y))
       for (int z = 0; z < g.st_size[2]; z++)
         cnt += ((score[(size_t)c + (size_t)z * sxy] > thr) == (greater != 0));
     colcnt[(size_t)x * g.st_size[1] + y] = cnt;  // x-major so that the scan runs in emission order
@@ -546,7 +548,7 @@ int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevB
   if (!ctx->map_ready)               \
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized (call vofod_map_resize / vofod_reset first)")
 
-static int map_alloc(vofod_ctx* ctx)
+int vf_map_alloc(vofod_ctx* ctx)
 {
   Geom& g = ctx->g;
   const long long n = geom_cells(g);
@@ -591,8 +593,9 @@ int vofod_map_resize_idx(vofod_ctx* ctx, const float offset[3], const int32_t si
   g.slab_axis = 0;
   g.own_lo = 0;
   g.own_hi = sizes[0];
+  ctx->slab_on = false;
   ctx->cfg_voxel_size = voxel_size;
-  return map_alloc(ctx);
+  return vf_map_alloc(ctx);
 }
 
 int vofod_map_resize(vofod_ctx* ctx, const float center[3], const float dims[3], float voxel_size)
@@ -647,6 +650,12 @@ int vofod_map_info_get(const vofod_ctx* ctx, vofod_map_info* out)
   out->slab_axis = g.slab_axis;
   out->slab_lo = g.own_lo;
   out->slab_hi = g.own_hi;
+  for (int a = 0; a < 3; a++)
+  {
+    out->storage_lo[a] = g.st_lo[a];
+    out->storage_size[a] = g.st_size[a];
+  }
+  out->_pad = 0;
   return VOFOD_OK;
 }
 
@@ -810,8 +819,9 @@ int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, cons
   const size_t n = (size_t)geom_cells(ctx->g);
   CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, p);
-  if (dirty)
-    LAUNCH(k_count_over_cols, vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 16), 128, 0, ctx->score.as<float>(), ctx->g, dirty, thr, d_out);
+  if (dirty || ctx->slab_on)  // a slab counts its own range only (halo columns belong to the neighbour)
+    LAUNCH(k_count_over_cols, dim3((unsigned)vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 4), (unsigned)((ctx->g.st_size[2] + 31) / 32)), 128, 0,
+           ctx->score.as<float>(), ctx->g, dirty, thr, d_out);
   else
     LAUNCH(k_count_over, vf_blocks(ctx, n / 4 + 1, 256, 8), 256, 0, ctx->score.as<float>(), n, thr, d_out);
   return 0;

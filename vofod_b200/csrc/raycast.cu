@@ -33,7 +33,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsi
 
 // RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
 // returns a few metres), so small blocks balance better: 128 threads = 4 warps = 128 neighbouring columns of one row.
-template <int RB, bool AGG>
+template <int RB, bool AGG, bool SLAB>
 __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
   int remx = 0, remy = 0, remz = 0;  // steps left before the ray stands in the last voxel of the map along that axis
   int dwx = 0, dwy = 0, dwz = 0;     // window-index stride of one step along each axis
   int widx = 0;
+  int spos = 0, sstep = 0;  // SLAB: window coordinate / step along the slab axis (the only axis a ray can leave the window on)
+  const int ssize = w.size[a.g.slab_axis];
   const int wn = w.size[0] * w.size[1] * w.size[2];
   if (alive)
   {
@@ -116,12 +118,18 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
     dwy = sty * w.size[0];
     dwz = stz * w.size[0] * w.size[1];
     widx = (cx - w.lo[0]) + (cy - w.lo[1]) * w.size[0] + (cz - w.lo[2]) * w.size[0] * w.size[1];
+    if (SLAB)
+    {
+      spos = a.g.slab_axis == 0 ? cx - w.lo[0] : (a.g.slab_axis == 1 ? cy - w.lo[1] : cz - w.lo[2]);
+      sstep = a.g.slab_axis == 0 ? stx : (a.g.slab_axis == 1 ? sty : stz);
+    }
     if (!(0.0f < len))  // while (prev_dist < length) with prev_dist = 0
       alive = false;
   }
   float prev = 0.0f;
   unsigned steps = 0;
   unsigned oob = 0;
+  bool anyq = false;  // some callback carried a positive path length <=> max_element(raycast) > 0 (:1542-1548)
   unsigned alive_mask = __ballot_sync(VOFOD_FULL, alive);
   while (alive_mask)
   {
@@ -134,7 +142,9 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
       const float dist = use_z ? tmz : d01;
       const float ddist = (len < dist ? len : dist) - prev;                                   // voxel_map.cpp:252
       const int q = __float2int_rn(ddist * a.scale);
-      const bool inside = (unsigned)widx < (unsigned)wn;  // always true: the window holds every voxel within max_dist
+      // unsharded: always true (the window holds every voxel within max_dist).  Slab: the window is cut at the slab's storage
+      // box, rays enter and leave it along the slab axis.
+      const bool inside = SLAB ? (unsigned)spos < (unsigned)ssize : (unsigned)widx < (unsigned)wn;
       const int key = inside ? widx : -1 - (int)lane;
       // lanes of the warp standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
       if (AGG)
@@ -145,7 +155,8 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
           red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
       } else if (inside)
         red_add_u64(acc + widx, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
-      oob += !inside;
+      oob += !SLAB && !inside;
+      anyq |= q > 0;
       steps++;
       prev = dist;
       // voxel_map.cpp:257-261
@@ -154,16 +165,21 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
       if (use_z)
       {
         remz--; tmz += tdz; widx += dwz;
+        if (SLAB && a.g.slab_axis == 2) spos += sstep;
       } else if (use_y)
       {
         remy--; tmy += tdy; widx += dwy;
+        if (SLAB && a.g.slab_axis == 1) spos += sstep;
       } else
       {
         remx--; tmx += tdx; widx += dwx;
+        if (SLAB && a.g.slab_axis == 0) spos += sstep;
       }
     }
     alive_mask = __ballot_sync(VOFOD_FULL, alive);
   }
+  if (__any_sync(VOFOD_FULL, anyq) && lane == 0)
+    atomicOr(counters + CNT_APPLY_ANY, 1ull);
   // per-block totals
   unsigned tot = prims::warp_sum(steps);
   unsigned toob = prims::warp_sum(oob);
@@ -240,7 +256,6 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     if (max_val == 0.0f)
       return;  // :1544-1548 (the host also skips the flag clear)
   }
-  bool any = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     const unsigned long long p = acc[i];
@@ -253,7 +268,6 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     const float rv = (float)((double)lq * a.inv_scale);
     if (!(rv > 0.0f))
       continue;
-    any = true;
     const int wx = (int)(i % wsx), wy = (int)((i / wsx) % wsy), wz = (int)(i / ((long long)wsx * wsy));
     const long long ci = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
     if (ci < 0 || flags[ci] != 0)  // flag == m_vflags_unmarked (:1561)
@@ -274,8 +288,6 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     const float w2 = 1.0f - w1;
     score[ci] = w1 * m + w2 * a.ray_score;                            // :1569 / :1597
   }
-  if (__any_sync(VOFOD_FULL, any) && (threadIdx.x & 31) == 0)
-    atomicOr(counters + CNT_APPLY_ANY, 1ull);
 }
 
 // m_voxel_flags.clear() (:1602) restricted to the cells flagged since the last clear; skipped when the apply was skipped
@@ -416,6 +428,7 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
   CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, ctx->stream));
   CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(cnt + CNT_APPLY_ANY, 0, 8, ctx->stream));
   // m_voxel_raycast.clear() (:1430): an accumulate that was never applied (or an old-rule apply that bailed out on
   // max_val == 0) must not leak into this one.  After a new-rule apply the accumulator is already all zero.
   if (ctx->acc_has_data)
@@ -432,12 +445,18 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.has_off = ctx->lut_has_off ? 1 : 0;
   constexpr int RB = 128;
   const int blocks = (int)((n + RB - 1) / RB);
+  const bool slab = ctx->slab_on;
+#define RAY_LAUNCH(AGG_, SLAB_)                                                                                                                              \
+  LAUNCH((k_raycast_accumulate<RB, AGG_, SLAB_>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),          \
+         ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt)
   if (ctx->raycast_no_agg)
-    LAUNCH((k_raycast_accumulate<RB, false>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
-           ctx->acc.as<unsigned long long>(), cnt);
-  else
-  LAUNCH((k_raycast_accumulate<RB, true>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(),
-         ctx->acc.as<unsigned long long>(), cnt);
+  {
+    if (slab) RAY_LAUNCH(false, true); else RAY_LAUNCH(false, false);
+  } else
+  {
+    if (slab) RAY_LAUNCH(true, true); else RAY_LAUNCH(true, false);
+  }
+#undef RAY_LAUNCH
   ctx->acc_has_data = true;
   return VOFOD_OK;
 }
@@ -449,7 +468,6 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   if (p.raycast_pause)
     return VOFOD_W_PAUSED;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  CK(cudaMemsetAsync(cnt + CNT_APPLY_ANY, 0, 8, ctx->stream));
   CK(cudaMemsetAsync(cnt + CNT_MAXVAL, 0, 8, ctx->stream));
   if (!ctx->win_valid || !ctx->acc_has_data)
     return VOFOD_W_EMPTY_RAYCAST;  // max_val == 0 (:1544-1548): nothing applied, flags NOT cleared

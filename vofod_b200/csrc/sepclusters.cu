@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, c
     if (!in_limits_idx(g, x, y, z))
       continue;
     const long long ci = cell_index(g, x, y, z);
-    if (ci < 0 || !cell_owned(g, x, y, z))
+    if (ci < 0)
       continue;
     unsigned* addr = reinterpret_cast<unsigned*>(score + ci);
     unsigned old = *addr;

@@ -252,6 +252,81 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
 
 
+def run_slab(args):
+    """Large-map mode (BASELINE.json configs[4]): 0.25 m voxels over 500 x 500 x 100 m (2001 x 2001 x 401 cells, 6.4 GB fp32
+    + 1.6 GB flags), the grid cut into N x-slabs, one per GPU; NCCL scan broadcast + all-reduce of the exchange buffers.
+    Mapping stages only (classification / sepclusters are not in slab mode yet).  Strong scaling: the same scans on 1..N GPUs."""
+    import torch
+    import torch.distributed as dist
+
+    from vofod_b200 import abi, capi, slab, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    K, Wm = args.steps, args.warmup
+    p = abi.default_params()
+    for i, (o, sz) in enumerate(zip((0.0, 0.0, -1.25), (500.0, 500.0, 100.0))):
+        p.oparea_offset[i] = o
+        p.oparea_size[i] = sz
+    p.raycast_max_distance = float(args.raycast_max)
+    dirs = synth.sim_lut(W, H)
+    v = capi.Vofod(local_rank)
+    worker = slab.SlabWorker(v, p, 0.25, (W, H), dirs, rank, world, halo=16)
+    N = W * H
+    n_scans = K + Wm
+    pinned = torch.empty((n_scans, N * abi.PT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+    poses, rps = [], []
+    if rank == 0:
+        host = pinned.numpy().view(abi.PT_DTYPE).reshape(n_scans, N)
+        for k in range(n_scans):
+            _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs, 2.5, out=host[k])
+            poses.append(pose)
+            rps.append(rp)
+    stream = worker.stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
+    trav = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for k in range(n_scans):
+        if k == Wm:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ev[k][0].record(stream)
+        res = worker.step(pinned[k] if rank == 0 else None, poses[k] if rank == 0 else None, rps[k] if rank == 0 else None)
+        ev[k][1].record(stream)
+        if k >= Wm:
+            trav += res.n_traversals
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total_ms = float(t[0])
+        mi = v.map_info()
+        print(json.dumps({
+            "metric": "scans/s", "value": K / (total_ms * 1e-3), "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores / u64 fixed-point path lengths", "data": "synthetic",
+            "config": {"workload": "cfg5 large map: 0.25 m voxels, 500x500x100 m (2001x2001x401 cells), x-slabs + 16-cell halo, mapping stages of schedule S1 "
+                                   "(seeds, filter/voxelize, cluster, close/far, point update, raycast accumulate+apply), raycast.max_distance %g m" % args.raycast_max,
+                       "parallelism": f"slab{world}: NCCL scan broadcast (5.2 MB) + all-reduce(SUM n_bg, MAX cluster flags)",
+                       "slab0_storage_cells": int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2]), "l2": "grid (GBs) far larger than L2"},
+            "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9, "traversals_per_scan": trav / K, "mode": "slab"}), flush=True)
+    v.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_baseline(n_scans, timed_from=2):
     """The oracle (CPU restatement of the reference's path) on the host, single thread, first scans of the same sequence."""
     from oracle import oracle  # the ONLY use of oracle/ in this file besides --impl reference: the reported CPU baseline
@@ -321,11 +396,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="streams", choices=["streams", "slab"],
+                    help="streams (default, the driver's contract): cfg2, one independent scan stream per GPU; slab: cfg5 large map cut into x-slabs")
+    ap.add_argument("--raycast-max", type=float, default=20.0, help="slab mode: raycast.max_distance [m] (yaml default 20, dynamic_reconfigure maximum 200)")
     ap.add_argument("--profile-leg", default="", choices=["", "graph", "eager"],
                     help="profiling aid: run ONLY the HBM-resident leg (graph replay or kernel-by-kernel) and print nothing the driver parses")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "slab":
+        run_slab(args)
     else:
         if args.warmup < 3:
             args.warmup = 3

@@ -244,12 +244,15 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(min(12, n_scans))
-    v.close()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    del stream, flush
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if out is not None:
-        print(json.dumps(out), flush=True)
+    torch.cuda.empty_cache()
+    v.close()
 
 
 def run_slab(args):
@@ -321,10 +324,12 @@ def run_slab(args):
                        "parallelism": f"slab{world}: NCCL scan broadcast (5.2 MB) + all-reduce(SUM n_bg, MAX cluster flags)",
                        "slab0_storage_cells": int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2]), "l2": "grid (GBs) far larger than L2"},
             "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9, "traversals_per_scan": trav / K, "mode": "slab"}), flush=True)
-    v.close()
+    del ev, stream
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    worker.close()
 
 
 def cpu_baseline(n_scans, timed_from=2):

@@ -58,3 +58,12 @@ class SlabWorker:
                 dist.all_reduce(nbg, op=dist.ReduceOp.SUM)
                 dist.all_reduce(close, op=dist.ReduceOp.MAX)
             return self.v.slab_scan_end(self.p, s)
+
+    def close(self):
+        """Release every torch object that lives on the library's stream BEFORE the context (and with it the stream) goes away."""
+        torch.cuda.synchronize()
+        self.scan_dev = None
+        self.meta = None
+        self.stream = None
+        torch.cuda.empty_cache()
+        self.v.close()

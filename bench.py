@@ -324,12 +324,14 @@ def run_slab(args):
                        "parallelism": f"slab{world}: NCCL scan broadcast (5.2 MB) + all-reduce(SUM n_bg, MAX cluster flags)",
                        "slab0_storage_cells": int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2]), "l2": "grid (GBs) far larger than L2"},
             "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9, "traversals_per_scan": trav / K, "mode": "slab"}), flush=True)
-    del ev, stream
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    worker.close()
+    # torch (caching allocators, NCCL) still holds events on the library's stream: leave the context to process exit and do
+    # not run torch's teardown against a destroyed stream
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def cpu_baseline(n_scans, timed_from=2):

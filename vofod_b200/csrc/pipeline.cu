@@ -621,9 +621,10 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
       if (hp[CNT_SEP_NUNIQ])
         return vf_fail(ctx, VOFOD_E_OVERFLOW, "sepclusters: voxel-grid index overflow");
     }
-    // keep the list comfortably larger than what the map currently holds (a change re-captures the graph)
+    // keep the list far larger than what the map currently holds: a change of capacity re-allocates and re-captures the graph
+    // (two kernel-by-kernel scans + one capture), which must stay a rare event while the map is being explored
     if (K * 5 / 4 + 1024 > ctx->sep_cap)
-      ctx->sep_cap = K * 2 + 65536;
+      ctx->sep_cap = K * 4 + (size_t(1) << 20);
   }
   ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
   ctx->sure_background_sufficient = sure_flag;

@@ -44,6 +44,15 @@ def make_params():
     return p
 
 
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None"""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_raycast_summary.json")
+    try:
+        return int(json.load(open(path))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -235,7 +244,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 64 * 8 + 16 * abi.DETECTION_DTYPE.itemsize, "ms_per_step": total_ms_e2e / K},
             "gpu_launches": int(tot_res["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_raycast_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": trav_per_launch * BYTES_PER_TRAVERSAL,
+                         "traffic": ncu_traffic(), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": trav_per_launch * BYTES_PER_TRAVERSAL,
                          "ms_per_launch": ray_ms_per_launch},
             "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot_res["stage"].items()},
             "stage_note": "stage times and the roofline kernel time come from a third, kernel-by-kernel leg (graph replay off): %.4f ms/step" % (sum(ms_eager) / K),

@@ -421,3 +421,22 @@ def test_slab_mode_emulated_on_one_gpu(cpu):
     finally:
         for g in slabs:
             g.close()
+
+
+def test_cfg3_full_size_detections(gpu, cpu):
+    """BASELINE.json configs[2] at full size: Gazebo-like scene (ground + 4 buildings + 3 sphere UAVs), 128 x 2048 rays,
+    cfg2 map, whole schedule S1 through bootstrap until detections fire; every scan compared with the oracle."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    n_det = _run_sequence(gpu, cpu, sensor, p, vs, 1, range(0, 24), fixed=True, check_maps_every=6)
+    assert n_det >= 3
+
+
+def test_quarter_metre_voxels(gpu, cpu):
+    """The cfg5 voxel size (0.25 m) on a map small enough for the oracle: exercises the larger exploreToGround horizon
+    (24 voxels), the 13-voxel submaps and the 2 197-point exact moment path."""
+    sensor = Sensor(1024, 64)
+    p = params_for((60.0, 60.0, 24.0))
+    p.background_sufficient_points_ratio = 0.03
+    n_det = _run_sequence(gpu, cpu, sensor, p, 0.25, 1, range(0, 30), fixed=True, check_maps_every=5)
+    assert n_det > 0

@@ -258,7 +258,12 @@ def _run_sequence(gpu, cpu, sensor, p, vs, scene, scans, fixed, check_maps_every
             assert np.array_equal(cg[f], cc[f]), (k, f)
         struct_close(cg, cc, ("aabb_min", "aabb_max"), rtol=0, atol=0)
         ok = cc["eig_gap"] > 1e-3                                         # OBB is ill-defined when eigenvalues tie
-        struct_close(cg[ok], cc[ok], ("obb_center", "obb_min", "obb_max"), rtol=1e-5, atol=1e-5)
+        # clusters that can pass the max_size gate (and so can become detections) are summed in the reference's order: 1e-5.
+        # Larger ones (always class `invalid`) use fp64 tree sums on the GPU; the reference's sequential fp32 sums over 10^3..10^4
+        # points carry ~1e-5 relative error themselves, so their reported box only agrees to ~1e-4.
+        small = cc["n_points"] <= (int(np.ceil(p.cls_max_size / vs)) + 2) ** 3
+        struct_close(cg[ok & small], cc[ok & small], ("obb_center", "obb_min", "obb_max"), rtol=1e-5, atol=1e-5)
+        struct_close(cg[ok & ~small], cc[ok & ~small], ("obb_center", "obb_min", "obb_max"), rtol=2e-4, atol=2e-4)
         assert len(dg) == len(dc)
         n_det += len(dc)
         for f in ("id", "label", "n_points"):

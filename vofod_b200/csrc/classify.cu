@@ -176,7 +176,8 @@ struct ClsArgs
 //     ALL lanes run the same sequential fp32 sums over them via shuffles — the reference's summation order, bit for bit,
 //     with the memory latency of the index indirection paid once per 32 points;
 //   n >  n_exact (cannot fit into max_size, so the class is `invalid` whatever the last bits are): lane-strided fp64
-//     partial sums + a fixed-shape warp reduction; the reported box agrees with the sequential fp32 one to ~1e-6.
+//     partial sums + a fixed-shape warp reduction; the reported box agrees with the sequential fp32 one to ~1e-4
+//     (measured 2e-5 on a 10^4-point cluster: the reference's own sequential fp32 sum is the less accurate of the two).
 __global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const ScanDyn* __restrict__ dyn, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
                                                      const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
                                                      vofod_cluster_info* __restrict__ out)

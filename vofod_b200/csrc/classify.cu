@@ -693,8 +693,8 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
 {
   using namespace prims;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  CK(cudaMemsetAsync(cnt + CNT_NDET, 0, 8, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_NFARPTS, 0, 8, ctx->stream));
+  ZERO_CNT(CNT_NDET, 1);
+  ZERO_CNT(CNT_NFARPTS, 1);
   if (m_cap == 0)
     return 0;
   const size_t np = padded(m_cap);
@@ -723,7 +723,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   ENSURE(ctx->cls_terms, terms_cap * 8);
   CK(cudaMemsetAsync(ctx->cls_sizes.p, 0, m_cap * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cls_maxidx.p, 0, m_cap * 4, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_CLS_CURSOR, 0, 8, ctx->stream));
+  ZERO_CNT(CNT_CLS_CURSOR, 1);
 
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
   LAUNCH(k_cls_mark, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>());

@@ -302,13 +302,17 @@ __global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __
 }
 
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol, int* d_labels,
-                   unsigned long long* d_ncl)
+                   unsigned long long* d_ncl, size_t table_points_hint)
 {
-  CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
+  const bool second_use = &ws == &ctx->cl_bg;  // the allocator cursor was already used by the scan's own clustering
+  if (!ctx->scan_prezero)
+    CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
   if (m_cap == 0)
     return 0;
+  // open addressing degrades gracefully: a table sized for the points EXPECTED (hint) still works up to its slot count
+  size_t want = table_points_hint && table_points_hint < m_cap ? table_points_hint : m_cap;
   size_t tsize = 1024;
-  while (tsize < 2 * m_cap)
+  while (tsize < 2 * want)
     tsize <<= 1;
   ENSURE(ws.pts, m_cap * 16);
   ENSURE(ws.table_key, tsize * 8);
@@ -321,7 +325,8 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   ENSURE(ws.minidx, m_cap * 4);
   CK(cudaMemsetAsync(ws.table_key.p, 0xFF, tsize * 8, ctx->stream));
   CK(cudaMemsetAsync(ws.table_head.p, 0, tsize * 4, ctx->stream));  // counts
-  CK(cudaMemsetAsync(vf_cnt(ctx, CNT_CL_CURSOR), 0, 8, ctx->stream));
+  if (!ctx->scan_prezero || second_use)
+    CK(cudaMemsetAsync(vf_cnt(ctx, CNT_CL_CURSOR), 0, 8, ctx->stream));
   int* tcount = ws.table_head.as<int>();
   int* tstart = tcount + tsize;
   int* slot_of = ws.next.as<int>();

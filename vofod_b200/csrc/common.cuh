@@ -195,6 +195,8 @@ struct vofod_ctx
   DevBuf d_counters;  // u32/u64 scratch counters (see enum below)
   DevBuf tile_state;  // u64 decoupled look-back states
   DevBuf sort_hist;   // u32 [passes][256]
+  bool scan_prezero = false;  // inside vofod_process_scan: k_begin_call zeroed every per-scan counter, the stages skip their own 8-byte memsets
+  size_t sep_table_hint = 0;  // hash-table sizing of the sepclusters clustering (points expected, not the list capacity)
   int epoch_local = 0;        // look-back launch number inside the current API call
   uint64_t epoch_calls = 0;   // host mirror of CNT_EPOCH_BASE / EPOCH_STRIDE
 
@@ -297,7 +299,7 @@ enum
 // ---- host helpers ----------------------------------------------------------------------------------
 int vf_fail(vofod_ctx* c, int code, const char* fmt, ...);
 int vf_ensure(vofod_ctx* c, DevBuf& b, size_t bytes);
-int vf_begin_call(vofod_ctx* ctx);  // advances the look-back generation; first thing of every entry point that sorts / scans
+int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters = false);  // advances the look-back generation; first thing of every entry point that sorts / scans
 int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
 #define CK(call)                                                                                         \
   do                                                                                                     \
@@ -314,6 +316,13 @@ int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
       return r__;          \
   } while (0)
 #define ENSURE(buf, bytes) RET(vf_ensure(ctx, buf, bytes))
+// zero `n` consecutive u64 counter slots, unless k_begin_call already did it for the whole scan
+#define ZERO_CNT(slot, n)                                                                        \
+  do                                                                                             \
+  {                                                                                              \
+    if (!ctx->scan_prezero)                                                                      \
+      CK(cudaMemsetAsync(vf_cnt(ctx, slot), 0, (size_t)(n) * 8, ctx->stream));                   \
+  } while (0)
 // kernel launch with accounting
 #define LAUNCH(kern, grid, block, smem, ...)                                                             \
   do                                                                                                     \
@@ -340,7 +349,7 @@ static inline unsigned long long* vf_cnt(vofod_ctx* c, int slot) { return c->d_c
 int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  // scan + pose come from ctx->dyn
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
-                   int* d_labels, unsigned long long* d_ncl);
+                   int* d_labels, unsigned long long* d_ncl, size_t table_points_hint = 0);
 // raycast.cu
 int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // scan comes from ctx->dyn
 int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // host only: OOB test + window -> h_dyn

@@ -234,16 +234,28 @@ void vofod_default_params(vofod_params* p)
 // ======================================================================================================
 // kernels
 // ======================================================================================================
-__global__ void k_begin_call(unsigned long long* __restrict__ counters) { counters[CNT_EPOCH_BASE] += EPOCH_STRIDE; }
+__global__ void k_begin_call(unsigned long long* __restrict__ counters, const int zero_scan_counters)
+{
+  if (threadIdx.x == 0)
+    counters[CNT_EPOCH_BASE] += EPOCH_STRIDE;
+  if (zero_scan_counters)
+  {
+    // every counter a scan accumulates into, in one place instead of ~15 eight-byte memset nodes
+    const int slots[] = {CNT_TRAVERSALS, CNT_OOB, CNT_APPLY_ANY, CNT_MAXVAL, CNT_NBG, CNT_NCLOSE, CNT_NFAR, CNT_NDET, CNT_NFARPTS, CNT_CLS_CURSOR,
+                         CNT_CL_CURSOR, CNT_SEP_K, CNT_SEP_NUNIQ, CNT_SEP_ANY_SURE, CNT_NCLUSTERS, CNT_SEP_NCL};
+    if (threadIdx.x < (int)(sizeof(slots) / sizeof(int)))
+      counters[slots[threadIdx.x]] = 0ull;
+  }
+}
 
-int vf_begin_call(vofod_ctx* ctx)
+int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters)
 {
   ctx->epoch_local = 0;
   ctx->epoch_calls++;
   // the generation field of a look-back state has 30 bits: before it can repeat, forget every old state
   if (((ctx->epoch_calls * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE && ctx->tile_state.p && !ctx->capturing)
     CK(cudaMemsetAsync(ctx->tile_state.p, 0, ctx->tile_state.cap, ctx->stream));
-  LAUNCH(k_begin_call, 1, 1, 0, ctx->d_counters.as<unsigned long long>());
+  LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0);
   return 0;
 }
 
@@ -817,7 +829,8 @@ const uint8_t* vf_dirty_cols(vofod_ctx* ctx, float thr, const vofod_params* p)
 int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, const vofod_params* p)
 {
   const size_t n = (size_t)geom_cells(ctx->g);
-  CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
+  if (!(ctx->scan_prezero && d_out == vf_cnt(ctx, CNT_NBG)))
+    CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, p);
   if (dirty || ctx->slab_on)  // a slab counts its own range only (halo columns belong to the neighbour)
     LAUNCH(k_count_over_cols, dim3((unsigned)vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 4), (unsigned)((ctx->g.st_size[2] + 31) / 32)), 128, 0,

@@ -216,7 +216,7 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
     volatile float a3 = a2 * p.background_sufficient_points_ratio;
     const unsigned long long min_sufficient = (unsigned long long)a3;
     LAUNCH(k_bg_state, 1, 1, 0, ctx->d_counters.as<unsigned long long>(), min_sufficient);
-    CK(cudaMemsetAsync(vf_cnt(ctx, CNT_NCLOSE), 0, 16, ctx->stream));  // NCLOSE, NFAR
+    ZERO_CNT(CNT_NCLOSE, 2);  // NCLOSE, NFAR
     if (m_cap)
       LAUNCH(k_close_finish, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_labels, d_m, m_cap, ctx->cl_close.as<int>(), ctx->pt_close.as<uint8_t>(),
              ctx->d_counters.as<unsigned long long>());
@@ -382,7 +382,13 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
       CK(cudaEventRecord(ctx->ev[e], st));    \
     e++;                                      \
   } while (0)
-  RET(vf_begin_call(ctx));
+  struct Prezero
+  {
+    vofod_ctx* c;
+    explicit Prezero(vofod_ctx* c_) : c(c_) { c->scan_prezero = true; }
+    ~Prezero() { c->scan_prezero = false; }
+  } prezero_guard(ctx);
+  RET(vf_begin_call(ctx, true));
   RET(vf_dyn_push(ctx));
   STAGE_EVENT();
   // rangefinder seeds (A23)
@@ -408,8 +414,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
   else
   {
-    CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, st));
-    CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, st));
+    ZERO_CNT(CNT_TRAVERSALS, 1);
+    ZERO_CNT(CNT_OOB, 1);
     // the reference clears m_voxel_raycast before the sensor-in-map test (:1430-1432)
     if (s.do_raycast && plan.raycast_status == VOFOD_W_SENSOR_OOB && ctx->acc_has_data && ctx->acc.p)
     {
@@ -426,13 +432,13 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     *applied_out = rc == VOFOD_OK;
   }
   STAGE_EVENT();  // 6 raycast "vmap update"
-  CK(cudaMemsetAsync(cnt + CNT_NDET, 0, 8, st));
+  ZERO_CNT(CNT_NDET, 1);
   if (s.do_classify)
     RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 7 "classification" (+ 8 detections, fused)
   STAGE_EVENT();
   *sep_status_out = VOFOD_W_PAUSED;
-  CK(cudaMemsetAsync(cnt + CNT_SEP_K, 0, 8, st));
+  ZERO_CNT(CNT_SEP_K, 1);
   if (s.do_sepclusters)
   {
     const int rc = vf_sepclusters_dev(ctx, s.sep_its_diff, p, plan.sep_cap);
@@ -503,6 +509,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   sig = fnv1a(&ctx->acc_cells_max, sizeof(size_t), sig);
   sig = fnv1a(&ctx->frac_bits, sizeof(int), sig);
   sig = fnv1a(&ctx->sep_cap, sizeof(size_t), sig);
+  sig = fnv1a(&ctx->sep_table_hint, sizeof(size_t), sig);
   sig = fnv1a(&ctx->alloc_gen, sizeof(uint64_t), sig);
   const int dirty_mode = ctx->col_all_dirty ? 1 : 0;
   sig = fnv1a(&dirty_mode, sizeof(int), sig);
@@ -625,6 +632,9 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     // (two kernel-by-kernel scans + one capture), which must stay a rare event while the map is being explored
     if (K * 5 / 4 + 1024 > ctx->sep_cap)
       ctx->sep_cap = K * 4 + (size_t(1) << 20);
+    // the clustering hash table is sized (and memset) for the points expected, not for the list capacity
+    if (K * 3 / 2 > ctx->sep_table_hint)
+      ctx->sep_table_hint = K * 3 + 65536;
   }
   ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
   ctx->sure_background_sufficient = sure_flag;

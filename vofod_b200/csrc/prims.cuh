@@ -208,6 +208,27 @@ __global__ void __launch_bounds__(NT) k_radix_pass(const KeyT* __restrict__ kin,
     uint32_t tot;
     gbase[threadIdx.x] = block_excl_scan(hist_pass[threadIdx.x], ws, tot);
   }
+  // a digit that has the same value in every key (the high digit of keys that do not use their full bit budget) leaves the
+  // order unchanged: plain copy, no ranking and no look-back chain
+  {
+    __shared__ int s_const;
+    if (threadIdx.x == 0)
+      s_const = 0;
+    __syncthreads();
+    if ((size_t)hist_pass[threadIdx.x] == n)
+      s_const = 1;
+    __syncthreads();
+    if (s_const)
+    {
+      for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n; i += (size_t)gridDim.x * NT)
+      {
+        kout[i] = kin[i];
+        if (HAS_VAL)
+          vout[i] = vin[i];
+      }
+      return;
+    }
+  }
   const int w = threadIdx.x >> 5;
   const unsigned lane = lane_id();
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)

@@ -426,9 +426,9 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
 {
   (void)tf;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_APPLY_ANY, 0, 8, ctx->stream));
+  ZERO_CNT(CNT_TRAVERSALS, 1);
+  ZERO_CNT(CNT_OOB, 1);
+  ZERO_CNT(CNT_APPLY_ANY, 1);
   // m_voxel_raycast.clear() (:1430): an accumulate that was never applied (or an old-rule apply that bailed out on
   // max_val == 0) must not leak into this one.  After a new-rule apply the accumulator is already all zero.
   if (ctx->acc_has_data)
@@ -468,7 +468,7 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   if (p.raycast_pause)
     return VOFOD_W_PAUSED;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  CK(cudaMemsetAsync(cnt + CNT_MAXVAL, 0, 8, ctx->stream));
+  ZERO_CNT(CNT_MAXVAL, 1);
   if (!ctx->win_valid || !ctx->acc_has_data)
     return VOFOD_W_EMPTY_RAYCAST;  // max_val == 0 (:1544-1548): nothing applied, flags NOT cleared
   ApplyArgs a;

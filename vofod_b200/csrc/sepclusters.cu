@@ -28,34 +28,35 @@ int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsi
 // Both orders come out of ONE counting pass and ONE emission pass over the (dirty columns of the) grid — no sort:
 // a warp owns a 32-wide x segment of a row y and walks z; ballots give the rank inside the segment.
 // ---------------------------------------------------------------------------------------------------------------
+// A warp owns (row y, 32-wide x segment, chunk of SEP_ZC z-levels): walking a whole column is a chain of ~20 dependent
+// memory round trips, which — not bandwidth — would set the pace.  Column counts are kept per (column, z-chunk) with the
+// chunk as the fastest index, so that their scan still runs in the reference's x-outer / z-inner emission order.
+#define SEP_ZC 32
 __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint8_t* __restrict__ dirty,
-                                                        const int nseg, uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segcnt)
+                                                        const int nseg, const int nzc, uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segcnt)
 {
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const size_t sxy = (size_t)sx * sy;
-  const int n_items = sy * nseg;
+  const int n_items = sy * nseg * nzc;
   for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
   {
-    const int y = item / nseg, seg = item % nseg;
+    const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
     const int x = seg * 32 + (int)lane;
     const bool in = x < sx;
     const size_t c = (size_t)y * sx + x;
-    const bool live = in && (!dirty || dirty[c]);
+    const bool live = in && (!dirty || dirty[c]) && column_owned(g, x, y);
     if (!__any_sync(VOFOD_FULL, live))
-    {
-      if (in)
-        colcnt[(size_t)x * sy + y] = 0;
-      continue;
-    }
+      continue;  // colcnt / segcnt were zero-filled
+    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
     uint32_t cnt = 0;
-    for (int z0 = 0; z0 < sz; z0 += 8)
+    for (int z0 = z_lo; z0 < z_hi; z0 += 8)
     {
       // 8 independent loads in flight, then the (cheap) ballots
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; k++)
-        v[k] = (live && z0 + k < sz) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+        v[k] = (live && z0 + k < z_hi) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
       unsigned mine = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++)
@@ -71,35 +72,37 @@ __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict_
           segcnt[((size_t)(z0 + k) * sy + y) * nseg + seg] = __popc(bal);
       }
     }
-    if (in)
-      colcnt[(size_t)x * sy + y] = cnt;  // x-major: the scan then runs in the reference's emission order
+    if (cnt)
+      colcnt[((size_t)x * sy + y) * nzc + zc] = cnt;
   }
 }
-__global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure,
-                                                       const uint8_t* __restrict__ dirty, const int nseg, const uint32_t* __restrict__ colcnt,
-                                                       const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds,
-                                                       uint32_t* __restrict__ flag_in_order, const size_t cap)
+__global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure, const int nseg,
+                                                       const int nzc, const uint32_t* __restrict__ colcnt, const uint32_t* __restrict__ coloff,
+                                                       const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds, uint32_t* __restrict__ flag_in_order,
+                                                       const size_t cap)
 {
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const size_t sxy = (size_t)sx * sy;
-  const int n_items = sy * nseg;
+  const int n_items = sy * nseg * nzc;
   for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
   {
-    const int y = item / nseg, seg = item % nseg;
+    const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
     const int x = seg * 32 + (int)lane;
     const bool in = x < sx;
     const size_t c = (size_t)y * sx + x;
-    const bool live = in && colcnt[(size_t)(in ? x : 0) * sy + y] != 0;
+    const size_t ci = ((size_t)(in ? x : 0) * sy + y) * nzc + zc;
+    const bool live = in && colcnt[ci] != 0;
     if (!__any_sync(VOFOD_FULL, live))
       continue;
-    size_t o = live ? coloff[(size_t)x * sy + y] : 0;
-    for (int z0 = 0; z0 < sz; z0 += 8)
+    size_t o = live ? coloff[ci] : 0;
+    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
+    for (int z0 = z_lo; z0 < z_hi; z0 += 8)
     {
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; k++)
-        v[k] = (live && z0 + k < sz) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
+        v[k] = (live && z0 + k < z_hi) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
       unsigned mine = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++)
@@ -150,19 +153,21 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   const Geom& g = ctx->g;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
   const int nseg = (g.st_size[0] + 31) / 32;
-  const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
-  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;
-  if (nsegs >= (size_t(1) << 31))
+  const int nzc = (g.st_size[2] + SEP_ZC - 1) / SEP_ZC;
+  const size_t ncc = (size_t)g.st_size[0] * g.st_size[1] * nzc;                // (column, z-chunk) counts
+  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;             // (z, y, x-segment) counts
+  if (nsegs >= (size_t(1) << 31) || ncc >= (size_t(1) << 31))
     return 1;  // not representable here: use the general path
-  ENSURE(ctx->sep_colcnt, padded(ncol) * 4);
-  ENSURE(ctx->sep_coloff, padded(ncol) * 4);
+  ENSURE(ctx->sep_colcnt, padded(ncc) * 4);
+  ENSURE(ctx->sep_coloff, padded(ncc) * 4);
   ENSURE(ctx->sep_segcnt, padded(nsegs) * 4);
   ENSURE(ctx->sep_segoff, padded(nsegs) * 4);
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, &p);
+  CK(cudaMemsetAsync(ctx->sep_colcnt.p, 0, ncc * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->sep_segcnt.p, 0, nsegs * 4, ctx->stream));
-  const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * 32, 256, 8);
-  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
-  RET(scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncol, cnt + CNT_SEP_K));
+  const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * nzc * 32, 256, 8);
+  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
+  RET(scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K));
   RET(scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr));
   if (host_total)
   {
@@ -176,7 +181,7 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   }
   ENSURE(ctx->sep_ds, padded(cap) * sizeof(vofod_vox));
   ENSURE(ctx->vg_flags, padded(cap) * 4);
-  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, dirty, nseg, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
+  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
          ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cap);
   LAUNCH(k_sep_fast_pair, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cnt + CNT_SEP_K, cap);
   return 0;
@@ -291,7 +296,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
       if (k_cap == 0 && K == 0)
         return VOFOD_W_EMPTY;  // :1155-1159
       d_kds = cnt + CNT_SEP_K;  // every voxel is its own leaf
-      CK(cudaMemsetAsync(cnt + CNT_SEP_NUNIQ, 0, 8, ctx->stream));
+      ZERO_CNT(CNT_SEP_NUNIQ, 1);
     }
   }
   if (!fast)
@@ -309,9 +314,10 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
+  RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
+                     k_cap ? ctx->sep_table_hint : 0));
   CK(cudaMemsetAsync(ctx->sep_nsure.p, 0, K * 4, ctx->stream));
-  CK(cudaMemsetAsync(cnt + CNT_SEP_ANY_SURE, 0, 8, ctx->stream));
+  ZERO_CNT(CNT_SEP_ANY_SURE, 1);
   const int nb = vf_blocks(ctx, K, 256, 8);
   LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(), d_kds, K, ctx->sep_nsure.as<int>());
   LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt);

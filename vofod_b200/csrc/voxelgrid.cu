@@ -40,7 +40,7 @@ struct MinMax
 {
   int mn[3], mx[3];
   unsigned n_valid;
-  unsigned pad;
+  unsigned n_append;  // cursor of the compacting writers
 };
 
 __global__ void k_minmax_init(MinMax* mm)
@@ -51,6 +51,7 @@ __global__ void k_minmax_init(MinMax* mm)
     mm->mx[a] = f2ord(-3.402823466e+38f);
   }
   mm->n_valid = 0;
+  mm->n_append = 0;
 }
 
 // block-wide min/max/count, then ONE set of 7 global atomics per block (a per-warp commit serialises ~8k warps on 7 words)
@@ -143,7 +144,30 @@ __global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const 
     Z = x * tf.R[6] + (y * tf.R[7] + (z * tf.R[8] + tf.t[2]));
     const bool outside2 = (X < a.op_min[0] || Y < a.op_min[1] || Z < a.op_min[2]) || (X > a.op_max[0] || Y > a.op_max[1] || Z > a.op_max[2]);
     valid = valid && isfinite(X) && isfinite(Y) && isfinite(Z) && !outside2;
-    pts[idx] = make_float4(X, Y, Z, valid ? 1.0f : 0.0f);
+  }
+  // survivors are written COMPACTLY (one cursor atomic per block): the sort then handles ~45 % of the rays, and no sentinel
+  // keys spoil its high digits.  Their order is scheduling dependent, which is harmless: only per-voxel COUNTS survive.
+  {
+    __shared__ unsigned s_wcnt[8], s_base;
+    const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(VOFOD_FULL, valid);
+    if (lane == 0)
+      s_wcnt[wrp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      unsigned tot = 0;
+      for (int i = 0; i < 8; i++)
+      {
+        const unsigned c = s_wcnt[i];
+        s_wcnt[i] = tot;
+        tot += c;
+      }
+      s_base = tot ? atomicAdd(&mm->n_append, tot) : 0u;
+    }
+    __syncthreads();
+    if (valid)
+      pts[s_base + s_wcnt[wrp] + __popc(bal & prims::lanemask_lt())] = make_float4(X, Y, Z, 1.0f);
   }
   block_minmax_commit(valid, X, Y, Z, mm);
 }
@@ -224,10 +248,12 @@ __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, con
 }
 
 // K1c — voxel_grid_weighted.cpp:122-139
-__global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, const int n, const VgLayout* __restrict__ Lp, uint32_t* __restrict__ keys)
+// `compact`: the first L.n_valid rows of pts are the valid points (k_crop_transform) and only those get keys
+__global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, const int n, const VgLayout* __restrict__ Lp, uint32_t* __restrict__ keys, const int compact)
 {
   const VgLayout L = *Lp;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+  const int rows = compact ? (int)L.n_valid : n;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows; i += gridDim.x * 256)
   {
     const float4 p = pts[i];
     uint32_t key = 0xFFFFFFFFu;
@@ -243,19 +269,22 @@ __global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts,
 }
 
 // K3a — run heads among the valid (non-sentinel) sorted keys
-__global__ void __launch_bounds__(256) k_vg_heads(const uint32_t* __restrict__ keys, const int n, uint32_t* __restrict__ heads)
+__global__ void __launch_bounds__(256) k_vg_heads(const uint32_t* __restrict__ keys, const int n, uint32_t* __restrict__ heads, const VgLayout* __restrict__ Lp,
+                                                  const int compact)
 {
+  const int rows = compact ? (int)Lp->n_valid : n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
   {
-    const uint32_t k = keys[i];
+    const uint32_t k = i < rows ? keys[i] : 0xFFFFFFFFu;
     heads[i] = (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
   }
 }
 // K3b — scatter run starts
 __global__ void __launch_bounds__(256) k_vg_starts(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ heads_scan, const int n, uint32_t* __restrict__ ukey,
-                                                   uint32_t* __restrict__ ustart)
+                                                   uint32_t* __restrict__ ustart, const VgLayout* __restrict__ Lp, const int compact)
 {
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+  const int rows = compact ? (int)Lp->n_valid : n;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < rows; i += gridDim.x * 256)
   {
     const uint32_t k = keys[i];
     if (k != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != k))
@@ -302,7 +331,8 @@ __global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restr
 
 // shared tail: pts (float4, w = validity) + minmax -> ctx->vox / CNT_VG_M.  key_bits_hint = 0 => sort all 32 bits.
 static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool align, const float* align_center, const int key_bits_hint, const vofod_xyzi* d_counted_in,
-                  const unsigned long long* d_counted_n, const float counted_thr, DevBuf& out_buf, const int slot_m = CNT_VG_M, const int slot_nvalid = CNT_VG_NVALID, const int slot_overflow = CNT_VG_OVERFLOW)
+                  const unsigned long long* d_counted_n, const float counted_thr, DevBuf& out_buf, const int slot_m = CNT_VG_M, const int slot_nvalid = CNT_VG_NVALID, const int slot_overflow = CNT_VG_OVERFLOW,
+                  const bool compact = false)
 {
   // `n` is the CAPACITY of the input (all kernels run over it); rows past the device-side count carry w == 0 (invalid)
   using namespace prims;
@@ -321,13 +351,15 @@ static int vg_run(vofod_ctx* ctx, const size_t n, const float leaf, const bool a
   const float ac[3] = {align ? align_center[0] : 0.f, align ? align_center[1] : 0.f, align ? align_center[2] : 0.f};
   LAUNCH(k_vg_layout, 1, 1, 0, mm, leaf, align ? 1 : 0, ac[0], ac[1], ac[2], L, cnt, slot_nvalid, slot_overflow);
   const int nb = vf_blocks(ctx, n, 256, 8);
-  LAUNCH(k_vg_keys, nb, 256, 0, ctx->vg_pts.as<float4>(), (int)n, L, ctx->vg_keys_a.as<uint32_t>());
+  LAUNCH(k_vg_keys, nb, 256, 0, ctx->vg_pts.as<float4>(), (int)n, L, ctx->vg_keys_a.as<uint32_t>(), compact ? 1 : 0);
+  // compact input: only the first n_valid rows exist; that count sits in the counter slot k_vg_layout filled
+  const unsigned long long* d_rows = compact ? cnt + slot_nvalid : nullptr;
   uint32_t* sorted = nullptr;
   const int bits = key_bits_hint > 0 && key_bits_hint < 32 ? key_bits_hint : 32;
-  RET((radix_sort<uint32_t, false>(ctx, ctx->vg_keys_a.as<uint32_t>(), ctx->vg_keys_b.as<uint32_t>(), nullptr, nullptr, nullptr, n, 0, bits, &sorted, nullptr)));
-  LAUNCH(k_vg_heads, nb, 256, 0, sorted, (int)n, ctx->vg_flags.as<uint32_t>());
+  RET((radix_sort<uint32_t, false>(ctx, ctx->vg_keys_a.as<uint32_t>(), ctx->vg_keys_b.as<uint32_t>(), nullptr, nullptr, d_rows, n, 0, bits, &sorted, nullptr)));
+  LAUNCH(k_vg_heads, nb, 256, 0, sorted, (int)n, ctx->vg_flags.as<uint32_t>(), L, compact ? 1 : 0);
   RET(scan_excl_u32(ctx, ctx->vg_flags.as<uint32_t>(), ctx->vg_scan.as<uint32_t>(), nullptr, n, cnt + slot_m));
-  LAUNCH(k_vg_starts, nb, 256, 0, sorted, ctx->vg_scan.as<uint32_t>(), (int)n, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>());
+  LAUNCH(k_vg_starts, nb, 256, 0, sorted, ctx->vg_scan.as<uint32_t>(), (int)n, ctx->vg_ukey.as<uint32_t>(), ctx->vg_ustart.as<uint32_t>(), L, compact ? 1 : 0);
   const uint32_t* over_prefix = nullptr;
   if (d_counted_in)
   {
@@ -395,7 +427,7 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
   for (int k = 0; k < 3; k++)
     cells *= (unsigned long long)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
   const int bits = cells + 1 < (1ull << 31) ? bits_for(cells + 1) : 32;
-  return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, nullptr, 0.f, ctx->vox);
+  return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, nullptr, 0.f, ctx->vox, CNT_VG_M, CNT_VG_NVALID, CNT_VG_OVERFLOW, true);
 }
 
 static int read_m(vofod_ctx* ctx, size_t* m, int* overflow)

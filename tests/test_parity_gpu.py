@@ -445,3 +445,53 @@ def test_quarter_metre_voxels(gpu, cpu):
     p.background_sufficient_points_ratio = 0.03
     n_det = _run_sequence(gpu, cpu, sensor, p, 0.25, 1, range(0, 30), fixed=True, check_maps_every=5)
     assert n_det > 0
+
+
+def test_staged_entry_points_reference_steady_state_schedule(gpu, cpu):
+    """Schedule S2 = what the reference's threads settle into: the raycast of scan k is applied only after
+    scan k+1 has done its point update (its_diff = 1, flags of BOTH scans still set), and only every other scan is raycast.
+    Driven through the STAGED entry points (one per L3 function of the nodelet) on both sides."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    setup_pair(cpu, gpu, p, vs, sensor)
+    pending = False
+    total_dets = 0
+    for k in range(30):
+        scan, pose, rp, _ = sensor.scan(1, k)
+        outs = []
+        for side in (gpu, cpu):
+            for _ in range(10):
+                side.range_update(rp, p)
+            vox = side.filter_voxelize(scan, pose, p)
+            labels, ncl = side.cluster(np.stack([vox["x"], vox["y"], vox["z"]], 1), p.ground_points_max_distance)
+            close, n_bg = side.close_far(vox, labels, p)
+            side.update_points(vox, close, 1, p.score_point, 2.0)
+            side.update_points(vox, close, 0, p.score_unknown, 3.0)
+            outs.append((vox, labels, ncl, close, n_bg))
+        (vg, lg, ng, cg, bg), (vc, lc, nc, cc, bc) = outs
+        assert_vox_equal(vg, vc)
+        assert ng == nc and bg == bc and np.array_equal(lg, lc) and np.array_equal(cg, cc)
+        if pending:                      # the raycast thread wakes up: apply scan k-1's rays, then clear the flags
+            assert gpu.raycast_apply(1, p) == cpu.raycast_apply(1, p)
+            pending = False
+        elif k % 2 == 0:                 # no raycast in flight: start one for this scan
+            rg, tg = gpu.raycast_accumulate(scan, pose, p)
+            cpu.set_modes(True, True, gpu.raycast_frac_bits())
+            rc, tc = cpu.raycast_accumulate(scan, pose, p)
+            assert (rg, tg) == (rc, tc)
+            pending = True
+        dg, ig = gpu.classify_detect(vg, lg, cg, pose, p)
+        dc, ic = cpu.classify_detect(vc, lc, cc, pose, p)
+        assert len(dg) == len(dc) and len(ig) == len(ic)
+        for f in ("label", "n_points", "cclass"):
+            assert np.array_equal(ig[f], ic[f]), (k, f)
+        for f in ("id", "label", "n_points"):
+            assert np.array_equal(dg[f], dc[f])
+        struct_close(dg, dc, ("position", "confidence", "detection_probability"), rtol=1e-5, atol=1e-7)
+        total_dets += len(dc)
+        assert gpu.sepclusters(1, p) == cpu.sepclusters(1, p)
+        assert gpu.state_get() == cpu.state_get()
+        assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
+        assert np.array_equal(gpu.map_download(abi.MAP_FLAGS), cpu.map_download(abi.MAP_FLAGS)), k
+    assert total_dets > 0

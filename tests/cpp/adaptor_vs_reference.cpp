@@ -1,0 +1,123 @@
+// The same sequence of calls on the REFERENCE's vofod::VoxelMap (from oracle/_ref/libvofod_ref.so = /root/reference/src/voxel_map.cpp
+// compiled in place) and on the GPU-backed adaptor vofod_b200::VoxelMap; every observable result must agree.
+// Built by tests/cpp/Makefile in the authoring container (needs /root/reference/include), run on the GPU box by
+// tests/test_parity_gpu.py::test_cpp_adaptor_against_reference_class.
+#include <vofod/voxel_map.h>
+#include <vofod_b200/voxel_map.hpp>
+
+#include <cstdio>
+#include <random>
+#include <set>
+
+#define CHECK(cond)                                                     \
+  do                                                                    \
+  {                                                                     \
+    if (!(cond))                                                        \
+    {                                                                   \
+      std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);     \
+      return 1;                                                         \
+    }                                                                   \
+  } while (0)
+
+int main()
+{
+  using R = vofod::VoxelMap;
+  using G = vofod_b200::VoxelMap;
+  R ref;
+  G gpu;
+  const R::vec3_t center(1.0f, -2.0f, 3.0f), dims(30.0f, 20.0f, 10.0f);
+  ref.resize(center, dims, 0.5f);
+  gpu.resize(G::vec3_t(1.0f, -2.0f, 3.0f), G::vec3_t(30.0f, 20.0f, 10.0f), 0.5f);
+  CHECK(ref.size() == gpu.size());
+  CHECK(ref.sizesIdx() == gpu.sizesIdx());
+  for (int a = 0; a < 3; a++)
+    CHECK(ref.origin()[a] == gpu.origin()[a] && ref.dimensions()[a] == gpu.dimensions()[a]);
+  ref.setTo(-740.0f);
+  gpu.setTo(-740.0f);
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<float> ux(-13.9f, 15.9f), uy(-11.9f, 7.9f), uz(-1.9f, 7.9f), uv(-1000.0f, 0.0f);
+  // writes through at(x,y,z) references (host mirror on the GPU side)
+  for (int i = 0; i < 5000; i++)
+  {
+    const float x = ux(rng), y = uy(rng), z = uz(rng), v = uv(rng);
+    CHECK(ref.coordToIdx(x, y, z) == gpu.coordToIdx(x, y, z));
+    CHECK(ref.inLimits(x, y, z) == gpu.inLimits(x, y, z));
+    ref.at(x, y, z) = v;
+    gpu.at(x, y, z) = v;
+  }
+  for (float thr : {-300.0f, -0.1f, -750.0f})
+    CHECK(ref.nVoxelsOver(thr) == gpu.nVoxelsOver(thr));
+  {
+    const auto a = ref.voxelsAsVoxelPC(-300.0f), b = gpu.voxelsAsVoxelPC(-300.0f);
+    CHECK(a->size() == b->size());
+    for (size_t i = 0; i < a->size(); i++)  // same cells in the same (x-outer, z-inner) order
+      CHECK(a->points[i].x == b->points[i].x && a->points[i].y == b->points[i].y && a->points[i].z == b->points[i].z && a->points[i].intensity == b->points[i].intensity);
+    const auto c = ref.voxelsAsPC(-500.0f), d = gpu.voxelsAsPC(-500.0f);
+    CHECK(c->size() == d->size());
+    for (size_t i = 0; i < c->size(); i++)
+      CHECK(c->points[i].x == d->points[i].x && c->points[i].z == d->points[i].z && c->points[i].intensity == d->points[i].intensity);
+  }
+  for (int i = 0; i < 3000; i++)
+  {
+    const float x = ux(rng), y = uy(rng), z = uz(rng);
+    CHECK(ref.hasCloseTo(x, y, z, 1.5f, -300.0f) == gpu.hasCloseTo(x, y, z, 1.5f, -300.0f));
+    CHECK(ref.isFloating(x, y, z, -300.0f) == gpu.isFloating(x, y, z, -300.0f));
+  }
+  // forEachRay: identical callback sequences
+  std::normal_distribution<float> nd;
+  for (int i = 0; i < 300; i++)
+  {
+    R::vec3_t s(ux(rng), uy(rng), uz(rng)), d(nd(rng), nd(rng), nd(rng));
+    const float nrm = std::sqrt(d.x() * d.x() + d.y() * d.y() + d.z() * d.z());
+    d = d / nrm;
+    const float len = 0.05f * float(i) - 1.0f;
+    std::vector<std::tuple<float, int, int, int>> a, b;
+    ref.forEachRay(s, d, len, [&](float dd, int x, int y, int z) { a.emplace_back(dd, x, y, z); });
+    gpu.forEachRay(G::vec3_t(s.x(), s.y(), s.z()), G::vec3_t(d.x(), d.y(), d.z()), len, [&](float dd, int x, int y, int z) { b.emplace_back(dd, x, y, z); });
+    CHECK(a == b);
+  }
+  // exploreToGround: same verdict, same cell set
+  ref.setTo(-1000.0f);
+  gpu.setTo(-1000.0f);
+  std::uniform_real_distribution<float> u01(0.0f, 1.0f);
+  ref.forEachIdx([&](float& v, int, int, int) { v = u01(rng) < 0.42f ? -740.0f : -1000.0f; });
+  {
+    // copy the reference's contents cell by cell through the adaptor's own visitor
+    gpu.forEachIdx([&](float& v, int x, int y, int z) { v = ref.atIdx(x, y, z); });
+  }
+  for (int i = 0; i < 60; i++)
+  {
+    const float x = ux(rng) * 0.8f, y = uy(rng) * 0.8f, z = 1.0f + 0.1f * float(i % 50);
+    const float md = float(2 + i % 11);
+    const auto [ca, ea] = ref.exploreToGround(x, y, z, -750.0f, -300.0f, md);
+    const auto [cb, eb] = gpu.exploreToGround(x, y, z, -750.0f, -300.0f, md);
+    CHECK(ca == cb);
+    if (!ca)
+      CHECK(std::set<R::idx3_t>(ea.begin(), ea.end()) == std::set<G::idx3_t>(eb.begin(), eb.end()));
+  }
+  // getSubmapCopy
+  {
+    R sa = ref.getSubmapCopy(R::vec3_t(-3.0f, -2.0f, 2.0f), R::vec3_t(2.2f, 1.1f, 5.0f), 2);
+    G sb = gpu.getSubmapCopy(G::vec3_t(-3.0f, -2.0f, 2.0f), G::vec3_t(2.2f, 1.1f, 5.0f), 2);
+    CHECK(sa.sizesIdx() == sb.sizesIdx());
+    for (int a = 0; a < 3; a++)
+      CHECK(sa.origin()[a] == sb.origin()[a]);
+    auto ia = sa.begin();
+    auto ib = sb.begin();
+    for (; ia != sa.end(); ++ia, ++ib)
+      CHECK(*ia == *ib);
+  }
+  // std::vector::at semantics on a bad index
+  bool threw = false;
+  try
+  {
+    gpu.atIdx(10000, 0, 0);
+  }
+  catch (const std::out_of_range&)
+  {
+    threw = true;
+  }
+  CHECK(threw);
+  std::printf("adaptor == reference class: OK\n");
+  return 0;
+}

@@ -495,3 +495,15 @@ def test_staged_entry_points_reference_steady_state_schedule(gpu, cpu):
         assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
         assert np.array_equal(gpu.map_download(abi.MAP_FLAGS), cpu.map_download(abi.MAP_FLAGS)), k
     assert total_dets > 0
+
+
+def test_cpp_adaptor_against_reference_class():
+    """include/vofod_b200/voxel_map.hpp (GPU-backed class with vofod::VoxelMap's public interface) next to the reference's own
+    vofod::VoxelMap, same calls, in one C++ program (tests/cpp/adaptor_vs_reference.cpp)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", "adaptor_vs_reference")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_build/adaptor_vs_reference not built (needs the reference headers: make -C tests/cpp)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr

@@ -111,7 +111,7 @@ int main()
   bool threw = false;
   try
   {
-    gpu.atIdx(10000, 0, 0);
+    gpu.atIdx(0, 0, 100000);  // linear index beyond the array (an in-array overshoot is accepted by the reference too)
   }
   catch (const std::out_of_range&)
   {

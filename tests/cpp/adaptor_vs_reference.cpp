@@ -2,7 +2,10 @@
 // compiled in place) and on the GPU-backed adaptor vofod_b200::VoxelMap; every observable result must agree.
 // Built by tests/cpp/Makefile in the authoring container (needs /root/reference/include), run on the GPU box by
 // tests/test_parity_gpu.py::test_cpp_adaptor_against_reference_class.
+#include <vofod/voxel_grid_counted.h>
+#include <vofod/voxel_grid_weighted.h>
 #include <vofod/voxel_map.h>
+#include <vofod_b200/voxel_grids.hpp>
 #include <vofod_b200/voxel_map.hpp>
 
 #include <cstdio>
@@ -118,6 +121,47 @@ int main()
     threw = true;
   }
   CHECK(threw);
+  // the two voxel filters: same setInputCloud / setLeafSize / setVoxelAlign / filter calls on both classes
+  {
+    auto in = boost::make_shared<pcl::PointCloud<ouster_ros::Point>>();
+    auto in_i = boost::make_shared<pcl::PointCloud<pcl::PointXYZI>>();
+    std::normal_distribution<float> gx(0.f, 20.f), gz(0.f, 4.f);
+    for (int i = 0; i < 30000; i++)
+    {
+      ouster_ros::Point p;
+      p.x = gx(rng); p.y = gx(rng); p.z = gz(rng);
+      in->points.push_back(p);
+      pcl::PointXYZI q;
+      q.x = std::floor(p.x); q.y = std::floor(p.y); q.z = std::floor(p.z);
+      q.intensity = u01(rng) * 1.5f - 1.0f;
+      in_i->points.push_back(q);
+    }
+    pcl::PointCloud<vofod::PointXYZR> a, b, c, d;
+    vofod::VoxelGridWeighted rw;
+    rw.setInputCloud(in);
+    rw.setLeafSize(0.5f, 0.5f, 0.5f);
+    rw.setVoxelAlign(Eigen::Vector4f(-99.75f, -99.75f, -1.0f, 0.f));
+    rw.filter(a);
+    vofod_b200::VoxelGridWeighted<ouster_ros::Point, vofod::PointXYZR> gw(gpu.handle());
+    gw.setInputCloud(in);
+    gw.setLeafSize(0.5f, 0.5f, 0.5f);
+    gw.setVoxelAlign(Eigen::Vector4f(-99.75f, -99.75f, -1.0f, 0.f));
+    gw.filter(b);
+    CHECK(a.points.size() == b.points.size() && !a.points.empty());
+    for (size_t i = 0; i < a.points.size(); i++)
+      CHECK(a.points[i].x == b.points[i].x && a.points[i].y == b.points[i].y && a.points[i].z == b.points[i].z && a.points[i].range == b.points[i].range);
+    vofod::VoxelGridCounted rc(-0.1f);
+    rc.setInputCloud(in_i);
+    rc.setLeafSize(1.0f, 1.0f, 1.0f);
+    rc.filter(c);
+    vofod_b200::VoxelGridCounted<pcl::PointXYZI, vofod::PointXYZR> gc(gpu.handle(), -0.1f);
+    gc.setInputCloud(in_i);
+    gc.setLeafSize(1.0f, 1.0f, 1.0f);
+    gc.filter(d);
+    CHECK(c.points.size() == d.points.size() && !c.points.empty());
+    for (size_t i = 0; i < c.points.size(); i++)
+      CHECK(c.points[i].x == d.points[i].x && c.points[i].y == d.points[i].y && c.points[i].z == d.points[i].z && c.points[i].range == d.points[i].range);
+  }
   std::printf("adaptor == reference class: OK\n");
   return 0;
 }

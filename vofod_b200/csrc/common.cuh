@@ -148,6 +148,8 @@ struct vofod_ctx
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // side branch for work that is independent of the main chain (raycast accumulate, second scan)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t n_launches = 0;
 
@@ -194,6 +196,7 @@ struct vofod_ctx
   DevBuf vox;       // vofod_vox per output voxel (cloud_weighted of the last scan)
   DevBuf d_counters;  // u32/u64 scratch counters (see enum below)
   DevBuf tile_state;  // u64 decoupled look-back states
+  DevBuf tile_state2; // same, for a scan running on the side branch
   DevBuf sort_hist;   // u32 [passes][256]
   bool scan_prezero = false;  // inside vofod_process_scan: k_begin_call zeroed every per-scan counter, the stages skip their own 8-byte memsets
   size_t sep_table_hint = 0;  // hash-table sizing of the sepclusters clustering (points expected, not the list capacity)

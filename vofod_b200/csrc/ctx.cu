@@ -91,6 +91,9 @@ int vofod_create(int device, vofod_ctx** out)
     delete ctx;
     return vf_fail(nullptr, VOFOD_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
     cudaEventCreate(&ctx->ev[i]);
   ctx->ev_ok = true;
@@ -137,7 +140,7 @@ int vofod_destroy(vofod_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
-                    &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
+                    &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
                     &ctx->far_keys_b, &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->scratch_d,
@@ -154,6 +157,12 @@ int vofod_destroy(vofod_ctx* ctx)
   if (ctx->ev_ok)
     for (int i = 0; i <= VOFOD_N_STAGES; i++)
       cudaEventDestroy(ctx->ev[i]);
+  if (ctx->ev_fork)
+    cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join)
+    cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2)
+    cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return VOFOD_OK;
@@ -254,7 +263,11 @@ int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters)
   ctx->epoch_calls++;
   // the generation field of a look-back state has 30 bits: before it can repeat, forget every old state
   if (((ctx->epoch_calls * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE && ctx->tile_state.p && !ctx->capturing)
+  {
     CK(cudaMemsetAsync(ctx->tile_state.p, 0, ctx->tile_state.cap, ctx->stream));
+    if (ctx->tile_state2.p)
+      CK(cudaMemsetAsync(ctx->tile_state2.p, 0, ctx->tile_state2.cap, ctx->stream));
+  }
   LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0);
   return 0;
 }

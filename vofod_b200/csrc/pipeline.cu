@@ -390,6 +390,22 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   } prezero_guard(ctx);
   RET(vf_begin_call(ctx, true));
   RET(vf_dyn_push(ctx));
+  // The raycast accumulate reads only the scan, the LUT and the per-scan arguments and writes only the accumulator window:
+  // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
+  // parallel branch of the graph (issue-bound kernel next to a chain of latency-bound ones); with per-stage timing on it
+  // stays in line so that the stage table means what it says.
+  const bool overlap_raycast = plan.raycast_on && !plan.timed && ctx->stream2 != nullptr;
+  if (overlap_raycast)
+  {
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->stream2;
+    const int rrc = vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p);
+    ctx->stream = st;
+    if (rrc < 0)
+      return rrc;
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  }
   STAGE_EVENT();
   // rangefinder seeds (A23)
   RET(vf_range_update_dev(ctx, p));
@@ -410,7 +426,9 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 0, cnt + CNT_VG_M, n, (float)p.score_unknown, 3.0f));
   STAGE_EVENT();  // 4 "vmap update"
   *applied_out = false;
-  if (plan.raycast_on)
+  if (overlap_raycast)
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join: the apply needs the accumulator
+  else if (plan.raycast_on)
     RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
   else
   {

@@ -303,13 +303,17 @@ static inline int persistent_grid(const vofod_ctx* c, const size_t cap_items)
 static inline size_t padded(const size_t n) { return ((n + TILE - 1) / TILE + 1) * TILE; }
 
 // host drivers ------------------------------------------------------------------------------------------------
-static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total)
+// `state`: look-back state buffer; two scans that may run CONCURRENTLY (parallel graph branches) need different ones
+static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total,
+                                DevBuf* state = nullptr)
 {
   const size_t tiles = (cap + TILE - 1) / TILE + 1;
-  ENSURE(ctx->tile_state, tiles * 256 * sizeof(unsigned long long));
+  if (!state)
+    state = &ctx->tile_state;
+  ENSURE(*state, tiles * 256 * sizeof(unsigned long long));
   if (ctx->epoch_local >= EPOCH_STRIDE)
     return vf_fail(ctx, VOFOD_E_INTERNAL, "more than %d look-back launches in one call", EPOCH_STRIDE);
-  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, ctx->tile_state.as<unsigned long long>(), vf_cnt(ctx, CNT_EPOCH_BASE),
+  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, state->as<unsigned long long>(), vf_cnt(ctx, CNT_EPOCH_BASE),
          (uint32_t)(ctx->epoch_local++), d_total, vf_cnt(ctx, CNT_WATCHDOG));
   return 0;
 }

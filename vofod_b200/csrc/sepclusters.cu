@@ -167,8 +167,25 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   CK(cudaMemsetAsync(ctx->sep_segcnt.p, 0, nsegs * 4, ctx->stream));
   const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * nzc * 32, 256, 8);
   LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
+  // the two scans are independent: the second one runs on the side stream (a parallel branch under graph replay)
+  const bool fork = ctx->stream2 != nullptr && host_total == nullptr;
+  cudaStream_t st = ctx->stream;
+  if (fork)
+  {
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->stream2;
+    const int rc2 = scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr, &ctx->tile_state2);
+    ctx->stream = st;
+    if (rc2 < 0)
+      return rc2;
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  }
   RET(scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K));
-  RET(scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr));
+  if (fork)
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  else
+    RET(scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr));
   if (host_total)
   {
     unsigned long long total = 0;

@@ -214,6 +214,7 @@ struct vofod_ctx
   size_t slab_n = 0;            // rays of the scan between vofod_slab_scan_begin and _end (0 = none in flight)
   int slab_raycast_status = 0;
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
+  bool overlap_enabled = true;  // raycast accumulate / second sep scan on the side stream
   bool graph_enabled = true;
   bool capturing = false;
   bool capture_broken = false;

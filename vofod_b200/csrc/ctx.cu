@@ -1,6 +1,7 @@
 // Context lifetime + vofod::VoxelMap (C1) entry points of libvofod_cuda.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -106,6 +107,8 @@ int vofod_create(int device, vofod_ctx** out)
     delete ctx;
     return rc;
   }
+  if (getenv("VOFOD_NO_OVERLAP"))
+    ctx->overlap_enabled = false;
   ctx->pinned_bytes = 1 << 20;
   if (cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault) != cudaSuccess)
   {
@@ -184,6 +187,12 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
   if (option == VOFOD_OPT_GRAPH)
   {
     ctx->graph_enabled = value != 0;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_OVERLAP)
+  {
+    ctx->overlap_enabled = value != 0;
+    ctx->alloc_gen++;
     return VOFOD_OK;
   }
   if (option == VOFOD_OPT_SEP_GENERAL)

@@ -394,7 +394,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
   // parallel branch of the graph (issue-bound kernel next to a chain of latency-bound ones); with per-stage timing on it
   // stays in line so that the stage table means what it says.
-  const bool overlap_raycast = plan.raycast_on && !plan.timed && ctx->stream2 != nullptr;
+  const bool overlap_raycast = plan.raycast_on && !plan.timed && ctx->stream2 != nullptr && ctx->overlap_enabled;
   if (overlap_raycast)
   {
     CK(cudaEventRecord(ctx->ev_fork, st));

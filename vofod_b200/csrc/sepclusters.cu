@@ -168,7 +168,7 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * nzc * 32, 256, 8);
   LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
   // the two scans are independent: the second one runs on the side stream (a parallel branch under graph replay)
-  const bool fork = ctx->stream2 != nullptr && host_total == nullptr;
+  const bool fork = ctx->stream2 != nullptr && host_total == nullptr && ctx->overlap_enabled;
   cudaStream_t st = ctx->stream;
   if (fork)
   {

@@ -187,7 +187,8 @@ def run_ours(args):
 
     if args.profile_leg:
         ms, tot = run_leg(True, graph=args.profile_leg == "graph")
-        print(json.dumps({"profile_leg": args.profile_leg, "ms_per_step": sum(ms) / K, "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot["stage"].items()}}))
+        print(json.dumps({"profile_leg": args.profile_leg, "ms_per_step": sum(ms) / K, "replay_stats": v.stats(),
+                          "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot["stage"].items()}}))
         v.close()
         return
     sampler = ClockSampler(local_rank)
@@ -195,6 +196,7 @@ def run_ours(args):
     ms_res, tot_res = run_leg(True)
     ms_e2e, tot_e2e = run_leg(False)
     clocks = sampler.stop()
+    stats_after_graph_legs = v.stats()
     # per-stage device times (CUDA events between the stages on the library's stream) need the kernel-by-kernel path:
     # the same sequence once more with graph replay switched off.  Only the stage table and the roofline use it.
     ms_eager, tot_eager = run_leg(True, graph=False)
@@ -249,6 +251,7 @@ def run_ours(args):
             "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot_res["stage"].items()},
             "stage_note": "stage times and the roofline kernel time come from a third, kernel-by-kernel leg (graph replay off): %.4f ms/step" % (sum(ms_eager) / K),
             "detections_in_timed_steps": int(tot_res["dets"]),
+            "replay_stats": stats_after_graph_legs,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -302,6 +302,8 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 #define VOFOD_OPT_SEP_GENERAL 3    /* test switch (default 0): sepclusters never takes its leaf-size-1 fast path */
 #define VOFOD_OPT_RAYCAST_NO_AGG 2 /* tuning switch (default 0): one RED per traversal instead of warp-aggregated REDs */
 int vofod_set_option(vofod_ctx*, int option, int value);
+/* scan-replay statistics: which = 0 graph replays, 1 captures, 2 failed captures, 3 kernel-by-kernel scans, 4 reason code of the last failed capture */
+uint64_t vofod_get_stat(const vofod_ctx*, int which);
 /* raw CUDA stream handle (cudaStream_t) the context enqueues on, for event timing by the caller */
 void* vofod_stream(vofod_ctx*);
 

@@ -88,6 +88,7 @@ def load_library():
         "vofod_kernel_launches": (C.c_uint64, [vp]),
         "vofod_stream": (vp, [vp]),
         "vofod_set_option": (i32, [vp, i32, i32]),
+        "vofod_get_stat": (C.c_uint64, [vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = a symbol of include/vofod_cuda.h is missing
@@ -421,6 +422,10 @@ class Vofod:
 
     def kernel_launches(self):
         return int(self.lib.vofod_kernel_launches(self.h))
+
+    def stats(self):
+        names = ("graph_replays", "captures", "failed_captures", "eager_scans", "last_capture_error")
+        return {n: int(self.lib.vofod_get_stat(self.h, i)) for i, n in enumerate(names)}
 
     def set_option(self, option, value):
         self._ck(self.lib.vofod_set_option(self.h, int(option), int(value)))

@@ -222,6 +222,8 @@ struct vofod_ctx
   uint64_t graph_sig = 0, last_eager_sig = 0, last_eager_alloc_gen = ~0ull;
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_kernels = 0;
+  uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;
+  int stat_last_capture_error = 0;  // 1 enqueue failed, 2 EndCapture failed, 3 buffer growth during capture, 4 instantiate failed, 5 BeginCapture failed
   size_t sep_cap = 0;         // capacity of the background-voxel list when sepclusters runs without a host round trip
 
   // clustering / per-scan products

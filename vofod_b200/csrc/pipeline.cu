@@ -543,6 +543,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   {
     // ---- replay
     ctx->epoch_calls++;
+    ctx->stat_replays++;
     CK(cudaGraphLaunch(ctx->graph_exec, st));
     ctx->n_launches += ctx->graph_kernels;
     sep_status = (s.do_sepclusters && !p.sep_pause) ? VOFOD_OK : VOFOD_W_PAUSED;
@@ -566,7 +567,24 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
       ce = cudaStreamEndCapture(st, &graph);
     ctx->capturing = false;
     cudaGraphExec_t exec = nullptr;
-    if (erc == 0 && ce == cudaSuccess && graph && !ctx->capture_broken && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+    ctx->stat_captures++;
+    int why = 0;
+    if (ce != cudaSuccess)
+      why = graph ? 2 : 5;
+    else if (erc != 0)
+      why = 1;
+    else if (ctx->capture_broken)
+      why = 3;
+    else if (!graph)
+      why = 2;
+    else if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
+      why = 4;
+    if (why)
+    {
+      ctx->stat_capture_failures++;
+      ctx->stat_last_capture_error = why;
+    }
+    if (why == 0)
     {
       if (ctx->graph_exec)
         cudaGraphExecDestroy(ctx->graph_exec);
@@ -592,6 +610,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (!used_graph)
   {
     // ---- eager
+    ctx->stat_eager++;
     plan.sep_cap = (graph_ok && ctx->sep_cap > 0) ? ctx->sep_cap : 0;
     plan.timed = true;
     const uint64_t gen_before = ctx->alloc_gen;
@@ -692,6 +711,22 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
 }
 
 extern "C" {
+
+/* instrumentation: 0 graph replays, 1 captures, 2 failed captures, 3 kernel-by-kernel scans, 4 reason of the last failed capture */
+uint64_t vofod_get_stat(const vofod_ctx* ctx, int which)
+{
+  if (!ctx)
+    return 0;
+  switch (which)
+  {
+    case 0: return ctx->stat_replays;
+    case 1: return ctx->stat_captures;
+    case 2: return ctx->stat_capture_failures;
+    case 3: return ctx->stat_eager;
+    case 4: return (uint64_t)ctx->stat_last_capture_error;
+    default: return 0;
+  }
+}
 
 int vofod_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vofod_pose* tf, const vofod_params* p, const vofod_schedule* s, vofod_scan_result* res,
                        vofod_detection* dets, size_t det_cap)

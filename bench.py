@@ -187,7 +187,9 @@ def run_ours(args):
 
     if args.profile_leg:
         ms, tot = run_leg(True, graph=args.profile_leg == "graph")
-        print(json.dumps({"profile_leg": args.profile_leg, "ms_per_step": sum(ms) / K, "replay_stats": v.stats(),
+        order = sorted(range(len(ms)), key=lambda i: -ms[i])[:6]
+        print(json.dumps({"profile_leg": args.profile_leg, "ms_per_step": sum(ms) / K, "median_ms": float(np.median(ms)),
+                          "slowest_steps": [(Wm + i, round(ms[i], 3)) for i in order], "replay_stats": v.stats(),
                           "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot["stage"].items()}}))
         v.close()
         return

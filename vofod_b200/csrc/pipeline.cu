@@ -670,8 +670,9 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     if (K * 5 / 4 + 1024 > ctx->sep_cap)
       ctx->sep_cap = K * 4 + (size_t(1) << 20);
     // the clustering hash table is sized (and memset) for the points expected, not for the list capacity
+    // (a growth re-allocates the table and re-captures the graph: a multi-millisecond hiccup, so start roomy and grow 4x)
     if (K * 3 / 2 > ctx->sep_table_hint)
-      ctx->sep_table_hint = K * 3 + 65536;
+      ctx->sep_table_hint = K * 4 + (size_t(1) << 18);
   }
   ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
   ctx->sure_background_sufficient = sure_flag;

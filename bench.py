@@ -171,6 +171,10 @@ def run_ours(args):
                 if resident:
                     res, d = v.process_scan_resident(k, poses[k], p, scheds[k], dets=dets)
                 else:
+                    # streaming sensor: the next scan's H2D copy is announced before this scan is processed, so it overlaps
+                    # this scan's kernels; every copy still happens inside the timed loop
+                    if k + 1 < n_scans:
+                        v.prefetch_scan(host_scans[k + 1])
                     res, d = v.process_scan(host_scans[k], poses[k], p, scheds[k])
                 ev[k][1].record(stream)
             if k >= Wm:

@@ -260,6 +260,9 @@ int vofod_state_set(vofod_ctx*, int background_pts_sufficient, int sure_backgrou
 int vofod_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*,
                        const vofod_params*, const vofod_schedule*, vofod_scan_result* res,
                        vofod_detection* dets, size_t det_cap);
+/* announce the NEXT scan: its host->device copy runs on a copy stream next to the current scan's kernels; the following
+ * vofod_process_scan with the same `scan` pointer consumes it.  Keep the host buffer (ideally pinned) untouched until then. */
+int vofod_prefetch_scan(vofod_ctx*, const vofod_pt* scan, size_t n);
 /* same, but the scan is already in device memory (bench "value" leg: inputs resident in HBM) */
 int vofod_upload_scan(vofod_ctx*, int slot, const vofod_pt* scan, size_t n);
 int vofod_process_scan_resident(vofod_ctx*, int slot, const vofod_pose*, const vofod_params*,

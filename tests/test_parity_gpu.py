@@ -507,3 +507,23 @@ def test_cpp_adaptor_against_reference_class():
         pytest.skip("tests/cpp/_build/adaptor_vs_reference not built (needs the reference headers: make -C tests/cpp)")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_prefetched_scans_give_identical_results(gpu):
+    """vofod_prefetch_scan (next scan's H2D copy overlapped with the current scan) must not change any result."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    scans = [sensor.scan(1, k) for k in range(24)]
+    outs = []
+    for prefetch in (False, True):
+        gpu.reset(p, vs)
+        gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        log = []
+        for k, (scan, pose, rp, _) in enumerate(scans):
+            if prefetch and k + 1 < len(scans):
+                gpu.prefetch_scan(scans[k + 1][0])
+            res, dets = gpu.process_scan(scan, pose, p, abi.schedule_s1(rp))
+            log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names)))
+        outs.append((log, gpu.map_download().tobytes()))
+    assert outs[0] == outs[1]

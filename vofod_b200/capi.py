@@ -74,6 +74,7 @@ def load_library():
         "vofod_state_set": (i32, [vp, i32, i32, C.c_uint32]),
         "vofod_process_scan": (i32, [vp, vp, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
         "vofod_upload_scan": (i32, [vp, i32, vp, sz]),
+        "vofod_prefetch_scan": (i32, [vp, vp, sz]),
         "vofod_process_scan_resident": (i32, [vp, i32, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
@@ -348,6 +349,10 @@ class Vofod:
         res = ScanResult()
         self._ck(self.lib.vofod_process_scan(self.h, _p(scan), len(scan), C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets), det_cap))
         return res, dets[:res.n_detections].copy()
+
+    def prefetch_scan(self, scan):
+        """scan: C-contiguous PT_DTYPE array in (pinned) host memory that the NEXT process_scan call will be given"""
+        self._ck(self.lib.vofod_prefetch_scan(self.h, _p(scan), len(scan)))
 
     def upload_scan(self, slot, scan):
         scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)

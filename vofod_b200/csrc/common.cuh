@@ -184,6 +184,11 @@ struct vofod_ctx
 
   // scan slots (device-resident scans)
   DevBuf scan_staging;  // device copy of the host scan of the current call
+  DevBuf scan_staging2; // target of vofod_prefetch_scan (the two swap roles when a prefetched scan is consumed)
+  cudaStream_t stream_copy = nullptr;
+  cudaEvent_t ev_prefetch = nullptr;
+  const void* prefetched_host = nullptr;
+  size_t prefetched_n = 0;
   DevBuf scan_slot[VOFOD_SCAN_SLOTS];
   size_t scan_slot_n[VOFOD_SCAN_SLOTS] = {0};
   void* pinned = nullptr;   // small pinned host block for result read-back

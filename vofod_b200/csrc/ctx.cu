@@ -93,6 +93,8 @@ int vofod_create(int device, vofod_ctx** out)
     return vf_fail(nullptr, VOFOD_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
@@ -142,7 +144,7 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->scan_staging2, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
@@ -166,6 +168,13 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2)
     cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_prefetch)
+    cudaEventDestroy(ctx->ev_prefetch);
+  if (ctx->stream_copy)
+  {
+    cudaStreamSynchronize(ctx->stream_copy);
+    cudaStreamDestroy(ctx->stream_copy);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return VOFOD_OK;

@@ -737,9 +737,43 @@ int vofod_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vof
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
-  ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
-  CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->prefetched_host == (const void*)scan && ctx->prefetched_n == n && ctx->scan_staging2.p)
+  {
+    // this scan was announced with vofod_prefetch_scan: its copy has been running next to the previous scan's kernels
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch, 0));
+    DevBuf t = ctx->scan_staging;
+    ctx->scan_staging = ctx->scan_staging2;
+    ctx->scan_staging2 = t;
+    ctx->prefetched_host = nullptr;
+  } else
+  {
+    ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+    CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  }
   return process_scan_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p, *s, res, dets, det_cap);
+}
+
+/* Start the host->device copy of the NEXT scan on a copy stream and return at once; a following vofod_process_scan on the
+ * same host pointer consumes it instead of copying.  The host buffer must stay untouched until that call (pinned memory
+ * for a truly asynchronous copy). */
+int vofod_prefetch_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!scan || n == 0)
+    return vf_fail(ctx, VOFOD_E_INVALID, "vofod_prefetch_scan: bad arguments");
+  if (ctx->scan_staging2.cap < n * sizeof(vofod_pt) + 64 || ctx->scan_staging.cap < n * sizeof(vofod_pt) + 64)
+  {
+    ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+    ENSURE(ctx->scan_staging2, n * sizeof(vofod_pt) + 64);
+    CK(cudaStreamSynchronize(ctx->stream));  // the allocation's zero-fill ran on the main stream
+  }
+  CK(cudaMemcpyAsync(ctx->scan_staging2.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream_copy));
+  CK(cudaEventRecord(ctx->ev_prefetch, ctx->stream_copy));
+  ctx->prefetched_host = scan;
+  ctx->prefetched_n = n;
+  return VOFOD_OK;
 }
 
 int vofod_process_scan_resident(vofod_ctx* ctx, int slot, const vofod_pose* tf, const vofod_params* p, const vofod_schedule* s, vofod_scan_result* res,

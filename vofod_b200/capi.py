@@ -429,7 +429,7 @@ class Vofod:
         return int(self.lib.vofod_kernel_launches(self.h))
 
     def stats(self):
-        names = ("graph_replays", "captures", "failed_captures", "eager_scans", "last_capture_error")
+        names = ("graph_replays", "captures", "failed_captures", "eager_scans", "last_capture_error", "prefetch_hits")
         return {n: int(self.lib.vofod_get_stat(self.h, i)) for i, n in enumerate(names)}
 
     def set_option(self, option, value):

@@ -189,6 +189,7 @@ struct vofod_ctx
   cudaEvent_t ev_prefetch = nullptr;
   const void* prefetched_host = nullptr;
   size_t prefetched_n = 0;
+  uint64_t stat_prefetch_hits = 0;
   DevBuf scan_slot[VOFOD_SCAN_SLOTS];
   size_t scan_slot_n[VOFOD_SCAN_SLOTS] = {0};
   void* pinned = nullptr;   // small pinned host block for result read-back

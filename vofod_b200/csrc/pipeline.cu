@@ -725,6 +725,7 @@ uint64_t vofod_get_stat(const vofod_ctx* ctx, int which)
     case 2: return ctx->stat_capture_failures;
     case 3: return ctx->stat_eager;
     case 4: return (uint64_t)ctx->stat_last_capture_error;
+    case 5: return ctx->stat_prefetch_hits;
     default: return 0;
   }
 }
@@ -745,6 +746,7 @@ int vofod_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vof
     ctx->scan_staging = ctx->scan_staging2;
     ctx->scan_staging2 = t;
     ctx->prefetched_host = nullptr;
+    ctx->stat_prefetch_hits++;
   } else
   {
     ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);

@@ -184,11 +184,13 @@ struct vofod_ctx
 
   // scan slots (device-resident scans)
   DevBuf scan_staging;  // device copy of the host scan of the current call
-  DevBuf scan_staging2; // target of vofod_prefetch_scan (the two swap roles when a prefetched scan is consumed)
+  // vofod_prefetch_scan: two device buffers used alternately; a record stays valid until a process_scan consumes it
+  DevBuf prefetch_buf[2];
   cudaStream_t stream_copy = nullptr;
-  cudaEvent_t ev_prefetch = nullptr;
-  const void* prefetched_host = nullptr;
-  size_t prefetched_n = 0;
+  cudaEvent_t ev_prefetch[2] = {nullptr, nullptr};
+  const void* prefetched_host[2] = {nullptr, nullptr};
+  size_t prefetched_n[2] = {0, 0};
+  int prefetch_next = 0;
   uint64_t stat_prefetch_hits = 0;
   DevBuf scan_slot[VOFOD_SCAN_SLOTS];
   size_t scan_slot_n[VOFOD_SCAN_SLOTS] = {0};

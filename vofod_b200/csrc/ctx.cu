@@ -94,7 +94,8 @@ int vofod_create(int device, vofod_ctx** out)
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_prefetch[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
@@ -144,7 +145,7 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->scan_staging2, &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list, &ctx->far_keys_a,
@@ -168,8 +169,9 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2)
     cudaStreamDestroy(ctx->stream2);
-  if (ctx->ev_prefetch)
-    cudaEventDestroy(ctx->ev_prefetch);
+  for (int i = 0; i < 2; i++)
+    if (ctx->ev_prefetch[i])
+      cudaEventDestroy(ctx->ev_prefetch[i]);
   if (ctx->stream_copy)
   {
     cudaStreamSynchronize(ctx->stream_copy);

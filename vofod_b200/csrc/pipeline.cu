@@ -738,26 +738,24 @@ int vofod_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vof
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
-  if (ctx->prefetched_host == (const void*)scan && ctx->prefetched_n == n && ctx->scan_staging2.p)
-  {
-    // this scan was announced with vofod_prefetch_scan: its copy has been running next to the previous scan's kernels
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch, 0));
-    DevBuf t = ctx->scan_staging;
-    ctx->scan_staging = ctx->scan_staging2;
-    ctx->scan_staging2 = t;
-    ctx->prefetched_host = nullptr;
-    ctx->stat_prefetch_hits++;
-  } else
-  {
-    ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
-    CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-  }
+  for (int i = 0; i < 2; i++)
+    if (ctx->prefetched_host[i] == (const void*)scan && ctx->prefetched_n[i] == n && ctx->prefetch_buf[i].p)
+    {
+      // this scan was announced with vofod_prefetch_scan: its copy has been running next to the previous scan's kernels
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch[i], 0));
+      ctx->prefetched_host[i] = nullptr;
+      ctx->stat_prefetch_hits++;
+      return process_scan_dev(ctx, ctx->prefetch_buf[i].as<vofod_pt>(), n, *tf, *p, *s, res, dets, det_cap);
+    }
+  ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+  CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
   return process_scan_dev(ctx, ctx->scan_staging.as<vofod_pt>(), n, *tf, *p, *s, res, dets, det_cap);
 }
 
-/* Start the host->device copy of the NEXT scan on a copy stream and return at once; a following vofod_process_scan on the
- * same host pointer consumes it instead of copying.  The host buffer must stay untouched until that call (pinned memory
- * for a truly asynchronous copy). */
+/* Start the host->device copy of a COMING scan on a copy stream and return at once; the vofod_process_scan call that is later
+ * given the same host pointer consumes it instead of copying.  Two scans can be announced ahead (typical use: announce scan
+ * k+1, then process scan k).  The host buffer must stay untouched until it is consumed (pinned memory for a truly asynchronous
+ * copy). */
 int vofod_prefetch_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n)
 {
   if (!ctx)
@@ -765,16 +763,18 @@ int vofod_prefetch_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n)
   CK(cudaSetDevice(ctx->device));
   if (!scan || n == 0)
     return vf_fail(ctx, VOFOD_E_INVALID, "vofod_prefetch_scan: bad arguments");
-  if (ctx->scan_staging2.cap < n * sizeof(vofod_pt) + 64 || ctx->scan_staging.cap < n * sizeof(vofod_pt) + 64)
+  // the buffer that was announced longest ago; an unconsumed record in it is dropped (its scan will be copied the normal way)
+  const int i = ctx->prefetch_next;
+  ctx->prefetch_next ^= 1;
+  if (ctx->prefetch_buf[i].cap < n * sizeof(vofod_pt) + 64)
   {
-    ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
-    ENSURE(ctx->scan_staging2, n * sizeof(vofod_pt) + 64);
+    ENSURE(ctx->prefetch_buf[i], n * sizeof(vofod_pt) + 64);
     CK(cudaStreamSynchronize(ctx->stream));  // the allocation's zero-fill ran on the main stream
   }
-  CK(cudaMemcpyAsync(ctx->scan_staging2.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream_copy));
-  CK(cudaEventRecord(ctx->ev_prefetch, ctx->stream_copy));
-  ctx->prefetched_host = scan;
-  ctx->prefetched_n = n;
+  CK(cudaMemcpyAsync(ctx->prefetch_buf[i].p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream_copy));
+  CK(cudaEventRecord(ctx->ev_prefetch[i], ctx->stream_copy));
+  ctx->prefetched_host[i] = scan;
+  ctx->prefetched_n[i] = n;
   return VOFOD_OK;
 }
 

@@ -527,3 +527,40 @@ def test_prefetched_scans_give_identical_results(gpu):
             log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names)))
         outs.append((log, gpu.map_download().tobytes()))
     assert outs[0] == outs[1]
+
+
+def test_edge_cases_empty_and_degenerate_scans(gpu, cpu):
+    """Empty / degenerate inputs through the whole per-scan call: a scan without a single return (no voxels, no clusters, rays
+    cast to max_dist), a scan whose returns all fall into the exclude box, one lone return, and a wrong-sized cloud."""
+    from vofod_b200.capi import VofodError
+    sensor = Sensor(256, 16)
+    p, vs = small_params()
+    setup_pair(cpu, gpu, p, vs, sensor)
+    base, pose, rp, _ = sensor.scan(0, 25)
+    variants = []
+    a = base.copy(); a["range_mm"] = 0; a["x"] = a["y"] = a["z"] = 0.0            # no returns at all
+    variants.append(a)
+    b = base.copy(); b["x"] *= 1e-3; b["y"] *= 1e-3; b["z"] *= 1e-3                # every point inside the exclude box
+    variants.append(b)
+    c = a.copy(); c[100] = base[np.argmax(base["range_mm"] > 0)]                   # a single return
+    variants.append(c)
+    variants.append(base)                                                           # and a normal scan after the odd ones
+    for k, scan in enumerate(variants * 2):
+        s = abi.schedule_s1(rp)
+        rg, dg = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits() or 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        assert rg.as_dict() == rc.as_dict(), (k, rg.as_dict(), rc.as_dict())
+        vg, lg, ig = gpu.last_voxels()
+        vc, lc, ic = cpu.last_voxels()
+        assert_vox_equal(vg, vc)
+        assert np.array_equal(lg, lc)
+        assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
+    with pytest.raises(VofodError) as e:
+        gpu.process_scan(base[:-3], pose, p, abi.schedule_s1(rp))
+    assert e.value.code == abi.VOFOD_E_DIMS
+    # voxel-grid index overflow guard (voxel_grid_weighted.cpp:61-69): a leaf far too small for the extent of the data
+    far = np.array([[0, 0, 0], [1e6, 1e6, 1e6]], np.float32)
+    with pytest.raises(VofodError) as e:
+        gpu.voxel_grid_weighted(far, 0.01)
+    assert e.value.code == abi.VOFOD_E_OVERFLOW

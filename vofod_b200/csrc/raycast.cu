@@ -129,55 +129,62 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
   float prev = 0.0f;
   unsigned steps = 0;
   unsigned oob = 0;
-  bool anyq = false;  // some callback carried a positive path length <=> max_element(raycast) > 0 (:1542-1548)
-  unsigned alive_mask = __ballot_sync(VOFOD_FULL, alive);
-  while (alive_mask)
+  int orq = 0;  // OR of all quantised path lengths: non-zero <=> some callback carried a positive length <=> max_element(raycast) > 0 (:1542-1548)
+  // Every lane walks its own ray; the lanes that are in the loop together (__activemask) merge their updates.  No warp-wide
+  // vote per step: lanes whose ray has ended simply leave the loop, and if the hardware ever splits the warp the only effect
+  // is less merging — the additions commute.
+  while (alive)
   {
-    if (alive)
+    // tmax.minCoeff(&i): first minimum, strict '<'
+    const bool use_y = tmy < tmx;
+    const float d01 = use_y ? tmy : tmx;
+    const bool use_z = tmz < d01;
+    const float dist = use_z ? tmz : d01;
+    const float ddist = (len < dist ? len : dist) - prev;                                     // voxel_map.cpp:252
+    const int q = __float2int_rn(ddist * a.scale);
+    int key;
+    bool inside = true;
+    if (SLAB)
     {
-      // tmax.minCoeff(&i): first minimum, strict '<'
-      const bool use_y = tmy < tmx;
-      const float d01 = use_y ? tmy : tmx;
-      const bool use_z = tmz < d01;
-      const float dist = use_z ? tmz : d01;
-      const float ddist = (len < dist ? len : dist) - prev;                                   // voxel_map.cpp:252
-      const int q = __float2int_rn(ddist * a.scale);
-      // unsharded: always true (the window holds every voxel within max_dist).  Slab: the window is cut at the slab's storage
-      // box, rays enter and leave it along the slab axis.
-      const bool inside = SLAB ? (unsigned)spos < (unsigned)ssize : (unsigned)widx < (unsigned)wn;
-      const int key = inside ? widx : -1 - (int)lane;
-      // lanes of the warp standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
-      if (AGG)
-      {
-        const unsigned m = __match_any_sync(alive_mask, key);
-        const int sum = __reduce_add_sync(m, q);
-        if (inside && lane == (unsigned)(__ffs(m) - 1))
-          red_add_u64(acc + widx, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
-      } else if (inside)
-        red_add_u64(acc + widx, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
-      oob += !SLAB && !inside;
-      anyq |= q > 0;
-      steps++;
-      prev = dist;
-      // voxel_map.cpp:257-261
-      const int rem = use_z ? remz : (use_y ? remy : remx);
-      alive = rem != 0 && dist < len;
-      if (use_z)
-      {
-        remz--; tmz += tdz; widx += dwz;
-        if (SLAB && a.g.slab_axis == 2) spos += sstep;
-      } else if (use_y)
-      {
-        remy--; tmy += tdy; widx += dwy;
-        if (SLAB && a.g.slab_axis == 1) spos += sstep;
-      } else
-      {
-        remx--; tmx += tdx; widx += dwx;
-        if (SLAB && a.g.slab_axis == 0) spos += sstep;
-      }
+      // the window is cut at the slab's storage box: rays enter and leave it along the slab axis
+      inside = (unsigned)spos < (unsigned)ssize;
+      key = inside ? widx : -1 - (int)lane;
+    } else
+      // unsharded: the window holds every voxel within max_dist, so this clamp never bites; if it ever did, the update would
+      // land in the spare cell behind the window (and the apply kernel reports it) instead of corrupting memory
+      key = (int)min((unsigned)widx, (unsigned)wn);
+    if (AGG)
+    {
+      // lanes standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
+      const unsigned am = __activemask();
+      const unsigned m = __match_any_sync(am, key);
+      const int sum = __reduce_add_sync(m, q);
+      if (inside && lane == (unsigned)(__ffs(m) - 1))
+        red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+    } else if (inside)
+      red_add_u64(acc + key, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
+    orq |= q;
+    steps++;
+    prev = dist;
+    // voxel_map.cpp:257-261
+    const int rem = use_z ? remz : (use_y ? remy : remx);
+    alive = rem != 0 && dist < len;
+    if (use_z)
+    {
+      remz--; tmz += tdz; widx += dwz;
+      if (SLAB && a.g.slab_axis == 2) spos += sstep;
+    } else if (use_y)
+    {
+      remy--; tmy += tdy; widx += dwy;
+      if (SLAB && a.g.slab_axis == 1) spos += sstep;
+    } else
+    {
+      remx--; tmx += tdx; widx += dwx;
+      if (SLAB && a.g.slab_axis == 0) spos += sstep;
     }
-    alive_mask = __ballot_sync(VOFOD_FULL, alive);
   }
+  __syncwarp();
+  const bool anyq = orq != 0;
   if (__any_sync(VOFOD_FULL, anyq) && lane == 0)
     atomicOr(counters + CNT_APPLY_ANY, 1ull);
   // per-block totals
@@ -248,6 +255,12 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
   const Window w = dyn->win;
   const float its = (float)dyn->its_raycast;  // detection_its_diff as float (:1539)
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
+  // the spare cell behind the window catches updates the accumulate kernel had to clamp (must never happen)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && acc[n] != 0ull)
+  {
+    atomicAdd(counters + CNT_OOB, 1ull);
+    acc[n] = 0ull;
+  }
   const int wsx = w.size[0], wsy = w.size[1];
   float max_val = 0.f;
   if (!a.new_rule)

@@ -200,6 +200,14 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->graph_enabled = value != 0;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_RAYCAST_BLOCK)
+  {
+    if (value != 64 && value != 128 && value != 256)
+      return vf_fail(ctx, VOFOD_E_INVALID, "raycast block must be 64, 128 or 256");
+    ctx->raycast_block = value;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_OVERLAP)
   {
     ctx->overlap_enabled = value != 0;

@@ -456,19 +456,21 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.scale = ldexpf(1.0f, ctx->frac_bits);
   a.n = (int)n;
   a.has_off = ctx->lut_has_off ? 1 : 0;
-  constexpr int RB = 128;
-  const int blocks = (int)((n + RB - 1) / RB);
   const bool slab = ctx->slab_on;
-#define RAY_LAUNCH(AGG_, SLAB_)                                                                                                                              \
-  LAUNCH((k_raycast_accumulate<RB, AGG_, SLAB_>), blocks, RB, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),          \
-         ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt)
+#define RAY_LAUNCH(RB_, AGG_, SLAB_)                                                                                                                         \
+  LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),               \
+         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt)
   if (ctx->raycast_no_agg)
   {
-    if (slab) RAY_LAUNCH(false, true); else RAY_LAUNCH(false, false);
-  } else
-  {
-    if (slab) RAY_LAUNCH(true, true); else RAY_LAUNCH(true, false);
-  }
+    if (slab) RAY_LAUNCH(128, false, true); else RAY_LAUNCH(128, false, false);
+  } else if (slab)
+    RAY_LAUNCH(128, true, true);
+  else if (ctx->raycast_block == 64)
+    RAY_LAUNCH(64, true, false);
+  else if (ctx->raycast_block == 256)
+    RAY_LAUNCH(256, true, false);
+  else
+    RAY_LAUNCH(128, true, false);
 #undef RAY_LAUNCH
   ctx->acc_has_data = true;
   return VOFOD_OK;

@@ -301,7 +301,7 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 /* options: VOFOD_OPT_GRAPH (default 1) replays vofod_process_scan[_resident] as a CUDA graph once its launch sequence has
  * been seen twice unchanged; with 0 every scan is enqueued kernel by kernel and vofod_stage_times is filled per stage */
 #define VOFOD_OPT_GRAPH 1
-#define VOFOD_OPT_RAYCAST_BLOCK 5  /* tuning: rays per thread block of the raycast accumulate kernel: 64, 128 (default) or 256 */
+#define VOFOD_OPT_RAYCAST_BLOCK 5  /* tuning: rays per thread block of the raycast accumulate kernel: 64 (default), 128 or 256 */
 #define VOFOD_OPT_OVERLAP 4        /* default 1: independent stages run as parallel branches of the scan graph */
 #define VOFOD_OPT_SEP_GENERAL 3    /* test switch (default 0): sepclusters never takes its leaf-size-1 fast path */
 #define VOFOD_OPT_RAYCAST_NO_AGG 2 /* tuning switch (default 0): one RED per traversal instead of warp-aggregated REDs */

@@ -221,7 +221,7 @@ struct vofod_ctx
   int slab_halo = 0;
   size_t slab_n = 0;            // rays of the scan between vofod_slab_scan_begin and _end (0 = none in flight)
   int slab_raycast_status = 0;
-  int raycast_block = 128;      // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
+  int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool overlap_enabled = true;  // raycast accumulate / second sep scan on the side stream
   bool graph_enabled = true;

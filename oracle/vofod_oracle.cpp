@@ -1174,6 +1174,7 @@ struct Oracle
     detection_its++;
     stage_ms[4] = clk.lap();  // "vmap update"
     res.raycast_status = VOFOD_W_PAUSED;
+    n_traversals = 0;  // reported per scan
     if (s.do_raycast)
     {
       res.raycast_status = raycast_accumulate(scan, n, tf, p);

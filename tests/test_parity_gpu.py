@@ -564,3 +564,41 @@ def test_edge_cases_empty_and_degenerate_scans(gpu, cpu):
     with pytest.raises(VofodError) as e:
         gpu.voxel_grid_weighted(far, 0.01)
     assert e.value.code == abi.VOFOD_E_OVERFLOW
+
+
+def test_live_reconfigure_between_scans(gpu, cpu):
+    """dynamic_reconfigure semantics: every tunable is passed per call and may change from one scan to the next (the replayed
+    graph must notice and fall back / re-capture): raycast distance, update rule, thresholds, schedule flags."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    setup_pair(cpu, gpu, p, vs, sensor)
+    for k in range(36):
+        if k == 10:
+            p.raycast_max_distance = 12.0
+        if k == 16:
+            p.raycast_new_update_rule = 0
+            p.raycast_weight_coefficient = 0.2
+        if k == 22:
+            p.raycast_new_update_rule = 1
+            p.raycast_weight_coefficient = 0.003
+            p.raycast_max_distance = 25.0
+            p.ground_points_max_distance = 1.0
+        if k == 28:
+            p.sep_pause = 1
+            p.raycast_min_intensity = 50.0
+        scan, pose, rp, _ = sensor.scan(1, k)
+        s = abi.schedule_s1(rp, do_raycast=(k % 5 != 4), do_sepclusters=(k % 3 != 2))
+        s.raycast_its_diff = 1 + (k % 2)
+        rg, dg = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits() or 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        assert rg.as_dict() == rc.as_dict(), (k, rg.as_dict(), rc.as_dict())
+        assert len(dg) == len(dc)
+        a, b = gpu.map_download(), cpu.map_download()
+        if k < 16:
+            assert np.array_equal(a, b, equal_nan=True), (k, int((a != b).sum()), float(np.abs(a - b).max()))
+        else:
+            # once the OLD update rule has run: its std::pow(float, float) is glibc's powf on the host (0.5x ulp, not correctly
+            # rounded) and an fp64 pow rounded to fp32 on the device — 1-ulp differences in a few cells, far inside 1e-5 relative
+            assert rel_err(a, b).max() < SCORE_RTOL, (k, float(rel_err(a, b).max()))

@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     {
       const float norm_val = rv / max_val;                            // :1587
       const float ws = a.ray_weight * sqrtf(norm_val);                // :1591
-      w1 = powf(1.0f - ws, its);                                    // :1593
+      // :1593 std::pow(float, float).  CUDA's powf is a few ulp off; the fp64 pow rounded to fp32 reproduces the host's
+      // (correctly rounded) powf except in vanishingly rare double-rounding cases
+      w1 = (float)pow((double)(1.0f - ws), (double)its);
       w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);                // std::clamp
     }
     const float w2 = 1.0f - w1;

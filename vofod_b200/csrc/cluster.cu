@@ -229,10 +229,16 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
           d2 += diff * diff;
           if (d2 < r2)
           {
-            const int rj = uf_find(parent, j);
-            ri = uf_find(parent, ri);
-            if (rj != ri)
-              ri = uf_link(parent, ri, rj);
+            // the usual case: j already hangs directly under the root this lane knows for i (every finished point
+            // compresses its own entry) — one load instead of two find chains
+            const int pj = parent[j];
+            if (pj != ri)
+            {
+              const int rj = uf_find(parent, pj);
+              ri = uf_find(parent, ri);
+              if (rj != ri)
+                ri = uf_link(parent, ri, rj);
+            }
           }
         }
       }

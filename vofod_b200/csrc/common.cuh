@@ -240,12 +240,12 @@ struct vofod_ctx
   DevBuf labels;      // i32 per voxel
   DevBuf pt_close;    // u8 per voxel: hasCloseTo result, then "in close cluster"
   DevBuf cl_close;    // i32 per voxel: per-root close flag
-  DevBuf far_list, far_keys_a, far_keys_b;  // classification order
+  DevBuf far_list;    // u32: member lists of the far clusters, ascending point index inside a cluster
   DevBuf cl_info;     // vofod_cluster_info per far cluster
   DevBuf dets;        // vofod_detection
   DevBuf explore_ws;
   DevBuf cls_sizes, cls_maxidx, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
-  DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
+  DevBuf scratch_a, scratch_b, scratch_d;
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace

@@ -1,8 +1,9 @@
 // classifyClusters + extractDetections (vofod_nodelet.cpp:819-879, 1648-1731) on the GPU.
 //
 //   1. far clusters are put into the reference's processing order (clusters sorted by size, largest first —
-//      pcl::EuclideanClusterExtraction; ties by smallest point index) with a radix sort of (size, label) keys,
-//      and their points into ascending index order with a stable radix sort by label
+//      pcl::EuclideanClusterExtraction; ties by smallest point index) by ranking their unique (size, label) keys, and
+//      their points into ascending index order by ballot-compacting labels[label .. max member index] (no sort: n_far
+//      is a handful in steady state)
 //   2. K13: one thread per far cluster restates pcl::MomentOfInertiaEstimation (fp32 mean / covariance summed in
 //      point order, eigenvectors, AABB, OBB) and evaluates the min_points / max_distance / max_size gates
 //   3. K14/K15: ONE thread block walks the gated clusters in order, because VoxelMap::exploreToGround of one point

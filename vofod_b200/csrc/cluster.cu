@@ -353,6 +353,78 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Grid-aligned special case (updateSeparatedBGClusters with leaf size 1, sepclusters.cu): the points are the centres
+// (i+0.5, j+0.5, k+0.5) of DISTINCT voxels and the tolerance is 2, so the fp32 squared distance is the exact integer
+// dx^2+dy^2+dz^2 and "d2 < 4" is 26-connectivity — no spatial hash, no candidate lists: the neighbours of a point are found
+// by reading the score grid itself, their point numbers from `idgrid` (cell -> point number, written by the emission pass
+// for exactly the cells that are in the list).  One thread per point examines the 13 "forward" neighbours.
+// parent[] / sizes[] / minidx[] must have been initialised by the caller (parent[i] = i, 0, INT_MAX).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const vofod_vox* __restrict__ ds, const Geom g,
+                                                  const float* __restrict__ score, const float thr, const uint32_t* __restrict__ idgrid, int* __restrict__ parent)
+{
+  const size_t m = prims::dev_count(d_m, m_cap);
+  const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
+  const long long sxy = (long long)sx * sy;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const vofod_vox v = ds[i];
+    const int lx = (int)v.x - g.st_lo[0], ly = (int)v.y - g.st_lo[1], lz = (int)v.z - g.st_lo[2];
+    const long long c = (long long)lx + (long long)ly * sx + (long long)lz * sxy;
+    // the 13 neighbours (dz,dy,dx) > (0,0,0): all loads are independent
+    unsigned hits = 0;
+#pragma unroll
+    for (int o = 0; o < 13; o++)
+    {
+      const int t = o + 14;
+      const int dz = t / 9 - 1, dy = (t / 3) % 3 - 1, dx = t % 3 - 1;
+      const int nx = lx + dx, ny = ly + dy, nz = lz + dz;
+      if (nx < 0 || nx >= sx || ny < 0 || ny >= sy || nz >= sz || !column_owned(g, nx, ny))
+        continue;
+      if (score[c + dx + (long long)dy * sx + (long long)dz * sxy] > thr)
+        hits |= 1u << o;
+    }
+    int ri = (int)i;
+    while (hits)
+    {
+      const int o = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int t = o + 14;
+      const int dz = t / 9 - 1, dy = (t / 3) % 3 - 1, dx = t % 3 - 1;
+      const uint32_t j = idgrid[c + dx + (long long)dy * sx + (long long)dz * sxy];
+      if ((size_t)j >= m)
+        continue;  // list overflow: the pass is void and redone with a larger list; only memory safety matters here
+      const int pj = parent[j];
+      if (pj != ri)
+      {
+        const int rj = uf_find(parent, pj);
+        ri = uf_find(parent, ri);
+        if (rj != ri)
+          ri = uf_link(parent, ri, rj);
+      }
+    }
+    const int r = uf_find(parent, (int)i);
+    if (r != (int)i && parent[i] != r)
+      parent[i] = r;
+  }
+}
+
+int vf_cluster_grid26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_idgrid, float thr, const unsigned long long* d_m, size_t m_cap,
+                          int* d_labels, unsigned long long* d_ncl)
+{
+  if (!ctx->scan_prezero)
+    CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
+  if (m_cap == 0)
+    return 0;
+  ENSURE(ws.root, m_cap * 4);
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  LAUNCH(k_cg_union, nb, 256, 0, d_m, m_cap, d_ds, ctx->g, ctx->score.as<float>(), thr, d_idgrid, ws.parent.as<int>());
+  LAUNCH(k_cl_roots, nb, 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
+  LAUNCH(k_cl_flatten, nb, 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
+  return 0;
+}
+
 extern "C" int vofod_cluster(vofod_ctx* ctx, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters)
 {
   if (!ctx)

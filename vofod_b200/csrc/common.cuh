@@ -83,6 +83,14 @@ __device__ __forceinline__ bool column_owned(const Geom& g, const int lx, const 
   return v >= g.own_lo && v < g.own_hi;
 }
 
+// "raised" marks (vofod_ctx::col_dirty): one byte per (chunk of DIRTY_ZC z-levels, column) of the storage box, x fastest
+#define DIRTY_ZC 32
+__host__ __device__ __forceinline__ int dirty_chunks(const Geom& g) { return (g.st_size[2] + DIRTY_ZC - 1) / DIRTY_ZC; }
+__device__ __forceinline__ size_t dirty_index(const Geom& g, const int lx, const int ly, const int lz)
+{
+  return ((size_t)(lz / DIRTY_ZC) * g.st_size[1] + ly) * g.st_size[0] + lx;
+}
+
 // ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
 #define ACC_LEN_BITS 44
 __device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
@@ -163,7 +171,7 @@ struct vofod_ctx
   // Columns (x,y) in which some cell was ever raised above the fill value by a point / rangefinder / apriori update.  Every
   // other column only holds values <= max(fill value, ray score, frontiers threshold), so threshold passes over the grid
   // (nVoxelsOver, voxelsAs*PC) can skip it without reading it.
-  DevBuf col_dirty;      // u8 per column of the storage box
+  DevBuf col_dirty;      // u8 per (z-chunk, column) of the storage box: someone RAISED a cell there (dirty_index)
   bool col_all_dirty = true;   // unknown contents (after an upload / single-cell set): every column must be read
   float untouched_max = 0.f;   // the fill value of the last setTo
   size_t flagged_cap = 0;
@@ -249,7 +257,7 @@ struct vofod_ctx
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace
-  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff;
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff, sep_idgrid;
   bool sep_force_general = false;  // test switch: never take the leaf-size-1 fast path
   int sep_off_n = -1, sep_off_mv = 0;
   float sep_off_md = 0.f;
@@ -365,6 +373,8 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  //
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
                    int* d_labels, unsigned long long* d_ncl, size_t table_points_hint = 0);
+int vf_cluster_grid26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_idgrid, float thr, const unsigned long long* d_m, size_t m_cap,
+                          int* d_labels, unsigned long long* d_ncl);
 // raycast.cu
 int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // scan comes from ctx->dyn
 int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // host only: OOB test + window -> h_dyn

@@ -150,7 +150,7 @@ int vofod_destroy(vofod_ctx* ctx)
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
                     &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_d,
-                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff,
+                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff, &ctx->sep_idgrid,
                     &ctx->cls_sizes, &ctx->cls_maxidx, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms};
   for (DevBuf* b : bufs)
     free_buf(*b);
@@ -364,11 +364,11 @@ __global__ void __launch_bounds__(128) k_count_over_cols(const float* __restrict
 {
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)ncol;
-  const int z_lo = blockIdx.y * 32, z_hi = min(z_lo + 32, g.st_size[2]);
+  const int z_lo = blockIdx.y * DIRTY_ZC, z_hi = min(z_lo + DIRTY_ZC, g.st_size[2]);
   unsigned cnt = 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x)
   {
-    if ((dirty && !dirty[c]) || !column_owned(g, c % g.st_size[0], c / g.st_size[0]))
+    if ((dirty && !dirty[(size_t)blockIdx.y * ncol + c]) || !column_owned(g, c % g.st_size[0], c / g.st_size[0]))
       continue;
     for (int z0 = z_lo; z0 < z_hi; z0 += 16)
     {
@@ -397,7 +397,7 @@ __global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* 
     if (ci >= 0)
     {
       score[ci] = __int_as_float(0x7f800000);
-      col_dirty[(x - g.st_lo[0]) + (y - g.st_lo[1]) * g.st_size[0]] = 1;
+      col_dirty[dirty_index(g, x - g.st_lo[0], y - g.st_lo[1], z - g.st_lo[2])] = 1;
     }
   }
 }
@@ -504,9 +504,15 @@ __global__ void k_compact_count(const float* __restrict__ score, const Geom g, c
   {
     const int x = c % g.st_size[0], y = c / g.st_size[0];
     uint32_t cnt = 0;
-    if ((!dirty || dirty[c]) && column_owned(g, x, y))
-      for (int z = 0; z < g.st_size[2]; z++)
-        cnt += ((score[(size_t)c + (size_t)z * sxy] > thr) == (greater != 0));
+    if (column_owned(g, x, y))
+      for (int z_lo = 0; z_lo < g.st_size[2]; z_lo += DIRTY_ZC)
+      {
+        if (dirty && !dirty[(size_t)(z_lo / DIRTY_ZC) * ncol + c])
+          continue;
+        const int z_hi = min(z_lo + DIRTY_ZC, g.st_size[2]);
+        for (int z = z_lo; z < z_hi; z++)
+          cnt += ((score[(size_t)c + (size_t)z * sxy] > thr) == (greater != 0));
+      }
     colcnt[(size_t)x * g.st_size[1] + y] = cnt;  // x-major so that the scan runs in emission order
   }
 }
@@ -609,8 +615,8 @@ int vf_map_alloc(vofod_ctx* ctx)
     return vf_fail(ctx, VOFOD_E_INVALID, "map has no cells");
   ENSURE(ctx->score, (size_t)n * sizeof(float) + 64);
   ENSURE(ctx->flags, (size_t)n + 64);
-  ENSURE(ctx->col_dirty, (size_t)g.st_size[0] * g.st_size[1] + 64);
-  CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)g.st_size[0] * g.st_size[1], ctx->stream));
+  ENSURE(ctx->col_dirty, (size_t)g.st_size[0] * g.st_size[1] * dirty_chunks(g) + 64);
+  CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)g.st_size[0] * g.st_size[1] * dirty_chunks(g), ctx->stream));
   ctx->col_all_dirty = true;  // the grid contents are unspecified until the first setTo
   CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)n, ctx->stream));
   ctx->flags_full_dirty = false;
@@ -719,7 +725,7 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
   if (which == VOFOD_MAP_SCORE)
   {
     LAUNCH(k_fill_f32, vf_blocks(ctx, n / 4 + 1, 256), 256, 0, ctx->score.as<float>(), value, n);
-    CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], ctx->stream));
+    CK(cudaMemsetAsync(ctx->col_dirty.p, 0, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1] * dirty_chunks(ctx->g), ctx->stream));
     ctx->col_all_dirty = !(value == value) || value == __builtin_inff();  // NaN / +inf fills defeat the bound
     ctx->untouched_max = value;
   } else if (which == VOFOD_MAP_FLAGS)
@@ -874,7 +880,7 @@ int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, cons
     CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, p);
   if (dirty || ctx->slab_on)  // a slab counts its own range only (halo columns belong to the neighbour)
-    LAUNCH(k_count_over_cols, dim3((unsigned)vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 4), (unsigned)((ctx->g.st_size[2] + 31) / 32)), 128, 0,
+    LAUNCH(k_count_over_cols, dim3((unsigned)vf_blocks(ctx, (size_t)ctx->g.st_size[0] * ctx->g.st_size[1], 128, 4), (unsigned)dirty_chunks(ctx->g)), 128, 0,
            ctx->score.as<float>(), ctx->g, dirty, thr, d_out);
   else
     LAUNCH(k_count_over, vf_blocks(ctx, n / 4 + 1, 256, 8), 256, 0, ctx->score.as<float>(), n, thr, d_out);

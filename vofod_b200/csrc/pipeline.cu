@@ -22,7 +22,7 @@ __global__ void k_range_update(float* __restrict__ score, const Geom g, const Sc
   for (int r = 0; r < repeats; r++)
     m = (float)(((double)m + score_point) / 2.0);  // :610
   score[ci] = m;
-  col_dirty[(ix - g.st_lo[0]) + (iy - g.st_lo[1]) * g.st_size[0]] = 1;
+  col_dirty[dirty_index(g, ix - g.st_lo[0], iy - g.st_lo[1], iz - g.st_lo[2])] = 1;
 }
 
 int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_update_points(float* __restrict__ score
     const float w = 1.0f / (float)(1ull << c);                          // :791
     score[ci] = w * score[ci] + (1.0f - w) * vmap_score;                // :794
     flags[ci] = vflag;                                                  // :796
-    col_dirty[(xc - g.st_lo[0]) + (yc - g.st_lo[1]) * g.st_size[0]] = 1;
+    col_dirty[dirty_index(g, xc - g.st_lo[0], yc - g.st_lo[1], zc - g.st_lo[2])] = 1;
     const unsigned long long k = atomicAdd(counters + CNT_FLAGGED, 1ull);
     if (k < flagged_cap)
       flagged[k] = (uint32_t)ci;

@@ -104,6 +104,58 @@ __device__ inline uint32_t lookback(unsigned long long* chain, const int stride,
   return excl;
 }
 
+// the same for ONE chain, walked by a whole warp: lane l inspects the l-th predecessor, so a chain of T tiles resolves in
+// ~T/32 round trips instead of T (the serial walk made a 1M-element scan cost 16 us).  All 32 lanes must call.
+__device__ inline uint32_t lookback_warp(unsigned long long* chain, const int tile, const uint32_t aggregate, const uint32_t epoch, unsigned long long* watchdog)
+{
+  const unsigned lane = lane_id();
+  if (tile == 0)
+  {
+    if (lane == 0)
+      st_store(chain, st_pack(epoch, 2ull, aggregate));
+    return 0u;
+  }
+  if (lane == 0)
+    st_store(chain + tile, st_pack(epoch, 1ull, aggregate));
+  uint32_t excl = 0;
+  int base = tile - 1;
+  int spins = 0;
+  while (true)
+  {
+    const int t = base - (int)lane;
+    unsigned status = 2u;  // before tile 0: an inclusive prefix of 0
+    uint32_t val = 0u;
+    if (t >= 0)
+    {
+      const unsigned long long s = st_load(chain + t);
+      status = (uint32_t)(s >> 34) == (epoch & 0x3fffffffu) ? (unsigned)((s >> 32) & 3ull) : 0u;
+      val = (uint32_t)s;
+    }
+    const unsigned not_ready = __ballot_sync(VOFOD_FULL, status == 0u);
+    const unsigned inclusive = __ballot_sync(VOFOD_FULL, status == 2u);
+    const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+    const int first_in = inclusive ? __ffs(inclusive) - 1 : 32;
+    const int take = first_in < first_nr ? first_in + 1 : first_nr;  // usable predecessors: lanes [0, take)
+    excl += __reduce_add_sync(VOFOD_FULL, (int)lane < take ? val : 0u);
+    if (first_in < first_nr)
+      break;
+    base -= take;
+    if (take == 0)
+    {
+      if (++spins > SPIN_LIMIT)
+      {
+        if (lane == 0)
+          atomicAdd(watchdog, 1ull);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  if (lane == 0)
+    st_store(chain + tile, st_pack(epoch, 2ull, excl + aggregate));
+  return excl;
+}
+
 __device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const size_t cap)
 {
   if (!d_n)
@@ -146,11 +198,15 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __r
     }
     uint32_t agg;
     const uint32_t texcl = block_excl_scan(tsum, ws, agg);
-    if (threadIdx.x == 0)
+    if (threadIdx.x < 32)
     {
-      s_base = lookback(state, 1, tile, agg, epoch, watchdog);
-      if (tile == n_tiles - 1 && total)
-        *total = (unsigned long long)s_base + agg;
+      const uint32_t e = lookback_warp(state, tile, agg, epoch, watchdog);
+      if (threadIdx.x == 0)
+      {
+        s_base = e;
+        if (tile == n_tiles - 1 && total)
+          *total = (unsigned long long)e + agg;
+      }
     }
     __syncthreads();
     uint32_t run = s_base + texcl;

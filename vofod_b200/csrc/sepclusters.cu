@@ -31,7 +31,7 @@ int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsi
 // A warp owns (row y, 32-wide x segment, chunk of SEP_ZC z-levels): walking a whole column is a chain of ~20 dependent
 // memory round trips, which — not bandwidth — would set the pace.  Column counts are kept per (column, z-chunk) with the
 // chunk as the fastest index, so that their scan still runs in the reference's x-outer / z-inner emission order.
-#define SEP_ZC 32
+#define SEP_ZC DIRTY_ZC
 __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint8_t* __restrict__ dirty,
                                                         const int nseg, const int nzc, uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segcnt)
 {
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict_
     const int x = seg * 32 + (int)lane;
     const bool in = x < sx;
     const size_t c = (size_t)y * sx + x;
-    const bool live = in && (!dirty || dirty[c]) && column_owned(g, x, y);
+    const bool live = in && (!dirty || dirty[(size_t)zc * sxy + c]) && column_owned(g, x, y);
     if (!__any_sync(VOFOD_FULL, live))
       continue;  // colcnt / segcnt were zero-filled
     const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict_
   }
 }
 __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure, const int nseg,
-                                                       const int nzc, const uint32_t* __restrict__ colcnt, const uint32_t* __restrict__ coloff,
+                                                       const int nzc, const uint8_t* __restrict__ dirty, const uint32_t* __restrict__ colcnt,
+                                                       const uint32_t* __restrict__ coloff,
                                                        const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds, uint32_t* __restrict__ flag_in_order,
-                                                       const size_t cap)
+                                                       uint32_t* __restrict__ idgrid, const size_t cap)
 {
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
     const bool in = x < sx;
     const size_t c = (size_t)y * sx + x;
     const size_t ci = ((size_t)(in ? x : 0) * sy + y) * nzc + zc;
-    const bool live = in && colcnt[ci] != 0;
+    const bool live = in && (!dirty || dirty[(size_t)zc * sxy + c]) && colcnt[ci] != 0;  // the (coalesced) marks spare most of the strided count reads
     if (!__any_sync(VOFOD_FULL, live))
       continue;
     size_t o = live ? coloff[ci] : 0;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
             out.z = (float)(z + g.st_lo[2]) + 0.5f;
             out.count = 0;
             ds[r] = out;
+            idgrid[c + (size_t)z * sxy] = (uint32_t)r;  // cell -> point number, for the 26-connectivity clustering
           }
           if (o < cap)
             flag_in_order[o] = v[k] > thr_sure ? 1u : 0u;
@@ -138,12 +140,18 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
     }
   }
 }
+// + the initial state of the union-find that vf_cluster_grid26_dev works on
 __global__ void __launch_bounds__(256) k_sep_fast_pair(vofod_vox* __restrict__ ds, const uint32_t* __restrict__ flag_in_order, const unsigned long long* __restrict__ d_k,
-                                                       const size_t cap)
+                                                       const size_t cap, int* __restrict__ parent, int* __restrict__ sizes, int* __restrict__ minidx)
 {
   const size_t k = prims::dev_count(d_k, cap);
   for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < k; r += (size_t)gridDim.x * blockDim.x)
+  {
     ds[r].count = flag_in_order[r];
+    parent[r] = (int)r;
+    sizes[r] = 0;
+    minidx[r] = 0x7fffffff;
+  }
 }
 
 // lists for the fast path; *host_total as in vf_compact_over_dev
@@ -198,9 +206,14 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   }
   ENSURE(ctx->sep_ds, padded(cap) * sizeof(vofod_vox));
   ENSURE(ctx->vg_flags, padded(cap) * 4);
-  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
-         ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cap);
-  LAUNCH(k_sep_fast_pair, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cnt + CNT_SEP_K, cap);
+  ENSURE(ctx->sep_idgrid, (size_t)geom_cells(g) * 4);  // only the listed cells are ever written or read: no clearing
+  ENSURE(ctx->cl_bg.parent, cap * 4);
+  ENSURE(ctx->cl_bg.sizes, cap * 4);
+  ENSURE(ctx->cl_bg.minidx, cap * 4);
+  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, nseg, nzc, dirty, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
+         ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), ctx->sep_idgrid.as<uint32_t>(), cap);
+  LAUNCH(k_sep_fast_pair, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cnt + CNT_SEP_K, cap,
+         ctx->cl_bg.parent.as<int>(), ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>());
   return 0;
 }
 
@@ -331,8 +344,12 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
-                     k_cap ? ctx->sep_table_hint : 0));
+  if (fast)  // leaf size 1 <=> tolerance 2 on distinct voxel centres: 26-connectivity, read off the grid
+    RET(vf_cluster_grid26_dev(ctx, ctx->cl_bg, ctx->sep_ds.as<vofod_vox>(), ctx->sep_idgrid.as<uint32_t>(), thr_new, d_kds, K, ctx->sep_labels.as<int>(),
+                              cnt + CNT_SEP_NCL));
+  else
+    RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
+                       k_cap ? ctx->sep_table_hint : 0));
   CK(cudaMemsetAsync(ctx->sep_nsure.p, 0, K * 4, ctx->stream));
   ZERO_CNT(CNT_SEP_ANY_SURE, 1);
   const int nb = vf_blocks(ctx, K, 256, 8);

@@ -356,45 +356,37 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
 // ---------------------------------------------------------------------------------------------------------------
 // Grid-aligned special case (updateSeparatedBGClusters with leaf size 1, sepclusters.cu): the points are the centres
 // (i+0.5, j+0.5, k+0.5) of DISTINCT voxels and the tolerance is 2, so the fp32 squared distance is the exact integer
-// dx^2+dy^2+dz^2 and "d2 < 4" is 26-connectivity — no spatial hash, no candidate lists: the neighbours of a point are found
-// by reading the score grid itself, their point numbers from `idgrid` (cell -> point number, written by the emission pass
-// for exactly the cells that are in the list).  One thread per point examines the 13 "forward" neighbours.
-// parent[] / sizes[] / minidx[] must have been initialised by the caller (parent[i] = i, 0, INT_MAX).
+// dx^2+dy^2+dz^2 and "d2 < 4" is 26-connectivity.  No spatial hash and no distance tests: the occupancy is a bit mask per
+// (z, y, 32-wide x segment) — `segbits` — and the number of a point is segoff[mask] + popcount(mask bits below it).
+// The emission pass has already hung every voxel under the first voxel of its RUN (consecutive set bits of one mask), so
+// only run heads work here: a head unites its run with
+//   * the run that continues it in the next segment of the same row, and
+//   * every run of the 4 "forward" rows (y+1,z), (y-1,z+1), (y,z+1), (y+1,z+1) that overlaps [x0-1, x1+1]
+// — one union per pair of touching runs instead of one per pair of touching voxels (a ground plane has ~10x fewer).
+// parent[] / sizes[] / minidx[] come initialised from the emission pass.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const vofod_vox* __restrict__ ds, const Geom g,
-                                                  const float* __restrict__ score, const float thr, const uint32_t* __restrict__ idgrid, int* __restrict__ parent)
+                                                  const uint32_t* __restrict__ segbits, const uint32_t* __restrict__ segoff, int* __restrict__ parent)
 {
   const size_t m = prims::dev_count(d_m, m_cap);
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
-  const long long sxy = (long long)sx * sy;
+  const int nseg = (sx + 31) / 32;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
   {
     const vofod_vox v = ds[i];
-    const int lx = (int)v.x - g.st_lo[0], ly = (int)v.y - g.st_lo[1], lz = (int)v.z - g.st_lo[2];
-    const long long c = (long long)lx + (long long)ly * sx + (long long)lz * sxy;
-    // the 13 neighbours (dz,dy,dx) > (0,0,0): all loads are independent
-    unsigned hits = 0;
-#pragma unroll
-    for (int o = 0; o < 13; o++)
-    {
-      const int t = o + 14;
-      const int dz = t / 9 - 1, dy = (t / 3) % 3 - 1, dx = t % 3 - 1;
-      const int nx = lx + dx, ny = ly + dy, nz = lz + dz;
-      if (nx < 0 || nx >= sx || ny < 0 || ny >= sy || nz >= sz || !column_owned(g, nx, ny))
-        continue;
-      if (score[c + dx + (long long)dy * sx + (long long)dz * sxy] > thr)
-        hits |= 1u << o;
-    }
+    const int x = (int)v.x - g.st_lo[0], y = (int)v.y - g.st_lo[1], z = (int)v.z - g.st_lo[2];
+    const int seg = x >> 5, b = x & 31;
+    const size_t row = ((size_t)z * sy + y) * nseg;
+    const uint32_t own = segbits[row + seg];
+    if (b > 0 && ((own >> (b - 1)) & 1u))
+      continue;  // not the head of its run
+    const uint32_t up = ~(own >> b);              // first zero at or above b ends the run (bits shifted in from the top are zero)
+    const int len = __ffs(up) ? __ffs(up) - 1 : 32;  // b == 0 and a full mask: 32
+    const int x1 = b + len - 1;                    // last bit of the run
     int ri = (int)i;
-    while (hits)
-    {
-      const int o = __ffs(hits) - 1;
-      hits &= hits - 1;
-      const int t = o + 14;
-      const int dz = t / 9 - 1, dy = (t / 3) % 3 - 1, dx = t % 3 - 1;
-      const uint32_t j = idgrid[c + dx + (long long)dy * sx + (long long)dz * sxy];
+    auto unite = [&](const uint32_t j) {
       if ((size_t)j >= m)
-        continue;  // list overflow: the pass is void and redone with a larger list; only memory safety matters here
+        return;  // list overflow: the pass is void and redone with a larger list; only memory safety matters here
       const int pj = parent[j];
       if (pj != ri)
       {
@@ -403,6 +395,38 @@ __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __re
         if (rj != ri)
           ri = uf_link(parent, ri, rj);
       }
+    };
+    if (x1 == 31 && seg + 1 < nseg && (segbits[row + seg + 1] & 1u))
+      unite(segoff[row + seg + 1]);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+      const int dy = q == 1 ? -1 : (q == 2 ? 0 : 1), dz = q == 0 ? 0 : 1;
+      const int ny = y + dy, nz = z + dz;
+      if (ny < 0 || ny >= sy || nz >= sz)
+        continue;
+      const size_t nrow = ((size_t)nz * sy + ny) * nseg;
+      const uint32_t wc = segbits[nrow + seg];
+      const uint32_t wl = (b == 0 && seg > 0) ? segbits[nrow + seg - 1] : 0u;
+      const uint32_t wr = (x1 == 31 && seg + 1 < nseg) ? segbits[nrow + seg + 1] : 0u;
+      // 34-bit window, position p <-> x = 32*seg - 1 + p; of interest: x in [x0-1, x1+1] <-> p in [b, x1+2]
+      unsigned long long w = (unsigned long long)(wl >> 31) | ((unsigned long long)wc << 1) | ((unsigned long long)(wr & 1u) << 33);
+      w &= ((1ull << (len + 2)) - 1ull) << b;
+      while (w)
+      {
+        const int p = __ffsll((long long)w) - 1;
+        const unsigned long long inv = ~(w >> p);
+        const int rl = __ffsll((long long)inv) - 1;  // >= 1; w has at most 34 bits, so inv always has a set bit
+        w &= ~(((1ull << rl) - 1ull) << p);
+        uint32_t j;
+        if (p == 0)
+          j = segoff[nrow + seg - 1] + (uint32_t)__popc(wl & 0x7fffffffu);
+        else if (p == 33)
+          j = segoff[nrow + seg + 1];
+        else
+          j = segoff[nrow + seg] + (uint32_t)__popc(wc & ((1u << (p - 1)) - 1u));
+        unite(j);
+      }
     }
     const int r = uf_find(parent, (int)i);
     if (r != (int)i && parent[i] != r)
@@ -410,8 +434,8 @@ __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __re
   }
 }
 
-int vf_cluster_grid26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_idgrid, float thr, const unsigned long long* d_m, size_t m_cap,
-                          int* d_labels, unsigned long long* d_ncl)
+int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_segbits, const uint32_t* d_segoff, const unsigned long long* d_m,
+                          size_t m_cap, int* d_labels, unsigned long long* d_ncl)
 {
   if (!ctx->scan_prezero)
     CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
@@ -419,7 +443,7 @@ int vf_cluster_grid26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, 
     return 0;
   ENSURE(ws.root, m_cap * 4);
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
-  LAUNCH(k_cg_union, nb, 256, 0, d_m, m_cap, d_ds, ctx->g, ctx->score.as<float>(), thr, d_idgrid, ws.parent.as<int>());
+  LAUNCH(k_cg_union, nb, 256, 0, d_m, m_cap, d_ds, ctx->g, d_segbits, d_segoff, ws.parent.as<int>());
   LAUNCH(k_cl_roots, nb, 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
   LAUNCH(k_cl_flatten, nb, 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;

@@ -257,7 +257,7 @@ struct vofod_ctx
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace
-  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff, sep_idgrid;
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff, sep_live;
   bool sep_force_general = false;  // test switch: never take the leaf-size-1 fast path
   int sep_off_n = -1, sep_off_mv = 0;
   float sep_off_md = 0.f;
@@ -312,6 +312,7 @@ enum
   CNT_SEP_NUNIQ,
   CNT_CL_CURSOR,      // range allocator of the clustering cell arrays
   CNT_CLS_CURSOR,     // range allocator of the far-cluster member lists
+  CNT_SEP_LIVE,       // length of the sepclusters work list
   // ---- persistent slots (never zeroed by a map resize) ----
   CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
   CNT_EPOCH_BASE,     // generation base of the decoupled look-back states, advanced on the DEVICE once per API call (graph replay safe)
@@ -373,8 +374,8 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  //
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
                    int* d_labels, unsigned long long* d_ncl, size_t table_points_hint = 0);
-int vf_cluster_grid26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_idgrid, float thr, const unsigned long long* d_m, size_t m_cap,
-                          int* d_labels, unsigned long long* d_ncl);
+int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_segbits, const uint32_t* d_segoff, const unsigned long long* d_m,
+                          size_t m_cap, int* d_labels, unsigned long long* d_ncl);
 // raycast.cu
 int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // scan comes from ctx->dyn
 int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vofod_params& p);  // host only: OOB test + window -> h_dyn

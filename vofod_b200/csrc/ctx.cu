@@ -150,7 +150,7 @@ int vofod_destroy(vofod_ctx* ctx)
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
                     &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_d,
-                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff, &ctx->sep_idgrid,
+                    &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff, &ctx->sep_live,
                     &ctx->cls_sizes, &ctx->cls_maxidx, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms};
   for (DevBuf* b : bufs)
     free_buf(*b);
@@ -279,7 +279,7 @@ __global__ void k_begin_call(unsigned long long* __restrict__ counters, const in
   {
     // every counter a scan accumulates into, in one place instead of ~15 eight-byte memset nodes
     const int slots[] = {CNT_TRAVERSALS, CNT_OOB, CNT_APPLY_ANY, CNT_MAXVAL, CNT_NBG, CNT_NCLOSE, CNT_NFAR, CNT_NDET, CNT_NFARPTS, CNT_CLS_CURSOR,
-                         CNT_CL_CURSOR, CNT_SEP_K, CNT_SEP_NUNIQ, CNT_SEP_ANY_SURE, CNT_NCLUSTERS, CNT_SEP_NCL};
+                         CNT_CL_CURSOR, CNT_SEP_K, CNT_SEP_NUNIQ, CNT_SEP_ANY_SURE, CNT_NCLUSTERS, CNT_SEP_NCL, CNT_SEP_LIVE};
     if (threadIdx.x < (int)(sizeof(slots) / sizeof(int)))
       counters[slots[threadIdx.x]] = 0ull;
   }

@@ -165,15 +165,34 @@ __device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const
 }
 
 // ---- exclusive scan of u32 ------------------------------------------------------------------------------
-// out[i] = sum_{j<i} in[j]; *total (u64, may be null) = sum of all.  in/out may alias.  Buffers must be padded to TILE.
-static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const unsigned long long* d_n, const size_t cap,
-                                                      unsigned long long* state, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local, unsigned long long* total,
-                                                      unsigned long long* watchdog)
+// out[i] = sum_{j<i} f(in[j]); *total (u64, may be null) = sum of all.  in/out may alias.  Buffers must be padded to TILE.
+// f = identity, or popcount (the input then is a bit mask per element and the scan ranks the set bits).
+// Up to two independent scans ride in one launch (blockIdx.y selects the job; each has its own look-back chain).
+struct ScanJob
+{
+  const uint32_t* in;
+  uint32_t* out;
+  const unsigned long long* d_n;  // element count on the device (clamped to cap), or NULL = cap
+  size_t cap;
+  unsigned long long* state;
+  unsigned long long* total;
+  int popc;
+};
+struct ScanJobs
+{
+  ScanJob j[2];
+};
+static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local,
+                                                             unsigned long long* watchdog)
 {
   __shared__ uint32_t ws[NT / 32];
   __shared__ uint32_t s_base;
+  const ScanJob& J = jobs.j[blockIdx.y];
+  const uint32_t* __restrict__ in = J.in;
+  uint32_t* __restrict__ out = J.out;
+  unsigned long long* total = J.total;
   const uint32_t epoch = (uint32_t)(*epoch_base + epoch_local) & 0x3fffffffu;
-  const size_t n = dev_count(d_n, cap);
+  const size_t n = dev_count(J.d_n, J.cap);
   const int n_tiles = (int)((n + TILE - 1) / TILE);
   if (n_tiles == 0)
   {
@@ -192,6 +211,8 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __r
 #pragma unroll
     for (int k = 0; k < IPT; k++)
     {
+      if (J.popc)
+        v[k] = (uint32_t)__popc(v[k]);
       if (base_i + k >= n)
         v[k] = 0;
       tsum += v[k];
@@ -200,7 +221,7 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const uint32_t* __r
     const uint32_t texcl = block_excl_scan(tsum, ws, agg);
     if (threadIdx.x < 32)
     {
-      const uint32_t e = lookback_warp(state, tile, agg, epoch, watchdog);
+      const uint32_t e = lookback_warp(J.state, tile, agg, epoch, watchdog);
       if (threadIdx.x == 0)
       {
         s_base = e;
@@ -359,19 +380,51 @@ static inline int persistent_grid(const vofod_ctx* c, const size_t cap_items)
 static inline size_t padded(const size_t n) { return ((n + TILE - 1) / TILE + 1) * TILE; }
 
 // host drivers ------------------------------------------------------------------------------------------------
-// `state`: look-back state buffer; two scans that may run CONCURRENTLY (parallel graph branches) need different ones
-static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total,
-                                DevBuf* state = nullptr)
+// one tile per CTA whenever the CTAs fit the machine at once: a CTA that loops over tiles pays the full load -> look-back ->
+// store latency once per tile, back to back (measured: 18 us for a 1M-element scan with 2 CTAs per SM)
+static inline int scan_grid(const vofod_ctx* c, const size_t cap_items)
 {
-  const size_t tiles = (cap + TILE - 1) / TILE + 1;
-  if (!state)
-    state = &ctx->tile_state;
-  ENSURE(*state, tiles * 256 * sizeof(unsigned long long));
+  static int occ = 0;
+  if (occ == 0)
+  {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan_excl_u32, NT, 0) != cudaSuccess || o < 1)
+      o = 2;
+    occ = o;
+  }
+  size_t tiles = (cap_items + TILE - 1) / TILE;
+  if (tiles < 1)
+    tiles = 1;
+  const size_t g = (size_t)c->num_sms * occ;
+  return (int)(tiles < g ? tiles : g);
+}
+// Two independent scans in one launch.  `b_*` may be all-null for a single scan.  Scan B uses ctx->tile_state2.
+static inline int scan_excl_u32_pair(vofod_ctx* ctx, const uint32_t* a_in, uint32_t* a_out, const unsigned long long* a_dn, const size_t a_cap, unsigned long long* a_total,
+                                     const bool a_popc, const uint32_t* b_in, uint32_t* b_out, const size_t b_cap, unsigned long long* b_total, const bool b_popc)
+{
+  const size_t a_tiles = (a_cap + TILE - 1) / TILE + 1;
+  ENSURE(ctx->tile_state, a_tiles * 256 * sizeof(unsigned long long));
+  ScanJobs jobs;
+  jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0};
+  jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
+  int gx = scan_grid(ctx, a_cap), gy = 1;
+  if (b_in)
+  {
+    const size_t b_tiles = (b_cap + TILE - 1) / TILE + 1;
+    ENSURE(ctx->tile_state2, b_tiles * sizeof(unsigned long long));
+    jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0};
+    const int gb = scan_grid(ctx, b_cap);
+    gx = gx > gb ? gx : gb;
+    gy = 2;
+  }
   if (ctx->epoch_local >= EPOCH_STRIDE)
     return vf_fail(ctx, VOFOD_E_INTERNAL, "more than %d look-back launches in one call", EPOCH_STRIDE);
-  LAUNCH(k_scan_excl_u32, persistent_grid(ctx, cap), NT, 0, in, out, d_n, cap, state->as<unsigned long long>(), vf_cnt(ctx, CNT_EPOCH_BASE),
-         (uint32_t)(ctx->epoch_local++), d_total, vf_cnt(ctx, CNT_WATCHDOG));
+  LAUNCH(k_scan_excl_u32, dim3((unsigned)gx, (unsigned)gy), NT, 0, jobs, vf_cnt(ctx, CNT_EPOCH_BASE), (uint32_t)(ctx->epoch_local++), vf_cnt(ctx, CNT_WATCHDOG));
   return 0;
+}
+static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total)
+{
+  return scan_excl_u32_pair(ctx, in, out, d_n, cap, d_total, false, nullptr, nullptr, 0, nullptr, false);
 }
 
 // sorts bits [begin_bit, end_bit) ascending, stable.  a/b (and va/vb) are ping-pong buffers; *out_k / *out_v receive the result pointers.

@@ -25,132 +25,139 @@ int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsi
 //     output r (r-th voxel in KEY order = storage order z,y,x) = centre (x+0.5, y+0.5, z+0.5) of that voxel,
 //     its count = [intensity > sure threshold] of the r-th voxel in INPUT order (= x-outer/z-inner emission order; this is
 //     the input-slice quirk of voxel_grid_counted.cpp:185-187 with runs of length one).
-// Both orders come out of ONE counting pass and ONE emission pass over the (dirty columns of the) grid — no sort:
-// a warp owns a 32-wide x segment of a row y and walks z; ballots give the rank inside the segment.
+// Both orders come out of ONE counting pass and ONE emission pass — no sort.  The unit of work is
+//     item = (row y, 32-wide x segment, chunk of SEP_ZC z-levels),   one warp per item, lane = x inside the segment.
+// Only a few percent of the items can hold a voxel above the threshold (the "raised" marks of vofod_ctx::col_dirty say
+// which), so a first kernel lists those and the two passes walk the list: with one listed item per warp and all its
+// SEP_ZC loads in flight at once the passes cost a few memory round trips instead of a sweep over the grid.
+//   count: per (z, y, segment) the BIT MASK of matching x (ranks in key order come from a popcount scan of the masks; the
+//          masks also are the occupancy structure the clustering works on) and per (x, y, chunk) the number of matches
+//          (chunk fastest, so that their scan runs in the reference's x-outer / z-inner emission order)
+//   emit : centres in key order, sure flags in input order, and the union-find forest of the clustering seeded with
+//          "every voxel hangs under the first voxel of its run" (run = consecutive set bits of one mask)
 // ---------------------------------------------------------------------------------------------------------------
-// A warp owns (row y, 32-wide x segment, chunk of SEP_ZC z-levels): walking a whole column is a chain of ~20 dependent
-// memory round trips, which — not bandwidth — would set the pace.  Column counts are kept per (column, z-chunk) with the
-// chunk as the fastest index, so that their scan still runs in the reference's x-outer / z-inner emission order.
 #define SEP_ZC DIRTY_ZC
-__global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint8_t* __restrict__ dirty,
-                                                        const int nseg, const int nzc, uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segcnt)
+static_assert(SEP_ZC == 32, "one lane per z-level of a chunk");
+__global__ void __launch_bounds__(256) k_sep_live(const uint8_t* __restrict__ dirty, const Geom g, const int nseg, const int nzc, uint2* __restrict__ live,
+                                                  unsigned long long* __restrict__ n_live)
 {
   const unsigned lane = threadIdx.x & 31;
-  const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
-  const size_t sxy = (size_t)sx * sy;
+  const int sx = g.st_size[0], sy = g.st_size[1];
   const int n_items = sy * nseg * nzc;
   for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
   {
     const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
     const int x = seg * 32 + (int)lane;
-    const bool in = x < sx;
-    const size_t c = (size_t)y * sx + x;
-    const bool live = in && (!dirty || dirty[(size_t)zc * sxy + c]) && column_owned(g, x, y);
-    if (!__any_sync(VOFOD_FULL, live))
-      continue;  // colcnt / segcnt were zero-filled
-    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
-    uint32_t cnt = 0;
-    for (int z0 = z_lo; z0 < z_hi; z0 += 8)
-    {
-      // 8 independent loads in flight, then the (cheap) ballots
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = (live && z0 + k < z_hi) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
-      unsigned mine = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        mine |= (v[k] > thr ? 1u : 0u) << k;
-      cnt += __popc(mine);
-      if (!__any_sync(VOFOD_FULL, mine != 0))
-        continue;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-      {
-        const unsigned bal = __ballot_sync(VOFOD_FULL, (mine >> k) & 1u);
-        if (bal && lane == 0)
-          segcnt[((size_t)(z0 + k) * sy + y) * nseg + seg] = __popc(bal);
-      }
-    }
-    if (cnt)
-      colcnt[((size_t)x * sy + y) * nzc + zc] = cnt;
+    const bool in = x < sx && (!dirty || dirty[((size_t)zc * sy + y) * sx + x]);
+    const unsigned mask = __ballot_sync(VOFOD_FULL, in);
+    if (mask && lane == 0)
+      live[atomicAdd(n_live, 1ull)] = make_uint2((unsigned)item, mask);
   }
 }
-__global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure, const int nseg,
-                                                       const int nzc, const uint8_t* __restrict__ dirty, const uint32_t* __restrict__ colcnt,
-                                                       const uint32_t* __restrict__ coloff,
-                                                       const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds, uint32_t* __restrict__ flag_in_order,
-                                                       uint32_t* __restrict__ idgrid, const size_t cap)
+// loads the SEP_ZC levels of the item's lane column and returns the bit mask of levels above thr
+__device__ __forceinline__ unsigned sep_load_levels(const float* __restrict__ score, const size_t c, const size_t sxy, const int z_lo, const int z_hi, const bool on,
+                                                    const float thr, float (&v)[SEP_ZC])
+{
+#pragma unroll
+  for (int k = 0; k < SEP_ZC; k++)
+    v[k] = (on && z_lo + k < z_hi) ? score[c + (size_t)(z_lo + k) * sxy] : __int_as_float(0xff800000);
+  unsigned mine = 0;
+#pragma unroll
+  for (int k = 0; k < SEP_ZC; k++)
+    mine |= (v[k] > thr ? 1u : 0u) << k;
+  return mine;
+}
+__global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint2* __restrict__ live,
+                                                        const unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
+                                                        uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segbits)
 {
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const size_t sxy = (size_t)sx * sy;
-  const int n_items = sy * nseg * nzc;
-  for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
+  const size_t n = (size_t)*n_live;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += ((size_t)gridDim.x * blockDim.x) >> 5)
   {
+    const uint2 it = live[w];
+    const int item = (int)it.x;
     const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
     const int x = seg * 32 + (int)lane;
-    const bool in = x < sx;
-    const size_t c = (size_t)y * sx + x;
-    const size_t ci = ((size_t)(in ? x : 0) * sy + y) * nzc + zc;
-    const bool live = in && (!dirty || dirty[(size_t)zc * sxy + c]) && colcnt[ci] != 0;  // the (coalesced) marks spare most of the strided count reads
-    if (!__any_sync(VOFOD_FULL, live))
+    const bool on = (it.y >> lane) & 1u;
+    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
+    float v[SEP_ZC];
+    const unsigned mine = sep_load_levels(score, (size_t)y * sx + x, sxy, z_lo, z_hi, on, thr, v);
+    if (!__any_sync(VOFOD_FULL, mine != 0))
+      continue;  // colcnt / segbits were zero-filled
+    unsigned my_level_mask = 0;  // lane k keeps the mask of level z_lo + k
+#pragma unroll
+    for (int k = 0; k < SEP_ZC; k++)
+    {
+      const unsigned bal = __ballot_sync(VOFOD_FULL, (mine >> k) & 1u);
+      if (lane == (unsigned)k)
+        my_level_mask = bal;
+    }
+    if (my_level_mask)
+      segbits[((size_t)(z_lo + (int)lane) * sy + y) * nseg + seg] = my_level_mask;
+    if (mine)
+      colcnt[((size_t)x * sy + y) * nzc + zc] = __popc(mine);
+  }
+}
+__global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure, const uint2* __restrict__ live,
+                                                       const unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
+                                                       const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds,
+                                                       uint32_t* __restrict__ flag_in_order, int* __restrict__ parent, int* __restrict__ sizes, int* __restrict__ minidx,
+                                                       const size_t cap)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
+  const size_t sxy = (size_t)sx * sy;
+  const size_t n = (size_t)*n_live;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += ((size_t)gridDim.x * blockDim.x) >> 5)
+  {
+    const uint2 it = live[w];
+    const int item = (int)it.x;
+    const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
+    const int x = seg * 32 + (int)lane;
+    const bool on = (it.y >> lane) & 1u;
+    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
+    // issued before the level loads so that everything is in flight together: the input-order offset of this lane's column
+    // chunk, and (lane k) the key-order offset of level z_lo + k
+    size_t o = on ? coloff[((size_t)x * sy + y) * nzc + zc] : 0;
+    const uint32_t my_level_off = (z_lo + (int)lane < z_hi) ? segoff[((size_t)(z_lo + (int)lane) * sy + y) * nseg + seg] : 0u;
+    float v[SEP_ZC];
+    const unsigned mine = sep_load_levels(score, (size_t)y * sx + x, sxy, z_lo, z_hi, on, thr, v);
+    if (!__any_sync(VOFOD_FULL, mine != 0))
       continue;
-    size_t o = live ? coloff[ci] : 0;
-    const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
-    for (int z0 = z_lo; z0 < z_hi; z0 += 8)
+#pragma unroll
+    for (int k = 0; k < SEP_ZC; k++)
     {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = (live && z0 + k < z_hi) ? score[c + (size_t)(z0 + k) * sxy] : __int_as_float(0xff800000);
-      unsigned mine = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        mine |= (v[k] > thr ? 1u : 0u) << k;
-      if (!__any_sync(VOFOD_FULL, mine != 0))
+      const bool match = (mine >> k) & 1u;
+      const unsigned bal = __ballot_sync(VOFOD_FULL, match);
+      if (!bal)
         continue;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
+      const size_t base = __shfl_sync(VOFOD_FULL, my_level_off, k);
+      if (match)
       {
-        const bool match = (mine >> k) & 1u;
-        const unsigned bal = __ballot_sync(VOFOD_FULL, match);
-        if (!bal)
-          continue;
-        const int z = z0 + k;
-        const size_t base = segoff[((size_t)z * sy + y) * nseg + seg];
-        if (match)
+        const size_t r = base + __popc(bal & prims::lanemask_lt());
+        if (r < cap)
         {
-          const size_t r = base + __popc(bal & prims::lanemask_lt());
-          if (r < cap)
-          {
-            vofod_vox out;
-            out.x = (float)(x + g.st_lo[0]) + 0.5f;  // (float(ijk) + 0.5f) * 1 + float(min_b) with ijk = idx - min_b: exact
-            out.y = (float)(y + g.st_lo[1]) + 0.5f;
-            out.z = (float)(z + g.st_lo[2]) + 0.5f;
-            out.count = 0;
-            ds[r] = out;
-            idgrid[c + (size_t)z * sxy] = (uint32_t)r;  // cell -> point number, for the 26-connectivity clustering
-          }
-          if (o < cap)
-            flag_in_order[o] = v[k] > thr_sure ? 1u : 0u;
-          o++;
+          vofod_vox out;
+          out.x = (float)(x + g.st_lo[0]) + 0.5f;  // (float(ijk) + 0.5f) * 1 + float(min_b) with ijk = idx - min_b: exact
+          out.y = (float)(y + g.st_lo[1]) + 0.5f;
+          out.z = (float)(z_lo + k + g.st_lo[2]) + 0.5f;
+          out.count = 0;  // the counts live in flag_in_order (see k_sep_nsure)
+          ds[r] = out;
+          // first lane of this lane's run of consecutive set bits
+          const unsigned zeros_below = ~bal & prims::lanemask_lt();
+          const int head = zeros_below ? 32 - __clz(zeros_below) : 0;
+          parent[r] = (int)(base + __popc(bal & ((1u << head) - 1u)));
+          sizes[r] = 0;
+          minidx[r] = 0x7fffffff;
         }
+        if (o < cap)
+          flag_in_order[o] = v[k] > thr_sure ? 1u : 0u;
+        o++;
       }
     }
-  }
-}
-// + the initial state of the union-find that vf_cluster_grid26_dev works on
-__global__ void __launch_bounds__(256) k_sep_fast_pair(vofod_vox* __restrict__ ds, const uint32_t* __restrict__ flag_in_order, const unsigned long long* __restrict__ d_k,
-                                                       const size_t cap, int* __restrict__ parent, int* __restrict__ sizes, int* __restrict__ minidx)
-{
-  const size_t k = prims::dev_count(d_k, cap);
-  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < k; r += (size_t)gridDim.x * blockDim.x)
-  {
-    ds[r].count = flag_in_order[r];
-    parent[r] = (int)r;
-    sizes[r] = 0;
-    minidx[r] = 0x7fffffff;
   }
 }
 
@@ -163,37 +170,25 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   const int nseg = (g.st_size[0] + 31) / 32;
   const int nzc = (g.st_size[2] + SEP_ZC - 1) / SEP_ZC;
   const size_t ncc = (size_t)g.st_size[0] * g.st_size[1] * nzc;                // (column, z-chunk) counts
-  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;             // (z, y, x-segment) counts
+  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;             // (z, y, x-segment) masks
+  const size_t n_items = (size_t)g.st_size[1] * nseg * nzc;
   if (nsegs >= (size_t(1) << 31) || ncc >= (size_t(1) << 31))
     return 1;  // not representable here: use the general path
   ENSURE(ctx->sep_colcnt, padded(ncc) * 4);
   ENSURE(ctx->sep_coloff, padded(ncc) * 4);
   ENSURE(ctx->sep_segcnt, padded(nsegs) * 4);
   ENSURE(ctx->sep_segoff, padded(nsegs) * 4);
+  ENSURE(ctx->sep_live, (n_items + 1) * sizeof(uint2));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, &p);
   CK(cudaMemsetAsync(ctx->sep_colcnt.p, 0, ncc * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->sep_segcnt.p, 0, nsegs * 4, ctx->stream));
-  const int nb = vf_blocks(ctx, (size_t)g.st_size[1] * nseg * nzc * 32, 256, 8);
-  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
-  // the two scans are independent: the second one runs on the side stream (a parallel branch under graph replay)
-  const bool fork = ctx->stream2 != nullptr && host_total == nullptr && ctx->overlap_enabled;
-  cudaStream_t st = ctx->stream;
-  if (fork)
-  {
-    CK(cudaEventRecord(ctx->ev_fork, st));
-    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    ctx->stream = ctx->stream2;
-    const int rc2 = scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr, &ctx->tile_state2);
-    ctx->stream = st;
-    if (rc2 < 0)
-      return rc2;
-    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
-  }
-  RET(scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K));
-  if (fork)
-    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  else
-    RET(scan_excl_u32(ctx, ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), nullptr, nsegs, nullptr));
+  ZERO_CNT(CNT_SEP_LIVE, 1);
+  const int nb = vf_blocks(ctx, n_items * 32, 256, 8);
+  LAUNCH(k_sep_live, nb, 256, 0, dirty, g, nseg, nzc, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE);
+  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(),
+         ctx->sep_segcnt.as<uint32_t>());
+  RET(scan_excl_u32_pair(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K, false, ctx->sep_segcnt.as<uint32_t>(),
+                         ctx->sep_segoff.as<uint32_t>(), nsegs, nullptr, true));
   if (host_total)
   {
     unsigned long long total = 0;
@@ -206,20 +201,19 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   }
   ENSURE(ctx->sep_ds, padded(cap) * sizeof(vofod_vox));
   ENSURE(ctx->vg_flags, padded(cap) * 4);
-  ENSURE(ctx->sep_idgrid, (size_t)geom_cells(g) * 4);  // only the listed cells are ever written or read: no clearing
   ENSURE(ctx->cl_bg.parent, cap * 4);
   ENSURE(ctx->cl_bg.sizes, cap * 4);
   ENSURE(ctx->cl_bg.minidx, cap * 4);
-  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, nseg, nzc, dirty, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(),
-         ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), ctx->sep_idgrid.as<uint32_t>(), cap);
-  LAUNCH(k_sep_fast_pair, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), cnt + CNT_SEP_K, cap,
-         ctx->cl_bg.parent.as<int>(), ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>());
+  LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
+         ctx->sep_coloff.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), ctx->cl_bg.parent.as<int>(),
+         ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>(), cap);
   return 0;
 }
 
 // :1174-1183 — n_sure[cluster] = std::accumulate(range, int 0)
-__global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__ ds, const int* __restrict__ labels, const unsigned long long* __restrict__ d_k,
-                                                   const size_t cap, int* __restrict__ nsure)
+// `counts` != NULL: the per-voxel counts are there (fast path), not in ds[].count
+__global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__ ds, const uint32_t* __restrict__ counts, const int* __restrict__ labels,
+                                                   const unsigned long long* __restrict__ d_k, const size_t cap, int* __restrict__ nsure)
 {
   const size_t k = prims::dev_count(d_k, cap);
   const unsigned lane = threadIdx.x & 31;
@@ -228,7 +222,7 @@ __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__
     const size_t i = i0 + lane;
     const bool valid = i < k;
     const int l = valid ? labels[i] : -1 - (int)lane;
-    const unsigned c = valid ? ds[i].count : 0u;
+    const unsigned c = valid ? (counts ? counts[i] : ds[i].count) : 0u;
     // one atomic per (warp, cluster): the big background body would otherwise serialise every point on one word
     const unsigned grp = __match_any_sync(VOFOD_FULL, l);
     const unsigned sum = __reduce_add_sync(grp, c);
@@ -314,7 +308,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
     return vf_fail(ctx, VOFOD_E_INVALID, "sepclusters: max_bg_distance/voxel_size <= 1 gives a zero leaf size (the reference divides by it)");
   size_t K = k_cap;
   const unsigned long long* d_kds = cnt + CNT_SEP_KDS;
-  bool fast = lsz == 1.0f && !ctx->sep_force_general;
+  bool fast = lsz == 1.0f && !ctx->sep_force_general && !ctx->slab_on;
   if (fast)
   {
     const int frc = sep_fast_lists(ctx, thr_new, thr_sure, p, k_cap == 0 ? &K : nullptr, k_cap);
@@ -344,16 +338,17 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   const unsigned long long cap_guard = k_cap ? (unsigned long long)k_cap : ~0ull;
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
-  if (fast)  // leaf size 1 <=> tolerance 2 on distinct voxel centres: 26-connectivity, read off the grid
-    RET(vf_cluster_grid26_dev(ctx, ctx->cl_bg, ctx->sep_ds.as<vofod_vox>(), ctx->sep_idgrid.as<uint32_t>(), thr_new, d_kds, K, ctx->sep_labels.as<int>(),
-                              cnt + CNT_SEP_NCL));
+  if (fast)  // leaf size 1 <=> tolerance 2 on distinct voxel centres: 26-connectivity, read off the occupancy masks
+    RET(vf_cluster_runs26_dev(ctx, ctx->cl_bg, ctx->sep_ds.as<vofod_vox>(), ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), d_kds, K,
+                              ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
   else
     RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
                        k_cap ? ctx->sep_table_hint : 0));
   CK(cudaMemsetAsync(ctx->sep_nsure.p, 0, K * 4, ctx->stream));
   ZERO_CNT(CNT_SEP_ANY_SURE, 1);
   const int nb = vf_blocks(ctx, K, 256, 8);
-  LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(), d_kds, K, ctx->sep_nsure.as<int>());
+  LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), fast ? ctx->vg_flags.as<uint32_t>() : nullptr, ctx->sep_labels.as<int>(), d_kds, K,
+         ctx->sep_nsure.as<int>());
   LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt);
   LAUNCH(k_sep_state, 1, 1, 0, cnt, cap_guard);
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)

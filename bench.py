@@ -126,6 +126,8 @@ def run_ours(args):
     v = capi.Vofod(local_rank)  # raises if libvofod_cuda.so / the device is missing: no CPU fallback
     p = make_params()
     dirs = synth.sim_lut(W, H)
+    if args.no_pdl:
+        v.set_option(abi.OPT_PDL, 0)
     v.reset(p, VOXEL)
     v.set_sensor(W, H, dirs)
     stream = torch.cuda.ExternalStream(v.stream(), device=torch.device("cuda", local_rank))
@@ -434,6 +436,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B switch: launch the kernels without programmatic dependent launch")
     ap.add_argument("--distinct-streams", action="store_true", help="N > 1: every rank processes a different part of the trajectory instead of the same sequence")
     ap.add_argument("--mode", default="streams", choices=["streams", "slab"],
                     help="streams (default, the driver's contract): cfg2, one independent scan stream per GPU; slab: cfg5 large map cut into x-slabs")

@@ -86,3 +86,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "libvofod_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_no_global_access_before_the_dependency_wait():
+    """Kernels are chained by programmatic dependent launch: each must execute griddepcontrol.wait (SASS ACQBULK) before its
+    first global memory access — checked on the SASS of the built library, because ptxas may hoist read-only loads."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_pdl_sass
+    n, bad = check_pdl_sass.check()
+    assert n >= 58 and not bad, bad

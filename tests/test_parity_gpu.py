@@ -294,6 +294,52 @@ def test_process_scan_small_gazebo_detections(gpu, cpu):
     assert n_det > 0
 
 
+def test_update_points_collisions_follow_cloud_order(gpu, cpu):
+    """Several points of one cloud in the SAME map cell (possible for callers of updateVMaps other than the scan path, whose
+    voxel grid is aligned with the map): the reference applies every update, in cloud order."""
+    p, vs = small_params()
+    rng = np.random.default_rng(5)
+    for o in (gpu, cpu):
+        o.reset(p, vs)
+    n = 6000
+    vox = np.zeros(n, dtype=abi.VOX_DTYPE)
+    base = rng.uniform(-6.0, 6.0, size=(n // 3, 3)).astype(np.float32)
+    xyz = np.repeat(base, 3, axis=0) + rng.uniform(-0.2, 0.2, size=(n, 3)).astype(np.float32)  # triples around one spot
+    vox["x"], vox["y"], vox["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2] + 5.0
+    vox["count"] = rng.integers(0, 5, size=n)
+    idx = cpu.coord_to_idx(np.stack([vox["x"], vox["y"], vox["z"]], 1))
+    _, c = np.unique(idx, axis=0, return_counts=True)
+    assert (c > 1).sum() > 500                                            # the case under test does occur
+    sel = rng.integers(0, 2, size=n).astype(np.uint8)
+    for o in (gpu, cpu):
+        o.update_points(vox, sel, 1, p.score_point, 2.0)                  # :946
+        o.update_points(vox, sel, 0, p.score_unknown, 3.0)                # :948
+        o.update_points(vox, None, 0, -123.25, 1.0)
+    assert np.array_equal(gpu.map_download(), cpu.map_download())
+    assert np.array_equal(gpu.map_download(abi.MAP_FLAGS), cpu.map_download(abi.MAP_FLAGS))
+
+
+def test_process_scan_operation_area_off_the_half_metre_raster(gpu, cpu):
+    """Operation area shifted by a fraction of a voxel in x and y: the filter's voxel grid follows the map (:664-665)."""
+    sensor = Sensor(512, 32)
+    p = params_for((80.0, 80.0, 30.0), offset_xyz=(0.13, 0.21, -1.25))
+    p.background_sufficient_points_ratio = 0.02
+    _run_sequence(gpu, cpu, sensor, p, 0.5, 0, range(0, 12), fixed=True)
+
+
+def test_scan_path_voxel_grid_sort_based_variant(gpu, cpu):
+    """The scan path normally voxelizes without sorting (dense counts + occupancy words); the generic sort-based
+    VoxelGridWeighted must give the same scans."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    gpu.set_option(abi.OPT_VG_SORT, 1)
+    try:
+        _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 10), fixed=True)
+    finally:
+        gpu.set_option(abi.OPT_VG_SORT, 0)
+
+
 def test_sepclusters_general_path_and_leaf2(gpu, cpu):
     """The separated-background-cluster pass outside its leaf-size-1 fast path: forced general path (compaction ->
     VoxelGridCounted radix sort), and max_bg_distance 1.2 m (ceil(2.4) = 3 -> leaf size 2, 125-offset ball)."""
@@ -325,6 +371,26 @@ def test_graph_replay_equals_kernel_by_kernel(gpu):
             log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names)))  # fields, not struct padding
         outs.append((log, gpu.map_download().tobytes()))
     gpu.set_option(abi.OPT_GRAPH, 1)
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+
+
+def test_programmatic_dependent_launch_is_transparent(gpu):
+    """Kernels chained by programmatic dependent launch (default) vs plainly serialised launches: identical maps and results."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    outs = []
+    for pdl in (1, 0):
+        gpu.set_option(abi.OPT_PDL, pdl)
+        gpu.reset(p, vs)
+        gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        log = []
+        for k in range(30):
+            scan, pose, rp, _ = sensor.scan(1, k)
+            res, dets = gpu.process_scan(scan, pose, p, abi.schedule_s1(rp))
+            log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names)))
+        outs.append((log, gpu.map_download().tobytes()))
+    gpu.set_option(abi.OPT_PDL, 1)
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
 
 

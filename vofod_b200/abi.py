@@ -192,3 +192,6 @@ def ptr(a, ctype=None):
         return a.ctypes.data_as(C.c_void_p)
     return a.ctypes.data_as(C.POINTER(ctype))
 OPT_GRAPH = 1
+OPT_PDL = 6
+OPT_VG_SORT = 7
+OPT_SEP_GENERAL = 3

@@ -23,6 +23,7 @@
 __global__ void __launch_bounds__(256) k_cls_mark(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const unsigned long long* __restrict__ d_m,
                                                   const size_t m_cap, int* __restrict__ sizes, int* __restrict__ maxidx)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) k_cls_roots(const int* __restrict__ label
                                                    const unsigned long long* __restrict__ d_m, const size_t m_cap, const int bits, unsigned long long* __restrict__ okeys,
                                                    unsigned long long* __restrict__ d_nfar)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned long long maxv = (1ull << bits) - 1ull;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
@@ -59,7 +61,8 @@ __global__ void __launch_bounds__(256) k_cls_roots(const int* __restrict__ label
 __global__ void __launch_bounds__(256) k_cls_rank(const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
                                                   unsigned long long* __restrict__ sorted)
 {
-  const unsigned long long n = *d_nfar;
+  pdl_enter();
+  const unsigned long long n = *after_wait(d_nfar);
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -80,7 +83,8 @@ __global__ void __launch_bounds__(256) k_cls_members(const int* __restrict__ lab
                                                      const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar, const int bits,
                                                      uint32_t* __restrict__ memb, int* __restrict__ seg_start, unsigned long long* __restrict__ cursor)
 {
-  const unsigned long long n_far = *d_nfar;
+  pdl_enter();
+  const unsigned long long n_far = *after_wait(d_nfar);
   const unsigned long long lmask = (1ull << bits) - 1ull;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -183,7 +187,8 @@ __global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const Scan
                                                      const int* __restrict__ sizes, const unsigned long long* __restrict__ okeys, const unsigned long long* __restrict__ d_nfar,
                                                      vofod_cluster_info* __restrict__ out)
 {
-  const unsigned long long n_far = *d_nfar;
+  pdl_enter();
+  const unsigned long long n_far = *after_wait(d_nfar);
   const unsigned long long lmask = (1ull << a.bits) - 1ull;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(256) k_explore_single(const float* score, cons
                                                         const float ground_thr, const float maxd, const ExploreWs w, int* __restrict__ out_idx3, const size_t cap,
                                                         unsigned long long* __restrict__ counters)
 {
+  pdl_enter();
   __shared__ int sh[4];
   __shared__ unsigned s_epoch;
   if (threadIdx.x == 0)
@@ -525,11 +531,12 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
                                                       double* __restrict__ terms, vofod_detection* __restrict__ dets, unsigned long long* __restrict__ counters,
                                                       const unsigned long long* __restrict__ d_nfar)
 {
+  pdl_enter();
   __shared__ int sh[4];
   __shared__ unsigned s_epoch;
   __shared__ unsigned long long s_det_id, s_ndet;
   const int tid = threadIdx.x;
-  const unsigned long long n_far = *d_nfar;
+  const unsigned long long n_far = *after_wait(d_nfar);
   const bool active = counters[CNT_STATE_BG] != 0ull && counters[CNT_STATE_SURE] != 0ull;  // :1695
   if (tid == 0)
   {
@@ -722,8 +729,10 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   ENSURE(ctx->explore_ws, cube * 4);          // stamps: zero-filled when (re)allocated
   ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
   ENSURE(ctx->cls_terms, terms_cap * 8);
-  CK(cudaMemsetAsync(ctx->cls_sizes.p, 0, m_cap * 4, ctx->stream));
-  CK(cudaMemsetAsync(ctx->cls_maxidx.p, 0, m_cap * 4, ctx->stream));
+  {
+    const FillJob fj[2] = {{ctx->cls_sizes.as<uint32_t>(), m_cap, 0u}, {ctx->cls_maxidx.as<uint32_t>(), m_cap, 0u}};
+    RET(vf_fill(ctx, fj, 2));
+  }
   ZERO_CNT(CNT_CLS_CURSOR, 1);
 
   const int nb = vf_blocks(ctx, m_cap, 256, 8);

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) k_cl_insert(const float* __restrict__ xyz
                                                    const unsigned tmask, int* __restrict__ slot_of, int* __restrict__ rank_of, int* __restrict__ parent,
                                                    int* __restrict__ sizes, int* __restrict__ minidx, unsigned long long* __restrict__ watchdog)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
   {
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) k_cl_alloc(const unsigned long long* __re
                                                   const int* __restrict__ rank_of, const int* __restrict__ tcount, int* __restrict__ tstart,
                                                   unsigned long long* __restrict__ cursor)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) k_cl_fill(const unsigned long long* __res
                                                  const int* __restrict__ slot_of, const int* __restrict__ rank_of, const int* __restrict__ tstart,
                                                  float4* __restrict__ cellpts)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
   {
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
                                                   const float4* __restrict__ pts, const unsigned long long* __restrict__ tkey, const int* __restrict__ tcount,
                                                   const int* __restrict__ tstart, const unsigned tmask, const float4* __restrict__ cellpts, int* __restrict__ parent)
 {
+  pdl_enter();
   if (inv_cell == 0.0)
     return;
   const size_t m = prims::dev_count(d_m, m_cap);
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(256) k_cl_union(const unsigned long long* __re
 __global__ void __launch_bounds__(256) k_cl_roots(const unsigned long long* __restrict__ d_m, const size_t m_cap, int* __restrict__ parent, int* __restrict__ root,
                                                   int* __restrict__ minidx)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
@@ -287,6 +292,7 @@ __global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __
                                                     const int* __restrict__ minidx, int* __restrict__ labels, int* __restrict__ sizes,
                                                     unsigned long long* __restrict__ d_ncl)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   unsigned roots = 0;
@@ -329,8 +335,10 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   ENSURE(ws.sizes, m_cap * 4);
   ENSURE(ws.root, m_cap * 4);
   ENSURE(ws.minidx, m_cap * 4);
-  CK(cudaMemsetAsync(ws.table_key.p, 0xFF, tsize * 8, ctx->stream));
-  CK(cudaMemsetAsync(ws.table_head.p, 0, tsize * 4, ctx->stream));  // counts
+  {
+    const FillJob fj[2] = {{ws.table_key.as<uint32_t>(), tsize * 2, 0xFFFFFFFFu}, {ws.table_head.as<uint32_t>(), tsize, 0u}};  // keys = CL_EMPTY, counts = 0
+    RET(vf_fill(ctx, fj, 2));
+  }
   if (!ctx->scan_prezero || second_use)
     CK(cudaMemsetAsync(vf_cnt(ctx, CNT_CL_CURSOR), 0, 8, ctx->stream));
   int* tcount = ws.table_head.as<int>();
@@ -368,6 +376,7 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
 __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const vofod_vox* __restrict__ ds, const Geom g,
                                                   const uint32_t* __restrict__ segbits, const uint32_t* __restrict__ segoff, int* __restrict__ parent)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const int nseg = (sx + 31) / 32;

@@ -37,6 +37,25 @@ __device__ __forceinline__ bool in_limits_idx(const Geom& g, const int x, const 
   return x >= 0 && x < g.size[0] && y >= 0 && y < g.size[1] && z >= 0 && z < g.size[2];
 }
 // storage index of a global cell, or -1 when this context does not hold it
+// first statement of every kernel (see LAUNCH): let the next kernel of the stream get launched, then wait until the previous
+// one has completed and its writes are visible.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// The "memory" clobber does not hold back loads through `const T* __restrict__` kernel parameters: they compile to
+// non-coherent loads (LDG.CONSTANT), the data counts as immutable for the kernel's lifetime, and ptxas scheduled such loads
+// of per-scan counters ABOVE the wait — reading the previous scan's value.  A pointer laundered through a volatile asm
+// cannot be dereferenced before that asm, and volatile asms keep their order.  Use it for whatever a kernel reads
+// unconditionally at entry; tools/check_pdl_sass.py (run by the tests) rejects a build with any global access above the wait.
+template <class T>
+__device__ __forceinline__ T* after_wait(T* p)
+{
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 __device__ __forceinline__ long long cell_index(const Geom& g, const int x, const int y, const int z)
 {
   const int lx = x - g.st_lo[0], ly = y - g.st_lo[1], lz = z - g.st_lo[2];
@@ -91,6 +110,32 @@ __device__ __forceinline__ size_t dirty_index(const Geom& g, const int lx, const
   return ((size_t)(lz / DIRTY_ZC) * g.st_size[1] + ly) * g.st_size[0] + lx;
 }
 
+// monotone float <-> int mapping for atomicMin/atomicMax
+__device__ __forceinline__ int f2ord(const float f)
+{
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(const int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
+
+struct MinMax
+{
+  int mn[3], mx[3];
+  unsigned n_valid;
+  unsigned n_append;  // cursor of the compacting writers
+};
+
+__device__ __forceinline__ void minmax_init(MinMax* mm)
+{
+  for (int a = 0; a < 3; a++)
+  {
+    mm->mn[a] = f2ord(3.402823466e+38f);
+    mm->mx[a] = f2ord(-3.402823466e+38f);
+  }
+  mm->n_valid = 0;
+  mm->n_append = 0;
+}
+
 // ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
 #define ACC_LEN_BITS 44
 __device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
@@ -134,6 +179,24 @@ struct ScanDyn
 };
 #define EPOCH_STRIDE 64      // look-back launches per API call are numbered 0..63
 
+// A23 rangefinder ground seed (vofod_nodelet.cpp:581-613), one thread
+__device__ inline void range_update(float* score, const Geom& g, const ScanDyn* dyn, const double score_point, uint8_t* col_dirty)
+{
+  const float x = dyn->range_pt[0], y = dyn->range_pt[1], z = dyn->range_pt[2];
+  const int repeats = dyn->n_seeds;
+  const int ix = coord_to_idx1(x, g.off[0], g.inv), iy = coord_to_idx1(y, g.off[1], g.inv), iz = coord_to_idx1(z, g.off[2], g.inv);
+  if (repeats <= 0 || !in_limits_idx(g, ix, iy, iz))  // :599
+    return;
+  const long long ci = cell_index(g, ix, iy, iz);
+  if (ci < 0)
+    return;
+  float m = score[ci];
+  for (int r = 0; r < repeats; r++)
+    m = (float)(((double)m + score_point) / 2.0);  // :610
+  score[ci] = m;
+  col_dirty[dirty_index(g, ix - g.st_lo[0], iy - g.st_lo[1], iz - g.st_lo[2])] = 1;
+}
+
 // Euclidean-cluster workspace handles (cluster.cu)
 struct ClusterWs
 {
@@ -171,6 +234,9 @@ struct vofod_ctx
   // Columns (x,y) in which some cell was ever raised above the fill value by a point / rangefinder / apriori update.  Every
   // other column only holds values <= max(fill value, ray score, frontiers threshold), so threshold passes over the grid
   // (nVoxelsOver, voxelsAs*PC) can skip it without reading it.
+  DevBuf upd_owner;      // u32 per cell: claim of the point update in flight (UPD_EMPTY otherwise), see k_update_points
+  DevBuf upd_leftover;   // u32 keys of the points that found their cell claimed
+  size_t upd_owner_cells = 0;
   DevBuf col_dirty;      // u8 per (z-chunk, column) of the storage box: someone RAISED a cell there (dirty_index)
   bool col_all_dirty = true;   // unknown contents (after an upload / single-cell set): every column must be read
   float untouched_max = 0.f;   // the fill value of the last setTo
@@ -208,6 +274,8 @@ struct vofod_ctx
   // voxel-grid workspace
   DevBuf vg_pts;    // float4 per input point (x,y,z,valid/intensity)
   DevBuf vg_keys_a, vg_keys_b;
+  DevBuf vgh_cnt, vgh_bits, vgh_off;  // sort-free scan-path voxel grid: dense per-leaf counts, occupancy words, their popcount scan
+  bool vg_force_sort = false;         // test switch: the scan path uses the generic sort-based voxel grid
   DevBuf vg_flags, vg_scan, vg_ustart, vg_ukey, vg_pref;
   DevBuf vox;       // vofod_vox per output voxel (cloud_weighted of the last scan)
   DevBuf d_counters;  // u32/u64 scratch counters (see enum below)
@@ -231,6 +299,8 @@ struct vofod_ctx
   int slab_raycast_status = 0;
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
+  bool pdl_enabled = true;      // programmatic dependent launch between consecutive kernels (see LAUNCH)
+  bool pdl_chain = false;       // the last operation put on ctx->stream was a kernel launch of this library
   bool overlap_enabled = true;  // raycast accumulate / second sep scan on the side stream
   bool graph_enabled = true;
   bool capturing = false;
@@ -313,6 +383,9 @@ enum
   CNT_CL_CURSOR,      // range allocator of the clustering cell arrays
   CNT_CLS_CURSOR,     // range allocator of the far-cluster member lists
   CNT_SEP_LIVE,       // length of the sepclusters work list
+  CNT_UPD_LEFT,       // k_update_points: left-over list length / block ticket (both return to 0 at the end of the kernel)
+  CNT_UPD_TICKET,
+  CNT_VGH_WORDS,      // occupancy words of the scan-path voxel grid (depends on the cloud's bounding box)
   // ---- persistent slots (never zeroed by a map resize) ----
   CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
   CNT_EPOCH_BASE,     // generation base of the decoupled look-back states, advanced on the DEVICE once per API call (graph replay safe)
@@ -323,11 +396,22 @@ enum
 // ---- host helpers ----------------------------------------------------------------------------------
 int vf_fail(vofod_ctx* c, int code, const char* fmt, ...);
 int vf_ensure(vofod_ctx* c, DevBuf& b, size_t bytes);
-int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters = false);  // advances the look-back generation; first thing of every entry point that sorts / scans
+int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters = false);
+int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p);  // vofod_process_scan: vf_begin_call + rangefinder seeds (A23) + min/max reset of the filter, one kernel  // advances the look-back generation; first thing of every entry point that sorts / scans
 int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
+// up to 4 word fills in ONE kernel launch (a stage's clears; unlike memset nodes they chain by programmatic dependent launch)
+struct FillJob
+{
+  uint32_t* p;
+  size_t n_words;
+  uint32_t value;
+};
+int vf_fill(vofod_ctx* ctx, const FillJob* jobs, int n_jobs);
+// (any runtime call other than a kernel launch ends a chain of programmatically dependent launches: see LAUNCH)
 #define CK(call)                                                                                         \
   do                                                                                                     \
   {                                                                                                      \
+    ctx->pdl_chain = false;                                                                              \
     cudaError_t e__ = (call);                                                                            \
     if (e__ != cudaSuccess)                                                                              \
       return vf_fail(ctx, VOFOD_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
@@ -347,13 +431,32 @@ int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
     if (!ctx->scan_prezero)                                                                      \
       CK(cudaMemsetAsync(vf_cnt(ctx, slot), 0, (size_t)(n) * 8, ctx->stream));                   \
   } while (0)
-// kernel launch with accounting
+// kernel launch with accounting.  Every kernel of the library starts with pdl_enter() and is launched with the
+// programmatic-stream-serialization attribute (programmatic dependent launch): the launch latency and block scheduling of
+// kernel N+1 overlap the execution of kernel N, and N+1 only starts to touch memory after griddepcontrol.wait, i.e. after N
+// has completed and flushed.  The scan is a chain of ~50 short kernels, so this latency is a large part of its duration.
+// The attribute is only set when the previous operation this context put on the stream was one of its own kernel
+// launches (pdl_chain): griddepcontrol.wait orders a kernel after its prerequisite GRIDS — measured: a kernel launched with
+// the attribute right behind a cudaMemsetAsync ran concurrently with that memset.  For the same reason the stage-local
+// clears on the scan path are kernels (vf_fill), not memset nodes.
 #define LAUNCH(kern, grid, block, smem, ...)                                                             \
   do                                                                                                     \
   {                                                                                                      \
-    kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                        \
+    cudaLaunchConfig_t cfg__ = {};                                                                       \
+    cfg__.gridDim = dim3(grid);                                                                          \
+    cfg__.blockDim = dim3(block);                                                                        \
+    cfg__.dynamicSmemBytes = (smem);                                                                     \
+    cfg__.stream = ctx->stream;                                                                          \
+    cudaLaunchAttribute at__[1];                                                                         \
+    at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                     \
+    at__[0].val.programmaticStreamSerializationAllowed = (ctx->pdl_enabled && ctx->pdl_chain) ? 1 : 0;   \
+    cfg__.attrs = at__;                                                                                  \
+    cfg__.numAttrs = 1;                                                                                  \
+    cudaError_t e__ = cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__);                                     \
     ctx->n_launches++;                                                                                   \
-    cudaError_t e__ = cudaGetLastError();                                                                \
+    ctx->pdl_chain = true;                                                                               \
+    if (e__ == cudaSuccess)                                                                              \
+      e__ = cudaGetLastError();                                                                          \
     if (e__ != cudaSuccess)                                                                              \
       return vf_fail(ctx, VOFOD_E_CUDA, "launch %s failed: %s (%s:%d)", #kern, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
@@ -383,7 +486,11 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p);
 int vf_raycast_expand(vofod_ctx* ctx, uint32_t* d_counts, float* d_lengths);
 // pipeline.cu
 int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p);  // point + repeat count come from ctx->dyn
-int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
+int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, bool claim_for_update);
+int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase,
+                       bool claim_for_update);
+int vf_update_points_scan_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
+int vf_update_owner(vofod_ctx* ctx);
 int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score,
                          float flag);
 int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, const vofod_params* p = nullptr);

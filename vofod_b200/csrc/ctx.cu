@@ -145,7 +145,7 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->upd_owner, &ctx->upd_leftover, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vgh_cnt, &ctx->vgh_bits, &ctx->vgh_off, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
@@ -214,6 +214,18 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->alloc_gen++;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_PDL)
+  {
+    ctx->pdl_enabled = value != 0;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_VG_SORT)
+  {
+    ctx->vg_force_sort = value != 0;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_SEP_GENERAL)
   {
     ctx->sep_force_general = value != 0;
@@ -271,8 +283,17 @@ void vofod_default_params(vofod_params* p)
 // ======================================================================================================
 // kernels
 // ======================================================================================================
-__global__ void k_begin_call(unsigned long long* __restrict__ counters, const int zero_scan_counters)
+// `scan` != 0 (vofod_process_scan): also the rangefinder ground seed (A23, vofod_nodelet.cpp:581-613) and the reset of the
+// filter's min/max cell — two single-thread kernels less on the scan's critical path
+__global__ void k_begin_call(unsigned long long* __restrict__ counters, const int zero_scan_counters, const int scan, float* score, const Geom g,
+                             const ScanDyn* dyn, const double score_point, uint8_t* col_dirty, MinMax* mm)
 {
+  pdl_enter();
+  if (scan && threadIdx.x == 31)
+  {
+    minmax_init(mm);
+    range_update(score, g, dyn, score_point, col_dirty);
+  }
   if (threadIdx.x == 0)
     counters[CNT_EPOCH_BASE] += EPOCH_STRIDE;
   if (zero_scan_counters)
@@ -285,7 +306,10 @@ __global__ void k_begin_call(unsigned long long* __restrict__ counters, const in
   }
 }
 
-int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters)
+static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params);
+int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters) { return begin_call(ctx, zero_scan_counters, nullptr); }
+int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p) { return begin_call(ctx, true, &p); }
+static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params)
 {
   ctx->epoch_local = 0;
   ctx->epoch_calls++;
@@ -296,7 +320,54 @@ int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters)
     if (ctx->tile_state2.p)
       CK(cudaMemsetAsync(ctx->tile_state2.p, 0, ctx->tile_state2.cap, ctx->stream));
   }
-  LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0);
+  ctx->pdl_chain = false;  // whatever precedes an API call on the stream (the caller's own work included) completes first
+  if (scan_params)
+    ENSURE(ctx->scratch_d, 1024);  // MinMax + VgLayout of the filter (voxelgrid.cu)
+  LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0, scan_params ? 1 : 0, ctx->score.as<float>(), ctx->g,
+         ctx->dyn.as<ScanDyn>(), scan_params ? scan_params->score_point : 0.0, ctx->col_dirty.as<uint8_t>(), ctx->scratch_d.as<MinMax>());
+  return 0;
+}
+
+struct FillJobs
+{
+  FillJob j[4];
+};
+__global__ void __launch_bounds__(256) k_fill_words(const FillJobs jobs)
+{
+  pdl_enter();
+  const FillJob J = jobs.j[blockIdx.y];
+  if (!J.p)
+    return;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  // scalar head up to 16-byte alignment, uint4 body, scalar tail
+  size_t head = ((16 - ((size_t)J.p & 15)) & 15) / 4;
+  if (head > J.n_words)
+    head = J.n_words;
+  const size_t n4 = (J.n_words - head) / 4;
+  uint4* p4 = reinterpret_cast<uint4*>(J.p + head);
+  const uint4 v4 = make_uint4(J.value, J.value, J.value, J.value);
+  for (size_t i = tid; i < n4; i += nth)
+    p4[i] = v4;
+  for (size_t i = tid; i < head; i += nth)
+    J.p[i] = J.value;
+  for (size_t i = head + n4 * 4 + tid; i < J.n_words; i += nth)
+    J.p[i] = J.value;
+}
+int vf_fill(vofod_ctx* ctx, const FillJob* jobs, int n_jobs)
+{
+  FillJobs js = {};
+  size_t most = 0;
+  int k = 0;
+  for (int i = 0; i < n_jobs && k < 4; i++)
+    if (jobs[i].p && jobs[i].n_words)
+    {
+      js.j[k++] = jobs[i];
+      if (jobs[i].n_words > most)
+        most = jobs[i].n_words;
+    }
+  if (k == 0)
+    return 0;
+  LAUNCH(k_fill_words, dim3((unsigned)vf_blocks(ctx, most / 4 + 1, 256, 8), (unsigned)k), 256, 0, js);
   return 0;
 }
 
@@ -308,6 +379,7 @@ int vf_dyn_push(vofod_ctx* ctx)
 
 __global__ void k_fill_f32(float* __restrict__ p, const float v, const size_t n)
 {
+  pdl_enter();
   const size_t n4 = n / 4;
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4 v4 = make_float4(v, v, v, v);
@@ -319,11 +391,13 @@ __global__ void k_fill_f32(float* __restrict__ p, const float v, const size_t n)
 
 __global__ void k_flags_to_f32(const uint8_t* __restrict__ f, float* __restrict__ out, const size_t n)
 {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = (float)f[i];
 }
 __global__ void k_f32_to_flags(const float* __restrict__ in, uint8_t* __restrict__ f, const size_t n)
 {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     f[i] = (uint8_t)in[i];
 }
@@ -331,6 +405,7 @@ __global__ void k_f32_to_flags(const float* __restrict__ in, uint8_t* __restrict
 // nVoxelsOver (voxel_map.cpp:216-222): streaming count of val > thr
 __global__ void __launch_bounds__(256) k_count_over(const float* __restrict__ p, const size_t n, const float thr, unsigned long long* out)
 {
+  pdl_enter();
   unsigned cnt = 0;
   const size_t n4 = n / 4;
   const float4* p4 = reinterpret_cast<const float4*>(p);
@@ -362,6 +437,7 @@ __global__ void __launch_bounds__(256) k_count_over(const float* __restrict__ p,
 __global__ void __launch_bounds__(128) k_count_over_cols(const float* __restrict__ p, const Geom g, const uint8_t* __restrict__ dirty, const float thr,
                                                          unsigned long long* out)
 {
+  pdl_enter();
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)ncol;
   const int z_lo = blockIdx.y * DIRTY_ZC, z_hi = min(z_lo + DIRTY_ZC, g.st_size[2]);
@@ -388,6 +464,7 @@ __global__ void __launch_bounds__(128) k_count_over_cols(const float* __restrict
 
 __global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const size_t n, uint8_t* __restrict__ col_dirty)
 {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
   {
     const int x = coord_to_idx1(xyz[3 * i], g.off[0], g.inv), y = coord_to_idx1(xyz[3 * i + 1], g.off[1], g.inv), z = coord_to_idx1(xyz[3 * i + 2], g.off[2], g.inv);
@@ -405,6 +482,7 @@ __global__ void k_set_inf(float* __restrict__ score, const Geom g, const float* 
 __global__ void k_has_close_to(const float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const int stride, const size_t n, const float max_dist,
                                const float thr, uint8_t* __restrict__ out)
 {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = has_close_to(score, g, xyz[stride * i], xyz[stride * i + 1], xyz[stride * i + 2], max_dist, thr);
 }
@@ -412,6 +490,7 @@ __global__ void k_has_close_to(const float* __restrict__ score, const Geom g, co
 // isFloatingIdx (voxel_map.cpp:497-516)
 __global__ void k_is_floating(const float* __restrict__ score, const Geom g, const float* __restrict__ xyz, const size_t n, const float thr, uint8_t* __restrict__ out)
 {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
   {
     const int x = coord_to_idx1(xyz[3 * i], g.off[0], g.inv), y = coord_to_idx1(xyz[3 * i + 1], g.off[1], g.inv), z = coord_to_idx1(xyz[3 * i + 2], g.off[2], g.inv);
@@ -438,6 +517,7 @@ __global__ void k_is_floating(const float* __restrict__ score, const Geom g, con
 __global__ void k_trace_ray(const Geom g, const float sx, const float sy, const float sz, const float dx, const float dy, const float dz, const float length,
                             float* __restrict__ ddist_out, int* __restrict__ idx3_out, const size_t cap, unsigned long long* n_out)
 {
+  pdl_enter();
   if (blockIdx.x || threadIdx.x)
     return;
   const float start[3] = {sx, sy, sz}, dir[3] = {dx, dy, dz};
@@ -484,6 +564,7 @@ __global__ void k_trace_ray(const Geom g, const float sx, const float sy, const 
 __global__ void k_submap_copy(const float* __restrict__ score, const Geom g, const int nx, const int ny, const int nz, const int sx, const int sy, const int sz,
                               float* __restrict__ out)
 {
+  pdl_enter();
   const size_t n = (size_t)sx * sy * sz;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
   {
@@ -498,6 +579,7 @@ __global__ void k_submap_copy(const float* __restrict__ score, const Geom g, con
 __global__ void k_compact_count(const float* __restrict__ score, const Geom g, const float thr, const int greater, uint32_t* __restrict__ colcnt,
                                 const uint8_t* __restrict__ dirty)
 {
+  pdl_enter();
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)g.st_size[0] * g.st_size[1];
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x)
@@ -521,6 +603,7 @@ __global__ void k_compact_count(const float* __restrict__ score, const Geom g, c
 __global__ void k_compact_emit(const float* __restrict__ score, const Geom g, const float thr, const int greater, const int metric, const uint32_t* __restrict__ colcnt,
                                const uint32_t* __restrict__ coloff, vofod_xyzi* __restrict__ out, const size_t cap)
 {
+  pdl_enter();
   const int ncol = g.st_size[0] * g.st_size[1];
   const size_t sxy = (size_t)g.st_size[0] * g.st_size[1];
   const int sz = g.st_size[2];

@@ -10,19 +10,8 @@
 // ---- A23 rangefinder ground seed (vofod_nodelet.cpp:581-613) ----------------------------------------
 __global__ void k_range_update(float* __restrict__ score, const Geom g, const ScanDyn* __restrict__ dyn, const double score_point, uint8_t* __restrict__ col_dirty)
 {
-  const float x = dyn->range_pt[0], y = dyn->range_pt[1], z = dyn->range_pt[2];
-  const int repeats = dyn->n_seeds;
-  const int ix = coord_to_idx1(x, g.off[0], g.inv), iy = coord_to_idx1(y, g.off[1], g.inv), iz = coord_to_idx1(z, g.off[2], g.inv);
-  if (repeats <= 0 || !in_limits_idx(g, ix, iy, iz))  // :599
-    return;
-  const long long ci = cell_index(g, ix, iy, iz);
-  if (ci < 0)
-    return;
-  float m = score[ci];
-  for (int r = 0; r < repeats; r++)
-    m = (float)(((double)m + score_point) / 2.0);  // :610
-  score[ci] = m;
-  col_dirty[dirty_index(g, ix - g.st_lo[0], iy - g.st_lo[1], iz - g.st_lo[2])] = 1;
+  pdl_enter();
+  range_update(score, g, dyn, score_point, col_dirty);
 }
 
 int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
@@ -32,34 +21,130 @@ int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
 }
 
 // ---- A11 updateVoxel / updateVMaps (vofod_nodelet.cpp:777-809) ---------------------------------------
-__global__ void __launch_bounds__(256) k_update_points(float* __restrict__ score, uint8_t* __restrict__ flags, const Geom g, const vofod_vox* __restrict__ vox,
-                                                       const uint8_t* __restrict__ sel, const int sel_value, const unsigned long long* __restrict__ d_m,
-                                                       const size_t m_cap, const float vmap_score, const uint8_t vflag, uint32_t* __restrict__ flagged,
-                                                       const size_t flagged_cap, unsigned long long* __restrict__ counters, uint8_t* __restrict__ col_dirty)
+// The reference walks the cloud twice (:946-948: points of close clusters with score_point / flag 2, then the others with
+// score_unknown / flag 3) and updates the voxel of each point in turn.  Inside a scan the points are the centroids of a
+// voxel grid that is aligned with the map (:664-665), one per cell; for any other cloud (the staged entry point, a
+// differently aligned filter) two points can share a cell, and then the reference applies both updates, in cloud order.
+// To get exactly that from a parallel kernel every active point first CLAIMS its cell with
+// atomicMin(owner[cell], key), key = (pass << 30) | index = its place in the reference's order.  The update kernel lets
+// only the claim holder apply its update (and release the claim); every other point of an already claimed cell goes to a
+// left-over list, which the last block to finish sorts by key and applies one by one (normally the list is empty).
+// Both passes of a scan run in ONE launch; their claims ride along in k_close_finish.
+#define UPD_EMPTY 0xFFFFFFFFu
+struct UpdArgs
 {
+  float score[2];    // [pass]
+  uint8_t flag[2];
+  int both;          // 1: every point is active, pass = (sel[i] == sel_value ? 0 : 1); 0: only points with sel[i] == sel_value (or all, sel == NULL), pass 0
+  int sel_value;
+};
+__device__ __forceinline__ bool upd_point(const Geom& g, const vofod_vox& v, long long& ci, int& xc, int& yc, int& zc)
+{
+  xc = coord_to_idx1(v.x, g.off[0], g.inv), yc = coord_to_idx1(v.y, g.off[1], g.inv), zc = coord_to_idx1(v.z, g.off[2], g.inv);
+  if (!in_limits_idx(g, xc, yc, zc))  // the reference's vector::at would throw; unreachable after the op-area crop
+    return false;
+  ci = cell_index(g, xc, yc, zc);
+  return ci >= 0;  // slab mode: every held cell (own range AND halo) takes the update, which keeps halos consistent without any exchange
+}
+__device__ __forceinline__ void upd_apply(float* __restrict__ score, uint8_t* __restrict__ flags, uint8_t* __restrict__ col_dirty, const Geom& g, const vofod_vox& v,
+                                          const long long ci, const int xc, const int yc, const int zc, const float vmap_score, const uint8_t vflag)
+{
+  const unsigned c = v.count > 63u ? 63u : v.count;                   // std::clamp(pt.range, 0u, 63u)
+  const float w = 1.0f / (float)(1ull << c);                          // :791
+  score[ci] = w * score[ci] + (1.0f - w) * vmap_score;                // :794
+  flags[ci] = vflag;                                                  // :796
+  col_dirty[dirty_index(g, xc - g.st_lo[0], yc - g.st_lo[1], zc - g.st_lo[2])] = 1;
+}
+__device__ __forceinline__ void upd_claim(const Geom& g, const vofod_vox& v, const unsigned key, unsigned* __restrict__ owner)
+{
+  long long ci;
+  int xc, yc, zc;
+  if (upd_point(g, v, ci, xc, yc, zc))
+    atomicMin(owner + ci, key);
+}
+// claims for the staged entry point (inside a scan k_close_finish places them)
+__global__ void __launch_bounds__(256) k_update_claim(const Geom g, const vofod_vox* __restrict__ vox, const uint8_t* __restrict__ sel, const UpdArgs a,
+                                                      const unsigned long long* __restrict__ d_m, const size_t m_cap, unsigned* __restrict__ owner)
+{
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
   {
-    if (sel && sel[i] != (uint8_t)sel_value)
+    const bool is_sel = !sel || sel[i] == (uint8_t)a.sel_value;
+    if (!a.both && !is_sel)
       continue;
+    upd_claim(g, vox[i], ((is_sel ? 0u : 1u) << 30) | (unsigned)i, owner);
+  }
+}
+__global__ void __launch_bounds__(256) k_update_points(float* __restrict__ score, uint8_t* __restrict__ flags, const Geom g, const vofod_vox* __restrict__ vox,
+                                                       const uint8_t* __restrict__ sel, const UpdArgs a, const unsigned long long* __restrict__ d_m, const size_t m_cap,
+                                                       uint32_t* __restrict__ flagged, const size_t flagged_cap, unsigned long long* __restrict__ counters,
+                                                       uint8_t* __restrict__ col_dirty, unsigned* __restrict__ owner, unsigned* __restrict__ leftover)
+{
+  pdl_enter();
+  __shared__ bool s_last;
+  const size_t m = prims::dev_count(d_m, m_cap);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const bool is_sel = !sel || sel[i] == (uint8_t)a.sel_value;
+    if (!a.both && !is_sel)
+      continue;
+    const int pass = is_sel ? 0 : 1;
+    const unsigned key = ((unsigned)pass << 30) | (unsigned)i;
     const vofod_vox v = vox[i];
-    const int xc = coord_to_idx1(v.x, g.off[0], g.inv), yc = coord_to_idx1(v.y, g.off[1], g.inv), zc = coord_to_idx1(v.z, g.off[2], g.inv);
-    if (!in_limits_idx(g, xc, yc, zc))  // the reference's vector::at would throw; unreachable after the op-area crop
+    long long ci;
+    int xc, yc, zc;
+    if (!upd_point(g, v, ci, xc, yc, zc))
       continue;
-    const long long ci = cell_index(g, xc, yc, zc);
-    if (ci < 0)  // slab mode: every held cell (own range AND halo) takes the update, which keeps halos consistent without any exchange
+    if (owner[ci] != key)
+    {
+      leftover[atomicAdd(counters + CNT_UPD_LEFT, 1ull)] = key;  // < m entries
       continue;
-    const unsigned c = v.count > 63u ? 63u : v.count;                   // std::clamp(pt.range, 0u, 63u)
-    const float w = 1.0f / (float)(1ull << c);                          // :791
-    score[ci] = w * score[ci] + (1.0f - w) * vmap_score;                // :794
-    flags[ci] = vflag;                                                  // :796
-    col_dirty[dirty_index(g, xc - g.st_lo[0], yc - g.st_lo[1], zc - g.st_lo[2])] = 1;
+    }
+    upd_apply(score, flags, col_dirty, g, v, ci, xc, yc, zc, a.score[pass], a.flag[pass]);
+    owner[ci] = UPD_EMPTY;
     const unsigned long long k = atomicAdd(counters + CNT_FLAGGED, 1ull);
     if (k < flagged_cap)
       flagged[k] = (uint32_t)ci;
     else
       counters[CNT_FLAGGED_OVERFLOW] = 1ull;
   }
+  // the last block to get here applies the left-overs in the reference's order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(counters + CNT_UPD_TICKET, 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0)
+    return;
+  __threadfence();
+  const unsigned long long n_left = *(volatile unsigned long long*)(counters + CNT_UPD_LEFT);
+  for (unsigned long long t = 1; t < n_left; t++)  // insertion sort: the list is empty or tiny
+  {
+    const unsigned key = *(volatile unsigned*)(leftover + t);
+    unsigned long long u = t;
+    for (; u > 0 && *(volatile unsigned*)(leftover + u - 1) > key; u--)
+      leftover[u] = *(volatile unsigned*)(leftover + u - 1);
+    leftover[u] = key;
+  }
+  for (unsigned long long t = 0; t < n_left; t++)
+  {
+    const unsigned key = *(volatile unsigned*)(leftover + t);
+    const int pass = (int)(key >> 30);
+    const vofod_vox v = vox[key & 0x3FFFFFFFu];
+    long long ci;
+    int xc, yc, zc;
+    if (upd_point(g, v, ci, xc, yc, zc))
+    {
+      volatile float* sc = score + ci;  // written by another block a moment ago
+      const unsigned c = v.count > 63u ? 63u : v.count;
+      const float w = 1.0f / (float)(1ull << c);
+      *sc = w * *sc + (1.0f - w) * a.score[pass];
+      flags[ci] = a.flag[pass];
+    }
+  }
+  counters[CNT_UPD_LEFT] = 0ull;
+  counters[CNT_UPD_TICKET] = 0ull;
 }
 
 static int ensure_flagged(vofod_ctx* ctx, size_t want)
@@ -74,19 +159,61 @@ static int ensure_flagged(vofod_ctx* ctx, size_t want)
   return 0;
 }
 
-int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score, float flag)
+static int update_points_launch(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, const UpdArgs& a, const unsigned long long* d_m, size_t m_cap, bool claim)
 {
   if (m_cap == 0)
     return 0;
+  if (m_cap >= (size_t(1) << 30))
+    return vf_fail(ctx, VOFOD_E_INVALID, "too many points for one update");
   RET(ensure_flagged(ctx, 4 * m_cap > (size_t(1) << 20) ? 4 * m_cap : (size_t(1) << 20)));
-  LAUNCH(k_update_points, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->score.as<float>(), ctx->flags.as<uint8_t>(), ctx->g, d_vox, d_sel, sel_value, d_m, m_cap, score,
-         (uint8_t)flag, ctx->flagged.as<uint32_t>(), ctx->flagged_cap, ctx->d_counters.as<unsigned long long>(), ctx->col_dirty.as<uint8_t>());
+  ENSURE(ctx->upd_leftover, m_cap * 4);
+  RET(vf_update_owner(ctx));
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  if (claim)
+    LAUNCH(k_update_claim, nb, 256, 0, ctx->g, d_vox, d_sel, a, d_m, m_cap, ctx->upd_owner.as<unsigned>());
+  LAUNCH(k_update_points, nb, 256, 0, ctx->score.as<float>(), ctx->flags.as<uint8_t>(), ctx->g, d_vox, d_sel, a, d_m, m_cap, ctx->flagged.as<uint32_t>(), ctx->flagged_cap,
+         ctx->d_counters.as<unsigned long long>(), ctx->col_dirty.as<uint8_t>(), ctx->upd_owner.as<unsigned>(), ctx->upd_leftover.as<unsigned>());
   return 0;
+}
+// the claim grid: one word per cell, UPD_EMPTY whenever no update is in flight (claims are released by their holders)
+int vf_update_owner(vofod_ctx* ctx)
+{
+  const size_t n = (size_t)geom_cells(ctx->g);
+  if (ctx->upd_owner.cap >= n * 4 && ctx->upd_owner_cells == n)
+    return 0;
+  ENSURE(ctx->upd_owner, n * 4);
+  CK(cudaMemsetAsync(ctx->upd_owner.p, 0xFF, n * 4, ctx->stream));
+  ctx->upd_owner_cells = n;
+  return 0;
+}
+
+// one pass (staged entry point): the points with sel[i] == sel_value (all when sel is NULL)
+int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score, float flag)
+{
+  UpdArgs a = {};
+  a.score[0] = score;
+  a.flag[0] = (uint8_t)flag;
+  a.both = 0;
+  a.sel_value = sel_value;
+  return update_points_launch(ctx, d_vox, d_sel, a, d_m, m_cap, true);
+}
+// both passes of a scan (:946-948); the claims were placed by k_close_finish
+int vf_update_points_scan_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap, const vofod_params& p)
+{
+  UpdArgs a = {};
+  a.score[0] = (float)p.score_point;
+  a.flag[0] = 2;
+  a.score[1] = (float)p.score_unknown;
+  a.flag[1] = 3;
+  a.both = 1;
+  a.sel_value = 1;
+  return update_points_launch(ctx, d_vox, d_in_close, a, d_m, m_cap, false);
 }
 
 // ---- A14/A15 findCloseFarClusters (vofod_nodelet.cpp:703-750) ----------------------------------------
 __global__ void k_bg_state(unsigned long long* __restrict__ counters, const unsigned long long min_sufficient)
 {
+  pdl_enter();
   if (counters[CNT_NBG] > min_sufficient)  // :716-721
     counters[CNT_STATE_BG] = 1ull;
 }
@@ -96,8 +223,9 @@ __global__ void k_bg_state(unsigned long long* __restrict__ counters, const unsi
 // here funnels every warp into one L2 sector once the ground cluster is background: measured 177 us instead of 10).
 __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ score, const Geom g, const vofod_vox* __restrict__ vox,
                                                       const unsigned long long* __restrict__ d_m, const size_t m_cap, const float max_dist, const float thr,
-                                                      uint8_t* __restrict__ pt_hit)
+                                                      uint8_t* __restrict__ pt_hit, int* __restrict__ cl_close)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -112,7 +240,10 @@ __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ 
     {
       // slab mode: the slab owning the point's voxel holds the whole window (halo >= mv) and answers for it
       if (lane == 0)
+      {
         pt_hit[i] = 0;
+        cl_close[i] = 0;
+      }
       continue;
     }
     const int bx = max(ox - mv, 0), by = max(oy - mv, 0), bz = max(oz - mv, 0);
@@ -142,13 +273,17 @@ __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ 
       }
     }
     if (lane == 0)
+    {
       pt_hit[i] = hit ? 1 : 0;
+      cl_close[i] = 0;  // per-cluster flags (indexed by label < m): cleared here, set by k_close_mark
+    }
   }
 }
 // a cluster is close iff ANY of its points is (:730-741)
 __global__ void __launch_bounds__(256) k_close_mark(const uint8_t* __restrict__ pt_hit, const int* __restrict__ labels, const unsigned long long* __restrict__ d_m,
                                                     const size_t m_cap, int* __restrict__ cl_close)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
@@ -161,9 +296,12 @@ __global__ void __launch_bounds__(256) k_close_mark(const uint8_t* __restrict__ 
       cl_close[l] = 1;
   }
 }
+// + (owner != NULL) the cell claims of the point update that follows inside a scan (see k_update_points)
 __global__ void __launch_bounds__(256) k_close_finish(const int* __restrict__ labels, const unsigned long long* __restrict__ d_m, const size_t m_cap,
-                                                      const int* __restrict__ cl_close, uint8_t* __restrict__ pt_close, unsigned long long* __restrict__ counters)
+                                                      const int* __restrict__ cl_close, uint8_t* __restrict__ pt_close, unsigned long long* __restrict__ counters,
+                                                      const Geom g, const vofod_vox* __restrict__ vox, unsigned* __restrict__ owner)
 {
+  pdl_enter();
   const size_t m = prims::dev_count(d_m, m_cap);
   unsigned n_close = 0, n_far = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
@@ -171,6 +309,8 @@ __global__ void __launch_bounds__(256) k_close_finish(const int* __restrict__ la
     const int l = labels[i];
     const int c = cl_close[l];
     pt_close[i] = (uint8_t)c;
+    if (owner)
+      upd_claim(g, vox[i], ((c != 0 ? 0u : 1u) << 30) | (unsigned)i, owner);
     if (l == (int)i)
     {
       n_close += c != 0;
@@ -190,7 +330,8 @@ __global__ void __launch_bounds__(256) k_close_finish(const int* __restrict__ la
 
 // phase 1 = everything up to the cross-slab exchange point (local background count, per-cluster close flags of the points this
 // slab answers for), phase 2 = the rest, phase 0 = both (unsharded)
-int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase)
+int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase,
+                       bool claim_for_update)
 {
   const float max_dist = (float)p.ground_points_max_distance;
   const float thr = (float)p.thr_new_obstacles;
@@ -201,8 +342,8 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
     {
       ENSURE(ctx->cl_close, m_cap * 4);
       ENSURE(ctx->pt_close, m_cap + 64);
-      CK(cudaMemsetAsync(ctx->cl_close.p, 0, m_cap * 4, ctx->stream));
-      LAUNCH(k_close_points, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>());
+      LAUNCH(k_close_points, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
+             ctx->cl_close.as<int>());
       LAUNCH(k_close_mark, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->pt_close.as<uint8_t>(), d_labels, d_m, m_cap, ctx->cl_close.as<int>());
     }
   }
@@ -218,14 +359,18 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
     LAUNCH(k_bg_state, 1, 1, 0, ctx->d_counters.as<unsigned long long>(), min_sufficient);
     ZERO_CNT(CNT_NCLOSE, 2);  // NCLOSE, NFAR
     if (m_cap)
+    {
+      if (claim_for_update)
+        RET(vf_update_owner(ctx));
       LAUNCH(k_close_finish, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_labels, d_m, m_cap, ctx->cl_close.as<int>(), ctx->pt_close.as<uint8_t>(),
-             ctx->d_counters.as<unsigned long long>());
+             ctx->d_counters.as<unsigned long long>(), ctx->g, d_vox, claim_for_update ? ctx->upd_owner.as<unsigned>() : nullptr);
+    }
   }
   return 0;
 }
-int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p)
+int vf_close_far_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, bool claim_for_update)
 {
-  return vf_close_far_phase(ctx, d_vox, d_labels, d_m, m_cap, p, 0);
+  return vf_close_far_phase(ctx, d_vox, d_labels, d_m, m_cap, p, 0, claim_for_update);
 }
 
 // ======================================================================================================
@@ -324,7 +469,7 @@ int vofod_close_far(vofod_ctx* ctx, const vofod_vox* pts, const int32_t* labels,
     CK(cudaMemcpyAsync(ctx->vox.p, pts, m * sizeof(vofod_vox), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->labels.p, labels, m * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
-  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), nullptr, m, *p));
+  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), nullptr, m, *p, false));
   unsigned long long nbg = 0;
   CK(cudaMemcpyAsync(&nbg, vf_cnt(ctx, CNT_NBG), 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (m)
@@ -388,8 +533,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     explicit Prezero(vofod_ctx* c_) : c(c_) { c->scan_prezero = true; }
     ~Prezero() { c->scan_prezero = false; }
   } prezero_guard(ctx);
-  RET(vf_begin_call(ctx, true));
   RET(vf_dyn_push(ctx));
+  RET(vf_begin_scan(ctx, p));  // + rangefinder seeds (A23) + the filter's min/max reset
   // The raycast accumulate reads only the scan, the LUT and the per-scan arguments and writes only the accumulator window:
   // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
   // parallel branch of the graph (issue-bound kernel next to a chain of latency-bound ones); with per-stage timing on it
@@ -407,9 +552,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
   STAGE_EVENT();
-  // rangefinder seeds (A23)
-  RET(vf_range_update_dev(ctx, p));
-  STAGE_EVENT();  // 0 "range"
+  STAGE_EVENT();  // 0 "range": the rangefinder seeds (A23) ride in the scan's first kernel (vf_begin_scan)
   // filterAndTransform (:928)
   RET(vf_filter_voxelize_dev(ctx, n, p));
   STAGE_EVENT();  // 1 "filtering"
@@ -419,11 +562,10 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
                      cnt + CNT_NCLUSTERS));
   STAGE_EVENT();  // 2 "clusterization"
   // findCloseFarClusters (:936)
-  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p));
+  RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p, true));
   STAGE_EVENT();  // 3 "close X far"
   // updateVMaps (:946-949)
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 1, cnt + CNT_VG_M, n, (float)p.score_point, 2.0f));
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 0, cnt + CNT_VG_M, n, (float)p.score_unknown, 3.0f));
+  RET(vf_update_points_scan_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 4 "vmap update"
   *applied_out = false;
   if (overlap_raycast)
@@ -868,7 +1010,7 @@ int vofod_slab_scan_begin(vofod_ctx* ctx, const vofod_pt* scan, int scan_on_devi
   ENSURE(ctx->labels, n * 4);
   RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p->ground_points_max_distance, ctx->labels.as<int>(),
                      cnt + CNT_NCLUSTERS));
-  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 1));
+  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 1, false));
   ctx->slab_n = n;
   return VOFOD_OK;
 }
@@ -892,9 +1034,8 @@ int vofod_slab_scan_end(vofod_ctx* ctx, const vofod_params* p, const vofod_sched
   const size_t n = ctx->slab_n;
   ctx->slab_n = 0;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 2));
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 1, cnt + CNT_VG_M, n, (float)p->score_point, 2.0f));
-  RET(vf_update_points_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), 0, cnt + CNT_VG_M, n, (float)p->score_unknown, 3.0f));
+  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 2, true));
+  RET(vf_update_points_scan_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, *p));
   ctx->detection_its++;
   int raycast_status = ctx->slab_raycast_status;
   bool applied = false;

@@ -160,7 +160,7 @@ __device__ __forceinline__ size_t dev_count(const unsigned long long* d_n, const
 {
   if (!d_n)
     return cap;
-  const unsigned long long n = *d_n;
+  const unsigned long long n = *after_wait(d_n);
   return n < cap ? (size_t)n : cap;
 }
 
@@ -185,6 +185,7 @@ struct ScanJobs
 static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local,
                                                              unsigned long long* watchdog)
 {
+  pdl_enter();
   __shared__ uint32_t ws[NT / 32];
   __shared__ uint32_t s_base;
   const ScanJob& J = jobs.j[blockIdx.y];
@@ -249,6 +250,7 @@ template <class KeyT>
 __global__ void __launch_bounds__(NT) k_radix_hist(const KeyT* __restrict__ keys, const unsigned long long* d_n, const size_t cap, uint32_t* __restrict__ hist,
                                                    const int begin_bit, const int passes)
 {
+  pdl_enter();
   __shared__ uint32_t sh[8 * 256];
   for (int i = threadIdx.x; i < passes * 256; i += NT)
     sh[i] = 0;
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(NT) k_radix_pass(const KeyT* __restrict__ kin,
                                                    unsigned long long* state, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local, const int shift,
                                                    unsigned long long* watchdog)
 {
+  pdl_enter();
   const uint32_t epoch = (uint32_t)(*epoch_base + epoch_local) & 0x3fffffffu;
   __shared__ uint32_t wcnt[NT / 32][256];
   __shared__ uint32_t gbase[256];
@@ -438,7 +441,10 @@ static inline int radix_sort(vofod_ctx* ctx, KeyT* a, KeyT* b, uint32_t* va, uin
   const size_t tiles = (cap + TILE - 1) / TILE + 1;
   ENSURE(ctx->tile_state, tiles * 256 * sizeof(unsigned long long));
   ENSURE(ctx->sort_hist, 8 * 256 * sizeof(uint32_t));
-  CK(cudaMemsetAsync(ctx->sort_hist.p, 0, 8 * 256 * sizeof(uint32_t), ctx->stream));
+  {
+    const FillJob fj[1] = {{ctx->sort_hist.as<uint32_t>(), 8 * 256, 0u}};
+    RET(vf_fill(ctx, fj, 1));
+  }
   uint32_t* hist = ctx->sort_hist.as<uint32_t>();
   LAUNCH((k_radix_hist<KeyT>), vf_blocks(ctx, cap, NT, 4), NT, 0, a, d_n, cap, hist, begin_bit, passes);
   KeyT* kin = a;

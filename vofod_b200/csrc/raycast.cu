@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
 {
+  pdl_enter();
   // stage this block's packed points (20 B each) through shared memory with coalesced 16 B loads
   __shared__ __align__(16) uint32_t s_pts[RB * 5];
   const vofod_pt* __restrict__ scan = dyn->scan;
@@ -227,7 +228,8 @@ struct ApplyArgs
 // max_element of the accumulator (:1542) — only needed by the old update rule
 __global__ void __launch_bounds__(256) k_raycast_max(const ScanDyn* __restrict__ dyn, const unsigned long long* __restrict__ acc, const double inv_scale, unsigned* __restrict__ out_bits)
 {
-  const Window w = dyn->win;
+  pdl_enter();
+  const Window w = after_wait(dyn)->win;
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
   float mx = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
                                                        const uint8_t* __restrict__ flags, const unsigned* __restrict__ max_bits,
                                                        unsigned long long* __restrict__ counters)
 {
+  pdl_enter();
   const Window w = dyn->win;
   const float its = (float)dyn->its_raycast;  // detection_its_diff as float (:1539)
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
@@ -309,6 +312,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
 __global__ void k_clear_flags(uint8_t* __restrict__ flags, const uint32_t* __restrict__ flagged, const size_t flagged_cap, const long long n_cells,
                               unsigned long long* __restrict__ counters, const int force_full)
 {
+  pdl_enter();
   if (counters[CNT_APPLY_ANY] == 0ull)
     return;
   const bool full = force_full || counters[CNT_FLAGGED_OVERFLOW] != 0ull;
@@ -327,6 +331,7 @@ __global__ void k_clear_flags(uint8_t* __restrict__ flags, const uint32_t* __res
 }
 __global__ void k_clear_flags_finish(unsigned long long* counters)
 {
+  pdl_enter();
   if (counters[CNT_APPLY_ANY] != 0ull)
   {
     counters[CNT_FLAGGED] = 0ull;
@@ -338,6 +343,7 @@ __global__ void k_clear_flags_finish(unsigned long long* counters)
 __global__ void k_raycast_expand(const Geom g, const Window w, const unsigned long long* __restrict__ acc, const double inv_scale, uint32_t* __restrict__ counts,
                                  float* __restrict__ lengths)
 {
+  pdl_enter();
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {

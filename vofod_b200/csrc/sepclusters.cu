@@ -38,22 +38,6 @@ int vf_voxel_grid_counted_dev(vofod_ctx* ctx, const vofod_xyzi* d_in, const unsi
 // ---------------------------------------------------------------------------------------------------------------
 #define SEP_ZC DIRTY_ZC
 static_assert(SEP_ZC == 32, "one lane per z-level of a chunk");
-__global__ void __launch_bounds__(256) k_sep_live(const uint8_t* __restrict__ dirty, const Geom g, const int nseg, const int nzc, uint2* __restrict__ live,
-                                                  unsigned long long* __restrict__ n_live)
-{
-  const unsigned lane = threadIdx.x & 31;
-  const int sx = g.st_size[0], sy = g.st_size[1];
-  const int n_items = sy * nseg * nzc;
-  for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
-  {
-    const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
-    const int x = seg * 32 + (int)lane;
-    const bool in = x < sx && (!dirty || dirty[((size_t)zc * sy + y) * sx + x]);
-    const unsigned mask = __ballot_sync(VOFOD_FULL, in);
-    if (mask && lane == 0)
-      live[atomicAdd(n_live, 1ull)] = make_uint2((unsigned)item, mask);
-  }
-}
 // loads the SEP_ZC levels of the item's lane column and returns the bit mask of levels above thr
 __device__ __forceinline__ unsigned sep_load_levels(const float* __restrict__ score, const size_t c, const size_t sxy, const int z_lo, const int z_hi, const bool on,
                                                     const float thr, float (&v)[SEP_ZC])
@@ -67,26 +51,31 @@ __device__ __forceinline__ unsigned sep_load_levels(const float* __restrict__ sc
     mine |= (v[k] > thr ? 1u : 0u) << k;
   return mine;
 }
-__global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint2* __restrict__ live,
-                                                        const unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
+// counting pass over ALL items; the ones that can hold a match are appended to `live` for the emission pass
+__global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict__ score, const Geom g, const float thr, const uint8_t* __restrict__ dirty,
+                                                        uint2* __restrict__ live, unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
                                                         uint32_t* __restrict__ colcnt, uint32_t* __restrict__ segbits)
 {
+  pdl_enter();
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const size_t sxy = (size_t)sx * sy;
-  const size_t n = (size_t)*n_live;
-  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += ((size_t)gridDim.x * blockDim.x) >> 5)
+  const int n_items = sy * nseg * nzc;
+  for (int item = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < n_items; item += (int)(((size_t)gridDim.x * blockDim.x) >> 5))
   {
-    const uint2 it = live[w];
-    const int item = (int)it.x;
     const int zc = item % nzc, seg = (item / nzc) % nseg, y = item / (nzc * nseg);
     const int x = seg * 32 + (int)lane;
-    const bool on = (it.y >> lane) & 1u;
+    const bool on = x < sx && (!dirty || dirty[((size_t)zc * sy + y) * sx + x]);
+    const unsigned mask = __ballot_sync(VOFOD_FULL, on);
+    if (!mask)
+      continue;
     const int z_lo = zc * SEP_ZC, z_hi = min(z_lo + SEP_ZC, sz);
     float v[SEP_ZC];
     const unsigned mine = sep_load_levels(score, (size_t)y * sx + x, sxy, z_lo, z_hi, on, thr, v);
     if (!__any_sync(VOFOD_FULL, mine != 0))
       continue;  // colcnt / segbits were zero-filled
+    if (lane == 0)
+      live[atomicAdd(n_live, 1ull)] = make_uint2((unsigned)item, mask);
     unsigned my_level_mask = 0;  // lane k keeps the mask of level z_lo + k
 #pragma unroll
     for (int k = 0; k < SEP_ZC; k++)
@@ -105,12 +94,13 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
                                                        const unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
                                                        const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds,
                                                        uint32_t* __restrict__ flag_in_order, int* __restrict__ parent, int* __restrict__ sizes, int* __restrict__ minidx,
-                                                       const size_t cap)
+                                                       int* __restrict__ nsure, const size_t cap)
 {
+  pdl_enter();
   const unsigned lane = threadIdx.x & 31;
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const size_t sxy = (size_t)sx * sy;
-  const size_t n = (size_t)*n_live;
+  const size_t n = (size_t)*after_wait(n_live);
   for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += ((size_t)gridDim.x * blockDim.x) >> 5)
   {
     const uint2 it = live[w];
@@ -152,6 +142,7 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
           parent[r] = (int)(base + __popc(bal & ((1u << head) - 1u)));
           sizes[r] = 0;
           minidx[r] = 0x7fffffff;
+          nsure[r] = 0;
         }
         if (o < cap)
           flag_in_order[o] = v[k] > thr_sure ? 1u : 0u;
@@ -180,13 +171,14 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   ENSURE(ctx->sep_segoff, padded(nsegs) * 4);
   ENSURE(ctx->sep_live, (n_items + 1) * sizeof(uint2));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, &p);
-  CK(cudaMemsetAsync(ctx->sep_colcnt.p, 0, ncc * 4, ctx->stream));
-  CK(cudaMemsetAsync(ctx->sep_segcnt.p, 0, nsegs * 4, ctx->stream));
+  {
+    const FillJob fj[2] = {{ctx->sep_colcnt.as<uint32_t>(), ncc, 0u}, {ctx->sep_segcnt.as<uint32_t>(), nsegs, 0u}};
+    RET(vf_fill(ctx, fj, 2));
+  }
   ZERO_CNT(CNT_SEP_LIVE, 1);
   const int nb = vf_blocks(ctx, n_items * 32, 256, 8);
-  LAUNCH(k_sep_live, nb, 256, 0, dirty, g, nseg, nzc, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE);
-  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc, ctx->sep_colcnt.as<uint32_t>(),
-         ctx->sep_segcnt.as<uint32_t>());
+  LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
+         ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
   RET(scan_excl_u32_pair(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K, false, ctx->sep_segcnt.as<uint32_t>(),
                          ctx->sep_segoff.as<uint32_t>(), nsegs, nullptr, true));
   if (host_total)
@@ -204,9 +196,10 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   ENSURE(ctx->cl_bg.parent, cap * 4);
   ENSURE(ctx->cl_bg.sizes, cap * 4);
   ENSURE(ctx->cl_bg.minidx, cap * 4);
+  ENSURE(ctx->sep_nsure, cap * 4);
   LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
          ctx->sep_coloff.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), ctx->cl_bg.parent.as<int>(),
-         ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>(), cap);
+         ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>(), ctx->sep_nsure.as<int>(), cap);
   return 0;
 }
 
@@ -215,6 +208,7 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
 __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__ ds, const uint32_t* __restrict__ counts, const int* __restrict__ labels,
                                                    const unsigned long long* __restrict__ d_k, const size_t cap, int* __restrict__ nsure)
 {
+  pdl_enter();
   const size_t k = prims::dev_count(d_k, cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < k; i0 += (size_t)gridDim.x * blockDim.x)
@@ -234,6 +228,7 @@ __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__
 __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels, const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
                                                  const unsigned min_sure, unsigned long long* __restrict__ counters)
 {
+  pdl_enter();
   const size_t k = prims::dev_count(d_k, cap);
   bool any = false;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
@@ -242,20 +237,28 @@ __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels,
   if (__any_sync(VOFOD_FULL, any) && (threadIdx.x & 31) == 0)
     counters[CNT_SEP_ANY_SURE] = 1ull;
 }
-__global__ void k_sep_state(unsigned long long* __restrict__ counters, const unsigned long long k_cap)
+__device__ __forceinline__ void sep_state(unsigned long long* __restrict__ counters, const unsigned long long k_cap)
 {
   const unsigned long long k = counters[CNT_SEP_K];
   if (k == 0ull || k > k_cap)
     return;  // empty cloud: the reference returns before touching the flag (:1155-1159); overflow: the host redoes the pass
   counters[CNT_STATE_SURE] = counters[CNT_SEP_ANY_SURE] ? 1ull : 0ull;  // :1196 / :1205
 }
+__global__ void k_sep_state(unsigned long long* __restrict__ counters, const unsigned long long k_cap)
+{
+  pdl_enter();
+  sep_state(counters, k_cap);
+}
 
 // K12 — :1244-1272
 __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, const vofod_vox* __restrict__ ds, const int* __restrict__ labels,
                                                    const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
                                                    const int3* __restrict__ offsets, const int n_off, const unsigned min_sure, const float w1, const float w2,
-                                                   const float update_val, const unsigned long long* __restrict__ counters, const unsigned long long k_cap)
+                                                   const float update_val, unsigned long long* counters, const unsigned long long k_cap)
 {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    sep_state(counters, k_cap);
   if (counters[CNT_SEP_ANY_SURE] == 0ull || counters[CNT_SEP_K] > k_cap)
     return;  // :1192-1199 (and: list overflow => nothing is touched, the host redoes the pass with a larger list)
   const size_t k = prims::dev_count(d_k, cap);
@@ -344,13 +347,16 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   else
     RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
                        k_cap ? ctx->sep_table_hint : 0));
-  CK(cudaMemsetAsync(ctx->sep_nsure.p, 0, K * 4, ctx->stream));
+  if (!fast)  // (the fast path's emission pass cleared its entries)
+  {
+    const FillJob fj[1] = {{ctx->sep_nsure.as<uint32_t>(), K, 0u}};
+    RET(vf_fill(ctx, fj, 1));
+  }
   ZERO_CNT(CNT_SEP_ANY_SURE, 1);
   const int nb = vf_blocks(ctx, K, 256, 8);
   LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), fast ? ctx->vg_flags.as<uint32_t>() : nullptr, ctx->sep_labels.as<int>(), d_kds, K,
          ctx->sep_nsure.as<int>());
   LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt);
-  LAUNCH(k_sep_state, 1, 1, 0, cnt, cap_guard);
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)
   if (ctx->sep_off_n < 0 || ctx->sep_off_mv != mv || ctx->sep_off_md != max_dist_idx)
   {
@@ -373,7 +379,10 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   }
   const size_t n_off = (size_t)ctx->sep_off_n;
   if (n_off == 0)
+  {
+    LAUNCH(k_sep_state, 1, 1, 0, cnt, cap_guard);
     return VOFOD_OK;
+  }
   const float dits = (float)(its_diff > 1 ? its_diff : 1);           // :1210-1217
   float w1 = powf(1.0f - 0.5f, dits);                                 // :1239-1241
   w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);

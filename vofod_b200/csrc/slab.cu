@@ -19,7 +19,6 @@
 
 int vf_map_alloc(vofod_ctx* ctx);  // ctx.cu
 void vf_bg_state_launch(vofod_ctx* ctx, const vofod_params& p);  // pipeline.cu
-int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase);
 
 extern "C" {
 int vofod_set_slab(vofod_ctx* ctx, int axis, int lo, int hi, int halo)

@@ -28,30 +28,10 @@ struct CropArgs
   int n;
 };
 
-// monotone float <-> int mapping for atomicMin/atomicMax
-__device__ __forceinline__ int f2ord(const float f)
-{
-  const int b = __float_as_int(f);
-  return b >= 0 ? b : b ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ord2f(const int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
-
-struct MinMax
-{
-  int mn[3], mx[3];
-  unsigned n_valid;
-  unsigned n_append;  // cursor of the compacting writers
-};
-
 __global__ void k_minmax_init(MinMax* mm)
 {
-  for (int a = 0; a < 3; a++)
-  {
-    mm->mn[a] = f2ord(3.402823466e+38f);
-    mm->mx[a] = f2ord(-3.402823466e+38f);
-  }
-  mm->n_valid = 0;
-  mm->n_append = 0;
+  pdl_enter();
+  minmax_init(mm);
 }
 
 // block-wide min/max/count, then ONE set of 7 global atomics per block (a per-warp commit serialises ~8k warps on 7 words)
@@ -112,6 +92,7 @@ __device__ __forceinline__ void block_minmax_commit(const bool valid, const floa
 // K1a — pcl::CropBox(negative) -> pcl::transformPointCloud -> pcl::CropBox (vofod_nodelet.cpp:626-655)
 __global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const ScanDyn* __restrict__ dyn, float4* __restrict__ pts, MinMax* mm)
 {
+  pdl_enter();
   __shared__ __align__(16) uint32_t s_pts[256 * 5];
   const vofod_pt* __restrict__ scan = dyn->scan;
   const Pose33 tf = dyn->tf;
@@ -176,6 +157,7 @@ __global__ void __launch_bounds__(256) k_crop_transform(const CropArgs a, const 
 __global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in, const int stride, const unsigned long long* __restrict__ d_n, const int cap,
                                                    float4* __restrict__ pts, MinMax* mm)
 {
+  pdl_enter();
   const int n = (int)prims::dev_count(d_n, (size_t)cap);
   const int idx = blockIdx.x * 256 + threadIdx.x;
   bool valid = idx < n;
@@ -193,24 +175,21 @@ __global__ void __launch_bounds__(256) k_load_cloud(const float* __restrict__ in
   block_minmax_commit(valid, x, y, z, mm);
 }
 
-// K1b — voxel_grid_weighted.cpp:56-111
-__global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, const int align, const float ac0, const float ac1, const float ac2, VgLayout* __restrict__ L,
-                            unsigned long long* __restrict__ counters, const int slot_nvalid, const int slot_overflow)
+// K1b — voxel_grid_weighted.cpp:56-111.  Returns the layout in L; n_valid == 0 gives the empty layout.
+__device__ inline void vg_layout_compute(const MinMax* mm, const float leaf, const int align, const float ac0, const float ac1, const float ac2, VgLayout& L)
 {
   const float inv = 1.0f / leaf;
-  L->leaf = leaf;
-  L->inv = inv;
-  L->n_valid = mm->n_valid;
-  L->overflow = 0;
-  counters[slot_nvalid] = mm->n_valid;
-  counters[slot_overflow] = 0;
-  if (mm->n_valid == 0)
+  L.leaf = leaf;
+  L.inv = inv;
+  L.n_valid = mm->n_valid;
+  L.overflow = 0;
+  if (L.n_valid == 0)
   {
     for (int a = 0; a < 3; a++)
     {
-      L->offset[a] = 0.f;
-      L->min_b[a] = L->max_b[a] = 0;
-      L->div[a] = 1;
+      L.offset[a] = 0.f;
+      L.min_b[a] = L.max_b[a] = 0;
+      L.div[a] = 1;
     }
     return;
   }
@@ -225,25 +204,171 @@ __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, con
   const long long dy = (long long)((max_p[1] - min_p[1]) * inv) + 2;
   const long long dz = (long long)((max_p[2] - min_p[2]) * inv) + 2;
   if (dx * dy * dz > 2147483647ll)
-  {
-    L->overflow = 1;
-    counters[slot_overflow] = 1;
-  }
+    L.overflow = 1;
   for (int a = 0; a < 3; a++)
   {
-    L->min_b[a] = (int)floorf(min_p[a] * inv);
-    L->max_b[a] = (int)floorf(max_p[a] * inv);
-    float off = (float)L->min_b[a] * leaf;
+    L.min_b[a] = (int)floorf(min_p[a] * inv);
+    L.max_b[a] = (int)floorf(max_p[a] * inv);
+    float off = (float)L.min_b[a] * leaf;
     if (align)
     {
       float aco = fmodf(ac[a] - leaf / 2, leaf);
       if (aco < 0)
         aco += leaf;
       off -= aco;
-      L->min_b[a] = (int)floorf(off * inv);
+      L.min_b[a] = (int)floorf(off * inv);
     }
-    L->offset[a] = off;
-    L->div[a] = L->max_b[a] - L->min_b[a] + 1;
+    L.offset[a] = off;
+    L.div[a] = L.max_b[a] - L.min_b[a] + 1;
+  }
+}
+__global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, const int align, const float ac0, const float ac1, const float ac2, VgLayout* __restrict__ L,
+                            unsigned long long* __restrict__ counters, const int slot_nvalid, const int slot_overflow)
+{
+  pdl_enter();
+  VgLayout l;
+  vg_layout_compute(mm, leaf, align, ac0, ac1, ac2, l);
+  *L = l;
+  counters[slot_nvalid] = l.n_valid;
+  counters[slot_overflow] = (unsigned long long)l.overflow;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sort-free VoxelGridWeighted for the scan path.  The filter's output is, per occupied leaf, its CENTRE and its point count,
+// in ascending key order (key = i + j*div0 + k*div0*div1) — nothing depends on the order of the points inside a leaf.  The
+// operation-area crop bounds the key range, so instead of sorting ~10^5 keys (histogram + 4 radix passes + run detection):
+//   count: every point adds 1 to cnt[key] (dense over the key range, zero at rest) and sets bit (i & 31) of the occupancy
+//          word of (k, j, i >> 5)                                  [one atomic pair per distinct key per warp]
+//   scan : popcount scan of the occupancy words = rank of every occupied leaf in key order (prims.cuh)
+//   emit : per set bit: centre + count -> out[rank]; the words and counts it read are put back to zero
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pts, const MinMax* mm, const float leaf, const float ac0, const float ac1,
+                                                   const float ac2, VgLayout* Lout, unsigned long long* counters, const int slot_nvalid, const int slot_overflow,
+                                                   const unsigned long long budget_cells, uint32_t* __restrict__ cnt, uint32_t* __restrict__ bits)
+{
+  pdl_enter();
+  __shared__ VgLayout sL;
+  if (threadIdx.x == 0)
+  {
+    VgLayout l;
+    vg_layout_compute(mm, leaf, 1, ac0, ac1, ac2, l);
+    const unsigned long long cells = (unsigned long long)l.div[0] * (unsigned long long)l.div[1] * (unsigned long long)l.div[2];
+    if (cells > budget_cells)
+      l.overflow = 1;  // cannot happen for points cropped to the operation area the budget was derived from
+    sL = l;
+    if (blockIdx.x == 0)
+    {
+      *Lout = l;
+      counters[slot_nvalid] = l.n_valid;
+      counters[slot_overflow] = (unsigned long long)l.overflow;
+      counters[CNT_VGH_WORDS] = l.overflow ? 0ull : (unsigned long long)((l.div[0] + 31) / 32) * (unsigned long long)l.div[1] * (unsigned long long)l.div[2];
+    }
+  }
+  __syncthreads();
+  const VgLayout L = sL;
+  if (L.overflow)
+    return;
+  const unsigned lane = threadIdx.x & 31;
+  const int rows = (int)L.n_valid;
+  const uint32_t d0 = (uint32_t)L.div[0], d01 = (uint32_t)L.div[0] * (uint32_t)L.div[1], total = d01 * (uint32_t)L.div[2];
+  const uint32_t nseg = (d0 + 31u) / 32u;
+  for (int i0 = (blockIdx.x * 256 + threadIdx.x) & ~31; i0 < rows; i0 += gridDim.x * 256)
+  {
+    const int i = i0 + (int)lane;
+    uint32_t key = 0xFFFFFF00u + lane;  // no point: a key of its own
+    bool valid = i < rows;
+    if (valid)
+    {
+      const float4 p = pts[i];
+      const int ijk0 = (int)floorf((p.x - L.offset[0]) * L.inv);
+      const int ijk1 = (int)floorf((p.y - L.offset[1]) * L.inv);
+      const int ijk2 = (int)floorf((p.z - L.offset[2]) * L.inv);
+      key = (uint32_t)(ijk0 + ijk1 * L.div[0] + ijk2 * L.div[0] * L.div[1]);
+      if (key >= total)
+      {
+        // a point outside its own bounding box (not reachable with finite inputs): the sort path would emit it with a wrapped
+        // key; here it is reported instead of written out of bounds
+        counters[slot_overflow] = 1ull;
+        valid = false;
+        key = 0xFFFFFF00u + lane;
+      }
+    }
+    const unsigned grp = __match_any_sync(VOFOD_FULL, key);
+    if (valid && lane == (unsigned)(__ffs(grp) - 1))
+    {
+      const uint32_t k2 = key / d01, rem = key - k2 * d01, k1 = rem / d0, k0 = rem - k1 * d0;
+      atomicAdd(cnt + key, (uint32_t)__popc(grp));
+      atomicOr(bits + ((size_t)k2 * L.div[1] + k1) * nseg + (k0 >> 5), 1u << (k0 & 31u));
+    }
+  }
+}
+// one warp per 32 consecutive occupancy words; the non-empty ones are handled 4 at a time, lane = bit
+__global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ Lp, const unsigned long long* __restrict__ d_words, const size_t words_cap,
+                                                  uint32_t* __restrict__ bits, const uint32_t* __restrict__ off, uint32_t* __restrict__ cnt, vofod_vox* __restrict__ out,
+                                                  const size_t out_cap)
+{
+  pdl_enter();
+  const VgLayout L = *after_wait(Lp);
+  const size_t n_words = prims::dev_count(d_words, words_cap);
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t d0 = (uint32_t)L.div[0], d1 = (uint32_t)L.div[1], d01 = d0 * d1;
+  const uint32_t nseg = (d0 + 31u) / 32u;
+  for (size_t w0 = (((size_t)blockIdx.x * 256 + threadIdx.x) >> 5) * 32; w0 < n_words; w0 += (((size_t)gridDim.x * 256) >> 5) * 32)
+  {
+    const size_t w = w0 + lane;
+    uint32_t my_bits = 0, my_off = 0;
+    if (w < n_words)
+    {
+      my_bits = bits[w];
+      if (my_bits)
+      {
+        my_off = off[w];
+        bits[w] = 0u;
+      }
+    }
+    unsigned todo = __ballot_sync(VOFOD_FULL, my_bits != 0u);
+    while (todo)
+    {
+      // up to 4 words per round: their count loads are independent and go out together
+      uint32_t key[4], c[4], r[4];
+      bool on[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+      {
+        on[q] = false;
+        if (!todo)
+          continue;
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t wb = __shfl_sync(VOFOD_FULL, my_bits, src);
+        const uint32_t wo = __shfl_sync(VOFOD_FULL, my_off, src);
+        const size_t ww = w0 + (size_t)src;
+        const uint32_t seg = (uint32_t)(ww % nseg), row = (uint32_t)(ww / nseg);
+        const uint32_t k1 = row % d1, k2 = row / d1;
+        on[q] = (wb >> lane) & 1u;
+        key[q] = (seg * 32u + lane) + k1 * d0 + k2 * d01;
+        r[q] = wo + (uint32_t)__popc(wb & prims::lanemask_lt());
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        c[q] = on[q] ? cnt[key[q]] : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (on[q])
+        {
+          cnt[key[q]] = 0u;
+          if (r[q] < out_cap)
+          {
+            const uint32_t k2 = key[q] / d01, rem = key[q] - k2 * d01, k1 = rem / d0, k0 = rem - k1 * d0;
+            vofod_vox v;
+            v.x = ((float)(int)k0 + 0.5f) * L.leaf + L.offset[0];
+            v.y = ((float)(int)k1 + 0.5f) * L.leaf + L.offset[1];
+            v.z = ((float)(int)k2 + 0.5f) * L.leaf + L.offset[2];
+            v.count = c[q];
+            out[r[q]] = v;
+          }
+        }
+    }
   }
 }
 
@@ -251,6 +376,7 @@ __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, con
 // `compact`: the first L.n_valid rows of pts are the valid points (k_crop_transform) and only those get keys
 __global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, const int n, const VgLayout* __restrict__ Lp, uint32_t* __restrict__ keys, const int compact)
 {
+  pdl_enter();
   const VgLayout L = *Lp;
   const int rows = compact ? (int)L.n_valid : n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < rows; i += gridDim.x * 256)
@@ -272,6 +398,7 @@ __global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts,
 __global__ void __launch_bounds__(256) k_vg_heads(const uint32_t* __restrict__ keys, const int n, uint32_t* __restrict__ heads, const VgLayout* __restrict__ Lp,
                                                   const int compact)
 {
+  pdl_enter();
   const int rows = compact ? (int)Lp->n_valid : n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
   {
@@ -283,6 +410,7 @@ __global__ void __launch_bounds__(256) k_vg_heads(const uint32_t* __restrict__ k
 __global__ void __launch_bounds__(256) k_vg_starts(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ heads_scan, const int n, uint32_t* __restrict__ ukey,
                                                    uint32_t* __restrict__ ustart, const VgLayout* __restrict__ Lp, const int compact)
 {
+  pdl_enter();
   const int rows = compact ? (int)Lp->n_valid : n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < rows; i += gridDim.x * 256)
   {
@@ -300,6 +428,7 @@ __global__ void __launch_bounds__(256) k_vg_emit(const uint32_t* __restrict__ uk
                                                  const unsigned long long* __restrict__ d_m, const uint32_t* __restrict__ over_prefix, vofod_vox* __restrict__ out,
                                                  const size_t out_cap)
 {
+  pdl_enter();
   const VgLayout L = *Lp;
   const unsigned m = (unsigned)*d_m;
   for (unsigned r = blockIdx.x * 256 + threadIdx.x; r < m && r < out_cap; r += gridDim.x * 256)
@@ -324,6 +453,7 @@ __global__ void __launch_bounds__(256) k_vg_emit(const uint32_t* __restrict__ uk
 __global__ void __launch_bounds__(256) k_vg_over_flags(const vofod_xyzi* __restrict__ in, const unsigned long long* __restrict__ d_n, const int cap, const float thr,
                                                       uint32_t* __restrict__ flags)
 {
+  pdl_enter();
   const int n = (int)prims::dev_count(d_n, (size_t)cap);
   for (int i = blockIdx.x * 256 + threadIdx.x; i <= cap; i += gridDim.x * 256)
     flags[i] = (i < n && in[i].intensity > thr) ? 1u : 0u;
@@ -412,7 +542,8 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
   }
   a.n = (int)n;
   MinMax* mm = ctx->scratch_d.as<MinMax>();
-  LAUNCH(k_minmax_init, 1, 1, 0, mm);
+  if (!ctx->scan_prezero)  // inside vofod_process_scan the scan's first kernel has done it (vf_begin_scan)
+    LAUNCH(k_minmax_init, 1, 1, 0, mm);
   LAUNCH(k_crop_transform, (int)((n + 255) / 256), 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->vg_pts.as<float4>(), mm);
   // align to the map: idxToCoord(0,0,0) (vofod_nodelet.cpp:664-665)
   const Geom& g = ctx->g;
@@ -427,6 +558,30 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
   for (int k = 0; k < 3; k++)
     cells *= (unsigned long long)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
   const int bits = cells + 1 < (1ull << 31) ? bits_for(cells + 1) : 32;
+  if (!ctx->vg_force_sort && cells < (1ull << 31) && cells * 4 <= (size_t(8) << 30))
+  {
+    // sort-free path: dense counts + occupancy words over the key range the crop allows
+    using namespace prims;
+    size_t words_cap = 1;
+    for (int k = 0; k < 3; k++)
+    {
+      const size_t d = (size_t)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
+      words_cap *= k == 0 ? (d + 31) / 32 : d;
+    }
+    ENSURE(ctx->vgh_cnt, (size_t)cells * 4);            // zero when (re)allocated, put back to zero by the emission pass
+    ENSURE(ctx->vgh_bits, padded(words_cap) * 4);       // the same
+    ENSURE(ctx->vgh_off, padded(words_cap) * 4);
+    ENSURE(ctx->vox, np * sizeof(vofod_vox));
+    unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+    VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
+    LAUNCH(k_vgh_count, vf_blocks(ctx, n, 256, 8), 256, 0, ctx->vg_pts.as<float4>(), mm, g.vs, ac[0], ac[1], ac[2], L, cnt, (int)CNT_VG_NVALID, (int)CNT_VG_OVERFLOW,
+           cells, ctx->vgh_cnt.as<uint32_t>(), ctx->vgh_bits.as<uint32_t>());
+    RET(scan_excl_u32_pair(ctx, ctx->vgh_bits.as<uint32_t>(), ctx->vgh_off.as<uint32_t>(), cnt + CNT_VGH_WORDS, words_cap, cnt + CNT_VG_M, true, nullptr, nullptr, 0,
+                           nullptr, false));
+    LAUNCH(k_vgh_emit, vf_blocks(ctx, words_cap, 256, 8), 256, 0, L, cnt + CNT_VGH_WORDS, words_cap, ctx->vgh_bits.as<uint32_t>(), ctx->vgh_off.as<uint32_t>(),
+           ctx->vgh_cnt.as<uint32_t>(), ctx->vox.as<vofod_vox>(), np);
+    return 0;
+  }
   return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, nullptr, 0.f, ctx->vox, CNT_VG_M, CNT_VG_NVALID, CNT_VG_OVERFLOW, true);
 }
 

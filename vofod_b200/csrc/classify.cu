@@ -696,6 +696,17 @@ static int bits_for_u(unsigned long long v)
   return b < 1 ? 1 : b;
 }
 
+// the clears of the next vf_classify_detect_dev over m_cap points (ahead of time, on the scan's side branch)
+int vf_classify_prefill(vofod_ctx* ctx, size_t m_cap)
+{
+  ENSURE(ctx->cls_sizes, m_cap * 4);
+  ENSURE(ctx->cls_maxidx, m_cap * 4);
+  const FillJob fj[2] = {{ctx->cls_sizes.as<uint32_t>(), m_cap, 0u}, {ctx->cls_maxidx.as<uint32_t>(), m_cap, 0u}};
+  RET(vf_fill(ctx, fj, 2));
+  ctx->cls_prefilled = m_cap;
+  return 0;
+}
+
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
                            const vofod_params& p)
 {
@@ -729,10 +740,9 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   ENSURE(ctx->explore_ws, cube * 4);          // stamps: zero-filled when (re)allocated
   ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
   ENSURE(ctx->cls_terms, terms_cap * 8);
-  {
-    const FillJob fj[2] = {{ctx->cls_sizes.as<uint32_t>(), m_cap, 0u}, {ctx->cls_maxidx.as<uint32_t>(), m_cap, 0u}};
-    RET(vf_fill(ctx, fj, 2));
-  }
+  if (ctx->cls_prefilled != m_cap)
+    RET(vf_classify_prefill(ctx, m_cap));
+  ctx->cls_prefilled = 0;
   ZERO_CNT(CNT_CLS_CURSOR, 1);
 
   const int nb = vf_blocks(ctx, m_cap, 256, 8);

@@ -313,6 +313,29 @@ __global__ void __launch_bounds__(256) k_cl_flatten(const unsigned long long* __
     atomicAdd(d_ncl, (unsigned long long)roots);
 }
 
+static size_t cl_table_size(const size_t m_cap, const size_t table_points_hint)
+{
+  // open addressing degrades gracefully: a table sized for the points EXPECTED (hint) still works up to its slot count
+  const size_t want = table_points_hint && table_points_hint < m_cap ? table_points_hint : m_cap;
+  size_t tsize = 1024;
+  while (tsize < 2 * want)
+    tsize <<= 1;
+  return tsize;
+}
+// the table clears of the NEXT vf_cluster_dev(ws, m_cap, hint), issued ahead of time (on the scan's side branch)
+int vf_cluster_prefill(vofod_ctx* ctx, ClusterWs& ws, size_t m_cap, size_t table_points_hint)
+{
+  if (m_cap == 0)
+    return 0;
+  const size_t tsize = cl_table_size(m_cap, table_points_hint);
+  ENSURE(ws.table_key, tsize * 8);
+  ENSURE(ws.table_head, tsize * 4 * 2);
+  const FillJob fj[2] = {{ws.table_key.as<uint32_t>(), tsize * 2, 0xFFFFFFFFu}, {ws.table_head.as<uint32_t>(), tsize, 0u}};  // keys = CL_EMPTY, counts = 0
+  RET(vf_fill(ctx, fj, 2));
+  ws.prefilled_tsize = tsize;
+  return 0;
+}
+
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol, int* d_labels,
                    unsigned long long* d_ncl, size_t table_points_hint)
 {
@@ -321,11 +344,7 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
     CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
   if (m_cap == 0)
     return 0;
-  // open addressing degrades gracefully: a table sized for the points EXPECTED (hint) still works up to its slot count
-  size_t want = table_points_hint && table_points_hint < m_cap ? table_points_hint : m_cap;
-  size_t tsize = 1024;
-  while (tsize < 2 * want)
-    tsize <<= 1;
+  const size_t tsize = cl_table_size(m_cap, table_points_hint);
   ENSURE(ws.pts, m_cap * 16);
   ENSURE(ws.table_key, tsize * 8);
   ENSURE(ws.table_head, tsize * 4 * 2);  // per slot: point count, start of the cell's range
@@ -335,10 +354,9 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
   ENSURE(ws.sizes, m_cap * 4);
   ENSURE(ws.root, m_cap * 4);
   ENSURE(ws.minidx, m_cap * 4);
-  {
-    const FillJob fj[2] = {{ws.table_key.as<uint32_t>(), tsize * 2, 0xFFFFFFFFu}, {ws.table_head.as<uint32_t>(), tsize, 0u}};  // keys = CL_EMPTY, counts = 0
-    RET(vf_fill(ctx, fj, 2));
-  }
+  if (ws.prefilled_tsize != tsize)
+    RET(vf_cluster_prefill(ctx, ws, m_cap, table_points_hint));
+  ws.prefilled_tsize = 0;
   if (!ctx->scan_prezero || second_use)
     CK(cudaMemsetAsync(vf_cnt(ctx, CNT_CL_CURSOR), 0, 8, ctx->stream));
   int* tcount = ws.table_head.as<int>();

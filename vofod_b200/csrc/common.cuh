@@ -200,6 +200,7 @@ __device__ inline void range_update(float* score, const Geom& g, const ScanDyn* 
 // Euclidean-cluster workspace handles (cluster.cu)
 struct ClusterWs
 {
+  size_t prefilled_tsize = 0;  // != 0: the hash table was cleared ahead of time for a table of this many slots (vf_cluster_prefill)
   DevBuf pts;        // float4 per point
   DevBuf table_key;  // u64 per slot
   DevBuf table_head; // i32 per slot
@@ -220,7 +221,9 @@ struct vofod_ctx
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // side branch for work that is independent of the main chain (raycast accumulate, second scan)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr;
+  size_t cls_prefilled = 0;     // classification work arrays cleared ahead of time for this many points
+  size_t sep_prefilled = 0;     // sepclusters fast-path count arrays cleared ahead of time (= their total length)
   std::string err;
   uint64_t n_launches = 0;
 
@@ -477,6 +480,9 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  //
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
                    int* d_labels, unsigned long long* d_ncl, size_t table_points_hint = 0);
+int vf_cluster_prefill(vofod_ctx* ctx, ClusterWs& ws, size_t m_cap, size_t table_points_hint);
+int vf_classify_prefill(vofod_ctx* ctx, size_t m_cap);
+int vf_sepclusters_prefill(vofod_ctx* ctx, const vofod_params& p);
 int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_segbits, const uint32_t* d_segoff, const unsigned long long* d_m,
                           size_t m_cap, int* d_labels, unsigned long long* d_ncl);
 // raycast.cu

@@ -98,6 +98,7 @@ int vofod_create(int device, vofod_ctx** out)
   cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fills, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
     cudaEventCreate(&ctx->ev[i]);
   ctx->ev_ok = true;
@@ -167,6 +168,8 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join)
     cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_fills)
+    cudaEventDestroy(ctx->ev_fills);
   if (ctx->stream2)
     cudaStreamDestroy(ctx->stream2);
   for (int i = 0; i < 2; i++)
@@ -659,6 +662,7 @@ int vf_compact_over_dev(vofod_ctx* ctx, float thr, int greater, int metric, DevB
   const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
   ENSURE(ctx->sep_colcnt, prims::padded(ncol) * sizeof(uint32_t));
   ENSURE(ctx->sep_coloff, prims::padded(ncol) * sizeof(uint32_t));
+  ctx->sep_prefilled = 0;  // sep_colcnt is about to be overwritten
   const uint8_t* dirty = greater ? vf_dirty_cols(ctx, thr, p) : nullptr;
   LAUNCH(k_compact_count, vf_blocks(ctx, ncol, 128, 16), 128, 0, ctx->score.as<float>(), g, thr, greater, ctx->sep_colcnt.as<uint32_t>(), dirty);
   RET(prims::scan_excl_u32(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncol, d_total));

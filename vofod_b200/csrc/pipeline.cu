@@ -539,16 +539,32 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
   // parallel branch of the graph (issue-bound kernel next to a chain of latency-bound ones); with per-stage timing on it
   // stays in line so that the stage table means what it says.
-  const bool overlap_raycast = plan.raycast_on && !plan.timed && ctx->stream2 != nullptr && ctx->overlap_enabled;
-  if (overlap_raycast)
+  // The stage-local clears (hash table of the clustering, work arrays of classification and sepclusters) depend on nothing
+  // either: they open the side branch, so that the main chain finds them done.
+  const bool side = !plan.timed && ctx->stream2 != nullptr && ctx->overlap_enabled;
+  const bool overlap_raycast = plan.raycast_on && side;
+  if (side)
   {
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     ctx->stream = ctx->stream2;
-    const int rrc = vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p);
+    int rrc = vf_cluster_prefill(ctx, ctx->cl, n, 0);
+    if (rrc >= 0 && s.do_classify)
+      rrc = vf_classify_prefill(ctx, n);
+    if (rrc >= 0 && s.do_sepclusters)
+      rrc = vf_sepclusters_prefill(ctx, p);
     ctx->stream = st;
     if (rrc < 0)
       return rrc;
+    CK(cudaEventRecord(ctx->ev_fills, ctx->stream2));
+    if (overlap_raycast)
+    {
+      ctx->stream = ctx->stream2;
+      rrc = vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p);
+      ctx->stream = st;
+      if (rrc < 0)
+        return rrc;
+    }
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
   STAGE_EVENT();
@@ -557,6 +573,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   RET(vf_filter_voxelize_dev(ctx, n, p));
   STAGE_EVENT();  // 1 "filtering"
   // clusterCloud (:932)
+  if (side)
+    CK(cudaStreamWaitEvent(st, ctx->ev_fills, 0));
   ENSURE(ctx->labels, n * 4);
   RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
                      cnt + CNT_NCLUSTERS));
@@ -568,8 +586,10 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   RET(vf_update_points_scan_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 4 "vmap update"
   *applied_out = false;
-  if (overlap_raycast)
+  if (side)
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join: the apply needs the accumulator
+  if (overlap_raycast)
+    ;
   else if (plan.raycast_on)
     RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
   else

@@ -182,10 +182,16 @@ struct ScanJobs
 {
   ScanJob j[2];
 };
+// SIPT = items per thread: 8 (2048-element tiles) for short inputs, 32 (8192) for long ones — the look-back chain of a long
+// input is what its scan waits for, and it is 4x shorter with the larger tile.
+constexpr int SCAN_BIG_IPT = 32;
+constexpr int SCAN_BIG_TILE = NT * SCAN_BIG_IPT;  // buffers are padded to this (padded())
+template <int SIPT>
 static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs, const unsigned long long* __restrict__ epoch_base, const uint32_t epoch_local,
                                                              unsigned long long* watchdog)
 {
   pdl_enter();
+  constexpr int STILE = NT * SIPT;
   __shared__ uint32_t ws[NT / 32];
   __shared__ uint32_t s_base;
   const ScanJob& J = jobs.j[blockIdx.y];
@@ -194,7 +200,7 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
   unsigned long long* total = J.total;
   const uint32_t epoch = (uint32_t)(*epoch_base + epoch_local) & 0x3fffffffu;
   const size_t n = dev_count(J.d_n, J.cap);
-  const int n_tiles = (int)((n + TILE - 1) / TILE);
+  const int n_tiles = (int)((n + STILE - 1) / STILE);
   if (n_tiles == 0)
   {
     if (blockIdx.x == 0 && threadIdx.x == 0 && total)
@@ -203,14 +209,17 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
-    const size_t base_i = (size_t)tile * TILE + (size_t)threadIdx.x * IPT;
-    uint32_t v[IPT];
-    const uint4 a = *reinterpret_cast<const uint4*>(in + base_i);
-    const uint4 b = *reinterpret_cast<const uint4*>(in + base_i + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const size_t base_i = (size_t)tile * STILE + (size_t)threadIdx.x * SIPT;
+    uint32_t v[SIPT];
+#pragma unroll
+    for (int q = 0; q < SIPT / 4; q++)
+    {
+      const uint4 a = *reinterpret_cast<const uint4*>(in + base_i + 4 * q);
+      v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
     uint32_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < IPT; k++)
+    for (int k = 0; k < SIPT; k++)
     {
       if (J.popc)
         v[k] = (uint32_t)__popc(v[k]);
@@ -232,15 +241,16 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
     }
     __syncthreads();
     uint32_t run = s_base + texcl;
-    uint32_t o[IPT];
 #pragma unroll
-    for (int k = 0; k < IPT; k++)
+    for (int q = 0; q < SIPT / 4; q++)
     {
-      o[k] = run;
-      run += v[k];
+      uint4 o;
+      o.x = run; run += v[4 * q];
+      o.y = run; run += v[4 * q + 1];
+      o.z = run; run += v[4 * q + 2];
+      o.w = run; run += v[4 * q + 3];
+      *reinterpret_cast<uint4*>(out + base_i + 4 * q) = o;
     }
-    *reinterpret_cast<uint4*>(out + base_i) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(out + base_i + 4) = make_uint4(o[4], o[5], o[6], o[7]);
     __syncthreads();
   }
 }
@@ -380,22 +390,24 @@ static inline int persistent_grid(const vofod_ctx* c, const size_t cap_items)
   const size_t g = (size_t)c->num_sms * 2;  // 2 x 256-thread CTAs per SM are always co-resident for these kernels
   return (int)(tiles < g ? tiles : g);
 }
-static inline size_t padded(const size_t n) { return ((n + TILE - 1) / TILE + 1) * TILE; }
+static inline size_t padded(const size_t n) { return ((n + SCAN_BIG_TILE - 1) / SCAN_BIG_TILE + 1) * SCAN_BIG_TILE; }
 
 // host drivers ------------------------------------------------------------------------------------------------
 // one tile per CTA whenever the CTAs fit the machine at once: a CTA that loops over tiles pays the full load -> look-back ->
 // store latency once per tile, back to back (measured: 18 us for a 1M-element scan with 2 CTAs per SM)
+template <int SIPT>
 static inline int scan_grid(const vofod_ctx* c, const size_t cap_items)
 {
   static int occ = 0;
   if (occ == 0)
   {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan_excl_u32, NT, 0) != cudaSuccess || o < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan_excl_u32<SIPT>, NT, 0) != cudaSuccess || o < 1)
       o = 2;
     occ = o;
   }
-  size_t tiles = (cap_items + TILE - 1) / TILE;
+  const size_t tile = (size_t)NT * SIPT;
+  size_t tiles = (cap_items + tile - 1) / tile;
   if (tiles < 1)
     tiles = 1;
   const size_t g = (size_t)c->num_sms * occ;
@@ -410,19 +422,24 @@ static inline int scan_excl_u32_pair(vofod_ctx* ctx, const uint32_t* a_in, uint3
   ScanJobs jobs;
   jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0};
   jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
-  int gx = scan_grid(ctx, a_cap), gy = 1;
+  const bool big = (a_cap > b_cap ? a_cap : b_cap) >= (size_t(1) << 18);
+  int gx = big ? scan_grid<SCAN_BIG_IPT>(ctx, a_cap) : scan_grid<IPT>(ctx, a_cap), gy = 1;
   if (b_in)
   {
     const size_t b_tiles = (b_cap + TILE - 1) / TILE + 1;
     ENSURE(ctx->tile_state2, b_tiles * sizeof(unsigned long long));
     jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0};
-    const int gb = scan_grid(ctx, b_cap);
+    const int gb = big ? scan_grid<SCAN_BIG_IPT>(ctx, b_cap) : scan_grid<IPT>(ctx, b_cap);
     gx = gx > gb ? gx : gb;
     gy = 2;
   }
   if (ctx->epoch_local >= EPOCH_STRIDE)
     return vf_fail(ctx, VOFOD_E_INTERNAL, "more than %d look-back launches in one call", EPOCH_STRIDE);
-  LAUNCH(k_scan_excl_u32, dim3((unsigned)gx, (unsigned)gy), NT, 0, jobs, vf_cnt(ctx, CNT_EPOCH_BASE), (uint32_t)(ctx->epoch_local++), vf_cnt(ctx, CNT_WATCHDOG));
+  if (big)
+    LAUNCH(k_scan_excl_u32<SCAN_BIG_IPT>, dim3((unsigned)gx, (unsigned)gy), NT, 0, jobs, vf_cnt(ctx, CNT_EPOCH_BASE), (uint32_t)(ctx->epoch_local++),
+           vf_cnt(ctx, CNT_WATCHDOG));
+  else
+    LAUNCH(k_scan_excl_u32<IPT>, dim3((unsigned)gx, (unsigned)gy), NT, 0, jobs, vf_cnt(ctx, CNT_EPOCH_BASE), (uint32_t)(ctx->epoch_local++), vf_cnt(ctx, CNT_WATCHDOG));
   return 0;
 }
 static inline int scan_excl_u32(vofod_ctx* ctx, const uint32_t* in, uint32_t* out, const unsigned long long* d_n, const size_t cap, unsigned long long* d_total)

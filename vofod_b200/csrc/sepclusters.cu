@@ -171,10 +171,12 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   ENSURE(ctx->sep_segoff, padded(nsegs) * 4);
   ENSURE(ctx->sep_live, (n_items + 1) * sizeof(uint2));
   const uint8_t* dirty = vf_dirty_cols(ctx, thr, &p);
+  if (ctx->sep_prefilled != ncc + nsegs)
   {
     const FillJob fj[2] = {{ctx->sep_colcnt.as<uint32_t>(), ncc, 0u}, {ctx->sep_segcnt.as<uint32_t>(), nsegs, 0u}};
     RET(vf_fill(ctx, fj, 2));
   }
+  ctx->sep_prefilled = 0;
   ZERO_CNT(CNT_SEP_LIVE, 1);
   const int nb = vf_blocks(ctx, n_items * 32, 256, 8);
   LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
@@ -289,6 +291,30 @@ __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, c
       old = prev;
     }
   }
+}
+
+// the clears of the next fast-path pass, ahead of time (on the scan's side branch); a no-op when that pass would not take
+// the fast path
+int vf_sepclusters_prefill(vofod_ctx* ctx, const vofod_params& p)
+{
+  using namespace prims;
+  const float vs = ctx->cfg_voxel_size > 0.f ? ctx->cfg_voxel_size : ctx->g.vs;
+  const int mv = (int)ceilf((float)(p.sep_max_bg_distance / (double)vs));
+  if (p.sep_pause || mv - 1 != 1 || ctx->sep_force_general || ctx->slab_on)
+    return 0;
+  const Geom& g = ctx->g;
+  const int nseg = (g.st_size[0] + 31) / 32;
+  const int nzc = (g.st_size[2] + SEP_ZC - 1) / SEP_ZC;
+  const size_t ncc = (size_t)g.st_size[0] * g.st_size[1] * nzc;
+  const size_t nsegs = (size_t)g.st_size[1] * g.st_size[2] * nseg;
+  if (nsegs >= (size_t(1) << 31) || ncc >= (size_t(1) << 31))
+    return 0;
+  ENSURE(ctx->sep_colcnt, padded(ncc) * 4);
+  ENSURE(ctx->sep_segcnt, padded(nsegs) * 4);
+  const FillJob fj[2] = {{ctx->sep_colcnt.as<uint32_t>(), ncc, 0u}, {ctx->sep_segcnt.as<uint32_t>(), nsegs, 0u}};
+  RET(vf_fill(ctx, fj, 2));
+  ctx->sep_prefilled = ncc + nsegs;
+  return 0;
 }
 
 // k_cap == 0: exact mode (one host read-back sizes the background-voxel list).  k_cap > 0: the list is capped at k_cap rows and

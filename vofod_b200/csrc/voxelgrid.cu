@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
     }
   }
 }
-// one warp per 32 consecutive occupancy words; the non-empty ones are handled 4 at a time, lane = bit
+// one warp per 32 consecutive occupancy words; the non-empty ones are handled VGH_ROUND at a time, lane = bit
+#define VGH_ROUND 8
 __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ Lp, const unsigned long long* __restrict__ d_words, const size_t words_cap,
                                                   uint32_t* __restrict__ bits, const uint32_t* __restrict__ off, uint32_t* __restrict__ cnt, vofod_vox* __restrict__ out,
                                                   const size_t out_cap)
@@ -329,11 +330,11 @@ __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ L
     unsigned todo = __ballot_sync(VOFOD_FULL, my_bits != 0u);
     while (todo)
     {
-      // up to 4 words per round: their count loads are independent and go out together
-      uint32_t key[4], c[4], r[4];
-      bool on[4];
+      // up to VGH_ROUND words per round: their count loads are independent and go out together
+      uint32_t key[VGH_ROUND], c[VGH_ROUND], r[VGH_ROUND];
+      bool on[VGH_ROUND];
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < VGH_ROUND; q++)
       {
         on[q] = false;
         if (!todo)
@@ -350,10 +351,10 @@ __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ L
         r[q] = wo + (uint32_t)__popc(wb & prims::lanemask_lt());
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < VGH_ROUND; q++)
         c[q] = on[q] ? cnt[key[q]] : 0u;
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < VGH_ROUND; q++)
         if (on[q])
         {
           cnt[key[q]] = 0u;

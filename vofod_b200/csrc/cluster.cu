@@ -391,6 +391,8 @@ int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride
 // — one union per pair of touching runs instead of one per pair of touching voxels (a ground plane has ~10x fewer).
 // parent[] / sizes[] / minidx[] come initialised from the emission pass.
 // ---------------------------------------------------------------------------------------------------------------
+// FOUR threads per point, one per forward row: the work of a head is a chain of dependent loads (own mask -> row masks ->
+// rank offsets -> parents), and four short chains side by side finish sooner than one long one.
 __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const vofod_vox* __restrict__ ds, const Geom g,
                                                   const uint32_t* __restrict__ segbits, const uint32_t* __restrict__ segoff, int* __restrict__ parent)
 {
@@ -398,8 +400,10 @@ __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __re
   const size_t m = prims::dev_count(d_m, m_cap);
   const int sx = g.st_size[0], sy = g.st_size[1], sz = g.st_size[2];
   const int nseg = (sx + 31) / 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < 4 * m; t += (size_t)gridDim.x * blockDim.x)
   {
+    const size_t i = t >> 2;
+    const int q = (int)(t & 3);
     const vofod_vox v = ds[i];
     const int x = (int)v.x - g.st_lo[0], y = (int)v.y - g.st_lo[1], z = (int)v.z - g.st_lo[2];
     const int seg = x >> 5, b = x & 31;
@@ -423,41 +427,34 @@ __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __re
           ri = uf_link(parent, ri, rj);
       }
     };
-    if (x1 == 31 && seg + 1 < nseg && (segbits[row + seg + 1] & 1u))
+    if (q == 0 && x1 == 31 && seg + 1 < nseg && (segbits[row + seg + 1] & 1u))
       unite(segoff[row + seg + 1]);
-#pragma unroll
-    for (int q = 0; q < 4; q++)
+    const int dy = q == 1 ? -1 : (q == 2 ? 0 : 1), dz = q == 0 ? 0 : 1;  // forward rows (y+1,z), (y-1,z+1), (y,z+1), (y+1,z+1)
+    const int ny = y + dy, nz = z + dz;
+    if (ny < 0 || ny >= sy || nz >= sz)
+      continue;
+    const size_t nrow = ((size_t)nz * sy + ny) * nseg;
+    const uint32_t wc = segbits[nrow + seg];
+    const uint32_t wl = (b == 0 && seg > 0) ? segbits[nrow + seg - 1] : 0u;
+    const uint32_t wr = (x1 == 31 && seg + 1 < nseg) ? segbits[nrow + seg + 1] : 0u;
+    // 34-bit window, position p <-> x = 32*seg - 1 + p; of interest: x in [x0-1, x1+1] <-> p in [b, x1+2]
+    unsigned long long w = (unsigned long long)(wl >> 31) | ((unsigned long long)wc << 1) | ((unsigned long long)(wr & 1u) << 33);
+    w &= ((1ull << (len + 2)) - 1ull) << b;
+    while (w)
     {
-      const int dy = q == 1 ? -1 : (q == 2 ? 0 : 1), dz = q == 0 ? 0 : 1;
-      const int ny = y + dy, nz = z + dz;
-      if (ny < 0 || ny >= sy || nz >= sz)
-        continue;
-      const size_t nrow = ((size_t)nz * sy + ny) * nseg;
-      const uint32_t wc = segbits[nrow + seg];
-      const uint32_t wl = (b == 0 && seg > 0) ? segbits[nrow + seg - 1] : 0u;
-      const uint32_t wr = (x1 == 31 && seg + 1 < nseg) ? segbits[nrow + seg + 1] : 0u;
-      // 34-bit window, position p <-> x = 32*seg - 1 + p; of interest: x in [x0-1, x1+1] <-> p in [b, x1+2]
-      unsigned long long w = (unsigned long long)(wl >> 31) | ((unsigned long long)wc << 1) | ((unsigned long long)(wr & 1u) << 33);
-      w &= ((1ull << (len + 2)) - 1ull) << b;
-      while (w)
-      {
-        const int p = __ffsll((long long)w) - 1;
-        const unsigned long long inv = ~(w >> p);
-        const int rl = __ffsll((long long)inv) - 1;  // >= 1; w has at most 34 bits, so inv always has a set bit
-        w &= ~(((1ull << rl) - 1ull) << p);
-        uint32_t j;
-        if (p == 0)
-          j = segoff[nrow + seg - 1] + (uint32_t)__popc(wl & 0x7fffffffu);
-        else if (p == 33)
-          j = segoff[nrow + seg + 1];
-        else
-          j = segoff[nrow + seg] + (uint32_t)__popc(wc & ((1u << (p - 1)) - 1u));
-        unite(j);
-      }
+      const int p = __ffsll((long long)w) - 1;
+      const unsigned long long inv = ~(w >> p);
+      const int rl = __ffsll((long long)inv) - 1;  // >= 1; w has at most 34 bits, so inv always has a set bit
+      w &= ~(((1ull << rl) - 1ull) << p);
+      uint32_t j;
+      if (p == 0)
+        j = segoff[nrow + seg - 1] + (uint32_t)__popc(wl & 0x7fffffffu);
+      else if (p == 33)
+        j = segoff[nrow + seg + 1];
+      else
+        j = segoff[nrow + seg] + (uint32_t)__popc(wc & ((1u << (p - 1)) - 1u));
+      unite(j);
     }
-    const int r = uf_find(parent, (int)i);
-    if (r != (int)i && parent[i] != r)
-      parent[i] = r;
   }
 }
 
@@ -470,7 +467,7 @@ int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, 
     return 0;
   ENSURE(ws.root, m_cap * 4);
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
-  LAUNCH(k_cg_union, nb, 256, 0, d_m, m_cap, d_ds, ctx->g, d_segbits, d_segoff, ws.parent.as<int>());
+  LAUNCH(k_cg_union, vf_blocks(ctx, m_cap * 4, 256, 8), 256, 0, d_m, m_cap, d_ds, ctx->g, d_segbits, d_segoff, ws.parent.as<int>());
   LAUNCH(k_cl_roots, nb, 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
   LAUNCH(k_cl_flatten, nb, 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;

@@ -218,15 +218,19 @@ __global__ void k_bg_state(unsigned long long* __restrict__ counters, const unsi
     counters[CNT_STATE_BG] = 1ull;
 }
 
-// one WARP per point: the lanes stride over the <= (2*mv)^3 window cells of VoxelMap::hasCloseTo (voxel_map.cpp:376-400).
+// one WARP per point: the lanes stride over the <= (2*mv)^3 window cells of VoxelMap::hasCloseTo (voxel_map.cpp:376-400),
+// 8 independent loads per lane in flight (the default window, 6^3 cells, is one such batch: one memory round trip).
 // The per-point result goes to pt_hit; clusters are marked afterwards (a shared per-cluster flag polled and written from
 // here funnels every warp into one L2 sector once the ground cluster is background: measured 177 us instead of 10).
+// Second part (n_bg_out != NULL): nVoxelsOver(thr) of :712 over the raised (chunk, column) cells — the same threshold, the
+// same grid, no dependency between the two, so they share a launch.
 __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ score, const Geom g, const vofod_vox* __restrict__ vox,
                                                       const unsigned long long* __restrict__ d_m, const size_t m_cap, const float max_dist, const float thr,
-                                                      uint8_t* __restrict__ pt_hit, int* __restrict__ cl_close)
+                                                      uint8_t* __restrict__ pt_hit, int* __restrict__ cl_close, const uint8_t* __restrict__ dirty,
+                                                      unsigned long long* __restrict__ n_bg_out)
 {
   pdl_enter();
-  const size_t m = prims::dev_count(d_m, m_cap);
+  const size_t m = vox ? prims::dev_count(d_m, m_cap) : 0;
   const unsigned lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -253,22 +257,32 @@ __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ 
     if (nx > 0 && ny > 0 && nz > 0)
     {
       const int total = nx * ny * nz;
-      for (int base = 0; base < total && !hit; base += 32)
+      for (int base = 0; base < total && !hit; base += 32 * 8)
       {
-        const int t = base + (int)lane;
-        bool h = false;
-        if (t < total)
+        float val[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
         {
-          const int xi = bx + t % nx, yi = by + (t / nx) % ny, zi = bz + t / (nx * ny);
-          const long long ci = cell_index(g, xi, yi, zi);
-          if (ci >= 0 && score[ci] > thr)
+          const int t = base + q * 32 + (int)lane;
+          val[q] = __int_as_float(0xff800000);
+          if (t < total)
           {
-            const int ddx = xi - ox, ddy = yi - oy, ddz = zi - oz;
-            // Eigen int-vector norm(): int(sqrt(d2)) <= md; the integer square root of d2 <= 3*mv^2 is exact in fp32 too
-            const int nrm = (int)sqrtf((float)(ddx * ddx + ddy * ddy + ddz * ddz));
-            h = (float)nrm <= md;
+            const long long ci = cell_index(g, bx + t % nx, by + (t / nx) % ny, bz + t / (nx * ny));
+            if (ci >= 0)
+              val[q] = score[ci];
           }
         }
+        bool h = false;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (val[q] > thr)
+          {
+            const int t = base + q * 32 + (int)lane;
+            const int ddx = bx + t % nx - ox, ddy = by + (t / nx) % ny - oy, ddz = bz + t / (nx * ny) - oz;
+            // Eigen int-vector norm(): int(sqrt(d2)) <= md; the integer square root of d2 <= 3*mv^2 is exact in fp32 too
+            const int nrm = (int)sqrtf((float)(ddx * ddx + ddy * ddy + ddz * ddz));
+            h = h || (float)nrm <= md;
+          }
         hit = __any_sync(VOFOD_FULL, h);
       }
     }
@@ -278,12 +292,44 @@ __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ 
       cl_close[i] = 0;  // per-cluster flags (indexed by label < m): cleared here, set by k_close_mark
     }
   }
+  if (!n_bg_out)
+    return;
+  // nVoxelsOver: one thread per (chunk of DIRTY_ZC levels, column), column fastest (coalesced marks and scores)
+  const size_t ncol = (size_t)g.st_size[0] * g.st_size[1];
+  const size_t n_items = ncol * (size_t)dirty_chunks(g);
+  unsigned cnt = 0;
+  for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (size_t)gridDim.x * blockDim.x)
+  {
+    if (dirty && !dirty[it])
+      continue;
+    const size_t c = it % ncol;
+    const int zc = (int)(it / ncol);
+    if (!column_owned(g, (int)(c % g.st_size[0]), (int)(c / g.st_size[0])))
+      continue;
+    const int z_lo = zc * DIRTY_ZC, z_hi = min(z_lo + DIRTY_ZC, g.st_size[2]);
+    for (int z0 = z_lo; z0 < z_hi; z0 += 16)
+    {
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        v[k] = (z0 + k < z_hi) ? score[c + (size_t)(z0 + k) * ncol] : __int_as_float(0xff800000);
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        cnt += v[k] > thr;
+    }
+  }
+  cnt = prims::warp_sum(cnt);
+  if (lane == 0 && cnt)
+    atomicAdd(n_bg_out, (unsigned long long)cnt);
 }
 // a cluster is close iff ANY of its points is (:730-741)
+// (+ the background-sufficient latch of :716-721 when `counters` is given: the count it reads was finished a kernel ago)
 __global__ void __launch_bounds__(256) k_close_mark(const uint8_t* __restrict__ pt_hit, const int* __restrict__ labels, const unsigned long long* __restrict__ d_m,
-                                                    const size_t m_cap, int* __restrict__ cl_close)
+                                                    const size_t m_cap, int* __restrict__ cl_close, unsigned long long* counters, const unsigned long long min_sufficient)
 {
   pdl_enter();
+  if (counters && blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_NBG] > min_sufficient)
+    counters[CNT_STATE_BG] = 1ull;
   const size_t m = prims::dev_count(d_m, m_cap);
   const unsigned lane = threadIdx.x & 31;
   for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < m; i0 += (size_t)gridDim.x * blockDim.x)
@@ -335,35 +381,45 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
 {
   const float max_dist = (float)p.ground_points_max_distance;
   const float thr = (float)p.thr_new_obstacles;
+  // vofod_nodelet.cpp:229-230 (fp32, left to right), converted to uint64_t
+  const float vs = ctx->cfg_voxel_size > 0.f ? ctx->cfg_voxel_size : ctx->g.vs;
+  volatile float a0 = p.oparea_size[0] / vs;
+  volatile float a1 = a0 * p.oparea_size[1];
+  volatile float a2 = a1 / vs;
+  volatile float a3 = a2 * p.background_sufficient_points_ratio;
+  const unsigned long long min_sufficient = (unsigned long long)a3;
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  bool state_done = false;
   if (phase != 2)
   {
-    RET(vf_count_over_dev(ctx, thr, vf_cnt(ctx, CNT_NBG), &p));
     if (m_cap)
     {
+      // :712 nVoxelsOver rides in the hasCloseTo kernel
       ENSURE(ctx->cl_close, m_cap * 4);
       ENSURE(ctx->pt_close, m_cap + 64);
-      LAUNCH(k_close_points, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
-             ctx->cl_close.as<int>());
-      LAUNCH(k_close_mark, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->pt_close.as<uint8_t>(), d_labels, d_m, m_cap, ctx->cl_close.as<int>());
-    }
+      if (!ctx->scan_prezero)
+        CK(cudaMemsetAsync(cnt + CNT_NBG, 0, sizeof(unsigned long long), ctx->stream));
+      const size_t items = (size_t)ctx->g.st_size[0] * ctx->g.st_size[1] * dirty_chunks(ctx->g);
+      const size_t work = m_cap * 32 > items ? m_cap * 32 : items;
+      LAUNCH(k_close_points, vf_blocks(ctx, work, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
+             ctx->cl_close.as<int>(), vf_dirty_cols(ctx, thr, &p), cnt + CNT_NBG);
+      state_done = phase == 0;  // unsharded: the count is final, the latch can ride in the next kernel
+      LAUNCH(k_close_mark, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->pt_close.as<uint8_t>(), d_labels, d_m, m_cap, ctx->cl_close.as<int>(),
+             state_done ? cnt : nullptr, min_sufficient);
+    } else
+      RET(vf_count_over_dev(ctx, thr, cnt + CNT_NBG, &p));
   }
   if (phase != 1)
   {
-    // vofod_nodelet.cpp:229-230 (fp32, left to right), converted to uint64_t
-    const float vs = ctx->cfg_voxel_size > 0.f ? ctx->cfg_voxel_size : ctx->g.vs;
-    volatile float a0 = p.oparea_size[0] / vs;
-    volatile float a1 = a0 * p.oparea_size[1];
-    volatile float a2 = a1 / vs;
-    volatile float a3 = a2 * p.background_sufficient_points_ratio;
-    const unsigned long long min_sufficient = (unsigned long long)a3;
-    LAUNCH(k_bg_state, 1, 1, 0, ctx->d_counters.as<unsigned long long>(), min_sufficient);
+    if (!state_done)
+      LAUNCH(k_bg_state, 1, 1, 0, cnt, min_sufficient);
     ZERO_CNT(CNT_NCLOSE, 2);  // NCLOSE, NFAR
     if (m_cap)
     {
       if (claim_for_update)
         RET(vf_update_owner(ctx));
-      LAUNCH(k_close_finish, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_labels, d_m, m_cap, ctx->cl_close.as<int>(), ctx->pt_close.as<uint8_t>(),
-             ctx->d_counters.as<unsigned long long>(), ctx->g, d_vox, claim_for_update ? ctx->upd_owner.as<unsigned>() : nullptr);
+      LAUNCH(k_close_finish, vf_blocks(ctx, m_cap, 256, 8), 256, 0, d_labels, d_m, m_cap, ctx->cl_close.as<int>(), ctx->pt_close.as<uint8_t>(), cnt, ctx->g, d_vox,
+             claim_for_update ? ctx->upd_owner.as<unsigned>() : nullptr);
     }
   }
   return 0;

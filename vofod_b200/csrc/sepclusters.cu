@@ -252,7 +252,8 @@ __global__ void k_sep_state(unsigned long long* __restrict__ counters, const uns
   sep_state(counters, k_cap);
 }
 
-// K12 — :1244-1272
+// K12 — :1244-1272.  One warp per 32 voxels: the cluster test is one coalesced pass; the (few) voxels of unsure clusters then
+// get the whole warp, one lane per offset.
 __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, const vofod_vox* __restrict__ ds, const int* __restrict__ labels,
                                                    const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
                                                    const int3* __restrict__ offsets, const int n_off, const unsigned min_sure, const float w1, const float w2,
@@ -264,31 +265,38 @@ __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, c
   if (counters[CNT_SEP_ANY_SURE] == 0ull || counters[CNT_SEP_K] > k_cap)
     return;  // :1192-1199 (and: list overflow => nothing is touched, the host redoes the pass with a larger list)
   const size_t k = prims::dev_count(d_k, cap);
-  const size_t total = k * (size_t)n_off;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < k; i0 += (size_t)gridDim.x * blockDim.x)
   {
-    const size_t i = t / n_off;
-    const int o = (int)(t - i * n_off);
-    if (!((unsigned)nsure[labels[i]] < min_sure))  // only the unsure clusters (:1246)
-      continue;
-    const vofod_vox v = ds[i];
-    const int3 of = offsets[o];
-    const int x = (int)v.x + of.x, y = (int)v.y + of.y, z = (int)v.z + of.z;  // cast<int>() truncation (:1252)
-    if (!in_limits_idx(g, x, y, z))
-      continue;
-    const long long ci = cell_index(g, x, y, z);
-    if (ci < 0)
-      continue;
-    unsigned* addr = reinterpret_cast<unsigned*>(score + ci);
-    unsigned old = *addr;
-    while (true)
+    const size_t i = i0 + lane;
+    const bool unsure = i < k && (unsigned)nsure[labels[i]] < min_sure;  // only the unsure clusters (:1246)
+    unsigned todo = __ballot_sync(VOFOD_FULL, unsure);
+    while (todo)
     {
-      const float m = __uint_as_float(old);
-      const float nv = w1 * m + w2 * update_val;  // :1259
-      const unsigned prev = atomicCAS(addr, old, __float_as_uint(nv));
-      if (prev == old)
-        break;
-      old = prev;
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const vofod_vox v = ds[i0 + src];
+      for (int o = (int)lane; o < n_off; o += 32)
+      {
+        const int3 of = offsets[o];
+        const int x = (int)v.x + of.x, y = (int)v.y + of.y, z = (int)v.z + of.z;  // cast<int>() truncation (:1252)
+        if (!in_limits_idx(g, x, y, z))
+          continue;
+        const long long ci = cell_index(g, x, y, z);
+        if (ci < 0)
+          continue;
+        unsigned* addr = reinterpret_cast<unsigned*>(score + ci);
+        unsigned old = *addr;
+        while (true)
+        {
+          const float mval = __uint_as_float(old);
+          const float nv = w1 * mval + w2 * update_val;  // :1259
+          const unsigned prev = atomicCAS(addr, old, __float_as_uint(nv));
+          if (prev == old)
+            break;
+          old = prev;
+        }
+      }
     }
   }
 }
@@ -414,7 +422,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);
   volatile float w2v = 1.0f - w1;
   const float w2 = w2v;
-  LAUNCH(k_sep_decay, vf_blocks(ctx, K * n_off, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(),
+  LAUNCH(k_sep_decay, vf_blocks(ctx, K, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(),
          ctx->sep_nsure.as<int>(), d_kds, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt, cap_guard);
   return VOFOD_OK;
 }

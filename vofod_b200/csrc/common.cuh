@@ -277,7 +277,7 @@ struct vofod_ctx
   // voxel-grid workspace
   DevBuf vg_pts;    // float4 per input point (x,y,z,valid/intensity)
   DevBuf vg_keys_a, vg_keys_b;
-  DevBuf vgh_cnt, vgh_bits, vgh_off;  // sort-free scan-path voxel grid: dense per-leaf counts, occupancy words, their popcount scan
+  DevBuf vgh_cnt, vgh_bits, vgh_list;  // sort-free scan-path voxel grid: dense per-leaf counts, occupancy words, their popcount scan
   bool vg_force_sort = false;         // test switch: the scan path uses the generic sort-based voxel grid
   DevBuf vg_flags, vg_scan, vg_ustart, vg_ukey, vg_pref;
   DevBuf vox;       // vofod_vox per output voxel (cloud_weighted of the last scan)
@@ -330,7 +330,7 @@ struct vofod_ctx
   size_t last_m = 0, last_far = 0;
 
   // sepclusters workspace
-  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff, sep_live;
+  DevBuf sep_colcnt, sep_coloff, sep_raw, sep_ds, sep_labels, sep_nsure, sep_offsets, sep_segcnt, sep_segoff, sep_live, sep_unsure;
   bool sep_force_general = false;  // test switch: never take the leaf-size-1 fast path
   int sep_off_n = -1, sep_off_mv = 0;
   float sep_off_md = 0.f;
@@ -388,6 +388,8 @@ enum
   CNT_SEP_LIVE,       // length of the sepclusters work list
   CNT_UPD_LEFT,       // k_update_points: left-over list length / block ticket (both return to 0 at the end of the kernel)
   CNT_UPD_TICKET,
+  CNT_VGH_LIST,       // non-empty occupancy words listed by the scan
+  CNT_SEP_NUNSURE,    // voxels of unsure clusters listed for the decay
   CNT_VGH_WORDS,      // occupancy words of the scan-path voxel grid (depends on the cloud's bounding box)
   // ---- persistent slots (never zeroed by a map resize) ----
   CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube

@@ -177,6 +177,9 @@ struct ScanJob
   unsigned long long* state;
   unsigned long long* total;
   int popc;
+  // optional: every non-zero element is appended (in no particular order) as (index, raw value, exclusive prefix, 0)
+  uint4* list;
+  unsigned long long* list_n;
 };
 struct ScanJobs
 {
@@ -217,10 +220,15 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
       const uint4 a = *reinterpret_cast<const uint4*>(in + base_i + 4 * q);
       v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
     }
+    uint32_t raw_nz = 0;  // which of this thread's elements are non-zero
+    uint32_t raw[SIPT];
     uint32_t tsum = 0;
 #pragma unroll
     for (int k = 0; k < SIPT; k++)
     {
+      raw[k] = v[k];
+      if (v[k] != 0u && base_i + k < n)
+        raw_nz |= 1u << k;
       if (J.popc)
         v[k] = (uint32_t)__popc(v[k]);
       if (base_i + k >= n)
@@ -241,6 +249,18 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
     }
     __syncthreads();
     uint32_t run = s_base + texcl;
+    if (J.list && raw_nz)
+    {
+      unsigned long long at = atomicAdd(J.list_n, (unsigned long long)__popc(raw_nz));
+      uint32_t r2 = run;
+#pragma unroll
+      for (int k = 0; k < SIPT; k++)
+      {
+        if ((raw_nz >> k) & 1u)
+          J.list[at++] = make_uint4((uint32_t)(base_i + k), raw[k], r2, 0u);
+        r2 += v[k];
+      }
+    }
 #pragma unroll
     for (int q = 0; q < SIPT / 4; q++)
     {
@@ -249,7 +269,8 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
       o.y = run; run += v[4 * q + 1];
       o.z = run; run += v[4 * q + 2];
       o.w = run; run += v[4 * q + 3];
-      *reinterpret_cast<uint4*>(out + base_i + 4 * q) = o;
+      if (out)  // (a caller that only wants the list and the total passes NULL)
+        *reinterpret_cast<uint4*>(out + base_i + 4 * q) = o;
     }
     __syncthreads();
   }
@@ -415,20 +436,21 @@ static inline int scan_grid(const vofod_ctx* c, const size_t cap_items)
 }
 // Two independent scans in one launch.  `b_*` may be all-null for a single scan.  Scan B uses ctx->tile_state2.
 static inline int scan_excl_u32_pair(vofod_ctx* ctx, const uint32_t* a_in, uint32_t* a_out, const unsigned long long* a_dn, const size_t a_cap, unsigned long long* a_total,
-                                     const bool a_popc, const uint32_t* b_in, uint32_t* b_out, const size_t b_cap, unsigned long long* b_total, const bool b_popc)
+                                     const bool a_popc, const uint32_t* b_in, uint32_t* b_out, const size_t b_cap, unsigned long long* b_total, const bool b_popc,
+                                     uint4* a_list = nullptr, unsigned long long* a_list_n = nullptr)
 {
   const size_t a_tiles = (a_cap + TILE - 1) / TILE + 1;
   ENSURE(ctx->tile_state, a_tiles * 256 * sizeof(unsigned long long));
   ScanJobs jobs;
-  jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0};
-  jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
+  jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0, a_list, a_list_n};
+  jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr};
   const bool big = (a_cap > b_cap ? a_cap : b_cap) >= (size_t(1) << 18);
   int gx = big ? scan_grid<SCAN_BIG_IPT>(ctx, a_cap) : scan_grid<IPT>(ctx, a_cap), gy = 1;
   if (b_in)
   {
     const size_t b_tiles = (b_cap + TILE - 1) / TILE + 1;
     ENSURE(ctx->tile_state2, b_tiles * sizeof(unsigned long long));
-    jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0};
+    jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0, nullptr, nullptr};
     const int gb = big ? scan_grid<SCAN_BIG_IPT>(ctx, b_cap) : scan_grid<IPT>(ctx, b_cap);
     gx = gx > gb ? gx : gb;
     gy = 2;

@@ -226,16 +226,22 @@ __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__
       atomicAdd(reinterpret_cast<unsigned*>(nsure) + l, sum);
   }
 }
-// :1186-1206
+// :1186-1206 — is any cluster sure?  + the list of the voxels of UNSURE clusters (normally a handful) for the decay
 __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels, const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
-                                                 const unsigned min_sure, unsigned long long* __restrict__ counters)
+                                                 const unsigned min_sure, unsigned long long* __restrict__ counters, uint32_t* __restrict__ unsure)
 {
   pdl_enter();
   const size_t k = prims::dev_count(d_k, cap);
   bool any = false;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
-    if (labels[i] == (int)i && (unsigned long long)(long long)nsure[i] >= (unsigned long long)min_sure)  // size_t(int) >= unsigned
+  {
+    const int l = labels[i];
+    const int ns = nsure[l];
+    if (l == (int)i && (unsigned long long)(long long)ns >= (unsigned long long)min_sure)  // size_t(int) >= unsigned
       any = true;
+    if ((unsigned)ns < min_sure)  // :1246
+      unsure[atomicAdd(counters + CNT_SEP_NUNSURE, 1ull)] = (uint32_t)i;
+  }
   if (__any_sync(VOFOD_FULL, any) && (threadIdx.x & 31) == 0)
     counters[CNT_SEP_ANY_SURE] = 1ull;
 }
@@ -252,11 +258,9 @@ __global__ void k_sep_state(unsigned long long* __restrict__ counters, const uns
   sep_state(counters, k_cap);
 }
 
-// K12 — :1244-1272.  One warp per 32 voxels: the cluster test is one coalesced pass; the (few) voxels of unsure clusters then
-// get the whole warp, one lane per offset.
-__global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, const vofod_vox* __restrict__ ds, const int* __restrict__ labels,
-                                                   const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
-                                                   const int3* __restrict__ offsets, const int n_off, const unsigned min_sure, const float w1, const float w2,
+// K12 — :1244-1272: one thread per (listed voxel, offset)
+__global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, const vofod_vox* __restrict__ ds, const uint32_t* __restrict__ unsure,
+                                                   const size_t cap, const int3* __restrict__ offsets, const int n_off, const float w1, const float w2,
                                                    const float update_val, unsigned long long* counters, const unsigned long long k_cap)
 {
   pdl_enter();
@@ -264,39 +268,30 @@ __global__ void __launch_bounds__(256) k_sep_decay(float* score, const Geom g, c
     sep_state(counters, k_cap);
   if (counters[CNT_SEP_ANY_SURE] == 0ull || counters[CNT_SEP_K] > k_cap)
     return;  // :1192-1199 (and: list overflow => nothing is touched, the host redoes the pass with a larger list)
-  const size_t k = prims::dev_count(d_k, cap);
-  const unsigned lane = threadIdx.x & 31;
-  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < k; i0 += (size_t)gridDim.x * blockDim.x)
+  const size_t n_list = prims::dev_count(counters + CNT_SEP_NUNSURE, cap);
+  const size_t total = n_list * (size_t)n_off;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
   {
-    const size_t i = i0 + lane;
-    const bool unsure = i < k && (unsigned)nsure[labels[i]] < min_sure;  // only the unsure clusters (:1246)
-    unsigned todo = __ballot_sync(VOFOD_FULL, unsure);
-    while (todo)
+    const size_t e = t / n_off;
+    const int o = (int)(t - e * n_off);
+    const vofod_vox v = ds[unsure[e]];
+    const int3 of = offsets[o];
+    const int x = (int)v.x + of.x, y = (int)v.y + of.y, z = (int)v.z + of.z;  // cast<int>() truncation (:1252)
+    if (!in_limits_idx(g, x, y, z))
+      continue;
+    const long long ci = cell_index(g, x, y, z);
+    if (ci < 0)
+      continue;
+    unsigned* addr = reinterpret_cast<unsigned*>(score + ci);
+    unsigned old = *addr;
+    while (true)
     {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const vofod_vox v = ds[i0 + src];
-      for (int o = (int)lane; o < n_off; o += 32)
-      {
-        const int3 of = offsets[o];
-        const int x = (int)v.x + of.x, y = (int)v.y + of.y, z = (int)v.z + of.z;  // cast<int>() truncation (:1252)
-        if (!in_limits_idx(g, x, y, z))
-          continue;
-        const long long ci = cell_index(g, x, y, z);
-        if (ci < 0)
-          continue;
-        unsigned* addr = reinterpret_cast<unsigned*>(score + ci);
-        unsigned old = *addr;
-        while (true)
-        {
-          const float mval = __uint_as_float(old);
-          const float nv = w1 * mval + w2 * update_val;  // :1259
-          const unsigned prev = atomicCAS(addr, old, __float_as_uint(nv));
-          if (prev == old)
-            break;
-          old = prev;
-        }
-      }
+      const float mval = __uint_as_float(old);
+      const float nv = w1 * mval + w2 * update_val;  // :1259
+      const unsigned prev = atomicCAS(addr, old, __float_as_uint(nv));
+      if (prev == old)
+        break;
+      old = prev;
     }
   }
 }
@@ -390,7 +385,9 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   const int nb = vf_blocks(ctx, K, 256, 8);
   LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), fast ? ctx->vg_flags.as<uint32_t>() : nullptr, ctx->sep_labels.as<int>(), d_kds, K,
          ctx->sep_nsure.as<int>());
-  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt);
+  ENSURE(ctx->sep_unsure, K * 4);
+  ZERO_CNT(CNT_SEP_NUNSURE, 1);
+  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt, ctx->sep_unsure.as<uint32_t>());
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)
   if (ctx->sep_off_n < 0 || ctx->sep_off_mv != mv || ctx->sep_off_md != max_dist_idx)
   {
@@ -422,8 +419,9 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);
   volatile float w2v = 1.0f - w1;
   const float w2 = w2v;
-  LAUNCH(k_sep_decay, vf_blocks(ctx, K, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(), ctx->sep_labels.as<int>(),
-         ctx->sep_nsure.as<int>(), d_kds, K, ctx->sep_offsets.as<int3>(), (int)n_off, min_sure, w1, w2, (float)p.score_ray, cnt, cap_guard);
+  // sized for a few thousand listed voxels per wave; the kernel strides over whatever the list holds
+  LAUNCH(k_sep_decay, vf_blocks(ctx, (K < 8192 ? K : 8192) * n_off, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ctx->sep_ds.as<vofod_vox>(),
+         ctx->sep_unsure.as<uint32_t>(), K, ctx->sep_offsets.as<int3>(), (int)n_off, w1, w2, (float)p.score_ray, cnt, cap_guard);
   return VOFOD_OK;
 }
 

@@ -302,73 +302,39 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
     }
   }
 }
-// one warp per 32 consecutive occupancy words; the non-empty ones are handled VGH_ROUND at a time, lane = bit
-#define VGH_ROUND 8
-__global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ Lp, const unsigned long long* __restrict__ d_words, const size_t words_cap,
-                                                  uint32_t* __restrict__ bits, const uint32_t* __restrict__ off, uint32_t* __restrict__ cnt, vofod_vox* __restrict__ out,
+// one warp per NON-EMPTY occupancy word (listed by the scan together with its rank offset), lane = bit
+__global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ Lp, const uint4* __restrict__ list, const unsigned long long* __restrict__ d_list_n,
+                                                  const size_t list_cap, uint32_t* __restrict__ bits, uint32_t* __restrict__ cnt, vofod_vox* __restrict__ out,
                                                   const size_t out_cap)
 {
   pdl_enter();
   const VgLayout L = *after_wait(Lp);
-  const size_t n_words = prims::dev_count(d_words, words_cap);
+  const size_t n_list = prims::dev_count(d_list_n, list_cap);
   const unsigned lane = threadIdx.x & 31;
   const uint32_t d0 = (uint32_t)L.div[0], d1 = (uint32_t)L.div[1], d01 = d0 * d1;
   const uint32_t nseg = (d0 + 31u) / 32u;
-  for (size_t w0 = (((size_t)blockIdx.x * 256 + threadIdx.x) >> 5) * 32; w0 < n_words; w0 += (((size_t)gridDim.x * 256) >> 5) * 32)
+  for (size_t e = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5; e < n_list; e += ((size_t)gridDim.x * 256) >> 5)
   {
-    const size_t w = w0 + lane;
-    uint32_t my_bits = 0, my_off = 0;
-    if (w < n_words)
+    const uint4 ent = list[e];  // (word index, occupancy bits, rank of its first set bit)
+    const uint32_t w = ent.x, wb = ent.y;
+    if (lane == 0)
+      bits[w] = 0u;
+    if (!((wb >> lane) & 1u))
+      continue;
+    const uint32_t seg = w % nseg, row = w / nseg;
+    const uint32_t k0 = seg * 32u + lane, k1 = row % d1, k2 = row / d1;
+    const uint32_t key = k0 + k1 * d0 + k2 * d01;
+    const uint32_t c = cnt[key];
+    cnt[key] = 0u;
+    const size_t r = (size_t)ent.z + (size_t)__popc(wb & prims::lanemask_lt());
+    if (r < out_cap)
     {
-      my_bits = bits[w];
-      if (my_bits)
-      {
-        my_off = off[w];
-        bits[w] = 0u;
-      }
-    }
-    unsigned todo = __ballot_sync(VOFOD_FULL, my_bits != 0u);
-    while (todo)
-    {
-      // up to VGH_ROUND words per round: their count loads are independent and go out together
-      uint32_t key[VGH_ROUND], c[VGH_ROUND], r[VGH_ROUND];
-      bool on[VGH_ROUND];
-#pragma unroll
-      for (int q = 0; q < VGH_ROUND; q++)
-      {
-        on[q] = false;
-        if (!todo)
-          continue;
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t wb = __shfl_sync(VOFOD_FULL, my_bits, src);
-        const uint32_t wo = __shfl_sync(VOFOD_FULL, my_off, src);
-        const size_t ww = w0 + (size_t)src;
-        const uint32_t seg = (uint32_t)(ww % nseg), row = (uint32_t)(ww / nseg);
-        const uint32_t k1 = row % d1, k2 = row / d1;
-        on[q] = (wb >> lane) & 1u;
-        key[q] = (seg * 32u + lane) + k1 * d0 + k2 * d01;
-        r[q] = wo + (uint32_t)__popc(wb & prims::lanemask_lt());
-      }
-#pragma unroll
-      for (int q = 0; q < VGH_ROUND; q++)
-        c[q] = on[q] ? cnt[key[q]] : 0u;
-#pragma unroll
-      for (int q = 0; q < VGH_ROUND; q++)
-        if (on[q])
-        {
-          cnt[key[q]] = 0u;
-          if (r[q] < out_cap)
-          {
-            const uint32_t k2 = key[q] / d01, rem = key[q] - k2 * d01, k1 = rem / d0, k0 = rem - k1 * d0;
-            vofod_vox v;
-            v.x = ((float)(int)k0 + 0.5f) * L.leaf + L.offset[0];
-            v.y = ((float)(int)k1 + 0.5f) * L.leaf + L.offset[1];
-            v.z = ((float)(int)k2 + 0.5f) * L.leaf + L.offset[2];
-            v.count = c[q];
-            out[r[q]] = v;
-          }
-        }
+      vofod_vox o;
+      o.x = ((float)(int)k0 + 0.5f) * L.leaf + L.offset[0];
+      o.y = ((float)(int)k1 + 0.5f) * L.leaf + L.offset[1];
+      o.z = ((float)(int)k2 + 0.5f) * L.leaf + L.offset[2];
+      o.count = c;
+      out[r] = o;
     }
   }
 }
@@ -571,15 +537,18 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
     }
     ENSURE(ctx->vgh_cnt, (size_t)cells * 4);            // zero when (re)allocated, put back to zero by the emission pass
     ENSURE(ctx->vgh_bits, padded(words_cap) * 4);       // the same
-    ENSURE(ctx->vgh_off, padded(words_cap) * 4);
     ENSURE(ctx->vox, np * sizeof(vofod_vox));
     unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
     VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
     LAUNCH(k_vgh_count, vf_blocks(ctx, n, 256, 8), 256, 0, ctx->vg_pts.as<float4>(), mm, g.vs, ac[0], ac[1], ac[2], L, cnt, (int)CNT_VG_NVALID, (int)CNT_VG_OVERFLOW,
            cells, ctx->vgh_cnt.as<uint32_t>(), ctx->vgh_bits.as<uint32_t>());
-    RET(scan_excl_u32_pair(ctx, ctx->vgh_bits.as<uint32_t>(), ctx->vgh_off.as<uint32_t>(), cnt + CNT_VGH_WORDS, words_cap, cnt + CNT_VG_M, true, nullptr, nullptr, 0,
-                           nullptr, false));
-    LAUNCH(k_vgh_emit, vf_blocks(ctx, words_cap, 256, 8), 256, 0, L, cnt + CNT_VGH_WORDS, words_cap, ctx->vgh_bits.as<uint32_t>(), ctx->vgh_off.as<uint32_t>(),
+    // a word holds at least one of the n points
+    const size_t list_cap = n < words_cap ? n : words_cap;
+    ENSURE(ctx->vgh_list, (list_cap + 1) * sizeof(uint4));
+    ZERO_CNT(CNT_VGH_LIST, 1);
+    RET(scan_excl_u32_pair(ctx, ctx->vgh_bits.as<uint32_t>(), nullptr, cnt + CNT_VGH_WORDS, words_cap, cnt + CNT_VG_M, true, nullptr, nullptr, 0,
+                           nullptr, false, ctx->vgh_list.as<uint4>(), cnt + CNT_VGH_LIST));
+    LAUNCH(k_vgh_emit, vf_blocks(ctx, list_cap * 32, 256, 8), 256, 0, L, ctx->vgh_list.as<uint4>(), cnt + CNT_VGH_LIST, list_cap, ctx->vgh_bits.as<uint32_t>(),
            ctx->vgh_cnt.as<uint32_t>(), ctx->vox.as<vofod_vox>(), np);
     return 0;
   }

@@ -707,13 +707,19 @@ int vf_classify_prefill(vofod_ctx* ctx, size_t m_cap)
   return 0;
 }
 
+// phase 1: everything that only looks at the voxel list (far clusters, member lists, moments of inertia + gates);
+// phase 2: the sequential part that reads and writes the map (exploreToGround, detections); phase 0: both.
+// Inside a scan phase 1 runs on the side branch next to the point update and the ray apply.
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
-                           const vofod_params& p)
+                           const vofod_params& p, int phase)
 {
   using namespace prims;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  ZERO_CNT(CNT_NDET, 1);
-  ZERO_CNT(CNT_NFARPTS, 1);
+  if (phase != 2)
+  {
+    ZERO_CNT(CNT_NDET, 1);
+    ZERO_CNT(CNT_NFARPTS, 1);
+  }
   if (m_cap == 0)
     return 0;
   const size_t np = padded(m_cap);
@@ -729,31 +735,8 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   const int sub_side = (int)ceil(p.cls_max_size / vs) + 8;
   const size_t terms_cap = (size_t)sub_side * sub_side * sub_side;
 
-  ENSURE(ctx->far_list, np * 4);            // member lists
-  ENSURE(ctx->cls_sizes, m_cap * 4);
-  ENSURE(ctx->cls_maxidx, m_cap * 4);
-  ENSURE(ctx->cls_seg, m_cap * 4);
-  ENSURE(ctx->cls_okeys_a, np * 8);
-  ENSURE(ctx->cls_okeys_b, np * 8);
-  ENSURE(ctx->cl_info, m_cap * sizeof(vofod_cluster_info));
-  ENSURE(ctx->dets, (size_t)MAX_DETS * sizeof(vofod_detection));
-  ENSURE(ctx->explore_ws, cube * 4);          // stamps: zero-filled when (re)allocated
-  ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
-  ENSURE(ctx->cls_terms, terms_cap * 8);
-  if (ctx->cls_prefilled != m_cap)
-    RET(vf_classify_prefill(ctx, m_cap));
-  ctx->cls_prefilled = 0;
-  ZERO_CNT(CNT_CLS_CURSOR, 1);
-
-  const int nb = vf_blocks(ctx, m_cap, 256, 8);
-  LAUNCH(k_cls_mark, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>());
-  LAUNCH(k_cls_roots, nb, 256, 0, d_labels, d_in_close, ctx->cls_sizes.as<int>(), d_m, m_cap, bits, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS);
-  const int nbw = vf_blocks(ctx, m_cap * 32, 256, 4);
-  LAUNCH(k_cls_rank, nbw, 256, 0, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS, ctx->cls_okeys_b.as<unsigned long long>());
   const unsigned long long* okeys = ctx->cls_okeys_b.as<unsigned long long>();
   uint32_t* sidx = ctx->far_list.as<uint32_t>();
-  LAUNCH(k_cls_members, nbw, 256, 0, d_labels, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>(), okeys, cnt + CNT_NFARPTS, bits, sidx, ctx->cls_seg.as<int>(),
-         cnt + CNT_CLS_CURSOR);
   ClsArgs a;
   a.g = ctx->g;
   a.min_points = p.cls_min_points;
@@ -780,8 +763,38 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
     if (a.n_exact < 64)
       a.n_exact = 64;
   }
+  if (phase != 2)
+  {
+  ENSURE(ctx->far_list, np * 4);            // member lists
+  ENSURE(ctx->cls_sizes, m_cap * 4);
+  ENSURE(ctx->cls_maxidx, m_cap * 4);
+  ENSURE(ctx->cls_seg, m_cap * 4);
+  ENSURE(ctx->cls_okeys_a, np * 8);
+  ENSURE(ctx->cls_okeys_b, np * 8);
+  ENSURE(ctx->cl_info, m_cap * sizeof(vofod_cluster_info));
+  ENSURE(ctx->dets, (size_t)MAX_DETS * sizeof(vofod_detection));
+  ENSURE(ctx->explore_ws, cube * 4);          // stamps: zero-filled when (re)allocated
+  ENSURE(ctx->cls_queues, cube * 4 * 3);      // q0, q1, explored
+  ENSURE(ctx->cls_terms, terms_cap * 8);
+  if (ctx->cls_prefilled != m_cap)
+    RET(vf_classify_prefill(ctx, m_cap));
+  ctx->cls_prefilled = 0;
+  ZERO_CNT(CNT_CLS_CURSOR, 1);
+
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  LAUNCH(k_cls_mark, nb, 256, 0, d_labels, d_in_close, d_m, m_cap, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>());
+  LAUNCH(k_cls_roots, nb, 256, 0, d_labels, d_in_close, ctx->cls_sizes.as<int>(), d_m, m_cap, bits, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS);
+  const int nbw = vf_blocks(ctx, m_cap * 32, 256, 4);
+  LAUNCH(k_cls_rank, nbw, 256, 0, ctx->cls_okeys_a.as<unsigned long long>(), cnt + CNT_NFARPTS, ctx->cls_okeys_b.as<unsigned long long>());
+  okeys = ctx->cls_okeys_b.as<unsigned long long>();
+  sidx = ctx->far_list.as<uint32_t>();
+  LAUNCH(k_cls_members, nbw, 256, 0, d_labels, ctx->cls_sizes.as<int>(), ctx->cls_maxidx.as<int>(), okeys, cnt + CNT_NFARPTS, bits, sidx, ctx->cls_seg.as<int>(),
+         cnt + CNT_CLS_CURSOR);
   LAUNCH(k_cluster_moi, vf_blocks(ctx, m_cap * 32, 256, 4), 256, 0, a, ctx->dyn.as<ScanDyn>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cls_sizes.as<int>(), okeys, cnt + CNT_NFARPTS,
          ctx->cl_info.as<vofod_cluster_info>());
+  }
+  if (phase == 1)
+    return 0;
   int* qbase = ctx->cls_queues.as<int>();
   ExploreWs w;
   w.stamps = ctx->explore_ws.as<unsigned>();

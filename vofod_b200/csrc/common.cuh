@@ -221,7 +221,7 @@ struct vofod_ctx
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // side branch for work that is independent of the main chain (raycast accumulate, second scan)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr, ev_fork2 = nullptr, ev_cls = nullptr;
   size_t cls_prefilled = 0;     // classification work arrays cleared ahead of time for this many points
   size_t sep_prefilled = 0;     // sepclusters fast-path count arrays cleared ahead of time (= their total length)
   std::string err;
@@ -505,6 +505,6 @@ int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, cons
 const uint8_t* vf_dirty_cols(vofod_ctx* ctx, float thr, const vofod_params* p);  // NULL = every column must be read
 // classify.cu
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
-                           const vofod_params& p);  // sensor position comes from ctx->dyn
+                           const vofod_params& p, int phase = 0);  // sensor position comes from ctx->dyn
 // sepclusters.cu
 int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap = 0);

@@ -99,6 +99,8 @@ int vofod_create(int device, vofod_ctx** out)
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fills, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_cls, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
     cudaEventCreate(&ctx->ev[i]);
   ctx->ev_ok = true;
@@ -170,6 +172,10 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_fills)
     cudaEventDestroy(ctx->ev_fills);
+  if (ctx->ev_fork2)
+    cudaEventDestroy(ctx->ev_fork2);
+  if (ctx->ev_cls)
+    cudaEventDestroy(ctx->ev_cls);
   if (ctx->stream2)
     cudaStreamDestroy(ctx->stream2);
   for (int i = 0; i < 2; i++)

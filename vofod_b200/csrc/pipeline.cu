@@ -638,6 +638,19 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   // findCloseFarClusters (:936)
   RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p, true));
   STAGE_EVENT();  // 3 "close X far"
+  // classifyClusters, the part that only looks at the voxel list: on the side branch, next to the point update and the ray apply
+  const bool cls_side = side && s.do_classify;
+  if (cls_side)
+  {
+    CK(cudaEventRecord(ctx->ev_fork2, st));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork2, 0));
+    ctx->stream = ctx->stream2;
+    const int crc = vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p, 1);
+    ctx->stream = st;
+    if (crc < 0)
+      return crc;
+    CK(cudaEventRecord(ctx->ev_cls, ctx->stream2));
+  }
   // updateVMaps (:946-949)
   RET(vf_update_points_scan_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 4 "vmap update"
@@ -669,7 +682,11 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   }
   STAGE_EVENT();  // 6 raycast "vmap update"
   ZERO_CNT(CNT_NDET, 1);
-  if (s.do_classify)
+  if (cls_side)
+  {
+    CK(cudaStreamWaitEvent(st, ctx->ev_cls, 0));
+    RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p, 2));
+  } else if (s.do_classify)
     RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 7 "classification" (+ 8 detections, fused)
   STAGE_EVENT();

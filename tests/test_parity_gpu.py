@@ -340,6 +340,21 @@ def test_scan_path_voxel_grid_sort_based_variant(gpu, cpu):
         gpu.set_option(abi.OPT_VG_SORT, 0)
 
 
+def test_scan_path_clustering_spatial_hash_variant(gpu, cpu):
+    """The scan normally clusters its voxel list as connected components on the occupancy grid; the generic spatial-hash
+    Euclidean clustering must give the same scans (also with the operation area off the voxel raster, where pairs at exactly
+    the tolerance are decided by fp32 rounding)."""
+    sensor = Sensor(512, 32)
+    gpu.set_option(abi.OPT_CLUSTER_HASH, 1)
+    try:
+        for off in ((0.0, 0.0, -1.25), (0.13, 0.21, -1.25)):
+            p = params_for((80.0, 80.0, 30.0), offset_xyz=off)
+            p.background_sufficient_points_ratio = 0.02
+            _run_sequence(gpu, cpu, sensor, p, 0.5, 0, range(0, 8), fixed=True)
+    finally:
+        gpu.set_option(abi.OPT_CLUSTER_HASH, 0)
+
+
 def test_sepclusters_general_path_and_leaf2(gpu, cpu):
     """The separated-background-cluster pass outside its leaf-size-1 fast path: forced general path (compaction ->
     VoxelGridCounted radix sort), and max_bg_distance 1.2 m (ceil(2.4) = 3 -> leaf size 2, 125-offset ball)."""

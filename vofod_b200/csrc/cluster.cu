@@ -473,6 +473,185 @@ int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The scan's own clustering (clusterCloud of the voxel-grid output, :932).  Its points are the CENTRES of the occupied
+// leaves of a grid, (ijk + 0.5) * leaf + offset, so whether two of them are within the tolerance is a property of their
+// index offset: n = dx^2+dy^2+dz^2 with n*leaf^2 clearly below tol^2 is always inside, clearly above never, and only when
+// n*leaf^2 EQUALS tol^2 (n = 9 for 1.5 m / 0.5 m) the fp32 rounding of the two centres decides — for exactly those pairs
+// the reference's fp32 distance is evaluated, on centres recomputed bit-identically from the indices.
+// The points of a run of consecutive occupied x hang under the run's first point (seeded by the voxel-grid emission
+// pass); one thread per (point, forward row) — only run heads work — unites the run with every run of that row inside the
+// window the row allows.  Occupancy comes from RunWord entries tagged with the API call number (no clearing).
+// ---------------------------------------------------------------------------------------------------------------
+bool vf_run_rows(const float tol, const float leaf, RunRows& rr)
+{
+  rr.n = 0;
+  if (!(tol > 0.0f) || !(leaf > 0.0f) || !(tol > leaf))
+    return false;
+  const double r2 = (double)(float)((double)tol * (double)tol);
+  const double l2 = (double)leaf * (double)leaf;
+  auto cls = [&](const long long n) {  // 0 inside, 1 border (decided in fp32), 2 outside
+    const double v = (double)n * l2;
+    if (fabs(v - r2) <= 1e-4 * r2)
+      return 1;
+    return v < r2 ? 0 : 2;
+  };
+  const int maxd = (int)ceil((double)tol / (double)leaf) + 1;
+  for (int dz = 0; dz <= maxd; dz++)
+    for (int dy = (dz == 0 ? 0 : -maxd); dy <= maxd; dy++)
+    {
+      const long long base = (long long)dy * dy + (long long)dz * dz;
+      const bool same = dy == 0 && dz == 0;
+      int R, shell;
+      if (!same && cls(base) == 2)
+        continue;
+      if (!same && cls(base) == 1)
+      {
+        if (cls(base + 1) != 2)
+          return false;
+        R = -1;
+        shell = 2;
+      } else
+      {
+        R = 0;
+        while (cls(base + (long long)(R + 1) * (R + 1)) == 0)
+          R++;
+        shell = cls(base + (long long)(R + 1) * (R + 1)) == 1 ? 1 : 0;
+        if (cls(base + (long long)(R + 2) * (R + 2)) != 2)
+          return false;
+        if (same && R == 0 && shell == 0)
+          return false;  // tol <= leaf: not a grid neighbourhood
+      }
+      if (R + 1 > 30 || rr.n >= RUN_ROWS_MAX)
+        return false;
+      rr.dy[rr.n] = (signed char)dy;
+      rr.dz[rr.n] = (signed char)dz;
+      rr.R[rr.n] = (signed char)R;
+      rr.shell[rr.n] = (signed char)shell;
+      rr.n++;
+    }
+  return rr.n > 0;
+}
+
+__global__ void __launch_bounds__(256) k_runs_union(const unsigned long long* __restrict__ d_m, const size_t m_cap, const uint32_t* __restrict__ cellkey,
+                                                    const RunWord* __restrict__ words, const VgLayout* __restrict__ Lp, const RunRows rows, const float r2,
+                                                    const unsigned long long* __restrict__ counters, int* __restrict__ parent)
+{
+  pdl_enter();
+  const size_t m = prims::dev_count(d_m, m_cap);
+  const VgLayout L = *after_wait(Lp);
+  const unsigned long long tag = *after_wait(counters + CNT_EPOCH_BASE);
+  const int d0 = L.div[0], d1 = L.div[1], d2 = L.div[2];
+  const uint32_t d01 = (uint32_t)d0 * (uint32_t)d1;
+  const int nseg = (d0 + 31) / 32;
+  const size_t total = m * (size_t)rows.n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+  {
+    const size_t i = t / rows.n;
+    const int q = (int)(t - i * rows.n);
+    const uint32_t key = cellkey[i];
+    const int k2 = (int)(key / d01), rem = (int)(key - (uint32_t)k2 * d01), k1 = rem / d0, k0 = rem - k1 * d0;
+    const int seg = k0 >> 5, b = k0 & 31;
+    const uint32_t own = words[((size_t)k2 * d1 + k1) * nseg + seg].bits;
+    if (b > 0 && ((own >> (b - 1)) & 1u))
+      continue;  // not the head of its run
+    const uint32_t up = ~(own >> b);
+    const int len = __ffs(up) ? __ffs(up) - 1 : 32;
+    const int x0 = k0, x1 = k0 + len - 1;
+    const int dy = rows.dy[q], dz = rows.dz[q], R = rows.R[q], shell = rows.shell[q];
+    const int ny = k1 + dy, nz = k2 + dz;
+    if (ny < 0 || ny >= d1 || nz >= d2)
+      continue;
+    const bool same = dy == 0 && dz == 0;
+    // window of candidate cells in the row, and its part that is inside for sure
+    int xa, xb, sa, sb;
+    if (same)
+    {
+      xa = x1 + 1, xb = x1 + R + (shell == 1 ? 1 : 0);
+      sa = x1 + 1, sb = x1 + R;
+    } else if (shell == 2)
+    {
+      xa = x0, xb = x1;
+      sa = 1, sb = 0;  // empty
+    } else
+    {
+      xa = x0 - R - shell, xb = x1 + R + shell;
+      sa = x0 - R, sb = x1 + R;
+    }
+    xa = max(xa, 0);
+    xb = min(xb, d0 - 1);
+    if (xa > xb)
+      continue;
+    int ri = (int)i;
+    auto unite = [&](const uint32_t j) {
+      if ((size_t)j >= m)
+        return;
+      const int pj = parent[j];
+      if (pj != ri)
+      {
+        const int rj = uf_find(parent, pj);
+        ri = uf_find(parent, ri);
+        if (rj != ri)
+          ri = uf_link(parent, ri, rj);
+      }
+    };
+    const size_t nrow = ((size_t)nz * d1 + ny) * nseg;
+    for (int ws = xa >> 5; ws <= (xb >> 5); ws++)
+    {
+      const RunWord rw = words[nrow + ws];
+      if (rw.tag != tag)
+        continue;  // nothing of this scan in that segment
+      const int lo = max(xa - ws * 32, 0), hi = min(xb - ws * 32, 31);
+      uint32_t wbits = rw.bits & (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+      while (wbits)
+      {
+        const int p = __ffs(wbits) - 1;
+        const uint32_t inv = ~(wbits >> p);
+        const int rl = __ffs(inv) ? __ffs(inv) - 1 : 32;
+        wbits = rl >= 32 ? 0u : (wbits & ~(((1u << rl) - 1u) << p));
+        const int p0 = ws * 32 + p, p1 = p0 + rl - 1;  // this run of the window, absolute x
+        const uint32_t j = rw.rank + (uint32_t)__popc(rw.bits & ((1u << p) - 1u));
+        if (p0 <= sb && p1 >= sa)
+        {
+          unite(j);  // some cell of it is inside for sure
+          continue;
+        }
+        // a border cell: the reference's fp32 test (FLANN L2_Simple: diff*diff summed over x, y, z) on the two centres
+        const int xh = shell == 2 ? p0 : (p0 < x0 ? x0 : x1);  // the cell of this run that faces it
+        const float ax = ((float)xh + 0.5f) * L.leaf + L.offset[0], bx = ((float)p0 + 0.5f) * L.leaf + L.offset[0];
+        const float ay = ((float)k1 + 0.5f) * L.leaf + L.offset[1], by = ((float)ny + 0.5f) * L.leaf + L.offset[1];
+        const float az = ((float)k2 + 0.5f) * L.leaf + L.offset[2], bz = ((float)nz + 0.5f) * L.leaf + L.offset[2];
+        float dd = 0.0f;
+        float diff = ax - bx;
+        dd += diff * diff;
+        diff = ay - by;
+        dd += diff * diff;
+        diff = az - bz;
+        dd += diff * diff;
+        if (dd < r2)
+          unite(j);
+      }
+    }
+  }
+}
+
+int vf_cluster_runs_dev(vofod_ctx* ctx, ClusterWs& ws, const uint32_t* d_cellkey, const RunWord* d_words, const VgLayout* d_layout, const RunRows& rows, float tol,
+                        const unsigned long long* d_m, size_t m_cap, int* d_labels, unsigned long long* d_ncl)
+{
+  if (!ctx->scan_prezero)
+    CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
+  if (m_cap == 0)
+    return 0;
+  ENSURE(ws.root, m_cap * 4);
+  const float r2 = (float)((double)tol * (double)tol);  // as vf_cluster_dev
+  const int nb = vf_blocks(ctx, m_cap, 256, 8);
+  LAUNCH(k_runs_union, vf_blocks(ctx, m_cap * (size_t)rows.n, 256, 8), 256, 0, d_m, m_cap, d_cellkey, d_words, d_layout, rows, r2,
+         (const unsigned long long*)ctx->d_counters.as<unsigned long long>(), ws.parent.as<int>());
+  LAUNCH(k_cl_roots, nb, 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
+  LAUNCH(k_cl_flatten, nb, 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
+  return 0;
+}
+
 extern "C" int vofod_cluster(vofod_ctx* ctx, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters)
 {
   if (!ctx)

@@ -136,6 +136,34 @@ __device__ __forceinline__ void minmax_init(MinMax* mm)
   mm->n_append = 0;
 }
 
+// layout of a voxel grid over a cloud (voxelgrid.cu): key = i + j*div[0] + k*div[0]*div[1], centre = (ijk + 0.5)*leaf + offset
+struct VgLayout
+{
+  float offset[3];
+  float leaf, inv;
+  int min_b[3], max_b[3], div[3];
+  int overflow;
+  unsigned n_valid;
+};
+
+// ---- run-based connected components on an occupancy grid (cluster.cu: vf_cluster_runs_dev) -------------------------
+// forward rows of the neighbourhood "squared index distance * leaf^2 < tol^2": for row (dy, dz) every cell with |dx| <= R is
+// surely inside, the cell at |dx| = R + 1 needs the fp32 distance test when shell == 1 (its exact squared distance EQUALS
+// tol^2, the rounding of the centres decides), and shell == 2 means R = -1 and dx = 0 itself is such a border case
+#define RUN_ROWS_MAX 16
+struct RunRows
+{
+  int n;
+  signed char dy[RUN_ROWS_MAX], dz[RUN_ROWS_MAX], R[RUN_ROWS_MAX], shell[RUN_ROWS_MAX];
+};
+// occupancy word of the grid clustering: valid iff tag == the current API call number (no clearing between scans)
+struct RunWord
+{
+  unsigned long long tag;
+  uint32_t bits;   // occupied x of this 32-cell segment
+  uint32_t rank;   // point number of its first occupied cell
+};
+
 // ---- raycast accumulator: one u64 per window cell = count (top 20 bits) | signed Q-length (low 44) ---
 #define ACC_LEN_BITS 44
 __device__ __forceinline__ void acc_decode(const unsigned long long p, unsigned& count, long long& len_q)
@@ -277,7 +305,9 @@ struct vofod_ctx
   // voxel-grid workspace
   DevBuf vg_pts;    // float4 per input point (x,y,z,valid/intensity)
   DevBuf vg_keys_a, vg_keys_b;
-  DevBuf vgh_cnt, vgh_bits, vgh_list;  // sort-free scan-path voxel grid: dense per-leaf counts, occupancy words, their popcount scan
+  DevBuf vgh_cnt, vgh_bits, vgh_list;
+  DevBuf cl_cellkey, cl_words;        // grid clustering of the scan's voxel list: key per point, RunWord per occupancy word  // sort-free scan-path voxel grid: dense per-leaf counts, occupancy words, their popcount scan
+  bool cl_force_hash = false;         // test switch: the scan clusters its voxel list with the generic spatial-hash clustering
   bool vg_force_sort = false;         // test switch: the scan path uses the generic sort-based voxel grid
   DevBuf vg_flags, vg_scan, vg_ustart, vg_ukey, vg_pref;
   DevBuf vox;       // vofod_vox per output voxel (cloud_weighted of the last scan)
@@ -478,13 +508,16 @@ static inline unsigned long long* vf_cnt(vofod_ctx* c, int slot) { return c->d_c
 
 // ---- stage entry points shared between the staged C ABI and vofod_process_scan (device pointers) ----
 // voxelgrid.cu
-int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p);  // scan + pose come from ctx->dyn
+int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p, bool seed_cluster = false);  // scan + pose come from ctx->dyn
 // cluster.cu: clusters `m_cap`-bounded points whose count lives in d_m (u64 slot); labels = min index
 int vf_cluster_dev(vofod_ctx* ctx, ClusterWs& ws, const float* d_xyz, int stride_floats, const unsigned long long* d_m, size_t m_cap, float tol,
                    int* d_labels, unsigned long long* d_ncl, size_t table_points_hint = 0);
 int vf_cluster_prefill(vofod_ctx* ctx, ClusterWs& ws, size_t m_cap, size_t table_points_hint);
 int vf_classify_prefill(vofod_ctx* ctx, size_t m_cap);
 int vf_sepclusters_prefill(vofod_ctx* ctx, const vofod_params& p);
+bool vf_run_rows(float tol, float leaf, RunRows& rr);  // false: neighbourhood too large for the grid clustering
+int vf_cluster_runs_dev(vofod_ctx* ctx, ClusterWs& ws, const uint32_t* d_cellkey, const RunWord* d_words, const VgLayout* d_layout, const RunRows& rows, float tol,
+                        const unsigned long long* d_m, size_t m_cap, int* d_labels, unsigned long long* d_ncl);
 int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_segbits, const uint32_t* d_segoff, const unsigned long long* d_m,
                           size_t m_cap, int* d_labels, unsigned long long* d_ncl);
 // raycast.cu

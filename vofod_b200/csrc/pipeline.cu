@@ -604,7 +604,9 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     ctx->stream = ctx->stream2;
-    int rrc = vf_cluster_prefill(ctx, ctx->cl, n, 0);
+    RunRows rows_probe;
+    const bool hash_cluster = ctx->cl_force_hash || ctx->vg_force_sort || !vf_run_rows((float)p.ground_points_max_distance, ctx->g.vs, rows_probe);
+    int rrc = hash_cluster ? vf_cluster_prefill(ctx, ctx->cl, n, 0) : 0;
     if (rrc >= 0 && s.do_classify)
       rrc = vf_classify_prefill(ctx, n);
     if (rrc >= 0 && s.do_sepclusters)
@@ -626,14 +628,25 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   STAGE_EVENT();
   STAGE_EVENT();  // 0 "range": the rangefinder seeds (A23) ride in the scan's first kernel (vf_begin_scan)
   // filterAndTransform (:928)
-  RET(vf_filter_voxelize_dev(ctx, n, p));
+  const int seeded = vf_filter_voxelize_dev(ctx, n, p, true);
+  if (seeded < 0)
+    return seeded;
   STAGE_EVENT();  // 1 "filtering"
   // clusterCloud (:932)
   if (side)
     CK(cudaStreamWaitEvent(st, ctx->ev_fills, 0));
   ENSURE(ctx->labels, n * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
-                     cnt + CNT_NCLUSTERS));
+  if (seeded)
+  {
+    // the voxel list is a set of grid cells: connected components on the occupancy words the filter left behind
+    RunRows rows;
+    vf_run_rows((float)p.ground_points_max_distance, ctx->g.vs, rows);
+    RET(vf_cluster_runs_dev(ctx, ctx->cl, ctx->cl_cellkey.as<uint32_t>(), ctx->cl_words.as<RunWord>(),
+                            reinterpret_cast<const VgLayout*>(ctx->scratch_d.as<char>() + 64), rows, (float)p.ground_points_max_distance, cnt + CNT_VG_M, n,
+                            ctx->labels.as<int>(), cnt + CNT_NCLUSTERS));
+  } else
+    RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
+                       cnt + CNT_NCLUSTERS));
   STAGE_EVENT();  // 2 "clusterization"
   // findCloseFarClusters (:936)
   RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p, true));

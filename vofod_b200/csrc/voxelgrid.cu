@@ -12,14 +12,6 @@
 #include "common.cuh"
 #include "prims.cuh"
 
-struct VgLayout
-{
-  float offset[3];
-  float leaf, inv;
-  int min_b[3], max_b[3], div[3];
-  int overflow;
-  unsigned n_valid;
-};
 
 struct CropArgs
 {
@@ -303,9 +295,18 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
   }
 }
 // one warp per NON-EMPTY occupancy word (listed by the scan together with its rank offset), lane = bit
+// seeds != NULL: also the input of the grid clustering (cluster.cu, vf_cluster_runs_dev): key per point, tagged occupancy
+// word, and the union-find forest with every point hung under the first point of its run
+struct VghSeeds
+{
+  uint32_t* cellkey;
+  RunWord* words;
+  int *parent, *sizes, *minidx;
+  const unsigned long long* counters;
+};
 __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ Lp, const uint4* __restrict__ list, const unsigned long long* __restrict__ d_list_n,
                                                   const size_t list_cap, uint32_t* __restrict__ bits, uint32_t* __restrict__ cnt, vofod_vox* __restrict__ out,
-                                                  const size_t out_cap)
+                                                  const size_t out_cap, const VghSeeds seeds)
 {
   pdl_enter();
   const VgLayout L = *after_wait(Lp);
@@ -318,7 +319,17 @@ __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ L
     const uint4 ent = list[e];  // (word index, occupancy bits, rank of its first set bit)
     const uint32_t w = ent.x, wb = ent.y;
     if (lane == 0)
+    {
       bits[w] = 0u;
+      if (seeds.words)
+      {
+        RunWord rw;
+        rw.tag = *after_wait(seeds.counters + CNT_EPOCH_BASE);
+        rw.bits = wb;
+        rw.rank = ent.z;
+        seeds.words[w] = rw;
+      }
+    }
     if (!((wb >> lane) & 1u))
       continue;
     const uint32_t seg = w % nseg, row = w / nseg;
@@ -335,6 +346,15 @@ __global__ void __launch_bounds__(256) k_vgh_emit(const VgLayout* __restrict__ L
       o.z = ((float)(int)k2 + 0.5f) * L.leaf + L.offset[2];
       o.count = c;
       out[r] = o;
+      if (seeds.words)
+      {
+        const unsigned zeros_below = ~wb & prims::lanemask_lt();
+        const int head = zeros_below ? 32 - __clz(zeros_below) : 0;  // first lane of this lane's run of consecutive set bits
+        seeds.cellkey[r] = key;
+        seeds.parent[r] = (int)(ent.z + (uint32_t)__popc(wb & ((1u << head) - 1u)));
+        seeds.sizes[r] = 0;
+        seeds.minidx[r] = 0x7fffffff;
+      }
     }
   }
 }
@@ -481,7 +501,9 @@ static int bits_for(unsigned long long v)
   return b;
 }
 
-int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
+// seed_cluster: also prepare the grid clustering of the output (returns 1 when that was done, 0 when the caller has to run
+// the generic clustering)
+int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p, bool seed_cluster)
 {
   const size_t np = prims::padded(n);
   ENSURE(ctx->vg_pts, np * 16);
@@ -545,12 +567,29 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p)
     // a word holds at least one of the n points
     const size_t list_cap = n < words_cap ? n : words_cap;
     ENSURE(ctx->vgh_list, (list_cap + 1) * sizeof(uint4));
+    VghSeeds seeds = {};
+    RunRows rows;
+    const bool seed = seed_cluster && !ctx->cl_force_hash && vf_run_rows((float)p.ground_points_max_distance, g.vs, rows);
+    if (seed)
+    {
+      ENSURE(ctx->cl_cellkey, np * 4);
+      ENSURE(ctx->cl_words, (words_cap + 1) * sizeof(RunWord));
+      ENSURE(ctx->cl.parent, n * 4);
+      ENSURE(ctx->cl.sizes, n * 4);
+      ENSURE(ctx->cl.minidx, n * 4);
+      seeds.cellkey = ctx->cl_cellkey.as<uint32_t>();
+      seeds.words = ctx->cl_words.as<RunWord>();
+      seeds.parent = ctx->cl.parent.as<int>();
+      seeds.sizes = ctx->cl.sizes.as<int>();
+      seeds.minidx = ctx->cl.minidx.as<int>();
+      seeds.counters = ctx->d_counters.as<unsigned long long>();
+    }
     ZERO_CNT(CNT_VGH_LIST, 1);
     RET(scan_excl_u32_pair(ctx, ctx->vgh_bits.as<uint32_t>(), nullptr, cnt + CNT_VGH_WORDS, words_cap, cnt + CNT_VG_M, true, nullptr, nullptr, 0,
                            nullptr, false, ctx->vgh_list.as<uint4>(), cnt + CNT_VGH_LIST));
     LAUNCH(k_vgh_emit, vf_blocks(ctx, list_cap * 32, 256, 8), 256, 0, L, ctx->vgh_list.as<uint4>(), cnt + CNT_VGH_LIST, list_cap, ctx->vgh_bits.as<uint32_t>(),
-           ctx->vgh_cnt.as<uint32_t>(), ctx->vox.as<vofod_vox>(), np);
-    return 0;
+           ctx->vgh_cnt.as<uint32_t>(), ctx->vox.as<vofod_vox>(), np, seeds);
+    return seed ? 1 : 0;
   }
   return vg_run(ctx, n, g.vs, true, ac, bits, nullptr, nullptr, 0.f, ctx->vox, CNT_VG_M, CNT_VG_NVALID, CNT_VG_OVERFLOW, true);
 }

@@ -418,6 +418,7 @@ enum
   CNT_SEP_LIVE,       // length of the sepclusters work list
   CNT_UPD_LEFT,       // k_update_points: left-over list length / block ticket (both return to 0 at the end of the kernel)
   CNT_UPD_TICKET,
+  CNT_CLEAR_TICKET,   // k_clear_flags: blocks done (returns to 0)
   CNT_VGH_LIST,       // non-empty occupancy words listed by the scan
   CNT_SEP_NUNSURE,    // voxels of unsure clusters listed for the decay
   CNT_VGH_WORDS,      // occupancy words of the scan-path voxel grid (depends on the cloud's bounding box)

@@ -328,17 +328,19 @@ __global__ void k_clear_flags(uint8_t* __restrict__ flags, const uint32_t* __res
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += (unsigned long long)gridDim.x * blockDim.x)
       flags[flagged[i]] = 0;
   }
-}
-__global__ void k_clear_flags_finish(unsigned long long* counters)
-{
-  pdl_enter();
-  if (counters[CNT_APPLY_ANY] != 0ull)
+  // the last block to finish empties the list (every block has read its length by then)
+  __syncthreads();
+  if (threadIdx.x == 0)
   {
-    counters[CNT_FLAGGED] = 0ull;
-    counters[CNT_FLAGGED_OVERFLOW] = 0ull;
+    __threadfence();
+    if (atomicAdd(counters + CNT_CLEAR_TICKET, 1ull) == (unsigned long long)gridDim.x - 1ull)
+    {
+      counters[CNT_FLAGGED] = 0ull;
+      counters[CNT_FLAGGED_OVERFLOW] = 0ull;
+      counters[CNT_CLEAR_TICKET] = 0ull;
+    }
   }
 }
-
 // parity/debug: expand the window accumulator into full-grid planes
 __global__ void k_raycast_expand(const Geom g, const Window w, const unsigned long long* __restrict__ acc, const double inv_scale, uint32_t* __restrict__ counts,
                                  float* __restrict__ lengths)
@@ -520,7 +522,6 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   const size_t work = ctx->flags_full_dirty ? (size_t)n_cells : ctx->flagged_cap;
   LAUNCH(k_clear_flags, vf_blocks(ctx, work ? work : 1, 256), 256, 0, ctx->flags.as<uint8_t>(), ctx->flagged.as<uint32_t>(), ctx->flagged_cap, n_cells, cnt,
          ctx->flags_full_dirty ? 1 : 0);
-  LAUNCH(k_clear_flags_finish, 1, 1, 0, cnt);
   // flags_full_dirty can only be dropped once we know (on the host) that the clear really ran; callers that
   // read CNT_APPLY_ANY back do that (see vofod_raycast_apply / process_scan).
   return VOFOD_OK;

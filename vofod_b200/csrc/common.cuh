@@ -250,6 +250,7 @@ struct vofod_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // side branch for work that is independent of the main chain (raycast accumulate, second scan)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr, ev_fork2 = nullptr, ev_cls = nullptr;
+  bool nbg_precounted = false;  // CNT_NBG of this scan was counted on the side branch
   size_t cls_prefilled = 0;     // classification work arrays cleared ahead of time for this many points
   size_t sep_prefilled = 0;     // sepclusters fast-path count arrays cleared ahead of time (= their total length)
   std::string err;

@@ -376,6 +376,16 @@ __global__ void __launch_bounds__(256) k_close_finish(const int* __restrict__ la
 
 // phase 1 = everything up to the cross-slab exchange point (local background count, per-cluster close flags of the points this
 // slab answers for), phase 2 = the rest, phase 0 = both (unsharded)
+// nVoxelsOver(thr_new_obstacles) into CNT_NBG (zeroed by the scan's first kernel): the counting part of k_close_points alone
+int vf_count_bg_dev(vofod_ctx* ctx, const vofod_params& p)
+{
+  const float thr = (float)p.thr_new_obstacles;
+  const size_t items = (size_t)ctx->g.st_size[0] * ctx->g.st_size[1] * dirty_chunks(ctx->g);
+  LAUNCH(k_close_points, vf_blocks(ctx, items, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, (const vofod_vox*)nullptr, (const unsigned long long*)nullptr, (size_t)0,
+         0.0f, thr, (uint8_t*)nullptr, (int*)nullptr, vf_dirty_cols(ctx, thr, &p), vf_cnt(ctx, CNT_NBG));
+  return 0;
+}
+
 int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase,
                        bool claim_for_update)
 {
@@ -397,17 +407,20 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
       // :712 nVoxelsOver rides in the hasCloseTo kernel
       ENSURE(ctx->cl_close, m_cap * 4);
       ENSURE(ctx->pt_close, m_cap + 64);
-      if (!ctx->scan_prezero)
+      const bool precounted = ctx->nbg_precounted;  // (the scan's side branch has done it)
+      ctx->nbg_precounted = false;
+      if (!ctx->scan_prezero && !precounted)
         CK(cudaMemsetAsync(cnt + CNT_NBG, 0, sizeof(unsigned long long), ctx->stream));
       const size_t items = (size_t)ctx->g.st_size[0] * ctx->g.st_size[1] * dirty_chunks(ctx->g);
-      const size_t work = m_cap * 32 > items ? m_cap * 32 : items;
+      const size_t work = m_cap * 32 > items || precounted ? m_cap * 32 : items;
       LAUNCH(k_close_points, vf_blocks(ctx, work, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
-             ctx->cl_close.as<int>(), vf_dirty_cols(ctx, thr, &p), cnt + CNT_NBG);
+             ctx->cl_close.as<int>(), vf_dirty_cols(ctx, thr, &p), precounted ? nullptr : cnt + CNT_NBG);
       state_done = phase == 0;  // unsharded: the count is final, the latch can ride in the next kernel
       LAUNCH(k_close_mark, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->pt_close.as<uint8_t>(), d_labels, d_m, m_cap, ctx->cl_close.as<int>(),
              state_done ? cnt : nullptr, min_sufficient);
-    } else
+    } else if (!ctx->nbg_precounted)
       RET(vf_count_over_dev(ctx, thr, cnt + CNT_NBG, &p));
+    ctx->nbg_precounted = false;
   }
   if (phase != 1)
   {
@@ -611,9 +624,13 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
       rrc = vf_classify_prefill(ctx, n);
     if (rrc >= 0 && s.do_sepclusters)
       rrc = vf_sepclusters_prefill(ctx, p);
+    // nVoxelsOver of :712 only needs the map as the previous scan (and this scan's rangefinder seed) left it
+    if (rrc >= 0)
+      rrc = vf_count_bg_dev(ctx, p);
     ctx->stream = st;
     if (rrc < 0)
       return rrc;
+    ctx->nbg_precounted = true;
     CK(cudaEventRecord(ctx->ev_fills, ctx->stream2));
     if (overlap_raycast)
     {
@@ -713,10 +730,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     *sep_status_out = rc;
   }
   STAGE_EVENT();  // 9 "sep bg clusters"
-  // one read-back of every count (+ a bounded prefix of the detections) into pinned memory
+  // one read-back of every count into pinned memory (detection records follow on demand: most scans have none)
   CK(cudaMemcpyAsync(ctx->pinned, cnt, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, st));
-  if (s.do_classify && ctx->dets.p)
-    CK(cudaMemcpyAsync((char*)ctx->pinned + 4096, ctx->dets.p, 16 * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
   STAGE_EVENT();  // 10 "readback"
 #undef STAGE_EVENT
   return 0;
@@ -876,7 +891,6 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[11]);
 
   const unsigned long long* hp = (const unsigned long long*)ctx->pinned;
-  const vofod_detection* hdets = (const vofod_detection*)((const char*)ctx->pinned + 4096);
   if (hp[CNT_WATCHDOG])
     return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", hp[CNT_WATCHDOG]);
   if (hp[CNT_OOB])
@@ -946,13 +960,8 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (n_det && dets)
   {
     const size_t k = n_det < det_cap ? n_det : det_cap;
-    if (k <= 16)
-      memcpy(dets, hdets, k * sizeof(vofod_detection));
-    else
-    {
-      CK(cudaMemcpyAsync(dets, ctx->dets.p, k * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
+    CK(cudaMemcpyAsync(dets, ctx->dets.p, k * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
   }
   if (n_det > det_cap && dets)
     return vf_fail(ctx, VOFOD_E_CAPACITY, "process_scan: %zu detections, capacity %zu", n_det, det_cap);

@@ -334,6 +334,7 @@ struct vofod_ctx
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool pdl_enabled = true;      // programmatic dependent launch between consecutive kernels (see LAUNCH)
+  bool pdl_in_graph = false;    // experiment switch (VOFOD_OPT_PDL = 2): keep the attribute under stream capture too
   bool pdl_chain = false;       // the last operation put on ctx->stream was a kernel launch of this library
   bool overlap_enabled = true;  // raycast accumulate / second sep scan on the side stream
   bool graph_enabled = true;
@@ -476,6 +477,9 @@ int vf_fill(vofod_ctx* ctx, const FillJob* jobs, int n_jobs);
 // launches (pdl_chain): griddepcontrol.wait orders a kernel after its prerequisite GRIDS — measured: a kernel launched with
 // the attribute right behind a cudaMemsetAsync ran concurrently with that memset.  For the same reason the stage-local
 // clears on the scan path are kernels (vf_fill), not memset nodes.
+// Under stream capture the attribute stays off: measured, a replayed graph with programmatic edges is ~2 % SLOWER than
+// one with plain edges (the graph already launches its nodes back to back; blocks parked in griddepcontrol.wait only take
+// SM slots from the side branch), while the kernel-by-kernel path gains 20 %.
 #define LAUNCH(kern, grid, block, smem, ...)                                                             \
   do                                                                                                     \
   {                                                                                                      \
@@ -486,7 +490,7 @@ int vf_fill(vofod_ctx* ctx, const FillJob* jobs, int n_jobs);
     cfg__.stream = ctx->stream;                                                                          \
     cudaLaunchAttribute at__[1];                                                                         \
     at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                     \
-    at__[0].val.programmaticStreamSerializationAllowed = (ctx->pdl_enabled && ctx->pdl_chain) ? 1 : 0;   \
+    at__[0].val.programmaticStreamSerializationAllowed = (ctx->pdl_enabled && ctx->pdl_chain && (!ctx->capturing || ctx->pdl_in_graph)) ? 1 : 0; \
     cfg__.attrs = at__;                                                                                  \
     cfg__.numAttrs = 1;                                                                                  \
     cudaError_t e__ = cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__);                                     \

@@ -226,6 +226,7 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
   if (option == VOFOD_OPT_PDL)
   {
     ctx->pdl_enabled = value != 0;
+    ctx->pdl_in_graph = value == 2;
     ctx->alloc_gen++;
     return VOFOD_OK;
   }

@@ -422,6 +422,15 @@ def test_process_scan_cfg2_full_size(gpu, cpu):
     _run_sequence(gpu, cpu, sensor, p, vs, 0, (0, 1, 2, 21), fixed=True, check_maps_every=1)
 
 
+def test_process_scan_cfg2_full_size_steady_state(gpu, cpu):
+    """BASELINE.json configs[1] at full size over the first 44 scans of the bench's sequence (take-off, bootstrap of the
+    background, steady state with graph replay): every per-scan result, the voxel lists, labels, clusters and detections
+    after every scan, the whole 26 M-cell score grid every 11 scans."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 44), fixed=True, check_maps_every=11)
+
+
 def test_full_size_properties(gpu):
     """Size-independent properties at full size, no oracle: traversal count is independent of aggregation, the
     accumulator returns to zero after apply, flags are cleared, repeated identical scans are deterministic."""

@@ -327,6 +327,12 @@ int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters) { return begin_call(c
 int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p) { return begin_call(ctx, true, &p); }
 static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params)
 {
+  // work done ahead of time by a previous call's side branch does not carry over (that call may have failed half way)
+  ctx->nbg_precounted = false;
+  ctx->cls_prefilled = 0;
+  ctx->sep_prefilled = 0;
+  ctx->cl.prefilled_tsize = 0;
+  ctx->cl_bg.prefilled_tsize = 0;
   ctx->epoch_local = 0;
   ctx->epoch_calls++;
   // the generation field of a look-back state has 30 bits: before it can repeat, forget every old state

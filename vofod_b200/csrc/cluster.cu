@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(256) k_cg_union(const unsigned long long* __re
   }
 }
 
+// d_labels == NULL: only the unions — the caller reads the forest (ws.parent) itself
 int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, const uint32_t* d_segbits, const uint32_t* d_segoff, const unsigned long long* d_m,
                           size_t m_cap, int* d_labels, unsigned long long* d_ncl)
 {
@@ -465,9 +466,11 @@ int vf_cluster_runs26_dev(vofod_ctx* ctx, ClusterWs& ws, const vofod_vox* d_ds, 
     CK(cudaMemsetAsync(d_ncl, 0, 8, ctx->stream));
   if (m_cap == 0)
     return 0;
-  ENSURE(ws.root, m_cap * 4);
   const int nb = vf_blocks(ctx, m_cap, 256, 8);
   LAUNCH(k_cg_union, vf_blocks(ctx, m_cap * 4, 256, 8), 256, 0, d_m, m_cap, d_ds, ctx->g, d_segbits, d_segoff, ws.parent.as<int>());
+  if (!d_labels)
+    return 0;
+  ENSURE(ws.root, m_cap * 4);
   LAUNCH(k_cl_roots, nb, 256, 0, d_m, m_cap, ws.parent.as<int>(), ws.root.as<int>(), ws.minidx.as<int>());
   LAUNCH(k_cl_flatten, nb, 256, 0, d_m, m_cap, ws.root.as<int>(), ws.minidx.as<int>(), d_labels, ws.sizes.as<int>(), d_ncl);
   return 0;

@@ -93,8 +93,7 @@ __global__ void __launch_bounds__(256) k_sep_fast_count(const float* __restrict_
 __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__ score, const Geom g, const float thr, const float thr_sure, const uint2* __restrict__ live,
                                                        const unsigned long long* __restrict__ n_live, const int nseg, const int nzc,
                                                        const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ segoff, vofod_vox* __restrict__ ds,
-                                                       uint32_t* __restrict__ flag_in_order, int* __restrict__ parent, int* __restrict__ sizes, int* __restrict__ minidx,
-                                                       int* __restrict__ nsure, const size_t cap)
+                                                       uint32_t* __restrict__ flag_in_order, int* __restrict__ parent, int* __restrict__ nsure, const size_t cap)
 {
   pdl_enter();
   const unsigned lane = threadIdx.x & 31;
@@ -140,8 +139,6 @@ __global__ void __launch_bounds__(256) k_sep_fast_emit(const float* __restrict__
           const unsigned zeros_below = ~bal & prims::lanemask_lt();
           const int head = zeros_below ? 32 - __clz(zeros_below) : 0;
           parent[r] = (int)(base + __popc(bal & ((1u << head) - 1u)));
-          sizes[r] = 0;
-          minidx[r] = 0x7fffffff;
           nsure[r] = 0;
         }
         if (o < cap)
@@ -196,12 +193,10 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   ENSURE(ctx->sep_ds, padded(cap) * sizeof(vofod_vox));
   ENSURE(ctx->vg_flags, padded(cap) * 4);
   ENSURE(ctx->cl_bg.parent, cap * 4);
-  ENSURE(ctx->cl_bg.sizes, cap * 4);
-  ENSURE(ctx->cl_bg.minidx, cap * 4);
   ENSURE(ctx->sep_nsure, cap * 4);
   LAUNCH(k_sep_fast_emit, nb, 256, 0, ctx->score.as<float>(), g, thr, thr_sure, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
          ctx->sep_coloff.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), ctx->sep_ds.as<vofod_vox>(), ctx->vg_flags.as<uint32_t>(), ctx->cl_bg.parent.as<int>(),
-         ctx->cl_bg.sizes.as<int>(), ctx->cl_bg.minidx.as<int>(), ctx->sep_nsure.as<int>(), cap);
+         ctx->sep_nsure.as<int>(), cap);
   return 0;
 }
 
@@ -226,24 +221,61 @@ __global__ void __launch_bounds__(256) k_sep_nsure(const vofod_vox* __restrict__
       atomicAdd(reinterpret_cast<unsigned*>(nsure) + l, sum);
   }
 }
+// fast path: root of every voxel + n_sure per ROOT in one pass over the forest.  Which member names a cluster is irrelevant to
+// this stage (only sums per cluster and "is any cluster sure" matter), so the canonical min-index labels are not computed.
+__global__ void __launch_bounds__(256) k_sep_roots_nsure(const int* __restrict__ parent, const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ d_k,
+                                                         const size_t cap, int* __restrict__ root, int* __restrict__ nsure)
+{
+  pdl_enter();
+  const size_t k = prims::dev_count(d_k, cap);
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; i0 < k; i0 += (size_t)gridDim.x * blockDim.x)
+  {
+    const size_t i = i0 + lane;
+    const bool valid = i < k;
+    int r = valid ? (int)i : -1 - (int)lane;
+    if (valid)
+      while (true)
+      {
+        const int pr = parent[r];
+        if (pr == r)
+          break;
+        r = pr;
+      }
+    if (valid)
+      root[i] = r;
+    const unsigned c = valid ? counts[i] : 0u;
+    // one atomic per (warp, cluster): the big background body would otherwise serialise every point on one word
+    const unsigned grp = __match_any_sync(VOFOD_FULL, r);
+    const unsigned sum = __reduce_add_sync(grp, c);
+    if (valid && sum && lane == (unsigned)(__ffs(grp) - 1))
+      atomicAdd(reinterpret_cast<unsigned*>(nsure) + r, sum);
+  }
+}
 // :1186-1206 — is any cluster sure?  + the list of the voxels of UNSURE clusters (normally a handful) for the decay
 __global__ void __launch_bounds__(256) k_sep_any(const int* __restrict__ labels, const int* __restrict__ nsure, const unsigned long long* __restrict__ d_k, const size_t cap,
-                                                 const unsigned min_sure, unsigned long long* __restrict__ counters, uint32_t* __restrict__ unsure)
+                                                 const unsigned min_sure, unsigned long long* __restrict__ counters, uint32_t* __restrict__ unsure,
+                                                 const int count_clusters)
 {
   pdl_enter();
   const size_t k = prims::dev_count(d_k, cap);
   bool any = false;
+  unsigned n_roots = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
   {
     const int l = labels[i];
     const int ns = nsure[l];
     if (l == (int)i && (unsigned long long)(long long)ns >= (unsigned long long)min_sure)  // size_t(int) >= unsigned
       any = true;
+    n_roots += l == (int)i;
     if ((unsigned)ns < min_sure)  // :1246
       unsure[atomicAdd(counters + CNT_SEP_NUNSURE, 1ull)] = (uint32_t)i;
   }
   if (__any_sync(VOFOD_FULL, any) && (threadIdx.x & 31) == 0)
     counters[CNT_SEP_ANY_SURE] = 1ull;
+  n_roots = prims::warp_sum(n_roots);
+  if (count_clusters && n_roots && (threadIdx.x & 31) == 0)
+    atomicAdd(counters + CNT_SEP_NCL, (unsigned long long)n_roots);
 }
 __device__ __forceinline__ void sep_state(unsigned long long* __restrict__ counters, const unsigned long long k_cap)
 {
@@ -371,8 +403,8 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   ENSURE(ctx->sep_labels, K * 4);
   ENSURE(ctx->sep_nsure, K * 4);
   if (fast)  // leaf size 1 <=> tolerance 2 on distinct voxel centres: 26-connectivity, read off the occupancy masks
-    RET(vf_cluster_runs26_dev(ctx, ctx->cl_bg, ctx->sep_ds.as<vofod_vox>(), ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), d_kds, K,
-                              ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL));
+    RET(vf_cluster_runs26_dev(ctx, ctx->cl_bg, ctx->sep_ds.as<vofod_vox>(), ctx->sep_segcnt.as<uint32_t>(), ctx->sep_segoff.as<uint32_t>(), d_kds, K, nullptr,
+                              cnt + CNT_SEP_NCL));
   else
     RET(vf_cluster_dev(ctx, ctx->cl_bg, reinterpret_cast<const float*>(ctx->sep_ds.p), 4, d_kds, K, (float)mv, ctx->sep_labels.as<int>(), cnt + CNT_SEP_NCL,
                        k_cap ? ctx->sep_table_hint : 0));
@@ -383,11 +415,13 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   }
   ZERO_CNT(CNT_SEP_ANY_SURE, 1);
   const int nb = vf_blocks(ctx, K, 256, 8);
-  LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), fast ? ctx->vg_flags.as<uint32_t>() : nullptr, ctx->sep_labels.as<int>(), d_kds, K,
-         ctx->sep_nsure.as<int>());
+  if (fast)  // sep_labels = root of every voxel (any member may name a cluster here)
+    LAUNCH(k_sep_roots_nsure, nb, 256, 0, ctx->cl_bg.parent.as<int>(), ctx->vg_flags.as<uint32_t>(), d_kds, K, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>());
+  else
+    LAUNCH(k_sep_nsure, nb, 256, 0, ctx->sep_ds.as<vofod_vox>(), (const uint32_t*)nullptr, ctx->sep_labels.as<int>(), d_kds, K, ctx->sep_nsure.as<int>());
   ENSURE(ctx->sep_unsure, K * 4);
   ZERO_CNT(CNT_SEP_NUNSURE, 1);
-  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt, ctx->sep_unsure.as<uint32_t>());
+  LAUNCH(k_sep_any, nb, 256, 0, ctx->sep_labels.as<int>(), ctx->sep_nsure.as<int>(), d_kds, K, min_sure, cnt, ctx->sep_unsure.as<uint32_t>(), fast ? 1 : 0);
   // :1219-1237 ball of offsets with Eigen's truncated integer norm (uploaded once per parameter change)
   if (ctx->sep_off_n < 0 || ctx->sep_off_mv != mv || ctx->sep_off_md != max_dist_idx)
   {

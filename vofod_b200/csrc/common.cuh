@@ -248,8 +248,10 @@ struct vofod_ctx
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream3 = nullptr;   // second side branch: hasCloseTo of the voxel list next to its clustering
   cudaStream_t stream2 = nullptr;   // side branch for work that is independent of the main chain (raycast accumulate, second scan)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr, ev_fork2 = nullptr, ev_cls = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fills = nullptr, ev_fork2 = nullptr, ev_cls = nullptr, ev_fork3 = nullptr, ev_cp = nullptr;
+  bool close_points_done = false;  // k_close_points of this scan ran on the second side branch
   bool nbg_precounted = false;  // CNT_NBG of this scan was counted on the side branch
   size_t cls_prefilled = 0;     // classification work arrays cleared ahead of time for this many points
   size_t sep_prefilled = 0;     // sepclusters fast-path count arrays cleared ahead of time (= their total length)
@@ -538,6 +540,7 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
                        bool claim_for_update);
 int vf_update_points_scan_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);
 int vf_update_owner(vofod_ctx* ctx);
+int vf_close_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const unsigned long long* d_m, size_t m_cap, const vofod_params& p);  // hasCloseTo per point, ahead of time
 int vf_update_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const uint8_t* d_sel, int sel_value, const unsigned long long* d_m, size_t m_cap, float score,
                          float flag);
 int vf_count_over_dev(vofod_ctx* ctx, float thr, unsigned long long* d_out, const vofod_params* p = nullptr);

@@ -93,6 +93,7 @@ int vofod_create(int device, vofod_ctx** out)
     return vf_fail(nullptr, VOFOD_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
@@ -101,6 +102,8 @@ int vofod_create(int device, vofod_ctx** out)
   cudaEventCreateWithFlags(&ctx->ev_fills, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_cls, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fork3, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_cp, cudaEventDisableTiming);
   for (int i = 0; i <= VOFOD_N_STAGES; i++)
     cudaEventCreate(&ctx->ev[i]);
   ctx->ev_ok = true;
@@ -176,8 +179,14 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_fork2);
   if (ctx->ev_cls)
     cudaEventDestroy(ctx->ev_cls);
+  if (ctx->ev_fork3)
+    cudaEventDestroy(ctx->ev_fork3);
+  if (ctx->ev_cp)
+    cudaEventDestroy(ctx->ev_cp);
   if (ctx->stream2)
     cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3)
+    cudaStreamDestroy(ctx->stream3);
   for (int i = 0; i < 2; i++)
     if (ctx->ev_prefetch[i])
       cudaEventDestroy(ctx->ev_prefetch[i]);
@@ -329,6 +338,7 @@ static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_param
 {
   // work done ahead of time by a previous call's side branch does not carry over (that call may have failed half way)
   ctx->nbg_precounted = false;
+  ctx->close_points_done = false;
   ctx->cls_prefilled = 0;
   ctx->sep_prefilled = 0;
   ctx->cl.prefilled_tsize = 0;

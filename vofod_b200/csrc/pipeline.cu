@@ -386,6 +386,19 @@ int vf_count_bg_dev(vofod_ctx* ctx, const vofod_params& p)
   return 0;
 }
 
+// hasCloseTo of every point (the part of findCloseFarClusters that does not look at the labels), ahead of time
+int vf_close_points_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const unsigned long long* d_m, size_t m_cap, const vofod_params& p)
+{
+  if (m_cap == 0)
+    return 0;
+  ENSURE(ctx->cl_close, m_cap * 4);
+  ENSURE(ctx->pt_close, m_cap + 64);
+  LAUNCH(k_close_points, vf_blocks(ctx, m_cap * 32, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, (float)p.ground_points_max_distance,
+         (float)p.thr_new_obstacles, ctx->pt_close.as<uint8_t>(), ctx->cl_close.as<int>(), (const uint8_t*)nullptr, (unsigned long long*)nullptr);
+  ctx->close_points_done = true;
+  return 0;
+}
+
 int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const unsigned long long* d_m, size_t m_cap, const vofod_params& p, int phase,
                        bool claim_for_update)
 {
@@ -413,8 +426,11 @@ int vf_close_far_phase(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labe
         CK(cudaMemsetAsync(cnt + CNT_NBG, 0, sizeof(unsigned long long), ctx->stream));
       const size_t items = (size_t)ctx->g.st_size[0] * ctx->g.st_size[1] * dirty_chunks(ctx->g);
       const size_t work = m_cap * 32 > items || precounted ? m_cap * 32 : items;
-      LAUNCH(k_close_points, vf_blocks(ctx, work, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
-             ctx->cl_close.as<int>(), vf_dirty_cols(ctx, thr, &p), precounted ? nullptr : cnt + CNT_NBG);
+      const bool points_done = ctx->close_points_done && precounted;  // (the scan's second side branch has done it)
+      ctx->close_points_done = false;
+      if (!points_done)
+        LAUNCH(k_close_points, vf_blocks(ctx, work, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, d_vox, d_m, m_cap, max_dist, thr, ctx->pt_close.as<uint8_t>(),
+               ctx->cl_close.as<int>(), vf_dirty_cols(ctx, thr, &p), precounted ? nullptr : cnt + CNT_NBG);
       state_done = phase == 0;  // unsharded: the count is final, the latch can ride in the next kernel
       LAUNCH(k_close_mark, vf_blocks(ctx, m_cap, 256, 8), 256, 0, ctx->pt_close.as<uint8_t>(), d_labels, d_m, m_cap, ctx->cl_close.as<int>(),
              state_done ? cnt : nullptr, min_sufficient);
@@ -649,6 +665,19 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   if (seeded < 0)
     return seeded;
   STAGE_EVENT();  // 1 "filtering"
+  // hasCloseTo of the voxels does not look at their labels: second side branch, next to the clustering
+  const bool cp_side = side && ctx->stream3 != nullptr && ctx->nbg_precounted;
+  if (cp_side)
+  {
+    CK(cudaEventRecord(ctx->ev_fork3, st));
+    CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork3, 0));
+    ctx->stream = ctx->stream3;
+    const int prc = vf_close_points_dev(ctx, ctx->vox.as<vofod_vox>(), cnt + CNT_VG_M, n, p);
+    ctx->stream = st;
+    if (prc < 0)
+      return prc;
+    CK(cudaEventRecord(ctx->ev_cp, ctx->stream3));
+  }
   // clusterCloud (:932)
   if (side)
     CK(cudaStreamWaitEvent(st, ctx->ev_fills, 0));
@@ -666,6 +695,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
                        cnt + CNT_NCLUSTERS));
   STAGE_EVENT();  // 2 "clusterization"
   // findCloseFarClusters (:936)
+  if (cp_side)
+    CK(cudaStreamWaitEvent(st, ctx->ev_cp, 0));
   RET(vf_close_far_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p, true));
   STAGE_EVENT();  // 3 "close X far"
   // classifyClusters, the part that only looks at the voxel list: on the side branch, next to the point update and the ray apply

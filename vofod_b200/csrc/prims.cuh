@@ -177,6 +177,7 @@ struct ScanJob
   unsigned long long* state;
   unsigned long long* total;
   int popc;
+  int sparse_out;  // 1: the caller only reads out[i] where in[i] != 0 — groups of four zero inputs are not stored
   // optional: every non-zero element is appended (in no particular order) as (index, raw value, exclusive prefix, 0)
   uint4* list;
   unsigned long long* list_n;
@@ -269,7 +270,7 @@ static __global__ void __launch_bounds__(NT) k_scan_excl_u32(const ScanJobs jobs
       o.y = run; run += v[4 * q + 1];
       o.z = run; run += v[4 * q + 2];
       o.w = run; run += v[4 * q + 3];
-      if (out)  // (a caller that only wants the list and the total passes NULL)
+      if (out && !(J.sparse_out && (v[4 * q] | v[4 * q + 1] | v[4 * q + 2] | v[4 * q + 3]) == 0u))  // (NULL: only list and total wanted)
         *reinterpret_cast<uint4*>(out + base_i + 4 * q) = o;
     }
     __syncthreads();
@@ -437,20 +438,20 @@ static inline int scan_grid(const vofod_ctx* c, const size_t cap_items)
 // Two independent scans in one launch.  `b_*` may be all-null for a single scan.  Scan B uses ctx->tile_state2.
 static inline int scan_excl_u32_pair(vofod_ctx* ctx, const uint32_t* a_in, uint32_t* a_out, const unsigned long long* a_dn, const size_t a_cap, unsigned long long* a_total,
                                      const bool a_popc, const uint32_t* b_in, uint32_t* b_out, const size_t b_cap, unsigned long long* b_total, const bool b_popc,
-                                     uint4* a_list = nullptr, unsigned long long* a_list_n = nullptr)
+                                     uint4* a_list = nullptr, unsigned long long* a_list_n = nullptr, const bool sparse_out = false)
 {
   const size_t a_tiles = (a_cap + TILE - 1) / TILE + 1;
   ENSURE(ctx->tile_state, a_tiles * 256 * sizeof(unsigned long long));
   ScanJobs jobs;
-  jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0, a_list, a_list_n};
-  jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr};
+  jobs.j[0] = ScanJob{a_in, a_out, a_dn, a_cap, ctx->tile_state.as<unsigned long long>(), a_total, a_popc ? 1 : 0, sparse_out ? 1 : 0, a_list, a_list_n};
+  jobs.j[1] = ScanJob{nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, nullptr};
   const bool big = (a_cap > b_cap ? a_cap : b_cap) >= (size_t(1) << 18);
   int gx = big ? scan_grid<SCAN_BIG_IPT>(ctx, a_cap) : scan_grid<IPT>(ctx, a_cap), gy = 1;
   if (b_in)
   {
     const size_t b_tiles = (b_cap + TILE - 1) / TILE + 1;
     ENSURE(ctx->tile_state2, b_tiles * sizeof(unsigned long long));
-    jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0, nullptr, nullptr};
+    jobs.j[1] = ScanJob{b_in, b_out, nullptr, b_cap, ctx->tile_state2.as<unsigned long long>(), b_total, b_popc ? 1 : 0, sparse_out ? 1 : 0, nullptr, nullptr};
     const int gb = big ? scan_grid<SCAN_BIG_IPT>(ctx, b_cap) : scan_grid<IPT>(ctx, b_cap);
     gx = gx > gb ? gx : gb;
     gy = 2;

@@ -179,7 +179,7 @@ static int sep_fast_lists(vofod_ctx* ctx, const float thr, const float thr_sure,
   LAUNCH(k_sep_fast_count, nb, 256, 0, ctx->score.as<float>(), g, thr, dirty, ctx->sep_live.as<uint2>(), cnt + CNT_SEP_LIVE, nseg, nzc,
          ctx->sep_colcnt.as<uint32_t>(), ctx->sep_segcnt.as<uint32_t>());
   RET(scan_excl_u32_pair(ctx, ctx->sep_colcnt.as<uint32_t>(), ctx->sep_coloff.as<uint32_t>(), nullptr, ncc, cnt + CNT_SEP_K, false, ctx->sep_segcnt.as<uint32_t>(),
-                         ctx->sep_segoff.as<uint32_t>(), nsegs, nullptr, true));
+                         ctx->sep_segoff.as<uint32_t>(), nsegs, nullptr, true, nullptr, nullptr, true));  // offsets are read at non-empty entries only
   if (host_total)
   {
     unsigned long long total = 0;

@@ -256,34 +256,49 @@ __global__ void __launch_bounds__(256) k_close_points(const float* __restrict__ 
     bool hit = false;
     if (nx > 0 && ny > 0 && nz > 0)
     {
-      const int total = nx * ny * nz;
-      for (int base = 0; base < total && !hit; base += 32 * 8)
+      // The answer is "any cell of the window ...", so the order of the cells is free: the point's own z-plane goes first, in
+      // a round of its own — for a point on mapped background its neighbours in that plane already decide, and the other
+      // planes (5/6 of the window's memory sectors, which is what this kernel is made of) are never fetched.
+      const int nxy = nx * ny;
+      const int zown = (oz >= bz && oz < ez) ? oz - bz : 0;  // window plane visited first
+      const int total = nxy * nz;
+      for (int base = 0; base < total && !hit;)
       {
-        float val[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++)
+        const int span = base == 0 ? nxy : 32 * 8;  // first round: one plane (<= 2 loads per lane with the default window)
+        const int end = min(base + span, total);
+        for (int b0 = base; b0 < end && !hit; b0 += 32 * 8)
         {
-          const int t = base + q * 32 + (int)lane;
-          val[q] = __int_as_float(0xff800000);
-          if (t < total)
-          {
-            const long long ci = cell_index(g, bx + t % nx, by + (t / nx) % ny, bz + t / (nx * ny));
-            if (ci >= 0)
-              val[q] = score[ci];
-          }
-        }
-        bool h = false;
+          float val[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-          if (val[q] > thr)
+          for (int q = 0; q < 8; q++)
           {
-            const int t = base + q * 32 + (int)lane;
-            const int ddx = bx + t % nx - ox, ddy = by + (t / nx) % ny - oy, ddz = bz + t / (nx * ny) - oz;
-            // Eigen int-vector norm(): int(sqrt(d2)) <= md; the integer square root of d2 <= 3*mv^2 is exact in fp32 too
-            const int nrm = (int)sqrtf((float)(ddx * ddx + ddy * ddy + ddz * ddz));
-            h = h || (float)nrm <= md;
+            const int t = b0 + q * 32 + (int)lane;
+            val[q] = __int_as_float(0xff800000);
+            if (t < end)
+            {
+              const int zr = t / nxy, rem = t - zr * nxy;
+              const int zi = zr == 0 ? zown : (zr <= zown ? zr - 1 : zr);
+              const long long ci = cell_index(g, bx + rem % nx, by + rem / nx, bz + zi);
+              if (ci >= 0)
+                val[q] = score[ci];
+            }
           }
-        hit = __any_sync(VOFOD_FULL, h);
+          bool h = false;
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            if (val[q] > thr)
+            {
+              const int t = b0 + q * 32 + (int)lane;
+              const int zr = t / nxy, rem = t - zr * nxy;
+              const int zi = zr == 0 ? zown : (zr <= zown ? zr - 1 : zr);
+              const int ddx = bx + rem % nx - ox, ddy = by + rem / nx - oy, ddz = bz + zi - oz;
+              // Eigen int-vector norm(): int(sqrt(d2)) <= md; the integer square root of d2 <= 3*mv^2 is exact in fp32 too
+              const int nrm = (int)sqrtf((float)(ddx * ddx + ddy * ddy + ddz * ddz));
+              h = h || (float)nrm <= md;
+            }
+          hit = __any_sync(VOFOD_FULL, h);
+        }
+        base = end;
       }
     }
     if (lane == 0)

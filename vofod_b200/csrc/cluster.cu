@@ -9,6 +9,9 @@
 //   K5b roots + atomicMin of the point index per root; K5c labels[i] = min index of i's component (the canonical label),
 //       per-label sizes, number of components
 // Linked-list order is scheduling dependent; the partition and the labels are not.
+// That is the GENERIC path (arbitrary points: staged vofod_cluster, sepclusters outside its fast path).  The two clusterings
+// a scan runs by default work on GRID CELLS and use run-based connected components on occupancy words instead (further
+// down: k_cg_union for sepclusters' 26-connectivity, k_runs_union for the voxel list with the reference's tolerance).
 #include <math.h>
 
 #include "common.cuh"

@@ -1,7 +1,8 @@
 // Per-scan orchestration of libvofod_cuda: the L3 functions of the nodelet (vofod_nodelet.cpp:581-613, 703-815,
 // 882-964) as device stages, and vofod_process_scan, which enqueues a whole scan of the deterministic schedule S1
 // on the context's stream with every count kept in DEVICE memory (no host round trip between stages) and reads
-// the results back once at the end.
+// the results back once at the end.  enqueue_scan is the launch sequence that gets captured into the scan's CUDA graph:
+// a main chain and two side branches (streams 2 and 3) for the work that does not depend on it.
 #include <math.h>
 
 #include "common.cuh"

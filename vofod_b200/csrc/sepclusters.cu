@@ -1,9 +1,12 @@
 // updateSeparatedBGClusters (vofod_nodelet.cpp:1126-1278) on the GPU: the background thread's pass that finds
 // background voxels which are NOT attached to a large "sure" background body and decays them towards the ray score.
 //
+// General path (any max_bg_distance / voxel_size):
 //   compaction of voxels > new_obstacles in the reference's x-outer/z-inner order (K11, ctx.cu)
 //   -> VoxelGridCounted (voxelgrid.cu, incl. its input-slice quirk) -> Euclidean clustering in index units (cluster.cu)
 //   -> per-cluster sum of sure counts -> decay scatter (K12).
+// Fast path (the default geometry, leaf size 1 — see below): occupancy masks + popcount scan instead of compaction and sort,
+//   26-connectivity run against run instead of the spatial hash, sure counts per union-find root.
 // The reference applies map = w1*map + w2*ray sequentially, so a cell hit by several (voxel, offset) pairs is
 // updated several times; every application is the SAME affine function, hence the result only depends on how
 // often a cell is hit: each hit is applied as one atomic CAS round and the outcome is bit-identical.

@@ -7,6 +7,9 @@
 //       index nor ijk (ijk is recovered from the key), and VoxelGridCounted's counts are prefix sums over the
 //       UNSORTED input (its slice quirk, voxel_grid_counted.cpp:185-187)
 //   K3  run heads -> exclusive scan -> unique keys + run starts -> voxel centre + count
+// The scan path (vf_filter_voxelize_dev) replaces K1c-K3 by a sort-free variant (k_vgh_count / popcount scan / k_vgh_emit,
+// see there) whenever the operation area bounds the key range; K2/K3 serve arbitrary clouds (staged entry points,
+// VoxelGridCounted of the sepclusters general path).
 #include <math.h>
 
 #include "common.cuh"

@@ -219,6 +219,12 @@ int vofod_voxel_grid_counted(vofod_ctx*, const vofod_xyzi* pts, size_t n, float 
 /* ---- A13: clusterCloud (vofod_nodelet.cpp:689-698; pcl::EuclideanClusterExtraction) ---------- */
 /* labels[i] = minimum point index of i's connected component under strict d^2 < tol^2 */
 int vofod_cluster(vofod_ctx*, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters);
+/* Host-only diagnostic (no device needed): the table the scan's own clustering works from.  Its points are centres of grid
+ * leaves, so "within the tolerance" is a property of the index offset (dx, dy, dz): for every forward row (dy, dz) listed,
+ * |dx| <= R is inside for sure, |dx| = R + 1 is decided by the fp32 distance when shell == 1 (exact squared distance == tol^2),
+ * and shell == 2 (R = -1) says that dx = 0 itself is such a border case; rows not listed are outside.  Returns the number of
+ * rows, or 0 when the neighbourhood needs more than 16 rows (the scan then clusters with the generic vofod_cluster path). */
+int vofod_cluster_grid_rows(float tolerance, float leaf, int8_t* dy, int8_t* dz, int8_t* R, int8_t* shell, int cap);
 
 /* ---- A14/A15: findCloseFarClusters (vofod_nodelet.cpp:703-750) -------------------------------- */
 int vofod_close_far(vofod_ctx*, const vofod_vox* pts, const int32_t* labels, size_t m,

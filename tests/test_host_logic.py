@@ -1,0 +1,71 @@
+"""Host-side logic of libvofod_cuda that needs no device (runs in the CPU tier)."""
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+from vofod_b200 import capi
+
+
+def _classes(tol, leaf):
+    """inside / border / outside of an index offset, straight from the definition (vofod_nodelet.cpp:689-698: strict
+    d^2 < tol^2 on fp32 centres): n * leaf^2 against float(tol^2); within 1e-4 relative the fp32 rounding of the centres decides."""
+    r2 = float(np.float32(float(tol) * float(tol)))
+    l2 = float(leaf) * float(leaf)
+
+    def cls(n):
+        v = n * l2
+        if abs(v - r2) <= 1e-4 * r2:
+            return 1
+        return 0 if v < r2 else 2
+    return cls
+
+
+@pytest.mark.parametrize("tol,leaf", [(1.5, 0.5), (1.0, 0.5), (0.8, 0.5), (1.2, 0.4), (0.75, 0.25), (1.5, 1.0)])
+def test_grid_clustering_row_table_equals_the_definition(tol, leaf):
+    rows = capi.cluster_grid_rows(tol, leaf)
+    assert rows, "these neighbourhoods fit the 16-row table"
+    table = {(dy, dz): (R, shell) for dy, dz, R, shell in rows}
+    assert len(table) == len(rows)
+    cls = _classes(tol, leaf)
+    m = int(math.ceil(tol / leaf)) + 2
+    for dx, dy, dz in itertools.product(range(-m, m + 1), repeat=3):
+        forward = dz > 0 or (dz == 0 and dy > 0) or (dz == 0 and dy == 0 and dx > 0)
+        if not forward:
+            continue
+        want = cls(dx * dx + dy * dy + dz * dz)
+        if (dy, dz) not in table:
+            got = 2
+        else:
+            R, shell = table[(dy, dz)]
+            if shell == 2:
+                got = 1 if dx == 0 else 2
+            elif abs(dx) <= R:
+                got = 0
+            elif shell == 1 and abs(dx) == R + 1:
+                got = 1
+            else:
+                got = 2
+        assert got == want, (dx, dy, dz, got, want)
+
+
+def test_grid_clustering_declines_what_it_cannot_cover():
+    assert capi.cluster_grid_rows(1.5, 0.25) == []      # 57 forward rows: generic spatial-hash clustering
+    assert capi.cluster_grid_rows(2.0, 0.5) == []       # 4 leaves: more than 16 rows as well
+    assert capi.cluster_grid_rows(0.5, 0.5) == []       # tolerance not above the leaf size
+    assert capi.cluster_grid_rows(0.0, 0.5) == []
+
+
+def test_default_geometry_table():
+    """1.5 m / 0.5 m (config/detection_params.yaml): 15 rows, border cases exactly the offsets of squared length 9."""
+    rows = capi.cluster_grid_rows(1.5, 0.5)
+    assert len(rows) == 15
+    border = set()
+    for dy, dz, R, shell in rows:
+        if shell == 1:
+            border.add((R + 1, abs(dy), dz))
+        if shell == 2:
+            border.add((0, abs(dy), dz))
+    assert all(dx * dx + dy * dy + dz * dz == 9 for dx, dy, dz in border)
+    assert border == {(3, 0, 0), (0, 3, 0), (0, 0, 3), (2, 2, 1), (2, 1, 2), (1, 2, 2)}

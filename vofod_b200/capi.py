@@ -17,6 +17,14 @@ LIB_PATH = os.path.join(_HERE, "libvofod_cuda.so")
 _lib = None
 
 
+def cluster_grid_rows(tolerance, leaf, lib=None):
+    """Host-only: [(dy, dz, R, shell)] of the scan's grid clustering for a tolerance / leaf pair ([] = generic path)."""
+    lib = lib or load_library()
+    arr = [np.zeros(16, dtype=np.int8) for _ in range(4)]
+    n = lib.vofod_cluster_grid_rows(float(tolerance), float(leaf), _p(arr[0]), _p(arr[1]), _p(arr[2]), _p(arr[3]), 16)
+    return [tuple(int(a[i]) for a in arr) for i in range(n)]
+
+
 class VofodError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libvofod_cuda error {code}: {msg}")
@@ -61,6 +69,7 @@ def load_library():
         "vofod_voxel_grid_weighted": (i32, [vp, vp, sz, f32, vp, vp, sz, P(sz)]),
         "vofod_voxel_grid_counted": (i32, [vp, vp, sz, f32, f32, vp, vp, sz, P(sz)]),
         "vofod_cluster": (i32, [vp, vp, sz, f32, vp, P(sz)]),
+        "vofod_cluster_grid_rows": (i32, [f32, f32, vp, vp, vp, vp, i32]),
         "vofod_close_far": (i32, [vp, vp, vp, sz, P(Params), vp, P(C.c_uint64)]),
         "vofod_range_update": (i32, [vp, vp, P(Params)]),
         "vofod_update_points": (i32, [vp, vp, vp, i32, sz, f32, f32]),

@@ -658,6 +658,21 @@ int vf_cluster_runs_dev(vofod_ctx* ctx, ClusterWs& ws, const uint32_t* d_cellkey
   return 0;
 }
 
+extern "C" int vofod_cluster_grid_rows(float tolerance, float leaf, int8_t* dy, int8_t* dz, int8_t* R, int8_t* shell, int cap)
+{
+  RunRows rr;
+  if (!vf_run_rows(tolerance, leaf, rr) || rr.n > cap)
+    return 0;
+  for (int i = 0; i < rr.n; i++)
+  {
+    if (dy) dy[i] = rr.dy[i];
+    if (dz) dz[i] = rr.dz[i];
+    if (R) R[i] = rr.R[i];
+    if (shell) shell[i] = rr.shell[i];
+  }
+  return rr.n;
+}
+
 extern "C" int vofod_cluster(vofod_ctx* ctx, const float* xyz, size_t m, float tol, int32_t* labels, size_t* n_clusters)
 {
   if (!ctx)

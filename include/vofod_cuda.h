@@ -310,6 +310,8 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 #define VOFOD_OPT_RAYCAST_BLOCK 5  /* tuning: rays per thread block of the raycast accumulate kernel: 64 (default), 128 or 256 */
 #define VOFOD_OPT_OVERLAP 4        /* default 1: independent stages run as parallel branches of the scan graph */
 #define VOFOD_OPT_SEP_GENERAL 3    /* test switch (default 0): sepclusters never takes its leaf-size-1 fast path */
+#define VOFOD_OPT_SEP_CAP 9        /* test switch (default 0 = automatic): fixed capacity of the background-voxel list of the capture-friendly sepclusters
+                                      pass; a list that overflows leaves the map untouched and the pass is redone exactly */
 #define VOFOD_OPT_CLUSTER_HASH 8   /* test switch (default 0): the scan path clusters with the generic spatial-hash clustering */
 #define VOFOD_OPT_VG_SORT 7        /* test switch (default 0): the scan path voxelizes with the generic sort-based voxel grid */
 #define VOFOD_OPT_PDL 6            /* default 1: consecutive kernels are chained by programmatic dependent launch */

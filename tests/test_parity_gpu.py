@@ -355,6 +355,21 @@ def test_scan_path_clustering_spatial_hash_variant(gpu, cpu):
         gpu.set_option(abi.OPT_CLUSTER_HASH, 0)
 
 
+def test_sepclusters_list_overflow_is_redone_exactly(gpu, cpu):
+    """Under graph replay the background-voxel list of sepclusters has a capacity instead of a host round trip.  With the
+    capacity forced far below the number of background voxels every pass overflows: it must leave the map untouched (and
+    stay inside its buffers), and the exact re-run must give the reference's result."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    gpu.set_option(abi.OPT_SEP_CAP, 64)
+    try:
+        _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 16), fixed=True)
+        assert gpu.process_scan(*sensor.scan(0, 16)[:2], p, abi.schedule_s1(sensor.scan(0, 16)[2]))[0].n_bg > 64
+    finally:
+        gpu.set_option(abi.OPT_SEP_CAP, 0)
+
+
 def test_sepclusters_general_path_and_leaf2(gpu, cpu):
     """The separated-background-cluster pass outside its leaf-size-1 fast path: forced general path (compaction ->
     VoxelGridCounted radix sort), and max_bg_distance 1.2 m (ceil(2.4) = 3 -> leaf size 2, 125-offset ball)."""

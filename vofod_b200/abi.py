@@ -195,4 +195,5 @@ OPT_GRAPH = 1
 OPT_PDL = 6
 OPT_VG_SORT = 7
 OPT_CLUSTER_HASH = 8
+OPT_SEP_CAP = 9
 OPT_SEP_GENERAL = 3

@@ -348,6 +348,7 @@ struct vofod_ctx
   uint64_t graph_kernels = 0;
   uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;
   int stat_last_capture_error = 0;  // 1 enqueue failed, 2 EndCapture failed, 3 buffer growth during capture, 4 instantiate failed, 5 BeginCapture failed
+  size_t sep_cap_forced = 0;  // VOFOD_OPT_SEP_CAP
   size_t sep_cap = 0;         // capacity of the background-voxel list when sepclusters runs without a host round trip
 
   // clustering / per-scan products

@@ -239,6 +239,13 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->alloc_gen++;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_SEP_CAP)
+  {
+    ctx->sep_cap_forced = value > 0 ? (size_t)value : 0;
+    ctx->sep_cap = ctx->sep_cap_forced;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_CLUSTER_HASH)
   {
     ctx->cl_force_hash = value != 0;

@@ -803,7 +803,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   cudaStream_t st = ctx->stream;
-  ScanPlan plan;
+  ScanPlan plan = {};
   plan.n = n;
   plan.p = p;
   plan.s = s;
@@ -852,6 +852,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (graph_ok && ctx->graph_exec && ctx->graph_sig == sig)
   {
     // ---- replay
+    plan.sep_cap = ctx->sep_cap;  // the capacity the captured pass runs with: the overflow check below needs it
     ctx->epoch_calls++;
     ctx->stat_replays++;
     CK(cudaGraphLaunch(ctx->graph_exec, st));
@@ -976,7 +977,9 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     }
     // keep the list far larger than what the map currently holds: a change of capacity re-allocates and re-captures the graph
     // (two kernel-by-kernel scans + one capture), which must stay a rare event while the map is being explored
-    if (K * 5 / 4 + 1024 > ctx->sep_cap)
+    if (ctx->sep_cap_forced)
+      ctx->sep_cap = ctx->sep_cap_forced;  // test switch: keeps the overflow-and-redo path in use
+    else if (K * 5 / 4 + 1024 > ctx->sep_cap)
       ctx->sep_cap = K * 4 + (size_t(1) << 20);
     // the clustering hash table is sized (and memset) for the points expected, not for the list capacity
     // (a growth re-allocates the table and re-captures the graph: a multi-millisecond hiccup, so start roomy and grow 4x)

@@ -239,7 +239,8 @@ __global__ void k_vg_layout(const MinMax* __restrict__ mm, const float leaf, con
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pts, const MinMax* mm, const float leaf, const float ac0, const float ac1,
                                                    const float ac2, VgLayout* Lout, unsigned long long* counters, const int slot_nvalid, const int slot_overflow,
-                                                   const unsigned long long budget_cells, uint32_t* __restrict__ cnt, uint32_t* __restrict__ bits)
+                                                   const int budget_x, const int budget_y, const int budget_z, uint32_t* __restrict__ cnt,
+                                                   uint32_t* __restrict__ bits)
 {
   pdl_enter();
   __shared__ VgLayout sL;
@@ -247,8 +248,7 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
   {
     VgLayout l;
     vg_layout_compute(mm, leaf, 1, ac0, ac1, ac2, l);
-    const unsigned long long cells = (unsigned long long)l.div[0] * (unsigned long long)l.div[1] * (unsigned long long)l.div[2];
-    if (cells > budget_cells)
+    if (l.div[0] > budget_x || l.div[1] > budget_y || l.div[2] > budget_z)
       l.overflow = 1;  // cannot happen for points cropped to the operation area the budget was derived from
     sL = l;
     if (blockIdx.x == 0)
@@ -547,9 +547,14 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p, bool
   }
   // the crop to the operation area bounds the key range: div <= size/leaf + 3 per axis
   unsigned long long cells = 1;
+  int budget[3];
   for (int k = 0; k < 3; k++)
-    cells *= (unsigned long long)(ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0);
-  const int bits = cells + 1 < (1ull << 31) ? bits_for(cells + 1) : 32;
+  {
+    const double d = ceil((double)p.oparea_size[k] / (double)g.vs) + 3.0;
+    budget[k] = d < 2147483647.0 ? (int)d : 2147483647;
+    cells = (d < 2097152.0 && cells < (1ull << 42)) ? cells * (unsigned long long)d : ~0ull;  // (saturates instead of wrapping)
+  }
+  const int bits = cells < (1ull << 31) - 1 ? bits_for(cells + 1) : 32;
   if (!ctx->vg_force_sort && cells < (1ull << 31) && cells * 4 <= (size_t(8) << 30))
   {
     // sort-free path: dense counts + occupancy words over the key range the crop allows
@@ -566,7 +571,7 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p, bool
     unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
     VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
     LAUNCH(k_vgh_count, vf_blocks(ctx, n, 256, 8), 256, 0, ctx->vg_pts.as<float4>(), mm, g.vs, ac[0], ac[1], ac[2], L, cnt, (int)CNT_VG_NVALID, (int)CNT_VG_OVERFLOW,
-           cells, ctx->vgh_cnt.as<uint32_t>(), ctx->vgh_bits.as<uint32_t>());
+           budget[0], budget[1], budget[2], ctx->vgh_cnt.as<uint32_t>(), ctx->vgh_bits.as<uint32_t>());
     // a word holds at least one of the n points
     const size_t list_cap = n < words_cap ? n : words_cap;
     ENSURE(ctx->vgh_list, (list_cap + 1) * sizeof(uint4));

@@ -261,7 +261,7 @@ def run_ours(args):
             "gvoxel_traversals_per_s_full_path": trav_all / (total_ms * 1e-3) / 1e9,
             "traversals_per_scan": trav_per_launch,
             "e2e": {"value": world * K / (total_ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize,
-                    "d2h_bytes_per_step": 64 * 8 + 16 * abi.DETECTION_DTYPE.itemsize, "ms_per_step": total_ms_e2e / K},
+                    "d2h_bytes_per_step": 64 * 8, "ms_per_step": total_ms_e2e / K},  # the 64 result counters; detection records (168 B each) follow only when a scan has detections
             "single_bracket": {"note": "one event pair around all K steps of each leg: includes the 256 MB L2-flush write per step and the host time "
                                        "between two synchronous calls, which the per-step events leave out",
                                "value": world * K / (whole_ms_max * 1e-3), "e2e": world * K / (whole_e2e_ms_max * 1e-3), "unit": "scans/s"},

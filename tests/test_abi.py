@@ -98,3 +98,15 @@ def test_no_global_access_before_the_dependency_wait():
     import check_pdl_sass
     n, bad = check_pdl_sass.check()
     assert n >= 58 and not bad, bad
+
+
+def test_option_constants_match_the_header():
+    """abi.OPT_* mirror the VOFOD_OPT_* switches of include/vofod_cuda.h."""
+    from vofod_b200 import abi
+    text = open(os.path.join(ROOT, "include", "vofod_cuda.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+VOFOD_OPT_(\w+)\s+(\d+)", text)}
+    assert len(set(defs.values())) == len(defs)                      # no two switches share a number
+    mirrored = {k[4:]: v for k, v in vars(abi).items() if k.startswith("OPT_")}
+    assert mirrored, "abi.py mirrors at least the switches the tests use"
+    for name, value in mirrored.items():
+        assert defs.get(name) == value, (name, value, defs.get(name))

@@ -316,7 +316,12 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 #define VOFOD_OPT_VG_SORT 7        /* test switch (default 0): the scan path voxelizes with the generic sort-based voxel grid */
 #define VOFOD_OPT_PDL 6            /* default 1: consecutive kernels are chained by programmatic dependent launch */
 #define VOFOD_OPT_RAYCAST_NO_AGG 2 /* tuning switch (default 0): one RED per traversal instead of warp-aggregated REDs */
+#define VOFOD_OPT_RAYCAST_STATS 10 /* instrumentation switch (default 0): the accumulate kernel also fills per warp-step histograms, see vofod_raycast_stats */
 int vofod_set_option(vofod_ctx*, int option, int value);
+/* VOFOD_OPT_RAYCAST_STATS: out[0..32] = warp-steps with that many lanes (rays) in the loop, out[33..65] = warp-steps with that many distinct
+ * voxels (= REDs issued), out[66] / out[67] = warp-steps of the fast / general loop, out[68] = DDA steps skipped by the slab fast-forward;
+ * accumulated since the last call (the call resets them).  n <= 72. */
+int vofod_raycast_stats(vofod_ctx*, uint64_t* out, size_t n);
 /* scan-replay statistics: which = 0 graph replays, 1 captures, 2 failed captures, 3 kernel-by-kernel scans, 4 reason code of the last failed capture */
 uint64_t vofod_get_stat(const vofod_ctx*, int which);
 /* raw CUDA stream handle (cudaStream_t) the context enqueues on, for event timing by the caller */

@@ -197,3 +197,7 @@ OPT_VG_SORT = 7
 OPT_CLUSTER_HASH = 8
 OPT_SEP_CAP = 9
 OPT_SEP_GENERAL = 3
+OPT_RAYCAST_STATS = 10
+OPT_RAYCAST_NO_AGG = 2
+OPT_RAYCAST_BLOCK = 5
+OPT_OVERLAP = 4

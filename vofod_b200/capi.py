@@ -77,6 +77,7 @@ def load_library():
         "vofod_raycast_download": (i32, [vp, vp, vp, sz]),
         "vofod_raycast_apply": (i32, [vp, i32, P(Params)]),
         "vofod_raycast_frac_bits": (i32, [vp]),
+        "vofod_raycast_stats": (i32, [vp, vp, sz]),
         "vofod_classify_detect": (i32, [vp, vp, vp, vp, sz, P(Pose), P(Params), vp, sz, P(sz), vp, sz, P(sz)]),
         "vofod_sepclusters": (i32, [vp, i32, P(Params), P(i32)]),
         "vofod_state_get": (i32, [vp, P(i32), P(i32), P(C.c_uint32)]),
@@ -323,6 +324,12 @@ class Vofod:
 
     def raycast_frac_bits(self):
         return int(self.lib.vofod_raycast_frac_bits(self.h))
+
+    def raycast_stats(self):
+        """VOFOD_OPT_RAYCAST_STATS histograms accumulated since the last call: (lanes[33], groups[33], fast, general, skipped)"""
+        out = np.zeros(72, dtype=np.uint64)
+        self._ck(self.lib.vofod_raycast_stats(self.h, _p(out), 72))
+        return out[:33].copy(), out[33:66].copy(), int(out[66]), int(out[67]), int(out[68])
 
     def raycast_apply(self, its_diff, params):
         return self._ck(self.lib.vofod_raycast_apply(self.h, int(its_diff), C.byref(params)))

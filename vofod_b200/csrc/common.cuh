@@ -335,6 +335,8 @@ struct vofod_ctx
   int slab_raycast_status = 0;
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
+  bool raycast_stats = false;   // instrumentation switch: the accumulate kernel fills ray_stats (see RAY_STATS_SLOTS in raycast.cu)
+  DevBuf ray_stats;
   bool pdl_enabled = true;      // programmatic dependent launch between consecutive kernels (see LAUNCH)
   bool pdl_in_graph = false;    // experiment switch (VOFOD_OPT_PDL = 2): keep the attribute under stream capture too
   bool pdl_chain = false;       // the last operation put on ctx->stream was a kernel launch of this library

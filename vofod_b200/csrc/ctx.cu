@@ -157,7 +157,7 @@ int vofod_destroy(vofod_ctx* ctx)
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
                     &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_d,
                     &ctx->sep_colcnt, &ctx->sep_coloff, &ctx->sep_raw, &ctx->sep_ds, &ctx->sep_labels, &ctx->sep_nsure, &ctx->sep_offsets, &ctx->sep_segcnt, &ctx->sep_segoff, &ctx->sep_live, &ctx->sep_unsure,
-                    &ctx->cls_sizes, &ctx->cls_maxidx, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms};
+                    &ctx->cls_sizes, &ctx->cls_maxidx, &ctx->cls_seg, &ctx->cls_okeys_a, &ctx->cls_okeys_b, &ctx->cls_queues, &ctx->cls_terms, &ctx->ray_stats};
   for (DevBuf* b : bufs)
     free_buf(*b);
   for (int i = 0; i < VOFOD_SCAN_SLOTS; i++)
@@ -261,6 +261,12 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
   if (option == VOFOD_OPT_SEP_GENERAL)
   {
     ctx->sep_force_general = value != 0;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_RAYCAST_STATS)
+  {
+    ctx->raycast_stats = value != 0;
     ctx->alloc_gen++;
     return VOFOD_OK;
   }

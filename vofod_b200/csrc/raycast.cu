@@ -31,12 +31,162 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsi
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 
+// ---- per-ray DDA state (voxel_map.cpp:229-263) --------------------------------------------------------------------
+struct RayState
+{
+  float len, prev;
+  float tmx, tmy, tmz, tdx, tdy, tdz;
+  int remx, remy, remz;  // steps left before the ray stands in the last voxel of the map along that axis (`cur[i] == last[i]`)
+  int dwx, dwy, dwz;     // window-index stride of one step along each axis
+  int widx;
+  int spos, sstep;       // SLAB: window coordinate / step along the slab axis (the only axis a ray can leave the window on)
+};
+
+// instrumentation (VOFOD_OPT_RAYCAST_STATS): per warp-step histograms of the lanes in the loop and of the distinct voxels among them
+#define RAY_STATS_SLOTS 72  // [0..32] lanes alive, [33..65] groups, [66] warp-steps of the fast loop, [67] of the general loop, [68] skipped steps
+template <bool STATS>
+__device__ __forceinline__ void ray_stats(unsigned long long* stats, const unsigned am, const bool leader, const int loop_slot)
+{
+  if (STATS)
+  {
+    const unsigned lead = __ballot_sync(am, leader);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(am) - 1))
+    {
+      atomicAdd(stats + __popc(am), 1ull);
+      atomicAdd(stats + 33 + __popc(lead), 1ull);
+      atomicAdd(stats + loop_slot, 1ull);
+    }
+  }
+}
+
+// One lane = one ray; the lanes that are in the loop together (__activemask) merge their updates: lanes standing in the same
+// voxel issue ONE 64-bit RED (count in the top 20 bits, path length below).  No warp-wide vote per step: lanes whose ray has
+// ended simply leave the loop, and if the hardware ever splits the warp the only effect is less merging — additions commute.
+//  FAST  = every ray of the warp provably ends by its length before it can reach the last voxel of the map along any axis
+//          (and, unsharded, stays inside the accumulator window): no countdown, no clamp.  With SLAB the ray also stops at the
+//          first step that leaves the slab's window along the slab axis (it never comes back).
+//  !FAST = the reference's loop with the `cur[i] == last[i]` countdown; with SLAB, steps outside the window are walked but not
+//          written.
+template <bool AGG, bool SLAB, bool FAST, bool STATS>
+__device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const float scale, const int slab_axis, const int ssize, const int own_lo, const int own_n,
+                                             const int wn, unsigned long long* __restrict__ acc, const unsigned lane, const unsigned lanemask_lt,
+                                             unsigned long long* stats)
+{
+  unsigned steps = 0;
+  while (alive)
+  {
+    // tmax.minCoeff(&i): first minimum, strict '<'
+    const bool use_y = r.tmy < r.tmx;
+    const float d01 = use_y ? r.tmy : r.tmx;
+    const bool use_z = r.tmz < d01;
+    const float dist = use_z ? r.tmz : d01;
+    const float ddist = (r.len < dist ? r.len : dist) - r.prev;                               // voxel_map.cpp:252
+    const int q = __float2int_rn(ddist * scale);
+    int key;
+    bool inside = true;
+    if (FAST)
+      key = r.widx;  // inside the window by construction (see the classification in the kernel)
+    else if (SLAB)
+    {
+      // the window is cut at the slab's storage box: rays enter and leave it along the slab axis
+      inside = (unsigned)r.spos < (unsigned)ssize;
+      key = inside ? r.widx : -1 - (int)lane;
+    } else
+      // the window holds every voxel within max_dist, so this clamp never bites; if it ever did, the update would land in the
+      // spare cell behind the window (and the apply kernel reports it) instead of corrupting memory
+      key = (int)min((unsigned)r.widx, (unsigned)wn);
+    if (AGG)
+    {
+      const unsigned am = __activemask();
+      const unsigned m = __match_any_sync(am, key);
+      const int sum = __reduce_add_sync(m, q);
+      const bool leader = (m & lanemask_lt) == 0;
+      if (inside && leader)
+        red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+      ray_stats<STATS>(stats, am, leader, FAST ? 66 : 67);
+    } else if (inside)
+      red_add_u64(acc + key, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
+    // SLAB: windows of neighbouring slabs overlap in the halos; a traversal is counted by the slab that OWNS the voxel, so that the
+    // counts of all slabs add up to the reference's
+    steps += SLAB ? ((unsigned)(r.spos - own_lo) < (unsigned)own_n ? 1u : 0u) : 1u;
+    r.prev = dist;
+    // voxel_map.cpp:257-261
+    if (FAST)
+      alive = dist < r.len;
+    else
+    {
+      const int rem = use_z ? r.remz : (use_y ? r.remy : r.remx);
+      alive = rem != 0 && dist < r.len;
+    }
+    if (use_z)
+    {
+      r.tmz += r.tdz; r.widx += r.dwz;
+      if (!FAST) r.remz--;
+      if (SLAB && slab_axis == 2) r.spos += r.sstep;
+    } else if (use_y)
+    {
+      r.tmy += r.tdy; r.widx += r.dwy;
+      if (!FAST) r.remy--;
+      if (SLAB && slab_axis == 1) r.spos += r.sstep;
+    } else
+    {
+      r.tmx += r.tdx; r.widx += r.dwx;
+      if (!FAST) r.remx--;
+      if (SLAB && slab_axis == 0) r.spos += r.sstep;
+    }
+    if (SLAB && FAST)
+      alive = alive && (unsigned)r.spos < (unsigned)ssize;
+  }
+  return steps;
+}
+
+// SLAB + FAST: bring the DDA of a ray that starts outside the slab's window to the state it has when it enters, WITHOUT walking
+// the voxels in between.  The DDA is a 3-way merge of the increasing sequences tm_a + j*td_a (each built by the same chain of
+// fp32 additions the loop performs) with ties going to x before y before z (first minimum).  The ka-th step along the slab axis
+// consumes T = tm_a after ka-1 additions; a step along another axis b comes before it iff its value is < T, or == T when b has
+// priority over the slab axis.  The state after that step is therefore: tm_a = T + td_a, prev = T, every other axis advanced past
+// T.  Bit-identical to walking (same additions in the same order per axis); the ray enters iff T < len.
+// Returns false when the ray never enters the window.
+__device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axis, const int ssize, unsigned& skipped)
+{
+  if ((unsigned)r.spos < (unsigned)ssize)
+    return true;
+  const int ka = r.spos < 0 ? (r.sstep > 0 ? -r.spos : 0) : (r.sstep < 0 ? r.spos - (ssize - 1) : 0);
+  if (ka <= 0)
+    return false;  // parallel to the slab or heading away from it
+  float& tma = slab_axis == 0 ? r.tmx : r.tmy;
+  const float tda = slab_axis == 0 ? r.tdx : r.tdy;
+  // the slab axis takes at most len/td_a + 1 steps before the ray ends
+  if ((float)(ka - 2) * tda >= r.len)
+    return false;
+  float T = tma;
+  for (int j = 1; j < ka; j++)
+    T += tda;
+  if (!(T < r.len))
+    return false;
+  tma = T + tda;
+  r.prev = T;
+  r.spos += ka * r.sstep;
+  r.widx += ka * (slab_axis == 0 ? r.dwx : r.dwy);
+  skipped += (unsigned)ka;
+  if (slab_axis == 0)
+  {
+    while (r.tmy < T) { r.tmy += r.tdy; r.widx += r.dwy; skipped++; }   // x has priority over y and z on ties
+  } else
+  {
+    while (r.tmx <= T) { r.tmx += r.tdx; r.widx += r.dwx; skipped++; }  // x has priority over y
+  }
+  while (r.tmz < T) { r.tmz += r.tdz; r.widx += r.dwz; skipped++; }
+  return true;
+}
+
 // RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
-// returns a few metres), so small blocks balance better: 128 threads = 4 warps = 128 neighbouring columns of one row.
-template <int RB, bool AGG, bool SLAB>
+// returns a few metres), so small blocks balance better: 64 threads = 2 warps = 64 neighbouring columns of one row.
+template <int RB, bool AGG, bool SLAB, bool STATS>
 __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
-                                                           unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters)
+                                                           unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters,
+                                                           unsigned long long* __restrict__ stats)
 {
   pdl_enter();
   // stage this block's packed points (20 B each) through shared memory with coalesced 16 B loads
@@ -60,14 +210,12 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
 
   const int idx = blk_first + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
+  const unsigned lanemask_lt = (1u << lane) - 1u;
   bool alive = idx < a.n;
-  float len = 0.f;
-  float tmx = 0.f, tmy = 0.f, tmz = 0.f, tdx = 0.f, tdy = 0.f, tdz = 0.f;
-  int remx = 0, remy = 0, remz = 0;  // steps left before the ray stands in the last voxel of the map along that axis
-  int dwx = 0, dwy = 0, dwz = 0;     // window-index stride of one step along each axis
-  int widx = 0;
-  int spos = 0, sstep = 0;  // SLAB: window coordinate / step along the slab axis (the only axis a ray can leave the window on)
-  const int ssize = w.size[a.g.slab_axis];
+  bool safe = true;
+  RayState r = {};
+  const int slab_axis = a.g.slab_axis;
+  const int ssize = w.size[slab_axis];
   const int wn = w.size[0] * w.size[1] * w.size[2];
   if (alive)
   {
@@ -83,7 +231,7 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
     const float dz = tf.R[6] * d1.x + (tf.R[7] * d1.y + tf.R[8] * d1.z);
     const float ray_dist = 0.001f * (float)range;                                             // :1456
     const float dmv = ray_dist - a.g.vs;
-    len = ray_dist == 0.0f ? a.max_dist : (a.max_dist < dmv ? a.max_dist : dmv);              // :1457 (std::min)
+    r.len = ray_dist == 0.0f ? a.max_dist : (a.max_dist < dmv ? a.max_dist : dmv);            // :1457 (std::min)
     float sx = tf.t[0], sy = tf.t[1], sz = tf.t[2];
     if (a.has_off)
     {
@@ -102,114 +250,69 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
     const int stx = (dx > 0.0f) - (dx < 0.0f);
     const int sty = (dy > 0.0f) - (dy < 0.0f);
     const int stz = (dz > 0.0f) - (dz < 0.0f);
-    tdx = (1.0f / ax) * a.g.vs;
-    tdy = (1.0f / ay) * a.g.vs;
-    tdz = (1.0f / az) * a.g.vs;
+    r.tdx = (1.0f / ax) * a.g.vs;
+    r.tdy = (1.0f / ay) * a.g.vs;
+    r.tdz = (1.0f / az) * a.g.vs;
     const float ox = idx_to_coord1(cx, a.g.off[0], a.g.vs) - sx;
     const float oy = idx_to_coord1(cy, a.g.off[1], a.g.vs) - sy;
     const float oz = idx_to_coord1(cz, a.g.off[2], a.g.vs) - sz;
-    tmx = (a.g.half + (float)stx * ox) / ax;
-    tmy = (a.g.half + (float)sty * oy) / ay;
-    tmz = (a.g.half + (float)stz * oz) / az;
+    r.tmx = (a.g.half + (float)stx * ox) / ax;
+    r.tmy = (a.g.half + (float)sty * oy) / ay;
+    r.tmz = (a.g.half + (float)stz * oz) / az;
     // `if (cur[i] == last[i]) break` with last = step > 0 ? size-1 : 0 (voxel_map.cpp:240-257), as a countdown
-    remx = stx > 0 ? a.g.size[0] - 1 - cx : cx;
-    remy = sty > 0 ? a.g.size[1] - 1 - cy : cy;
-    remz = stz > 0 ? a.g.size[2] - 1 - cz : cz;
-    dwx = stx;
-    dwy = sty * w.size[0];
-    dwz = stz * w.size[0] * w.size[1];
-    widx = (cx - w.lo[0]) + (cy - w.lo[1]) * w.size[0] + (cz - w.lo[2]) * w.size[0] * w.size[1];
+    r.remx = stx > 0 ? a.g.size[0] - 1 - cx : cx;
+    r.remy = sty > 0 ? a.g.size[1] - 1 - cy : cy;
+    r.remz = stz > 0 ? a.g.size[2] - 1 - cz : cz;
+    r.dwx = stx;
+    r.dwy = sty * w.size[0];
+    r.dwz = stz * w.size[0] * w.size[1];
+    r.widx = (cx - w.lo[0]) + (cy - w.lo[1]) * w.size[0] + (cz - w.lo[2]) * w.size[0] * w.size[1];
     if (SLAB)
     {
-      spos = a.g.slab_axis == 0 ? cx - w.lo[0] : (a.g.slab_axis == 1 ? cy - w.lo[1] : cz - w.lo[2]);
-      sstep = a.g.slab_axis == 0 ? stx : (a.g.slab_axis == 1 ? sty : stz);
+      r.spos = slab_axis == 0 ? cx - w.lo[0] : (slab_axis == 1 ? cy - w.lo[1] : cz - w.lo[2]);
+      r.sstep = slab_axis == 0 ? stx : (slab_axis == 1 ? sty : stz);
     }
-    if (!(0.0f < len))  // while (prev_dist < length) with prev_dist = 0
+    if (!(0.0f < r.len))  // while (prev_dist < length) with prev_dist = 0
       alive = false;
+    // An axis steps when its tmax (>= j * td, up to rounding) is below len: at most len*|d|/vs + 1 times.  With more than that
+    // (+1 for the rounding) to go before the last voxel of the map, the countdown of the reference's loop can never trigger.
+    const float li = r.len * a.g.inv;
+    safe = r.remx > (int)(li * ax) + 2 && r.remy > (int)(li * ay) + 2 && r.remz > (int)(li * az) + 2;
+    // (such a ray also stays inside the accumulator window: vf_raycast_prepare sizes it ceil(reach/vs) + 2 cells around the sensor
+    //  voxel, clamped to the held box — and a safe ray does not leave the map)
   }
-  float prev = 0.0f;
-  unsigned steps = 0;
-  unsigned oob = 0;
-  int orq = 0;  // OR of all quantised path lengths: non-zero <=> some callback carried a positive length <=> max_element(raycast) > 0 (:1542-1548)
-  // Every lane walks its own ray; the lanes that are in the loop together (__activemask) merge their updates.  No warp-wide
-  // vote per step: lanes whose ray has ended simply leave the loop, and if the hardware ever splits the warp the only effect
-  // is less merging — the additions commute.
-  while (alive)
-  {
-    // tmax.minCoeff(&i): first minimum, strict '<'
-    const bool use_y = tmy < tmx;
-    const float d01 = use_y ? tmy : tmx;
-    const bool use_z = tmz < d01;
-    const float dist = use_z ? tmz : d01;
-    const float ddist = (len < dist ? len : dist) - prev;                                     // voxel_map.cpp:252
-    const int q = __float2int_rn(ddist * a.scale);
-    int key;
-    bool inside = true;
-    if (SLAB)
-    {
-      // the window is cut at the slab's storage box: rays enter and leave it along the slab axis
-      inside = (unsigned)spos < (unsigned)ssize;
-      key = inside ? widx : -1 - (int)lane;
-    } else
-      // unsharded: the window holds every voxel within max_dist, so this clamp never bites; if it ever did, the update would
-      // land in the spare cell behind the window (and the apply kernel reports it) instead of corrupting memory
-      key = (int)min((unsigned)widx, (unsigned)wn);
-    if (AGG)
-    {
-      // lanes standing in the same voxel issue ONE 64-bit RED: count in the top 20 bits, path length below
-      const unsigned am = __activemask();
-      const unsigned m = __match_any_sync(am, key);
-      const int sum = __reduce_add_sync(m, q);
-      if (inside && lane == (unsigned)(__ffs(m) - 1))
-        red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
-    } else if (inside)
-      red_add_u64(acc + key, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
-    orq |= q;
-    steps++;
-    prev = dist;
-    // voxel_map.cpp:257-261
-    const int rem = use_z ? remz : (use_y ? remy : remx);
-    alive = rem != 0 && dist < len;
-    if (use_z)
-    {
-      remz--; tmz += tdz; widx += dwz;
-      if (SLAB && a.g.slab_axis == 2) spos += sstep;
-    } else if (use_y)
-    {
-      remy--; tmy += tdy; widx += dwy;
-      if (SLAB && a.g.slab_axis == 1) spos += sstep;
-    } else
-    {
-      remx--; tmx += tdx; widx += dwx;
-      if (SLAB && a.g.slab_axis == 0) spos += sstep;
-    }
-  }
-  __syncwarp();
-  const bool anyq = orq != 0;
-  if (__any_sync(VOFOD_FULL, anyq) && lane == 0)
+  unsigned steps = 0, skipped = 0;
+  const int own_lo = a.g.own_lo - w.lo[slab_axis], own_n = a.g.own_hi - a.g.own_lo;  // owned range in window coordinates along the slab axis
+  // SLAB: max_element(raycast) > 0 (:1542-1548) is a property of the WHOLE map, and a slab only sees its part of the rays' voxels.  Every
+  // slab runs this set-up for every ray, so "some ray is cast" is known to all of them without an exchange; it differs from the
+  // reference's test only when every cast ray is shorter than one quantum of the fixed-point length (2^-F m).
+  if (SLAB && __any_sync(VOFOD_FULL, alive) && lane == 0)
     atomicOr(counters + CNT_APPLY_ANY, 1ull);
+  // one decision per warp, so that the lanes of a warp stay in the same loop and keep merging
+  const bool fast = __all_sync(VOFOD_FULL, safe || !alive) && (!SLAB || slab_axis < 2);
+  if (fast)
+  {
+    if (SLAB && alive)
+      alive = ray_skip_to_slab(r, slab_axis, ssize, skipped);
+    steps = ray_loop<AGG, SLAB, true, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats);
+  } else
+    steps = ray_loop<AGG, SLAB, false, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats);
+  __syncwarp();
+  if (STATS && skipped)
+    atomicAdd(stats + 68, (unsigned long long)skipped);
   // per-block totals
   unsigned tot = prims::warp_sum(steps);
-  unsigned toob = prims::warp_sum(oob);
-  __shared__ unsigned s_tot[RB / 32], s_oob[RB / 32];
+  __shared__ unsigned s_tot[RB / 32];
   if (lane == 0)
-  {
     s_tot[threadIdx.x >> 5] = tot;
-    s_oob[threadIdx.x >> 5] = toob;
-  }
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    unsigned t = 0, o = 0;
+    unsigned t = 0;
     for (int i = 0; i < RB / 32; i++)
-    {
       t += s_tot[i];
-      o += s_oob[i];
-    }
     if (t)
       atomicAdd(counters + CNT_TRAVERSALS, (unsigned long long)t);
-    if (o)
-      atomicAdd(counters + CNT_OOB, (unsigned long long)o);
   }
 }
 
@@ -272,6 +375,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     if (max_val == 0.0f)
       return;  // :1544-1548 (the host also skips the flag clear)
   }
+  bool any_pos = false;  // max_element(raycast) > 0 (:1542-1548): some cell holds a positive length
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     const unsigned long long p = acc[i];
@@ -284,6 +388,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     const float rv = (float)((double)lq * a.inv_scale);
     if (!(rv > 0.0f))
       continue;
+    any_pos = true;
     const int wx = (int)(i % wsx), wy = (int)((i / wsx) % wsy), wz = (int)(i / ((long long)wsx * wsy));
     const long long ci = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
     if (ci < 0 || flags[ci] != 0)  // flag == m_vflags_unmarked (:1561)
@@ -306,6 +411,8 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     const float w2 = 1.0f - w1;
     score[ci] = w1 * m + w2 * a.ray_score;                            // :1569 / :1597
   }
+  if (__any_sync(VOFOD_FULL, any_pos) && (threadIdx.x & 31) == 0)
+    atomicOr(counters + CNT_APPLY_ANY, 1ull);
 }
 
 // m_voxel_flags.clear() (:1602) restricted to the cells flagged since the last clear; skipped when the apply was skipped
@@ -467,20 +574,29 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.n = (int)n;
   a.has_off = ctx->lut_has_off ? 1 : 0;
   const bool slab = ctx->slab_on;
-#define RAY_LAUNCH(RB_, AGG_, SLAB_)                                                                                                                         \
-  LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),               \
-         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt)
+  unsigned long long* stats = nullptr;
+  if (ctx->raycast_stats)
+  {
+    ENSURE(ctx->ray_stats, RAY_STATS_SLOTS * 8);
+    stats = ctx->ray_stats.as<unsigned long long>();
+  }
+#define RAY_LAUNCH(RB_, AGG_, SLAB_, STATS_)                                                                                                                 \
+  LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_, STATS_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),       \
+         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats)
   if (ctx->raycast_no_agg)
   {
-    if (slab) RAY_LAUNCH(128, false, true); else RAY_LAUNCH(128, false, false);
+    if (slab) RAY_LAUNCH(64, false, true, false); else RAY_LAUNCH(64, false, false, false);
+  } else if (stats)
+  {
+    if (slab) RAY_LAUNCH(64, true, true, true); else RAY_LAUNCH(64, true, false, true);
   } else if (slab)
-    RAY_LAUNCH(128, true, true);
-  else if (ctx->raycast_block == 64)
-    RAY_LAUNCH(64, true, false);
+    RAY_LAUNCH(64, true, true, false);
+  else if (ctx->raycast_block == 128)
+    RAY_LAUNCH(128, true, false, false);
   else if (ctx->raycast_block == 256)
-    RAY_LAUNCH(256, true, false);
+    RAY_LAUNCH(256, true, false, false);
   else
-    RAY_LAUNCH(128, true, false);
+    RAY_LAUNCH(64, true, false, false);
 #undef RAY_LAUNCH
   ctx->acc_has_data = true;
   return VOFOD_OK;
@@ -576,6 +692,22 @@ int vofod_raycast_accumulate(vofod_ctx* ctx, const vofod_pt* scan, size_t n, con
   if (t[1])
     return vf_fail(ctx, VOFOD_E_INTERNAL, "%llu traversals fell outside the accumulator window", t[1]);
   return rc;
+}
+
+int vofod_raycast_stats(vofod_ctx* ctx, uint64_t* out, size_t n)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (!out || n > RAY_STATS_SLOTS)
+    return vf_fail(ctx, VOFOD_E_INVALID, "vofod_raycast_stats: bad arguments");
+  memset(out, 0, n * 8);
+  if (!ctx->ray_stats.p)
+    return VOFOD_OK;
+  CK(cudaMemcpyAsync(out, ctx->ray_stats.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->ray_stats.p, 0, RAY_STATS_SLOTS * 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VOFOD_OK;
 }
 
 int vofod_raycast_download(vofod_ctx* ctx, uint32_t* counts, float* lengths, size_t n_cells)

@@ -519,8 +519,11 @@ def test_slab_mode_emulated_on_one_gpu(cpu):
                 results.append(g.slab_scan_end(p, s).as_dict())
             cpu.set_modes(True, True, slabs[0].raycast_frac_bits() or 24)
             want, _ = cpu.process_scan(scan, pose, p, s)
+            # a traversal is counted by the slab that owns the voxel: the slabs' counts add up to the reference's
+            wd = want.as_dict()
+            assert sum(r["n_traversals"] for r in results) == wd["n_traversals"], (k, [r["n_traversals"] for r in results], wd["n_traversals"])
             for r in results:
-                assert r == want.as_dict(), (k, r, want.as_dict())
+                assert dict(r, n_traversals=0) == dict(wd, n_traversals=0), (k, r, wd)
             full = cpu.map_download().reshape(sz, sy, sx)
             flags = cpu.map_download(abi.MAP_FLAGS).reshape(sz, sy, sx)
             for g in slabs:

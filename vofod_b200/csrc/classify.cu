@@ -447,12 +447,12 @@ __device__ bool explore_to_ground_block(const float* score, const Geom& g, const
     w.stamps[rel0] = epoch;
   }
   __syncthreads();
-  int cur = 0;
-  while (true)
+  // The loop decision is latched into registers between the two trailing barriers, where nobody writes sh[3] or the
+  // next queue's size: every thread of the block takes the same branch, so the barriers always pair up.
+  int cur = 0, qn = 1;
+  bool stop = false;
+  while (qn != 0 && !stop)
   {
-    const int qn = sh[cur];
-    if (qn == 0 || sh[3])
-      break;
     for (int t = tid; t < qn; t += blockDim.x)
     {
       const int rel = q[cur][t];
@@ -491,14 +491,14 @@ __device__ bool explore_to_ground_block(const float* score, const Geom& g, const
       }
     }
     __syncthreads();
+    stop = sh[3] != 0;
+    qn = sh[cur ^ 1];
     if (tid == 0)
       sh[cur] = 0;
     cur ^= 1;
     __syncthreads();
   }
-  const bool connected = sh[3] != 0;
-  __syncthreads();
-  return connected;
+  return stop;
 }
 
 // staged entry point (vofod_map_explore_to_ground): one exploration, NO write-back (the caller of the reference's

@@ -9,7 +9,8 @@ import os
 
 import numpy as np
 
-from vofod_b200.abi import VOX_DTYPE, XYZI_DTYPE, MapInfo
+from vofod_b200.abi import (CLUSTER_DTYPE, DETECTION_DTYPE, PT_DTYPE, VOX_DTYPE, XYZI_DTYPE, MapInfo, Params, Pose, ScanResult,
+                            Schedule)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libvofod_ref.so")
@@ -37,6 +38,15 @@ def _load():
             "vr_count_rays": (C.c_uint64, [vp, vp, vp, vp, sz]),
             "vr_voxel_grid_weighted": (i32, [vp, sz, f32, vp, i32, vp, sz, P(sz)]),
             "vr_voxel_grid_counted": (i32, [vp, sz, f32, f32, vp, i32, vp, sz, P(sz)]),
+            # the sliced member functions of vofod_nodelet.cpp (oracle/ref_nodelet_glue.cpp)
+            "vn_create": (vp, []), "vn_destroy": (None, [vp]), "vn_reset": (None, [vp, P(Params), f32]), "vn_set_params": (None, [vp, P(Params)]), "vn_sensor_sim": (None, [vp, i32, i32]),
+            "vn_sensor_set": (None, [vp, vp, vp, vp]), "vn_sensor_get": (None, [vp, vp, vp]),
+            "vn_load_mask": (None, [vp, vp, i32, i32, i32, i32, i32, vp, vp]), "vn_range": (None, [vp, vp]),
+            "vn_map": (P(f32), [vp, i32, P(sz)]), "vn_map_info": (None, [vp, P(MapInfo)]),
+            "vn_state_get": (None, [vp, P(i32), P(i32), P(C.c_uint32)]), "vn_state_set": (None, [vp, i32, i32, C.c_uint32]),
+            "vn_process_scan": (i32, [vp, vp, sz, P(Pose), P(Schedule), P(ScanResult)]),
+            "vn_last_voxels": (sz, [vp, vp, vp, vp, sz]), "vn_last_clusters": (sz, [vp, vp, sz]), "vn_last_detections": (sz, [vp, vp, sz]),
+            "vn_load_cloud": (C.c_long, [C.c_char_p, vp, sz]), "vn_apriori": (None, [vp, C.c_char_p, P(Pose)]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
@@ -177,3 +187,106 @@ def voxel_grid_counted(pts, leaf, thr, align=None, dense=True):
     m = C.c_size_t()
     _load().vr_voxel_grid_counted(_p(pts), len(pts), float(leaf), float(thr), _p(al), int(dense), _p(out), len(out), C.byref(m))
     return out[:m.value].copy()
+
+
+class RefNodelet:
+    """The reference's per-scan member functions of src/vofod_nodelet.cpp (sliced at build time, oracle/ref_nodelet_glue.cpp), driven in
+    the order of schedule S1.  Method names mirror oracle.Oracle / capi.Vofod."""
+
+    def __init__(self):
+        self.lib = _load()
+        self.h = C.c_void_p(self.lib.vn_create())
+        self.params = None
+
+    def close(self):
+        if self.h:
+            self.lib.vn_destroy(self.h)
+            self.h = None
+
+    def reset(self, params, voxel_size):
+        self.params = params
+        self.lib.vn_reset(self.h, C.byref(params), float(voxel_size))
+
+    def set_sensor(self, W, H, dirs=None, offs=None, mask=None):
+        """initialize_sensor_lut_simulation(W, H) + all-ones mask; explicit dirs / offs / mask override them"""
+        self.lib.vn_sensor_sim(self.h, int(W), int(H))
+        d = None if dirs is None else _f32(dirs).reshape(-1)
+        o = None if offs is None else _f32(offs).reshape(-1)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        if d is not None or o is not None or m is not None:
+            self.lib.vn_sensor_set(self.h, _p(d), _p(o), _p(m))
+        self.n_rays = int(W) * int(H)
+
+    def sensor_dirs(self):
+        d = np.zeros((self.n_rays, 3), dtype=np.float32)
+        self.lib.vn_sensor_get(self.h, _p(d), None)
+        return d
+
+    def load_mask(self, img, W, H, mangle, pixel_shift_by_row):
+        """load_mask (vofod_nodelet.cpp:506-560) on an in-memory H x W u8 image; img None = file not found"""
+        out = np.zeros(W * H, dtype=np.uint8)
+        sh = np.ascontiguousarray(pixel_shift_by_row, dtype=np.int32)
+        if img is None:
+            self.lib.vn_load_mask(self.h, None, 0, 0, W, H, int(mangle), _p(sh), _p(out))
+        else:
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            self.lib.vn_load_mask(self.h, _p(img), img.shape[1], img.shape[0], W, H, int(mangle), _p(sh), _p(out))
+        return out
+
+    def range_update(self, pt, _params=None):
+        p = _f32(pt, 3)
+        self.lib.vn_range(self.h, _p(p))
+
+    def map_info(self):
+        mi = MapInfo()
+        self.lib.vn_map_info(self.h, C.byref(mi))
+        return mi
+
+    def map_view(self, which=0):
+        n = C.c_size_t()
+        ptr = self.lib.vn_map(self.h, int(which), C.byref(n))
+        return np.ctypeslib.as_array(ptr, shape=(n.value,))
+
+    def map_download(self, which=0):
+        return self.map_view(which).copy()
+
+    def state_get(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_uint32()
+        self.lib.vn_state_get(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def state_set(self, bg, sure, det_id):
+        self.lib.vn_state_set(self.h, int(bg), int(sure), int(det_id))
+
+    def process_scan(self, scan, pose, params, sched, det_cap=256):
+        self.lib.vn_set_params(self.h, C.byref(params))  # dynamic_reconfigure: the values are re-read on every use
+        scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+        res = ScanResult()
+        rc = self.lib.vn_process_scan(self.h, _p(scan), len(scan), C.byref(pose), C.byref(sched), C.byref(res))
+        assert rc == 0
+        dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        k = self.lib.vn_last_detections(self.h, _p(dets), det_cap)
+        return res, dets[:k].copy()
+
+    def last_voxels(self, cap=1 << 20):
+        vox = np.zeros(cap, dtype=VOX_DTYPE)
+        lab = np.zeros(cap, dtype=np.int32)
+        inc = np.zeros(cap, dtype=np.uint8)
+        m = self.lib.vn_last_voxels(self.h, _p(vox), _p(lab), _p(inc), cap)
+        return vox[:m].copy(), lab[:m].copy(), inc[:m].copy()
+
+    def last_clusters(self, cap=1 << 16):
+        out = np.zeros(cap, dtype=CLUSTER_DTYPE)
+        k = self.lib.vn_last_clusters(self.h, _p(out), cap)
+        return out[:k].copy()
+
+    def apriori(self, filename, pose):
+        """initialize_apriori_map (vofod_nodelet.cpp:305-353)"""
+        self.lib.vn_apriori(self.h, filename.encode(), C.byref(pose))
+
+
+def load_cloud(filename, cap=1 << 22):
+    """load_cloud (src/pc_loader.cpp:17-90): N x 3 float32, or None where the reference returns nullptr"""
+    out = np.zeros((cap, 3), dtype=np.float32)
+    n = _load().vn_load_cloud(filename.encode(), _p(out), cap)
+    return None if n < 0 else out[:n].copy()

@@ -110,7 +110,22 @@ using Vector4i = Matrix<int, 4>;
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 #define EIGEN_ALIGN16 alignas(16)
-#define PCL_ADD_POINT4D union { float data[4]; struct { float x; float y; float z; }; }
+// getVector3fMap(): an Eigen::Map in PCL; here a reference-like proxy (assignable, convertible, cast<int>() truncating)
+namespace Eigen
+{
+struct Map3f
+{
+  float* p;
+  Map3f& operator=(const Vector3f& v) { p[0] = v.v[0]; p[1] = v.v[1]; p[2] = v.v[2]; return *this; }
+  operator Vector3f() const { return Vector3f(p[0], p[1], p[2]); }
+  template <class U>
+  Matrix<U, 3> cast() const { return Matrix<U, 3>(static_cast<U>(p[0]), static_cast<U>(p[1]), static_cast<U>(p[2])); }
+};
+}  // namespace Eigen
+#define PCL_ADD_POINT4D                                                                                     \
+  union { float data[4]; struct { float x; float y; float z; }; };                                          \
+  Eigen::Map3f getVector3fMap() { return Eigen::Map3f{data}; }                                              \
+  Eigen::Vector3f getVector3fMap() const { return Eigen::Vector3f(data[0], data[1], data[2]); }
 #define POINT_CLOUD_REGISTER_POINT_STRUCT(name, fields)
 #define PCL_WARN(...) do { } while (0)
 
@@ -131,6 +146,8 @@ struct PCLHeader
 struct alignas(16) PointXYZ
 {
   PCL_ADD_POINT4D;
+  PointXYZ() { data[0] = data[1] = data[2] = 0.f; data[3] = 1.f; }
+  PointXYZ(float x_, float y_, float z_) { data[0] = x_; data[1] = y_; data[2] = z_; data[3] = 1.f; }
 };
 struct alignas(16) PointXYZI
 {
@@ -150,8 +167,11 @@ public:
   bool is_dense = true;
   Eigen::Vector4f sensor_origin_;
   Eigen::Vector4f sensor_orientation_;
+  using PointType = PointT;
   void reserve(std::size_t n) { points.reserve(n); }
   std::size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  const PointT& at(int column, int row) const { return points.at(std::size_t(row) * width + column); }  // organised access (point_cloud.h)
   void push_back(const PointT& p) { points.push_back(p); width = std::uint32_t(points.size()); height = 1; }
   auto begin() { return points.begin(); }
   auto end() { return points.end(); }

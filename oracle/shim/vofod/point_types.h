@@ -23,4 +23,10 @@ struct alignas(16) PointXYZR
   PCL_ADD_POINT4D;
   std::uint32_t range = 0;
 };
+struct alignas(16) PointXYZRI
+{
+  PCL_ADD_POINT4D;
+  float intensity = 0.f;
+  std::uint32_t range = 0;
+};
 }

@@ -1363,8 +1363,10 @@ int vo_set_sensor(Oracle* o, int W, int H, const float* dirs, const float* offs,
   return 0;
 }
 // initialize_sensor_lut_simulation: vofod_nodelet.cpp:374-420 (double math, stored fp32, not renormalised)
-void vo_sim_lut(int w, int h, double vfov, float* dirs3xN)
+void vo_sim_lut(int w, int h, double vfov_in, float* dirs3xN)
 {
+  const float m_sensor_vfov = float(vfov_in);  // a float member of the nodelet (:2311) — pinned by oracle/_ref (the sliced function itself)
+  const double vfov = m_sensor_vfov;
   const double yAngle_step = (2.0 * M_PI - 0.0) / (w - 1);
   const double pAngle_step = (vfov / 2.0 - (-vfov / 2.0)) / (h - 1);
   for (int row = 0; row < h; row++)

@@ -446,6 +446,76 @@ def test_process_scan_cfg2_full_size_steady_state(gpu, cpu):
     _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 44), fixed=True, check_maps_every=11)
 
 
+def test_cfg2_full_size_vs_sequential_fp32_steady_state(gpu, cpu):
+    """BASELINE.json configs[1] at full size against the reference's NATIVE arithmetic — `raycast[v] += ddist` in sequential fp32 over
+    262 144 rays, where the fp32 sum is at its worst in the voxels around the sensor — through take-off and bootstrap into steady state
+    (classification active from scan ~19): every discrete output bit for bit on every scan, the whole 26 M-cell score grid within 1e-5
+    relative on the last 4 scans."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    setup_pair(cpu, gpu, p, vs, sensor)
+    scans = range(0, 24)
+    for k in scans:
+        scan, pose, rp, _ = sensor.scan(0, k)
+        s = abi.schedule_s1(rp)
+        rg, dg = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, False, 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        assert rg.as_dict() == rc.as_dict(), (k, rg.as_dict(), rc.as_dict())
+        vg, lg, ig = gpu.last_voxels()
+        vc, lc, ic = cpu.last_voxels()
+        assert_vox_equal(vg, vc)
+        assert np.array_equal(lg, lc) and np.array_equal(ig, ic)
+        assert len(dg) == len(dc)
+        if k >= scans[-1] - 3:
+            e = rel_err(gpu.map_download(), cpu.map_download())
+            assert e.max() < SCORE_RTOL, (k, float(e.max()))
+    assert rc.background_pts_sufficient and rc.sure_background_sufficient
+
+
+@pytest.mark.parametrize("name", ["gazebo_default", "city_old_rule_itsdiff", "quarter_metre", "mask_offsets_intensity"])
+def test_nodelet_sequences_against_reference_fixture(gpu, oracle_mod, name):
+    """libvofod_cuda on the scan sequences of tests/nodelet_cases.py against (a) tests/golden/ref_nodelet.npz = what the REFERENCE's own
+    member functions of vofod_nodelet.cpp produce (oracle/_ref), for everything discrete: result records, voxels, labels, close/far split,
+    SHA-256 of the flag grid, detection ids / sizes / boxes bit for bit; and (b) the oracle in native mode (pinned to the same fixture bit
+    for bit by tests/test_ref_nodelet.py) for the score grid: 1e-5 relative (the GPU sums path lengths in exact fixed point)."""
+    import os
+    from nodelet_cases import case_list, run_case
+    c = case_list()[name]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_nodelet.npz"))
+    want = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+    got = run_case(gpu, c, keep_maps=True)
+    o = oracle_mod.Oracle(track_counts=False, apply_from_fixed=False)
+    try:
+        ref_maps = run_case(o, c, keep_maps=True)["_maps"]
+    finally:
+        o.close()
+    for k in ("res", "flags_sha", "vox_sha", "labels_sha", "close_sha", "n_det", "det_id", "det_n_points", "det_aabb_min", "det_aabb_max"):
+        assert np.array_equal(got[k], want[k]), (name, k)
+    well = np.minimum(got["det_gap"], want["det_gap"]) > 1e-3
+    for k in ("det_position", "det_covariance", "det_confidence", "det_detection_probability"):
+        np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64)[well], np.asarray(want[k], dtype=np.float64)[well], rtol=1e-5, atol=1e-6, err_msg=k)
+    for i, (a, b) in enumerate(zip(got["_maps"], ref_maps)):
+        assert rel_err(a, b).max() < SCORE_RTOL, (name, i)
+
+
+def test_pcl_parts_against_independent_implementations(gpu):
+    """pcl::EuclideanClusterExtraction / MomentOfInertiaEstimation have no source here: second opinions from scipy (kd-tree + connected
+    components with the exact fp32 strict-'<' test) and numpy.linalg.eigh — the same checks tests/test_pcl_crosscheck.py runs on the oracle"""
+    from test_pcl_crosscheck import check_obb, cluster_clouds, scipy_min_index_labels
+    for name, xyz, tol in cluster_clouds():
+        labels, n = gpu.cluster(xyz, tol)
+        want = scipy_min_index_labels(xyz, tol)
+        assert np.array_equal(labels, want), name
+        assert n == len(np.unique(want))
+    p = abi.default_params()
+    for i, (o, s) in enumerate(zip((-150.0, -150.0, -150.0), (300.0, 300.0, 300.0))):
+        p.oparea_offset[i], p.oparea_size[i] = o, s
+    gpu.map_resize((0, 0, 0), (300, 300, 300), 2.0)
+    n_checked, n = check_obb(gpu, p)
+    assert n == 60 and n_checked >= 40
+
+
 def test_full_size_properties(gpu):
     """Size-independent properties at full size, no oracle: traversal count is independent of aggregation, the
     accumulator returns to zero after apply, flags are cleared, repeated identical scans are deterministic."""

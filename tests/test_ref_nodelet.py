@@ -1,0 +1,57 @@
+"""not gpu: the oracle's restatement of the NODELET-level arithmetic (point / ray update rules, close-far split, classification
+gates + exploreToGround loop, detections, separated-background-cluster pass, rangefinder seed, sim LUT) against the reference's
+own member functions of src/vofod_nodelet.cpp, compiled from /root/reference (oracle/_ref) — through the committed fixture
+tests/golden/ref_nodelet.npz everywhere, and directly where oracle/_ref exists."""
+import os
+
+import numpy as np
+import pytest
+
+from nodelet_cases import case_list, compare_exact, run_case
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_nodelet.npz")
+
+
+def _want(name):
+    z = np.load(GOLDEN)
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+@pytest.mark.parametrize("name", list(case_list()))
+def test_oracle_matches_reference_nodelet_sequences(oracle_mod, name):
+    """every scan: result record, SHA-256 of the whole score grid and of the flag grid, voxels, labels, close/far split, detections —
+    bit for bit (the oracle in its native mode: sequential fp32 path-length sums, like the reference)"""
+    o = oracle_mod.Oracle(track_counts=False, apply_from_fixed=False)
+    try:
+        got = run_case(o, case_list()[name])
+    finally:
+        o.close()
+    compare_exact(got, _want(name), "oracle", name)
+
+
+def test_fixture_is_what_the_reference_build_produces():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built here (needs /root/reference); the committed fixture stands in")
+    name = "gazebo_default"
+    side = ref.RefNodelet()
+    got = run_case(side, case_list()[name])
+    side.close()
+    compare_exact(got, _want(name), "reference", name)
+
+
+def test_sim_lut_against_the_reference_function(oracle_mod):
+    """initialize_sensor_lut_simulation (vofod_nodelet.cpp:374-420) itself: m_sensor_vfov is a FLOAT member, so the angle is rounded
+    to fp32 before the double arithmetic — found by this test, fixed in the oracle and in the harness generator"""
+    from oracle import ref
+    from vofod_b200 import abi, synth
+    if not ref.available():
+        pytest.skip("oracle/_ref not built here")
+    for (W, H) in ((512, 32), (2048, 128)):
+        rn = ref.RefNodelet()
+        rn.reset(abi.default_params(), 0.5)
+        rn.set_sensor(W, H)
+        want = rn.sensor_dirs()
+        rn.close()
+        assert np.array_equal(oracle_mod.sim_lut(W, H, np.pi / 2), want)
+        assert np.array_equal(synth.sim_lut(W, H, np.pi / 2), want)

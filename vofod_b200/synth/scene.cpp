@@ -107,8 +107,9 @@ extern "C" {
 // Simulated-sensor XYZ LUT with the geometry of the reference's initialize_sensor_lut_simulation
 // (vofod_nodelet.cpp:374-420): yaw = col*2pi/(W-1), pitch = -vfov/2 + row*vfov/(H-1), double math stored as fp32,
 // ray id = row*W + col.  Harness input only; tests check it against the oracle's restatement.
-void vsyn_sim_lut(int W, int H, double vfov, float* dirs3xN)
+void vsyn_sim_lut(int W, int H, double vfov_in, float* dirs3xN)
 {
+  const double vfov = double(float(vfov_in));  // m_sensor_vfov is a float member (vofod_nodelet.cpp:2311): the angle is rounded to fp32 first
   const double ystep = (2.0 * M_PI) / (W - 1), pstep = vfov / (H - 1);
   for (int row = 0; row < H; row++)
     for (int col = 0; col < W; col++)

@@ -277,92 +277,134 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(min(12, n_scans))
-    if out is not None:
-        print(json.dumps(out), flush=True)
     del stream, flush
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    v.close()
+    if not args.no_slab:
+        # BASELINE.json configs[4]: the 6.4 GB map cut into `world` slabs, strong scaling (the same scans whatever N), both ray lengths
+        rec = slab_record(local_rank, rank, world, args.slab_steps, args.slab_warmup)
+        if out is not None:
+            out["slab_cfg5"] = rec
+    if out is not None:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    torch.cuda.empty_cache()
-    v.close()
 
 
-def run_slab(args):
-    """Large-map mode (BASELINE.json configs[4]): 0.25 m voxels over 500 x 500 x 100 m (2001 x 2001 x 401 cells, 6.4 GB fp32
-    + 1.6 GB flags), the grid cut into N x-slabs, one per GPU; NCCL scan broadcast + all-reduce of the exchange buffers.
-    Mapping stages only (classification / sepclusters are not in slab mode yet).  Strong scaling: the same scans on 1..N GPUs."""
+SLAB_WORKLOAD = ("cfg5 large map: 0.25 m voxels, 500x500x100 m (2001x2001x401 cells = 6.4 GB fp32 grid), cut into x-slabs (one per GPU) + 16-cell halo, "
+                 "whole schedule S1 (seeds, filter/voxelize, cluster, close/far, point update, clipped raycast + apply, classification + detections on exchanged "
+                 "map boxes, separated-background pass on the gathered voxel lists)")
+
+
+def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None):
+    """scans/s of the slab path on `world` slabs (device-timed on the library's stream, max over ranks).  The scan of step k starts in
+    pinned host memory on rank 0: H2D + NCCL broadcast are inside the timed region."""
     import torch
     import torch.distributed as dist
 
     from vofod_b200 import abi, capi, slab, synth
+    p = abi.default_params()
+    for i, (o, sz) in enumerate(zip((0.0, 0.0, -1.25), (500.0, 500.0, 100.0))):
+        p.oparea_offset[i] = o
+        p.oparea_size[i] = sz
+    p.raycast_max_distance = float(raycast_max)
+    dirs = synth.sim_lut(W, H)
+    v = capi.Vofod(local_rank)
+    worker = slab.SlabWorker(v, p, 0.25, (W, H), dirs, rank, world, halo=16)
+    N = W * H
+    n_scans = K + Wm
+    if scans is None:
+        pinned = torch.empty((n_scans, N * abi.PT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        host = pinned.numpy().view(abi.PT_DTYPE).reshape(n_scans, N)
+        poses, scheds = [], []
+        for k in range(n_scans):
+            # every rank generates the (deterministic) pose and seed point; only rank 0's scan buffer is ever read
+            _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs, 2.5, out=host[k])
+            poses.append(pose)
+            scheds.append(abi.schedule_s1(rp))
+        scans = (pinned, host, poses, scheds)
+    pinned, host, poses, scheds = scans
+    stream = torch.cuda.ExternalStream(v.stream(), device=torch.device("cuda", local_rank))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
+    trav, dets, l0 = 0, 0, 0
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    for k in range(n_scans):
+        if k == Wm:
+            barrier()
+            l0 = v.kernel_launches()
+        ev[k][0].record(stream)
+        res, d = worker.step(host[k], poses[k], scheds[k])
+        ev[k][1].record(stream)
+        if k >= Wm:
+            trav += res.n_traversals  # summed over the slabs by the library (a traversal is counted by the slab that owns the voxel)
+            dets += res.n_detections
+    barrier()
+    launches = v.kernel_launches() - l0
+    ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    mi = v.map_info()
+    cells = int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2])
+    del stream
+    torch.cuda.synchronize()
+    worker.close()
+    torch.cuda.empty_cache()
+    return {"value": K / (total_ms * 1e-3), "unit": "scans/s", "ms_per_step": total_ms / K, "n_slabs": world, "steps": K, "warmup": Wm,
+            "raycast_max_distance_m": raycast_max, "traversals_per_scan": trav / K, "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9,
+            "detections_in_timed_steps": dets, "gpu_launches_rank0": int(launches), "slab0_storage_cells": cells,
+            "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize, "scaling": "strong"}, scans
+
+
+def slab_record(local_rank, rank, world, K, Wm, dists=(20.0, 200.0)):
+    """cfg5 sub-record: scans/s on `world` slabs for both ray lengths and, when world > 1, the same scans on ONE GPU (rank 0, the other
+    ranks wait) measured in the same run, so that the strong-scaling efficiency needs no second file"""
+    import torch.distributed as dist
+    rec = {"workload": SLAB_WORKLOAD, "parallelism": f"slab{world}: ncclBroadcast of the packed scan (5.2 MB) + ncclAllReduce / ncclAllGather of the exchange buffers "
+                                                     "inside libvofod_cuda, one host wait per scan" if world > 1 else "1 slab = the whole grid on one GPU"}
+    for d in dists:
+        r, scans = slab_leg(local_rank, rank, world, d, K, Wm)
+        key = "%gm" % d
+        rec[key] = r
+        if world > 1:
+            if rank == 0:
+                one, _ = slab_leg(local_rank, 0, 1, d, K, Wm, scans=scans)
+                r["one_gpu_same_run"] = {"value": one["value"], "ms_per_step": one["ms_per_step"]}
+                r["strong_scaling_efficiency"] = r["value"] / one["value"] / world
+            dist.barrier()
+    return rec
+
+
+def run_slab(args):
+    """Large-map mode (BASELINE.json configs[4]) on its own: `--mode slab [--raycast-max D]`.  Strong scaling: the same scans on 1..N GPUs."""
+    import torch
+    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    K, Wm = args.steps, args.warmup
-    p = abi.default_params()
-    for i, (o, sz) in enumerate(zip((0.0, 0.0, -1.25), (500.0, 500.0, 100.0))):
-        p.oparea_offset[i] = o
-        p.oparea_size[i] = sz
-    p.raycast_max_distance = float(args.raycast_max)
-    dirs = synth.sim_lut(W, H)
-    v = capi.Vofod(local_rank)
-    worker = slab.SlabWorker(v, p, 0.25, (W, H), dirs, rank, world, halo=16)
-    N = W * H
-    n_scans = K + Wm
-    pinned = torch.empty((n_scans, N * abi.PT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
-    poses, rps = [], []
+    rec = slab_record(local_rank, rank, world, args.steps, args.warmup, dists=(float(args.raycast_max),))
+    r = rec["%gm" % float(args.raycast_max)]
     if rank == 0:
-        host = pinned.numpy().view(abi.PT_DTYPE).reshape(n_scans, N)
-        for k in range(n_scans):
-            _, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs, 2.5, out=host[k])
-            poses.append(pose)
-            rps.append(rp)
-    stream = worker.stream
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
-    trav = 0
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    for k in range(n_scans):
-        if k == Wm:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-        ev[k][0].record(stream)
-        res = worker.step(pinned[k] if rank == 0 else None, poses[k] if rank == 0 else None, rps[k] if rank == 0 else None)
-        ev[k][1].record(stream)
-        if k >= Wm:
-            trav += res.n_traversals
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans))
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        total_ms = float(t[0])
-        mi = v.map_info()
         print(json.dumps({
-            "metric": "scans/s", "value": K / (total_ms * 1e-3), "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K,
+            "metric": "scans/s", "value": r["value"], "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores / u64 fixed-point path lengths", "data": "synthetic",
-            "config": {"workload": "cfg5 large map: 0.25 m voxels, 500x500x100 m (2001x2001x401 cells), x-slabs + 16-cell halo, mapping stages of schedule S1 "
-                                   "(seeds, filter/voxelize, cluster, close/far, point update, raycast accumulate+apply), raycast.max_distance %g m" % args.raycast_max,
-                       "parallelism": f"slab{world}: NCCL scan broadcast (5.2 MB) + all-reduce(SUM n_bg, MAX cluster flags)",
-                       "slab0_storage_cells": int(mi.storage_size[0]) * int(mi.storage_size[1]) * int(mi.storage_size[2]), "l2": "grid (GBs) far larger than L2"},
-            "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9, "traversals_per_scan": trav / K, "mode": "slab"}), flush=True)
-    torch.cuda.synchronize()
+            "config": {"workload": SLAB_WORKLOAD + ", raycast.max_distance %g m" % args.raycast_max, "parallelism": rec["parallelism"],
+                       "l2": "grids (GBs) far larger than L2"}, "mode": "slab", "slab": r}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    # torch (caching allocators, NCCL) still holds events on the library's stream: leave the context to process exit and do
-    # not run torch's teardown against a destroyed stream
     sys.stdout.flush()
     os._exit(0)
 
@@ -440,6 +482,9 @@ def main():
     ap.add_argument("--distinct-streams", action="store_true", help="N > 1: every rank processes a different part of the trajectory instead of the same sequence")
     ap.add_argument("--mode", default="streams", choices=["streams", "slab"],
                     help="streams (default, the driver's contract): cfg2, one independent scan stream per GPU; slab: cfg5 large map cut into x-slabs")
+    ap.add_argument("--no-slab", action="store_true", help="skip the cfg5 slab sub-record")
+    ap.add_argument("--slab-steps", type=int, default=20)
+    ap.add_argument("--slab-warmup", type=int, default=6)
     ap.add_argument("--raycast-max", type=float, default=20.0, help="slab mode: raycast.max_distance [m] (yaml default 20, dynamic_reconfigure maximum 200)")
     ap.add_argument("--profile-leg", default="", choices=["", "graph", "eager"],
                     help="profiling aid: run ONLY the HBM-resident leg (graph replay or kernel-by-kernel) and print nothing the driver parses")

@@ -278,23 +278,47 @@ int vofod_process_scan_resident(vofod_ctx*, int slot, const vofod_pose*, const v
 int vofod_last_voxels(vofod_ctx*, vofod_vox* out, int32_t* labels, uint8_t* in_close, size_t cap, size_t* m);
 int vofod_last_clusters(vofod_ctx*, vofod_cluster_info* out, size_t cap, size_t* n);
 
-/* ---- multi-GPU slab mode (no counterpart in the reference) ---------------------- */
-/* this context keeps only cells lo-halo <= idx[axis] < hi+halo of the global grid (axis 0 = x or 1 = y) and OWNS lo <= idx[axis] < hi.
- * Call after vofod_map_resize / vofod_reset; the grid contents are unspecified afterwards (vofod_map_set_to).  Map downloads /
- * uploads then address the storage box (vofod_map_info_get reports the global geometry and the own range). */
+/* ---- multi-GPU slab mode (no counterpart in the reference; SURVEY.md §8e, BASELINE.json configs[4]) -------------------------------- */
+/* The global grid is cut along a horizontal axis (0 = x or 1 = y), one slab per context / GPU: this context keeps only cells
+ * lo-halo <= idx[axis] < hi+halo and OWNS lo <= idx[axis] < hi.  Call after vofod_map_resize / vofod_reset; the grid contents are
+ * unspecified afterwards (vofod_map_set_to).  Map downloads / uploads then address the storage box (vofod_map_info_get reports the
+ * global geometry and the own range).  halo >= vofod_slab_min_halo(params, voxel_size) keeps every result bit-identical to the
+ * unsharded run (checked when a scan starts: VOFOD_E_INVALID otherwise). */
 int vofod_set_slab(vofod_ctx*, int axis, int lo, int hi, int halo);
-/* One scan of the MAPPING stages (seeds, filter/voxelize, cluster, close/far, point update, raycast accumulate + apply) in slab
- * mode, in two phases.  Between them the caller combines, over all slabs, the two buffers vofod_slab_exchange_buffers returns:
- * SUM of n_bg (u64[1]) and element-wise MAX of cluster_close (i32[n]) — ncclAllReduce on vofod_stream(), or a host loop through
- * vofod_slab_exchange_io when several slabs are emulated on one device.  `scan` is a host pointer, or (scan_on_device) a device
- * pointer, e.g. the target of the NCCL scan broadcast.  Classification / detections / sepclusters do not run in slab mode yet. */
-int vofod_slab_scan_begin(vofod_ctx*, const vofod_pt* scan, int scan_on_device, size_t n, const vofod_pose*, const vofod_params*,
-                          const vofod_schedule*);
-int vofod_slab_exchange_buffers(vofod_ctx*, void** d_n_bg, void** d_cluster_close, size_t* n_cluster_close);
-int vofod_slab_exchange_io(vofod_ctx*, uint64_t* n_bg, int32_t* cluster_close, size_t n, int to_device);
-int vofod_slab_scan_end(vofod_ctx*, const vofod_params*, const vofod_schedule*, vofod_scan_result* res);
-/* boundary fragments for the cross-slab cluster merge: points within `halo` cells of a slab face */
-int vofod_slab_boundary(vofod_ctx*, int32_t* point_idx, int32_t* labels, size_t cap, size_t* n);
+int vofod_slab_min_halo(const vofod_params*, float voxel_size);
+/* A scan of schedule S1 in slab mode = 4 phases; after each, some device buffers are combined over all slabs (vofod_csrc/slab.cu says
+ * which and why): rays are clipped to the slab, grids and grid passes are sharded, the small per-scan point pipeline is replicated. */
+#define VOFOD_XCHG_SUM_U64    0   /* all-reduce, sum of uint64                                          */
+#define VOFOD_XCHG_MAX_I32    1   /* all-reduce, max of int32                                           */
+#define VOFOD_XCHG_SUM_U32    2   /* all-reduce, sum of uint32 (every element is non-zero on one slab)  */
+#define VOFOD_XCHG_GATHER_U32 3   /* all-gather: `count` uint32 of every slab into gather_out, rank-major */
+#define VOFOD_W_REDO          5   /* vofod_slab_phase(3): a gathered list overflowed, nothing was touched: repeat phases 2 and 3 */
+typedef struct vofod_slab_exchange {
+  int32_t kind;        /* VOFOD_XCHG_*                                   */
+  int32_t _pad;
+  void*   buf;         /* device memory; all-reduces are done in place   */
+  size_t  count;       /* elements                                       */
+  void*   gather_out;  /* VOFOD_XCHG_GATHER_U32 only: nranks * count elements */
+} vofod_slab_exchange;
+/* (a) caller-driven: phase 0 takes the scan (host pointer, or device pointer with scan_on_device != 0) and the arguments, phases 1..3
+ * continue it and ignore them; after every phase combine the buffers vofod_slab_exchanges lists (at most 4) over all slabs — a host
+ * loop when several slabs live on one device (tests), any collective library otherwise; phase 3 delivers the results.
+ * vofod_slab_set_world tells a context how many slabs there are (it sizes the gather buffers). */
+int vofod_slab_set_world(vofod_ctx*, int rank, int nranks);
+int vofod_slab_phase(vofod_ctx*, int phase, const vofod_pt* scan, int scan_on_device, size_t n, const vofod_pose*, const vofod_params*,
+                     const vofod_schedule*, vofod_scan_result* res, vofod_detection* dets, size_t det_cap);
+int vofod_slab_exchanges(vofod_ctx*, int phase, vofod_slab_exchange out[4], int* n_out);
+/* (b) over NCCL inside the library (libnccl.so.2 is resolved at run time): one communicator per context, created from an id that rank 0
+ * makes with vofod_comm_unique_id (128 bytes) and hands to the other ranks.  vofod_slab_process_scan then runs the four phases with
+ * ncclBroadcast of the packed scan (rank 0 passes it, in host memory; other ranks may pass NULL) and ncclAllReduce / ncclAllGather of
+ * the exchange buffers on the context's stream; pose, parameters and schedule are given on every rank.  One host wait per scan. */
+int vofod_comm_unique_id(void* out128);
+int vofod_comm_init(vofod_ctx*, int rank, int nranks, const void* nccl_unique_id);
+int vofod_slab_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*, const vofod_params*, const vofod_schedule*,
+                            vofod_scan_result* res, vofod_detection* dets, size_t det_cap);
+/* voxels of the last scan within `margin` cells of a face of the owned range, with their cluster labels (the cluster fragments that
+ * reach into the neighbouring slab) */
+int vofod_slab_boundary(vofod_ctx*, int margin, int32_t* point_idx, int32_t* labels, size_t cap, size_t* n);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* device time [ms] of the stages of the last process_scan, names follow the reference's ScopeTimer
@@ -316,6 +340,7 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 #define VOFOD_OPT_VG_SORT 7        /* test switch (default 0): the scan path voxelizes with the generic sort-based voxel grid */
 #define VOFOD_OPT_PDL 6            /* default 1: consecutive kernels are chained by programmatic dependent launch */
 #define VOFOD_OPT_RAYCAST_NO_AGG 2 /* tuning switch (default 0): one RED per traversal instead of warp-aggregated REDs */
+#define VOFOD_OPT_SLAB_PATCH_WORDS 11 /* slab mode: capacity (uint32 words) of the buffer that carries the classification candidates' map boxes (0 = automatic) */
 #define VOFOD_OPT_RAYCAST_STATS 10 /* instrumentation switch (default 0): the accumulate kernel also fills per warp-step histograms, see vofod_raycast_stats */
 int vofod_set_option(vofod_ctx*, int option, int value);
 /* VOFOD_OPT_RAYCAST_STATS: out[0..32] = warp-steps with that many lanes (rays) in the loop, out[33..65] = warp-steps with that many distinct
@@ -326,6 +351,9 @@ int vofod_raycast_stats(vofod_ctx*, uint64_t* out, size_t n);
 uint64_t vofod_get_stat(const vofod_ctx*, int which);
 /* raw CUDA stream handle (cudaStream_t) the context enqueues on, for event timing by the caller */
 void* vofod_stream(vofod_ctx*);
+/* stream-ordered, synchronous copies between host memory and a device buffer the library handed out (vofod_slab_exchanges) */
+int vofod_dev_read(vofod_ctx*, const void* dev, void* host, size_t bytes);
+int vofod_dev_write(vofod_ctx*, void* dev, const void* host, size_t bytes);
 
 #ifdef __cplusplus
 }

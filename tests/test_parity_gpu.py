@@ -495,8 +495,15 @@ def test_nodelet_sequences_against_reference_fixture(gpu, oracle_mod, name):
     well = np.minimum(got["det_gap"], want["det_gap"]) > 1e-3
     for k in ("det_position", "det_covariance", "det_confidence", "det_detection_probability"):
         np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64)[well], np.asarray(want[k], dtype=np.float64)[well], rtol=1e-5, atol=1e-6, err_msg=k)
+    # The OLD update rule (:1574-1601, not the yaml default) divides every path length by max_element(raycast) — the sensor's own voxel, where
+    # the reference's sequential fp32 sum over ~10^4 rays is ~1e-4 off the exact sum the GPU holds.  That error is the reference's, it
+    # scales every weight of the scan, and on cells near 0 it is an absolute 1e-4 (1e-7 of the score range): bounded here in absolute terms.
+    old_rule = not c["p"].raycast_new_update_rule
     for i, (a, b) in enumerate(zip(got["_maps"], ref_maps)):
-        assert rel_err(a, b).max() < SCORE_RTOL, (name, i)
+        if old_rule:
+            assert np.abs(a.astype(np.float64) - b).max() < 1e-3 and rel_err(a, b, floor=100.0).max() < SCORE_RTOL, (name, i)
+        else:
+            assert rel_err(a, b).max() < SCORE_RTOL, (name, i)
 
 
 def test_pcl_parts_against_independent_implementations(gpu):
@@ -552,58 +559,110 @@ def test_golden_vectors_from_reference_build(gpu):
     compare(got, want, "libvofod_cuda")
 
 
+def _slab_sequence(cpu, sensor, p, vs, scene, scans, n_slab, halo, map_scale=1.0, check_every=1, sep_cap=0):
+    """whole schedule S1 (classification, detections, separated background clusters included) on `n_slab` slabs emulated as contexts
+    on one device, the exchange buffers combined by a host loop (vofod_b200/slab.py) — against the MONOLITHIC oracle: every result
+    record, voxels, labels, detections, and every slab's storage box (own range + halo) of the score and flag grids bit for bit."""
+    from vofod_b200 import capi, slab
+    ctxs = [capi.Vofod(0) for _ in range(n_slab)]
+    n_det = 0
+    try:
+        for g in ctxs:
+            g.set_option(abi.OPT_SEP_CAP, sep_cap)
+        slab.make_slabs(ctxs, p, vs, (sensor.W, sensor.H), sensor.dirs, halo)
+        cpu.reset(p, vs)
+        cpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        sx, sy, sz = list(cpu.map_info().sizes)
+        for k in scans:
+            scan, pose, rp, _ = sensor.scan(scene, k, map_scale)
+            s = abi.schedule_s1(rp)
+            out = slab.run_emulated(ctxs, scan, pose, p, s)
+            cpu.set_modes(True, True, ctxs[0].raycast_frac_bits() or 24)
+            want, dc = cpu.process_scan(scan, pose, p, s)
+            wd = want.as_dict()
+            vc, lc, ic = cpu.last_voxels()
+            n_det += len(dc)
+            for g, (res, dg) in zip(ctxs, out):
+                assert res.as_dict() == wd, (k, res.as_dict(), wd)
+                vg, lg, ig = g.last_voxels()
+                assert_vox_equal(vg, vc)
+                assert np.array_equal(lg, lc) and np.array_equal(ig, ic)
+                assert len(dg) == len(dc)
+                for f in ("id", "label", "n_points"):
+                    assert np.array_equal(dg[f], dc[f]), (k, f)
+                struct_close(dg, dc, ("position", "covariance", "confidence", "detection_probability"), rtol=1e-5, atol=1e-7)
+            if k % check_every == 0:
+                full = cpu.map_download().reshape(sz, sy, sx)
+                flags = cpu.map_download(abi.MAP_FLAGS).reshape(sz, sy, sx)
+                for g in ctxs:
+                    mi = g.map_info()
+                    x0, nx = mi.storage_lo[0], mi.storage_size[0]
+                    assert np.array_equal(g.map_download().reshape(sz, sy, nx), full[:, :, x0:x0 + nx], equal_nan=True), k   # own range AND halo
+                    assert np.array_equal(g.map_download(abi.MAP_FLAGS).reshape(sz, sy, nx), flags[:, :, x0:x0 + nx]), k
+        # cluster fragments at the slab faces: neighbouring slabs report the same labels for the voxels they both see
+        frag = [dict(zip(*g.slab_boundary(halo))) for g in ctxs]
+        for a, b in zip(frag[:-1], frag[1:]):
+            common = set(a) & set(b)
+            assert all(a[i] == b[i] for i in common)
+    finally:
+        for g in ctxs:
+            g.close()
+    return n_det
+
+
 def test_slab_mode_emulated_on_one_gpu(cpu):
-    """Spatial-slab sharding of the grid (BASELINE configs[4]) with 3 slabs emulated as 3 contexts on one device: after every
-    scan each slab's storage box (own range + halo) must equal the matching slice of the monolithic oracle map bit for bit,
-    and the per-scan counts must agree.  The exchange (SUM n_bg, MAX cluster flags) is done on the host here; on several GPUs
-    it is an NCCL all-reduce (vofod_b200/slab.py)."""
-    from vofod_b200 import capi, multi
+    """Spatial-slab sharding of the grid (BASELINE configs[4]), 3 slabs, the Gazebo-like scene through bootstrap into detections: the UAV
+    clusters are classified on exchanged map boxes, the separated-background pass runs on the gathered voxel lists."""
     sensor = Sensor(512, 32)
     p, vs = small_params()
     p.background_sufficient_points_ratio = 0.02
-    n_slab, halo = 3, 8
-    cpu.reset(p, vs)
-    cpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
-    sx, sy, sz = list(cpu.map_info().sizes)
-    slabs = []
-    for r in range(n_slab):
-        g = capi.Vofod(0)
-        g.reset(p, vs)
-        lo, hi = multi.partition(sx, r, n_slab)
-        g.set_slab(0, lo, hi, halo)
-        g.map_set_to(abi.MAP_SCORE, p.score_init)
-        g.set_sensor(sensor.W, sensor.H, sensor.dirs)
-        slabs.append(g)
-    try:
-        for k in range(26):
-            scan, pose, rp, _ = sensor.scan(0, k)
-            s = abi.schedule_s1(rp, do_classify=False, do_sepclusters=False)
-            for g in slabs:
-                g.slab_scan_begin(scan, pose, p, s)
-            parts = [g.slab_exchange_get(len(scan)) for g in slabs]
-            n_bg = sum(x[0] for x in parts)
-            close = np.maximum.reduce([x[1] for x in parts])
-            results = []
-            for g in slabs:
-                g.slab_exchange_set(n_bg, close)
-                results.append(g.slab_scan_end(p, s).as_dict())
-            cpu.set_modes(True, True, slabs[0].raycast_frac_bits() or 24)
-            want, _ = cpu.process_scan(scan, pose, p, s)
-            # a traversal is counted by the slab that owns the voxel: the slabs' counts add up to the reference's
-            wd = want.as_dict()
-            assert sum(r["n_traversals"] for r in results) == wd["n_traversals"], (k, [r["n_traversals"] for r in results], wd["n_traversals"])
-            for r in results:
-                assert dict(r, n_traversals=0) == dict(wd, n_traversals=0), (k, r, wd)
-            full = cpu.map_download().reshape(sz, sy, sx)
-            flags = cpu.map_download(abi.MAP_FLAGS).reshape(sz, sy, sx)
-            for g in slabs:
-                mi = g.map_info()
-                x0, nx = mi.storage_lo[0], mi.storage_size[0]
-                assert np.array_equal(g.map_download().reshape(sz, sy, nx), full[:, :, x0:x0 + nx]), k   # own range AND halo
-                assert np.array_equal(g.map_download(abi.MAP_FLAGS).reshape(sz, sy, nx), flags[:, :, x0:x0 + nx]), k
-    finally:
-        for g in slabs:
-            g.close()
+    n_det = _slab_sequence(cpu, sensor, p, vs, 1, range(0, 30), n_slab=3, halo=8)
+    assert n_det > 0
+
+
+def test_slab_mode_city_four_slabs_small_buffers(cpu):
+    """4 slabs on the city scene with the background-list capacity forced to 64 entries: every scan overflows, is left untouched and redone
+    (VOFOD_W_REDO) with a grown list"""
+    from vofod_b200 import capi
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    _slab_sequence(cpu, sensor, p, vs, 0, range(0, 16), n_slab=4, halo=6, sep_cap=64)
+
+
+def test_slab_mode_over_nccl():
+    """the same check over real NCCL, one process per GPU (tools/check_slab_nccl.py): needs a box with >= 2 GPUs"""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on one box (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for world in sorted({2, min(n, 4), min(n, 8)}):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
+                            str(29570 + world), os.path.join(root, "tools", "check_slab_nccl.py")], capture_output=True, text=True, timeout=900)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert r.returncode == 0 and lines, (world, r.stdout[-2000:], r.stderr[-3000:])
+        out = json.loads(lines[-1])
+        assert out["all_slabs_bit_exact"] and out["world"] == world and out["detections"] > 0, out
+
+
+def test_slab_halo_too_small_is_rejected(gpu):
+    sensor = Sensor(64, 8)
+    p, vs = small_params()
+    gpu.reset(p, vs)
+    sx = gpu.map_info().sizes[0]
+    gpu.set_slab(0, 0, sx // 2, 2)  # hasCloseTo needs ceil(1.5 / 0.5) + 1 = 4 cells
+    gpu.map_set_to(abi.MAP_SCORE, p.score_init)
+    gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+    gpu.slab_set_world(0, 2)
+    assert gpu.slab_min_halo(p, vs) == 4
+    scan, pose, rp, _ = sensor.scan(0, 3)
+    with pytest.raises(RuntimeError):
+        gpu.slab_phase(0, scan, pose, p, abi.schedule_s1(rp))
 
 
 def test_cfg3_full_size_detections(gpu, cpu):

@@ -201,3 +201,13 @@ OPT_RAYCAST_STATS = 10
 OPT_RAYCAST_NO_AGG = 2
 OPT_RAYCAST_BLOCK = 5
 OPT_OVERLAP = 4
+
+
+class SlabExchange(C.Structure):
+    """vofod_slab_exchange (include/vofod_cuda.h)"""
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("buf", C.c_void_p), ("count", C.c_size_t), ("gather_out", C.c_void_p)]
+
+
+XCHG_SUM_U64, XCHG_MAX_I32, XCHG_SUM_U32, XCHG_GATHER_U32 = 0, 1, 2, 3
+VOFOD_W_REDO = 5
+OPT_SLAB_PATCH_WORDS = 11

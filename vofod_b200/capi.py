@@ -89,11 +89,16 @@ def load_library():
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
         "vofod_set_slab": (i32, [vp, i32, i32, i32, i32]),
-        "vofod_slab_scan_begin": (i32, [vp, vp, i32, sz, P(Pose), P(Params), P(Schedule)]),
-        "vofod_slab_exchange_buffers": (i32, [vp, P(vp), P(vp), P(sz)]),
-        "vofod_slab_exchange_io": (i32, [vp, P(C.c_uint64), vp, sz, i32]),
-        "vofod_slab_scan_end": (i32, [vp, P(Params), P(Schedule), P(ScanResult)]),
-        "vofod_slab_boundary": (i32, [vp, vp, vp, sz, P(sz)]),
+        "vofod_slab_min_halo": (i32, [P(Params), f32]),
+        "vofod_slab_set_world": (i32, [vp, i32, i32]),
+        "vofod_slab_phase": (i32, [vp, i32, vp, i32, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
+        "vofod_slab_exchanges": (i32, [vp, i32, P(abi.SlabExchange), P(i32)]),
+        "vofod_comm_unique_id": (i32, [vp]),
+        "vofod_comm_init": (i32, [vp, i32, i32, vp]),
+        "vofod_slab_process_scan": (i32, [vp, vp, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
+        "vofod_dev_read": (i32, [vp, vp, vp, sz]),
+        "vofod_dev_write": (i32, [vp, vp, vp, sz]),
+        "vofod_slab_boundary": (i32, [vp, i32, vp, vp, sz, P(sz)]),
         "vofod_stage_times": (i32, [vp, vp]),
         "vofod_stage_name": (C.c_char_p, [i32]),
         "vofod_kernel_launches": (C.c_uint64, [vp]),
@@ -407,34 +412,70 @@ class Vofod:
     def set_slab(self, axis, lo, hi, halo):
         self._ck(self.lib.vofod_set_slab(self.h, int(axis), int(lo), int(hi), int(halo)))
 
-    def slab_scan_begin(self, scan, pose, params, sched, device_ptr=None):
-        """scan: numpy array of PT_DTYPE on the host, or device_ptr = raw device address of the (broadcast) scan"""
-        if device_ptr is not None:
-            self._ck(self.lib.vofod_slab_scan_begin(self.h, C.c_void_p(device_ptr), 1, self.n_rays, C.byref(pose), C.byref(params), C.byref(sched)))
-        else:
-            scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
-            self._ck(self.lib.vofod_slab_scan_begin(self.h, _p(scan), 0, len(scan), C.byref(pose), C.byref(params), C.byref(sched)))
+    def slab_min_halo(self, params, voxel_size):
+        return int(self.lib.vofod_slab_min_halo(C.byref(params), float(voxel_size)))
 
-    def slab_exchange_buffers(self):
-        a, b, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
-        self._ck(self.lib.vofod_slab_exchange_buffers(self.h, C.byref(a), C.byref(b), C.byref(n)))
-        return a.value, b.value, n.value
+    def slab_set_world(self, rank, nranks):
+        self._ck(self.lib.vofod_slab_set_world(self.h, int(rank), int(nranks)))
 
-    def slab_exchange_get(self, n):
-        nbg = C.c_uint64()
-        close = np.zeros(n, dtype=np.int32)
-        self._ck(self.lib.vofod_slab_exchange_io(self.h, C.byref(nbg), _p(close), n, 0))
-        return nbg.value, close
-
-    def slab_exchange_set(self, nbg, close):
-        v = C.c_uint64(int(nbg))
-        close = np.ascontiguousarray(close, dtype=np.int32)
-        self._ck(self.lib.vofod_slab_exchange_io(self.h, C.byref(v), _p(close), len(close), 1))
-
-    def slab_scan_end(self, params, sched):
+    def slab_phase(self, phase, scan=None, pose=None, params=None, sched=None, device_ptr=None, det_cap=256):
+        """one phase of a slab-mode scan (include/vofod_cuda.h); phase 0 takes the scan (numpy array on the host, or device_ptr = raw
+        device address), phase 3 returns (status, ScanResult, detections); phases 0..2 return the status"""
         res = ScanResult()
-        self._ck(self.lib.vofod_slab_scan_end(self.h, C.byref(params), C.byref(sched), C.byref(res)))
-        return res
+        dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        if phase == 0:
+            if device_ptr is not None:
+                rc = self.lib.vofod_slab_phase(self.h, 0, C.c_void_p(device_ptr), 1, self.n_rays, C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets), det_cap)
+            else:
+                self._slab_scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+                rc = self.lib.vofod_slab_phase(self.h, 0, _p(self._slab_scan), 0, len(self._slab_scan), C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets),
+                                               det_cap)
+        else:
+            rc = self.lib.vofod_slab_phase(self.h, int(phase), None, 0, 0, None, None, None, C.byref(res), _p(dets), det_cap)
+        if rc < 0:
+            self._ck(rc)
+        if phase == 3:
+            return rc, res, dets[:res.n_detections].copy()
+        return rc
+
+    def slab_exchanges(self, phase):
+        x = (abi.SlabExchange * 4)()
+        n = C.c_int()
+        self._ck(self.lib.vofod_slab_exchanges(self.h, int(phase), x, C.byref(n)))
+        return [x[i] for i in range(n.value)]
+
+    def dev_read(self, dev_ptr, dtype, count):
+        out = np.zeros(count, dtype=dtype)
+        self._ck(self.lib.vofod_dev_read(self.h, C.c_void_p(dev_ptr), _p(out), out.nbytes))
+        return out
+
+    def dev_write(self, dev_ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self.lib.vofod_dev_write(self.h, C.c_void_p(dev_ptr), _p(arr), arr.nbytes))
+
+    def comm_init(self, rank, nranks, unique_id=None):
+        buf = None if unique_id is None else np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        self._ck(self.lib.vofod_comm_init(self.h, int(rank), int(nranks), _p(buf)))
+
+    def slab_process_scan(self, scan, pose, params, sched, det_cap=256):
+        """the whole slab-mode scan over NCCL (vofod_comm_init first); scan is read on rank 0 only"""
+        res = ScanResult()
+        dets = np.zeros(det_cap, dtype=DETECTION_DTYPE)
+        if scan is not None and not isinstance(scan, int):
+            scan = np.ascontiguousarray(scan, dtype=PT_DTYPE)
+            rc = self.lib.vofod_slab_process_scan(self.h, _p(scan), len(scan), C.byref(pose), C.byref(params), C.byref(sched), C.byref(res), _p(dets), det_cap)
+        else:
+            rc = self.lib.vofod_slab_process_scan(self.h, C.c_void_p(scan) if scan else None, self.n_rays, C.byref(pose), C.byref(params), C.byref(sched), C.byref(res),
+                                                  _p(dets), det_cap)
+        self._ck(rc)
+        return res, dets[:res.n_detections].copy()
+
+    def slab_boundary(self, margin, cap=1 << 20):
+        idx = np.zeros(cap, dtype=np.int32)
+        lab = np.zeros(cap, dtype=np.int32)
+        n = C.c_size_t()
+        self._ck(self.lib.vofod_slab_boundary(self.h, int(margin), _p(idx), _p(lab), cap, C.byref(n)))
+        return idx[:n.value].copy(), lab[:n.value].copy()
 
     def stage_times(self):
         ms = np.zeros(abi.N_STAGES, dtype=np.float32)

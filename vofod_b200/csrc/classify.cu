@@ -403,6 +403,51 @@ __global__ void __launch_bounds__(256) k_cluster_moi(const ClsArgs a, const Scan
   }
 }
 
+// ---- slab mode: classification on exchanged PATCHES of the map (slab.cu) ------------------------------------------------------------
+// A candidate's exploreToGround reads (and its frontier write-back writes) cells up to R voxels around its points, which may lie in
+// other slabs.  Every slab therefore packs, for each candidate in classification order, the cells it OWNS of the box
+// [aabb - R - 1, aabb + R + 1] as raw bit patterns (zero elsewhere); the sum over all slabs (each cell has one owner) gives every slab
+// the same dense copy of every box, the sequential classification runs replicated on those copies, and writes go through to the held
+// part of the grid and to every other box that contains the cell.
+#define PATCH_MAX 64
+struct PatchDesc
+{
+  int lo[3], size[3];
+  unsigned off;  // first word of the box in the patch buffer
+  int far_idx;   // index of the candidate among the far clusters
+};
+struct PatchSet
+{
+  PatchDesc* desc;            // PATCH_MAX entries
+  uint32_t* words;            // bit patterns of the score cells
+  unsigned long long* meta;   // [0] number of boxes, [1] words used, [2] overflow flag (a candidate did not fit: the host reports it)
+  unsigned budget;            // capacity of `words`
+};
+__device__ __forceinline__ long long patch_cell(const PatchDesc& d, const int x, const int y, const int z)
+{
+  const int lx = x - d.lo[0], ly = y - d.lo[1], lz = z - d.lo[2];
+  if (lx < 0 || ly < 0 || lz < 0 || lx >= d.size[0] || ly >= d.size[1] || lz >= d.size[2])
+    return -1;
+  return (long long)d.off + lx + (long long)ly * d.size[0] + (long long)lz * d.size[0] * d.size[1];
+}
+// value of a map cell as the sequential classification sees it
+template <bool PATCH>
+__device__ __forceinline__ float cls_load(const float* score, const Geom& g, const PatchDesc* pd, const uint32_t* words, const int x, const int y, const int z)
+{
+  if (PATCH)
+  {
+    const long long w = patch_cell(*pd, x, y, z);
+    return w >= 0 ? __uint_as_float(words[w]) : 0.0f;
+  }
+  const long long ci = cell_index(g, x, y, z);
+  return ci >= 0 ? score[ci] : 0.0f;
+}
+// explore radius of a candidate (:1698) and its box
+__device__ __forceinline__ int cls_explore_radius(const float obb_size, const double max_explore_distance, const float vs)
+{
+  return (int)(((double)obb_size + max_explore_distance) / (double)vs);
+}
+
 // K14 — VoxelMap::exploreToGround (voxel_map.cpp:402-488) as a block-parallel flood fill.  All threads of the block
 // call it with identical arguments.  Returns `connected`; when not connected, explored[0..*n_explored) holds the
 // cube-relative ids of the visited "unknown" cells (decode with explore_decode).  Shared scratch: sh[0..1] queue
@@ -420,8 +465,10 @@ __device__ __forceinline__ void explore_decode(const ExploreWs& w, const int rel
   dy = (rel / w.side) % w.side - w.rm;
   dx = rel % w.side - w.rm;
 }
+template <bool PATCH>
 __device__ bool explore_to_ground_block(const float* score, const Geom& g, const int ox, const int oy, const int oz, const float unknown_thr, const float ground_thr,
-                                        const float maxd, const unsigned epoch, const ExploreWs& w, int* sh)
+                                        const float maxd, const unsigned epoch, const ExploreWs& w, int* sh, const PatchDesc* pd = nullptr,
+                                        const uint32_t* words = nullptr)
 {
   const int tid = threadIdx.x;
   const int side = w.side, side2 = w.side * w.side, rm = w.rm;
@@ -459,8 +506,7 @@ __device__ bool explore_to_ground_block(const float* score, const Geom& g, const
       int dx, dy, dz;
       explore_decode(w, rel, dx, dy, dz);
       const int x = ox + dx, y = oy + dy, z = oz + dz;
-      const long long ci = cell_index(g, x, y, z);
-      const float val = ci >= 0 ? score[ci] : 0.0f;
+      const float val = cls_load<PATCH>(score, g, pd, words, x, y, z);
       if (val > ground_thr)  // :423 -> connected
         sh[3] = 1;
       else if (val > unknown_thr)  // :427
@@ -520,7 +566,7 @@ __global__ void __launch_bounds__(256) k_explore_single(const float* score, cons
   }
   __syncthreads();
   const int ox = coord_to_idx1(x, g.off[0], g.inv), oy = coord_to_idx1(y, g.off[1], g.inv), oz = coord_to_idx1(z, g.off[2], g.inv);
-  const bool connected = explore_to_ground_block(score, g, ox, oy, oz, unknown_thr, ground_thr, maxd, s_epoch, w, sh);
+  const bool connected = explore_to_ground_block<false>(score, g, ox, oy, oz, unknown_thr, ground_thr, maxd, s_epoch, w, sh);
   const int ne = connected ? 0 : sh[2];
   for (int t = threadIdx.x; t < ne && (size_t)t < cap; t += blockDim.x)
   {
@@ -537,13 +583,16 @@ __global__ void __launch_bounds__(256) k_explore_single(const float* score, cons
   }
 }
 
-// K14 + K15 — one block, sequential over clusters (see file header)
+// K14 + K15 — one block, sequential over clusters (see file header).  PATCH: slab mode, the map is read through the exchanged boxes.
+template <bool PATCH>
 __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const ScanDyn* __restrict__ dyn, float* score, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx,
                                                       const int* __restrict__ seg_start, vofod_cluster_info* __restrict__ infos, const ExploreWs w,
                                                       double* __restrict__ terms, vofod_detection* __restrict__ dets, unsigned long long* __restrict__ counters,
-                                                      const unsigned long long* __restrict__ d_nfar)
+                                                      const unsigned long long* __restrict__ d_nfar, const PatchSet ps)
 {
   pdl_enter();
+  const int n_patch = PATCH ? (int)ps.meta[0] : 0;
+  int next_patch = 0;
   __shared__ int sh[4];
   __shared__ unsigned s_epoch;
   __shared__ unsigned long long s_det_id, s_ndet;
@@ -562,12 +611,21 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
   {
     if (infos[c].cclass != CLS_CANDIDATE)
       continue;  // uniform: every thread reads the same global word
+    const PatchDesc* pd = nullptr;
+    if (PATCH)
+    {
+      // the boxes were laid out in this order; a candidate without a box (buffer overflow, reported to the host) stays unclassified
+      if (next_patch < n_patch && ps.desc[next_patch].far_idx == (int)c)
+        pd = ps.desc + next_patch++;
+      else
+        continue;
+    }
     bool is_floating = true;
     if (active)
     {
       const int label = infos[c].label, n = infos[c].n_points;
       const uint32_t* idcs = sidx + seg_start[label];
-      const int R = (int)(((double)infos[c].obb_size + a.max_explore_distance) / (double)g.vs);  // :1698
+      const int R = cls_explore_radius(infos[c].obb_size, a.max_explore_distance, g.vs);  // :1698
       for (int k = 0; k < n && is_floating; k++)
       {
         const vofod_vox v = vox[idcs[k]];
@@ -580,7 +638,7 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
             s_epoch = 1u;
         }
         __syncthreads();
-        const bool connected = explore_to_ground_block(score, g, ox, oy, oz, a.thr_frontiers, a.thr_new, (float)R, s_epoch, w, sh);
+        const bool connected = explore_to_ground_block<PATCH>(score, g, ox, oy, oz, a.thr_frontiers, a.thr_new, (float)R, s_epoch, w, sh, pd, ps.words);
         if (connected)
           is_floating = false;
         else
@@ -594,6 +652,13 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
             const long long ci = cell_index(g, ox + dx, oy + dy, oz + dz);
             if (ci >= 0)
               score[ci] = a.thr_frontiers;
+            if (PATCH)  // every box that holds the cell (later explorations and the detections' submaps read them)
+              for (int q = 0; q < n_patch; q++)
+              {
+                const long long pw = patch_cell(ps.desc[q], ox + dx, oy + dy, oz + dz);
+                if (pw >= 0)
+                  ps.words[pw] = __float_as_uint(a.thr_frontiers);
+              }
           }
         }
         __syncthreads();
@@ -607,8 +672,17 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
   }
 
   // ---- extractDetections (:834-879) ----
+  next_patch = 0;
   for (unsigned long long c = 0; c < n_far; c++)
   {
+    const PatchDesc* pd = nullptr;
+    if (PATCH)
+    {
+      while (next_patch < n_patch && ps.desc[next_patch].far_idx < (int)c)
+        next_patch++;
+      if (next_patch < n_patch && ps.desc[next_patch].far_idx == (int)c)
+        pd = ps.desc + next_patch;
+    }
     if (infos[c].cclass != VOFOD_CLASS_MAV)
       continue;
     const vofod_cluster_info ci = infos[c];
@@ -633,8 +707,7 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
       for (int t = tid; t < (int)ncell; t += blockDim.x)
       {
         const int x = t % ssz[0], y = (t / ssz[0]) % ssz[1], z = t / (ssz[0] * ssz[1]);
-        const long long cell = cell_index(g, x + lo[0], y + lo[1], z + lo[2]);
-        const float val = cell >= 0 ? score[cell] : 0.0f;
+        const float val = cls_load<PATCH>(score, g, pd, ps.words, x + lo[0], y + lo[1], z + lo[2]);
         terms[t] = 1.0 - (double)val / a.score_ray;  // :862
       }
       __syncthreads();
@@ -697,6 +770,79 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
   }
 }
 
+// ---- slab mode: lay out and pack the candidates' boxes --------------------------------------------------------------------------
+// one thread: boxes in classification order (few candidates: clusters that passed the size / distance / point-count gates)
+__global__ void k_patch_layout(const ClsArgs a, const vofod_cluster_info* __restrict__ infos, const unsigned long long* __restrict__ d_nfar, const PatchSet ps)
+{
+  pdl_enter();
+  const unsigned long long n_far = *after_wait(d_nfar);
+  const Geom& g = a.g;
+  unsigned used = 0;
+  int n = 0;
+  unsigned long long overflow = 0ull;
+  for (unsigned long long c = 0; c < n_far; c++)
+  {
+    if (infos[c].cclass != CLS_CANDIDATE)
+      continue;
+    int R = cls_explore_radius(infos[c].obb_size, a.max_explore_distance, g.vs) + 1;
+    if (R < 3)
+      R = 3;  // the detection's submap reaches 2 voxels beyond the AABB (:850)
+    PatchDesc d;
+    unsigned long long vol = 1;
+    for (int q = 0; q < 3; q++)
+    {
+      int mn = coord_to_idx1(infos[c].aabb_min[q], g.off[q], g.inv) - R, mx = coord_to_idx1(infos[c].aabb_max[q], g.off[q], g.inv) + R;
+      mn = mn < 0 ? 0 : mn;
+      mx = mx > g.size[q] - 1 ? g.size[q] - 1 : mx;
+      d.lo[q] = mn;
+      d.size[q] = mx >= mn ? mx - mn + 1 : 0;
+      vol *= (unsigned long long)d.size[q];
+    }
+    if (n >= PATCH_MAX || used + vol > (unsigned long long)ps.budget)
+    {
+      overflow = 1ull;
+      break;
+    }
+    d.off = used;
+    d.far_idx = (int)c;
+    ps.desc[n++] = d;
+    used += (unsigned)vol;
+  }
+  ps.meta[0] = (unsigned long long)n;
+  ps.meta[1] = (unsigned long long)used;
+  ps.meta[2] = overflow;
+}
+// every word of the buffer: the bit pattern of the cell when this slab owns it, zero otherwise (and zero behind the last box)
+__global__ void __launch_bounds__(256) k_patch_fill(const float* __restrict__ score, const Geom g, const PatchSet ps)
+{
+  pdl_enter();
+  __shared__ PatchDesc sd[PATCH_MAX];
+  const int n = (int)*after_wait(ps.meta);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    sd[i] = ps.desc[i];
+  __syncthreads();
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < (size_t)ps.budget; w += (size_t)gridDim.x * blockDim.x)
+  {
+    int q = n - 1;
+    while (q >= 0 && (size_t)sd[q].off > w)
+      q--;
+    uint32_t v = 0u;
+    if (q >= 0)
+    {
+      const size_t r = w - sd[q].off;
+      const size_t sxy = (size_t)sd[q].size[0] * sd[q].size[1];
+      if (r < sxy * (size_t)sd[q].size[2])
+      {
+        const int z = (int)(r / sxy) + sd[q].lo[2], y = (int)((r % sxy) / sd[q].size[0]) + sd[q].lo[1], x = (int)(r % sd[q].size[0]) + sd[q].lo[0];
+        const long long ci = cell_index(g, x, y, z);
+        if (ci >= 0 && cell_owned(g, x, y, z))
+          v = __float_as_uint(score[ci]);
+      }
+    }
+    ps.words[w] = v;
+  }
+}
+
 static int bits_for_u(unsigned long long v)
 {
   int b = 0;
@@ -720,14 +866,15 @@ int vf_classify_prefill(vofod_ctx* ctx, size_t m_cap)
 }
 
 // phase 1: everything that only looks at the voxel list (far clusters, member lists, moments of inertia + gates);
-// phase 2: the sequential part that reads and writes the map (exploreToGround, detections); phase 0: both.
+// phase 2: the sequential part that reads and writes the map (exploreToGround, detections); phase 0: both;
+// slab mode: 1, then 3 (lay out + pack the candidates' boxes for the cross-slab sum), then 4 (phase 2 on the summed boxes).
 // Inside a scan phase 1 runs on the side branch next to the point update and the ray apply.
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
                            const vofod_params& p, int phase)
 {
   using namespace prims;
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  if (phase != 2)
+  if (phase != 2 && phase != 3 && phase != 4)
   {
     ZERO_CNT(CNT_NDET, 1);
     ZERO_CNT(CNT_NFARPTS, 1);
@@ -775,7 +922,7 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
     if (a.n_exact < 64)
       a.n_exact = 64;
   }
-  if (phase != 2)
+  if (phase != 2 && phase != 3 && phase != 4)
   {
   ENSURE(ctx->far_list, np * 4);            // member lists
   ENSURE(ctx->cls_sizes, m_cap * 4);
@@ -807,6 +954,20 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   }
   if (phase == 1)
     return 0;
+  PatchSet ps = {};
+  if (phase == 3 || phase == 4)
+  {
+    ps.desc = ctx->slab_patch_desc.as<PatchDesc>();
+    ps.words = ctx->slab_patch.as<uint32_t>();
+    ps.meta = ctx->slab_patch_meta.as<unsigned long long>();
+    ps.budget = (unsigned)ctx->slab_patch_words;
+  }
+  if (phase == 3)
+  {
+    LAUNCH(k_patch_layout, 1, 1, 0, a, ctx->cl_info.as<vofod_cluster_info>(), cnt + CNT_NFARPTS, ps);
+    LAUNCH(k_patch_fill, vf_blocks(ctx, ctx->slab_patch_words, 256, 8), 256, 0, ctx->score.as<float>(), ctx->g, ps);
+    return 0;
+  }
   int* qbase = ctx->cls_queues.as<int>();
   ExploreWs w;
   w.stamps = ctx->explore_ws.as<unsigned>();
@@ -815,8 +976,12 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   w.explored = qbase + 2 * cube;
   w.side = side;
   w.rm = rmax;
-  LAUNCH(k_classify_seq, 1, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w, ctx->cls_terms.as<double>(),
-         ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS);
+  if (phase == 4)
+    LAUNCH(k_classify_seq<true>, 1, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w,
+           ctx->cls_terms.as<double>(), ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS, ps);
+  else
+    LAUNCH(k_classify_seq<false>, 1, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w,
+           ctx->cls_terms.as<double>(), ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS, ps);
   return 0;
 }
 

@@ -333,6 +333,19 @@ struct vofod_ctx
   int slab_halo = 0;
   size_t slab_n = 0;            // rays of the scan between vofod_slab_scan_begin and _end (0 = none in flight)
   int slab_raycast_status = 0;
+  // slab mode v2 (slab.cu): exchanged buffers and the scan in flight between two phases
+  DevBuf slab_patch, slab_patch_desc, slab_patch_meta;  // candidates' boxes for the classification (classify.cu: PatchSet)
+  size_t slab_patch_words = 0;
+  DevBuf slab_bg_send, slab_bg_recv;                    // packed background-voxel lists of the sepclusters pass: own / every slab's
+  size_t slab_bg_cap = 0;                               // entries per slab (identical on every slab: it sizes the allgather)
+  int slab_next_phase = 0;
+  int slab_nranks = 1, slab_rank = 0;
+  bool slab_redo_sep = false;
+  bool slab_applied = false;
+  size_t slab_patch_words_forced = 0;                   // VOFOD_OPT_SLAB_PATCH_WORDS
+  vofod_params slab_p;
+  vofod_schedule slab_s;
+  void* nccl_comm = nullptr;                            // ncclComm_t (vofod_comm_init)
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool raycast_stats = false;   // instrumentation switch: the accumulate kernel fills ray_stats (see RAY_STATS_SLOTS in raycast.cu)
@@ -551,5 +564,9 @@ const uint8_t* vf_dirty_cols(vofod_ctx* ctx, float thr, const vofod_params* p); 
 // classify.cu
 int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_labels, const uint8_t* d_in_close, const unsigned long long* d_m, size_t m_cap,
                            const vofod_params& p, int phase = 0);  // sensor position comes from ctx->dyn
+// slab.cu
+void vf_slab_destroy(vofod_ctx* ctx);
 // sepclusters.cu
-int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap = 0);
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap = 0, int slab_ranks = 0);
+int vf_sep_slab_pack(vofod_ctx* ctx, const vofod_params& p, size_t cap);
+int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks);

@@ -151,7 +151,8 @@ int vofod_destroy(vofod_ctx* ctx)
     return VOFOD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->upd_owner, &ctx->upd_leftover, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vgh_cnt, &ctx->vgh_bits, &ctx->vgh_list, &ctx->cl_cellkey, &ctx->cl_words, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
+  vf_slab_destroy(ctx);
+  DevBuf* bufs[] = {&ctx->slab_patch, &ctx->slab_patch_desc, &ctx->slab_patch_meta, &ctx->slab_bg_send, &ctx->slab_bg_recv, &ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->upd_owner, &ctx->upd_leftover, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vgh_cnt, &ctx->vgh_bits, &ctx->vgh_list, &ctx->cl_cellkey, &ctx->cl_words, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
                     &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
@@ -270,6 +271,12 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->alloc_gen++;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_SLAB_PATCH_WORDS)
+  {
+    ctx->slab_patch_words_forced = value > 0 ? (size_t)value : 0;
+    ctx->slab_patch_words = 0;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_RAYCAST_NO_AGG)
   {
     ctx->raycast_no_agg = value != 0;
@@ -280,6 +287,32 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
 }
 
 void* vofod_stream(vofod_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+/* stream-ordered copies between host memory and a device buffer the library handed out (vofod_slab_exchanges): lets a host loop
+ * combine the exchange buffers of several contexts that share one device */
+int vofod_dev_read(vofod_ctx* ctx, const void* dev, void* host, size_t bytes)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (bytes && (!dev || !host))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  if (bytes)
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VOFOD_OK;
+}
+int vofod_dev_write(vofod_ctx* ctx, void* dev, const void* host, size_t bytes)
+{
+  if (!ctx)
+    return vf_fail(nullptr, VOFOD_E_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (bytes && (!dev || !host))
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  if (bytes)
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VOFOD_OK;
+}
 uint64_t vofod_kernel_launches(const vofod_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
 void vofod_default_params(vofod_params* p)

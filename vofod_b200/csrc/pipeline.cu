@@ -1131,145 +1131,3 @@ int vofod_last_clusters(vofod_ctx* ctx, vofod_cluster_info* out, size_t cap, siz
 }
 }  // extern "C"
 
-// ======================================================================================================
-// slab mode: the mapping stages of one scan in two phases around the cross-slab exchange (see slab.cu)
-// ======================================================================================================
-extern "C" {
-
-int vofod_slab_scan_begin(vofod_ctx* ctx, const vofod_pt* scan, int scan_on_device, size_t n, const vofod_pose* tf, const vofod_params* p, const vofod_schedule* s)
-{
-  NEED_MAP();
-  if (!scan || !tf || !p || !s)
-    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
-  if (!ctx->W || n != (size_t)ctx->W * ctx->H)
-    return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
-  if (!p->raycast_new_update_rule && s->do_raycast && ctx->slab_on)
-    return vf_fail(ctx, VOFOD_E_INVALID, "slab mode supports the new raycast update rule only (the old rule needs a global max)");
-  const vofod_pt* d_scan = scan;
-  if (!scan_on_device)
-  {
-    ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
-    CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
-    d_scan = ctx->scan_staging.as<vofod_pt>();
-  }
-  ctx->slab_raycast_status = VOFOD_W_PAUSED;
-  if (s->do_raycast)
-  {
-    ctx->slab_raycast_status = vf_raycast_prepare(ctx, n, *tf, *p);
-    if (ctx->slab_raycast_status < 0)
-      return ctx->slab_raycast_status;
-  }
-  ScanDyn* hd = ctx->h_dyn;
-  memcpy(hd->tf.R, tf->R, sizeof(tf->R));
-  memcpy(hd->tf.t, tf->t, sizeof(tf->t));
-  for (int a = 0; a < 3; a++)
-    hd->range_pt[a] = s->range_pt[a];
-  hd->n_seeds = s->n_range_seeds > 0 ? s->n_range_seeds : 0;
-  hd->scan = d_scan;
-  hd->its_raycast = s->raycast_its_diff > 1 ? s->raycast_its_diff : 1;
-  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  RET(vf_begin_call(ctx));
-  RET(vf_dyn_push(ctx));
-  RET(vf_range_update_dev(ctx, *p));
-  RET(vf_filter_voxelize_dev(ctx, n, *p));
-  ENSURE(ctx->labels, n * 4);
-  RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p->ground_points_max_distance, ctx->labels.as<int>(),
-                     cnt + CNT_NCLUSTERS));
-  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 1, false));
-  ctx->slab_n = n;
-  return VOFOD_OK;
-}
-
-int vofod_slab_exchange_buffers(vofod_ctx* ctx, void** d_n_bg, void** d_cluster_close, size_t* n_cluster_close)
-{
-  NEED_MAP();
-  if (!ctx->slab_n || !d_n_bg || !d_cluster_close || !n_cluster_close)
-    return vf_fail(ctx, VOFOD_E_STATE, "vofod_slab_exchange_buffers: no scan in flight / NULL argument");
-  *d_n_bg = vf_cnt(ctx, CNT_NBG);            /* u64[1]: SUM over slabs */
-  *d_cluster_close = ctx->cl_close.p;        /* i32[n]: MAX over slabs */
-  *n_cluster_close = ctx->slab_n;
-  return VOFOD_OK;
-}
-
-int vofod_slab_scan_end(vofod_ctx* ctx, const vofod_params* p, const vofod_schedule* s, vofod_scan_result* res)
-{
-  NEED_MAP();
-  if (!p || !s || !ctx->slab_n)
-    return vf_fail(ctx, VOFOD_E_STATE, "vofod_slab_scan_end without vofod_slab_scan_begin");
-  const size_t n = ctx->slab_n;
-  ctx->slab_n = 0;
-  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, *p, 2, true));
-  RET(vf_update_points_scan_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, *p));
-  ctx->detection_its++;
-  int raycast_status = ctx->slab_raycast_status;
-  bool applied = false;
-  if (s->do_raycast && raycast_status == VOFOD_OK)
-  {
-    RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), *p));
-    const int rc = vf_raycast_apply_dev(ctx, 0, *p);
-    if (rc < 0)
-      return rc;
-    applied = rc == VOFOD_OK;
-  } else
-  {
-    CK(cudaMemsetAsync(cnt + CNT_TRAVERSALS, 0, 8, ctx->stream));
-    CK(cudaMemsetAsync(cnt + CNT_OOB, 0, 8, ctx->stream));
-  }
-  CK(cudaMemcpyAsync(ctx->pinned, cnt, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  const unsigned long long* hp = (const unsigned long long*)ctx->pinned;
-  if (hp[CNT_WATCHDOG])
-    return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", hp[CNT_WATCHDOG]);
-  if (hp[CNT_OOB])
-    return vf_fail(ctx, VOFOD_E_INTERNAL, "%llu traversals fell outside the accumulator window", hp[CNT_OOB]);
-  if (applied)
-  {
-    if (hp[CNT_APPLY_ANY])
-      ctx->flags_full_dirty = false;
-    else
-      raycast_status = VOFOD_W_EMPTY_RAYCAST;
-  }
-  ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
-  ctx->last_m = (size_t)hp[CNT_VG_M];
-  ctx->last_far = 0;
-  if (res)
-  {
-    memset(res, 0, sizeof(*res));
-    res->n_traversals = hp[CNT_TRAVERSALS];
-    res->n_bg = hp[CNT_NBG];
-    res->n_filtered = (uint32_t)hp[CNT_VG_NVALID];
-    res->n_voxels = (uint32_t)hp[CNT_VG_M];
-    res->n_clusters = (uint32_t)hp[CNT_NCLUSTERS];
-    res->n_close_clusters = (uint32_t)hp[CNT_NCLOSE];
-    res->n_far_clusters = (uint32_t)hp[CNT_NFAR];
-    res->background_pts_sufficient = ctx->background_pts_sufficient;
-    res->sure_background_sufficient = ctx->sure_background_sufficient;
-    res->raycast_status = raycast_status;
-    res->sep_status = VOFOD_W_PAUSED;
-  }
-  return VOFOD_OK;
-}
-
-/* host access to the exchange buffers, for emulating several slabs on one device */
-int vofod_slab_exchange_io(vofod_ctx* ctx, uint64_t* n_bg, int32_t* cluster_close, size_t n, int to_device)
-{
-  NEED_MAP();
-  if (!n_bg || (n && !cluster_close) || n > ctx->slab_n)
-    return vf_fail(ctx, VOFOD_E_INVALID, "vofod_slab_exchange_io: bad arguments");
-  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-  if (to_device)
-  {
-    CK(cudaMemcpyAsync(vf_cnt(ctx, CNT_NBG), n_bg, 8, kind, ctx->stream));
-    if (n)
-      CK(cudaMemcpyAsync(ctx->cl_close.p, cluster_close, n * 4, kind, ctx->stream));
-  } else
-  {
-    CK(cudaMemcpyAsync(n_bg, vf_cnt(ctx, CNT_NBG), 8, kind, ctx->stream));
-    if (n)
-      CK(cudaMemcpyAsync(cluster_close, ctx->cl_close.p, n * 4, kind, ctx->stream));
-  }
-  CK(cudaStreamSynchronize(ctx->stream));
-  return VOFOD_OK;
-}
-}  // extern "C"

@@ -358,7 +358,94 @@ int vf_sepclusters_prefill(vofod_ctx* ctx, const vofod_params& p)
 // k_cap == 0: exact mode (one host read-back sizes the background-voxel list).  k_cap > 0: the list is capped at k_cap rows and
 // nothing returns to the host; when the true count exceeds k_cap the pass leaves the map untouched and the caller, who sees
 // CNT_SEP_K > k_cap in its read-back, repeats it in exact mode.
-int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap)
+// ---- slab mode (slab.cu): the background voxels of all slabs, gathered ------------------------------------------------------------
+// Every slab compacts the cells it OWNS (x-outer / z-inner, global index coordinates) and packs them as
+//   word 0 = its true count, word 1 + i = global linear cell index | (value > sure threshold) << 31.
+// After the allgather (fixed capacity per slab) every slab unpacks the segments in rank order — slabs cut the x axis in ascending
+// order, so the concatenation IS the reference's emission order over the whole map — and runs the rest of the pass replicated on the
+// same list; the decay touches the cells a slab holds.
+__global__ void __launch_bounds__(256) k_sep_slab_pack(const vofod_xyzi* __restrict__ raw, const unsigned long long* __restrict__ d_k, const size_t cap, const Geom g,
+                                                       const float thr_sure, uint32_t* __restrict__ send)
+{
+  pdl_enter();
+  const unsigned long long k_true = *after_wait(d_k);
+  const size_t k = k_true < cap ? (size_t)k_true : cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    send[0] = k_true > 0xffffffffull ? 0xffffffffu : (uint32_t)k_true;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const vofod_xyzi v = raw[i];
+    const unsigned lin = (unsigned)((int)v.x + ((int)v.y + (int)v.z * g.size[1]) * g.size[0]);
+    send[1 + i] = lin | (v.intensity > thr_sure ? 0x80000000u : 0u);
+  }
+}
+__global__ void __launch_bounds__(256) k_sep_slab_unpack(const uint32_t* __restrict__ recv, const int nranks, const size_t cap, const Geom g, vofod_xyzi* __restrict__ raw,
+                                                         unsigned long long* __restrict__ counters)
+{
+  pdl_enter();
+  __shared__ unsigned long long s_off[65];
+  __shared__ int s_over;
+  if (threadIdx.x == 0)
+  {
+    unsigned long long o = 0;
+    int over = 0;
+    for (int r = 0; r < nranks; r++)
+    {
+      s_off[r] = o;
+      const unsigned long long c = after_wait(recv)[(size_t)r * (cap + 1)];
+      over |= c > cap;
+      o += c < cap ? c : cap;
+    }
+    s_off[nranks] = o;
+    s_over = over;
+    if (blockIdx.x == 0)
+      // an overflowing slab: report a count above every capacity, the pass then leaves the map untouched (k_sep_decay) and the host redoes it
+      counters[CNT_SEP_K] = over ? ~0ull >> 1 : o;
+  }
+  __syncthreads();
+  if (s_over)
+    return;
+  const size_t total = (size_t)s_off[nranks];
+  const size_t sxy = (size_t)g.size[0] * g.size[1];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    int r = 0;
+    while (i >= s_off[r + 1])
+      r++;
+    const uint32_t w = recv[(size_t)r * (cap + 1) + 1 + (i - s_off[r])];
+    const unsigned lin = w & 0x7fffffffu;
+    vofod_xyzi v;
+    v.x = (float)(lin % (unsigned)g.size[0]);
+    v.y = (float)((lin / (unsigned)g.size[0]) % (unsigned)g.size[1]);
+    v.z = (float)(lin / sxy);
+    v.intensity = (w >> 31) ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);  // only "> sure threshold" is ever asked of it (voxel_grid_counted.cpp:185-187)
+    raw[i] = v;
+  }
+}
+// phase A: this slab's list into ctx->slab_bg_send ((cap + 1) words)
+int vf_sep_slab_pack(vofod_ctx* ctx, const vofod_params& p, size_t cap)
+{
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  if (geom_cells(ctx->g) <= 0 || (long long)ctx->g.size[0] * ctx->g.size[1] * ctx->g.size[2] >= (1ll << 31))
+    return vf_fail(ctx, VOFOD_E_INVALID, "slab sepclusters: the global grid must have fewer than 2^31 cells");
+  RET(vf_compact_over_dev(ctx, (float)p.thr_new_obstacles, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, nullptr, cap, &p));
+  LAUNCH(k_sep_slab_pack, vf_blocks(ctx, cap, 256, 8), 256, 0, ctx->sep_raw.as<vofod_xyzi>(), cnt + CNT_SEP_K, cap, ctx->g, (float)p.thr_sure_obstacles,
+         ctx->slab_bg_send.as<uint32_t>());
+  return 0;
+}
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap, int slab_ranks);
+// phase B: the gathered lists (ctx->slab_bg_recv, nranks x (cap + 1) words) -> the rest of the pass
+int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks)
+{
+  unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
+  const size_t K = cap * (size_t)nranks;
+  ENSURE(ctx->sep_raw, prims::padded(K) * sizeof(vofod_xyzi));
+  LAUNCH(k_sep_slab_unpack, vf_blocks(ctx, K, 256, 8), 256, 0, ctx->slab_bg_recv.as<uint32_t>(), nranks, cap, ctx->g, ctx->sep_raw.as<vofod_xyzi>(), cnt);
+  return vf_sepclusters_dev(ctx, its_diff, p, K, nranks);
+}
+
+// slab_ranks > 0: the raw list (ctx->sep_raw, CNT_SEP_K) is there already (vf_sep_slab_finish)
+int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap, int slab_ranks)
 {
   if (p.sep_pause)
     return VOFOD_W_PAUSED;
@@ -375,7 +462,7 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
     return vf_fail(ctx, VOFOD_E_INVALID, "sepclusters: max_bg_distance/voxel_size <= 1 gives a zero leaf size (the reference divides by it)");
   size_t K = k_cap;
   const unsigned long long* d_kds = cnt + CNT_SEP_KDS;
-  bool fast = lsz == 1.0f && !ctx->sep_force_general && !ctx->slab_on;
+  bool fast = lsz == 1.0f && !ctx->sep_force_general && !ctx->slab_on && slab_ranks == 0;
   if (fast)
   {
     const int frc = sep_fast_lists(ctx, thr_new, thr_sure, p, k_cap == 0 ? &K : nullptr, k_cap);
@@ -393,7 +480,9 @@ int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size
   if (!fast)
   {
     K = k_cap;
-    if (k_cap == 0)
+    if (slab_ranks > 0)
+      ;
+    else if (k_cap == 0)
     {
       RET(vf_compact_over_dev(ctx, thr_new, 1, 0, ctx->sep_raw, cnt + CNT_SEP_K, &K, 0, &p));
       if (K == 0)

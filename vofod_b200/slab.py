@@ -1,26 +1,77 @@
-"""Large-map mode (BASELINE.json configs[4]): the grid is cut into spatial slabs along x, one slab per GPU / process.
+"""Large-map mode (BASELINE.json configs[4]): the grid is cut into spatial slabs along x, one slab per GPU / process
+(vofod_b200/csrc/slab.cu says what is sharded, what is replicated and what crosses slabs).
 
-Per scan: rank 0 holds the scan -> NCCL broadcast of the packed scan (5.2 MB) and of the pose / seed record -> every rank runs
-vofod_slab_scan_begin on the broadcast buffer (device pointer) -> NCCL all-reduce of the two exchange buffers (SUM of the
-8-byte background count, MAX of the per-cluster close flags), enqueued on the library's own stream so that nothing waits on the
-host -> vofod_slab_scan_end.  See vofod_b200/csrc/slab.cu for why halos need no exchange."""
+Two drivers over the same four-phase scan of the library:
+  * SlabWorker     — one process per GPU: the library's own NCCL path (vofod_comm_init + vofod_slab_process_scan): scan broadcast,
+                     all-reduces and all-gather on the library's stream, one host wait per scan.  torch.distributed only carries the
+                     128-byte NCCL id to the other ranks.
+  * run_emulated   — several slabs as several contexts on ONE device, the exchange buffers combined by a host loop (tests)."""
 import ctypes as C
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
 from . import abi, multi
 
 
-class _Raw:
-    """__cuda_array_interface__ view of a raw device pointer, so that torch can wrap library-owned memory."""
+def make_slabs(ctxs, params, voxel_size, sensor_wh, dirs, halo, axis=0, offs=None, mask=None):
+    """reset every context, give it its slab of the grid and the sensor"""
+    W, H = sensor_wh
+    n = len(ctxs)
+    for r, g in enumerate(ctxs):
+        g.reset(params, voxel_size)
+        sizes = list(g.map_info().sizes)
+        lo, hi = multi.partition(sizes[axis], r, n)
+        g.set_slab(axis, lo, hi, halo)
+        g.map_set_to(abi.MAP_SCORE, params.score_init)
+        g.set_sensor(W, H, dirs, offs, mask)
+        g.slab_set_world(r, n)
 
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+_NP = {abi.XCHG_SUM_U64: np.uint64, abi.XCHG_MAX_I32: np.int32, abi.XCHG_SUM_U32: np.uint32, abi.XCHG_GATHER_U32: np.uint32}
+
+
+def _combine(ctxs, phase):
+    lists = [g.slab_exchanges(phase) for g in ctxs]
+    for j in range(len(lists[0])):
+        kind, count = lists[0][j].kind, lists[0][j].count
+        assert all(x[j].kind == kind and x[j].count == count for x in lists)
+        parts = [g.dev_read(x[j].buf, _NP[kind], count) for g, x in zip(ctxs, lists)]
+        if kind == abi.XCHG_GATHER_U32:
+            allp = np.concatenate(parts)
+            for g, x in zip(ctxs, lists):
+                g.dev_write(x[j].gather_out, allp)
+            continue
+        if kind == abi.XCHG_MAX_I32:
+            comb = np.maximum.reduce(parts)
+        else:
+            comb = np.add.reduce(np.stack(parts), axis=0, dtype=_NP[kind])
+        for g, x in zip(ctxs, lists):
+            g.dev_write(x[j].buf, comb)
+
+
+def run_emulated(ctxs, scan, pose, params, sched, det_cap=256):
+    """one slab-mode scan on every context of `ctxs` (all slabs of one map); returns [(ScanResult, detections)] per slab"""
+    for g in ctxs:
+        g.slab_phase(0, scan, pose, params, sched)
+    _combine(ctxs, 0)
+    for g in ctxs:
+        g.slab_phase(1)
+    _combine(ctxs, 1)
+    while True:
+        for g in ctxs:
+            g.slab_phase(2)
+        _combine(ctxs, 2)
+        out = [g.slab_phase(3, det_cap=det_cap) for g in ctxs]
+        codes = {o[0] for o in out}
+        assert len(codes) == 1, codes  # every slab sees the same gathered counts
+        if codes == {abi.VOFOD_W_REDO}:
+            continue
+        return [(o[1], o[2]) for o in out]
 
 
 class SlabWorker:
+    """one slab of the map in this process; rank / world come from torch.distributed (NCCL or gloo: it only ships the NCCL id)"""
+
     def __init__(self, ctx, params, voxel_size, sensor_wh, dirs, rank, world, halo=16, axis=0):
         self.v, self.p, self.rank, self.world = ctx, params, rank, world
         W, H = sensor_wh
@@ -30,40 +81,24 @@ class SlabWorker:
         ctx.set_slab(axis, lo, hi, halo)
         ctx.map_set_to(abi.MAP_SCORE, params.score_init)
         ctx.set_sensor(W, H, dirs)
-        self.n = W * H
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.dev)
-        self.scan_dev = torch.empty(self.n * abi.PT_DTYPE.itemsize, dtype=torch.uint8, device=self.dev)
-        self.meta = torch.empty(16, dtype=torch.float32, device=self.dev)  # R[9], t[3], range_pt[3], pad
+        uid = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            buf = np.zeros(128, dtype=np.uint8)
+            if rank == 0:
+                rc = ctx.lib.vofod_comm_unique_id(buf.ctypes.data_as(C.c_void_p))
+                assert rc == 0, "libnccl.so.2 not loadable"
+            t = torch.from_numpy(buf)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            uid = t.cpu().numpy().tobytes()
+        ctx.comm_init(rank, world, uid)
 
-    def step(self, scan_host_pinned, pose, range_pt, do_raycast=True):
-        """scan_host_pinned / pose / range_pt are read on rank 0 only.  Returns the vofod_scan_result of this slab."""
-        with torch.cuda.stream(self.stream):
-            if self.rank == 0:
-                self.scan_dev.copy_(scan_host_pinned, non_blocking=True)
-                m = np.zeros(16, dtype=np.float32)
-                m[:9], m[9:12], m[12:15] = list(pose.R), list(pose.t), list(range_pt)
-                self.meta.copy_(torch.from_numpy(m))
-            if self.world > 1:
-                dist.broadcast(self.scan_dev, src=0)
-                dist.broadcast(self.meta, src=0)
-            m = self.meta.cpu().numpy()
-            pose = abi.Pose.from_arrays(m[:9], m[9:12])
-            s = abi.schedule_s1(m[12:15], do_raycast=do_raycast, do_classify=False, do_sepclusters=False)
-            self.v.slab_scan_begin(None, pose, self.p, s, device_ptr=self.scan_dev.data_ptr())
-            if self.world > 1:
-                p_nbg, p_close, n = self.v.slab_exchange_buffers()
-                nbg = torch.as_tensor(_Raw(p_nbg, 1, "<i8"), device=self.dev)
-                close = torch.as_tensor(_Raw(p_close, n, "<i4"), device=self.dev)
-                dist.all_reduce(nbg, op=dist.ReduceOp.SUM)
-                dist.all_reduce(close, op=dist.ReduceOp.MAX)
-            return self.v.slab_scan_end(self.p, s)
+    def step(self, scan_host, pose, sched):
+        """scan_host is read on rank 0 only; pose and schedule are given on every rank.  -> (ScanResult, detections)"""
+        return self.v.slab_process_scan(scan_host if self.rank == 0 else None, pose, self.p, sched)
 
     def close(self):
-        """Release every torch object that lives on the library's stream BEFORE the context (and with it the stream) goes away."""
-        torch.cuda.synchronize()
-        self.scan_dev = None
-        self.meta = None
-        self.stream = None
-        torch.cuda.empty_cache()
         self.v.close()

@@ -5,7 +5,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: every fp32/fp64 mul+add stays separately rounded, like the reference's x86-64 build without -march
 NVFLAGS  := -std=c++17 -O3 $(ARCH) -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall
 CSRC     := vofod_b200/csrc
-OBJ      := build/ctx.o build/raycast.o build/voxelgrid.o build/cluster.o build/pipeline.o build/classify.o build/sepclusters.o build/slab.o
+OBJ      := build/ctx.o build/raycast.o build/voxelgrid.o build/cluster.o build/pipeline.o build/classify.o build/sepclusters.o build/slab.o build/apriori.o build/sensor.o
 HDR      := $(CSRC)/common.cuh $(CSRC)/prims.cuh include/vofod_cuda.h
 
 all: vofod_b200/libvofod_cuda.so oracle synth

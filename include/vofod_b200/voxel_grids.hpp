@@ -12,6 +12,16 @@
 
 namespace vofod_b200
 {
+// one library context per process for the filters that the nodelet default-constructs (`VoxelGridWeighted vgw;`, vofod_nodelet.cpp:661):
+// they hold no state between calls, only workspace
+inline vofod_ctx* shared_ctx(int device = 0)
+{
+  static vofod_ctx* ctx = nullptr;
+  if (!ctx && vofod_create(device, &ctx) != VOFOD_OK)
+    throw std::runtime_error(std::string("vofod_create: ") + vofod_last_error(nullptr));
+  return ctx;
+}
+
 template <class PointIn, class PointOut>
 class VoxelGridBase
 {

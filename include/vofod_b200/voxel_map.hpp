@@ -5,13 +5,17 @@
 //
 // Same types as the reference header: Eigen vectors, pcl::PointCloud<pcl::PointXYZI>, std::tuple index triples.  In a ROS
 // workspace <pcl/common/common.h> is the real PCL; in this repository's tests it is the stand-in of oracle/shim.
-// Not mirrored: visualization() / borderVisualization() / *VisualizationThreshold (RViz markers, out of scope).
+// visualization() builds its CUBE_LIST from the GPU compaction (the reference's x-outer / z-inner loop order is the compaction's
+// emission order); borderVisualization() / *VisualizationThreshold are host code.  Copies are deep (a new context on the same device), as
+// cheap as the reference's for the empty maps that live in every cluster_t (vofod_nodelet.cpp:110-119).
 // Differences a caller can observe: exploreToGround returns each explored cell once (the reference's DFS may list a cell
 // several times) and in a different order; the class is as thread-unsafe as the reference's.
 #pragma once
 #include <pcl/common/common.h>
+#include <visualization_msgs/Marker.h>
 #include <vofod_cuda.h>
 
+#include <algorithm>
 #include <functional>
 #include <limits>
 #include <stdexcept>
@@ -34,14 +38,33 @@ public:
   using vec3i_t = Eigen::Matrix<idx_t, 3, 1>;
   using idx3_t = std::tuple<idx_t, idx_t, idx_t>;
 
-  explicit VoxelMap(int device = 0) : m_device(device)
+  explicit VoxelMap(int device = 0) : m_device(device) {}  // the device context is created with the first resize
+  ~VoxelMap()
   {
-    if (vofod_create(device, &m_ctx) != VOFOD_OK)
-      throw std::runtime_error(std::string("vofod_create: ") + vofod_last_error(nullptr));  // no CPU fallback
+    if (m_ctx)
+      vofod_destroy(m_ctx);
   }
-  ~VoxelMap() { vofod_destroy(m_ctx); }
-  VoxelMap(const VoxelMap&) = delete;
-  VoxelMap& operator=(const VoxelMap&) = delete;
+  VoxelMap(const VoxelMap& o) : m_device(o.m_device) { *this = o; }
+  VoxelMap& operator=(const VoxelMap& o)
+  {
+    if (this == &o)
+      return *this;
+    m_thresholds = o.m_thresholds;
+    if (!o.m_ctx || o.size() == 0)
+    {
+      if (m_ctx)
+        vofod_destroy(m_ctx);
+      m_ctx = nullptr;
+      m_info = vofod_map_info{};
+      m_host.clear();
+      m_host_valid = m_host_dirty = false;
+      return *this;
+    }
+    resizeAs(o);
+    copyDataIdx(const_cast<VoxelMap&>(o));
+    to_device();
+    return *this;
+  }
   VoxelMap(VoxelMap&& o) noexcept { *this = std::move(o); }
   VoxelMap& operator=(VoxelMap&& o) noexcept
   {
@@ -53,19 +76,26 @@ public:
       o.m_ctx = nullptr;
       m_device = o.m_device;
       m_info = o.m_info;
+      o.m_info = vofod_map_info{};
       m_host = std::move(o.m_host);
       m_host_valid = o.m_host_valid;
       m_host_dirty = o.m_host_dirty;
+      m_thresholds = std::move(o.m_thresholds);
     }
     return *this;
   }
-  vofod_ctx* handle() { return m_ctx; }
+  vofod_ctx* handle()
+  {
+    need_ctx();
+    return m_ctx;
+  }
 
   // ---- modifiers (voxel_map.cpp:11-63, 268-285) ----
   void resize(const vec3_t& offset, const vec3i_t& sizes, const coord_t voxel_size)
   {
     const float off[3] = {offset.x(), offset.y(), offset.z()};
     const int32_t sz[3] = {sizes.x(), sizes.y(), sizes.z()};
+    need_ctx();
     ck(vofod_map_resize_idx(m_ctx, off, sz, voxel_size));
     after_resize();
   }
@@ -73,6 +103,7 @@ public:
   {
     const float c[3] = {center.x(), center.y(), center.z()};
     const float d[3] = {dimensions.x(), dimensions.y(), dimensions.z()};
+    need_ctx();
     ck(vofod_map_resize(m_ctx, c, d, voxel_size));
     after_resize();
   }
@@ -296,7 +327,88 @@ public:
       f(dd[i], idx[3 * i], idx[3 * i + 1], idx[3 * i + 2]);
   }
 
+  // ---- RViz markers (voxel_map.cpp:622-786) ----
+  void clearVisualizationThresholds() { m_thresholds.clear(); }
+  void addVisualizationThreshold(const data_t th, const std_msgs::ColorRGBA& th_color)
+  {
+    m_thresholds.emplace_back(th, th_color);
+    std::sort(std::begin(m_thresholds), std::end(m_thresholds), [](const auto& v1, const auto& v2) { return v1.first < v2.first; });
+  }
+  // CUBE_LIST of every voxel above the lowest threshold, coloured by the highest threshold it exceeds (:622-669).  The reference walks
+  // x (outer), y, z (inner) — the emission order of vofod_map_compact_over, so the cells come straight from the GPU compaction.
+  visualization_msgs::Marker visualization(const std_msgs::Header& header) const
+  {
+    visualization_msgs::Marker ret;
+    ret.header = header;
+    ret.pose.position.x = m_info.offset[0] + m_info.voxel_size / coord_t(2);
+    ret.pose.position.y = m_info.offset[1] + m_info.voxel_size / coord_t(2);
+    ret.pose.position.z = m_info.offset[2] + m_info.voxel_size / coord_t(2);
+    ret.pose.orientation.w = 1.0;
+    ret.scale.x = ret.scale.y = ret.scale.z = m_info.voxel_size;
+    ret.color.a = 1.0;
+    ret.type = visualization_msgs::Marker::CUBE_LIST;
+    if (m_thresholds.empty() || !m_ctx || size() == 0)
+      return ret;
+    VoxelMap* self = const_cast<VoxelMap*>(this);
+    self->to_device();
+    const data_t lowest = m_thresholds.front().first;
+    size_t n = 0;
+    int rc = vofod_map_compact_over(m_ctx, lowest, 1, 0, nullptr, 0, &n);
+    std::vector<vofod_xyzi> buf(n);
+    if (n)
+      rc = vofod_map_compact_over(m_ctx, lowest, 1, 0, buf.data(), buf.size(), &n);
+    ck(n ? rc : VOFOD_OK);
+    ret.points.reserve(n);
+    ret.colors.reserve(n);
+    for (const vofod_xyzi& b : buf)
+    {
+      std_msgs::ColorRGBA color;
+      for (const auto& [th, clr] : m_thresholds)
+        if (b.intensity > th)
+          color = clr;
+      geometry_msgs::Point pt;
+      pt.x = idx_t(b.x) * m_info.voxel_size;
+      pt.y = idx_t(b.y) * m_info.voxel_size;
+      pt.z = idx_t(b.z) * m_info.voxel_size;
+      ret.points.push_back(pt);
+      ret.colors.push_back(color);
+    }
+    return ret;
+  }
+  // LINE_LIST of the 12 edges of the map's box (:672-786): bottom loop, one riser, top loop, the three other risers
+  visualization_msgs::Marker borderVisualization(const std_msgs::Header& header) const
+  {
+    visualization_msgs::Marker ret;
+    ret.header = header;
+    ret.pose.position.x = m_info.offset[0];
+    ret.pose.position.y = m_info.offset[1];
+    ret.pose.position.z = m_info.offset[2];
+    ret.pose.orientation.w = 1.0;
+    ret.scale.x = 0.05;
+    ret.color.r = ret.color.g = ret.color.b = ret.color.a = 1.0;
+    ret.type = visualization_msgs::Marker::LINE_LIST;
+    const coord_t dim[3] = {m_info.sizes[0] * m_info.voxel_size, m_info.sizes[1] * m_info.voxel_size, m_info.sizes[2] * m_info.voxel_size};
+    // corners as bit masks (x = 1, y = 2, z = 4), edges in the reference's order
+    static const unsigned char edges[12][2] = {{0, 1}, {1, 3}, {3, 2}, {2, 0}, {0, 4}, {4, 5}, {5, 7}, {7, 6}, {6, 4}, {1, 5}, {3, 7}, {2, 6}};
+    ret.points.reserve(24);
+    for (const auto& e : edges)
+      for (int k = 0; k < 2; k++)
+      {
+        geometry_msgs::Point pt;
+        pt.x = (e[k] & 1) ? dim[0] : coord_t(0);
+        pt.y = (e[k] & 2) ? dim[1] : coord_t(0);
+        pt.z = (e[k] & 4) ? dim[2] : coord_t(0);
+        ret.points.push_back(pt);
+      }
+    return ret;
+  }
+
 private:
+  void need_ctx()
+  {
+    if (!m_ctx && vofod_create(m_device, &m_ctx) != VOFOD_OK)
+      throw std::runtime_error(std::string("vofod_create: ") + vofod_last_error(nullptr));  // no CPU fallback
+  }
   void ck(const int rc) const
   {
     if (rc < 0)
@@ -317,6 +429,12 @@ private:
   {
     if (m_host_valid)
       return;
+    if (!m_ctx)  // never sized: an empty map, as the reference's default-constructed one
+    {
+      m_host.clear();
+      m_host_valid = true;
+      return;
+    }
     m_host.resize(size());
     ck(vofod_map_download(m_ctx, VOFOD_MAP_SCORE, m_host.data(), m_host.size()));
     m_host_valid = true;
@@ -359,5 +477,6 @@ private:
   vofod_map_info m_info{};
   data_container_t m_host;
   bool m_host_valid = false, m_host_dirty = false;
+  std::vector<std::pair<data_t, std_msgs::ColorRGBA>> m_thresholds;
 };
 }  // namespace vofod_b200

@@ -40,6 +40,7 @@ extern "C" {
 #define VOFOD_E_OVERFLOW     -6  /* voxel-grid index overflow (voxel_grid_weighted.cpp:61-69)                   */
 #define VOFOD_E_NOMEM        -7
 #define VOFOD_E_INTERNAL     -8  /* device-side watchdog tripped (bounded spin exceeded)                        */
+#define VOFOD_E_IO           -9  /* file could not be opened (load_cloud returns nullptr, pc_loader.cpp:22-27)  */
 
 /* which grid (vofod_nodelet.cpp:2333-2339) */
 #define VOFOD_MAP_SCORE   0      /* m_voxel_map     : fp32 score                                   */
@@ -198,11 +199,33 @@ int vofod_map_submap_copy(vofod_ctx*, const float min_pt[3], const float max_pt[
 int vofod_map_trace_ray(vofod_ctx*, const float start[3], const float dir[3], float length,
                         float* ddist, int32_t* idx3, size_t cap, size_t* n);
 
+/* ---- apriori map ingest (vofod_nodelet.cpp:305-353, src/pc_loader.cpp:17-90) ------------------- */
+/* load_cloud: text cloud (one "x y z ..." per line; a ".pts" file has the point count on its first line) -> xyz triples.  Host only.
+ * *n = points in the file (up to cap are written).  VOFOD_E_IO: cannot open (the reference returns nullptr); VOFOD_E_CAPACITY: call
+ * again with cap >= *n. */
+int vofod_load_cloud(const char* filename, float* xyz, size_t cap, size_t* n);
+/* initialize_apriori_map from a loaded cloud: transformPointCloud(tf) -> pcl::VoxelGrid centroid down-sample at the map's voxel size
+ * -> voxels of the in-map centroids := +inf -> both background latches set (:343-344).  centroids (optional, cap points) receives the
+ * down-sampled cloud the reference publishes (:347-352), *n_voxels its size. */
+int vofod_apriori_map(vofod_ctx*, const float* xyz, size_t n, const vofod_pose* tf, float* centroids, size_t cap, size_t* n_voxels);
+
 /* ---- sensor model (vofod_nodelet.cpp:77-81, 374-420, 506-560) ------------------------------- */
 /* dirs/offs: 3xN column-major as Eigen stores them (= N consecutive xyz triples), ray id = row*W+col;
  * mask: N bytes, nonzero = valid pixel (NULL = all ones, :558) */
 int vofod_set_sensor(vofod_ctx*, int W, int H, const float* dirs3xN, const float* offs3xN,
                      const uint8_t* mask);
+
+/* host-only helpers of the sensor model (no device needed) */
+/* load_mask (vofod_nodelet.cpp:506-560) on a decoded rows x cols u8 image (NULL = file missing): the "mangle" re-ordering
+ * out[((v + pixel_shift_by_row[u]) % W) * H + u] = img[u * W + v] (:537-548), the plain copy, or all ones on missing / wrong-size input */
+int vofod_mask_mangle(const uint8_t* img, int cols, int rows, int W, int H, int mangle, const int32_t* pixel_shift_by_row, uint8_t* out);
+/* initialize_sensor_lut (:358-371): ouster::make_xyz_lut, cast to float, directions normalised; transform4x4 row-major (NULL = identity) */
+int vofod_make_xyz_lut(int w, int h, double range_unit, double lidar_origin_to_beam_origin_mm, const double* transform4x4,
+                       const double* azimuth_angles_deg, const double* altitude_angles_deg, float* dirs3xN, float* offs3xN);
+/* initialize_sensor_lut_simulation (:374-420); offs may be NULL */
+int vofod_sim_xyz_lut(int w, int h, float vfov, float* dirs3xN, float* offs3xN);
+/* 48-byte ouster_ros::Point records (include/vofod/types.h:7) -> packed vofod_pt; stride 0 = that layout */
+int vofod_pack_ouster(const void* points, size_t n, size_t stride, size_t intensity_offset, size_t range_offset, vofod_pt* out);
 
 /* ---- C2/C3: voxel grids ---------------------------------------------------------------------- */
 /* filterAndTransform (vofod_nodelet.cpp:621-684): exclude-box crop, rigid transform, op-area crop,

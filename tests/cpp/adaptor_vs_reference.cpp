@@ -110,6 +110,47 @@ int main()
     for (; ia != sa.end(); ++ia, ++ib)
       CHECK(*ia == *ib);
   }
+  // RViz markers (voxel_map.cpp:622-786): thresholds added out of order, same cubes in the same order with the same colours
+  {
+    std_msgs::Header hdr;
+    hdr.frame_id = "world";
+    auto color = [](float r, float g, float b) { std_msgs::ColorRGBA c; c.r = r; c.g = g; c.b = b; c.a = 1.f; return c; };
+    for (int round = 0; round < 2; round++)
+    {
+      ref.clearVisualizationThresholds();
+      gpu.clearVisualizationThresholds();
+      if (round == 1)
+      {
+        ref.addVisualizationThreshold(-0.1f, color(1, 0, 0));
+        gpu.addVisualizationThreshold(-0.1f, color(1, 0, 0));
+      }
+      ref.addVisualizationThreshold(-800.0f, color(0, 0, 1));
+      gpu.addVisualizationThreshold(-800.0f, color(0, 0, 1));
+      ref.addVisualizationThreshold(-900.0f, color(0, 1, 0));
+      gpu.addVisualizationThreshold(-900.0f, color(0, 1, 0));
+      const auto ma = ref.visualization(hdr), mb = gpu.visualization(hdr);
+      CHECK(ma.type == mb.type && ma.points.size() == mb.points.size() && ma.colors.size() == mb.colors.size() && !ma.points.empty());
+      CHECK(ma.pose.position.x == mb.pose.position.x && ma.pose.position.y == mb.pose.position.y && ma.pose.position.z == mb.pose.position.z);
+      CHECK(ma.scale.x == mb.scale.x && ma.pose.orientation.w == mb.pose.orientation.w && ma.header.frame_id == mb.header.frame_id);
+      for (size_t i = 0; i < ma.points.size(); i++)
+      {
+        CHECK(ma.points[i].x == mb.points[i].x && ma.points[i].y == mb.points[i].y && ma.points[i].z == mb.points[i].z);
+        CHECK(ma.colors[i].r == mb.colors[i].r && ma.colors[i].g == mb.colors[i].g && ma.colors[i].b == mb.colors[i].b);
+      }
+    }
+    const auto ba = ref.borderVisualization(hdr), bb = gpu.borderVisualization(hdr);
+    CHECK(ba.type == bb.type && ba.points.size() == 24 && bb.points.size() == 24 && ba.scale.x == bb.scale.x);
+    CHECK(ba.pose.position.x == bb.pose.position.x && ba.pose.position.y == bb.pose.position.y && ba.pose.position.z == bb.pose.position.z);
+    for (size_t i = 0; i < 24; i++)
+      CHECK(ba.points[i].x == bb.points[i].x && ba.points[i].y == bb.points[i].y && ba.points[i].z == bb.points[i].z);
+    // deep copies (cluster_t carries a VoxelMap by value, vofod_nodelet.cpp:116)
+    G copy = gpu;
+    CHECK(copy.size() == gpu.size() && copy.nVoxelsOver(-800.0f) == gpu.nVoxelsOver(-800.0f));
+    copy.atIdx(1, 1, 1) = 5.0f;
+    CHECK(gpu.atIdx(1, 1, 1) != 5.0f);
+    G empty, empty2 = empty;
+    CHECK(empty2.size() == 0);
+  }
   // std::vector::at semantics on a bad index
   bool threw = false;
   try

@@ -523,6 +523,35 @@ def test_pcl_parts_against_independent_implementations(gpu):
     assert n == 60 and n_checked >= 40
 
 
+def test_apriori_map_ingest_against_reference_function(gpu, tmp_path):
+    """N3: load_cloud + initialize_apriori_map (vofod_nodelet.cpp:305-353) — text cloud -> transform -> pcl::VoxelGrid centroids -> +inf
+    voxels — against the reference's own functions (oracle/_ref: pc_loader.cpp compiled as it is, initialize_apriori_map sliced out of the
+    nodelet; pcl::VoxelGrid is the shim's restatement)."""
+    from frontend_cases import apriori_cloud
+    from oracle import ref
+    from vofod_b200 import capi
+    if not ref.available():
+        pytest.skip("oracle/_ref not in this checkout")
+    path, pose = apriori_cloud(str(tmp_path))
+    p, vs = small_params()
+    rn = ref.RefNodelet()
+    rn.reset(p, vs)
+    rn.apriori(path, pose)
+    want = rn.map_download()
+    gpu.reset(p, vs)
+    xyz = capi.load_cloud(path)
+    assert np.array_equal(xyz, ref.load_cloud(path))
+    cent = gpu.apriori_map(xyz, pose)
+    got = gpu.map_download()
+    assert np.isinf(want).sum() > 5000
+    assert np.array_equal(np.isinf(got), np.isinf(want))          # the stamped voxel set
+    assert np.array_equal(got[~np.isinf(got)], want[~np.isinf(want)])
+    assert gpu.state_get()[:2] == (True, True) and rn.state_get()[:2] == (1, 1)   # :343-344
+    assert len(cent) > np.isinf(want).sum()                       # centroids outside the map are in the cloud but stamp nothing
+    # +inf voxels then behave like the reference's under the point and ray updates (Q17) — covered by test_raycast_edge_cases
+    rn.close()
+
+
 def test_full_size_properties(gpu):
     """Size-independent properties at full size, no oracle: traversal count is independent of aggregation, the
     accumulator returns to zero after apply, flags are cleared, repeated identical scans are deterministic."""
@@ -742,6 +771,19 @@ def test_cpp_adaptor_against_reference_class():
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", "adaptor_vs_reference")
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_build/adaptor_vs_reference not built (needs the reference headers: make -C tests/cpp)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_dropin_names_cover_the_nodelet_calls():
+    """include/vofod_dropin: the headers vofod_nodelet.cpp includes, re-pointed at the GPU-backed classes under the names it uses
+    (vofod::VoxelMap, vofod::VoxelGridWeighted, vofod::VoxelGridCounted, load_cloud); tests/cpp/dropin_nodelet_calls.cpp makes every call the
+    nodelet makes on them with the nodelet's argument types and never sees a reference header."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", "dropin_nodelet_calls")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_build/dropin_nodelet_calls not built (make -C tests/cpp)")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 

@@ -17,6 +17,7 @@ VOFOD_E_DIMS = -5
 VOFOD_E_OVERFLOW = -6
 VOFOD_E_NOMEM = -7
 VOFOD_E_INTERNAL = -8
+VOFOD_E_IO = -9
 
 MAP_SCORE, MAP_FLAGS, MAP_RAYCAST = 0, 1, 2
 CLASS_MAV, CLASS_UNKNOWN, CLASS_INVALID = 0, 1, 2

@@ -17,6 +17,66 @@ LIB_PATH = os.path.join(_HERE, "libvofod_cuda.so")
 _lib = None
 
 
+def load_cloud(filename, lib=None):
+    """load_cloud (src/pc_loader.cpp:17-90): N x 3 float32, or None when the file cannot be opened (the reference returns nullptr)"""
+    lib = lib or load_library()
+    n = C.c_size_t()
+    rc = lib.vofod_load_cloud(filename.encode(), None, 0, C.byref(n))
+    if rc == abi.VOFOD_E_IO:
+        return None
+    out = np.zeros((n.value, 3), dtype=np.float32)
+    if n.value:
+        rc = lib.vofod_load_cloud(filename.encode(), _p(out), n.value, C.byref(n))
+        assert rc == 0, rc
+    return out
+
+
+def mask_mangle(img, W, H, mangle, pixel_shift_by_row, lib=None):
+    lib = lib or load_library()
+    out = np.zeros(W * H, dtype=np.uint8)
+    sh = np.ascontiguousarray(pixel_shift_by_row, dtype=np.int32)
+    if img is None:
+        rc = lib.vofod_mask_mangle(None, 0, 0, W, H, int(mangle), _p(sh), _p(out))
+    else:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        rc = lib.vofod_mask_mangle(_p(img), img.shape[1], img.shape[0], W, H, int(mangle), _p(sh), _p(out))
+    if rc < 0:
+        raise VofodError(rc, "vofod_mask_mangle")
+    return out
+
+
+def make_xyz_lut(w, h, azimuth_deg, altitude_deg, range_unit=0.001, beam_origin_mm=0.0, transform=None, lib=None):
+    lib = lib or load_library()
+    az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
+    al = np.ascontiguousarray(altitude_deg, dtype=np.float64)
+    T = None if transform is None else np.ascontiguousarray(transform, dtype=np.float64).reshape(16)
+    d = np.zeros((w * h, 3), dtype=np.float32)
+    o = np.zeros((w * h, 3), dtype=np.float32)
+    rc = lib.vofod_make_xyz_lut(w, h, float(range_unit), float(beam_origin_mm), _p(T), _p(az), _p(al), _p(d), _p(o))
+    assert rc == 0, rc
+    return d, o
+
+
+def sim_xyz_lut(w, h, vfov, lib=None):
+    lib = lib or load_library()
+    d = np.zeros((w * h, 3), dtype=np.float32)
+    assert lib.vofod_sim_xyz_lut(w, h, float(vfov), _p(d), None) == 0
+    return d
+
+
+OUSTER_POINT_DTYPE = np.dtype({"names": ["x", "y", "z", "intensity", "t", "reflectivity", "ring", "ambient", "range"],
+                               "formats": ["<f4", "<f4", "<f4", "<f4", "<u4", "<u2", "u1", "<u2", "<u4"], "offsets": [0, 4, 8, 16, 20, 24, 26, 28, 32], "itemsize": 48})
+
+
+def pack_ouster(points, lib=None):
+    """48-byte ouster_ros::Point records -> packed PT_DTYPE"""
+    lib = lib or load_library()
+    points = np.ascontiguousarray(points, dtype=OUSTER_POINT_DTYPE)
+    out = np.zeros(len(points), dtype=PT_DTYPE)
+    assert lib.vofod_pack_ouster(_p(points), len(points), 0, 0, 0, _p(out)) == 0
+    return out
+
+
 def cluster_grid_rows(tolerance, leaf, lib=None):
     """Host-only: [(dy, dz, R, shell)] of the scan's grid clustering for a tolerance / leaf pair ([] = generic path)."""
     lib = lib or load_library()
@@ -89,6 +149,12 @@ def load_library():
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
         "vofod_set_slab": (i32, [vp, i32, i32, i32, i32]),
+        "vofod_load_cloud": (i32, [C.c_char_p, vp, sz, P(sz)]),
+        "vofod_apriori_map": (i32, [vp, vp, sz, P(Pose), vp, sz, P(sz)]),
+        "vofod_mask_mangle": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+        "vofod_make_xyz_lut": (i32, [i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+        "vofod_sim_xyz_lut": (i32, [i32, i32, f32, vp, vp]),
+        "vofod_pack_ouster": (i32, [vp, sz, sz, sz, sz, vp]),
         "vofod_slab_min_halo": (i32, [P(Params), f32]),
         "vofod_slab_set_world": (i32, [vp, i32, i32]),
         "vofod_slab_phase": (i32, [vp, i32, vp, i32, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
@@ -408,6 +474,15 @@ class Vofod:
         if n.value:
             self._ck(self.lib.vofod_last_clusters(self.h, _p(out), n.value, C.byref(n)))
         return out
+
+    def apriori_map(self, xyz, pose, want_centroids=True):
+        """initialize_apriori_map (vofod_nodelet.cpp:305-353) from a loaded cloud -> the down-sampled cloud (M x 3)"""
+        xyz = _f32(xyz).reshape(-1, 3)
+        cap = len(xyz) if want_centroids else 0
+        out = np.zeros((max(cap, 1), 3), dtype=np.float32)
+        m = C.c_size_t()
+        self._ck(self.lib.vofod_apriori_map(self.h, _p(xyz), len(xyz), C.byref(pose), _p(out) if cap else None, cap, C.byref(m)))
+        return out[:m.value].copy() if cap else m.value
 
     def set_slab(self, axis, lo, hi, halo):
         self._ck(self.lib.vofod_set_slab(self.h, int(axis), int(lo), int(hi), int(halo)))

@@ -282,6 +282,11 @@ struct vofod_ctx
   bool win_valid = false;   // window allocated + zeroed and matches `win`
   int frac_bits = 24;
   bool acc_has_data = false;
+  // large windows (long rays on a fine grid: GBs): one "touched" byte per 32 accumulator cells behind the cells, set by the accumulate
+  // kernel, so that the apply pass reads 1/256 of the window + the touched 256-byte groups instead of all of it
+  bool acc_sparse = false;
+  size_t acc_dirty_off = 0;    // byte offset of the touched marks inside ctx->acc
+  size_t acc_total_bytes = 0;  // cells + spare + marks: what a clear of the accumulator has to zero
 
   // sensor
   int W = 0, H = 0;

@@ -900,7 +900,7 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
     if (value != 0.0f)
       return vf_fail(ctx, VOFOD_E_INVALID, "the raycast accumulator can only be cleared");
     if (ctx->win_valid)
-      CK(cudaMemsetAsync(ctx->acc.p, 0, (size_t)ctx->win.size[0] * ctx->win.size[1] * ctx->win.size[2] * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, ctx->stream));
     ctx->acc_has_data = false;
   } else
     return vf_fail(ctx, VOFOD_E_INVALID, "bad map id %d", which);

@@ -745,7 +745,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     // the reference clears m_voxel_raycast before the sensor-in-map test (:1430-1432)
     if (s.do_raycast && plan.raycast_status == VOFOD_W_SENSOR_OOB && ctx->acc_has_data && ctx->acc.p)
     {
-      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, st));
+      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, st));
       ctx->acc_has_data = false;
     }
   }

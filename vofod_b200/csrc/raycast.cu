@@ -70,7 +70,7 @@ __device__ __forceinline__ void ray_stats(unsigned long long* stats, const unsig
 template <bool AGG, bool SLAB, bool FAST, bool STATS>
 __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const float scale, const int slab_axis, const int ssize, const int own_lo, const int own_n,
                                              const int wn, unsigned long long* __restrict__ acc, const unsigned lane, const unsigned lanemask_lt,
-                                             unsigned long long* stats)
+                                             unsigned long long* stats, uint8_t* __restrict__ touched)
 {
   unsigned steps = 0;
   while (alive)
@@ -102,10 +102,18 @@ __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const floa
       const int sum = __reduce_add_sync(m, q);
       const bool leader = (m & lanemask_lt) == 0;
       if (inside && leader)
+      {
         red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+        if (touched)
+          touched[key >> 5] = 1;  // plain store: every writer stores the same value
+      }
       ray_stats<STATS>(stats, am, leader, FAST ? 66 : 67);
     } else if (inside)
+    {
       red_add_u64(acc + key, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
+      if (touched)
+        touched[key >> 5] = 1;
+    }
     // SLAB: windows of neighbouring slabs overlap in the halos; a traversal is counted by the slab that OWNS the voxel, so that the
     // counts of all slabs add up to the reference's
     steps += SLAB ? ((unsigned)(r.spos - own_lo) < (unsigned)own_n ? 1u : 0u) : 1u;
@@ -134,19 +142,23 @@ __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const floa
       if (!FAST) r.remx--;
       if (SLAB && slab_axis == 0) r.spos += r.sstep;
     }
-    if (SLAB && FAST)
+    // a ray that has left the window along the slab axis never comes back (the general loop is entered fast-forwarded as well)
+    if (SLAB && (FAST || slab_axis < 2))
       alive = alive && (unsigned)r.spos < (unsigned)ssize;
   }
   return steps;
 }
 
-// SLAB + FAST: bring the DDA of a ray that starts outside the slab's window to the state it has when it enters, WITHOUT walking
-// the voxels in between.  The DDA is a 3-way merge of the increasing sequences tm_a + j*td_a (each built by the same chain of
-// fp32 additions the loop performs) with ties going to x before y before z (first minimum).  The ka-th step along the slab axis
-// consumes T = tm_a after ka-1 additions; a step along another axis b comes before it iff its value is < T, or == T when b has
-// priority over the slab axis.  The state after that step is therefore: tm_a = T + td_a, prev = T, every other axis advanced past
-// T.  Bit-identical to walking (same additions in the same order per axis); the ray enters iff T < len.
+// SLAB: bring the DDA of a ray that starts outside the slab's window to the state it has when it enters, WITHOUT walking the voxels
+// in between.  The DDA is a 3-way merge of the increasing sequences tm_a + j*td_a (each built by the same chain of fp32 additions the
+// loop performs) with ties going to x before y before z (first minimum).  The ka-th step along the slab axis consumes T = tm_a after
+// ka-1 additions; a step along another axis b comes before it iff its value is < T, or == T when b has priority over the slab axis.
+// The state after that step is therefore: tm_a = T + td_a, prev = T, every other axis advanced past T.  Bit-identical to walking (same
+// additions in the same order per axis); the ray enters iff T < len — and, for a ray that can reach the edge of the MAP (!FAST), iff no
+// axis runs out of voxels on the way: an axis that needs more steps than it has left (`cur[i] == last[i]`, voxel_map.cpp:257) ends the
+// ray before it gets here.
 // Returns false when the ray never enters the window.
+template <bool FAST>
 __device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axis, const int ssize, unsigned& skipped)
 {
   if ((unsigned)r.spos < (unsigned)ssize)
@@ -159,6 +171,13 @@ __device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axi
   // the slab axis takes at most len/td_a + 1 steps before the ray ends
   if ((float)(ka - 2) * tda >= r.len)
     return false;
+  if (!FAST)
+  {
+    int& rema = slab_axis == 0 ? r.remx : r.remy;
+    if (rema < ka)
+      return false;
+    rema -= ka;
+  }
   float T = tma;
   for (int j = 1; j < ka; j++)
     T += tda;
@@ -169,14 +188,21 @@ __device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axi
   r.spos += ka * r.sstep;
   r.widx += ka * (slab_axis == 0 ? r.dwx : r.dwy);
   skipped += (unsigned)ka;
+  int nb = 0;
   if (slab_axis == 0)
   {
-    while (r.tmy < T) { r.tmy += r.tdy; r.widx += r.dwy; skipped++; }   // x has priority over y and z on ties
+    while (r.tmy < T) { r.tmy += r.tdy; r.widx += r.dwy; nb++; }   // x has priority over y and z on ties
+    if (!FAST) { if (r.remy < nb) return false; r.remy -= nb; }
   } else
   {
-    while (r.tmx <= T) { r.tmx += r.tdx; r.widx += r.dwx; skipped++; }  // x has priority over y
+    while (r.tmx <= T) { r.tmx += r.tdx; r.widx += r.dwx; nb++; }  // x has priority over y
+    if (!FAST) { if (r.remx < nb) return false; r.remx -= nb; }
   }
-  while (r.tmz < T) { r.tmz += r.tdz; r.widx += r.dwz; skipped++; }
+  skipped += (unsigned)nb;
+  nb = 0;
+  while (r.tmz < T) { r.tmz += r.tdz; r.widx += r.dwz; nb++; }
+  if (!FAST) { if (r.remz < nb) return false; r.remz -= nb; }
+  skipped += (unsigned)nb;
   return true;
 }
 
@@ -186,7 +212,7 @@ template <int RB, bool AGG, bool SLAB, bool STATS>
 __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters,
-                                                           unsigned long long* __restrict__ stats)
+                                                           unsigned long long* __restrict__ stats, uint8_t* __restrict__ touched)
 {
   pdl_enter();
   // stage this block's packed points (20 B each) through shared memory with coalesced 16 B loads
@@ -293,10 +319,14 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
   if (fast)
   {
     if (SLAB && alive)
-      alive = ray_skip_to_slab(r, slab_axis, ssize, skipped);
-    steps = ray_loop<AGG, SLAB, true, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats);
+      alive = ray_skip_to_slab<true>(r, slab_axis, ssize, skipped);
+    steps = ray_loop<AGG, SLAB, true, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
   } else
-    steps = ray_loop<AGG, SLAB, false, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats);
+  {
+    if (SLAB && slab_axis < 2 && alive)
+      alive = ray_skip_to_slab<false>(r, slab_axis, ssize, skipped);
+    steps = ray_loop<AGG, SLAB, false, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+  }
   __syncwarp();
   if (STATS && skipped)
     atomicAdd(stats + 68, (unsigned long long)skipped);
@@ -355,7 +385,7 @@ __global__ void __launch_bounds__(256) k_raycast_max(const ScanDyn* __restrict__
 
 __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const ScanDyn* __restrict__ dyn, unsigned long long* __restrict__ acc, float* __restrict__ score,
                                                        const uint8_t* __restrict__ flags, const unsigned* __restrict__ max_bits,
-                                                       unsigned long long* __restrict__ counters)
+                                                       unsigned long long* __restrict__ counters, uint8_t* __restrict__ touched)
 {
   pdl_enter();
   const Window w = dyn->win;
@@ -376,12 +406,52 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
       return;  // :1544-1548 (the host also skips the flag clear)
   }
   bool any_pos = false;  // max_element(raycast) > 0 (:1542-1548): some cell holds a positive length
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  // `touched` != NULL (large windows): the accumulate kernel marked every group of 32 cells it added to; a warp fetches 32 marks at a
+  // time and visits the marked groups only.  Otherwise: every cell of the window.
+  const unsigned lane = threadIdx.x & 31;
+  const long long n_groups = (n + 31) >> 5;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  long long gbase = touched ? warp0 * 32 : 0;
+  unsigned pending = 0;
+  long long i = touched ? -1 : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  while (true)
   {
-    const unsigned long long p = acc[i];
+    if (touched)
+    {
+      // next marked group of this warp
+      while (pending == 0)
+      {
+        if (gbase >= n_groups)
+          break;
+        const long long g = gbase + lane;
+        const bool mark = g < n_groups && touched[g] != 0;
+        pending = __ballot_sync(VOFOD_FULL, mark);
+        if (mark)
+          touched[g] = 0;
+        if (pending == 0)
+          gbase += n_warps * 32;
+      }
+      if (pending == 0)
+        break;
+      const int b = __ffs(pending) - 1;
+      pending &= pending - 1;
+      i = ((gbase + b) << 5) + lane;
+      if (pending == 0)
+        gbase += n_warps * 32;
+      if (i >= n)
+        continue;
+    } else
+    {
+      if (i >= n)
+        break;
+    }
+    const long long i_cur = i;
+    if (!touched)
+      i += (long long)gridDim.x * blockDim.x;
+    const unsigned long long p = acc[i_cur];
     if (!p)
       continue;
-    acc[i] = 0ull;  // m_voxel_raycast.clear() for the next scan (:1430)
+    acc[i_cur] = 0ull;  // m_voxel_raycast.clear() for the next scan (:1430)
     unsigned c;
     long long lq;
     acc_decode(p, c, lq);
@@ -389,7 +459,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     if (!(rv > 0.0f))
       continue;
     any_pos = true;
-    const int wx = (int)(i % wsx), wy = (int)((i / wsx) % wsy), wz = (int)(i / ((long long)wsx * wsy));
+    const int wx = (int)(i_cur % wsx), wy = (int)((i_cur / wsx) % wsy), wz = (int)(i_cur / ((long long)wsx * wsy));
     const long long ci = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
     if (ci < 0 || flags[ci] != 0)  // flag == m_vflags_unmarked (:1561)
       continue;
@@ -411,6 +481,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
     const float w2 = 1.0f - w1;
     score[ci] = w1 * m + w2 * a.ray_score;                            // :1569 / :1597
   }
+  __syncwarp();
   if (__any_sync(VOFOD_FULL, any_pos) && (threadIdx.x & 31) == 0)
     atomicOr(counters + CNT_APPLY_ANY, 1ull);
 }
@@ -539,11 +610,21 @@ int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vof
     wn_max *= (size_t)full;
   }
   // sized for the largest window this max_dist can produce, so that the buffer (and the launch grids) never change
-  if (ctx->acc.cap < (wn_max + 32) * 8)
+  const size_t dirty_off = (wn_max + 32) * 8, total = dirty_off + wn_max / 32 + 64;
+  if (ctx->acc.cap < total)
   {
-    ENSURE(ctx->acc, (wn_max + 32) * 8);  // fresh allocations are zero-filled
+    ENSURE(ctx->acc, total);  // fresh allocations are zero-filled
     ctx->acc_has_data = false;
   }
+  if (ctx->acc_cells_max != wn_max && ctx->acc_has_data && ctx->acc_total_bytes)
+  {
+    // the layout changes with max_dist (dynamic_reconfigure): start from a clean buffer
+    CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes > total ? ctx->acc_total_bytes : total, ctx->stream));
+    ctx->acc_has_data = false;
+  }
+  ctx->acc_dirty_off = dirty_off;
+  ctx->acc_total_bytes = total;
+  ctx->acc_sparse = wn_max >= (size_t(1) << 25);
   ctx->acc_cells_max = wn_max;
   ctx->win = w;
   ctx->win_valid = true;
@@ -563,7 +644,7 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   // max_val == 0) must not leak into this one.  After a new-rule apply the accumulator is already all zero.
   if (ctx->acc_has_data)
   {
-    CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, ctx->stream));
     ctx->acc_has_data = false;
   }
   RayArgs a;
@@ -574,6 +655,7 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   a.n = (int)n;
   a.has_off = ctx->lut_has_off ? 1 : 0;
   const bool slab = ctx->slab_on;
+  uint8_t* touched = ctx->acc_sparse ? ctx->acc.as<uint8_t>() + ctx->acc_dirty_off : nullptr;
   unsigned long long* stats = nullptr;
   if (ctx->raycast_stats)
   {
@@ -582,7 +664,7 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
   }
 #define RAY_LAUNCH(RB_, AGG_, SLAB_, STATS_)                                                                                                                 \
   LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_, STATS_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),       \
-         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats)
+         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched)
   if (ctx->raycast_no_agg)
   {
     if (slab) RAY_LAUNCH(64, false, true, false); else RAY_LAUNCH(64, false, false, false);
@@ -629,8 +711,10 @@ int vf_raycast_apply_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p)
   const ScanDyn* dyn = ctx->dyn.as<ScanDyn>();
   if (!a.new_rule)
     LAUNCH(k_raycast_max, vf_blocks(ctx, wn, 256), 256, 0, dyn, ctx->acc.as<unsigned long long>(), a.inv_scale, (unsigned*)(cnt + CNT_MAXVAL));
-  LAUNCH(k_raycast_apply, vf_blocks(ctx, wn, 256), 256, 0, a, dyn, ctx->acc.as<unsigned long long>(), ctx->score.as<float>(), ctx->flags.as<uint8_t>(),
-         (const unsigned*)(cnt + CNT_MAXVAL), cnt);
+  // (old rule: when the apply bails out on max_val == 0 the marks stay set and the next accumulate's clear removes them with the cells)
+  uint8_t* touched = ctx->acc_sparse ? ctx->acc.as<uint8_t>() + ctx->acc_dirty_off : nullptr;
+  LAUNCH(k_raycast_apply, vf_blocks(ctx, touched ? wn / 8 : wn, 256), 256, 0, a, dyn, ctx->acc.as<unsigned long long>(), ctx->score.as<float>(), ctx->flags.as<uint8_t>(),
+         (const unsigned*)(cnt + CNT_MAXVAL), cnt, touched);
   // NOTE (old rule): when max_val == 0 the apply kernel returns before zeroing; the accumulator then only holds cells
   // whose length is <= 0, which the next accumulate clears because acc_has_data stays true.
   ctx->acc_has_data = !a.new_rule;
@@ -670,7 +754,7 @@ int vofod_raycast_accumulate(vofod_ctx* ctx, const vofod_pt* scan, size_t n, con
     // the reference clears m_voxel_raycast before the sensor-in-map test (:1430-1432)
     if (prc == VOFOD_W_SENSOR_OOB && ctx->acc_has_data && ctx->acc.p)
     {
-      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_cells_max * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, ctx->stream));
       ctx->acc_has_data = false;
     }
     CK(cudaStreamSynchronize(ctx->stream));

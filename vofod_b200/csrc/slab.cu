@@ -273,10 +273,21 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
       RET(vf_begin_call(ctx));
       RET(vf_dyn_push(ctx));
       RET(vf_range_update_dev(ctx, p));
-      RET(vf_filter_voxelize_dev(ctx, n, p));
+      const int seeded = vf_filter_voxelize_dev(ctx, n, p, true);
+      if (seeded < 0)
+        return seeded;
       ENSURE(ctx->labels, n * 4);
-      RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
-                         cnt + CNT_NCLUSTERS));
+      if (seeded)
+      {
+        // the voxel list is a set of grid cells: connected components on the occupancy words the filter left behind (as in vofod_process_scan)
+        RunRows rows;
+        vf_run_rows((float)p.ground_points_max_distance, ctx->g.vs, rows);
+        RET(vf_cluster_runs_dev(ctx, ctx->cl, ctx->cl_cellkey.as<uint32_t>(), ctx->cl_words.as<RunWord>(),
+                                reinterpret_cast<const VgLayout*>(ctx->scratch_d.as<char>() + 64), rows, (float)p.ground_points_max_distance, cnt + CNT_VG_M, n,
+                                ctx->labels.as<int>(), cnt + CNT_NCLUSTERS));
+      } else
+        RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
+                           cnt + CNT_NCLUSTERS));
       RET(vf_close_far_phase(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), cnt + CNT_VG_M, n, p, 1, false));
       return VOFOD_OK;
     }

@@ -60,6 +60,57 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank's host side (and place its pinned buffers, first touch) on the NUMA node its GPU hangs off: N processes that all
+    pull their scans through one node's memory controllers is what capped the 8-GPU e2e scaling in round 1."""
+    info = {"applied": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info.update({"pci": bdf, "node": node})
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info.update({"applied": True, "n_cpus": len(cpus)})
+    except Exception as e:  # not fatal: unpinned is what round 1 measured
+        info["error"] = str(e)[:80]
+    return info
+
+
+def l2_peaks():
+    """L2 yardsticks measured on this pool's B200 by tools/l2_microbench.cu (SURVEY.md §8d asks for them next to the HBM figure)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_l2_microbench.json")))
+    except Exception:
+        return None
+
+
+def whole_scan_bytes(n_rays, m_vox, traversals, window_cells, grid_cells, n_bg_cells):
+    """SURVEY.md §8d byte table for one scan of schedule S1.  Two totals: `algorithmic_min` counts the grid passes over the cells they can
+    concern (ray window, raised chunks), `reference_faithful` counts them over the whole grid as the reference executes them."""
+    ingest = n_rays * (20 + 24 + 1)
+    trav = traversals * BYTES_PER_TRAVERSAL
+    vg = n_rays * (12 + 8) + 4 * n_rays * 16 + m_vox * 16
+    upd = m_vox * (16 + 8 + 4)
+    clus = m_vox * (12 + 8 + 27 * 4 + 4 * 4)
+    apply_win = window_cells * 28
+    apply_full = grid_cells * 28
+    nover_full = grid_cells * 4
+    sep_full = grid_cells * 12
+    sep_min = n_bg_cells * (12 + 16)
+    common = ingest + trav + vg + upd + clus
+    return {"algorithmic_min": common + apply_win + n_bg_cells * 4 + sep_min, "reference_faithful": common + apply_full + nover_full + sep_full,
+            "terms": {"scan_ingest": ingest, "traversal": trav, "voxel_grid": vg, "point_update": upd, "clustering": clus, "ray_apply_windowed": apply_win,
+                      "ray_apply_full_grid": apply_full, "n_voxels_over_full_grid": nover_full, "sepclusters_full_grid": sep_full}}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -120,6 +171,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(local_rank) if not args.no_numa_pin else {"applied": False, "off": True}
     K, Wm = args.steps, args.warmup
     n_scans = K + Wm
 
@@ -162,7 +214,7 @@ def run_ours(args):
             for k in range(n_scans):
                 v.upload_scan(k, host_scans[k])
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
-        tot = {"trav": 0, "ray_ms": 0.0, "dets": 0, "stage": {}}
+        tot = {"trav": 0, "ray_ms": 0.0, "dets": 0, "stage": {}, "m_vox": 0, "n_bg": 0}
         l0 = v.kernel_launches()
         whole = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         barrier()
@@ -188,6 +240,8 @@ def run_ours(args):
                 tot["trav"] += res.n_traversals
                 tot["ray_ms"] += st["raycasting"]
                 tot["dets"] += res.n_detections
+                tot["m_vox"] += res.n_voxels
+                tot["n_bg"] += res.n_bg
                 for name, ms in st.items():
                     tot["stage"][name] = tot["stage"].get(name, 0.0) + ms
         whole[1].record(stream)
@@ -197,6 +251,55 @@ def run_ours(args):
         # one bracket around all K steps: additionally contains the L2-flush writes and the host time between two scans
         tot["whole_ms"] = whole[0].elapsed_time(whole[1])
         return ms, tot
+
+    def run_streaming():
+        """e2e as a user gets it: K scans from pinned host buffers through ONE call of the C ABI (vofod_process_scan_batch: scan k + 1's H2D
+        copy overlaps scan k's kernels, results read back per scan), ONE event bracket around all K scans, no L2 flush — every step's input
+        is a new 5.2 MB scan from host memory (K x 5.2 MB over the leg), the map stays wherever the previous scan left it, as in production."""
+        v.set_option(abi.OPT_GRAPH, 1)
+        v.reset(p, VOXEL)
+        v.process_scan_batch([host_scans[k] for k in range(Wm)], poses[:Wm], p, scheds[:Wm])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = v.kernel_launches()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            res, done = v.process_scan_batch([host_scans[k] for k in range(Wm, n_scans)], poses[Wm:], p, scheds[Wm:])
+            e1.record(stream)
+        barrier()
+        assert done == K
+        return e0.elapsed_time(e1), sum(r.n_traversals for r in res), sum(r.n_detections for r in res), v.kernel_launches() - l0
+
+    def run_cfg3(K3=40, W3=32):
+        """BASELINE.json configs[2]: Gazebo-like scene with 3 sphere UAVs — the scans that DO produce detections (exploreToGround, frontier
+        write-back, submap confidence) — same map, same per-step timing as the resident leg"""
+        v.set_option(abi.OPT_GRAPH, 1)
+        v.reset(p, VOXEL)
+        n3 = K3 + W3
+        buf = np.zeros((n3, N), dtype=abi.PT_DTYPE)
+        ps, ss = [], []
+        for k in range(n3):
+            _, pose, rp, _ = synth.generate(synth.SCENE_GAZEBO, k, W, H, dirs, 1.0, out=buf[k])
+            ps.append(pose)
+            ss.append(abi.schedule_s1(rp))
+            v.upload_scan(k, buf[k])
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n3)]
+        nd = nfar = 0
+        barrier()
+        for k in range(n3):
+            with torch.cuda.stream(stream):
+                flush.fill_(k & 0xFF)
+                ev3[k][0].record(stream)
+                res, d = v.process_scan_resident(k, ps[k], p, ss[k], dets=dets)
+                ev3[k][1].record(stream)
+            if k >= W3:
+                nd += res.n_detections
+                nfar += res.n_far_clusters
+        barrier()
+        ms3 = sum(ev3[k][0].elapsed_time(ev3[k][1]) for k in range(W3, n3))
+        return {"workload": "cfg3: Gazebo-like scene (ground + 4 buildings + 3 sphere UAVs), 128x2048 rays, cfg2 map, schedule S1, scans resident in HBM",
+                "value": K3 / (ms3 * 1e-3), "unit": "scans/s", "ms_per_step": ms3 / K3, "steps": K3, "warmup": W3, "detections_in_timed_steps": int(nd),
+                "far_clusters_per_scan": nfar / K3}
 
     if args.profile_leg:
         ms, tot = run_leg(True, graph=args.profile_leg == "graph")
@@ -210,7 +313,11 @@ def run_ours(args):
     sampler.start()
     ms_res, tot_res = run_leg(True)
     ms_e2e, tot_e2e = run_leg(False)
+    stream_ms, stream_trav, stream_dets, stream_launches = run_streaming()
     clocks = sampler.stop()
+    cfg3 = run_cfg3() if rank == 0 and not args.no_cfg3 else None
+    if world > 1:
+        dist.barrier()
     stats_after_graph_legs = v.stats()
     # per-stage device times (CUDA events between the stages on the library's stream) need the kernel-by-kernel path:
     # the same sequence once more with graph replay switched off.  Only the stage table and the roofline use it.
@@ -219,7 +326,7 @@ def run_ours(args):
     tot_res["stage"] = tot_eager["stage"]
     assert tot_eager["trav"] == tot_res["trav"]
 
-    t_res = torch.tensor([sum(ms_res), sum(ms_e2e), float(tot_res["trav"]), tot_res["ray_ms"], tot_res["whole_ms"], tot_e2e["whole_ms"]], dtype=torch.float64,
+    t_res = torch.tensor([sum(ms_res), sum(ms_e2e), float(tot_res["trav"]), tot_res["ray_ms"], tot_res["whole_ms"], tot_e2e["whole_ms"], stream_ms], dtype=torch.float64,
                          device="cuda")
     if world > 1:
         tmax = t_res.clone()
@@ -231,6 +338,7 @@ def run_ours(args):
     total_ms, total_ms_e2e = float(tmax[0]), float(tmax[1])
     trav_all, ray_ms_max = float(tsum[2]), float(tmax[3])
     whole_ms_max, whole_e2e_ms_max = float(tmax[4]), float(tmax[5])
+    stream_ms_max = float(tmax[6])
 
     out = None
     if rank == 0:
@@ -260,11 +368,18 @@ def run_ours(args):
             "gvoxel_traversals_per_s": trav_all / (ray_ms_max * 1e-3) / 1e9 if ray_ms_max > 0 else None,
             "gvoxel_traversals_per_s_full_path": trav_all / (total_ms * 1e-3) / 1e9,
             "traversals_per_scan": trav_per_launch,
-            "e2e": {"value": world * K / (total_ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize,
-                    "d2h_bytes_per_step": 64 * 8, "ms_per_step": total_ms_e2e / K},  # the 64 result counters; detection records (168 B each) follow only when a scan has detections
-            "single_bracket": {"note": "one event pair around all K steps of each leg: includes the 256 MB L2-flush write per step and the host time "
-                                       "between two synchronous calls, which the per-step events leave out",
+            # headline: the streaming leg — ONE event bracket around K scans fed from pinned host memory through one C-ABI call, no flush
+            "e2e": {"value": world * K / (stream_ms_max * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize,
+                    "d2h_bytes_per_step": 64 * 8, "ms_per_step": stream_ms_max / K,  # the 64 result counters; detection records (168 B each) follow only when a scan has detections
+                    "how": "vofod_process_scan_batch: K scans from pinned host buffers, scan k+1's H2D copy overlapped with scan k's kernels, results read back per "
+                           "scan; one CUDA-event bracket on the library's stream around the whole call; no L2 flush (every step's input is a new scan from host "
+                           "memory; the map stays where the previous scan left it)", "gpu_launches": int(stream_launches)},
+            "e2e_flushed_per_step": {"value": world * K / (total_ms_e2e * 1e-3), "unit": "scans/s", "ms_per_step": total_ms_e2e / K,
+                                     "note": "round-1 definition: one vofod_process_scan call per step from Python, per-step events, 256 MB L2 flush before every step"},
+            "single_bracket": {"note": "one event pair around all K steps of the two per-step legs: includes the 256 MB L2-flush write per step (~40 us) and the host "
+                                       "time between two synchronous calls from Python, which the per-step events leave out",
                                "value": world * K / (whole_ms_max * 1e-3), "e2e": world * K / (whole_e2e_ms_max * 1e-3), "unit": "scans/s"},
+            "numa": numa,
             "gpu_launches": int(tot_res["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_raycast_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": trav_per_launch * BYTES_PER_TRAVERSAL,
@@ -272,11 +387,31 @@ def run_ours(args):
             "stage_ms_per_step": {k: round(x / K, 4) for k, x in tot_res["stage"].items()},
             "stage_note": "stage times and the roofline kernel time come from a third, kernel-by-kernel leg (graph replay off): %.4f ms/step" % (sum(ms_eager) / K),
             "detections_in_timed_steps": int(tot_res["dets"]),
+            "cfg3": cfg3,
             "replay_stats": stats_after_graph_legs,
             "clocks": clocks,
         }
+        l2 = l2_peaks()
+        if l2:
+            # the memory-side yardsticks of an L2-resident window (tools/l2_microbench.cu): RED lane-operations per second against the
+            # measured random-address RED rate, and the 8 B/traversal figure against the L2 streaming bandwidth
+            reds_per_scan = l2.get("raycast_red_lane_ops_per_scan")
+            out["roofline"]["l2"] = {"red_peak_gred_s": l2["red_u64_random_lane_Gred_s"], "l2_read_peak_gbs": l2["read_64MB_GBs"],
+                                     "frac_of_l2_read_bw": achieved / l2["read_64MB_GBs"],
+                                     "achieved_gred_s": (reds_per_scan / (ray_ms_per_launch * 1e-3) / 1e9) if reds_per_scan else None,
+                                     "frac_of_red_peak": (reds_per_scan / (ray_ms_per_launch * 1e-3) / 1e9 / l2["red_u64_random_lane_Gred_s"]) if reds_per_scan else None,
+                                     "floor_note": l2.get("raycast_floor_note")}
+        wb = whole_scan_bytes(N, tot_res["m_vox"] / K, trav_per_launch, 87 ** 3, 401 * 401 * 161, tot_res["n_bg"] / K)
+        step_s = total_ms / K * 1e-3
+        out["roofline_whole_scan"] = {"bound": "hbm", "unit": "GB/s", "peak": peak, "ms_per_step": total_ms / K,
+                                      "achieved_algorithmic_min": wb["algorithmic_min"] / step_s / 1e9, "frac_algorithmic_min": wb["algorithmic_min"] / step_s / 1e9 / peak,
+                                      "achieved_reference_faithful": wb["reference_faithful"] / step_s / 1e9,
+                                      "frac_reference_faithful": wb["reference_faithful"] / step_s / 1e9 / peak, "bytes": wb,
+                                      "note": "SURVEY.md §8d byte table per scan / ms_per_step of the resident leg, per GPU; the reference-faithful total counts the "
+                                              "full-grid passes (apply 28 B/cell, nVoxelsOver 4 B/cell, sepclusters 12 B/cell) that the GPU path replaces by passes over "
+                                              "the ray window and the raised chunks"}
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(min(12, n_scans))
+            out["cpu_baseline"] = cpu_baseline(min(14, n_scans))
     del stream, flush
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
@@ -410,7 +545,9 @@ def run_slab(args):
 
 
 def cpu_baseline(n_scans, timed_from=2):
-    """The oracle (CPU restatement of the reference's path) on the host, single thread, first scans of the same sequence."""
+    """The oracle (CPU restatement of the reference's path, pinned to the reference's own compiled functions) on the host, single thread,
+    first scans of the same sequence; per-stage times under the reference's ScopeTimer checkpoint names, and what its three actors
+    (scan thread, raycast thread, background-cluster thread, one core each) would sustain if they overlapped perfectly."""
     from oracle import oracle  # the ONLY use of oracle/ in this file besides --impl reference: the reported CPU baseline
     from vofod_b200 import abi, synth
     p = make_params()
@@ -419,6 +556,7 @@ def cpu_baseline(n_scans, timed_from=2):
     o.reset(p, VOXEL)
     o.set_sensor(W, H, dirs)
     t_total, n = 0.0, 0
+    stage = np.zeros(abi.N_STAGES)
     for k in range(n_scans):
         scan, pose, rp, _ = synth.generate(synth.SCENE_CITY, k, W, H, dirs)
         s = abi.schedule_s1(rp)
@@ -428,9 +566,23 @@ def cpu_baseline(n_scans, timed_from=2):
         if k >= timed_from:
             t_total += dt
             n += 1
+            stage += o.stage_times()
     o.close()
+    stage /= max(n, 1)
+    names = ["range", "filtering", "clusterization", "close X far", "vmap update", "raycasting", "raycast vmap update", "classification", "detections",
+             "sep bg clusters"]
+    table = {nm: round(float(stage[i]), 3) for i, nm in enumerate(names)}
+    scan_actor = float(stage[0] + stage[1] + stage[2] + stage[3] + stage[4] + stage[7] + stage[8])   # processMsg (:882-1096)
+    ray_actor = float(stage[5] + stage[6])                                                             # raycast_cloud (:1397-1606)
+    bg_actor = float(stage[9])                                                                         # updateSeparatedBGClusters (:1126-1278)
+    slowest = max(scan_actor, ray_actor, bg_actor)
     return {"value": n / t_total if t_total > 0 else None, "unit": "scans/s", "cores": 1, "kind": "port",
-            "sample": f"scans {timed_from}..{n_scans - 1} of the same sequence, schedule S1, g++ -O3 -DNDEBUG (reference flags), 1 thread; host has {os.cpu_count()} cpus"}
+            "sample": f"scans {timed_from}..{n_scans - 1} of the same sequence, schedule S1, g++ -O3 -DNDEBUG (reference flags), 1 thread; host has {os.cpu_count()} cpus",
+            "stage_ms_per_scan": table,
+            "three_actors_on_three_cores": {"value": 1e3 / slowest if slowest > 0 else None, "unit": "scans/s", "cores": 3,
+                                            "actor_ms": {"scan thread": round(scan_actor, 3), "raycast thread": round(ray_actor, 3), "bg-cluster thread": round(bg_actor, 3)},
+                                            "note": "upper bound derived from the per-stage times above: the reference's three actors on one core each, perfectly "
+                                                    "overlapped, are paced by the slowest one (the raycast thread also skips scans while it is busy, :952-957)"}}
 
 
 def run_reference(args):
@@ -483,6 +635,8 @@ def main():
     ap.add_argument("--mode", default="streams", choices=["streams", "slab"],
                     help="streams (default, the driver's contract): cfg2, one independent scan stream per GPU; slab: cfg5 large map cut into x-slabs")
     ap.add_argument("--no-slab", action="store_true", help="skip the cfg5 slab sub-record")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 (scene with UAVs / detections) sub-record")
+    ap.add_argument("--no-numa-pin", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--slab-steps", type=int, default=20)
     ap.add_argument("--slab-warmup", type=int, default=6)
     ap.add_argument("--raycast-max", type=float, default=20.0, help="slab mode: raycast.max_distance [m] (yaml default 20, dynamic_reconfigure maximum 200)")

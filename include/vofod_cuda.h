@@ -146,6 +146,13 @@ typedef struct vofod_schedule {
   int32_t do_classify;          /* classifyClusters + extractDetections                         */
   int32_t do_sepclusters;       /* updateSeparatedBGClusters(its_diff) after the detections     */
   int32_t sep_its_diff;
+  /* The reference's steady state (vofod_nodelet.cpp:950-957, 1530-1539, 1602): the raycast thread accumulates scan k while the scan
+   * thread carries on, and applies it only after scan k + 1 has done its point update — with the flags of BOTH scans still set — and
+   * no new raycast starts while one is in flight.  Reproduce it with
+   *   scan k    : do_raycast = 1, raycast_defer_apply = 1      (accumulate, leave the result pending)
+   *   scan k + 1: do_raycast = 0, raycast_apply_pending = 1    (after this scan's point update: apply(raycast_its_diff) + flags.clear()) */
+  int32_t raycast_defer_apply;
+  int32_t raycast_apply_pending;
 } vofod_schedule;
 
 typedef struct vofod_scan_result {
@@ -292,6 +299,11 @@ int vofod_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_p
 /* announce the NEXT scan: its host->device copy runs on a copy stream next to the current scan's kernels; the following
  * vofod_process_scan with the same `scan` pointer consumes it.  Keep the host buffer (ideally pinned) untouched until then. */
 int vofod_prefetch_scan(vofod_ctx*, const vofod_pt* scan, size_t n);
+/* a sequence of scans from host buffers back to back (replay, benchmarks): the copy of scan k + 1 overlaps the kernels of scan k and the
+ * host spends microseconds between two scans.  poses / scheds / results: one per scan; dets: det_cap records per scan (may be NULL). */
+int vofod_process_scan_batch(vofod_ctx*, const vofod_pt* const* scans, size_t n_scans, size_t n, const vofod_pose* poses,
+                             const vofod_params*, const vofod_schedule* scheds, vofod_scan_result* results,
+                             vofod_detection* dets, size_t det_cap, uint32_t* n_dets, size_t* n_done);
 /* same, but the scan is already in device memory (bench "value" leg: inputs resident in HBM) */
 int vofod_upload_scan(vofod_ctx*, int slot, const vofod_pt* scan, size_t n);
 int vofod_process_scan_resident(vofod_ctx*, int slot, const vofod_pose*, const vofod_params*,
@@ -364,6 +376,10 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
 #define VOFOD_OPT_PDL 6            /* default 1: consecutive kernels are chained by programmatic dependent launch */
 #define VOFOD_OPT_RAYCAST_NO_AGG 2 /* tuning switch (default 0): one RED per traversal instead of warp-aggregated REDs */
 #define VOFOD_OPT_SLAB_PATCH_WORDS 11 /* slab mode: capacity (uint32 words) of the buffer that carries the classification candidates' map boxes (0 = automatic) */
+#define VOFOD_OPT_ACC_SPARSE 12   /* raycast accumulator "touched" marks (apply visits only groups of 32 cells the rays added to): 0 automatic (windows of 2^25 cells and
+                                      more, i.e. long rays on a fine grid), 1 always, 2 never */
+#define VOFOD_OPT_RAYCAST_EXP 13   /* MEASUREMENT ONLY (the raycast results are wrong while it is set): 1 = the accumulate kernel does everything but the RED itself,
+                                      2 = the DDA alone (no match / redux / RED): what the instruction stream costs without the memory side */
 #define VOFOD_OPT_RAYCAST_STATS 10 /* instrumentation switch (default 0): the accumulate kernel also fills per warp-step histograms, see vofod_raycast_stats */
 int vofod_set_option(vofod_ctx*, int option, int value);
 /* VOFOD_OPT_RAYCAST_STATS: out[0..32] = warp-steps with that many lanes (rays) in the loop, out[33..65] = warp-steps with that many distinct

@@ -758,6 +758,7 @@ struct Oracle
     bg_local.resizeAs(voxel_map);
     on_resize();
     detection_its = 0;
+    raycast_pending = false;
     background_pts_sufficient = sure_background_sufficient = false;
     last_detection_id = 0;
   }
@@ -1150,6 +1151,7 @@ struct Oracle
   }
 
   // ---- processMsg in the deterministic schedule S1
+  bool raycast_pending = false;  // an accumulate whose apply was deferred to a later scan
   int process_scan(const vofod_pt* scan, const size_t n, const vofod_pose& tf, const vofod_params& p, const vofod_schedule& s, vofod_scan_result& res)
   {
     std::memset(&res, 0, sizeof(res));
@@ -1175,13 +1177,26 @@ struct Oracle
     stage_ms[4] = clk.lap();  // "vmap update"
     res.raycast_status = VOFOD_W_PAUSED;
     n_traversals = 0;  // reported per scan
+    // the raycast thread (:1397-1606): accumulate, wait for a detection to finish, apply.  With raycast_defer_apply the apply waits
+    // for the NEXT scan's point update (raycast_apply_pending), as the reference's threads settle (:950-957, 1530-1539)
+    if (s.raycast_apply_pending && raycast_pending)
+    {
+      raycast_pending = false;
+      res.raycast_status = raycast_apply(std::max(s.raycast_its_diff, 1), p);
+      stage_ms[6] = clk.lap();
+    }
     if (s.do_raycast)
     {
       res.raycast_status = raycast_accumulate(scan, n, tf, p);
       stage_ms[5] = clk.lap();  // "raycasting"
-      if (res.raycast_status >= 0 && res.raycast_status != VOFOD_W_PAUSED)
-        res.raycast_status = std::max(res.raycast_status, raycast_apply(std::max(s.raycast_its_diff, 1), p));
-      stage_ms[6] = clk.lap();  // raycast "vmap update"
+      if (res.raycast_status >= 0 && res.raycast_status != VOFOD_W_PAUSED && res.raycast_status != VOFOD_W_SENSOR_OOB)
+      {
+        if (s.raycast_defer_apply)
+          raycast_pending = true;
+        else
+          res.raycast_status = std::max(res.raycast_status, raycast_apply(std::max(s.raycast_its_diff, 1), p));
+      }
+      stage_ms[6] += clk.lap();  // raycast "vmap update"
     }
     cluster_infos.clear();
     detections.clear();

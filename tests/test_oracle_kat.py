@@ -150,3 +150,44 @@ def test_bootstrap_and_detection_sequence(cpu):
             assert dist < 1.0, (k, det["position"], sph)
             seen += 1
     assert res.background_pts_sufficient and res.sure_background_sufficient and seen >= 3
+
+
+def test_deferred_apply_flags_equal_the_staged_calls(oracle_mod):
+    """vofod_schedule::raycast_defer_apply / raycast_apply_pending in the fused call = the reference's steady state driven call by call
+    (accumulate at scan k, apply after scan k + 1's point update, no new raycast while one is in flight)"""
+    from harness import Sensor, small_params
+    sensor = Sensor(256, 16)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    a, b = oracle_mod.Oracle(False, False), oracle_mod.Oracle(False, False)
+    for o in (a, b):
+        o.reset(p, vs)
+        o.set_sensor(sensor.W, sensor.H, sensor.dirs)
+    pending = False
+    for k in range(16):
+        scan, pose, rp, _ = sensor.scan(1, k)
+        s = abi.schedule_s1(rp, do_raycast=False)
+        do_apply, do_acc = False, False
+        if pending:
+            s.raycast_apply_pending, do_apply, pending = 1, True, False
+        elif k % 2 == 0:
+            s.do_raycast, s.raycast_defer_apply, do_acc, pending = 1, 1, True, True
+        a.process_scan(scan, pose, p, s)
+        # the same scan through the staged entry points
+        for _ in range(10):
+            b.range_update(rp, p)
+        vox = b.filter_voxelize(scan, pose, p)
+        labels, _ = b.cluster(np.stack([vox["x"], vox["y"], vox["z"]], 1), p.ground_points_max_distance)
+        close, _ = b.close_far(vox, labels, p)
+        b.update_points(vox, close, 1, p.score_point, 2.0)
+        b.update_points(vox, close, 0, p.score_unknown, 3.0)
+        if do_apply:
+            b.raycast_apply(1, p)
+        if do_acc:
+            b.raycast_accumulate(scan, pose, p)
+        b.classify_detect(vox, labels, close, pose, p)
+        b.sepclusters(1, p)
+        assert np.array_equal(a.map_download(), b.map_download(), equal_nan=True), k
+        assert np.array_equal(a.map_download(abi.MAP_FLAGS), b.map_download(abi.MAP_FLAGS)), k
+    a.close()
+    b.close()

@@ -285,6 +285,26 @@ def test_process_scan_small_city(gpu, cpu):
     _run_sequence(gpu, cpu, sensor, p, vs, 0, range(0, 30), fixed=True)
 
 
+def test_process_scan_sparse_accumulator_marks(gpu, cpu):
+    """the raycast apply that visits only the groups of 32 accumulator cells the rays touched (automatic for GB-sized windows: long rays on
+    a fine grid), forced on here on a small map: same results bit for bit, and back to the dense pass in the middle of the sequence"""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    gpu.set_option(abi.OPT_ACC_SPARSE, 1)
+    setup_pair(cpu, gpu, p, vs, sensor)
+    for k in range(0, 20):
+        if k == 12:
+            gpu.set_option(abi.OPT_ACC_SPARSE, 2)
+        scan, pose, rp, _ = sensor.scan(0, k)
+        s = abi.schedule_s1(rp)
+        rg, _ = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits() or 24)
+        rc, _ = cpu.process_scan(scan, pose, p, s)
+        assert rg.as_dict() == rc.as_dict(), k
+        assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
+
+
 def test_process_scan_small_gazebo_detections(gpu, cpu):
     """cfg3 shape: ground + buildings + 3 sphere UAVs; detections must fire and agree."""
     sensor = Sensor(1024, 64)
@@ -881,3 +901,35 @@ def test_live_reconfigure_between_scans(gpu, cpu):
             # once the OLD update rule has run: its std::pow(float, float) is glibc's powf on the host (0.5x ulp, not correctly
             # rounded) and an fp64 pow rounded to fp32 on the device — 1-ulp differences in a few cells, far inside 1e-5 relative
             assert rel_err(a, b).max() < SCORE_RTOL, (k, float(rel_err(a, b).max()))
+
+
+def test_fused_call_reference_steady_state_schedule(gpu, cpu):
+    """Schedule S2 (what the reference's threads settle into, vofod_nodelet.cpp:950-957, 1530-1539, 1602) through the FUSED call: scan k
+    accumulates its rays and leaves them pending (raycast_defer_apply), scan k + 1 applies them after its own point update with the flags
+    of both scans still set (raycast_apply_pending), scan k + 2 starts the next raycast.  Two launch sequences alternate, both get captured
+    and replayed as CUDA graphs.  Compared with the oracle running the same flags — which tests/test_oracle_kat.py pins to the staged calls."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    setup_pair(cpu, gpu, p, vs, sensor)
+    pending, n_det = False, 0
+    for k in range(40):
+        scan, pose, rp, _ = sensor.scan(1, k)
+        s = abi.schedule_s1(rp, do_raycast=False)
+        if pending:
+            s.raycast_apply_pending = 1
+            pending = False
+        elif k % 2 == 0:
+            s.do_raycast, s.raycast_defer_apply = 1, 1
+            pending = True
+        rg, dg = gpu.process_scan(scan, pose, p, s)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits() or 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        assert rg.as_dict() == rc.as_dict(), (k, rg.as_dict(), rc.as_dict())
+        assert len(dg) == len(dc) and np.array_equal(dg["id"], dc["id"])
+        n_det += len(dc)
+        assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
+        assert np.array_equal(gpu.map_download(abi.MAP_FLAGS), cpu.map_download(abi.MAP_FLAGS)), k
+    assert n_det > 0
+    st = gpu.stats()
+    assert st["graph_replays"] >= 20 and st["captures"] >= 2, st

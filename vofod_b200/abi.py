@@ -111,7 +111,7 @@ class Detection(C.Structure):
 class Schedule(C.Structure):
     _fields_ = [("n_range_seeds", C.c_int32), ("range_pt", C.c_float * 3), ("do_raycast", C.c_int32),
                 ("raycast_its_diff", C.c_int32), ("do_classify", C.c_int32), ("do_sepclusters", C.c_int32),
-                ("sep_its_diff", C.c_int32)]
+                ("sep_its_diff", C.c_int32), ("raycast_defer_apply", C.c_int32), ("raycast_apply_pending", C.c_int32)]
 
 
 class ScanResult(C.Structure):
@@ -212,3 +212,5 @@ class SlabExchange(C.Structure):
 XCHG_SUM_U64, XCHG_MAX_I32, XCHG_SUM_U32, XCHG_GATHER_U32 = 0, 1, 2, 3
 VOFOD_W_REDO = 5
 OPT_SLAB_PATCH_WORDS = 11
+OPT_ACC_SPARSE = 12
+OPT_RAYCAST_EXP = 13

@@ -149,6 +149,7 @@ def load_library():
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
         "vofod_set_slab": (i32, [vp, i32, i32, i32, i32]),
+        "vofod_process_scan_batch": (i32, [vp, vp, sz, sz, vp, P(Params), vp, vp, vp, sz, vp, P(sz)]),
         "vofod_load_cloud": (i32, [C.c_char_p, vp, sz, P(sz)]),
         "vofod_apriori_map": (i32, [vp, vp, sz, P(Pose), vp, sz, P(sz)]),
         "vofod_mask_mangle": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
@@ -474,6 +475,19 @@ class Vofod:
         if n.value:
             self._ck(self.lib.vofod_last_clusters(self.h, _p(out), n.value, C.byref(n)))
         return out
+
+    def process_scan_batch(self, scans, poses, params, scheds, det_cap=64):
+        """scans: list of PT_DTYPE arrays (ideally views of pinned memory); -> (list of ScanResult, number of scans done)"""
+        k = len(scans)
+        ptrs = (C.c_void_p * k)(*[s.ctypes.data for s in scans])
+        pose_arr = (Pose * k)(*poses)
+        sched_arr = (Schedule * k)(*scheds)
+        res_arr = (ScanResult * k)()
+        dets = np.zeros(k * det_cap, dtype=DETECTION_DTYPE)
+        ndet = np.zeros(k, dtype=np.uint32)
+        done = C.c_size_t()
+        self._ck(self.lib.vofod_process_scan_batch(self.h, ptrs, k, len(scans[0]), pose_arr, C.byref(params), sched_arr, res_arr, _p(dets), det_cap, _p(ndet), C.byref(done)))
+        return list(res_arr), done.value
 
     def apriori_map(self, xyz, pose, want_centroids=True):
         """initialize_apriori_map (vofod_nodelet.cpp:305-353) from a loaded cloud -> the down-sampled cloud (M x 3)"""

@@ -204,6 +204,7 @@ struct ScanDyn
   const vofod_pt* scan;      // packed scan of this call (staging buffer or resident slot)
   int its_raycast;           // detection_its_diff of the raycast apply
   int pad;
+  Window win_apply;          // window of the accumulate that this call applies (= win, or the window of an earlier scan whose apply was deferred)
 };
 #define EPOCH_STRIDE 64      // look-back launches per API call are numbered 0..63
 
@@ -285,6 +286,7 @@ struct vofod_ctx
   // large windows (long rays on a fine grid: GBs): one "touched" byte per 32 accumulator cells behind the cells, set by the accumulate
   // kernel, so that the apply pass reads 1/256 of the window + the touched 256-byte groups instead of all of it
   bool acc_sparse = false;
+  int acc_sparse_mode = 0;     // VOFOD_OPT_ACC_SPARSE: 0 automatic (windows of 2^25 cells and more), 1 always, 2 never
   size_t acc_dirty_off = 0;    // byte offset of the touched marks inside ctx->acc
   size_t acc_total_bytes = 0;  // cells + spare + marks: what a clear of the accumulator has to zero
 
@@ -352,6 +354,7 @@ struct vofod_ctx
   vofod_schedule slab_s;
   void* nccl_comm = nullptr;                            // ncclComm_t (vofod_comm_init)
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
+  int raycast_exp = 0;          // VOFOD_OPT_RAYCAST_EXP (measurement only)
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool raycast_stats = false;   // instrumentation switch: the accumulate kernel fills ray_stats (see RAY_STATS_SLOTS in raycast.cu)
   DevBuf ray_stats;
@@ -363,9 +366,21 @@ struct vofod_ctx
   bool capturing = false;
   bool capture_broken = false;
   uint64_t alloc_gen = 0;
-  uint64_t graph_sig = 0, last_eager_sig = 0, last_eager_alloc_gen = ~0ull;
-  cudaGraphExec_t graph_exec = nullptr;
-  uint64_t graph_kernels = 0;
+  // a few captured scans, keyed by the signature of their launch sequence (the reference's steady-state schedule alternates between two)
+  struct GraphSlot
+  {
+    uint64_t sig = 0;            // signature of `exec`
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;
+    uint64_t seen_sig = 0;       // signature of a kernel-by-kernel scan that ran without allocating (a second one like it gets captured)
+    uint64_t seen_gen = ~0ull;
+    uint64_t last_use = 0;
+  };
+  static constexpr int N_GRAPH_SLOTS = 4;
+  GraphSlot gslot[N_GRAPH_SLOTS];
+  uint64_t gslot_clock = 0;
+  bool ray_pending = false;     // an accumulate whose apply was deferred (vofod_schedule::raycast_defer_apply)
+  Window ray_pending_win;
   uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;
   int stat_last_capture_error = 0;  // 1 enqueue failed, 2 EndCapture failed, 3 buffer growth during capture, 4 instantiate failed, 5 BeginCapture failed
   size_t sep_cap_forced = 0;  // VOFOD_OPT_SEP_CAP

@@ -163,8 +163,9 @@ int vofod_destroy(vofod_ctx* ctx)
     free_buf(*b);
   for (int i = 0; i < VOFOD_SCAN_SLOTS; i++)
     free_buf(ctx->scan_slot[i]);
-  if (ctx->graph_exec)
-    cudaGraphExecDestroy(ctx->graph_exec);
+  for (auto& gs : ctx->gslot)
+    if (gs.exec)
+      cudaGraphExecDestroy(gs.exec);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   if (ctx->ev_ok)
@@ -271,10 +272,23 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->alloc_gen++;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_ACC_SPARSE)
+  {
+    ctx->acc_sparse_mode = value;
+    ctx->acc_cells_max = 0;  // forces vf_raycast_prepare to lay the accumulator out again (and clear it)
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_SLAB_PATCH_WORDS)
   {
     ctx->slab_patch_words_forced = value > 0 ? (size_t)value : 0;
     ctx->slab_patch_words = 0;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_RAYCAST_EXP)
+  {
+    ctx->raycast_exp = value;
+    ctx->alloc_gen++;
     return VOFOD_OK;
   }
   if (option == VOFOD_OPT_RAYCAST_NO_AGG)
@@ -787,6 +801,7 @@ int vf_map_alloc(vofod_ctx* ctx)
   ctx->alloc_gen++;
   ctx->win_valid = false;
   ctx->acc_has_data = false;
+  ctx->ray_pending = false;
   ctx->map_ready = true;
   return 0;
 }
@@ -902,6 +917,7 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
     if (ctx->win_valid)
       CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, ctx->stream));
     ctx->acc_has_data = false;
+  ctx->ray_pending = false;
   } else
     return vf_fail(ctx, VOFOD_E_INVALID, "bad map id %d", which);
   return VOFOD_OK;

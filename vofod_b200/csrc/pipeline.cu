@@ -605,7 +605,9 @@ struct ScanPlan
   size_t n;
   vofod_params p;
   vofod_schedule s;
-  bool raycast_on;     // do_raycast && not paused && sensor inside the map
+  bool raycast_on;     // do_raycast && not paused && sensor inside the map: this scan's rays are accumulated
+  bool apply_on;       // an accumulate is applied in this call: this scan's (unless deferred) or a pending one
+  bool apply_first;    // the pending one: before this scan's own accumulate may touch the accumulator
   int raycast_status;  // VOFOD_OK / W_PAUSED / W_SENSOR_OOB as known on the host before launching
   size_t sep_cap;      // 0 = exact sepclusters (host round trip inside), else capped list
   bool timed;          // record the per-stage events
@@ -643,7 +645,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   // The stage-local clears (hash table of the clustering, work arrays of classification and sepclusters) depend on nothing
   // either: they open the side branch, so that the main chain finds them done.
   const bool side = !plan.timed && ctx->stream2 != nullptr && ctx->overlap_enabled;
-  const bool overlap_raycast = plan.raycast_on && side;
+  const bool overlap_raycast = plan.raycast_on && side && !plan.apply_first;
   if (side)
   {
     CK(cudaEventRecord(ctx->ev_fork, st));
@@ -734,7 +736,16 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   *applied_out = false;
   if (side)
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));  // join: the apply needs the accumulator
-  if (overlap_raycast)
+  if (plan.apply_first)
+  {
+    // the raycast thread wakes up after this scan's point update: apply the pending accumulate, clear the flags (:1530-1602)
+    const int rc = vf_raycast_apply_dev(ctx, 0, p);
+    if (rc < 0)
+      return rc;
+    *applied_out = rc == VOFOD_OK;
+    ZERO_CNT(CNT_TRAVERSALS, 1);
+    ZERO_CNT(CNT_OOB, 1);
+  } else if (overlap_raycast)
     ;
   else if (plan.raycast_on)
     RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
@@ -750,7 +761,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     }
   }
   STAGE_EVENT();  // 5 "raycasting"
-  if (plan.raycast_on)
+  if (plan.apply_on && !plan.apply_first)
   {
     const int rc = vf_raycast_apply_dev(ctx, 0, p);
     if (rc < 0)
@@ -809,12 +820,20 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   plan.s = s;
   plan.raycast_status = VOFOD_W_PAUSED;
   plan.raycast_on = false;
-  if (s.do_raycast)
+  plan.apply_first = s.raycast_apply_pending && ctx->ray_pending && !p.raycast_pause;
+  if (plan.apply_first)
+  {
+    // a raycast is "in flight": like the reference (:952-957) no new one starts in this call, whatever do_raycast says
+    ctx->h_dyn->win_apply = ctx->ray_pending_win;
+    plan.raycast_status = VOFOD_OK;
+    plan.apply_on = true;
+  } else if (s.do_raycast)
   {
     plan.raycast_status = vf_raycast_prepare(ctx, n, tf, p);  // host only; fills h_dyn->win
     if (plan.raycast_status < 0)
       return plan.raycast_status;
     plan.raycast_on = plan.raycast_status == VOFOD_OK;
+    plan.apply_on = plan.raycast_on && !s.raycast_defer_apply;
   }
   // per-scan dynamic arguments
   ScanDyn* hd = ctx->h_dyn;
@@ -829,8 +848,8 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   // ---- signature of the launch sequence: everything by-value or host-decided that enqueue_scan depends on
   uint64_t sig = 1469598103934665603ull;
   sig = fnv1a(&p, sizeof(p), sig);
-  const int flags[8] = {s.do_raycast, s.do_classify, s.do_sepclusters, s.sep_its_diff, plan.raycast_on ? 1 : 0, plan.raycast_status, ctx->flags_full_dirty ? 1 : 0,
-                        ctx->acc_has_data ? 1 : 0};
+  const int flags[10] = {s.do_raycast, s.do_classify, s.do_sepclusters, s.sep_its_diff, plan.raycast_on ? 1 : 0, plan.raycast_status, ctx->flags_full_dirty ? 1 : 0,
+                         ctx->acc_has_data ? 1 : 0, plan.apply_on ? 1 : 0, plan.apply_first ? 1 : 0};
   sig = fnv1a(flags, sizeof(flags), sig);
   sig = fnv1a(&n, sizeof(n), sig);
   sig = fnv1a(&ctx->g, sizeof(ctx->g), sig);
@@ -849,21 +868,34 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   const bool epoch_wrap_soon = (((ctx->epoch_calls + 1) * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE;
   const bool graph_ok = ctx->graph_enabled && !epoch_wrap_soon && (!s.do_sepclusters || p.sep_pause || ctx->sep_cap > 0);
   CK(cudaEventRecord(ctx->ev[0], st));
-  if (graph_ok && ctx->graph_exec && ctx->graph_sig == sig)
+  // what the accumulator holds after this scan
+  const bool acc_after = plan.apply_on ? !p.raycast_new_update_rule
+                                       : (plan.raycast_on ? true : ((s.do_raycast && plan.raycast_status == VOFOD_W_SENSOR_OOB) ? false : ctx->acc_has_data));
+  vofod_ctx::GraphSlot* hit = nullptr;
+  vofod_ctx::GraphSlot* seen = nullptr;
+  for (auto& gs : ctx->gslot)
+  {
+    if (gs.exec && gs.sig == sig)
+      hit = &gs;
+    if (gs.seen_sig == sig && gs.seen_gen == ctx->alloc_gen)
+      seen = &gs;
+  }
+  if (graph_ok && hit)
   {
     // ---- replay
     plan.sep_cap = ctx->sep_cap;  // the capacity the captured pass runs with: the overflow check below needs it
     ctx->epoch_calls++;
     ctx->stat_replays++;
-    CK(cudaGraphLaunch(ctx->graph_exec, st));
-    ctx->n_launches += ctx->graph_kernels;
+    hit->last_use = ++ctx->gslot_clock;
+    CK(cudaGraphLaunch(hit->exec, st));
+    ctx->n_launches += hit->kernels;
     sep_status = (s.do_sepclusters && !p.sep_pause) ? VOFOD_OK : VOFOD_W_PAUSED;
-    applied = plan.raycast_on;
-    ctx->acc_has_data = plan.raycast_on ? !p.raycast_new_update_rule : ctx->acc_has_data;
+    applied = plan.apply_on;
+    ctx->acc_has_data = acc_after;
     used_graph = true;
-  } else if (graph_ok && ctx->last_eager_sig == sig && ctx->last_eager_alloc_gen == ctx->alloc_gen)
+  } else if (graph_ok && seen)
   {
-    // ---- second identical eager scan without any allocation in between: capture, instantiate, launch
+    // ---- a kernel-by-kernel scan with this signature ran before without any allocation: capture, instantiate, launch
     plan.sep_cap = ctx->sep_cap;
     plan.timed = false;
     const bool acc_before = ctx->acc_has_data;
@@ -897,13 +929,15 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     }
     if (why == 0)
     {
-      if (ctx->graph_exec)
-        cudaGraphExecDestroy(ctx->graph_exec);
-      ctx->graph_exec = exec;
-      ctx->graph_sig = sig;
-      ctx->graph_kernels = ctx->n_launches - launches_before;
+      if (seen->exec)
+        cudaGraphExecDestroy(seen->exec);
+      seen->exec = exec;
+      seen->sig = sig;
+      seen->kernels = ctx->n_launches - launches_before;
+      seen->last_use = ++ctx->gslot_clock;
       cudaGraphDestroy(graph);
-      CK(cudaGraphLaunch(ctx->graph_exec, st));
+      CK(cudaGraphLaunch(seen->exec, st));
+      ctx->acc_has_data = acc_after;
       used_graph = true;
     } else
     {
@@ -914,7 +948,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
       ctx->acc_has_data = acc_before;
       ctx->epoch_calls = calls_before;
       ctx->n_launches = launches_before;
-      ctx->last_eager_sig = 0;
+      seen->seen_sig = 0;
       ctx->err.clear();
     }
   }
@@ -926,9 +960,28 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     plan.timed = true;
     const uint64_t gen_before = ctx->alloc_gen;
     RET(enqueue_scan(ctx, plan, &sep_status, &applied));
-    ctx->last_eager_sig = (gen_before == ctx->alloc_gen) ? sig : 0;
-    ctx->last_eager_alloc_gen = ctx->alloc_gen;
+    ctx->acc_has_data = acc_after;
+    if (gen_before == ctx->alloc_gen)
+    {
+      // remember the signature in the slot used longest ago (a slot that already remembers it, first)
+      vofod_ctx::GraphSlot* slot = &ctx->gslot[0];
+      for (auto& gs : ctx->gslot)
+        if (gs.last_use < slot->last_use)
+          slot = &gs;
+      for (auto& gs : ctx->gslot)
+        if (gs.sig == sig || gs.seen_sig == sig)
+          slot = &gs;
+      slot->seen_sig = sig;
+      slot->seen_gen = ctx->alloc_gen;
+      slot->last_use = ++ctx->gslot_clock;
+    }
   }
+  if (plan.raycast_on && !plan.apply_on)
+  {
+    ctx->ray_pending = true;  // its apply comes with a later scan (raycast_apply_pending)
+    ctx->ray_pending_win = ctx->win;
+  } else if (plan.apply_first)
+    ctx->ray_pending = false;
   ctx->detection_its++;
   CK(cudaEventRecord(ctx->ev[11], st));
   CK(cudaStreamSynchronize(st));
@@ -1092,6 +1145,33 @@ int vofod_process_scan_resident(vofod_ctx* ctx, int slot, const vofod_pose* tf, 
   if (!tf || !p || !s || slot < 0 || slot >= VOFOD_SCAN_SLOTS || !ctx->scan_slot_n[slot])
     return vf_fail(ctx, VOFOD_E_INVALID, "bad argument / empty scan slot");
   return process_scan_dev(ctx, ctx->scan_slot[slot].as<vofod_pt>(), ctx->scan_slot_n[slot], *tf, *p, *s, res, dets, det_cap);
+}
+
+/* A sequence of scans from host buffers, back to back (rosbag replay, benchmarks): scan k + 1's host->device copy is announced before scan
+ * k is processed, so it overlaps scan k's kernels, and the host spends a few microseconds between two scans instead of a round trip
+ * through the caller's language binding.  results[k] / the detections of scan k (dets + k * det_cap, n_dets[k]) are those of
+ * vofod_process_scan on the same inputs.  Stops at the first error and returns it; *n_done = scans completed. */
+int vofod_process_scan_batch(vofod_ctx* ctx, const vofod_pt* const* scans, size_t n_scans, size_t n, const vofod_pose* poses, const vofod_params* p,
+                             const vofod_schedule* scheds, vofod_scan_result* results, vofod_detection* dets, size_t det_cap, uint32_t* n_dets, size_t* n_done)
+{
+  NEED_MAP();
+  if (!scans || !poses || !p || !scheds || !results)
+    return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
+  if (n_done)
+    *n_done = 0;
+  for (size_t k = 0; k < n_scans; k++)
+  {
+    if (k + 1 < n_scans)
+      RET(vofod_prefetch_scan(ctx, scans[k + 1], n));
+    const int rc = vofod_process_scan(ctx, scans[k], n, poses + k, p, scheds + k, results + k, dets ? dets + k * det_cap : nullptr, det_cap);
+    if (rc < 0)
+      return rc;
+    if (n_dets)
+      n_dets[k] = results[k].n_detections;
+    if (n_done)
+      *n_done = k + 1;
+  }
+  return VOFOD_OK;
 }
 
 int vofod_last_voxels(vofod_ctx* ctx, vofod_vox* out, int32_t* labels, uint8_t* in_close, size_t cap, size_t* m)

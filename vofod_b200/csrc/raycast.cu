@@ -67,7 +67,8 @@ __device__ __forceinline__ void ray_stats(unsigned long long* stats, const unsig
 //          first step that leaves the slab's window along the slab axis (it never comes back).
 //  !FAST = the reference's loop with the `cur[i] == last[i]` countdown; with SLAB, steps outside the window are walked but not
 //          written.
-template <bool AGG, bool SLAB, bool FAST, bool STATS>
+// EXP (VOFOD_OPT_RAYCAST_EXP, measurement only — results are wrong): 1 = everything but the RED itself, 2 = the DDA alone (no match / redux / RED)
+template <bool AGG, bool SLAB, bool FAST, bool STATS, int EXP = 0>
 __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const float scale, const int slab_axis, const int ssize, const int own_lo, const int own_n,
                                              const int wn, unsigned long long* __restrict__ acc, const unsigned lane, const unsigned lanemask_lt,
                                              unsigned long long* stats, uint8_t* __restrict__ touched)
@@ -95,13 +96,21 @@ __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const floa
       // the window holds every voxel within max_dist, so this clamp never bites; if it ever did, the update would land in the
       // spare cell behind the window (and the apply kernel reports it) instead of corrupting memory
       key = (int)min((unsigned)r.widx, (unsigned)wn);
-    if (AGG)
+    if (EXP == 2)
+    {
+      if (q == 0x7fffffff && key == -12345)  // keeps q and key alive
+        steps += 1000u;
+    } else if (AGG)
     {
       const unsigned am = __activemask();
       const unsigned m = __match_any_sync(am, key);
       const int sum = __reduce_add_sync(m, q);
       const bool leader = (m & lanemask_lt) == 0;
-      if (inside && leader)
+      if (EXP == 1)
+      {
+        if (leader && sum == 0x7fffffff && __popc(m) == 33)
+          steps += 1000u;
+      } else if (inside && leader)
       {
         red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
         if (touched)
@@ -208,7 +217,7 @@ __device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axi
 
 // RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
 // returns a few metres), so small blocks balance better: 64 threads = 2 warps = 64 neighbouring columns of one row.
-template <int RB, bool AGG, bool SLAB, bool STATS>
+template <int RB, bool AGG, bool SLAB, bool STATS, int EXP = 0>
 __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters,
@@ -320,12 +329,12 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
   {
     if (SLAB && alive)
       alive = ray_skip_to_slab<true>(r, slab_axis, ssize, skipped);
-    steps = ray_loop<AGG, SLAB, true, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    steps = ray_loop<AGG, SLAB, true, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
   } else
   {
     if (SLAB && slab_axis < 2 && alive)
       alive = ray_skip_to_slab<false>(r, slab_axis, ssize, skipped);
-    steps = ray_loop<AGG, SLAB, false, STATS>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    steps = ray_loop<AGG, SLAB, false, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
   }
   __syncwarp();
   if (STATS && skipped)
@@ -362,7 +371,7 @@ struct ApplyArgs
 __global__ void __launch_bounds__(256) k_raycast_max(const ScanDyn* __restrict__ dyn, const unsigned long long* __restrict__ acc, const double inv_scale, unsigned* __restrict__ out_bits)
 {
   pdl_enter();
-  const Window w = after_wait(dyn)->win;
+  const Window w = after_wait(dyn)->win_apply;
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
   float mx = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
                                                        unsigned long long* __restrict__ counters, uint8_t* __restrict__ touched)
 {
   pdl_enter();
-  const Window w = dyn->win;
+  const Window w = dyn->win_apply;
   const float its = (float)dyn->its_raycast;  // detection_its_diff as float (:1539)
   const long long n = (long long)w.size[0] * w.size[1] * w.size[2];
   // the spare cell behind the window catches updates the accumulate kernel had to clamp (must never happen)
@@ -406,80 +415,139 @@ __global__ void __launch_bounds__(256) k_raycast_apply(const ApplyArgs a, const 
       return;  // :1544-1548 (the host also skips the flag clear)
   }
   bool any_pos = false;  // max_element(raycast) > 0 (:1542-1548): some cell holds a positive length
+  // Every thread keeps APPLY_U cells in flight, stage by stage (accumulator words, then flags, then scores): with one cell per
+  // iteration the pass is a chain of three dependent memory round trips per cell and runs at a third of the bandwidth.
   // `touched` != NULL (large windows): the accumulate kernel marked every group of 32 cells it added to; a warp fetches 32 marks at a
-  // time and visits the marked groups only.  Otherwise: every cell of the window.
+  // time and visits the marked groups only, APPLY_U groups per round.  Otherwise: every cell of the window.
+  constexpr int APPLY_U = 4;
   const unsigned lane = threadIdx.x & 31;
   const long long n_groups = (n + 31) >> 5;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned wsxy = (unsigned)wsx * (unsigned)wsy;
+  const bool idx32 = n < (1ll << 32);
   long long gbase = touched ? warp0 * 32 : 0;
   unsigned pending = 0;
-  long long i = touched ? -1 : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i_next = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   while (true)
   {
+    long long idx[APPLY_U];
     if (touched)
     {
-      // next marked group of this warp
-      while (pending == 0)
+      bool have_first = false;  // warp-uniform: slot 0 got a group (slots are filled in order: none for slot 0 = nothing left)
+#pragma unroll
+      for (int k = 0; k < APPLY_U; k++)
       {
-        if (gbase >= n_groups)
-          break;
-        const long long g = gbase + lane;
-        const bool mark = g < n_groups && touched[g] != 0;
-        pending = __ballot_sync(VOFOD_FULL, mark);
-        if (mark)
-          touched[g] = 0;
-        if (pending == 0)
-          gbase += n_warps * 32;
+        // next marked group of this warp (all decisions are warp-uniform)
+        while (pending == 0 && gbase < n_groups)
+        {
+          const long long g = gbase + lane;
+          const bool mark = g < n_groups && touched[g] != 0;
+          pending = __ballot_sync(VOFOD_FULL, mark);
+          if (mark)
+            touched[g] = 0;
+          if (pending == 0)
+            gbase += n_warps * 32;
+        }
+        idx[k] = -1;
+        if (pending != 0)
+        {
+          const int bit = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const long long c = ((gbase + bit) << 5) + lane;
+          if (c < n)
+            idx[k] = c;
+          if (k == 0)
+            have_first = true;
+          if (pending == 0)
+            gbase += n_warps * 32;
+        }
       }
-      if (pending == 0)
+      if (!have_first)
         break;
-      const int b = __ffs(pending) - 1;
-      pending &= pending - 1;
-      i = ((gbase + b) << 5) + lane;
-      if (pending == 0)
-        gbase += n_warps * 32;
-      if (i >= n)
+    } else
+    {
+      if (i_next >= n)
+        break;
+#pragma unroll
+      for (int k = 0; k < APPLY_U; k++)
+      {
+        idx[k] = i_next < n ? i_next : -1;
+        i_next += stride;
+      }
+    }
+    // stage 1: accumulator words
+    unsigned long long pw[APPLY_U];
+#pragma unroll
+    for (int k = 0; k < APPLY_U; k++)
+      pw[k] = idx[k] >= 0 ? acc[idx[k]] : 0ull;
+    // stage 2: decode, window -> grid index
+    float rv[APPLY_U];
+    long long ci[APPLY_U];
+#pragma unroll
+    for (int k = 0; k < APPLY_U; k++)
+    {
+      rv[k] = 0.f;
+      ci[k] = -1;
+      if (pw[k])
+      {
+        acc[idx[k]] = 0ull;  // m_voxel_raycast.clear() for the next scan (:1430)
+        unsigned c;
+        long long lq;
+        acc_decode(pw[k], c, lq);
+        rv[k] = (float)((double)lq * a.inv_scale);
+        if (rv[k] > 0.0f)
+        {
+          any_pos = true;
+          int wx, wy, wz;
+          if (idx32)
+          {
+            const unsigned u = (unsigned)idx[k];
+            wz = (int)(u / wsxy);
+            const unsigned r = u - (unsigned)wz * wsxy;
+            wy = (int)(r / (unsigned)wsx);
+            wx = (int)(r - (unsigned)wy * (unsigned)wsx);
+          } else
+          {
+            wx = (int)(idx[k] % wsx);
+            wy = (int)((idx[k] / wsx) % wsy);
+            wz = (int)(idx[k] / ((long long)wsx * wsy));
+          }
+          ci[k] = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
+        }
+      }
+    }
+    // stage 3: flags (flag == m_vflags_unmarked, :1561), stage 4: scores
+    uint8_t fl[APPLY_U];
+#pragma unroll
+    for (int k = 0; k < APPLY_U; k++)
+      fl[k] = ci[k] >= 0 ? flags[ci[k]] : (uint8_t)1;
+    float mv[APPLY_U];
+#pragma unroll
+    for (int k = 0; k < APPLY_U; k++)
+      mv[k] = fl[k] == 0 ? score[ci[k]] : 0.f;
+#pragma unroll
+    for (int k = 0; k < APPLY_U; k++)
+    {
+      if (fl[k] != 0)
         continue;
-    } else
-    {
-      if (i >= n)
-        break;
+      float w1;
+      if (a.new_rule)
+      {
+        const float n_int = a.weighting_factor * rv[k];                 // :1565
+        w1 = (float)exp2((double)(-its * n_int));                     // :1567  std::pow(2, float) -> double pow
+      } else
+      {
+        const float norm_val = rv[k] / max_val;                         // :1587
+        const float ws = a.ray_weight * sqrtf(norm_val);                // :1591
+        // :1593 std::pow(float, float).  CUDA's powf is a few ulp off; the fp64 pow rounded to fp32 reproduces the host's
+        // (correctly rounded) powf except in vanishingly rare double-rounding cases
+        w1 = (float)pow((double)(1.0f - ws), (double)its);
+        w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);                // std::clamp
+      }
+      const float w2 = 1.0f - w1;
+      score[ci[k]] = w1 * mv[k] + w2 * a.ray_score;                     // :1569 / :1597
     }
-    const long long i_cur = i;
-    if (!touched)
-      i += (long long)gridDim.x * blockDim.x;
-    const unsigned long long p = acc[i_cur];
-    if (!p)
-      continue;
-    acc[i_cur] = 0ull;  // m_voxel_raycast.clear() for the next scan (:1430)
-    unsigned c;
-    long long lq;
-    acc_decode(p, c, lq);
-    const float rv = (float)((double)lq * a.inv_scale);
-    if (!(rv > 0.0f))
-      continue;
-    any_pos = true;
-    const int wx = (int)(i_cur % wsx), wy = (int)((i_cur / wsx) % wsy), wz = (int)(i_cur / ((long long)wsx * wsy));
-    const long long ci = cell_index(a.g, wx + w.lo[0], wy + w.lo[1], wz + w.lo[2]);
-    if (ci < 0 || flags[ci] != 0)  // flag == m_vflags_unmarked (:1561)
-      continue;
-    const float m = score[ci];
-    float w1;
-    if (a.new_rule)
-    {
-      const float n_int = a.weighting_factor * rv;                    // :1565
-      w1 = (float)exp2((double)(-its * n_int));                     // :1567  std::pow(2, float) -> double pow
-    } else
-    {
-      const float norm_val = rv / max_val;                            // :1587
-      const float ws = a.ray_weight * sqrtf(norm_val);                // :1591
-      // :1593 std::pow(float, float).  CUDA's powf is a few ulp off; the fp64 pow rounded to fp32 reproduces the host's
-      // (correctly rounded) powf except in vanishingly rare double-rounding cases
-      w1 = (float)pow((double)(1.0f - ws), (double)its);
-      w1 = w1 < 0.0f ? 0.0f : (1.0f < w1 ? 1.0f : w1);                // std::clamp
-    }
-    const float w2 = 1.0f - w1;
-    score[ci] = w1 * m + w2 * a.ray_score;                            // :1569 / :1597
   }
   __syncwarp();
   if (__any_sync(VOFOD_FULL, any_pos) && (threadIdx.x & 31) == 0)
@@ -616,7 +684,7 @@ int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vof
     ENSURE(ctx->acc, total);  // fresh allocations are zero-filled
     ctx->acc_has_data = false;
   }
-  if (ctx->acc_cells_max != wn_max && ctx->acc_has_data && ctx->acc_total_bytes)
+  if (ctx->acc_cells_max != wn_max && ctx->acc_total_bytes && (ctx->acc_has_data || ctx->acc_cells_max == 0))
   {
     // the layout changes with max_dist (dynamic_reconfigure): start from a clean buffer
     CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes > total ? ctx->acc_total_bytes : total, ctx->stream));
@@ -624,11 +692,12 @@ int vf_raycast_prepare(vofod_ctx* ctx, size_t n, const vofod_pose& tf, const vof
   }
   ctx->acc_dirty_off = dirty_off;
   ctx->acc_total_bytes = total;
-  ctx->acc_sparse = wn_max >= (size_t(1) << 25);
+  ctx->acc_sparse = ctx->acc_sparse_mode == 1 || (ctx->acc_sparse_mode == 0 && wn_max >= (size_t(1) << 25));
   ctx->acc_cells_max = wn_max;
   ctx->win = w;
   ctx->win_valid = true;
   ctx->h_dyn->win = w;
+  ctx->h_dyn->win_apply = w;  // (a call that applies an earlier, deferred accumulate overrides it)
   ctx->frac_bits = choose_frac_bits(n, ctx->g.vs);
   return VOFOD_OK;
 }
@@ -665,7 +734,13 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
 #define RAY_LAUNCH(RB_, AGG_, SLAB_, STATS_)                                                                                                                 \
   LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_, STATS_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),       \
          ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched)
-  if (ctx->raycast_no_agg)
+  if (ctx->raycast_exp == 1 && !slab)
+    LAUNCH((k_raycast_accumulate<64, true, false, false, 1>), (int)((n + 63) / 64), 64, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),
+           ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched);
+  else if (ctx->raycast_exp == 2 && !slab)
+    LAUNCH((k_raycast_accumulate<64, true, false, false, 2>), (int)((n + 63) / 64), 64, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),
+           ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched);
+  else if (ctx->raycast_no_agg)
   {
     if (slab) RAY_LAUNCH(64, false, true, false); else RAY_LAUNCH(64, false, false, false);
   } else if (stats)

@@ -933,3 +933,4 @@ def test_fused_call_reference_steady_state_schedule(gpu, cpu):
     assert n_det > 0
     st = gpu.stats()
     assert st["graph_replays"] >= 20 and st["captures"] >= 2, st
+

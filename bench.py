@@ -433,7 +433,7 @@ SLAB_WORKLOAD = ("cfg5 large map: 0.25 m voxels, 500x500x100 m (2001x2001x401 ce
                  "map boxes, separated-background pass on the gathered voxel lists)")
 
 
-def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None):
+def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None, balanced=False):
     """scans/s of the slab path on `world` slabs (device-timed on the library's stream, max over ranks).  The scan of step k starts in
     pinned host memory on rank 0: H2D + NCCL broadcast are inside the timed region."""
     import torch
@@ -447,7 +447,15 @@ def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None):
     p.raycast_max_distance = float(raycast_max)
     dirs = synth.sim_lut(W, H)
     v = capi.Vofod(local_rank)
-    worker = slab.SlabWorker(v, p, 0.25, (W, H), dirs, rank, world, halo=16)
+    cuts = None
+    if balanced and world > 1:
+        # slab widths tuned to the flight area (a deployment knows where it flies): the sensor's x over the timed scans is around
+        # 30 sin(0.02 k) m, i.e. cell (x + 250) / 0.25; rays reach raycast_max around it
+        from vofod_b200 import multi
+        ks = np.arange(Wm, Wm + K)
+        centre = (float(np.mean(30.0 * np.sin(0.02 * ks))) + 250.0) / 0.25
+        cuts = multi.partition_by_ray_load(2001, world, centre, raycast_max / 0.25 + 120.0)
+    worker = slab.SlabWorker(v, p, 0.25, (W, H), dirs, rank, world, halo=16, cuts=cuts)
     N = W * H
     n_scans = K + Wm
     if scans is None:
@@ -497,7 +505,8 @@ def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None):
     return {"value": K / (total_ms * 1e-3), "unit": "scans/s", "ms_per_step": total_ms / K, "n_slabs": world, "steps": K, "warmup": Wm,
             "raycast_max_distance_m": raycast_max, "traversals_per_scan": trav / K, "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9,
             "detections_in_timed_steps": dets, "gpu_launches_rank0": int(launches), "slab0_storage_cells": cells,
-            "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize, "scaling": "strong"}, scans
+            "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize, "scaling": "strong",
+            "slab_cut": "by ray load (multi.partition_by_ray_load)" if cuts is not None else "equal width", "own_range_rank0": [int(worker.lo), int(worker.hi)]}, scans
 
 
 def slab_record(local_rank, rank, world, K, Wm, dists=(20.0, 200.0)):
@@ -511,10 +520,13 @@ def slab_record(local_rank, rank, world, K, Wm, dists=(20.0, 200.0)):
         key = "%gm" % d
         rec[key] = r
         if world > 1:
+            rb, _ = slab_leg(local_rank, rank, world, d, K, Wm, scans=scans, balanced=True)
+            r["cut_by_ray_load"] = {k: rb[k] for k in ("value", "ms_per_step", "slab_cut", "own_range_rank0", "slab0_storage_cells")}
             if rank == 0:
                 one, _ = slab_leg(local_rank, 0, 1, d, K, Wm, scans=scans)
                 r["one_gpu_same_run"] = {"value": one["value"], "ms_per_step": one["ms_per_step"]}
                 r["strong_scaling_efficiency"] = r["value"] / one["value"] / world
+                r["cut_by_ray_load"]["strong_scaling_efficiency"] = rb["value"] / one["value"] / world
             dist.barrier()
     return rec
 
@@ -638,7 +650,7 @@ def main():
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 (scene with UAVs / detections) sub-record")
     ap.add_argument("--no-numa-pin", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--slab-steps", type=int, default=20)
-    ap.add_argument("--slab-warmup", type=int, default=6)
+    ap.add_argument("--slab-warmup", type=int, default=30, help="past the bootstrap of the background (far clusters of 10^4 points until then)")
     ap.add_argument("--raycast-max", type=float, default=20.0, help="slab mode: raycast.max_distance [m] (yaml default 20, dynamic_reconfigure maximum 200)")
     ap.add_argument("--profile-leg", default="", choices=["", "graph", "eager"],
                     help="profiling aid: run ONLY the HBM-resident leg (graph replay or kernel-by-kernel) and print nothing the driver parses")

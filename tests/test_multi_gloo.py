@@ -54,3 +54,18 @@ def test_partition_covers_everything():
             edges = [multi.partition(n, r, world) for r in range(world)]
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+def test_partition_by_ray_load():
+    """the load-balanced slab cut: contiguous cover, narrow slabs around the sensor, and a far more even share of the ray work"""
+    import numpy as np
+    n, world, centre, reach = 2001, 8, 1080.0, 800.0
+    cuts = multi.partition_by_ray_load(n, world, centre, reach)
+    assert cuts[0][0] == 0 and cuts[-1][1] == n and all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+    assert all(hi - lo >= 8 for lo, hi in cuts)
+    x = np.arange(n) + 0.5
+    dens = np.where(np.abs(x - centre) < reach, np.log(reach / np.maximum(np.abs(x - centre), 0.5)), 0.0)
+    share = lambda c: np.array([dens[lo:hi].sum() for lo, hi in c]) / dens.sum()
+    uniform = [multi.partition(n, r, world) for r in range(world)]
+    assert share(cuts).max() < 0.2 < 0.3 < share(uniform).max()
+    assert multi.partition_by_ray_load(401, 1, 200.0, 80.0) == [(0, 401)]

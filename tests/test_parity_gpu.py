@@ -934,3 +934,63 @@ def test_fused_call_reference_steady_state_schedule(gpu, cpu):
     st = gpu.stats()
     assert st["graph_replays"] >= 20 and st["captures"] >= 2, st
 
+
+
+def test_cfg5_full_size_parity_one_gpu_and_two_slabs(oracle_mod):
+    """BASELINE.json configs[4] at FULL size: 0.25 m voxels over 500 x 500 x 100 m = 2001 x 2001 x 401 cells (1.6 G cells, `int` indices up
+    to 1.6e9, 6.4 GB per fp32 grid), 128 x 2048 rays, whole schedule S1, 3 scans — the unsharded library path AND two x-slabs (emulated as two
+    contexts on this device, exchange buffers combined on the host) against the monolithic oracle: result records, voxels, labels and
+    every cell of the score grid bit for bit.  Needs ~45 GB of host memory for the oracle's grids (skipped on smaller hosts) and a few minutes."""
+    import os
+    from vofod_b200 import capi, slab
+    avail_kb = 0
+    for line in open("/proc/meminfo"):
+        if line.startswith("MemAvailable:"):
+            avail_kb = int(line.split()[1])
+    if avail_kb < 100 * 1024 * 1024:
+        pytest.skip(f"host has {avail_kb >> 20} GB available; the full-size oracle + comparisons need ~100 GB")
+    sensor = Sensor(2048, 128)
+    p = params_for((500.0, 500.0, 100.0))
+    vs = 0.25
+    cpu = oracle_mod.Oracle(track_counts=True, apply_from_fixed=True)
+    one = capi.Vofod(0)
+    two = [capi.Vofod(0), capi.Vofod(0)]
+    try:
+        cpu.reset(p, vs)
+        cpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        one.reset(p, vs)
+        one.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        slab.make_slabs(two, p, vs, (sensor.W, sensor.H), sensor.dirs, halo=16)
+        sx, sy, sz = list(cpu.map_info().sizes)
+        assert (sx, sy, sz) == (2001, 2001, 401)
+        for k in (0, 1, 2):
+            scan, pose, rp, _ = sensor.scan(0, k, 2.5)
+            s = abi.schedule_s1(rp)
+            rg, _ = one.process_scan(scan, pose, p, s)
+            out = slab.run_emulated(two, scan, pose, p, s)
+            cpu.set_modes(True, True, one.raycast_frac_bits())
+            want, _ = cpu.process_scan(scan, pose, p, s)
+            wd = want.as_dict()
+            assert rg.as_dict() == wd, (k, rg.as_dict(), wd)
+            vc, lc, ic = cpu.last_voxels()
+            for g in [one] + two:
+                vg, lg, ig = g.last_voxels()
+                assert_vox_equal(vg, vc)
+                assert np.array_equal(lg, lc) and np.array_equal(ig, ic)
+            for (res, _) in out:
+                assert res.as_dict() == wd, (k, res.as_dict(), wd)
+            full = cpu.map_view().reshape(sz, sy, sx)
+            got = one.map_download().reshape(sz, sy, sx)
+            assert np.array_equal(got, full), k
+            del got
+            for g in two:
+                mi = g.map_info()
+                x0, nx = mi.storage_lo[0], mi.storage_size[0]
+                part = g.map_download().reshape(sz, sy, nx)
+                assert np.array_equal(part, full[:, :, x0:x0 + nx]), (k, x0)
+                del part
+    finally:
+        cpu.close()
+        one.close()
+        for g in two:
+            g.close()

@@ -72,12 +72,14 @@ def run_emulated(ctxs, scan, pose, params, sched, det_cap=256):
 class SlabWorker:
     """one slab of the map in this process; rank / world come from torch.distributed (NCCL or gloo: it only ships the NCCL id)"""
 
-    def __init__(self, ctx, params, voxel_size, sensor_wh, dirs, rank, world, halo=16, axis=0):
+    def __init__(self, ctx, params, voxel_size, sensor_wh, dirs, rank, world, halo=16, axis=0, cuts=None):
+        """cuts: None = equal-width slabs, or the [lo, hi) list of multi.partition_by_ray_load"""
         self.v, self.p, self.rank, self.world = ctx, params, rank, world
         W, H = sensor_wh
         ctx.reset(params, voxel_size)
         sizes = list(ctx.map_info().sizes)
-        lo, hi = multi.partition(sizes[axis], rank, world)
+        lo, hi = cuts[rank] if cuts is not None else multi.partition(sizes[axis], rank, world)
+        self.lo, self.hi = lo, hi
         ctx.set_slab(axis, lo, hi, halo)
         ctx.map_set_to(abi.MAP_SCORE, params.score_init)
         ctx.set_sensor(W, H, dirs)

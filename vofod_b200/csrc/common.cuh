@@ -345,6 +345,7 @@ struct vofod_ctx
   size_t slab_patch_words = 0;
   DevBuf slab_bg_send, slab_bg_recv;                    // packed background-voxel lists of the sepclusters pass: own / every slab's
   size_t slab_bg_cap = 0;                               // entries per slab (identical on every slab: it sizes the allgather)
+  size_t slab_bg_consume = 0;                           // rows the replicated rest of the pass is sized for (identical on every slab)
   int slab_next_phase = 0;
   int slab_nranks = 1, slab_rank = 0;
   bool slab_redo_sep = false;
@@ -589,4 +590,4 @@ void vf_slab_destroy(vofod_ctx* ctx);
 // sepclusters.cu
 int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap = 0, int slab_ranks = 0);
 int vf_sep_slab_pack(vofod_ctx* ctx, const vofod_params& p, size_t cap);
-int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks);
+int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks, size_t k_consume);

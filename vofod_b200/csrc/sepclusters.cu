@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(256) k_sep_slab_pack(const vofod_xyzi* __restr
     send[1 + i] = lin | (v.intensity > thr_sure ? 0x80000000u : 0u);
   }
 }
-__global__ void __launch_bounds__(256) k_sep_slab_unpack(const uint32_t* __restrict__ recv, const int nranks, const size_t cap, const Geom g, vofod_xyzi* __restrict__ raw,
-                                                         unsigned long long* __restrict__ counters)
+__global__ void __launch_bounds__(256) k_sep_slab_unpack(const uint32_t* __restrict__ recv, const int nranks, const size_t cap, const size_t k_consume, const Geom g,
+                                                         vofod_xyzi* __restrict__ raw, unsigned long long* __restrict__ counters)
 {
   pdl_enter();
   __shared__ unsigned long long s_off[65];
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(256) k_sep_slab_unpack(const uint32_t* __restr
       o += c < cap ? c : cap;
     }
     s_off[nranks] = o;
+    over |= o > k_consume;  // the rest of the pass is sized for k_consume rows (about twice the list of the previous scan), not for nranks * cap
     s_over = over;
     if (blockIdx.x == 0)
       // an overflowing slab: report a count above every capacity, the pass then leaves the map untouched (k_sep_decay) and the host redoes it
@@ -435,12 +436,12 @@ int vf_sep_slab_pack(vofod_ctx* ctx, const vofod_params& p, size_t cap)
 }
 int vf_sepclusters_dev(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t k_cap, int slab_ranks);
 // phase B: the gathered lists (ctx->slab_bg_recv, nranks x (cap + 1) words) -> the rest of the pass
-int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks)
+int vf_sep_slab_finish(vofod_ctx* ctx, int its_diff, const vofod_params& p, size_t cap, int nranks, size_t k_consume)
 {
   unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
-  const size_t K = cap * (size_t)nranks;
+  const size_t K = k_consume < cap * (size_t)nranks ? k_consume : cap * (size_t)nranks;
   ENSURE(ctx->sep_raw, prims::padded(K) * sizeof(vofod_xyzi));
-  LAUNCH(k_sep_slab_unpack, vf_blocks(ctx, K, 256, 8), 256, 0, ctx->slab_bg_recv.as<uint32_t>(), nranks, cap, ctx->g, ctx->sep_raw.as<vofod_xyzi>(), cnt);
+  LAUNCH(k_sep_slab_unpack, vf_blocks(ctx, K, 256, 8), 256, 0, ctx->slab_bg_recv.as<uint32_t>(), nranks, cap, K, ctx->g, ctx->sep_raw.as<vofod_xyzi>(), cnt);
   return vf_sepclusters_dev(ctx, its_diff, p, K, nranks);
 }
 

@@ -342,7 +342,7 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
   int sep_status = VOFOD_W_PAUSED;
   if (sep)
   {
-    sep_status = vf_sep_slab_finish(ctx, s.sep_its_diff, p, ctx->slab_bg_cap, ctx->slab_nranks);
+    sep_status = vf_sep_slab_finish(ctx, s.sep_its_diff, p, ctx->slab_bg_cap, ctx->slab_nranks, ctx->slab_bg_consume);
     if (sep_status < 0)
       return sep_status;
   }
@@ -362,11 +362,12 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
   {
     const unsigned long long K = hp[CNT_SEP_K];
     const size_t cap_all = ctx->slab_bg_cap * (size_t)ctx->slab_nranks;
-    if (K > cap_all)
+    if (K > cap_all || K > ctx->slab_bg_consume)
     {
-      // some slab's list did not fit: nothing was touched (k_sep_decay), every slab sees the same gathered counts and takes the same
-      // decision — grow and let the caller repeat phases 2 and 3
+      // some slab's list (or their sum) did not fit: nothing was touched (k_sep_decay), every slab sees the same gathered counts and
+      // takes the same decision — grow and let the caller repeat phases 2 and 3
       ctx->slab_bg_cap *= 4;
+      ctx->slab_bg_consume *= 4;
       ctx->slab_redo_sep = true;
       ctx->slab_next_phase = 2;
       return VOFOD_W_REDO;
@@ -375,8 +376,17 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
       return vf_fail(ctx, VOFOD_E_OVERFLOW, "sepclusters: voxel-grid index overflow");
     if (K == 0)
       sep_status = VOFOD_W_EMPTY;
-    if (K * 2 > ctx->slab_bg_cap)  // a single slab may come to hold most of the list: keep its capacity above the global count
-      ctx->slab_bg_cap = (size_t)K * 4;
+    // capacities follow the list (a single slab may come to hold most of it): both are functions of the GLOBAL count, which every slab
+    // reads from the same gathered buffer, so all slabs keep identical sizes — the allgather needs that
+    if (!ctx->sep_cap_forced && (K * 3 / 2 > ctx->slab_bg_cap || K * 8 < ctx->slab_bg_cap))
+      ctx->slab_bg_cap = (size_t)K * 2 + 4096;
+    if (!ctx->sep_cap_forced && (K * 3 / 2 > ctx->slab_bg_consume || K * 8 < ctx->slab_bg_consume))
+      ctx->slab_bg_consume = (size_t)K * 2 + 4096;
+    if (ctx->sep_cap_forced && K * 3 / 2 > ctx->slab_bg_cap)
+    {
+      ctx->slab_bg_cap = (size_t)K * 2 + 4096;
+      ctx->slab_bg_consume = ctx->slab_bg_cap;
+    }
     if ((size_t)K * 3 / 2 > ctx->sep_table_hint)
       ctx->sep_table_hint = (size_t)K * 4 + (size_t(1) << 18);
   }
@@ -459,7 +469,10 @@ static int slab_begin(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vo
   else if (ctx->slab_patch_words == 0)
     ctx->slab_patch_words = patch_budget_words(ctx, *p);
   if (ctx->slab_bg_cap == 0)
-    ctx->slab_bg_cap = ctx->sep_cap_forced ? ctx->sep_cap_forced : (size_t(1) << 20);
+  {
+    ctx->slab_bg_cap = ctx->sep_cap_forced ? ctx->sep_cap_forced : (size_t(1) << 16);
+    ctx->slab_bg_consume = ctx->slab_bg_cap;
+  }
   ctx->slab_redo_sep = false;
   return VOFOD_OK;
 }

@@ -153,6 +153,13 @@ typedef struct vofod_schedule {
    *   scan k + 1: do_raycast = 0, raycast_apply_pending = 1    (after this scan's point update: apply(raycast_its_diff) + flags.clear()) */
   int32_t raycast_defer_apply;
   int32_t raycast_apply_pending;
+  /* Software pipelining of the background thread (bgclusters_loop, :1280-1294, runs beside the scan thread in the reference): with
+   * sep_deferred = 1 the separated-background pass this scan asks for (do_sepclusters) is carried out at the START of the next
+   * vofod_process_scan[_resident] call — before that scan touches the map, so the order of all map operations is still schedule S1's —
+   * where it overlaps the next scan's map-independent front end (crop, voxel grid, clustering).  The sep_status / sure_background_sufficient
+   * fields of a result then describe the pass that ran in that call (the previous scan's).  Any other entry point that reads or writes
+   * the map, and vofod_flush, carry out a pending pass first. */
+  int32_t sep_deferred;
 } vofod_schedule;
 
 typedef struct vofod_scan_result {
@@ -299,6 +306,8 @@ int vofod_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_p
 /* announce the NEXT scan: its host->device copy runs on a copy stream next to the current scan's kernels; the following
  * vofod_process_scan with the same `scan` pointer consumes it.  Keep the host buffer (ideally pinned) untouched until then. */
 int vofod_prefetch_scan(vofod_ctx*, const vofod_pt* scan, size_t n);
+/* carries out a pending deferred separated-background pass (vofod_schedule::sep_deferred); no-op when there is none */
+int vofod_flush(vofod_ctx*);
 /* a sequence of scans from host buffers back to back (replay, benchmarks): the copy of scan k + 1 overlaps the kernels of scan k and the
  * host spends microseconds between two scans.  poses / scheds / results: one per scan; dets: det_cap records per scan (may be NULL). */
 int vofod_process_scan_batch(vofod_ctx*, const vofod_pt* const* scans, size_t n_scans, size_t n, const vofod_pose* poses,

@@ -994,3 +994,45 @@ def test_cfg5_full_size_parity_one_gpu_and_two_slabs(oracle_mod):
         one.close()
         for g in two:
             g.close()
+
+
+@pytest.mark.parametrize("flush_every_scan", [True, False])
+def test_deferred_sepclusters_pass_is_schedule_s1(gpu, cpu, flush_every_scan):
+    """vofod_schedule::sep_deferred: the separated-background pass of scan k runs at the start of call k + 1, beside that scan's
+    map-independent front end (replayed as one CUDA graph) — the order of all map operations is still S1's.  (a) with vofod_flush after
+    every scan the map equals the oracle's after every scan; (b) without, every per-scan output that does not name the pass itself
+    (voxels, labels, detections, counts) and the map after the final flush equal the oracle's."""
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    setup_pair(cpu, gpu, p, vs, sensor)
+    n_det, prev_sure = 0, 0
+    for k in range(36):
+        scan, pose, rp, _ = sensor.scan(1, k)
+        s = abi.schedule_s1(rp)
+        sd = abi.schedule_s1(rp)
+        sd.sep_deferred = 1
+        rg, dg = gpu.process_scan(scan, pose, p, sd)
+        cpu.set_modes(True, True, gpu.raycast_frac_bits() or 24)
+        rc, dc = cpu.process_scan(scan, pose, p, s)
+        a, b = rg.as_dict(), rc.as_dict()
+        # the pass that ran in this call is the previous scan's
+        assert a.pop("sure_background_sufficient") == prev_sure, k
+        prev_sure = b.pop("sure_background_sufficient")
+        a.pop("sep_status"), b.pop("sep_status")
+        assert a == b, (k, a, b)
+        vg, lg, ig = gpu.last_voxels()
+        vc, lc, ic = cpu.last_voxels()
+        assert_vox_equal(vg, vc)
+        assert np.array_equal(lg, lc) and np.array_equal(ig, ic)
+        assert len(dg) == len(dc) and np.array_equal(dg["id"], dc["id"]) and np.array_equal(dg["label"], dc["label"])
+        struct_close(dg, dc, ("position", "confidence"), rtol=1e-5, atol=1e-7)
+        n_det += len(dc)
+        if flush_every_scan:
+            gpu.flush()
+            assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True), k
+    assert np.array_equal(gpu.map_download(), cpu.map_download(), equal_nan=True)   # (map_download carries out a pending pass itself)
+    assert gpu.state_get()[:2] == cpu.state_get()[:2]
+    assert n_det > 0
+    if not flush_every_scan:
+        assert gpu.stats()["graph_replays"] >= 25

@@ -111,7 +111,8 @@ class Detection(C.Structure):
 class Schedule(C.Structure):
     _fields_ = [("n_range_seeds", C.c_int32), ("range_pt", C.c_float * 3), ("do_raycast", C.c_int32),
                 ("raycast_its_diff", C.c_int32), ("do_classify", C.c_int32), ("do_sepclusters", C.c_int32),
-                ("sep_its_diff", C.c_int32), ("raycast_defer_apply", C.c_int32), ("raycast_apply_pending", C.c_int32)]
+                ("sep_its_diff", C.c_int32), ("raycast_defer_apply", C.c_int32), ("raycast_apply_pending", C.c_int32),
+                ("sep_deferred", C.c_int32)]
 
 
 class ScanResult(C.Structure):

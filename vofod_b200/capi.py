@@ -149,6 +149,7 @@ def load_library():
         "vofod_last_voxels": (i32, [vp, vp, vp, vp, sz, P(sz)]),
         "vofod_last_clusters": (i32, [vp, vp, sz, P(sz)]),
         "vofod_set_slab": (i32, [vp, i32, i32, i32, i32]),
+        "vofod_flush": (i32, [vp]),
         "vofod_process_scan_batch": (i32, [vp, vp, sz, sz, vp, P(Params), vp, vp, vp, sz, vp, P(sz)]),
         "vofod_load_cloud": (i32, [C.c_char_p, vp, sz, P(sz)]),
         "vofod_apriori_map": (i32, [vp, vp, sz, P(Pose), vp, sz, P(sz)]),
@@ -475,6 +476,9 @@ class Vofod:
         if n.value:
             self._ck(self.lib.vofod_last_clusters(self.h, _p(out), n.value, C.byref(n)))
         return out
+
+    def flush(self):
+        self._ck(self.lib.vofod_flush(self.h))
 
     def process_scan_batch(self, scans, poses, params, scheds, det_cap=64):
         """scans: list of PT_DTYPE arrays (ideally views of pinned memory); -> (list of ScanResult, number of scans done)"""

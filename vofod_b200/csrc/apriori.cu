@@ -230,6 +230,7 @@ int vofod_apriori_map(vofod_ctx* ctx, const float* xyz, size_t n, const vofod_po
   CK(cudaSetDevice(ctx->device));
   if (!ctx->map_ready)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  FLUSH_PENDING();
   if (!tf || (n && !xyz) || (cap && !centroids))
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (n >= (size_t(1) << 31))

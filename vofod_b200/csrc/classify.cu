@@ -993,6 +993,7 @@ extern "C" int vofod_map_explore_to_ground(vofod_ctx* ctx, const float pt[3], fl
   CK(cudaSetDevice(ctx->device));
   if (!ctx->map_ready)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  FLUSH_PENDING();
   if (!pt || !connected || !n_explored || (cap && !explored_idx3))
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (!(max_voxel_dist >= 0.0f) || max_voxel_dist > 200.0f)
@@ -1038,6 +1039,7 @@ extern "C" int vofod_classify_detect(vofod_ctx* ctx, const vofod_vox* pts, const
   CK(cudaSetDevice(ctx->device));
   if (!ctx->map_ready)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  FLUSH_PENDING();
   if (!tf || !p || !n_dets || !n_far_clusters || (m && (!pts || !labels || !point_in_close_cluster)))
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   *n_dets = 0;

@@ -380,6 +380,12 @@ struct vofod_ctx
   static constexpr int N_GRAPH_SLOTS = 4;
   GraphSlot gslot[N_GRAPH_SLOTS];
   uint64_t gslot_clock = 0;
+  bool sep_pending = false;     // a separated-background pass deferred to the start of the next scan (vofod_schedule::sep_deferred)
+  int sep_pending_its = 1;
+  vofod_params sep_pending_p;
+  DevBuf tile_state_b, tile_state2_b;  // look-back states of the deferred pass, which runs next to the front end's own scans
+  cudaStream_t stream4 = nullptr;      // the next scan's front end beside the deferred pass
+  cudaEvent_t ev_fork4 = nullptr, ev_front = nullptr;
   bool ray_pending = false;     // an accumulate whose apply was deferred (vofod_schedule::raycast_defer_apply)
   Window ray_pending_win;
   uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;
@@ -474,7 +480,14 @@ enum
 int vf_fail(vofod_ctx* c, int code, const char* fmt, ...);
 int vf_ensure(vofod_ctx* c, DevBuf& b, size_t bytes);
 int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters = false);
-int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p);  // vofod_process_scan: vf_begin_call + rangefinder seeds (A23) + min/max reset of the filter, one kernel  // advances the look-back generation; first thing of every entry point that sorts / scans
+int vf_flush_pending(vofod_ctx* ctx);  // pipeline.cu: carries out a deferred separated-background pass, if any
+#define FLUSH_PENDING()          \
+  do                             \
+  {                              \
+    if (ctx->sep_pending)        \
+      RET(vf_flush_pending(ctx)); \
+  } while (0)
+int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p, bool seed_now = true);  // vofod_process_scan: vf_begin_call + rangefinder seeds (A23) + min/max reset of the filter, one kernel  // advances the look-back generation; first thing of every entry point that sorts / scans
 int vf_dyn_push(vofod_ctx* ctx);    // h_dyn -> device (stream ordered)
 // up to 4 word fills in ONE kernel launch (a stage's clears; unlike memset nodes they chain by programmatic dependent launch)
 struct FillJob

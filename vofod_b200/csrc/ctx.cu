@@ -94,6 +94,9 @@ int vofod_create(int device, vofod_ctx** out)
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork4, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
@@ -153,7 +156,7 @@ int vofod_destroy(vofod_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   vf_slab_destroy(ctx);
   DevBuf* bufs[] = {&ctx->slab_patch, &ctx->slab_patch_desc, &ctx->slab_patch_meta, &ctx->slab_bg_send, &ctx->slab_bg_recv, &ctx->score, &ctx->flags, &ctx->col_dirty, &ctx->upd_owner, &ctx->upd_leftover, &ctx->flagged, &ctx->acc, &ctx->lut_dir, &ctx->lut_off, &ctx->mask, &ctx->dyn, &ctx->scan_staging, &ctx->prefetch_buf[0], &ctx->prefetch_buf[1], &ctx->vg_pts, &ctx->vg_keys_a, &ctx->vg_keys_b, &ctx->vgh_cnt, &ctx->vgh_bits, &ctx->vgh_list, &ctx->cl_cellkey, &ctx->cl_words, &ctx->vg_flags, &ctx->vg_scan, &ctx->vg_ustart,
-                    &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
+                    &ctx->vg_ukey, &ctx->vg_pref, &ctx->vox, &ctx->d_counters, &ctx->tile_state, &ctx->tile_state2, &ctx->tile_state_b, &ctx->tile_state2_b, &ctx->sort_hist, &ctx->cl.pts, &ctx->cl.table_key,
                     &ctx->cl.table_head, &ctx->cl.next, &ctx->cl.parent, &ctx->cl.sizes, &ctx->cl.root, &ctx->cl.minidx, &ctx->cl.cellpts, &ctx->cl_bg.cellpts, &ctx->cl_bg.root, &ctx->cl_bg.minidx, &ctx->cl_bg.pts, &ctx->cl_bg.table_key, &ctx->cl_bg.table_head,
                     &ctx->cl_bg.next, &ctx->cl_bg.parent, &ctx->cl_bg.sizes, &ctx->labels, &ctx->pt_close, &ctx->cl_close, &ctx->far_list,
                     &ctx->cl_info, &ctx->dets, &ctx->explore_ws, &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_d,
@@ -189,6 +192,12 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaStreamDestroy(ctx->stream2);
   if (ctx->stream3)
     cudaStreamDestroy(ctx->stream3);
+  if (ctx->stream4)
+    cudaStreamDestroy(ctx->stream4);
+  if (ctx->ev_fork4)
+    cudaEventDestroy(ctx->ev_fork4);
+  if (ctx->ev_front)
+    cudaEventDestroy(ctx->ev_front);
   for (int i = 0; i < 2; i++)
     if (ctx->ev_prefetch[i])
       cudaEventDestroy(ctx->ev_prefetch[i]);
@@ -377,7 +386,8 @@ __global__ void k_begin_call(unsigned long long* __restrict__ counters, const in
   if (scan && threadIdx.x == 31)
   {
     minmax_init(mm);
-    range_update(score, g, dyn, score_point, col_dirty);
+    if (scan == 1)  // (2: a deferred separated-background pass comes first, the seeds follow it — k_range_update)
+      range_update(score, g, dyn, score_point, col_dirty);
   }
   if (threadIdx.x == 0)
     counters[CNT_EPOCH_BASE] += EPOCH_STRIDE;
@@ -391,10 +401,10 @@ __global__ void k_begin_call(unsigned long long* __restrict__ counters, const in
   }
 }
 
-static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params);
-int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters) { return begin_call(ctx, zero_scan_counters, nullptr); }
-int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p) { return begin_call(ctx, true, &p); }
-static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params)
+static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params, bool seed_now);
+int vf_begin_call(vofod_ctx* ctx, bool zero_scan_counters) { return begin_call(ctx, zero_scan_counters, nullptr, true); }
+int vf_begin_scan(vofod_ctx* ctx, const vofod_params& p, bool seed_now) { return begin_call(ctx, true, &p, seed_now); }
+static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_params* scan_params, bool seed_now)
 {
   // work done ahead of time by a previous call's side branch does not carry over (that call may have failed half way)
   ctx->nbg_precounted = false;
@@ -411,11 +421,15 @@ static int begin_call(vofod_ctx* ctx, bool zero_scan_counters, const vofod_param
     CK(cudaMemsetAsync(ctx->tile_state.p, 0, ctx->tile_state.cap, ctx->stream));
     if (ctx->tile_state2.p)
       CK(cudaMemsetAsync(ctx->tile_state2.p, 0, ctx->tile_state2.cap, ctx->stream));
+    if (ctx->tile_state_b.p)
+      CK(cudaMemsetAsync(ctx->tile_state_b.p, 0, ctx->tile_state_b.cap, ctx->stream));
+    if (ctx->tile_state2_b.p)
+      CK(cudaMemsetAsync(ctx->tile_state2_b.p, 0, ctx->tile_state2_b.cap, ctx->stream));
   }
   ctx->pdl_chain = false;  // whatever precedes an API call on the stream (the caller's own work included) completes first
   if (scan_params)
     ENSURE(ctx->scratch_d, 1024);  // MinMax + VgLayout of the filter (voxelgrid.cu)
-  LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0, scan_params ? 1 : 0, ctx->score.as<float>(), ctx->g,
+  LAUNCH(k_begin_call, 1, 32, 0, ctx->d_counters.as<unsigned long long>(), zero_scan_counters ? 1 : 0, scan_params ? (seed_now ? 1 : 2) : 0, ctx->score.as<float>(), ctx->g,
          ctx->dyn.as<ScanDyn>(), scan_params ? scan_params->score_point : 0.0, ctx->col_dirty.as<uint8_t>(), ctx->scratch_d.as<MinMax>());
   return 0;
 }
@@ -802,6 +816,7 @@ int vf_map_alloc(vofod_ctx* ctx)
   ctx->win_valid = false;
   ctx->acc_has_data = false;
   ctx->ray_pending = false;
+  ctx->sep_pending = false;
   ctx->map_ready = true;
   return 0;
 }
@@ -898,6 +913,7 @@ int vofod_map_info_get(const vofod_ctx* ctx, vofod_map_info* out)
 int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   const size_t n = (size_t)geom_cells(ctx->g);
   if (which == VOFOD_MAP_SCORE)
   {
@@ -917,7 +933,7 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
     if (ctx->win_valid)
       CK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc_total_bytes, ctx->stream));
     ctx->acc_has_data = false;
-  ctx->ray_pending = false;
+    ctx->ray_pending = false;
   } else
     return vf_fail(ctx, VOFOD_E_INVALID, "bad map id %d", which);
   return VOFOD_OK;
@@ -926,6 +942,7 @@ int vofod_map_set_to(vofod_ctx* ctx, int which, float value)
 int vofod_map_set_inf(vofod_ctx* ctx, const float* xyz, size_t n)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (n == 0)
     return VOFOD_OK;
   if (!xyz)
@@ -941,6 +958,7 @@ int vofod_map_set_inf(vofod_ctx* ctx, const float* xyz, size_t n)
 int vofod_map_download(vofod_ctx* ctx, int which, float* host, size_t n_cells)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   const size_t n = (size_t)geom_cells(ctx->g);
   if (!host || n_cells != n)
     return vf_fail(ctx, VOFOD_E_INVALID, "vofod_map_download: expected %zu cells", n);
@@ -965,6 +983,7 @@ int vofod_map_download(vofod_ctx* ctx, int which, float* host, size_t n_cells)
 int vofod_map_upload(vofod_ctx* ctx, int which, const float* host, size_t n_cells)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   const size_t n = (size_t)geom_cells(ctx->g);
   if (!host || n_cells != n)
     return vf_fail(ctx, VOFOD_E_INVALID, "vofod_map_upload: expected %zu cells", n);
@@ -988,6 +1007,7 @@ int vofod_map_upload(vofod_ctx* ctx, int which, const float* host, size_t n_cell
 int vofod_map_get(vofod_ctx* ctx, int which, int ix, int iy, int iz, float* value)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   const Geom& g = ctx->g;
   // std::vector::at semantics (voxel_map.cpp:82,117): out of range is an error, not UB
   if (!value || ix < 0 || iy < 0 || iz < 0 || ix >= g.size[0] || iy >= g.size[1] || iz >= g.size[2])
@@ -1014,6 +1034,7 @@ int vofod_map_get(vofod_ctx* ctx, int which, int ix, int iy, int iz, float* valu
 int vofod_map_set(vofod_ctx* ctx, int which, int ix, int iy, int iz, float value)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   const Geom& g = ctx->g;
   if (ix < 0 || iy < 0 || iz < 0 || ix >= g.size[0] || iy >= g.size[1] || iz >= g.size[2])
     return vf_fail(ctx, VOFOD_E_INVALID, "index [%d,%d,%d] out of range", ix, iy, iz);
@@ -1070,6 +1091,7 @@ extern "C" {
 int vofod_map_count_over(vofod_ctx* ctx, float threshold, uint64_t* out)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (!out)
     return vf_fail(ctx, VOFOD_E_INVALID, "out is NULL");
   RET(vf_count_over_dev(ctx, threshold, vf_cnt(ctx, CNT_NBG)));
@@ -1083,6 +1105,7 @@ int vofod_map_count_over(vofod_ctx* ctx, float threshold, uint64_t* out)
 int vofod_map_compact_over(vofod_ctx* ctx, float threshold, int greater_than, int metric, vofod_xyzi* out, size_t cap, size_t* n)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (!n)
     return vf_fail(ctx, VOFOD_E_INVALID, "n is NULL");
   size_t total = 0;
@@ -1100,6 +1123,7 @@ int vofod_map_compact_over(vofod_ctx* ctx, float threshold, int greater_than, in
 int vofod_map_has_close_to(vofod_ctx* ctx, const float* xyz, size_t n, float max_dist, float threshold, uint8_t* out)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (n == 0)
     return VOFOD_OK;
   if (!xyz || !out)
@@ -1117,6 +1141,7 @@ int vofod_map_has_close_to(vofod_ctx* ctx, const float* xyz, size_t n, float max
 int vofod_map_is_floating(vofod_ctx* ctx, const float* xyz, size_t n, float threshold, uint8_t* out)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (n == 0)
     return VOFOD_OK;
   if (!xyz || !out)
@@ -1156,6 +1181,7 @@ int vofod_map_trace_ray(vofod_ctx* ctx, const float start[3], const float dir[3]
 int vofod_map_submap_copy(vofod_ctx* ctx, const float min_pt[3], const float max_pt[3], int inflate, float* out, size_t cap, int32_t sizes_out[3], float offset_out[3])
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (!min_pt || !max_pt || !sizes_out || !offset_out)
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL buffer");
   const Geom& g = ctx->g;

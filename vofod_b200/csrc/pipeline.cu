@@ -523,6 +523,8 @@ int vofod_state_set(vofod_ctx* ctx, int bg, int sure, uint32_t id)
 int vofod_range_update(vofod_ctx* ctx, const float world_pt[3], const vofod_params* p)
 {
   NEED_MAP();
+  FLUSH_PENDING();
+  FLUSH_PENDING();
   if (!world_pt || !p)
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   for (int a = 0; a < 3; a++)
@@ -537,6 +539,7 @@ int vofod_range_update(vofod_ctx* ctx, const float world_pt[3], const vofod_para
 int vofod_update_points(vofod_ctx* ctx, const vofod_vox* pts, const uint8_t* sel, int sel_value, size_t n, float score, float flag)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (n == 0)
     return VOFOD_OK;
   if (!pts)
@@ -558,6 +561,7 @@ int vofod_update_points(vofod_ctx* ctx, const vofod_vox* pts, const uint8_t* sel
 int vofod_close_far(vofod_ctx* ctx, const vofod_vox* pts, const int32_t* labels, size_t m, const vofod_params* p, uint8_t* point_in_close_cluster, uint64_t* n_bg)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (!p || (m && (!pts || !labels || !point_in_close_cluster)))
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   for (size_t i = 0; i < m; i++)
@@ -609,6 +613,9 @@ struct ScanPlan
   bool apply_on;       // an accumulate is applied in this call: this scan's (unless deferred) or a pending one
   bool apply_first;    // the pending one: before this scan's own accumulate may touch the accumulator
   int raycast_status;  // VOFOD_OK / W_PAUSED / W_SENSOR_OOB as known on the host before launching
+  bool sep_first;      // a separated-background pass deferred by the previous call runs at the start of this one
+  int sep_first_its;
+  vofod_params sep_first_p;
   size_t sep_cap;      // 0 = exact sepclusters (host round trip inside), else capped list
   bool timed;          // record the per-stage events
 };
@@ -637,7 +644,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     ~Prezero() { c->scan_prezero = false; }
   } prezero_guard(ctx);
   RET(vf_dyn_push(ctx));
-  RET(vf_begin_scan(ctx, p));  // + rangefinder seeds (A23) + the filter's min/max reset
+  RET(vf_begin_scan(ctx, p, !plan.sep_first));  // + rangefinder seeds (A23; after a deferred pass when there is one) + the filter's min/max reset
   // The raycast accumulate reads only the scan, the LUT and the per-scan arguments and writes only the accumulator window:
   // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
   // parallel branch of the graph (issue-bound kernel next to a chain of latency-bound ones); with per-stage timing on it
@@ -658,13 +665,14 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
       rrc = vf_classify_prefill(ctx, n);
     if (rrc >= 0 && s.do_sepclusters)
       rrc = vf_sepclusters_prefill(ctx, p);
-    // nVoxelsOver of :712 only needs the map as the previous scan (and this scan's rangefinder seed) left it
-    if (rrc >= 0)
+    // nVoxelsOver of :712 only needs the map as the previous scan (and this scan's rangefinder seed) left it — with a deferred
+    // separated-background pass still to come it has to wait for that (it then rides in the hasCloseTo kernel)
+    if (rrc >= 0 && !plan.sep_first)
       rrc = vf_count_bg_dev(ctx, p);
     ctx->stream = st;
     if (rrc < 0)
       return rrc;
-    ctx->nbg_precounted = true;
+    ctx->nbg_precounted = !plan.sep_first;
     CK(cudaEventRecord(ctx->ev_fills, ctx->stream2));
     if (overlap_raycast)
     {
@@ -677,11 +685,39 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
   STAGE_EVENT();
+  // The previous scan's separated-background pass (vofod_schedule::sep_deferred): it must precede everything of this scan that touches
+  // the map (first of all the rangefinder seeds), but this scan's front end — crop, voxel grid, clustering — never looks at the map:
+  // in replay mode the front end runs on a branch of its own beside the pass.
+  *sep_status_out = VOFOD_W_PAUSED;
+  const bool front_side = plan.sep_first && side && ctx->stream4 != nullptr && !ctx->vg_force_sort && !ctx->cl_force_hash;
+  if (front_side)
+  {
+    CK(cudaEventRecord(ctx->ev_fork4, st));
+    CK(cudaStreamWaitEvent(ctx->stream4, ctx->ev_fork4, 0));
+    CK(cudaStreamWaitEvent(ctx->stream4, ctx->ev_fills, 0));
+  }
+  if (plan.sep_first)
+  {
+    std::swap(ctx->tile_state, ctx->tile_state_b);
+    std::swap(ctx->tile_state2, ctx->tile_state2_b);
+    const int src = vf_sepclusters_dev(ctx, plan.sep_first_its, plan.sep_first_p, plan.sep_cap);
+    std::swap(ctx->tile_state, ctx->tile_state_b);
+    std::swap(ctx->tile_state2, ctx->tile_state2_b);
+    if (src < 0)
+      return src;
+    *sep_status_out = src;
+    RET(vf_range_update_dev(ctx, p));  // this scan's rangefinder seeds (A23)
+  }
   STAGE_EVENT();  // 0 "range": the rangefinder seeds (A23) ride in the scan's first kernel (vf_begin_scan)
   // filterAndTransform (:928)
+  if (front_side)
+    ctx->stream = ctx->stream4;
   const int seeded = vf_filter_voxelize_dev(ctx, n, p, true);
   if (seeded < 0)
+  {
+    ctx->stream = st;
     return seeded;
+  }
   STAGE_EVENT();  // 1 "filtering"
   // hasCloseTo of the voxels does not look at their labels: second side branch, next to the clustering
   const bool cp_side = side && ctx->stream3 != nullptr && ctx->nbg_precounted;
@@ -697,7 +733,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     CK(cudaEventRecord(ctx->ev_cp, ctx->stream3));
   }
   // clusterCloud (:932)
-  if (side)
+  if (side && !front_side)
     CK(cudaStreamWaitEvent(st, ctx->ev_fills, 0));
   ENSURE(ctx->labels, n * 4);
   if (seeded)
@@ -711,6 +747,13 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   } else
     RET(vf_cluster_dev(ctx, ctx->cl, reinterpret_cast<const float*>(ctx->vox.p), 4, cnt + CNT_VG_M, n, (float)p.ground_points_max_distance, ctx->labels.as<int>(),
                        cnt + CNT_NCLUSTERS));
+  if (front_side)
+  {
+    ctx->stream = st;
+    CK(cudaEventRecord(ctx->ev_front, ctx->stream4));
+    CK(cudaStreamWaitEvent(st, ctx->ev_front, 0));
+    CK(cudaStreamWaitEvent(st, ctx->ev_fills, 0));
+  }
   STAGE_EVENT();  // 2 "clusterization"
   // findCloseFarClusters (:936)
   if (cp_side)
@@ -778,9 +821,9 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     RET(vf_classify_detect_dev(ctx, ctx->vox.as<vofod_vox>(), ctx->labels.as<int>(), ctx->pt_close.as<uint8_t>(), cnt + CNT_VG_M, n, p));
   STAGE_EVENT();  // 7 "classification" (+ 8 detections, fused)
   STAGE_EVENT();
-  *sep_status_out = VOFOD_W_PAUSED;
-  ZERO_CNT(CNT_SEP_K, 1);
-  if (s.do_sepclusters)
+  if (!plan.sep_first)
+    ZERO_CNT(CNT_SEP_K, 1);
+  if (s.do_sepclusters && !s.sep_deferred)
   {
     const int rc = vf_sepclusters_dev(ctx, s.sep_its_diff, p, plan.sep_cap);
     if (rc < 0)
@@ -814,10 +857,19 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   cudaStream_t st = ctx->stream;
+  // a pending deferred pass runs at the start of this call, beside the front end — unless this scan wants a pass of its own right away
+  if (ctx->sep_pending && s.do_sepclusters && !s.sep_deferred)
+    RET(vf_flush_pending(ctx));
   ScanPlan plan = {};
   plan.n = n;
   plan.p = p;
   plan.s = s;
+  plan.sep_first = ctx->sep_pending;
+  plan.sep_first_its = ctx->sep_pending_its;
+  if (plan.sep_first)
+    plan.sep_first_p = ctx->sep_pending_p;
+  const bool sep_inline = s.do_sepclusters && !s.sep_deferred && !p.sep_pause;
+  const bool sep_ran = plan.sep_first || sep_inline;
   plan.raycast_status = VOFOD_W_PAUSED;
   plan.raycast_on = false;
   plan.apply_first = s.raycast_apply_pending && ctx->ray_pending && !p.raycast_pause;
@@ -860,13 +912,17 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   sig = fnv1a(&ctx->alloc_gen, sizeof(uint64_t), sig);
   const int dirty_mode = ctx->col_all_dirty ? 1 : 0;
   sig = fnv1a(&dirty_mode, sizeof(int), sig);
+  const int sepf[3] = {plan.sep_first ? 1 : 0, plan.sep_first ? plan.sep_first_its : 0, s.sep_deferred};
+  sig = fnv1a(sepf, sizeof(sepf), sig);
+  if (plan.sep_first)
+    sig = fnv1a(&plan.sep_first_p, sizeof(vofod_params), sig);
   sig = fnv1a(&ctx->untouched_max, sizeof(float), sig);
 
   int sep_status = VOFOD_W_PAUSED;
   bool applied = false;
   bool used_graph = false;
   const bool epoch_wrap_soon = (((ctx->epoch_calls + 1) * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE;
-  const bool graph_ok = ctx->graph_enabled && !epoch_wrap_soon && (!s.do_sepclusters || p.sep_pause || ctx->sep_cap > 0);
+  const bool graph_ok = ctx->graph_enabled && !epoch_wrap_soon && (!sep_ran || ctx->sep_cap > 0);
   CK(cudaEventRecord(ctx->ev[0], st));
   // what the accumulator holds after this scan
   const bool acc_after = plan.apply_on ? !p.raycast_new_update_rule
@@ -889,7 +945,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     hit->last_use = ++ctx->gslot_clock;
     CK(cudaGraphLaunch(hit->exec, st));
     ctx->n_launches += hit->kernels;
-    sep_status = (s.do_sepclusters && !p.sep_pause) ? VOFOD_OK : VOFOD_W_PAUSED;
+    sep_status = sep_ran ? VOFOD_OK : VOFOD_W_PAUSED;
     applied = plan.apply_on;
     ctx->acc_has_data = acc_after;
     used_graph = true;
@@ -1007,11 +1063,26 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
       raycast_status = VOFOD_W_EMPTY_RAYCAST;
   }
   bool sure_flag = hp[CNT_STATE_SURE] != 0;
-  if (s.do_sepclusters && !p.sep_pause)
+  // the pass this scan asked for waits for the next call (or vofod_flush)
+  ctx->sep_pending = s.do_sepclusters && s.sep_deferred && !p.sep_pause;
+  if (ctx->sep_pending)
+  {
+    ctx->sep_pending_its = s.sep_its_diff;
+    ctx->sep_pending_p = p;
+  }
+  if (sep_ran)
   {
     const size_t K = (size_t)hp[CNT_SEP_K];
     if (plan.sep_cap > 0)
     {
+      if (K > plan.sep_cap && plan.sep_first)
+      {
+        // the deferred pass ran with a list that was too short and left the map untouched — but this scan has been applied on top of
+        // that already, so the exact redo the in-line pass gets is no longer possible: grow the list and tell the caller
+        ctx->sep_cap = K * 4 + (size_t(1) << 20);
+        return vf_fail(ctx, VOFOD_E_CAPACITY, "the deferred separated-background pass found %zu background voxels, its list held %zu: the pass was skipped "
+                                              "(the map now differs from schedule S1); the list has been grown", K, plan.sep_cap);
+      }
       if (K > plan.sep_cap)
       {
         // the capped list overflowed: the pass did not touch the map; redo it exactly, and grow the list for the next scans
@@ -1145,6 +1216,35 @@ int vofod_process_scan_resident(vofod_ctx* ctx, int slot, const vofod_pose* tf, 
   if (!tf || !p || !s || slot < 0 || slot >= VOFOD_SCAN_SLOTS || !ctx->scan_slot_n[slot])
     return vf_fail(ctx, VOFOD_E_INVALID, "bad argument / empty scan slot");
   return process_scan_dev(ctx, ctx->scan_slot[slot].as<vofod_pt>(), ctx->scan_slot_n[slot], *tf, *p, *s, res, dets, det_cap);
+}
+
+}  // extern "C"
+// a deferred separated-background pass, carried out in line (exact list, one host round trip inside)
+int vf_flush_pending(vofod_ctx* ctx)
+{
+  if (!ctx->sep_pending)
+    return 0;
+  ctx->sep_pending = false;
+  RET(vf_begin_call(ctx));
+  const int rc = vf_sepclusters_dev(ctx, ctx->sep_pending_its, ctx->sep_pending_p, 0);
+  if (rc < 0)
+    return rc;
+  unsigned long long h[CNT_N_SLOTS];
+  CK(cudaMemcpyAsync(h, ctx->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h[CNT_WATCHDOG])
+    return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", h[CNT_WATCHDOG]);
+  if (h[CNT_SEP_NUNIQ])
+    return vf_fail(ctx, VOFOD_E_OVERFLOW, "sepclusters: voxel-grid index overflow");
+  ctx->sure_background_sufficient = h[CNT_STATE_SURE] != 0;
+  return 0;
+}
+extern "C" {
+int vofod_flush(vofod_ctx* ctx)
+{
+  NEED_MAP();
+  RET(vf_flush_pending(ctx));
+  return VOFOD_OK;
 }
 
 /* A sequence of scans from host buffers, back to back (rosbag replay, benchmarks): scan k + 1's host->device copy is announced before scan

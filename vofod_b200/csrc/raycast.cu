@@ -897,6 +897,7 @@ int vofod_raycast_apply(vofod_ctx* ctx, int its_diff, const vofod_params* p)
   CK(cudaSetDevice(ctx->device));
   if (!ctx->map_ready)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  FLUSH_PENDING();
   if (!p || its_diff < 1)
     return vf_fail(ctx, VOFOD_E_INVALID, "bad argument (its_diff must be >= 1)");
   ctx->h_dyn->its_raycast = its_diff;

@@ -559,6 +559,7 @@ extern "C" int vofod_sepclusters(vofod_ctx* ctx, int its_diff, const vofod_param
   CK(cudaSetDevice(ctx->device));
   if (!ctx->map_ready)
     return vf_fail(ctx, VOFOD_E_STATE, "voxel map not sized");
+  FLUSH_PENDING();
   if (!p)
     return vf_fail(ctx, VOFOD_E_INVALID, "params is NULL");
   RET(vf_begin_call(ctx));

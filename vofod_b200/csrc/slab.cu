@@ -486,6 +486,7 @@ int vofod_slab_phase(vofod_ctx* ctx, int phase, const vofod_pt* scan, int scan_o
                      vofod_scan_result* res, vofod_detection* dets, size_t det_cap)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (phase < 0 || phase > 3)
     return vf_fail(ctx, VOFOD_E_INVALID, "vofod_slab_phase: phase %d", phase);
   if (phase == 0)
@@ -547,6 +548,7 @@ int vofod_slab_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, cons
                             vofod_detection* dets, size_t det_cap)
 {
   NEED_MAP();
+  FLUSH_PENDING();
   if (!tf || !p || !s || (ctx->slab_rank == 0 && !scan))
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   NcclApi* nc = ctx->slab_nranks > 1 ? nccl_api() : nullptr;

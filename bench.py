@@ -46,11 +46,12 @@ def make_params():
 
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None"""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_raycast_summary.json")
-    try:
-        return int(json.load(open(path))["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_ncu_raycast_summary.json", "r01_ncu_raycast_summary.json"):
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", name)))["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def peaks():

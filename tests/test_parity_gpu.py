@@ -1036,3 +1036,39 @@ def test_deferred_sepclusters_pass_is_schedule_s1(gpu, cpu, flush_every_scan):
     assert n_det > 0
     if not flush_every_scan:
         assert gpu.stats()["graph_replays"] >= 25
+
+
+def test_pipelined_batch_equals_scan_by_scan(gpu):
+    """vofod_process_scan_batch keeps two scans in flight (scan k + 1 is launched before the results of scan k are read): same result
+    records, same detections, same final map as one vofod_process_scan call per scan — with the deferred separated-background pass on, as
+    the bench runs it, and with the pass in line."""
+    from vofod_b200 import capi
+    sensor = Sensor(512, 32)
+    p, vs = small_params()
+    p.background_sufficient_points_ratio = 0.02
+    n_scans = 40
+    scans, poses, scheds = [], [], []
+    for k in range(n_scans):
+        scan, pose, rp, _ = sensor.scan(1, k)
+        scans.append(scan.copy())
+        poses.append(pose)
+        scheds.append(abi.schedule_s1(rp))
+    for deferred in (1, 0):
+        for s in scheds:
+            s.sep_deferred = deferred
+        ref = capi.Vofod(0)
+        try:
+            for g in (gpu, ref):
+                g.reset(p, vs)
+                g.set_sensor(sensor.W, sensor.H, sensor.dirs)
+            want = [ref.process_scan(scans[k], poses[k], p, scheds[k]) for k in range(n_scans)]
+            res, done = gpu.process_scan_batch(scans, poses, p, scheds, det_cap=16)
+            assert done == n_scans
+            for k in range(n_scans):
+                assert res[k].as_dict() == want[k][0].as_dict(), (deferred, k, res[k].as_dict(), want[k][0].as_dict())
+            assert sum(r.n_detections for r in res) > 0
+            assert np.array_equal(gpu.map_download(), ref.map_download(), equal_nan=True)
+            assert np.array_equal(gpu.map_download(abi.MAP_FLAGS), ref.map_download(abi.MAP_FLAGS))
+            assert gpu.stats()["graph_replays"] > 20
+        finally:
+            ref.close()

@@ -241,6 +241,30 @@ struct ClusterWs
   DevBuf minidx;     // i32 per point (min member index, valid at roots)
 };
 
+// ---- one scan of vofod_process_scan, as planned on the host (pipeline.cu) -------------------------------------------------------------
+struct ScanPlan
+{
+  size_t n;
+  vofod_params p;
+  vofod_schedule s;
+  bool raycast_on;     // do_raycast && not paused && sensor inside the map: this scan's rays are accumulated
+  bool apply_on;       // an accumulate is applied in this call: this scan's (unless deferred) or a pending one
+  bool apply_first;    // the pending one: before this scan's own accumulate may touch the accumulator
+  int raycast_status;  // VOFOD_OK / W_PAUSED / W_SENSOR_OOB as known on the host before launching
+  bool sep_first;      // a separated-background pass deferred by the previous call runs at the start of this one
+  int sep_first_its;
+  vofod_params sep_first_p;
+  size_t sep_cap;      // 0 = exact sepclusters (host round trip inside), else capped list
+  bool timed;          // record the per-stage events
+};
+// a scan whose device work has been enqueued and whose results have not been read yet
+struct ScanInFlight
+{
+  ScanPlan plan;
+  int sep_status = 0;
+  bool applied = false, used_graph = false, sep_ran = false, pipelined = false, active = false;
+};
+
 #define MAX_TILE_STATES (1 << 15)
 #define VOFOD_SCAN_SLOTS 256
 
@@ -386,6 +410,8 @@ struct vofod_ctx
   DevBuf tile_state_b, tile_state2_b;  // look-back states of the deferred pass, which runs next to the front end's own scans
   cudaStream_t stream4 = nullptr;      // the next scan's front end beside the deferred pass
   cudaEvent_t ev_fork4 = nullptr, ev_front = nullptr;
+  ScanInFlight fl[2];           // vofod_process_scan_batch keeps two scans in flight; a single call uses slot 0
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
   bool ray_pending = false;     // an accumulate whose apply was deferred (vofod_schedule::raycast_defer_apply)
   Window ray_pending_win;
   uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;

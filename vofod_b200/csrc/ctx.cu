@@ -97,6 +97,8 @@ int vofod_create(int device, vofod_ctx** out)
   cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_fork4, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
@@ -198,6 +200,9 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaEventDestroy(ctx->ev_fork4);
   if (ctx->ev_front)
     cudaEventDestroy(ctx->ev_front);
+  for (int i = 0; i < 2; i++)
+    if (ctx->ev_done[i])
+      cudaEventDestroy(ctx->ev_done[i]);
   for (int i = 0; i < 2; i++)
     if (ctx->ev_prefetch[i])
       cudaEventDestroy(ctx->ev_prefetch[i]);

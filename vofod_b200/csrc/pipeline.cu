@@ -604,21 +604,6 @@ int vofod_upload_scan(vofod_ctx* ctx, int slot, const vofod_pt* scan, size_t n)
 // ======================================================================================================
 // vofod_process_scan: one scan of schedule S1
 // ======================================================================================================
-struct ScanPlan
-{
-  size_t n;
-  vofod_params p;
-  vofod_schedule s;
-  bool raycast_on;     // do_raycast && not paused && sensor inside the map: this scan's rays are accumulated
-  bool apply_on;       // an accumulate is applied in this call: this scan's (unless deferred) or a pending one
-  bool apply_first;    // the pending one: before this scan's own accumulate may touch the accumulator
-  int raycast_status;  // VOFOD_OK / W_PAUSED / W_SENSOR_OOB as known on the host before launching
-  bool sep_first;      // a separated-background pass deferred by the previous call runs at the start of this one
-  int sep_first_its;
-  vofod_params sep_first_p;
-  size_t sep_cap;      // 0 = exact sepclusters (host round trip inside), else capped list
-  bool timed;          // record the per-stage events
-};
 
 // Enqueues every device operation of one scan on ctx->stream.  Called directly (eager mode) or under stream capture
 // (graph mode): it must not synchronise, allocate or touch pageable host memory when plan.sep_cap != 0.
@@ -643,7 +628,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     explicit Prezero(vofod_ctx* c_) : c(c_) { c->scan_prezero = true; }
     ~Prezero() { c->scan_prezero = false; }
   } prezero_guard(ctx);
-  RET(vf_dyn_push(ctx));
+  // (the ScanDyn upload and the read-back of the counters are enqueued by the caller, outside a captured graph: their host addresses
+  //  belong to the pinned slot of the scan, and a graph would bake them in)
   RET(vf_begin_scan(ctx, p, !plan.sep_first));  // + rangefinder seeds (A23; after a deferred pass when there is one) + the filter's min/max reset
   // The raycast accumulate reads only the scan, the LUT and the per-scan arguments and writes only the accumulator window:
   // it is independent of the whole filter -> cluster -> close/far -> point-update chain.  In replay mode it runs as a
@@ -831,9 +817,7 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     *sep_status_out = rc;
   }
   STAGE_EVENT();  // 9 "sep bg clusters"
-  // one read-back of every count into pinned memory (detection records follow on demand: most scans have none)
-  CK(cudaMemcpyAsync(ctx->pinned, cnt, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, st));
-  STAGE_EVENT();  // 10 "readback"
+  STAGE_EVENT();  // 10 "readback" (enqueued by the caller right behind this sequence)
 #undef STAGE_EVENT
   return 0;
 }
@@ -849,14 +833,24 @@ static uint64_t fnv1a(const void* data, size_t len, uint64_t h)
   return h;
 }
 
-static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p, const vofod_schedule& s, vofod_scan_result* res,
-                            vofod_detection* dets, size_t det_cap)
+// pinned slot `slot` of the context: 64 result counters (+ spare), the ScanDyn source, the first PIPE_DETS detection records
+#define PIPE_DETS 32
+static inline unsigned long long* slot_counters(vofod_ctx* ctx, int slot) { return (unsigned long long*)((char*)ctx->pinned + slot * 2048); }
+static inline ScanDyn* slot_dyn(vofod_ctx* ctx, int slot) { return reinterpret_cast<ScanDyn*>((char*)ctx->pinned + 65536 + slot * 1024); }
+static inline vofod_detection* slot_dets(vofod_ctx* ctx, int slot) { return reinterpret_cast<vofod_detection*>((char*)ctx->pinned + 131072 + slot * 16384); }
+
+// A scan = scan_launch (everything the host enqueues: no wait) + scan_finish (wait for it, read the results, host-side bookkeeping).
+// vofod_process_scan runs them back to back; vofod_process_scan_batch keeps two scans in flight.
+static int scan_launch(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p, const vofod_schedule& s, const int slot,
+                       const bool pipelined)
 {
-  if (res)
-    memset(res, 0, sizeof(*res));
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
   cudaStream_t st = ctx->stream;
+  ctx->h_dyn = slot_dyn(ctx, slot);
+  ScanInFlight& fl = ctx->fl[slot];
+  fl = ScanInFlight();
+  fl.pipelined = pipelined;
   // a pending deferred pass runs at the start of this call, beside the front end — unless this scan wants a pass of its own right away
   if (ctx->sep_pending && s.do_sepclusters && !s.sep_deferred)
     RET(vf_flush_pending(ctx));
@@ -923,6 +917,7 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   bool used_graph = false;
   const bool epoch_wrap_soon = (((ctx->epoch_calls + 1) * EPOCH_STRIDE) & 0x3fffffffull) < EPOCH_STRIDE;
   const bool graph_ok = ctx->graph_enabled && !epoch_wrap_soon && (!sep_ran || ctx->sep_cap > 0);
+  RET(vf_dyn_push(ctx));
   CK(cudaEventRecord(ctx->ev[0], st));
   // what the accumulator holds after this scan
   const bool acc_after = plan.apply_on ? !p.raycast_new_update_rule
@@ -1039,15 +1034,54 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   } else if (plan.apply_first)
     ctx->ray_pending = false;
   ctx->detection_its++;
+  // one read-back of every count into the scan's pinned slot (detection records follow on demand: most scans have none — a pipelined
+  // scan takes the first PIPE_DETS along, because the next scan's classification reuses the device array)
+  CK(cudaMemcpyAsync(slot_counters(ctx, slot), ctx->d_counters.p, CNT_N_SLOTS * 8, cudaMemcpyDeviceToHost, st));
+  if (pipelined && s.do_classify && ctx->dets.p)
+    CK(cudaMemcpyAsync(slot_dets(ctx, slot), ctx->dets.p, PIPE_DETS * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->ev[11], st));
-  CK(cudaStreamSynchronize(st));
-  memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
-  if (!used_graph)
-    for (int i = 0; i < 11; i++)
-      cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-  cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[11]);
+  CK(cudaEventRecord(ctx->ev_done[slot], st));
+  // the pass this scan asked for waits for the next call (or vofod_flush)
+  ctx->sep_pending = s.do_sepclusters && s.sep_deferred && !p.sep_pause;
+  if (ctx->sep_pending)
+  {
+    ctx->sep_pending_its = s.sep_its_diff;
+    ctx->sep_pending_p = p;
+  }
+  fl.plan = plan;
+  fl.sep_status = sep_status;
+  fl.applied = applied;
+  fl.used_graph = used_graph;
+  fl.sep_ran = sep_ran;
+  fl.active = true;
+  return VOFOD_OK;
+}
 
-  const unsigned long long* hp = (const unsigned long long*)ctx->pinned;
+static int scan_finish(vofod_ctx* ctx, const int slot, vofod_scan_result* res, vofod_detection* dets, size_t det_cap)
+{
+  ScanInFlight& fl = ctx->fl[slot];
+  if (res)
+    memset(res, 0, sizeof(*res));
+  if (!fl.active)
+    return vf_fail(ctx, VOFOD_E_STATE, "no scan in flight in slot %d", slot);
+  fl.active = false;
+  cudaStream_t st = ctx->stream;
+  const ScanPlan& plan = fl.plan;
+  const vofod_params& p = plan.p;
+  const vofod_schedule& s = plan.s;
+  int sep_status = fl.sep_status;
+  const bool applied = fl.applied, used_graph = fl.used_graph, sep_ran = fl.sep_ran;
+  CK(cudaEventSynchronize(ctx->ev_done[slot]));
+  if (!fl.pipelined)
+  {
+    memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
+    if (!used_graph)
+      for (int i = 0; i < 11; i++)
+        cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&ctx->stage_ms[11], ctx->ev[0], ctx->ev[11]);
+  }
+
+  const unsigned long long* hp = slot_counters(ctx, slot);
   if (hp[CNT_WATCHDOG])
     return vf_fail(ctx, VOFOD_E_INTERNAL, "device watchdog tripped (%llu)", hp[CNT_WATCHDOG]);
   if (hp[CNT_OOB])
@@ -1063,13 +1097,6 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
       raycast_status = VOFOD_W_EMPTY_RAYCAST;
   }
   bool sure_flag = hp[CNT_STATE_SURE] != 0;
-  // the pass this scan asked for waits for the next call (or vofod_flush)
-  ctx->sep_pending = s.do_sepclusters && s.sep_deferred && !p.sep_pause;
-  if (ctx->sep_pending)
-  {
-    ctx->sep_pending_its = s.sep_its_diff;
-    ctx->sep_pending_p = p;
-  }
   if (sep_ran)
   {
     const size_t K = (size_t)hp[CNT_SEP_K];
@@ -1082,6 +1109,12 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
         ctx->sep_cap = K * 4 + (size_t(1) << 20);
         return vf_fail(ctx, VOFOD_E_CAPACITY, "the deferred separated-background pass found %zu background voxels, its list held %zu: the pass was skipped "
                                               "(the map now differs from schedule S1); the list has been grown", K, plan.sep_cap);
+      }
+      if (K > plan.sep_cap && fl.pipelined)
+      {
+        ctx->sep_cap = K * 4 + (size_t(1) << 20);
+        return vf_fail(ctx, VOFOD_E_CAPACITY, "pipelined scan: the separated-background pass found %zu background voxels, its list held %zu, and the next scan is "
+                                              "in flight already: the pass was skipped (the map now differs from schedule S1); the list has been grown", K, plan.sep_cap);
       }
       if (K > plan.sep_cap)
       {
@@ -1131,7 +1164,15 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
     res->raycast_status = raycast_status;
     res->sep_status = sep_status;
   }
-  if (n_det && dets)
+  if (n_det && dets && fl.pipelined)
+  {
+    size_t k = n_det < det_cap ? n_det : det_cap;
+    if (k > PIPE_DETS)
+      k = PIPE_DETS;
+    memcpy(dets, slot_dets(ctx, slot), k * sizeof(vofod_detection));
+    if (n_det > PIPE_DETS && det_cap > PIPE_DETS)
+      return vf_fail(ctx, VOFOD_E_CAPACITY, "pipelined scan: %zu detections, only the first %d are kept (use vofod_process_scan for more)", n_det, PIPE_DETS);
+  } else if (n_det && dets)
   {
     const size_t k = n_det < det_cap ? n_det : det_cap;
     CK(cudaMemcpyAsync(dets, ctx->dets.p, k * sizeof(vofod_detection), cudaMemcpyDeviceToHost, st));
@@ -1140,6 +1181,15 @@ static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, co
   if (n_det > det_cap && dets)
     return vf_fail(ctx, VOFOD_E_CAPACITY, "process_scan: %zu detections, capacity %zu", n_det, det_cap);
   return VOFOD_OK;
+}
+
+static int process_scan_dev(vofod_ctx* ctx, const vofod_pt* d_scan, size_t n, const vofod_pose& tf, const vofod_params& p, const vofod_schedule& s, vofod_scan_result* res,
+                            vofod_detection* dets, size_t det_cap)
+{
+  if (res)
+    memset(res, 0, sizeof(*res));
+  RET(scan_launch(ctx, d_scan, n, tf, p, s, 0, false));
+  return scan_finish(ctx, 0, res, dets, det_cap);
 }
 
 extern "C" {
@@ -1259,18 +1309,62 @@ int vofod_process_scan_batch(vofod_ctx* ctx, const vofod_pt* const* scans, size_
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (n_done)
     *n_done = 0;
-  for (size_t k = 0; k < n_scans; k++)
+  if (n_scans == 0)
+    return VOFOD_OK;
+  if (!ctx->W || n != (size_t)ctx->W * ctx->H)
+    return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
+  // Two scans in flight: while scan k runs, the host launches scan k + 1 behind it (nothing it decides needs scan k's results), reads the
+  // results of scan k - 1 and starts the copy of scan k + 1 — the GPU never waits for the host between two scans.  What a scan leaves
+  // for the host to adapt (list capacities, the full-grid flag clear of the very first scans) takes effect one scan later.
+  const size_t bytes = n * sizeof(vofod_pt);
+  for (int i = 0; i < 2; i++)
   {
-    if (k + 1 < n_scans)
-      RET(vofod_prefetch_scan(ctx, scans[k + 1], n));
-    const int rc = vofod_process_scan(ctx, scans[k], n, poses + k, p, scheds + k, results + k, dets ? dets + k * det_cap : nullptr, det_cap);
+    if (ctx->prefetch_buf[i].cap < bytes + 64)
+      ENSURE(ctx->prefetch_buf[i], bytes + 64);
+    ctx->prefetched_host[i] = nullptr;  // records of vofod_prefetch_scan do not survive a batch
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // (fresh allocations are zero-filled on the main stream)
+  auto copy_in = [&](size_t k) -> int {
+    const int slot = (int)(k & 1);
+    CK(cudaMemcpyAsync(ctx->prefetch_buf[slot].p, scans[k], bytes, cudaMemcpyHostToDevice, ctx->stream_copy));
+    CK(cudaEventRecord(ctx->ev_prefetch[slot], ctx->stream_copy));
+    return 0;
+  };
+  auto finish = [&](size_t k) -> int {
+    const int rc = scan_finish(ctx, (int)(k & 1), results + k, dets ? dets + k * det_cap : nullptr, det_cap);
     if (rc < 0)
       return rc;
     if (n_dets)
       n_dets[k] = results[k].n_detections;
     if (n_done)
       *n_done = k + 1;
+    return 0;
+  };
+  RET(copy_in(0));
+  for (size_t k = 0; k < n_scans; k++)
+  {
+    const int slot = (int)(k & 1);
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch[slot], 0));
+    const int lrc = scan_launch(ctx, ctx->prefetch_buf[slot].as<vofod_pt>(), n, poses[k], *p, scheds[k], slot, true);
+    if (lrc < 0)
+    {
+      if (k >= 1)
+        finish(k - 1);
+      return lrc;
+    }
+    if (k >= 1)
+    {
+      const int frc = finish(k - 1);
+      if (frc < 0)
+      {
+        scan_finish(ctx, slot, nullptr, nullptr, 0);  // drain the scan that is in flight
+        return frc;
+      }
+    }
+    if (k + 1 < n_scans)
+      RET(copy_in(k + 1));  // into the buffer scan k - 1 has just finished with; overlaps scan k's kernels
   }
+  RET(finish(n_scans - 1));
   return VOFOD_OK;
 }
 

@@ -389,6 +389,8 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
                                       more, i.e. long rays on a fine grid), 1 always, 2 never */
 #define VOFOD_OPT_RAYCAST_EXP 13   /* MEASUREMENT ONLY (the raycast results are wrong while it is set): 1 = the accumulate kernel does everything but the RED itself,
                                       2 = the DDA alone (no match / redux / RED): what the instruction stream costs without the memory side */
+#define VOFOD_OPT_RAYCAST_SPREAD 14 /* tuning (default 64): the accumulate kernel merges the updates of a warp's lanes up to this many voxel sizes along a ray; beyond it
+                                     neighbouring rays stand in different voxels anyway and every lane adds its own value */
 #define VOFOD_OPT_RAYCAST_STATS 10 /* instrumentation switch (default 0): the accumulate kernel also fills per warp-step histograms, see vofod_raycast_stats */
 int vofod_set_option(vofod_ctx*, int option, int value);
 /* VOFOD_OPT_RAYCAST_STATS: out[0..32] = warp-steps with that many lanes (rays) in the loop, out[33..65] = warp-steps with that many distinct

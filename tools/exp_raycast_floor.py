@@ -21,7 +21,7 @@ v.reset(p, 0.5)
 v.set_sensor(W, H, d)
 scans = [synth.generate(0, k, W, H, d) for k in range(40, 44)]
 out = {}
-for name, exp in (("full", 0), ("no_red", 1), ("dda_only", 2), ("full_again", 0)):
+for name, exp in (("full", 0), ("round1_loop_56regs", 3), ("no_red_round1_loop", 1), ("dda_only_round1_loop", 2), ("full_again", 0)):
     v.set_option(abi.OPT_RAYCAST_EXP, exp)
     ts = []
     for (scan, pose, rp, _) in scans * 3:
@@ -29,5 +29,5 @@ for name, exp in (("full", 0), ("no_red", 1), ("dda_only", 2), ("full_again", 0)
         res, _ = v.process_scan(scan, pose, p, s)
         ts.append(v.stage_times()['raycasting'])
     out[name + "_ms"] = round(float(np.median(ts[4:])), 4)
-    out["traversals"] = int(res.n_traversals) if exp == 0 else out.get("traversals")
+    out["traversals"] = int(res.n_traversals) if exp not in (1, 2) else out.get("traversals")
 print(json.dumps(out))

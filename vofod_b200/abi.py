@@ -215,3 +215,4 @@ VOFOD_W_REDO = 5
 OPT_SLAB_PATCH_WORDS = 11
 OPT_ACC_SPARSE = 12
 OPT_RAYCAST_EXP = 13
+OPT_RAYCAST_SPREAD = 14

@@ -380,6 +380,7 @@ struct vofod_ctx
   void* nccl_comm = nullptr;                            // ncclComm_t (vofod_comm_init)
   int raycast_block = 64;       // tuning: rays per block of the accumulate kernel (64 / 128 / 256)
   int raycast_exp = 0;          // VOFOD_OPT_RAYCAST_EXP (measurement only)
+  int raycast_spread_voxels = 64;  // VOFOD_OPT_RAYCAST_SPREAD: warp aggregation ends this many voxel sizes along a ray
   bool raycast_no_agg = false;  // experiment switch: one RED per traversal instead of warp-aggregated REDs
   bool raycast_stats = false;   // instrumentation switch: the accumulate kernel fills ray_stats (see RAY_STATS_SLOTS in raycast.cu)
   DevBuf ray_stats;

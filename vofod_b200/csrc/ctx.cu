@@ -123,6 +123,10 @@ int vofod_create(int device, vofod_ctx** out)
   }
   if (getenv("VOFOD_NO_OVERLAP"))
     ctx->overlap_enabled = false;
+  if (const char* e = getenv("VOFOD_RAYCAST_EXP"))  // A/B runs of the accumulate kernel's variants under the whole test suite (values >= 3 give correct results)
+    ctx->raycast_exp = atoi(e);
+  if (const char* e = getenv("VOFOD_RAYCAST_SPREAD"))
+    ctx->raycast_spread_voxels = atoi(e);
   ctx->pinned_bytes = 1 << 20;
   if (cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault) != cudaSuccess)
   {
@@ -297,6 +301,14 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
   {
     ctx->slab_patch_words_forced = value > 0 ? (size_t)value : 0;
     ctx->slab_patch_words = 0;
+    return VOFOD_OK;
+  }
+  if (option == VOFOD_OPT_RAYCAST_SPREAD)
+  {
+    if (value < 0)
+      return vf_fail(ctx, VOFOD_E_INVALID, "raycast spread distance must be >= 0 voxels");
+    ctx->raycast_spread_voxels = value;
+    ctx->alloc_gen++;
     return VOFOD_OK;
   }
   if (option == VOFOD_OPT_RAYCAST_EXP)

@@ -24,6 +24,7 @@ struct RayArgs
   float scale;  // 2^F
   int n;
   int has_off;
+  float spread_len;  // aggregation ends this far along a ray [m]
 };
 
 __device__ __forceinline__ void red_add_u64(unsigned long long* addr, const unsigned long long v)
@@ -158,6 +159,87 @@ __device__ __forceinline__ unsigned ray_loop(RayState& r, bool alive, const floa
   return steps;
 }
 
+// ---- ray_loop3 (VER 5): the fewest instructions per step ---------------------------------------------------------------------------------
+// The kernel is bound by instruction issue (~65 % of the slots filled, every attempt to trade instructions for fewer warp collectives made it
+// slower — profiles/r02_raycast_variants.json): predicated axis updates, no bookkeeping that is not needed in the instantiation (TOUCH, SLAB,
+// FAST are template switches), one match.any + one redux + one RED block per step.  Aggregation ends by DISTANCE, at no cost per step: the loop
+// runs while dist < stop; the caller runs it once with AGG up to `spread_len` along the ray and once without for what is left (rays of a warp
+// are 3 mrad apart: past ~50 voxels most lanes stand alone, and a redux per lane costs more than the REDs it saves).
+template <bool AGG, bool SLAB, bool FAST, bool TOUCH>
+__device__ __forceinline__ unsigned ray_loop3(RayState& r, bool& alive, const float stop, const float scale, const int slab_axis, const int ssize, const int own_lo,
+                                              const int own_n, const int wn, unsigned long long* __restrict__ acc, const unsigned lane, const unsigned lanemask_lt,
+                                              uint8_t* __restrict__ touched)
+{
+  unsigned steps = 0;
+  bool go = alive && r.prev < stop;
+  while (go)
+  {
+    const float dist = fminf(fminf(r.tmx, r.tmy), r.tmz);
+    const bool step_x = r.tmx == dist;                 // tmax.minCoeff(&i): the first minimum
+    const bool step_y = !step_x && r.tmy == dist;
+    const bool step_z = !step_x && !step_y;
+    const float ddist = fminf(r.len, dist) - r.prev;   // voxel_map.cpp:252 (no NaNs here: fminf == the reference's ?:)
+    const int q = __float2int_rn(ddist * scale);
+    int key;
+    bool inside = true;
+    if (FAST && !SLAB)
+      key = r.widx;
+    else if (SLAB)
+    {
+      inside = (unsigned)r.spos < (unsigned)ssize;
+      key = inside ? r.widx : -1 - (int)lane;
+    } else
+      key = (int)min((unsigned)r.widx, (unsigned)wn);
+    if (AGG)
+    {
+      const unsigned am = __activemask();
+      const unsigned m = __match_any_sync(am, key);
+      const int sum = __reduce_add_sync(m, q);
+      if (inside && (m & lanemask_lt) == 0)
+      {
+        // (q can be negative: a start point that rounding puts a hair outside its voxel gives a first tmax below zero)
+        red_add_u64(acc + key, ((unsigned long long)__popc(m) << ACC_LEN_BITS) + (unsigned long long)(long long)sum);
+        if (TOUCH)
+          touched[key >> 5] = 1;
+      }
+    } else if (inside)
+    {
+      red_add_u64(acc + key, (1ull << ACC_LEN_BITS) + (unsigned long long)(long long)q);
+      if (TOUCH)
+        touched[key >> 5] = 1;
+    }
+    steps += SLAB ? ((unsigned)(r.spos - own_lo) < (unsigned)own_n ? 1u : 0u) : 1u;
+    r.prev = dist;
+    // voxel_map.cpp:257-261
+    alive = dist < r.len;
+    if (!FAST)
+    {
+      const int rem = step_z ? r.remz : (step_y ? r.remy : r.remx);
+      alive = alive && rem != 0;
+    }
+    if (step_x) r.tmx += r.tdx;
+    if (step_y) r.tmy += r.tdy;
+    if (step_z) r.tmz += r.tdz;
+    r.widx += step_x ? r.dwx : (step_y ? r.dwy : r.dwz);
+    if (!FAST)
+    {
+      if (step_x) r.remx--;
+      if (step_y) r.remy--;
+      if (step_z) r.remz--;
+    }
+    if (SLAB)
+    {
+      if (slab_axis == 0 ? step_x : (slab_axis == 1 ? step_y : step_z))
+        r.spos += r.sstep;
+      // a ray that has left the window along the slab axis never comes back (the general loop is entered fast-forwarded as well)
+      if (FAST || slab_axis < 2)
+        alive = alive && (unsigned)r.spos < (unsigned)ssize;
+    }
+    go = alive && dist < stop;
+  }
+  return steps;
+}
+
 // SLAB: bring the DDA of a ray that starts outside the slab's window to the state it has when it enters, WITHOUT walking the voxels
 // in between.  The DDA is a 3-way merge of the increasing sequences tm_a + j*td_a (each built by the same chain of fp32 additions the
 // loop performs) with ties going to x before y before z (first minimum).  The ka-th step along the slab axis consumes T = tm_a after
@@ -217,8 +299,10 @@ __device__ __forceinline__ bool ray_skip_to_slab(RayState& r, const int slab_axi
 
 // RB = rays (threads) per block.  Ray lengths differ a lot between LiDAR rows (no-return rays walk max_dist, ground
 // returns a few metres), so small blocks balance better: 64 threads = 2 warps = 64 neighbouring columns of one row.
-template <int RB, bool AGG, bool SLAB, bool STATS, int EXP = 0>
-__global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
+// VER 5 = ray_loop3 in 32 registers (2048 threads per SM: every ray of a 128 x 2048 scan is resident at once — with 56 registers only 36 of the
+// 55 warps an SM receives were, and the rest ran as a second, half-empty wave); VER 0 = round 1's loop and register budget (statistics, A/B runs).
+template <int RB, bool AGG, bool SLAB, bool STATS, int EXP = 0, int VER = 5, bool TOUCH = false>
+__global__ void __launch_bounds__(RB, VER == 0 ? 0 : 2048 / RB) k_raycast_accumulate(const RayArgs a, const ScanDyn* __restrict__ dyn, const float4* __restrict__ lut_dir,
                                                            const float4* __restrict__ lut_off, const uint8_t* __restrict__ mask,
                                                            unsigned long long* __restrict__ acc, unsigned long long* __restrict__ counters,
                                                            unsigned long long* __restrict__ stats, uint8_t* __restrict__ touched)
@@ -329,12 +413,26 @@ __global__ void __launch_bounds__(RB) k_raycast_accumulate(const RayArgs a, cons
   {
     if (SLAB && alive)
       alive = ray_skip_to_slab<true>(r, slab_axis, ssize, skipped);
-    steps = ray_loop<AGG, SLAB, true, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    if (VER == 0)
+      steps = ray_loop<AGG, SLAB, true, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    else
+    {
+      // merged up to spread_len along the ray, lane by lane beyond
+      steps = ray_loop3<true, SLAB, true, TOUCH>(r, alive, a.spread_len, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, touched);
+      steps += ray_loop3<false, SLAB, true, TOUCH>(r, alive, __int_as_float(0x7f800000), a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, touched);
+    }
   } else
   {
     if (SLAB && slab_axis < 2 && alive)
       alive = ray_skip_to_slab<false>(r, slab_axis, ssize, skipped);
-    steps = ray_loop<AGG, SLAB, false, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    if (VER == 0)
+      steps = ray_loop<AGG, SLAB, false, STATS, EXP>(r, alive, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, stats, touched);
+    else
+    {
+      // merged up to spread_len along the ray, lane by lane beyond
+      steps = ray_loop3<true, SLAB, false, TOUCH>(r, alive, a.spread_len, a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, touched);
+      steps += ray_loop3<false, SLAB, false, TOUCH>(r, alive, __int_as_float(0x7f800000), a.scale, slab_axis, ssize, own_lo, own_n, wn, acc, lane, lanemask_lt, touched);
+    }
   }
   __syncwarp();
   if (STATS && skipped)
@@ -731,30 +829,35 @@ int vf_raycast_accumulate_dev(vofod_ctx* ctx, size_t n, const vofod_pose& tf, co
     ENSURE(ctx->ray_stats, RAY_STATS_SLOTS * 8);
     stats = ctx->ray_stats.as<unsigned long long>();
   }
-#define RAY_LAUNCH(RB_, AGG_, SLAB_, STATS_)                                                                                                                 \
-  LAUNCH((k_raycast_accumulate<RB_, AGG_, SLAB_, STATS_>), (int)((n + RB_ - 1) / RB_), RB_, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(),       \
-         ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched)
+  // VOFOD_OPT_RAYCAST_NO_AGG: no merging at all = merging that ends at distance 0
+  a.spread_len = ctx->raycast_no_agg ? 0.0f : (float)ctx->raycast_spread_voxels * ctx->g.vs;
+#define RAY_ARGS a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(), ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched
+#define RAY_LAUNCH(RB_, SLAB_, TOUCH_) LAUNCH((k_raycast_accumulate<RB_, true, SLAB_, false, 0, 5, TOUCH_>), (int)((n + RB_ - 1) / RB_), RB_, 0, RAY_ARGS)
+#define RAY_OLD(SLAB_, STATS_, EXP_) LAUNCH((k_raycast_accumulate<64, true, SLAB_, STATS_, EXP_, 0>), (int)((n + 63) / 64), 64, 0, RAY_ARGS)
   if (ctx->raycast_exp == 1 && !slab)
-    LAUNCH((k_raycast_accumulate<64, true, false, false, 1>), (int)((n + 63) / 64), 64, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),
-           ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched);
+    RAY_OLD(false, false, 1);
   else if (ctx->raycast_exp == 2 && !slab)
-    LAUNCH((k_raycast_accumulate<64, true, false, false, 2>), (int)((n + 63) / 64), 64, 0, a, ctx->dyn.as<ScanDyn>(), ctx->lut_dir.as<float4>(), ctx->lut_off.as<float4>(),
-           ctx->mask.as<uint8_t>(), ctx->acc.as<unsigned long long>(), cnt, stats, touched);
-  else if (ctx->raycast_no_agg)
+    RAY_OLD(false, false, 2);
+  else if (ctx->raycast_exp == 3)  // round 1's loop, for A/B runs (results are correct)
   {
-    if (slab) RAY_LAUNCH(64, false, true, false); else RAY_LAUNCH(64, false, false, false);
+    if (slab) RAY_OLD(true, false, 0); else RAY_OLD(false, false, 0);
   } else if (stats)
   {
-    if (slab) RAY_LAUNCH(64, true, true, true); else RAY_LAUNCH(64, true, false, true);
+    if (slab) RAY_OLD(true, true, 0); else RAY_OLD(false, true, 0);
   } else if (slab)
-    RAY_LAUNCH(64, true, true, false);
+  {
+    if (touched) RAY_LAUNCH(64, true, true); else RAY_LAUNCH(64, true, false);
+  } else if (touched)
+    RAY_LAUNCH(64, false, true);
   else if (ctx->raycast_block == 128)
-    RAY_LAUNCH(128, true, false, false);
+    RAY_LAUNCH(128, false, false);
   else if (ctx->raycast_block == 256)
-    RAY_LAUNCH(256, true, false, false);
+    RAY_LAUNCH(256, false, false);
   else
-    RAY_LAUNCH(64, true, false, false);
+    RAY_LAUNCH(64, false, false);
 #undef RAY_LAUNCH
+#undef RAY_OLD
+#undef RAY_ARGS
   ctx->acc_has_data = true;
   return VOFOD_OK;
 }

@@ -486,6 +486,7 @@ def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None, balanced=F
     stream = torch.cuda.ExternalStream(v.stream(), device=torch.device("cuda", local_rank))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_scans)]
     trav, dets, l0 = 0, 0, 0
+    parts = np.zeros(8)
 
     def barrier():
         torch.cuda.synchronize()
@@ -498,13 +499,23 @@ def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None, balanced=F
             barrier()
             l0 = v.kernel_launches()
         ev[k][0].record(stream)
-        res, d = worker.step(host[k], poses[k], scheds[k])
+        res, d = worker.step(host[k], poses[k], scheds[k], next_scan_host=host[k + 1] if k + 1 < n_scans else None)
         ev[k][1].record(stream)
         if k >= Wm:
             trav += res.n_traversals  # summed over the slabs by the library (a traversal is counted by the slab that owns the voxel)
             dets += res.n_detections
+            parts += v.slab_times()
     barrier()
     launches = v.kernel_launches() - l0
+    # where a scan's time goes on every rank: [broadcast, phase 0, exchange 0, phase 1, exchange 1, phase 2, exchange 2, phase 3] (ms, mean of the
+    # timed scans; an exchange includes the wait for the slowest slab)
+    pt = torch.tensor(parts / K, dtype=torch.float64, device="cuda")
+    if world > 1:
+        allp = [torch.zeros_like(pt) for _ in range(world)]
+        dist.all_gather(allp, pt)
+    else:
+        allp = [pt]
+    parts_by_rank = [[round(float(x), 4) for x in t.tolist()] for t in allp]
     ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(Wm, n_scans))
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -520,7 +531,8 @@ def slab_leg(local_rank, rank, world, raycast_max, K, Wm, scans=None, balanced=F
             "raycast_max_distance_m": raycast_max, "traversals_per_scan": trav / K, "gvoxel_traversals_per_s_full_path": trav / (total_ms * 1e-3) / 1e9,
             "detections_in_timed_steps": dets, "gpu_launches_rank0": int(launches), "slab0_storage_cells": cells,
             "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize, "scaling": "strong",
-            "slab_cut": "by ray load (multi.partition_by_ray_load)" if cuts is not None else "equal width", "own_range_rank0": [int(worker.lo), int(worker.hi)]}, scans
+            "slab_cut": "by ray load (multi.partition_by_ray_load)" if cuts is not None else "equal width", "own_range_rank0": [int(worker.lo), int(worker.hi)],
+            "ms_by_rank_bcast_p0_x0_p1_x1_p2_x2_p3": parts_by_rank}, scans
 
 
 def slab_record(local_rank, rank, world, K, Wm, dists=(20.0, 200.0)):
@@ -535,7 +547,7 @@ def slab_record(local_rank, rank, world, K, Wm, dists=(20.0, 200.0)):
         rec[key] = r
         if world > 1:
             rb, _ = slab_leg(local_rank, rank, world, d, K, Wm, scans=scans, balanced=True)
-            r["cut_by_ray_load"] = {k: rb[k] for k in ("value", "ms_per_step", "slab_cut", "own_range_rank0", "slab0_storage_cells")}
+            r["cut_by_ray_load"] = {k: rb[k] for k in ("value", "ms_per_step", "slab_cut", "own_range_rank0", "slab0_storage_cells", "ms_by_rank_bcast_p0_x0_p1_x1_p2_x2_p3")}
             if rank == 0:
                 one, _ = slab_leg(local_rank, 0, 1, d, K, Wm, scans=scans)
                 r["one_gpu_same_run"] = {"value": one["value"], "ms_per_step": one["ms_per_step"]}

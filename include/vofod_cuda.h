@@ -360,6 +360,9 @@ int vofod_comm_unique_id(void* out128);
 int vofod_comm_init(vofod_ctx*, int rank, int nranks, const void* nccl_unique_id);
 int vofod_slab_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_pose*, const vofod_params*, const vofod_schedule*,
                             vofod_scan_result* res, vofod_detection* dets, size_t det_cap);
+/* device time [ms] of the parts of the last vofod_slab_process_scan on this rank: [0] scan copy + broadcast, [1],[3],[5] the kernels of phases
+ * 0..2, [2],[4],[6] the exchange after each (includes waiting for the slowest slab), [7] phase 3 with its read-back */
+int vofod_slab_times(vofod_ctx*, float ms[8]);
 /* voxels of the last scan within `margin` cells of a face of the owned range, with their cluster labels (the cluster fragments that
  * reach into the neighbouring slab) */
 int vofod_slab_boundary(vofod_ctx*, int margin, int32_t* point_idx, int32_t* labels, size_t cap, size_t* n);

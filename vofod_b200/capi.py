@@ -163,6 +163,7 @@ def load_library():
         "vofod_slab_exchanges": (i32, [vp, i32, P(abi.SlabExchange), P(i32)]),
         "vofod_comm_unique_id": (i32, [vp]),
         "vofod_comm_init": (i32, [vp, i32, i32, vp]),
+        "vofod_slab_times": (i32, [vp, vp]),
         "vofod_slab_process_scan": (i32, [vp, vp, sz, P(Pose), P(Params), P(Schedule), P(ScanResult), vp, sz]),
         "vofod_dev_read": (i32, [vp, vp, vp, sz]),
         "vofod_dev_write": (i32, [vp, vp, vp, sz]),
@@ -569,6 +570,12 @@ class Vofod:
         n = C.c_size_t()
         self._ck(self.lib.vofod_slab_boundary(self.h, int(margin), _p(idx), _p(lab), cap, C.byref(n)))
         return idx[:n.value].copy(), lab[:n.value].copy()
+
+    def slab_times(self):
+        """ms of the last vofod_slab_process_scan: broadcast, (phase k, exchange k) for k = 0..2, phase 3"""
+        ms = np.zeros(8, dtype=np.float32)
+        self._ck(self.lib.vofod_slab_times(self.h, _p(ms)))
+        return ms
 
     def stage_times(self):
         ms = np.zeros(abi.N_STAGES, dtype=np.float32)

@@ -413,6 +413,9 @@ struct vofod_ctx
   cudaEvent_t ev_fork4 = nullptr, ev_front = nullptr;
   ScanInFlight fl[2];           // vofod_process_scan_batch keeps two scans in flight; a single call uses slot 0
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_slab[9] = {};  // vofod_slab_process_scan: start, broadcast, (phase, exchange) x 3, phase 3
+  float slab_ms[8] = {};        // vofod_slab_times
+  bool slab_acc_forked = false; // the scan's raycast accumulate runs on stream2 (phase 0 .. phase 1)
   bool ray_pending = false;     // an accumulate whose apply was deferred (vofod_schedule::raycast_defer_apply)
   Window ray_pending_win;
   uint64_t stat_replays = 0, stat_captures = 0, stat_capture_failures = 0, stat_eager = 0;

@@ -99,6 +99,8 @@ int vofod_create(int device, vofod_ctx** out)
   cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming);
+  for (auto& e : ctx->ev_slab)
+    cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_prefetch[1], cudaEventDisableTiming);
@@ -216,6 +218,9 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaStreamDestroy(ctx->stream_copy);
   }
   cudaStreamDestroy(ctx->stream);
+  for (auto& e : ctx->ev_slab)
+    if (e)
+      cudaEventDestroy(e);
   delete ctx;
   return VOFOD_OK;
 }

@@ -273,6 +273,25 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
       RET(vf_begin_call(ctx));
       RET(vf_dyn_push(ctx));
       RET(vf_range_update_dev(ctx, p));
+      // The clipped raycast reads only the scan, the LUT and the per-scan arguments and writes only the accumulator window: it runs on the
+      // second stream beside phase 0, the exchange after it and the head of phase 1 (an issue-bound kernel next to chains of short,
+      // latency-bound ones); phase 1 joins before the apply.  Only for windows that live in L2 (20 m rays: 1.28 -> 1.18 ms per scan on two
+      // slabs): a GB-sized window's accumulate runs for milliseconds with every warp slot taken, and the short kernels of phase 0 then
+      // wait for slots launch after launch (200 m rays: 4.34 -> 4.52 ms, measured).
+      ctx->slab_acc_forked = false;
+      if (s.do_raycast && ctx->slab_raycast_status == VOFOD_OK && ctx->stream2 != nullptr && ctx->overlap_enabled && !ctx->acc_sparse)
+      {
+        cudaStream_t st = ctx->stream;
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        ctx->stream = ctx->stream2;
+        const int rrc = vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p);
+        ctx->stream = st;
+        if (rrc < 0)
+          return rrc;
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        ctx->slab_acc_forked = true;
+      }
       const int seeded = vf_filter_voxelize_dev(ctx, n, p, true);
       if (seeded < 0)
         return seeded;
@@ -298,7 +317,11 @@ static int slab_phase(vofod_ctx* ctx, const int phase, vofod_scan_result* res, v
       ctx->detection_its++;
       if (s.do_raycast && ctx->slab_raycast_status == VOFOD_OK)
       {
-        RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
+        if (ctx->slab_acc_forked)
+          CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        else
+          RET(vf_raycast_accumulate_dev(ctx, n, vofod_pose(), p));
+        ctx->slab_acc_forked = false;
         const int rc = vf_raycast_apply_dev(ctx, 0, p);
         if (rc < 0)
           return rc;
@@ -556,25 +579,63 @@ int vofod_slab_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, cons
   if (ctx->slab_nranks > 1 && (!nc || !comm))
     return vf_fail(ctx, VOFOD_E_STATE, "vofod_slab_process_scan on %d ranks needs vofod_comm_init", ctx->slab_nranks);
   ENSURE(ctx->scan_staging, n * sizeof(vofod_pt) + 64);
+  // where the scan's time goes (vofod_slab_times): events on the stream before the copy, after the broadcast, after every phase's kernels and
+  // after every exchange
+  CK(cudaEventRecord(ctx->ev_slab[0], ctx->stream));
+  const void* d_src = ctx->scan_staging.p;
   if (ctx->slab_rank == 0)
-    CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // a scan announced with vofod_prefetch_scan has been copied next to the previous scan's kernels
+    int hit = -1;
+    for (int i = 0; i < 2; i++)
+      if (ctx->prefetched_host[i] == (const void*)scan && ctx->prefetched_n[i] == n && ctx->prefetch_buf[i].p)
+        hit = i;
+    if (hit >= 0)
+    {
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch[hit], 0));
+      ctx->prefetched_host[hit] = nullptr;
+      ctx->stat_prefetch_hits++;
+      d_src = ctx->prefetch_buf[hit].p;
+    } else
+      CK(cudaMemcpyAsync(ctx->scan_staging.p, scan, n * sizeof(vofod_pt), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const vofod_pt* d_scan = ctx->scan_staging.as<vofod_pt>();
   if (nc)
-    NCK(nc->Broadcast(ctx->scan_staging.p, ctx->scan_staging.p, n * sizeof(vofod_pt), ncclUint8, 0, comm, ctx->stream));
-  RET(slab_begin(ctx, ctx->scan_staging.as<vofod_pt>(), n, tf, p, s));
+    NCK(nc->Broadcast(d_src, ctx->scan_staging.p, n * sizeof(vofod_pt), ncclUint8, 0, comm, ctx->stream));
+  else
+    d_scan = (const vofod_pt*)d_src;
+  CK(cudaEventRecord(ctx->ev_slab[1], ctx->stream));
+  RET(slab_begin(ctx, d_scan, n, tf, p, s));
   int rc = VOFOD_OK;
+  bool redone = false;
   for (int phase = 0; phase <= 3; phase++)
   {
     ctx->slab_next_phase = phase + 1;
+    if (phase == 3)
+      CK(cudaEventRecord(ctx->ev_slab[8], ctx->stream));  // (phase 3 ends with the host wait: its end is taken on the host side below)
     rc = slab_phase(ctx, phase, res, dets, det_cap);
     if (rc < 0)
       return rc;
     if (rc == VOFOD_W_REDO)
     {
       phase = 1;  // continue with phase 2
+      redone = true;
       continue;
     }
     if (phase == 3)
+    {
+      // the stream is idle here (phase 3 waited for it)
+      if (!redone)
+      {
+        for (int i = 0; i < 7; i++)
+          cudaEventElapsedTime(&ctx->slab_ms[i], ctx->ev_slab[i], ctx->ev_slab[i + 1]);
+        CK(cudaEventRecord(ctx->ev_slab[0], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev_slab[0]));
+        cudaEventElapsedTime(&ctx->slab_ms[7], ctx->ev_slab[8], ctx->ev_slab[0]);
+      }
       continue;
+    }
+    CK(cudaEventRecord(ctx->ev_slab[2 + 2 * phase], ctx->stream));
     vofod_slab_exchange x[4];
     int nx = 0;
     RET(vofod_slab_exchanges(ctx, phase, x, &nx));
@@ -584,10 +645,14 @@ int vofod_slab_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, cons
       for (int i = 0; i < nx; i++)
         if (x[i].kind == VOFOD_XCHG_GATHER_U32)
           CK(cudaMemcpyAsync(x[i].gather_out, x[i].buf, x[i].count * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(cudaEventRecord(ctx->ev_slab[3 + 2 * phase], ctx->stream));
       continue;
     }
     if (nx == 0)
+    {
+      CK(cudaEventRecord(ctx->ev_slab[3 + 2 * phase], ctx->stream));
       continue;
+    }
     NCK(nc->GroupStart());
     for (int i = 0; i < nx; i++)
     {
@@ -606,7 +671,18 @@ int vofod_slab_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, cons
       }
     }
     NCK(nc->GroupEnd());
+    CK(cudaEventRecord(ctx->ev_slab[3 + 2 * phase], ctx->stream));
   }
   return rc;
+}
+
+/* device time [ms] of the parts of the last vofod_slab_process_scan on this rank: scan copy + broadcast, then (phase k kernels, exchange
+ * after phase k) for k = 0..2, then phase 3 (with its read-back).  An exchange's time includes waiting for the slowest rank. */
+int vofod_slab_times(vofod_ctx* ctx, float ms[8])
+{
+  if (!ctx || !ms)
+    return VOFOD_E_INVALID;
+  memcpy(ms, ctx->slab_ms, sizeof(ctx->slab_ms));
+  return VOFOD_OK;
 }
 }  // extern "C"

@@ -98,8 +98,11 @@ class SlabWorker:
             uid = t.cpu().numpy().tobytes()
         ctx.comm_init(rank, world, uid)
 
-    def step(self, scan_host, pose, sched):
-        """scan_host is read on rank 0 only; pose and schedule are given on every rank.  -> (ScanResult, detections)"""
+    def step(self, scan_host, pose, sched, next_scan_host=None):
+        """scan_host is read on rank 0 only; pose and schedule are given on every rank.  next_scan_host (rank 0): the scan of the NEXT step,
+        announced with vofod_prefetch_scan so that its host->device copy runs beside this step's kernels.  -> (ScanResult, detections)"""
+        if self.rank == 0 and next_scan_host is not None:
+            self.v.prefetch_scan(next_scan_host)
         return self.v.slab_process_scan(scan_host if self.rank == 0 else None, pose, self.p, sched)
 
     def close(self):

@@ -282,16 +282,54 @@ def run_ours(args):
         assert done == K
         return e0.elapsed_time(e1), sum(r.n_traversals for r in res), sum(r.n_detections for r in res), v.kernel_launches() - l0
 
-    def run_cfg3(K3=40, W3=32):
+    def run_streams_on_this_gpu(S=8):
+        """BASELINE.json configs[3] on the GPUs at hand: S independent scan streams (S contexts, S maps, S host threads) share this GPU; every
+        stream runs the e2e leg (vofod_process_scan_batch from pinned host buffers).  A single scan is a chain of short dependent kernels that
+        leaves most of the machine idle; independent streams fill it.  Timed on the host (start barrier -> last stream done + device idle)."""
+        import threading
+        import time
+        ctxs = [capi.Vofod(local_rank) for _ in range(S)]
+        for c in ctxs:
+            c.reset(p, VOXEL)
+            c.set_sensor(W, H, dirs)
+            c.process_scan_batch([host_scans[k] for k in range(Wm)], poses[:Wm], p, scheds[:Wm])
+        torch.cuda.synchronize()
+        start = threading.Barrier(S + 1)
+        done_n = [0] * S
+
+        def work(i):
+            start.wait()
+            res, done = ctxs[i].process_scan_batch([host_scans[k] for k in range(Wm, n_scans)], poses[Wm:], p, scheds[Wm:])
+            ctxs[i].flush()
+            done_n[i] = done
+        th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+        for t in th:
+            t.start()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert all(d == K for d in done_n), done_n
+        for c in ctxs:
+            c.close()
+        return {"workload": f"{S} independent scan streams (cfg2 scans, one context and one map each) on ONE GPU, each through vofod_process_scan_batch from pinned "
+                            "host buffers; host-timed from a common start to the last stream's last result",
+                "streams": S, "value": S * K / dt, "unit": "scans/s", "ms_per_scan": dt * 1e3 / (S * K), "h2d_bytes_per_step": N * abi.PT_DTYPE.itemsize}
+
+    def run_cfg3(K3=40, W3=32, scene=None, what=None):
         """BASELINE.json configs[2]: Gazebo-like scene with 3 sphere UAVs — the scans that DO produce detections (exploreToGround, frontier
-        write-back, submap confidence) — same map, same per-step timing as the resident leg"""
+        write-back, submap confidence) — same map, same per-step timing as the resident leg.  scene = SCENE_SWARM: the same with 200 spheres
+        (~230 far clusters per scan through the one-block sequential classification kernel)"""
+        scene = synth.SCENE_GAZEBO if scene is None else scene
         v.set_option(abi.OPT_GRAPH, 1)
         v.reset(p, VOXEL)
         n3 = K3 + W3
         buf = np.zeros((n3, N), dtype=abi.PT_DTYPE)
         ps, ss = [], []
         for k in range(n3):
-            _, pose, rp, _ = synth.generate(synth.SCENE_GAZEBO, k, W, H, dirs, 1.0, out=buf[k])
+            _, pose, rp, _ = synth.generate(scene, k, W, H, dirs, 1.0, out=buf[k])
             ps.append(pose)
             ss.append(abi.schedule_s1(rp))
             v.upload_scan(k, buf[k])
@@ -309,7 +347,7 @@ def run_ours(args):
                 nfar += res.n_far_clusters
         barrier()
         ms3 = sum(ev3[k][0].elapsed_time(ev3[k][1]) for k in range(W3, n3))
-        return {"workload": "cfg3: Gazebo-like scene (ground + 4 buildings + 3 sphere UAVs), 128x2048 rays, cfg2 map, schedule S1, scans resident in HBM",
+        return {"workload": what or "cfg3: Gazebo-like scene (ground + 4 buildings + 3 sphere UAVs), 128x2048 rays, cfg2 map, schedule S1, scans resident in HBM",
                 "value": K3 / (ms3 * 1e-3), "unit": "scans/s", "ms_per_step": ms3 / K3, "steps": K3, "warmup": W3, "detections_in_timed_steps": int(nd),
                 "far_clusters_per_scan": nfar / K3}
 
@@ -327,7 +365,10 @@ def run_ours(args):
     ms_e2e, tot_e2e = run_leg(False)
     stream_ms, stream_trav, stream_dets, stream_launches = run_streaming()
     clocks = sampler.stop()
+    streams8 = run_streams_on_this_gpu(8) if world == 1 and not args.no_cfg3 else None
     cfg3 = run_cfg3() if rank == 0 and not args.no_cfg3 else None
+    swarm = run_cfg3(scene=synth.SCENE_SWARM, what="stress: the cfg3 scene with 200 sphere UAVs on rings around the sensor (~230 far clusters, > 100 detections per "
+                     "scan), 128x2048 rays, cfg2 map, schedule S1, scans resident in HBM") if rank == 0 and not args.no_cfg3 else None
     if world > 1:
         dist.barrier()
     stats_after_graph_legs = v.stats()
@@ -402,6 +443,8 @@ def run_ours(args):
             "stage_note": "stage times and the roofline kernel time come from a third, kernel-by-kernel leg (graph replay off): %.4f ms/step" % (sum(ms_eager) / K),
             "detections_in_timed_steps": int(tot_res["dets"]),
             "cfg3": cfg3,
+            "cfg4_streams_on_one_gpu": streams8,
+            "cfg3_swarm_200_uavs": swarm,
             "replay_stats": stats_after_graph_legs,
             "clocks": clocks,
         }

@@ -304,7 +304,9 @@ int vofod_process_scan(vofod_ctx*, const vofod_pt* scan, size_t n, const vofod_p
                        const vofod_params*, const vofod_schedule*, vofod_scan_result* res,
                        vofod_detection* dets, size_t det_cap);
 /* announce the NEXT scan: its host->device copy runs on a copy stream next to the current scan's kernels; the following
- * vofod_process_scan with the same `scan` pointer consumes it.  Keep the host buffer (ideally pinned) untouched until then. */
+ * vofod_process_scan (or vofod_slab_process_scan on rank 0) with the same `scan` pointer consumes it.  Keep the host buffer (ideally pinned)
+ * untouched until then.  An announcement is matched by host pointer and is good for the next TWO scan calls only (announce k+1, process k,
+ * process k+1): one that was not consumed by then is void, so a buffer that is refilled later is copied again. */
 int vofod_prefetch_scan(vofod_ctx*, const vofod_pt* scan, size_t n);
 /* carries out a pending deferred separated-background pass (vofod_schedule::sep_deferred); no-op when there is none */
 int vofod_flush(vofod_ctx*);
@@ -394,6 +396,8 @@ uint64_t vofod_kernel_launches(const vofod_ctx*);
                                       2 = the DDA alone (no match / redux / RED): what the instruction stream costs without the memory side */
 #define VOFOD_OPT_RAYCAST_SPREAD 14 /* tuning (default 64): the accumulate kernel merges the updates of a warp's lanes up to this many voxel sizes along a ray; beyond it
                                      neighbouring rays stand in different voxels anyway and every lane adds its own value */
+#define VOFOD_OPT_CLASSIFY_SEQ 15   /* test switch (default 0): exploreToGround / detection extraction in one thread block, cluster after cluster (round 1's kernel)
+                                     instead of in parallel over the far clusters whose explore boxes do not meet */
 #define VOFOD_OPT_RAYCAST_STATS 10 /* instrumentation switch (default 0): the accumulate kernel also fills per warp-step histograms, see vofod_raycast_stats */
 int vofod_set_option(vofod_ctx*, int option, int value);
 /* VOFOD_OPT_RAYCAST_STATS: out[0..32] = warp-steps with that many lanes (rays) in the loop, out[33..65] = warp-steps with that many distinct

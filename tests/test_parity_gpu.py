@@ -424,6 +424,31 @@ def test_graph_replay_equals_kernel_by_kernel(gpu):
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
 
 
+def test_parallel_classification_equals_cluster_by_cluster(gpu):
+    """exploreToGround / detections in parallel over the far clusters (default; a cluster waits for the earlier ones whose explore box meets
+    its own) vs round 1's one-block kernel that takes them in turn: identical classes, detections, ids and maps.  Swarm scene: ~200 sphere
+    UAVs, many with neighbouring explore boxes."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    outs = []
+    for seq in (0, 1):
+        gpu.set_option(abi.OPT_CLASSIFY_SEQ, seq)
+        gpu.reset(p, vs)
+        gpu.set_sensor(sensor.W, sensor.H, sensor.dirs)
+        log = []
+        n_det = 0
+        for k in range(30):
+            scan, pose, rp, _ = sensor.scan(2, k)
+            res, dets = gpu.process_scan(scan, pose, p, abi.schedule_s1(rp))
+            cl = gpu.last_clusters()
+            n_det += len(dets)
+            log.append((tuple(res.as_dict().items()), tuple(dets[f].tobytes() for f in dets.dtype.names), cl["cclass"].tobytes()))
+        outs.append((log, gpu.map_download().tobytes()))
+    gpu.set_option(abi.OPT_CLASSIFY_SEQ, 0)
+    assert n_det > 100
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+
+
 def test_programmatic_dependent_launch_is_transparent(gpu):
     """Kernels chained by programmatic dependent launch (default) vs plainly serialised launches: identical maps and results."""
     sensor = Sensor(512, 32)
@@ -721,6 +746,16 @@ def test_cfg3_full_size_detections(gpu, cpu):
     p, vs = cfg2_params()
     n_det = _run_sequence(gpu, cpu, sensor, p, vs, 1, range(0, 24), fixed=True, check_maps_every=6)
     assert n_det >= 3
+
+
+def test_swarm_two_hundred_far_clusters(gpu, cpu):
+    """Stress case for the classification stage (one thread block, sequential over the clusters by construction): the Gazebo scene with 200
+    sphere UAVs on rings around the sensor (synth scene 2) — ~230 far clusters and > 100 detections per scan once the background is known;
+    full sensor, cfg2 map, every scan compared with the oracle (classes, frontier write-back through the map, detection records)."""
+    sensor = Sensor(2048, 128)
+    p, vs = cfg2_params()
+    n_det = _run_sequence(gpu, cpu, sensor, p, vs, 2, range(0, 27), fixed=True, check_maps_every=13)
+    assert n_det >= 200
 
 
 def test_quarter_metre_voxels(gpu, cpu):

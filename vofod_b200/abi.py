@@ -216,3 +216,4 @@ OPT_SLAB_PATCH_WORDS = 11
 OPT_ACC_SPARSE = 12
 OPT_RAYCAST_EXP = 13
 OPT_RAYCAST_SPREAD = 14
+OPT_CLASSIFY_SEQ = 15

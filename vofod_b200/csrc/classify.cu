@@ -18,6 +18,7 @@
 
 #define CLS_CANDIDATE (-1)
 #define MAX_DETS 16384
+#define CLS_PAR_BLOCKS 64  // thread blocks (and stamp cubes) of the parallel classification
 
 // far clusters: per-label size and largest member index, list of far roots (unordered) with their sort keys
 __global__ void __launch_bounds__(256) k_cls_mark(const int* __restrict__ labels, const uint8_t* __restrict__ in_close, const unsigned long long* __restrict__ d_m,
@@ -442,6 +443,13 @@ __device__ __forceinline__ float cls_load(const float* score, const Geom& g, con
   const long long ci = cell_index(g, x, y, z);
   return ci >= 0 ? score[ci] : 0.0f;
 }
+// the same read straight from L2: the parallel classification reads cells that a block on ANOTHER SM may have written earlier in the same
+// launch, and an SM's L1 is not coherent with those writes
+__device__ __forceinline__ float cls_load_cg(const float* score, const Geom& g, const int x, const int y, const int z)
+{
+  const long long ci = cell_index(g, x, y, z);
+  return ci >= 0 ? __ldcg(score + ci) : 0.0f;
+}
 // explore radius of a candidate (:1698) and its box
 __device__ __forceinline__ int cls_explore_radius(const float obb_size, const double max_explore_distance, const float vs)
 {
@@ -465,7 +473,7 @@ __device__ __forceinline__ void explore_decode(const ExploreWs& w, const int rel
   dy = (rel / w.side) % w.side - w.rm;
   dx = rel % w.side - w.rm;
 }
-template <bool PATCH>
+template <bool PATCH, bool CG = false>
 __device__ bool explore_to_ground_block(const float* score, const Geom& g, const int ox, const int oy, const int oz, const float unknown_thr, const float ground_thr,
                                         const float maxd, const unsigned epoch, const ExploreWs& w, int* sh, const PatchDesc* pd = nullptr,
                                         const uint32_t* words = nullptr)
@@ -506,7 +514,7 @@ __device__ bool explore_to_ground_block(const float* score, const Geom& g, const
       int dx, dy, dz;
       explore_decode(w, rel, dx, dy, dz);
       const int x = ox + dx, y = oy + dy, z = oz + dz;
-      const float val = cls_load<PATCH>(score, g, pd, words, x, y, z);
+      const float val = CG ? cls_load_cg(score, g, x, y, z) : cls_load<PATCH>(score, g, pd, words, x, y, z);
       if (val > ground_thr)  // :423 -> connected
         sh[3] = 1;
       else if (val > unknown_thr)  // :427
@@ -770,6 +778,278 @@ __global__ void __launch_bounds__(256) k_classify_seq(const ClsArgs a, const Sca
   }
 }
 
+// K14 in parallel.  The order of the explorations matters only through the map: an exploration that does not reach the ground writes its
+// visited cells back as frontiers (:1712-1715), and a later exploration that meets such a cell stops there.  Explorations of one cluster
+// stay inside the cluster's index box grown by its explore radius, so two clusters whose grown boxes do not meet cannot see each other.
+// NB blocks take the far clusters in the reference's order from a ticket counter; a block waits for every EARLIER cluster whose grown box
+// meets its own to be finished (the blocks holding them are running: the lowest unfinished ticket never waits, so this cannot deadlock),
+// then runs the cluster's explorations exactly as the sequential kernel does, on a stamp cube / queues of its own, reading the map from L2.
+// The last block to finish counts the MAVs, hands k_extract_detections the first detection id and advances m_last_detection_id.
+struct ClsParWs
+{
+  unsigned* stamps;   // [NB][cube]
+  int* queues;        // [NB][3][cube]
+  unsigned* epochs;   // [NB] stamp generation of each block's cube (persistent)
+  unsigned* done;     // [far cluster] == tag: finished in this call
+  size_t cube;
+};
+__device__ __forceinline__ void cls_grown_box(const ClsArgs& a, const vofod_cluster_info& ci, int lo[3], int hi[3])
+{
+  const int R = cls_explore_radius(ci.obb_size, a.max_explore_distance, a.g.vs) + 1;
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+  {
+    lo[q] = coord_to_idx1(ci.aabb_min[q], a.g.off[q], a.g.inv) - R;
+    hi[q] = coord_to_idx1(ci.aabb_max[q], a.g.off[q], a.g.inv) + R;
+  }
+}
+__global__ void __launch_bounds__(256) k_classify_par(const ClsArgs a, float* score, const vofod_vox* __restrict__ vox, const uint32_t* __restrict__ sidx,
+                                                      const int* __restrict__ seg_start, vofod_cluster_info* infos, const ClsParWs ws,
+                                                      unsigned long long* counters, const unsigned long long* __restrict__ d_nfar)
+{
+  pdl_enter();
+  __shared__ int sh[4];
+  __shared__ unsigned s_epoch;
+  __shared__ unsigned long long s_ticket;
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const unsigned long long n_far = *after_wait(d_nfar);
+  const bool active = counters[CNT_STATE_BG] != 0ull && counters[CNT_STATE_SURE] != 0ull;  // :1695
+  const unsigned tag = (unsigned)(counters[CNT_EPOCH_BASE] / EPOCH_STRIDE) | 0x80000000u;   // this API call (k_begin_call advanced it)
+  ExploreWs w;
+  w.stamps = ws.stamps + (size_t)blockIdx.x * ws.cube;
+  w.q0 = ws.queues + (size_t)blockIdx.x * 3 * ws.cube;
+  w.q1 = w.q0 + ws.cube;
+  w.explored = w.q1 + ws.cube;
+  w.side = a.side;
+  w.rm = a.rmax;
+  if (tid == 0)
+    s_epoch = ws.epochs[blockIdx.x];
+  const Geom& g = a.g;
+  while (true)
+  {
+    __syncthreads();
+    if (tid == 0)
+    {
+      s_ticket = atomicAdd(counters + CNT_CLS_TICKET, 1ull);
+      s_last = 0;
+    }
+    __syncthreads();
+    const unsigned long long c = s_ticket;
+    if (c >= n_far)
+      break;
+    const vofod_cluster_info me = infos[c];
+    if (me.cclass == CLS_CANDIDATE)
+    {
+      bool is_floating = true;
+      if (active)
+      {
+        int lo[3], hi[3];
+        cls_grown_box(a, me, lo, hi);
+        // earlier clusters whose grown box meets this one: finished first (the geometry of every cluster is final since k_cluster_moi;
+        // clusters that are no candidates finish at once)
+        for (unsigned long long j = tid; j < c; j += blockDim.x)
+        {
+          int lj[3], hj[3];
+          cls_grown_box(a, infos[j], lj, hj);
+          if (lj[0] > hi[0] || hj[0] < lo[0] || lj[1] > hi[1] || hj[1] < lo[1] || lj[2] > hi[2] || hj[2] < lo[2])
+            continue;
+          const volatile unsigned* dj = ws.done + j;
+          unsigned spins = 0;
+          while (*dj != tag)
+          {
+            __nanosleep(64);
+            if (++spins > (1u << 24))
+            {
+              atomicAdd(counters + CNT_WATCHDOG, 1ull);
+              break;
+            }
+          }
+        }
+        __threadfence();
+        __syncthreads();
+        const int n = me.n_points;
+        const uint32_t* idcs = sidx + seg_start[me.label];
+        const int R = cls_explore_radius(me.obb_size, a.max_explore_distance, g.vs);  // :1698
+        for (int k = 0; k < n && is_floating; k++)
+        {
+          const vofod_vox v = vox[idcs[k]];
+          const int ox = coord_to_idx1(v.x, g.off[0], g.inv), oy = coord_to_idx1(v.y, g.off[1], g.inv), oz = coord_to_idx1(v.z, g.off[2], g.inv);
+          __syncthreads();
+          if (tid == 0)
+          {
+            s_epoch++;
+            if (s_epoch == 0u)
+              s_epoch = 1u;
+          }
+          __syncthreads();
+          const bool connected = explore_to_ground_block<false, true>(score, g, ox, oy, oz, a.thr_frontiers, a.thr_new, (float)R, s_epoch, w, sh);
+          if (connected)
+            is_floating = false;
+          else
+          {
+            // :1712-1715 — mark the explored unknown cells as frontiers
+            const int ne = sh[2];
+            for (int t = tid; t < ne; t += blockDim.x)
+            {
+              int dx, dy, dz;
+              explore_decode(w, w.explored[t], dx, dy, dz);
+              const long long ci = cell_index(g, ox + dx, oy + dy, oz + dz);
+              if (ci >= 0)
+                __stcg(score + ci, a.thr_frontiers);
+            }
+          }
+          __syncthreads();
+        }
+      } else
+        is_floating = false;
+      if (tid == 0)
+        infos[c].cclass = is_floating ? VOFOD_CLASS_MAV : VOFOD_CLASS_UNKNOWN;
+    }
+    // publish: everything this block wrote for cluster c (frontier cells, the class) before the flag
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+      *(volatile unsigned*)(ws.done + c) = tag;
+      __threadfence();
+      s_last = atomicAdd(counters + CNT_CLS_FINISHED, 1ull) == n_far - 1ull ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last)
+    {
+      // every cluster is finished: count the MAVs (= detections, :834-879), fix the ids
+      __threadfence();
+      if (tid == 0)
+        sh[0] = 0;
+      __syncthreads();
+      int mine = 0;
+      for (unsigned long long j = tid; j < n_far; j += blockDim.x)
+        mine += __ldcg(&infos[j].cclass) == VOFOD_CLASS_MAV ? 1 : 0;
+      if (mine)
+        atomicAdd(&sh[0], mine);
+      __syncthreads();
+      if (tid == 0)
+      {
+        const unsigned long long base = counters[CNT_DET_ID];
+        counters[CNT_DET_BASE] = base;
+        counters[CNT_DET_ID] = base + (unsigned long long)sh[0];
+        counters[CNT_NDET] = (unsigned long long)sh[0];
+        // (the ticket and finished counters are zeroed before the next launch, not here: other blocks are still asking for tickets)
+      }
+    }
+  }
+  if (tid == 0)
+    ws.epochs[blockIdx.x] = s_epoch;
+}
+
+// K15 in parallel — extractDetections (:834-879): one block per MAV, detection number = its rank among the MAVs in cluster order
+__global__ void __launch_bounds__(256) k_extract_detections(const ClsArgs a, const ScanDyn* __restrict__ dyn, const float* __restrict__ score, const vofod_vox* __restrict__ vox,
+                                                            const uint32_t* __restrict__ sidx, const int* __restrict__ seg_start,
+                                                            const vofod_cluster_info* __restrict__ infos, double* __restrict__ terms_all,
+                                                            vofod_detection* __restrict__ dets, const unsigned long long* counters,
+                                                            const unsigned long long* __restrict__ d_nfar)
+{
+  pdl_enter();
+  __shared__ int s_rank;
+  const int tid = threadIdx.x;
+  const unsigned long long n_far = *after_wait(d_nfar);
+  const unsigned long long det_base = after_wait(counters)[CNT_DET_BASE];
+  double* terms = terms_all + (size_t)blockIdx.x * (size_t)a.terms_cap;
+  const Geom& g = a.g;
+  for (unsigned long long c = blockIdx.x; c < n_far; c += gridDim.x)
+  {
+    if (infos[c].cclass != VOFOD_CLASS_MAV)
+      continue;  // uniform
+    __syncthreads();
+    if (tid == 0)
+      s_rank = 0;
+    __syncthreads();
+    int mine = 0;
+    for (unsigned long long j = tid; j < c; j += blockDim.x)
+      mine += infos[j].cclass == VOFOD_CLASS_MAV ? 1 : 0;
+    if (mine)
+      atomicAdd(&s_rank, mine);
+    __syncthreads();
+    const int rank = s_rank;
+    const vofod_cluster_info ci = infos[c];
+    const uint32_t* idcs = sidx + seg_start[ci.label];
+    // getSubmapCopy(aabb, inflate 2) (voxel_map.cpp:547-584)
+    int lo[3], ssz[3];
+    float sub_off[3];
+#pragma unroll
+    for (int q2 = 0; q2 < 3; q2++)
+    {
+      int mn = coord_to_idx1(ci.aabb_min[q2], g.off[q2], g.inv) - 2, mx = coord_to_idx1(ci.aabb_max[q2], g.off[q2], g.inv) + 2;
+      mn = mn < 0 ? 0 : (mn > g.size[q2] - 1 ? g.size[q2] - 1 : mn);
+      mx = mx < 0 ? 0 : (mx > g.size[q2] - 1 ? g.size[q2] - 1 : mx);
+      lo[q2] = mn;
+      ssz[q2] = mx - mn + 1;
+      sub_off[q2] = idx_to_coord1(mn, g.off[q2], g.vs) - g.vs / 2.0f;
+    }
+    const long long ncell = (long long)ssz[0] * ssz[1] * ssz[2];
+    const bool fits = ncell <= (long long)a.terms_cap;
+    if (fits)
+    {
+      for (int t = tid; t < (int)ncell; t += blockDim.x)
+      {
+        const int x = t % ssz[0], y = (t / ssz[0]) % ssz[1], z = t / (ssz[0] * ssz[1]);
+        const float val = cls_load<false>(score, g, nullptr, nullptr, x + lo[0], y + lo[1], z + lo[2]);
+        terms[t] = 1.0 - (double)val / a.score_ray;  // :862
+      }
+      __syncthreads();
+      const float ray_f = (float)a.score_ray;
+      const double self_term = 1.0 - (double)ray_f / a.score_ray;
+      for (int k = tid; k < ci.n_points; k += blockDim.x)  // :855-859 cluster voxels count as certain
+      {
+        const vofod_vox v = vox[idcs[k]];
+        const int x = coord_to_idx1(v.x, sub_off[0], g.inv), y = coord_to_idx1(v.y, sub_off[1], g.inv), z = coord_to_idx1(v.z, sub_off[2], g.inv);
+        if (x >= 0 && y >= 0 && z >= 0 && x < ssz[0] && y < ssz[1] && z < ssz[2])
+          terms[x + y * ssz[0] + z * ssz[0] * ssz[1]] = self_term;
+      }
+      __syncthreads();
+    }
+    if (tid == 0)
+    {
+      const float ddx = dyn->tf.t[0] - ci.obb_center[0], ddy = dyn->tf.t[1] - ci.obb_center[1], ddz = dyn->tf.t[2] - ci.obb_center[2];
+      const double det_dist = (double)sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+      vofod_detection d;
+      memset(&d, 0, sizeof(d));
+      d.id = (int32_t)(uint32_t)(det_base + (unsigned long long)rank);
+      d.label = ci.label;
+      d.n_points = (uint64_t)ci.n_points;
+      for (int q2 = 0; q2 < 3; q2++)
+      {
+        d.aabb_min[q2] = ci.aabb_min[q2];
+        d.aabb_max[q2] = ci.aabb_max[q2];
+        d.obb_min[q2] = ci.obb_min[q2];
+        d.obb_max[q2] = ci.obb_max[q2];
+        d.position[q2] = ci.obb_center[q2];
+      }
+      for (int q2 = 0; q2 < 9; q2++)
+        d.obb_rot[q2] = ci.obb_rot[q2];
+      const float cv = (float)(sqrt(det_dist) * a.position_sigma);
+      d.covariance[0] = d.covariance[4] = d.covariance[8] = cv;
+      double u = 0.0;
+      if (fits)
+        for (long long t = 0; t < ncell; t++)
+          u += terms[t];  // the reference's order (one running double sum)
+      else
+        u = __longlong_as_double(0x7ff8000000000000ll);
+      u /= (double)ci.n_points;
+      d.confidence = (double)(float)(1.0 / exp(u));
+      const double vray_res = a.vfov / (double)a.H;
+      const double hray_res = 2 * 3.14159265358979323846 / (double)a.W;
+      const double pv = fmin(atan(1.0 / det_dist) / (vray_res * a.min_points), 1.0);
+      const double ph = fmin(atan(1.0 / det_dist) / hray_res, 1.0);
+      d.detection_probability = pv * ph;
+      if (rank < MAX_DETS)
+        dets[rank] = d;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- slab mode: lay out and pack the candidates' boxes --------------------------------------------------------------------------
 // one thread: boxes in classification order (few candidates: clusters that passed the size / distance / point-count gates)
 __global__ void k_patch_layout(const ClsArgs a, const vofod_cluster_info* __restrict__ infos, const unsigned long long* __restrict__ d_nfar, const PatchSet ps)
@@ -976,6 +1256,28 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
   w.explored = qbase + 2 * cube;
   w.side = side;
   w.rm = rmax;
+  if (phase != 4 && !ctx->cls_force_seq)
+  {
+    // parallel over the far clusters (see k_classify_par); the sequential kernel stays for slab mode (the map is read through exchanged
+    // boxes there) and as VOFOD_OPT_CLASSIFY_SEQ
+    const int NB = CLS_PAR_BLOCKS;
+    ENSURE(ctx->cls_par_stamps, (size_t)NB * cube * 4);   // zero-filled when (re)allocated, like the epochs: generation 0 is never used
+    ENSURE(ctx->cls_par_queues, (size_t)NB * cube * 4 * 3);
+    ENSURE(ctx->cls_par_epochs, (size_t)NB * 4);
+    ENSURE(ctx->cls_par_done, m_cap * 4);
+    ENSURE(ctx->cls_par_terms, (size_t)NB * terms_cap * 8);
+    ZERO_CNT(CNT_CLS_TICKET, 2);  // + CNT_CLS_FINISHED
+    ClsParWs pw;
+    pw.stamps = ctx->cls_par_stamps.as<unsigned>();
+    pw.queues = ctx->cls_par_queues.as<int>();
+    pw.epochs = ctx->cls_par_epochs.as<unsigned>();
+    pw.done = ctx->cls_par_done.as<unsigned>();
+    pw.cube = cube;
+    LAUNCH(k_classify_par, NB, 256, 0, a, ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), pw, cnt, cnt + CNT_NFARPTS);
+    LAUNCH(k_extract_detections, NB, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(),
+           ctx->cls_par_terms.as<double>(), ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS);
+    return 0;
+  }
   if (phase == 4)
     LAUNCH(k_classify_seq<true>, 1, 256, 0, a, ctx->dyn.as<ScanDyn>(), ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), w,
            ctx->cls_terms.as<double>(), ctx->dets.as<vofod_detection>(), cnt, cnt + CNT_NFARPTS, ps);

@@ -329,6 +329,8 @@ struct vofod_ctx
   cudaEvent_t ev_prefetch[2] = {nullptr, nullptr};
   const void* prefetched_host[2] = {nullptr, nullptr};
   size_t prefetched_n[2] = {0, 0};
+  uint64_t prefetched_call[2] = {0, 0};  // scan_calls when the record was made: a record is good for the next two scan calls only
+  uint64_t scan_calls = 0;
   int prefetch_next = 0;
   uint64_t stat_prefetch_hits = 0;
   DevBuf scan_slot[VOFOD_SCAN_SLOTS];
@@ -432,6 +434,8 @@ struct vofod_ctx
   DevBuf cl_info;     // vofod_cluster_info per far cluster
   DevBuf dets;        // vofod_detection
   DevBuf explore_ws;
+  DevBuf cls_par_stamps, cls_par_queues, cls_par_epochs, cls_par_done, cls_par_terms;  // k_classify_par / k_extract_detections
+  bool cls_force_seq = false;  // VOFOD_OPT_CLASSIFY_SEQ
   DevBuf cls_sizes, cls_maxidx, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
   DevBuf scratch_a, scratch_b, scratch_d;
   size_t last_m = 0, last_far = 0;
@@ -499,6 +503,9 @@ enum
   CNT_VGH_LIST,       // non-empty occupancy words listed by the scan
   CNT_SEP_NUNSURE,    // voxels of unsure clusters listed for the decay
   CNT_VGH_WORDS,      // occupancy words of the scan-path voxel grid (depends on the cloud's bounding box)
+  CNT_CLS_TICKET,     // k_classify_par: next far cluster to take / clusters finished (adjacent: zeroed together)
+  CNT_CLS_FINISHED,
+  CNT_DET_BASE,       // id of the scan's first detection (k_classify_par -> k_extract_detections)
   // ---- persistent slots (never zeroed by a map resize) ----
   CNT_EXPLORE_EPOCH,  // stamp generation of the exploreToGround visited cube
   CNT_EPOCH_BASE,     // generation base of the decoupled look-back states, advanced on the DEVICE once per API call (graph replay safe)

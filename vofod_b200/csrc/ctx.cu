@@ -308,6 +308,12 @@ int vofod_set_option(vofod_ctx* ctx, int option, int value)
     ctx->slab_patch_words = 0;
     return VOFOD_OK;
   }
+  if (option == VOFOD_OPT_CLASSIFY_SEQ)
+  {
+    ctx->cls_force_seq = value != 0;
+    ctx->alloc_gen++;
+    return VOFOD_OK;
+  }
   if (option == VOFOD_OPT_RAYCAST_SPREAD)
   {
     if (value < 0)
@@ -417,7 +423,8 @@ __global__ void k_begin_call(unsigned long long* __restrict__ counters, const in
   {
     // every counter a scan accumulates into, in one place instead of ~15 eight-byte memset nodes
     const int slots[] = {CNT_TRAVERSALS, CNT_OOB, CNT_APPLY_ANY, CNT_MAXVAL, CNT_NBG, CNT_NCLOSE, CNT_NFAR, CNT_NDET, CNT_NFARPTS, CNT_CLS_CURSOR,
-                         CNT_CL_CURSOR, CNT_SEP_K, CNT_SEP_NUNIQ, CNT_SEP_ANY_SURE, CNT_NCLUSTERS, CNT_SEP_NCL, CNT_SEP_LIVE, CNT_VGH_LIST, CNT_SEP_NUNSURE};
+                         CNT_CL_CURSOR, CNT_SEP_K, CNT_SEP_NUNIQ, CNT_SEP_ANY_SURE, CNT_NCLUSTERS, CNT_SEP_NCL, CNT_SEP_LIVE, CNT_VGH_LIST, CNT_SEP_NUNSURE,
+                         CNT_VG_OVERFLOW, CNT_CLS_TICKET, CNT_CLS_FINISHED};
     if (threadIdx.x < (int)(sizeof(slots) / sizeof(int)))
       counters[slots[threadIdx.x]] = 0ull;
   }

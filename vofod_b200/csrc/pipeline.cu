@@ -26,6 +26,9 @@ int vf_range_update_dev(vofod_ctx* ctx, const vofod_params& p)
 // score_unknown / flag 3) and updates the voxel of each point in turn.  Inside a scan the points are the centroids of a
 // voxel grid that is aligned with the map (:664-665), one per cell; for any other cloud (the staged entry point, a
 // differently aligned filter) two points can share a cell, and then the reference applies both updates, in cloud order.
+// (Cloud order is exact for the whole-cloud overload, :811, which is what the staged entry point mirrors.  The per-cluster overload of
+// the scan path, :946-948, walks PCL's size-sorted clusters: for a filter that is NOT aligned with the map two points of one cell would
+// be applied in cluster order there, and the last bit of w*m + (1-w)*s could differ.  Unreachable with the reference's aligned filter.)
 // To get exactly that from a parallel kernel every active point first CLAIMS its cell with
 // atomicMin(owner[cell], key), key = (pass << 30) | index = its place in the reference's order.  The update kernel lets
 // only the claim holder apply its update (and release the claim); every other point of an already claimed cell goes to a
@@ -1219,6 +1222,12 @@ int vofod_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, const vof
     return vf_fail(ctx, VOFOD_E_INVALID, "NULL argument");
   if (!ctx->W || n != (size_t)ctx->W * ctx->H)
     return vf_fail(ctx, VOFOD_E_DIMS, "cloud has %zu points, sensor LUT has %zu", n, (size_t)ctx->W * ctx->H);
+  // an announcement that was not consumed by the two scan calls after it is void: the caller has moved on, and the host buffer may since
+  // have been refilled with another scan
+  ctx->scan_calls++;
+  for (int i = 0; i < 2; i++)
+    if (ctx->prefetched_host[i] && ctx->scan_calls - ctx->prefetched_call[i] > 2)
+      ctx->prefetched_host[i] = nullptr;
   for (int i = 0; i < 2; i++)
     if (ctx->prefetched_host[i] == (const void*)scan && ctx->prefetched_n[i] == n && ctx->prefetch_buf[i].p)
     {
@@ -1256,6 +1265,7 @@ int vofod_prefetch_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n)
   CK(cudaEventRecord(ctx->ev_prefetch[i], ctx->stream_copy));
   ctx->prefetched_host[i] = scan;
   ctx->prefetched_n[i] = n;
+  ctx->prefetched_call[i] = ctx->scan_calls;
   return VOFOD_OK;
 }
 

@@ -587,6 +587,10 @@ int vofod_slab_process_scan(vofod_ctx* ctx, const vofod_pt* scan, size_t n, cons
   {
     // a scan announced with vofod_prefetch_scan has been copied next to the previous scan's kernels
     int hit = -1;
+    ctx->scan_calls++;
+    for (int i = 0; i < 2; i++)
+      if (ctx->prefetched_host[i] && ctx->scan_calls - ctx->prefetched_call[i] > 2)
+        ctx->prefetched_host[i] = nullptr;  // (see vofod_process_scan)
     for (int i = 0; i < 2; i++)
       if (ctx->prefetched_host[i] == (const void*)scan && ctx->prefetched_n[i] == n && ctx->prefetch_buf[i].p)
         hit = i;

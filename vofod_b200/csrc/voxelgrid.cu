@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
     {
       *Lout = l;
       counters[slot_nvalid] = l.n_valid;
-      counters[slot_overflow] = (unsigned long long)l.overflow;
+      if (l.overflow)
+        counters[slot_overflow] = 1ull;  // (zeroed by k_begin_call: every writer only ever raises it, in whatever order the blocks run)
       counters[CNT_VGH_WORDS] = l.overflow ? 0ull : (unsigned long long)((l.div[0] + 31) / 32) * (unsigned long long)l.div[1] * (unsigned long long)l.div[2];
     }
   }
@@ -279,7 +280,8 @@ __global__ void __launch_bounds__(256) k_vgh_count(const float4* __restrict__ pt
       const int ijk1 = (int)floorf((p.y - L.offset[1]) * L.inv);
       const int ijk2 = (int)floorf((p.z - L.offset[2]) * L.inv);
       key = (uint32_t)(ijk0 + ijk1 * L.div[0] + ijk2 * L.div[0] * L.div[1]);
-      if (key >= total)
+      // per axis, not just key < total: an index that leaves its axis aliases another leaf's key, and the emit kernel rebuilds ijk from the key
+      if ((unsigned)ijk0 >= (unsigned)L.div[0] || (unsigned)ijk1 >= (unsigned)L.div[1] || (unsigned)ijk2 >= (unsigned)L.div[2] || key >= total)
       {
         // a point outside its own bounding box (not reachable with finite inputs): the sort path would emit it with a wrapped
         // key; here it is reported instead of written out of bounds
@@ -570,6 +572,7 @@ int vf_filter_voxelize_dev(vofod_ctx* ctx, size_t n, const vofod_params& p, bool
     ENSURE(ctx->vox, np * sizeof(vofod_vox));
     unsigned long long* cnt = ctx->d_counters.as<unsigned long long>();
     VgLayout* L = reinterpret_cast<VgLayout*>(ctx->scratch_d.as<char>() + 64);
+    ZERO_CNT(CNT_VG_OVERFLOW, 1);  // (inside a scan k_begin_call has done it: the kernel's blocks only ever raise the flag)
     LAUNCH(k_vgh_count, vf_blocks(ctx, n, 256, 8), 256, 0, ctx->vg_pts.as<float4>(), mm, g.vs, ac[0], ac[1], ac[2], L, cnt, (int)CNT_VG_NVALID, (int)CNT_VG_OVERFLOW,
            budget[0], budget[1], budget[2], ctx->vgh_cnt.as<uint32_t>(), ctx->vgh_bits.as<uint32_t>());
     // a word holds at least one of the n points

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvofod_synth.so")
 _lib = None
 
-SCENE_CITY, SCENE_GAZEBO = 0, 1
+SCENE_CITY, SCENE_GAZEBO, SCENE_SWARM = 0, 1, 2
 
 
 def _load():

@@ -122,16 +122,17 @@ void vsyn_sim_lut(int W, int H, double vfov_in, float* dirs3xN)
     }
 }
 
-// scene_id: 0 = city (24 boxes), 1 = gazebo-like (4 boxes + 3 spheres)
+// scene_id: 0 = city (24 boxes), 1 = gazebo-like (4 boxes + 3 spheres), 2 = swarm (the gazebo scene with 200 spheres on 10 rings around the
+// sensor, 2.4 m or more apart: 200 far clusters for the classification stage)
 // k: scan index.  dirs: 3xN LUT (column-major, ray id = row*W+col).  out: N points.
 // range_pt: ground point below the sensor for the rangefinder seeds of schedule S1.
 // map_scale: multiplies the trajectory amplitude and scene extent (1 for cfg2, 2.5 for the cfg5 large map).
 int vsyn_generate(int scene_id, int k, int W, int H, const float* dirs, float map_scale, vofod_pt* out, vofod_pose* pose, float range_pt[3],
                   float* sphere_centers /* 3x3 or NULL */)
 {
-  static scene_t scenes[2];
-  static float built_scale[2] = {0, 0};
-  if (scene_id < 0 || scene_id > 1)
+  static scene_t scenes[3];
+  static float built_scale[3] = {0, 0, 0};
+  if (scene_id < 0 || scene_id > 2)
     return -1;
   scene_t& sc = scenes[scene_id];
   if (built_scale[scene_id] != map_scale)
@@ -139,7 +140,7 @@ int vsyn_generate(int scene_id, int k, int W, int H, const float* dirs, float ma
     sc = scene_t();
     sc.extent = 90.0 * map_scale;
     make_boxes(sc, scene_id == 0 ? int(24 * map_scale * map_scale) : 4, 0xB2000001ULL, 34.0 * map_scale);
-    sc.n_spheres = scene_id == 1 ? 3 : 0;
+    sc.n_spheres = scene_id == 1 ? 3 : (scene_id == 2 ? 200 : 0);
     built_scale[scene_id] = map_scale;
   }
   // sensor pose
@@ -158,14 +159,22 @@ int vsyn_generate(int scene_id, int k, int W, int H, const float* dirs, float ma
   pose->t[0] = float(px); pose->t[1] = float(py); pose->t[2] = float(pz);
   range_pt[0] = pose->t[0]; range_pt[1] = pose->t[1]; range_pt[2] = 0.0f;
 
-  sphere_t spheres[3];
+  std::vector<sphere_t> spheres(size_t(sc.n_spheres));
   for (int s = 0; s < sc.n_spheres; s++)
   {
-    const double rad = 8.0 + 4.0 * s, h = 5.0 + 2.0 * s, ang = 0.05 * k + 2.0943951023931953 * s;
-    spheres[s] = {{px + rad * std::cos(ang), py + rad * std::sin(ang), h}, 0.35};
-    if (sphere_centers)
+    double rad = 8.0 + 4.0 * s, h = 5.0 + 2.0 * s, ang = 0.05 * k + 2.0943951023931953 * s;
+    if (scene_id == 2)
+    {
+      // ring r = s / 20 (radius 9 + 2 r m), 20 spheres per ring, neighbouring rings half a step apart in angle and 1.6 m in height
+      const int ring = s / 20, j = s % 20;
+      rad = 9.0 + 2.0 * ring;
+      ang = 0.01 * k + 0.3141592653589793 * (j + 0.5 * (ring & 1));
+      h = 4.0 + 1.6 * (ring & 1) + 0.8 * ((j % 3) - 1) * ((ring >> 1) & 1) + 0.15 * ring;
+    }
+    spheres[size_t(s)] = {{px + rad * std::cos(ang), py + rad * std::sin(ang), h}, 0.35};
+    if (sphere_centers && s < 3)
       for (int a = 0; a < 3; a++)
-        sphere_centers[3 * s + a] = float(spheres[s].c[a]);
+        sphere_centers[3 * s + a] = float(spheres[size_t(s)].c[a]);
   }
 
   // the simulated driver works from the float pose (what tf would deliver)
@@ -189,7 +198,7 @@ int vsyn_generate(int scene_id, int k, int W, int H, const float* dirs, float ma
       }
       for (int s = 0; s < sc.n_spheres; s++)
       {
-        const double ts = hit_sphere(spheres[s], o, d);
+        const double ts = hit_sphere(spheres[size_t(s)], o, d);
         if (ts > 0.0 && ts < t)
           t = ts;
       }

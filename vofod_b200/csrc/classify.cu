@@ -789,7 +789,6 @@ struct ClsParWs
 {
   unsigned* stamps;   // [NB][cube]
   int* queues;        // [NB][3][cube]
-  unsigned* epochs;   // [NB] stamp generation of each block's cube (persistent)
   unsigned* done;     // [far cluster] == tag: finished in this call
   size_t cube;
 };
@@ -823,8 +822,6 @@ __global__ void __launch_bounds__(256) k_classify_par(const ClsArgs a, float* sc
   w.explored = w.q1 + ws.cube;
   w.side = a.side;
   w.rm = a.rmax;
-  if (tid == 0)
-    s_epoch = ws.epochs[blockIdx.x];
   const Geom& g = a.g;
   while (true)
   {
@@ -878,9 +875,12 @@ __global__ void __launch_bounds__(256) k_classify_par(const ClsArgs a, float* sc
           __syncthreads();
           if (tid == 0)
           {
-            s_epoch++;
-            if (s_epoch == 0u)
-              s_epoch = 1u;
+            // stamp generations come from ONE counter shared by all blocks (and by the sequential kernels): a cube's layout follows the
+            // parameters, so after a change a block can find another block's old stamps in its cube — they must never equal its own
+            unsigned e = (unsigned)atomicAdd(counters + CNT_EXPLORE_EPOCH, 1ull) + 1u;
+            if (e == 0u)
+              e = (unsigned)atomicAdd(counters + CNT_EXPLORE_EPOCH, 1ull) + 1u;
+            s_epoch = e;
           }
           __syncthreads();
           const bool connected = explore_to_ground_block<false, true>(score, g, ox, oy, oz, a.thr_frontiers, a.thr_new, (float)R, s_epoch, w, sh);
@@ -939,8 +939,6 @@ __global__ void __launch_bounds__(256) k_classify_par(const ClsArgs a, float* sc
       }
     }
   }
-  if (tid == 0)
-    ws.epochs[blockIdx.x] = s_epoch;
 }
 
 // K15 in parallel — extractDetections (:834-879): one block per MAV, detection number = its rank among the MAVs in cluster order
@@ -1261,16 +1259,14 @@ int vf_classify_detect_dev(vofod_ctx* ctx, const vofod_vox* d_vox, const int* d_
     // parallel over the far clusters (see k_classify_par); the sequential kernel stays for slab mode (the map is read through exchanged
     // boxes there) and as VOFOD_OPT_CLASSIFY_SEQ
     const int NB = CLS_PAR_BLOCKS;
-    ENSURE(ctx->cls_par_stamps, (size_t)NB * cube * 4);   // zero-filled when (re)allocated, like the epochs: generation 0 is never used
+    ENSURE(ctx->cls_par_stamps, (size_t)NB * cube * 4);   // zero-filled when (re)allocated: generation 0 is never used
     ENSURE(ctx->cls_par_queues, (size_t)NB * cube * 4 * 3);
-    ENSURE(ctx->cls_par_epochs, (size_t)NB * 4);
     ENSURE(ctx->cls_par_done, m_cap * 4);
     ENSURE(ctx->cls_par_terms, (size_t)NB * terms_cap * 8);
     ZERO_CNT(CNT_CLS_TICKET, 2);  // + CNT_CLS_FINISHED
     ClsParWs pw;
     pw.stamps = ctx->cls_par_stamps.as<unsigned>();
     pw.queues = ctx->cls_par_queues.as<int>();
-    pw.epochs = ctx->cls_par_epochs.as<unsigned>();
     pw.done = ctx->cls_par_done.as<unsigned>();
     pw.cube = cube;
     LAUNCH(k_classify_par, NB, 256, 0, a, ctx->score.as<float>(), d_vox, sidx, ctx->cls_seg.as<int>(), ctx->cl_info.as<vofod_cluster_info>(), pw, cnt, cnt + CNT_NFARPTS);

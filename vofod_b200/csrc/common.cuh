@@ -412,7 +412,7 @@ struct vofod_ctx
   vofod_params sep_pending_p;
   DevBuf tile_state_b, tile_state2_b;  // look-back states of the deferred pass, which runs next to the front end's own scans
   cudaStream_t stream4 = nullptr;      // the next scan's front end beside the deferred pass
-  cudaEvent_t ev_fork4 = nullptr, ev_front = nullptr;
+  cudaEvent_t ev_fork4 = nullptr, ev_front = nullptr, ev_sepfill = nullptr;
   ScanInFlight fl[2];           // vofod_process_scan_batch keeps two scans in flight; a single call uses slot 0
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_slab[9] = {};  // vofod_slab_process_scan: start, broadcast, (phase, exchange) x 3, phase 3
@@ -434,7 +434,7 @@ struct vofod_ctx
   DevBuf cl_info;     // vofod_cluster_info per far cluster
   DevBuf dets;        // vofod_detection
   DevBuf explore_ws;
-  DevBuf cls_par_stamps, cls_par_queues, cls_par_epochs, cls_par_done, cls_par_terms;  // k_classify_par / k_extract_detections
+  DevBuf cls_par_stamps, cls_par_queues, cls_par_done, cls_par_terms;  // k_classify_par / k_extract_detections
   bool cls_force_seq = false;  // VOFOD_OPT_CLASSIFY_SEQ
   DevBuf cls_sizes, cls_maxidx, cls_seg, cls_okeys_a, cls_okeys_b, cls_queues, cls_terms;
   DevBuf scratch_a, scratch_b, scratch_d;

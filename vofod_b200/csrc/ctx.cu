@@ -96,6 +96,7 @@ int vofod_create(int device, vofod_ctx** out)
   cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_fork4, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_sepfill, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming);
@@ -127,6 +128,8 @@ int vofod_create(int device, vofod_ctx** out)
     ctx->overlap_enabled = false;
   if (const char* e = getenv("VOFOD_RAYCAST_EXP"))  // A/B runs of the accumulate kernel's variants under the whole test suite (values >= 3 give correct results)
     ctx->raycast_exp = atoi(e);
+  if (const char* e = getenv("VOFOD_CLASSIFY_SEQ"))
+    ctx->cls_force_seq = atoi(e) != 0;
   if (const char* e = getenv("VOFOD_RAYCAST_SPREAD"))
     ctx->raycast_spread_voxels = atoi(e);
   ctx->pinned_bytes = 1 << 20;
@@ -204,6 +207,8 @@ int vofod_destroy(vofod_ctx* ctx)
     cudaStreamDestroy(ctx->stream4);
   if (ctx->ev_fork4)
     cudaEventDestroy(ctx->ev_fork4);
+  if (ctx->ev_sepfill)
+    cudaEventDestroy(ctx->ev_sepfill);
   if (ctx->ev_front)
     cudaEventDestroy(ctx->ev_front);
   for (int i = 0; i < 2; i++)

@@ -649,10 +649,20 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
     ctx->stream = ctx->stream2;
     RunRows rows_probe;
     const bool hash_cluster = ctx->cl_force_hash || ctx->vg_force_sort || !vf_run_rows((float)p.ground_points_max_distance, ctx->g.vs, rows_probe);
-    int rrc = hash_cluster ? vf_cluster_prefill(ctx, ctx->cl, n, 0) : 0;
+    // a deferred pass is the first thing on the main chain: its clears come first here, with an event of their own for it to wait on
+    // (without the wait the pass raced these fills — its counts could be wiped under it, and it then found an empty background cloud)
+    int rrc = 0;
+    if (plan.sep_first)
+    {
+      rrc = vf_sepclusters_prefill(ctx, plan.sep_first_p);
+      if (rrc >= 0)
+        CK(cudaEventRecord(ctx->ev_sepfill, ctx->stream2));
+    }
+    if (rrc >= 0 && hash_cluster)
+      rrc = vf_cluster_prefill(ctx, ctx->cl, n, 0);
     if (rrc >= 0 && s.do_classify)
       rrc = vf_classify_prefill(ctx, n);
-    if (rrc >= 0 && s.do_sepclusters)
+    if (rrc >= 0 && s.do_sepclusters && !plan.sep_first)
       rrc = vf_sepclusters_prefill(ctx, p);
     // nVoxelsOver of :712 only needs the map as the previous scan (and this scan's rangefinder seed) left it — with a deferred
     // separated-background pass still to come it has to wait for that (it then rides in the hasCloseTo kernel)
@@ -687,6 +697,8 @@ static int enqueue_scan(vofod_ctx* ctx, const ScanPlan& plan, int* sep_status_ou
   }
   if (plan.sep_first)
   {
+    if (side)
+      CK(cudaStreamWaitEvent(st, ctx->ev_sepfill, 0));
     std::swap(ctx->tile_state, ctx->tile_state_b);
     std::swap(ctx->tile_state2, ctx->tile_state2_b);
     const int src = vf_sepclusters_dev(ctx, plan.sep_first_its, plan.sep_first_p, plan.sep_cap);
@@ -1146,6 +1158,10 @@ static int scan_finish(vofod_ctx* ctx, const int slot, vofod_scan_result* res, v
     if (K * 3 / 2 > ctx->sep_table_hint)
       ctx->sep_table_hint = K * 4 + (size_t(1) << 18);
   }
+  // an empty background cloud (:1155) is reported the same way whichever list the pass ran with (a pipelined scan launched before the
+  // previous one's counts were read may still use the exact list while a scan-by-scan caller has moved on to the capped one)
+  if (sep_ran && sep_status == VOFOD_OK && hp[CNT_SEP_K] == 0ull)
+    sep_status = VOFOD_W_EMPTY;
   ctx->background_pts_sufficient = hp[CNT_STATE_BG] != 0;
   ctx->sure_background_sufficient = sure_flag;
   ctx->last_detection_id = (uint32_t)hp[CNT_DET_ID];

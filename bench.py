@@ -335,7 +335,7 @@ def run_ours(args):
             v.upload_scan(k, buf[k])
         ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n3)]
         nd = nfar = 0
-        barrier()
+        torch.cuda.synchronize()  # (rank 0 runs this leg alone: no collective in here — a dist.barrier would pair up with the other ranks' NEXT one)
         for k in range(n3):
             with torch.cuda.stream(stream):
                 flush.fill_(k & 0xFF)
@@ -345,7 +345,7 @@ def run_ours(args):
             if k >= W3:
                 nd += res.n_detections
                 nfar += res.n_far_clusters
-        barrier()
+        torch.cuda.synchronize()
         ms3 = sum(ev3[k][0].elapsed_time(ev3[k][1]) for k in range(W3, n3))
         return {"workload": what or "cfg3: Gazebo-like scene (ground + 4 buildings + 3 sphere UAVs), 128x2048 rays, cfg2 map, schedule S1, scans resident in HBM",
                 "value": K3 / (ms3 * 1e-3), "unit": "scans/s", "ms_per_step": ms3 / K3, "steps": K3, "warmup": W3, "detections_in_timed_steps": int(nd),

@@ -69,3 +69,35 @@ def test_default_geometry_table():
             border.add((0, abs(dy), dz))
     assert all(dx * dx + dy * dy + dz * dz == 9 for dx, dy, dz in border)
     assert border == {(3, 0, 0), (0, 3, 0), (0, 0, 3), (2, 2, 1), (2, 1, 2), (1, 2, 2)}
+
+
+def test_bench_legs_that_run_on_one_rank_hold_no_collective():
+    """bench.py --gpus N: the cfg3 / swarm / streams-on-one-GPU legs run on rank 0 (or at N = 1) only.  A dist.barrier inside them pairs up with the
+    OTHER ranks' next collective — an all-reduce of another size — and the run hangs (it did, for every N > 1, until this was found in round 2).
+    Static guard: those functions contain no collective, and every `if rank == 0` block of run_ours is free of them too."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+
+    def calls(node):
+        out = []
+        for n in ast.walk(node):
+            if isinstance(n, ast.Call):
+                f = n.func
+                if isinstance(f, ast.Name):
+                    out.append(f.id)
+                elif isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name):
+                    out.append(f.value.id + "." + f.attr)
+        return out
+
+    run_ours = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_ours")
+    single_rank = [n for n in ast.walk(run_ours) if isinstance(n, ast.FunctionDef) and n.name in ("run_cfg3", "run_streams_on_this_gpu")]
+    assert len(single_rank) == 2
+    for fn in single_rank:
+        bad = [c for c in calls(fn) if c == "barrier" or c.startswith("dist.")]
+        assert not bad, (fn.name, bad)
+    for n in ast.walk(run_ours):
+        if isinstance(n, ast.If) and "rank == 0" in ast.unparse(n.test) and "world" not in ast.unparse(n.test):
+            bad = [c for c in calls(ast.Module(body=n.body, type_ignores=[])) if c == "barrier" or c.startswith("dist.")]
+            assert not bad, (ast.unparse(n.test), bad)

@@ -69,3 +69,42 @@ def test_partition_by_ray_load():
     uniform = [multi.partition(n, r, world) for r in range(world)]
     assert share(cuts).max() < 0.2 < 0.3 < share(uniform).max()
     assert multi.partition_by_ray_load(401, 1, 200.0, 80.0) == [(0, 401)]
+
+
+def _dry_run(world, extra, timeout=240):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(root, "tests", "dry", "bench_dry_run.py"), "--gpus", str(world)] + extra
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        pytest.fail(f"bench.py --gpus {world} {' '.join(extra)} did not finish: the ranks' collective sequences do not pair up (dry run, gloo)")
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, (r.returncode, r.stdout[-1000:], r.stderr[-2000:])
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bench_control_flow_under_torchrun(world):
+    """`python -m torch.distributed.run --nproc-per-node N bench.py --gpus N` as the driver launches it, with the CUDA library / runtime and
+    the scan generator replaced by stand-ins (tests/dry/bench_dry_run.py) and gloo for NCCL: every rank issues the same collectives in the
+    same order (the run ends instead of hanging), rank 0 prints exactly one JSON line with the contract's keys and the sub-records, all
+    ranks exit 0.  Round 2's first 8-GPU run of the final bench hung on a rank-0-only dist.barrier; this is the guard."""
+    d = _dry_run(world, ["--steps", "3", "--warmup", "3", "--slab-steps", "2", "--slab-warmup", "2"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
+                "gpu_launches", "roofline", "clocks", "slab_cfg5", "cfg3"):
+        assert key in d, key
+    assert d["n_gpus"] == world and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    slab = d["slab_cfg5"]
+    assert "error" not in slab and slab["20m"]["n_slabs"] == world and slab["200m"]["n_slabs"] == world
+    assert "one_gpu_same_run" in slab["200m"] and "cut_by_ray_load" in slab["200m"]
+    assert len(slab["20m"]["ms_by_rank_bcast_p0_x0_p1_x1_p2_x2_p3"]) == world
+
+
+def test_bench_slab_mode_control_flow_under_torchrun():
+    d = _dry_run(2, ["--mode", "slab", "--raycast-max", "200", "--steps", "2", "--warmup", "2"])
+    assert d["mode"] == "slab" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["slab"]["n_slabs"] == 2

@@ -106,6 +106,9 @@ class FakeVofod:
         return self._res(), np.zeros(0, dtype=abi.DETECTION_DTYPE)
 
     def slab_process_scan(self, scan, pose, p, s, **k):
+        if os.environ.get("DRY_RUN_HANG_IN_SLAB") and int(os.environ.get("RANK", "0")) == 1:
+            import time
+            time.sleep(3600)  # a stuck rank: the bench's deadline guard must still get the headline line out
         return self._res(), np.zeros(0, dtype=abi.DETECTION_DTYPE)
 
     def process_scan_batch(self, scans, poses, p, scheds, **k):

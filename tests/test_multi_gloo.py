@@ -108,3 +108,12 @@ def test_bench_control_flow_under_torchrun(world):
 def test_bench_slab_mode_control_flow_under_torchrun():
     d = _dry_run(2, ["--mode", "slab", "--raycast-max", "200", "--steps", "2", "--warmup", "2"])
     assert d["mode"] == "slab" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["slab"]["n_slabs"] == 2
+
+
+def test_bench_headline_survives_a_stuck_slab_sub_record(monkeypatch):
+    """one rank never returns from the cfg5 slab sub-record: after VOFOD_BENCH_SLAB_LIMIT_S every rank abandons it, rank 0 still prints the
+    headline line (with the reason in place of the sub-record) and all ranks exit 0"""
+    monkeypatch.setenv("DRY_RUN_HANG_IN_SLAB", "1")
+    monkeypatch.setenv("VOFOD_BENCH_SLAB_LIMIT_S", "12")
+    d = _dry_run(2, ["--steps", "3", "--warmup", "3", "--slab-steps", "2", "--slab-warmup", "2"], timeout=120)
+    assert d["n_gpus"] == 2 and d["value"] > 0 and "error" in d["slab_cfg5"]

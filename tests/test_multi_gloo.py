@@ -117,3 +117,21 @@ def test_bench_headline_survives_a_stuck_slab_sub_record(monkeypatch):
     monkeypatch.setenv("VOFOD_BENCH_SLAB_LIMIT_S", "12")
     d = _dry_run(2, ["--steps", "3", "--warmup", "3", "--slab-steps", "2", "--slab-warmup", "2"], timeout=120)
     assert d["n_gpus"] == 2 and d["value"] > 0 and "error" in d["slab_cfg5"]
+
+
+def test_reference_arm_under_torchrun():
+    """`bench.py --impl reference --gpus N` launched like the GPU arm: rank 0 alone runs the reference's CPU path and prints the line, the
+    other ranks leave at once with status 0 (the real thing, no stand-ins: the arm needs no GPU)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "scans/s" and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

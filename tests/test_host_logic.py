@@ -101,3 +101,31 @@ def test_bench_legs_that_run_on_one_rank_hold_no_collective():
         if isinstance(n, ast.If) and "rank == 0" in ast.unparse(n.test) and "world" not in ast.unparse(n.test):
             bad = [c for c in calls(ast.Module(body=n.body, type_ignores=[])) if c == "barrier" or c.startswith("dist.")]
             assert not bad, (ast.unparse(n.test), bad)
+
+
+def test_dda_axis_predicates_equal_first_minimum():
+    """the raycast loop picks the stepping axis with three predicates of `dist == tmax_i` (x if tmx == dist, else y if tmy == dist, else z)
+    instead of the reference's `tmax.minCoeff(&i)` (first minimum, strict '<' comparisons, voxel_map.cpp:250): the same axis for every input,
+    ties and infinities (a ray parallel to an axis has tmax = tdelta = +inf there) included"""
+    rng = np.random.default_rng(7)
+    vals = np.array([0.0, 0.25, 0.5, 1.0, 1.5, 3.0, np.inf, 1e-30, 7.5], dtype=np.float32)
+    grid = np.array(list(itertools.product(vals, repeat=3)), dtype=np.float32)
+    rand = rng.random((20000, 3), dtype=np.float32) * 4
+    ties = rand.copy()
+    ties[::3, 1] = ties[::3, 0]
+    ties[1::3, 2] = ties[1::3, 1]
+    ties[2::5, 2] = ties[2::5, 0]
+    for t in (grid, rand, ties):
+        tmx, tmy, tmz = t[:, 0], t[:, 1], t[:, 2]
+        # reference: first minimum
+        use_y = tmy < tmx
+        d01 = np.where(use_y, tmy, tmx)
+        use_z = tmz < d01
+        ref_axis = np.where(use_z, 2, np.where(use_y, 1, 0))
+        # kernel: predicates of dist == tmax_i
+        dist = np.minimum(np.minimum(tmx, tmy), tmz)
+        step_x = tmx == dist
+        step_y = ~step_x & (tmy == dist)
+        ker_axis = np.where(step_x, 0, np.where(step_y, 1, 2))
+        assert np.array_equal(ref_axis, ker_axis)
+        assert np.array_equal(dist, np.where(use_z, tmz, d01))

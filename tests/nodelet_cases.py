@@ -43,6 +43,12 @@ def case_list():
     p.background_sufficient_points_ratio = 0.02
     p.raycast_min_intensity = 50.0
     cases["mask_offsets_intensity"] = dict(W=512, H=32, p=p, vs=0.5, scene=1, scans=range(0, 8), sched={}, mask_offsets=7, dim_every=5)
+    # 200 sphere UAVs on rings around the sensor (synth scene 2): ~150 far clusters per scan whose explore boxes neighbour each other, so
+    # the ORDER in which classify_cluster explores them and writes frontiers back (:1699-1717) is what this case pins (CPU: oracle vs the
+    # reference's own code; the GPU runs the same scene against the oracle in test_swarm_two_hundred_far_clusters)
+    p = params_for((80.0, 80.0, 30.0))
+    p.background_sufficient_points_ratio = 0.02
+    cases["swarm_many_clusters"] = dict(W=1024, H=64, p=p, vs=0.5, scene=2, scans=range(0, 30), sched={})
     return cases
 
 
@@ -102,6 +108,30 @@ DET_FIELDS = ("id", "n_points", "aabb_min", "aabb_max", "position", "obb_min", "
 # detection fields that come out of the eigen-solve of pcl::MomentOfInertiaEstimation (Eigen::EigenSolver in the reference, source absent):
 # compared with a tolerance, everything else bit for bit
 EIGEN_FIELDS = ("position", "obb_min", "obb_max", "covariance", "confidence", "detection_probability")
+
+
+def canonical_detection_order(r):
+    """Detections come out in far-cluster order = PCL's cluster order: `std::sort(clusters.rbegin(), clusters.rend(), by size)` — NOT stable, so
+    the order of clusters of EQUAL size is whatever libstdc++'s introsort leaves (the reference build, through the shim's verbatim call); the
+    oracle and the GPU break such ties by the smallest point index.  The partition, the classes and the map do not depend on it; the order of the
+    detection records (and with it which record carries which of the scan's consecutive ids) does.  For sequences with many equal-size clusters
+    both sides' records are put into one canonical order per scan (by AABB) before they are compared, and the ids are compared as the scan's set."""
+    r = dict(r)
+    n_det = np.asarray(r["n_det"])
+    starts = np.concatenate([[0], np.cumsum(n_det)])
+    perm = np.arange(int(starts[-1]))
+    for a, b in zip(starts[:-1], starts[1:]):
+        if b > a:
+            key = np.concatenate([r["det_aabb_min"][a:b], r["det_aabb_max"][a:b]], axis=1)
+            perm[a:b] = a + np.lexsort(key.T[::-1])
+    for k in list(r):
+        if k.startswith("det_") and k != "det_id":
+            r[k] = r[k][perm]
+    ids = np.array(r["det_id"])
+    for a, b in zip(starts[:-1], starts[1:]):
+        ids[a:b] = np.sort(ids[a:b])
+    r["det_id"] = ids
+    return r
 
 
 def compare_exact(got, want, who, name):

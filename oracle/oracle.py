@@ -38,6 +38,7 @@ def load_library():
         "vo_create": (vp, []),
         "vo_destroy": (None, [vp]),
         "vo_set_modes": (None, [vp, i32, i32, i32]),
+        "vo_set_std_sort_ties": (None, [vp, i32]),
         "vo_reset": (None, [vp, P(Params), f32]),
         "vo_map_resize": (None, [vp, vp, vp, f32]),
         "vo_map_resize_idx": (None, [vp, vp, vp, f32]),
@@ -107,6 +108,10 @@ class Oracle:
         self.lib = load_library()
         self.h = C.c_void_p(self.lib.vo_create())
         self.lib.vo_set_modes(self.h, int(track_counts), int(apply_from_fixed), int(frac_bits))
+
+    def set_std_sort_ties(self, on=True):
+        """clusters of equal size in the order libstdc++'s (unstable) std::sort leaves them, as in the reference build, instead of by smallest index"""
+        self.lib.vo_set_std_sort_ties(self.h, int(on))
 
     def set_modes(self, track_counts=True, apply_from_fixed=False, frac_bits=24):
         self.lib.vo_set_modes(self.h, int(track_counts), int(apply_from_fixed), int(frac_bits))

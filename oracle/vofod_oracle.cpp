@@ -484,7 +484,10 @@ static inline uint64_t cell_key(int64_t cx, int64_t cy, int64_t cz)
   return (uint64_t(cx + (1 << 20)) & 0x1FFFFF) | ((uint64_t(cy + (1 << 20)) & 0x1FFFFF) << 21) | ((uint64_t(cz + (1 << 20)) & 0x1FFFFF) << 42);
 }
 
-static clusters_t euclidean_clusters(const float* xyz, const size_t stride, const size_t m, const float tol)
+// std_sort_ties: order the clusters with PCL's own call, std::sort through reverse iterators by size — not stable: clusters of equal size end up
+// in whatever order libstdc++'s introsort leaves (what the reference build produces).  Default: ties by the smallest point index, which is what
+// the GPU implements; the switch exists to show that the tie order is the ONLY thing that separates the two (tests/test_ref_nodelet.py).
+static clusters_t euclidean_clusters(const float* xyz, const size_t stride, const size_t m, const float tol, const bool std_sort_ties = false)
 {
   clusters_t ret;
   ret.labels.assign(m, -1);
@@ -542,11 +545,14 @@ static clusters_t euclidean_clusters(const float* xyz, const size_t stride, cons
       ret.labels[k] = idcs.front();
     ret.clusters.push_back(std::move(idcs));
   }
-  std::stable_sort(ret.clusters.begin(), ret.clusters.end(), [](const auto& a, const auto& b) {
-    if (a.size() != b.size())
-      return a.size() > b.size();
-    return a.front() < b.front();
-  });
+  if (std_sort_ties)
+    std::sort(ret.clusters.rbegin(), ret.clusters.rend(), [](const auto& a, const auto& b) { return a.size() < b.size(); });  // extract_clusters.hpp, 1.10
+  else
+    std::stable_sort(ret.clusters.begin(), ret.clusters.end(), [](const auto& a, const auto& b) {
+      if (a.size() != b.size())
+        return a.size() > b.size();
+      return a.front() < b.front();
+    });
   return ret;
 }
 
@@ -723,6 +729,7 @@ struct Oracle
   int frac_bits = 26;
   bool track_counts = true;       // maintain ray_count / ray_fixed (off for pure CPU-baseline timing)
   bool apply_from_fixed = false;  // apply uses float(fixed) instead of the sequential fp32 sum
+  bool std_sort_ties = false;     // cluster order among equal sizes as libstdc++'s std::sort leaves it (see euclidean_clusters)
 
   int W = 0, H = 0;
   std::vector<float> lut_dirs, lut_offs;  // 3 x N column-major
@@ -1099,7 +1106,7 @@ struct Oracle
     const float no_align[3] = {0, 0, 0};
     if (voxel_grid_counted(sep_raw, lsz, thr_sure, false, no_align, sep_ds) < 0)
       return VOFOD_E_OVERFLOW;
-    sep_clusters = euclidean_clusters(&sep_ds[0].x, 4, sep_ds.size(), float(max_voxel_dist));
+    sep_clusters = euclidean_clusters(&sep_ds[0].x, 4, sep_ds.size(), float(max_voxel_dist), std_sort_ties);
     std::vector<size_t> n_sure;
     n_sure.reserve(sep_clusters.clusters.size());
     for (const auto& cl : sep_clusters.clusters)
@@ -1167,7 +1174,7 @@ struct Oracle
     if (rc < 0)
       return VOFOD_E_OVERFLOW;
     stage_ms[1] = clk.lap();  // "filtering"
-    clusters = euclidean_clusters(cloud_weighted.empty() ? nullptr : &cloud_weighted[0].x, 4, cloud_weighted.size(), float(p.ground_points_max_distance));
+    clusters = euclidean_clusters(cloud_weighted.empty() ? nullptr : &cloud_weighted[0].x, 4, cloud_weighted.size(), float(p.ground_points_max_distance), std_sort_ties);
     stage_ms[2] = clk.lap();  // "clusterization"
     find_close_far(p);
     stage_ms[3] = clk.lap();  // "close X far"
@@ -1245,6 +1252,8 @@ void vo_set_modes(Oracle* o, int track_counts, int apply_from_fixed, int frac_bi
   o->apply_from_fixed = apply_from_fixed != 0;
   o->frac_bits = frac_bits;
 }
+
+void vo_set_std_sort_ties(Oracle* o, int on) { o->std_sort_ties = on != 0; }
 
 void vo_reset(Oracle* o, const vofod_params* p, float voxel_size) { o->reset(*p, voxel_size); }
 

@@ -37,6 +37,20 @@ def test_oracle_matches_reference_nodelet_sequences(oracle_mod, name):
     compare_exact(got, want, "oracle", name)
 
 
+def test_tie_order_is_the_only_difference_on_many_clusters(oracle_mod):
+    """the oracle with its clusters ordered by PCL's own (unstable) std::sort call instead of "equal sizes by smallest index": the 200-UAV
+    sequence then equals the reference build's output bit for bit INCLUDING the order of the detection records and their ids — the tie order
+    is the one thing that separates oracle / GPU from the reference there, nothing else hides behind the canonical re-ordering above"""
+    name = "swarm_many_clusters"
+    o = oracle_mod.Oracle(track_counts=False, apply_from_fixed=False)
+    o.set_std_sort_ties(True)
+    try:
+        got = run_case(o, case_list()[name])
+    finally:
+        o.close()
+    compare_exact(got, _want(name), "oracle(std::sort ties)", name)
+
+
 def test_fixture_is_what_the_reference_build_produces():
     from oracle import ref
     if not ref.available():

@@ -129,3 +129,16 @@ def test_dda_axis_predicates_equal_first_minimum():
         ker_axis = np.where(step_x, 0, np.where(step_y, 1, 2))
         assert np.array_equal(ref_axis, ker_axis)
         assert np.array_equal(dist, np.where(use_z, tmz, d01))
+
+
+def test_introsort_restatement_equals_std_sort():
+    """vofod_b200/csrc/introsort_ties.h — libstdc++'s std::sort restated so that one device thread can reproduce the order PCL's (unstable)
+    cluster sort leaves among clusters of equal size — against std::sort itself, called through reverse iterators as PCL calls it
+    (tests/cpp/introsort_vs_std_sort.cpp: 3 000 random arrays with many ties, structured inputs, median-of-three killers that reach the
+    heap-sort fallback).  The header is not wired into the GPU ranking yet."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp"), "_build/introsort_vs_std_sort"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(root, "tests", "cpp", "_build", "introsort_vs_std_sort")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "== std::sort" in r.stdout, r.stdout[-500:]

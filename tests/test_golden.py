@@ -28,3 +28,17 @@ def test_fixture_is_what_the_reference_build_produces(want):
         pytest.skip("oracle/_ref not built here (needs /root/reference); the committed fixture stands in")
     got = run_cases(RefSide())
     compare(got, want, "reference")
+
+
+def test_fuzz_classes_against_the_reference_build():
+    """a few rounds of tools/fuzz_classes_vs_reference.py: the reference's own VoxelMap / VoxelGridWeighted / VoxelGridCounted (oracle/_ref) against the
+    oracle on random inputs, bit for bit (skipped where oracle/_ref is not built: the committed golden vectors stand in)"""
+    import os
+    import subprocess
+    import sys
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_classes_vs_reference.py"), "11", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-1500:]
